@@ -1,0 +1,754 @@
+// HBM-bound kernels of the GPTDolomite training step: RMSNorm, RoPE, SwiGLU, embedding, cross-entropy,
+// bias-gradient column sums, residual adds and the flat-shard optimizer kernels.
+// All are coalesced 16-byte vector kernels with warp-shuffle reductions; fp32 math, bf16 storage.
+#include "common.cuh"
+#include "../../include/dolomite_b200.h"
+
+using namespace dolo;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    // red: >= 8 floats of shared memory.  Two barriers so `red` can be reused immediately.
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    float t = (lane < (blockDim.x >> 5)) ? red[lane] : 0.f;
+    t = warp_sum(t);
+    __syncthreads();
+    return t;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
+    f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z);
+    f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 v;
+    v.x = pack_bf16(f[0], f[1]);
+    v.y = pack_bf16(f[2], f[3]);
+    v.z = pack_bf16(f[4], f[5]);
+    v.w = pack_bf16(f[6], f[7]);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// RMSNorm forward: one block per row (grid-stride), NV 16-byte vectors per thread held in registers.
+// ------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kThreads) rmsnorm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w,
+                                                               uint4* __restrict__ y, float* __restrict__ rstd,
+                                                               int64_t T, int H8, float eps, float inv_h) {
+    __shared__ float red[8];
+    for (int64_t row = blockIdx.x; row < T; row += gridDim.x) {
+        const uint4* xr = x + row * H8;
+        uint4 xv[NV];
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int idx = threadIdx.x + i * kThreads;
+            if (idx < H8) {
+                xv[i] = __ldg(xr + idx);
+                float f[8];
+                unpack8(xv[i], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+            }
+        }
+        ss = block_sum(ss, red);
+        const float r = rsqrtf(ss * inv_h + eps);
+        if (threadIdx.x == 0) rstd[row] = r;
+        uint4* yr = y + row * H8;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int idx = threadIdx.x + i * kThreads;
+            if (idx < H8) {
+                float f[8], g[8];
+                unpack8(xv[i], f);
+                unpack8(__ldg(w + idx), g);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = g[j] * bf16_round(f[j] * r);  // weight * bf16(normalised)
+                yr[idx] = pack8(f);
+            }
+        }
+    }
+}
+
+// RMSNorm backward.  dx = r * (dy*w - xn * mean(dy*w*xn)),  dw += sum_rows dy * bf16(xn).
+// Persistent blocks; per-thread dw partials in registers, written to workspace [gridDim.x, H].
+template <int NV>
+__global__ void __launch_bounds__(kThreads)
+    rmsnorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ w,
+                       const float* __restrict__ rstd, const uint4* __restrict__ dx_add, uint4* __restrict__ dx,
+                       float* __restrict__ ws, int64_t T, int H8, float inv_h) {
+    __shared__ float red[8];
+    float dwacc[NV][8];
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dwacc[i][j] = 0.f;
+
+    for (int64_t row = blockIdx.x; row < T; row += gridDim.x) {
+        const float r = rstd[row];
+        uint4 xv[NV], gv[NV];
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int idx = threadIdx.x + i * kThreads;
+            if (idx < H8) {
+                xv[i] = __ldg(x + row * H8 + idx);
+                gv[i] = __ldg(dy + row * H8 + idx);
+                float xf[8], gf[8], wf[8];
+                unpack8(xv[i], xf);
+                unpack8(gv[i], gf);
+                unpack8(__ldg(w + idx), wf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float xn = xf[j] * r;
+                    dot += gf[j] * wf[j] * xn;
+                    dwacc[i][j] += gf[j] * bf16_round(xn);
+                }
+            }
+        }
+        dot = block_sum(dot, red) * inv_h;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int idx = threadIdx.x + i * kThreads;
+            if (idx < H8) {
+                float xf[8], gf[8], wf[8], o[8];
+                unpack8(xv[i], xf);
+                unpack8(gv[i], gf);
+                unpack8(__ldg(w + idx), wf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = r * (gf[j] * wf[j] - xf[j] * r * dot);
+                if (dx_add != nullptr) {
+                    float a[8];
+                    unpack8(__ldg(dx_add + row * H8 + idx), a);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] += a[j];
+                }
+                dx[row * H8 + idx] = pack8(o);
+            }
+        }
+    }
+    float* wrow = ws + int64_t(blockIdx.x) * H8 * 8;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int idx = threadIdx.x + i * kThreads;
+        if (idx < H8) {
+            float4* p = reinterpret_cast<float4*>(wrow + idx * 8);
+            p[0] = make_float4(dwacc[i][0], dwacc[i][1], dwacc[i][2], dwacc[i][3]);
+            p[1] = make_float4(dwacc[i][4], dwacc[i][5], dwacc[i][6], dwacc[i][7]);
+        }
+    }
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ ws, float* __restrict__ out, int parts, int H) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= H) return;
+    float s = 0.f;
+    for (int p = 0; p < parts; ++p) s += ws[int64_t(p) * H + c];
+    out[c] += s;
+}
+
+// ------------------------------------------------------------------------------------------
+// RoPE in place on packed qkv.  One block per token; each work item = one 8-wide vector of the first half of a
+// rotated head slot and its partner in the second half.  bf16 rounding after every op like the eager reference.
+// ------------------------------------------------------------------------------------------
+template <typename PosT>
+__global__ void __launch_bounds__(kThreads)
+    rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t row_stride, int64_t T, int n_groups, int q_per_group, int hd,
+                const __nv_bfloat16* __restrict__ cos_t, const __nv_bfloat16* __restrict__ sin_t,
+                const PosT* __restrict__ pos_ids, int64_t n_pos, float sin_sign) {
+    const int half = hd >> 1;
+    const int vec_per_half = half >> 3;
+    const int rot_slots = q_per_group + 1;
+    const int items = n_groups * rot_slots * vec_per_half;
+    for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
+        int64_t pos = static_cast<int64_t>(pos_ids[t]);
+        pos = pos < 0 ? 0 : (pos >= n_pos ? n_pos - 1 : pos);
+        const __nv_bfloat16* c = cos_t + pos * hd;
+        const __nv_bfloat16* s = sin_t + pos * hd;
+        __nv_bfloat16* row = qkv + t * row_stride;
+        for (int it = threadIdx.x; it < items; it += blockDim.x) {
+            const int v = it % vec_per_half;
+            const int slot_lin = it / vec_per_half;
+            const int g = slot_lin / rot_slots, sl = slot_lin % rot_slots;
+            __nv_bfloat16* base = row + int64_t(g) * (q_per_group + 2) * hd + int64_t(sl) * hd + v * 8;
+            uint4 a = *reinterpret_cast<uint4*>(base);
+            uint4 b = *reinterpret_cast<uint4*>(base + half);
+            float x1[8], x2[8], c1[8], c2[8], s1[8], s2[8], o1[8], o2[8];
+            unpack8(a, x1);
+            unpack8(b, x2);
+            unpack8(*reinterpret_cast<const uint4*>(c + v * 8), c1);
+            unpack8(*reinterpret_cast<const uint4*>(c + half + v * 8), c2);
+            unpack8(*reinterpret_cast<const uint4*>(s + v * 8), s1);
+            unpack8(*reinterpret_cast<const uint4*>(s + half + v * 8), s2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                // y = x*cos + rotate_half(x)*sin ; rotate_half(x) = cat(-x2, x1)
+                o1[j] = bf16_round(x1[j] * c1[j]) + bf16_round(-x2[j] * (s1[j] * sin_sign));
+                o2[j] = bf16_round(x2[j] * c2[j]) + bf16_round(x1[j] * (s2[j] * sin_sign));
+            }
+            *reinterpret_cast<uint4*>(base) = pack8(o1);
+            *reinterpret_cast<uint4*>(base + half) = pack8(o2);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// SwiGLU
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+__global__ void __launch_bounds__(kThreads)
+    swiglu_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t T, int64_t F8) {
+    const int64_t total = T * F8;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t t = i / F8, c = i - t * F8;
+        float u[8], g[8], o[8];
+        unpack8(__ldg(x + t * 2 * F8 + c), u);
+        unpack8(__ldg(x + t * 2 * F8 + F8 + c), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = u[j] * bf16_round(g[j] * sigmoidf_(g[j]));
+        y[i] = pack8(o);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) swiglu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
+                                                              uint4* __restrict__ dx, int64_t T, int64_t F8) {
+    const int64_t total = T * F8;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t t = i / F8, c = i - t * F8;
+        float u[8], g[8], d[8], du[8], dg[8];
+        unpack8(__ldg(x + t * 2 * F8 + c), u);
+        unpack8(__ldg(x + t * 2 * F8 + F8 + c), g);
+        unpack8(__ldg(dy + i), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float sg = sigmoidf_(g[j]);
+            const float silu = g[j] * sg;
+            du[j] = d[j] * silu;
+            dg[j] = d[j] * u[j] * (sg * (1.f + g[j] * (1.f - sg)));
+        }
+        dx[t * 2 * F8 + c] = pack8(du);
+        dx[t * 2 * F8 + F8 + c] = pack8(dg);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Embedding
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    embedding_fwd_kernel(const int64_t* __restrict__ ids, const uint4* __restrict__ wte, uint4* __restrict__ out,
+                         int64_t T, int H8, int64_t V, float scale, int apply_scale) {
+    for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
+        int64_t id = ids[t];
+        id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+        const uint4* src = wte + id * H8;
+        for (int i = threadIdx.x; i < H8; i += blockDim.x) {
+            uint4 v = __ldg(src + i);
+            if (apply_scale) {
+                float f[8];
+                unpack8(v, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] *= scale;
+                v = pack8(f);
+            }
+            out[t * H8 + i] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+    embedding_bwd_kernel(const int64_t* __restrict__ ids, const uint4* __restrict__ dout, float* __restrict__ dwte,
+                         int64_t T, int H8, int64_t V, float scale) {
+    for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
+        int64_t id = ids[t];
+        id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+        float* dst = dwte + id * H8 * 8;
+        for (int i = threadIdx.x; i < H8; i += blockDim.x) {
+            float f[8];
+            unpack8(__ldg(dout + t * H8 + i), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(dst + i * 8 + j, f[j] * scale);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Cross entropy: one block per row.  Pass 1 online (max, sumexp); pass 2 rewrites the row as the gradient.
+// ------------------------------------------------------------------------------------------
+constexpr int kCeThreads = 512;
+
+__global__ void ce_count_kernel(const int64_t* __restrict__ labels, int64_t T, int64_t ignore_index,
+                                float* __restrict__ scratch) {
+    // single block; scratch[0] = n_valid, scratch[1] = 0 (loss accumulator)
+    __shared__ float red[32];
+    float c = 0.f;
+    for (int64_t i = threadIdx.x; i < T; i += blockDim.x) c += (labels[i] != ignore_index) ? 1.f : 0.f;
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) {
+            scratch[0] = t;
+            scratch[1] = 0.f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kCeThreads)
+    ce_fwd_bwd_kernel(const uint4* __restrict__ logits, int64_t ld8, const int64_t* __restrict__ labels,
+                      uint4* __restrict__ dlogits, float* __restrict__ loss_tok, const float* __restrict__ scratch,
+                      int64_t T, int64_t V, int64_t ignore_index, float logit_scale, float grad_scale) {
+    __shared__ float red_m[kCeThreads / 32], red_s[kCeThreads / 32];
+    __shared__ float s_lse;
+    const int64_t V8 = V >> 3;
+    const float n_valid = scratch[0];
+    const float gs = n_valid > 0.f ? grad_scale / n_valid : 0.f;
+    for (int64_t row = blockIdx.x; row < T; row += gridDim.x) {
+        const uint4* lr = logits + row * ld8;
+        uint4* dr = dlogits + row * ld8;
+        const int64_t label = labels[row];
+        const bool valid = (label != ignore_index);
+        if (!valid) {
+            // uniform per block: zero gradient row
+            for (int64_t i = threadIdx.x; i < V8; i += blockDim.x) dr[i] = make_uint4(0, 0, 0, 0);
+            if (threadIdx.x == 0) loss_tok[row] = 0.f;
+            continue;
+        }
+        float m = -INFINITY, s = 0.f;
+        for (int64_t i = threadIdx.x; i < V8; i += blockDim.x) {
+            float f[8];
+            unpack8(__ldg(lr + i), f);
+            float lm = f[0] * logit_scale;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { f[j] *= logit_scale; lm = fmaxf(lm, f[j]); }
+            if (lm > m) { s *= __expf(m - lm); m = lm; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += __expf(f[j] - m);
+        }
+        // warp combine
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+            const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+            const float mn = fmaxf(m, m2);
+            s = (m == -INFINITY ? 0.f : s * __expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
+            m = mn;
+        }
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) { red_m[wid] = m; red_s[wid] = s; }
+        __syncthreads();
+        if (wid == 0) {
+            float mm = lane < (kCeThreads / 32) ? red_m[lane] : -INFINITY;
+            float sv = lane < (kCeThreads / 32) ? red_s[lane] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float m2 = __shfl_xor_sync(0xffffffffu, mm, o);
+                const float s2 = __shfl_xor_sync(0xffffffffu, sv, o);
+                const float mn = fmaxf(mm, m2);
+                sv = (mm == -INFINITY ? 0.f : sv * __expf(mm - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
+                mm = mn;
+            }
+            if (lane == 0) s_lse = mm + __logf(sv);
+        }
+        __syncthreads();
+        const float lse = s_lse;
+        if (threadIdx.x == 0) {
+            const __nv_bfloat16* lrow = reinterpret_cast<const __nv_bfloat16*>(lr);
+            const float xl = __bfloat162float(lrow[label]) * logit_scale;
+            loss_tok[row] = lse - xl;
+        }
+        __syncthreads();  // label logit read before the row is overwritten (dlogits may alias logits)
+        const int64_t lvec = label >> 3;
+        const int lsub = int(label & 7);
+        for (int64_t i = threadIdx.x; i < V8; i += blockDim.x) {
+            float f[8];
+            unpack8(__ldg(lr + i), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __expf(f[j] * logit_scale - lse);
+            if (i == lvec) f[lsub] -= 1.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] *= gs * logit_scale;
+            dr[i] = pack8(f);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void ce_mean_kernel(const float* __restrict__ loss_tok, int64_t T, const float* __restrict__ scratch,
+                               float* __restrict__ loss_mean) {
+    // single block, deterministic order
+    __shared__ float red[32];
+    float s = 0.f;
+    for (int64_t i = threadIdx.x; i < T; i += blockDim.x) s += loss_tok[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) loss_mean[0] = scratch[0] > 0.f ? t / scratch[0] : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// column sums: grid (col tiles of 256 columns, row splits).  each thread owns 8 columns (one 16-B vector)
+// of 32 lanes; 8 warps stride rows; smem combine; atomicAdd to out.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t T, int64_t N,
+                  int rows_per_block) {
+    __shared__ float sm[8][256];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t col = int64_t(blockIdx.x) * 256 + lane * 8;
+    const int64_t r0 = int64_t(blockIdx.y) * rows_per_block;
+    const int64_t r1 = min(T, r0 + rows_per_block);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (col < N) {
+        for (int64_t r = r0 + wid; r < r1; r += 8) {
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * ldx + col)), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[wid][lane * 8 + j] = acc[j];
+    __syncthreads();
+    const int c = threadIdx.x;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sm[w][c];
+    const int64_t gc = int64_t(blockIdx.x) * 256 + c;
+    if (gc < N) atomicAdd(out + gc, s);
+}
+
+__global__ void __launch_bounds__(kThreads) add_scaled_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                                              uint4* __restrict__ out, float alpha, int64_t n8) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += int64_t(gridDim.x) * blockDim.x) {
+        float x[8], y[8];
+        unpack8(a[i], x);
+        unpack8(b[i], y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = x[j] + bf16_round(alpha * y[j]);
+        out[i] = pack8(x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// optimizer kernels on flat fp32 shards
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
+    __shared__ float red[8];
+    float s = 0.f;
+    const int64_t n4 = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+        const float4 v = __ldg(g4 + i);
+        s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    for (int64_t i = (n4 << 2) + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += int64_t(gridDim.x) * blockDim.x)
+        s += g[i] * g[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+__global__ void clip_coef_kernel(const float* sumsq, float max_norm, float* coef, float* norm_out) {
+    const float norm = sqrtf(sumsq[0]);
+    if (norm_out) norm_out[0] = norm;
+    float c = 1.f;
+    if (max_norm > 0.f) c = fminf(1.f, max_norm / (norm + 1e-6f));
+    coef[0] = c;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 __nv_bfloat16* __restrict__ pb, int64_t n, float lr, float b1, float b2, float eps, float wd,
+                 float bc1, float bc2_sqrt, const float* __restrict__ clip) {
+    const float cc = clip ? clip[0] : 1.f;
+    const float step_size = lr / bc1;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const float gi = g[i] * cc;
+        float pi = p[i] * (1.f - lr * wd);
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        pi -= step_size * (mi / denom);
+        p[i] = pi;
+        m[i] = mi;
+        v[i] = vi;
+        if (pb) pb[i] = __float2bfloat16_rn(pi);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+    cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, int64_t n) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+        d[i] = __float2bfloat16_rn(s[i]);
+}
+__global__ void __launch_bounds__(kThreads)
+    accum_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, float* __restrict__ d, float scale, int64_t n) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+        d[i] += scale * __bfloat162float(s[i]);
+}
+
+inline int grid_for(int64_t work_items, int per_block) {
+    int64_t b = (work_items + per_block - 1) / per_block;
+    const int64_t cap = int64_t(dolo_num_sms()) * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return int(b);
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" int dolomite_b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t T, int H,
+                                         float eps, void* stream) {
+    DOLO_REQUIRE(H > 0 && H % 8 == 0, "rmsnorm: H=%d must be a positive multiple of 8", H);
+    DOLO_REQUIRE(H <= 8 * kThreads * 8, "rmsnorm: H=%d too large (max %d)", H, 8 * kThreads * 8);
+    DOLO_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y), "rmsnorm: pointers must be 16-byte aligned");
+    if (T == 0) return DOLO_OK;
+    const int H8 = H / 8;
+    const int nv = (H8 + kThreads - 1) / kThreads;
+    const int grid = int(T < int64_t(dolo_num_sms()) * 16 ? T : int64_t(dolo_num_sms()) * 16);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto X = static_cast<const uint4*>(x);
+    auto W = static_cast<const uint4*>(w);
+    auto Y = static_cast<uint4*>(y);
+    const float inv_h = 1.f / float(H);
+    switch (nv) {
+        case 1: rmsnorm_fwd_kernel<1><<<grid, kThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h); break;
+        case 2: rmsnorm_fwd_kernel<2><<<grid, kThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h); break;
+        case 3:
+        case 4: rmsnorm_fwd_kernel<4><<<grid, kThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h); break;
+        default: rmsnorm_fwd_kernel<8><<<grid, kThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h); break;
+    }
+    DOLO_LAUNCH_OK("rmsnorm_fwd");
+    return DOLO_OK;
+}
+
+static int rmsnorm_bwd_parts() { return dolo_num_sms() * 4; }
+
+extern "C" int64_t dolomite_b200_rmsnorm_bwd_workspace_bytes(int H) {
+    return int64_t(rmsnorm_bwd_parts()) * H * sizeof(float);
+}
+
+extern "C" int dolomite_b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd,
+                                         const void* dx_add, void* dx, float* dw_accum, void* workspace, int64_t T,
+                                         int H, void* stream) {
+    DOLO_REQUIRE(H > 0 && H % 8 == 0, "rmsnorm_bwd: H=%d must be a positive multiple of 8", H);
+    DOLO_REQUIRE(H <= 8 * kThreads * 8, "rmsnorm_bwd: H=%d too large", H);
+    DOLO_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(w) && aligned16(dx) && aligned16(workspace) &&
+                     aligned16(dx_add),
+                 "rmsnorm_bwd: pointers must be 16-byte aligned");
+    if (T == 0) return DOLO_OK;
+    const int H8 = H / 8;
+    const int nv = (H8 + kThreads - 1) / kThreads;
+    int parts = rmsnorm_bwd_parts();
+    if (T < parts) parts = int(T);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto DY = static_cast<const uint4*>(dy);
+    auto X = static_cast<const uint4*>(x);
+    auto W = static_cast<const uint4*>(w);
+    auto DA = static_cast<const uint4*>(dx_add);
+    auto DX = static_cast<uint4*>(dx);
+    auto WS = static_cast<float*>(workspace);
+    const float inv_h = 1.f / float(H);
+    switch (nv) {
+        case 1: rmsnorm_bwd_kernel<1><<<parts, kThreads, 0, st>>>(DY, X, W, rstd, DA, DX, WS, T, H8, inv_h); break;
+        case 2: rmsnorm_bwd_kernel<2><<<parts, kThreads, 0, st>>>(DY, X, W, rstd, DA, DX, WS, T, H8, inv_h); break;
+        case 3:
+        case 4: rmsnorm_bwd_kernel<4><<<parts, kThreads, 0, st>>>(DY, X, W, rstd, DA, DX, WS, T, H8, inv_h); break;
+        default: rmsnorm_bwd_kernel<8><<<parts, kThreads, 0, st>>>(DY, X, W, rstd, DA, DX, WS, T, H8, inv_h); break;
+    }
+    DOLO_LAUNCH_OK("rmsnorm_bwd");
+    if (dw_accum != nullptr) {
+        reduce_partials_kernel<<<(H + 255) / 256, 256, 0, st>>>(WS, dw_accum, parts, H);
+        DOLO_LAUNCH_OK("rmsnorm_bwd_reduce");
+    }
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_rope_qk_inplace(void* qkv, int64_t row_stride, int64_t T, int n_groups, int q_per_group,
+                                             int head_dim, const void* cos_table, const void* sin_table,
+                                             const void* position_ids, int position_ids_is_int64, int64_t n_positions,
+                                             int inverse, void* stream) {
+    DOLO_REQUIRE(head_dim > 0 && head_dim % 16 == 0, "rope: head_dim=%d must be a multiple of 16", head_dim);
+    DOLO_REQUIRE(row_stride % 8 == 0 && aligned16(qkv) && aligned16(cos_table) && aligned16(sin_table),
+                 "rope: 16-byte alignment required (row_stride %lld)", (long long)row_stride);
+    DOLO_REQUIRE(int64_t(n_groups) * (q_per_group + 2) * head_dim <= row_stride, "rope: slot layout exceeds row stride");
+    DOLO_REQUIRE(n_positions > 0, "rope: empty cos/sin table");
+    if (T == 0) return DOLO_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = int(T < int64_t(dolo_num_sms()) * 16 ? T : int64_t(dolo_num_sms()) * 16);
+    const float sgn = inverse ? -1.f : 1.f;
+    auto Q = static_cast<__nv_bfloat16*>(qkv);
+    auto C = static_cast<const __nv_bfloat16*>(cos_table);
+    auto S = static_cast<const __nv_bfloat16*>(sin_table);
+    if (position_ids_is_int64)
+        rope_kernel<int64_t><<<grid, kThreads, 0, st>>>(Q, row_stride, T, n_groups, q_per_group, head_dim, C, S,
+                                                        static_cast<const int64_t*>(position_ids), n_positions, sgn);
+    else
+        rope_kernel<int32_t><<<grid, kThreads, 0, st>>>(Q, row_stride, T, n_groups, q_per_group, head_dim, C, S,
+                                                        static_cast<const int32_t*>(position_ids), n_positions, sgn);
+    DOLO_LAUNCH_OK("rope");
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_swiglu_fwd(const void* x, void* y, int64_t T, int64_t F, void* stream) {
+    DOLO_REQUIRE(F > 0 && F % 8 == 0, "swiglu: F=%lld must be a positive multiple of 8", (long long)F);
+    DOLO_REQUIRE(aligned16(x) && aligned16(y), "swiglu: pointers must be 16-byte aligned");
+    if (T == 0) return DOLO_OK;
+    const int64_t F8 = F / 8;
+    swiglu_fwd_kernel<<<grid_for(T * F8, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(x), static_cast<uint4*>(y), T, F8);
+    DOLO_LAUNCH_OK("swiglu_fwd");
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_swiglu_bwd(const void* dy, const void* x, void* dx, int64_t T, int64_t F, void* stream) {
+    DOLO_REQUIRE(F > 0 && F % 8 == 0, "swiglu_bwd: F=%lld must be a positive multiple of 8", (long long)F);
+    DOLO_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dx), "swiglu_bwd: pointers must be 16-byte aligned");
+    if (T == 0) return DOLO_OK;
+    const int64_t F8 = F / 8;
+    swiglu_bwd_kernel<<<grid_for(T * F8, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(dy), static_cast<const uint4*>(x), static_cast<uint4*>(dx), T, F8);
+    DOLO_LAUNCH_OK("swiglu_bwd");
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_embedding_fwd(const int64_t* ids, const void* wte, void* out, int64_t T, int H, int64_t V,
+                                           float scale, void* stream) {
+    DOLO_REQUIRE(H > 0 && H % 8 == 0, "embedding: H=%d must be a multiple of 8", H);
+    DOLO_REQUIRE(aligned16(wte) && aligned16(out), "embedding: pointers must be 16-byte aligned");
+    if (T == 0) return DOLO_OK;
+    const int grid = int(T < int64_t(dolo_num_sms()) * 16 ? T : int64_t(dolo_num_sms()) * 16);
+    embedding_fwd_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        ids, static_cast<const uint4*>(wte), static_cast<uint4*>(out), T, H / 8, V, scale, scale != 1.f);
+    DOLO_LAUNCH_OK("embedding_fwd");
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_embedding_bwd(const int64_t* ids, const void* dout, float* dwte, int64_t T, int H,
+                                           int64_t V, float scale, void* stream) {
+    DOLO_REQUIRE(H > 0 && H % 8 == 0, "embedding_bwd: H=%d must be a multiple of 8", H);
+    DOLO_REQUIRE(aligned16(dout), "embedding_bwd: pointers must be 16-byte aligned");
+    if (T == 0) return DOLO_OK;
+    const int grid = int(T < int64_t(dolo_num_sms()) * 16 ? T : int64_t(dolo_num_sms()) * 16);
+    embedding_bwd_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        ids, static_cast<const uint4*>(dout), dwte, T, H / 8, V, scale);
+    DOLO_LAUNCH_OK("embedding_bwd");
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_cross_entropy_fwd_bwd(const void* logits, int64_t ldl, const int64_t* labels,
+                                                   void* dlogits, float* loss_per_token, float* loss_mean,
+                                                   float* scratch, int64_t T, int64_t V, int64_t ignore_index,
+                                                   float logit_scale, float grad_scale, void* stream) {
+    DOLO_REQUIRE(V > 0 && V % 8 == 0 && ldl % 8 == 0 && ldl >= V,
+                 "cross_entropy: V=%lld / ld=%lld must be multiples of 8", (long long)V, (long long)ldl);
+    DOLO_REQUIRE(aligned16(logits) && aligned16(dlogits), "cross_entropy: pointers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ce_count_kernel<<<1, 1024, 0, st>>>(labels, T, ignore_index, scratch);
+    DOLO_LAUNCH_OK("ce_count");
+    if (T > 0) {
+        const int grid = int(T < int64_t(dolo_num_sms()) * 4 ? T : int64_t(dolo_num_sms()) * 4);
+        ce_fwd_bwd_kernel<<<grid, kCeThreads, 0, st>>>(static_cast<const uint4*>(logits), ldl / 8, labels,
+                                                       static_cast<uint4*>(dlogits), loss_per_token, scratch, T, V,
+                                                       ignore_index, logit_scale, grad_scale);
+        DOLO_LAUNCH_OK("ce_fwd_bwd");
+    }
+    ce_mean_kernel<<<1, 1024, 0, st>>>(loss_per_token, T, scratch, loss_mean);
+    DOLO_LAUNCH_OK("ce_mean");
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_colsum_accum(const void* x, int64_t ldx, float* out, int64_t T, int64_t N, void* stream) {
+    DOLO_REQUIRE(N > 0 && N % 8 == 0 && ldx % 8 == 0, "colsum: N=%lld / ld=%lld must be multiples of 8", (long long)N,
+                 (long long)ldx);
+    DOLO_REQUIRE(aligned16(x), "colsum: pointer must be 16-byte aligned");
+    if (T == 0) return DOLO_OK;
+    const int col_tiles = int((N + 255) / 256);
+    int row_splits = (dolo_num_sms() * 4 + col_tiles - 1) / col_tiles;
+    if (row_splits > (T + 63) / 64) row_splits = int((T + 63) / 64);
+    if (row_splits < 1) row_splits = 1;
+    const int rows_per_block = int((T + row_splits - 1) / row_splits);
+    dim3 grid(col_tiles, row_splits);
+    colsum_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ldx,
+                                                                            out, T, N, rows_per_block);
+    DOLO_LAUNCH_OK("colsum");
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_add_scaled(const void* a, const void* b, void* out, float alpha, int64_t n, void* stream) {
+    DOLO_REQUIRE(n % 8 == 0, "add_scaled: n=%lld must be a multiple of 8", (long long)n);
+    DOLO_REQUIRE(aligned16(a) && aligned16(b) && aligned16(out), "add_scaled: pointers must be 16-byte aligned");
+    if (n == 0) return DOLO_OK;
+    add_scaled_kernel<<<grid_for(n / 8, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(out), alpha, n / 8);
+    DOLO_LAUNCH_OK("add_scaled");
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_sumsq_accum(const float* g, int64_t n, float* out, void* stream) {
+    DOLO_REQUIRE(aligned16(g), "sumsq: pointer must be 16-byte aligned");
+    if (n == 0) return DOLO_OK;
+    sumsq_kernel<<<grid_for(n / 4 + 1, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(g, n, out);
+    DOLO_LAUNCH_OK("sumsq");
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_clip_coef(const float* sumsq, float max_norm, float* coef_out, float* norm_out,
+                                       void* stream) {
+    clip_coef_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(sumsq, max_norm, coef_out, norm_out);
+    DOLO_LAUNCH_OK("clip_coef");
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
+                                        float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                                        const float* clip_coef, void* stream) {
+    DOLO_REQUIRE(step >= 1, "adamw: step must be >= 1 (got %lld)", (long long)step);
+    if (n == 0) return DOLO_OK;
+    const float bc1 = 1.f - powf(beta1, float(step));
+    const float bc2 = 1.f - powf(beta2, float(step));
+    adamw_kernel<<<grid_for(n, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        p, g, m, v, static_cast<__nv_bfloat16*>(p_bf16), n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2),
+        clip_coef);
+    DOLO_LAUNCH_OK("adamw");
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+    if (n == 0) return DOLO_OK;
+    cast_f32_bf16_kernel<<<grid_for(n, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, static_cast<__nv_bfloat16*>(dst), n);
+    DOLO_LAUNCH_OK("cast_f32_to_bf16");
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_accum_bf16_into_f32(const void* src, float* dst, float scale, int64_t n, void* stream) {
+    if (n == 0) return DOLO_OK;
+    accum_bf16_f32_kernel<<<grid_for(n, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(src), dst, scale, n);
+    DOLO_LAUNCH_OK("accum_bf16_into_f32");
+    return DOLO_OK;
+}

@@ -1,0 +1,378 @@
+// bf16 GEMM for sm_100a:  TMA (cp.async.bulk.tensor) -> 128B-swizzled smem ring -> tcgen05.mma (UMMA 128x256x16,
+// fp32 accumulators in TMEM, double buffered) -> epilogue warps (tcgen05.ld, alpha/bias/beta*C, bf16|fp32 store).
+//
+// Persistent, warp-specialised:  warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue.
+// Both operands may be K-major (row-major [rows, K]) or MN-major (stored [K, rows]); the latter is what dgrad / wgrad
+// need, so no transposes are ever materialised:
+//     fwd   Y[T,N]  = X[T,K]  . W[N,K]^T          A K-major,  B K-major
+//     dgrad dX[T,K] = dY[T,N] . W[N,K]            A K-major,  B MN-major (stored [N(contraction), K(out)])
+//     wgrad dW[N,K] = dY[T,N]^T . X[T,K]          A MN-major, B MN-major (contraction over T)
+#include "common.cuh"
+#include "../../include/dolomite_b200.h"
+
+using namespace dolo;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle span
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int EPI_SLAB_BYTES = BM * 64 * 2;  // 128 rows x 64 bf16 columns, SW128
+constexpr int EPI_BUFS = 2;
+constexpr int GEMM_THREADS = 192;
+constexpr int TMEM_COLS = 512;  // 2 accumulator stages x 256 fp32 columns
+constexpr int GROUP_M = 8;
+
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BUFS * EPI_SLAB_BYTES + 256 /*barriers*/;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+
+struct GemmParams {
+    void* D;
+    const void* C;
+    const __nv_bfloat16* bias;
+    int64_t ldd, ldc;
+    int M, N, K;
+    float alpha, beta;
+    int d_is_f32;
+    int tma_store;
+    int num_m, num_n, num_kb;
+};
+
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
+    const int per_group = GROUP_M * num_n;
+    const int group = t / per_group;
+    const int first_m = group * GROUP_M;
+    const int gsize = min(num_m - first_m, GROUP_M);
+    const int r = t - group * per_group;
+    m_blk = first_m + r % gsize;
+    n_blk = r / gsize;
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+    uint8_t* smem_epi = smem + STAGES * STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_BUFS * EPI_SLAB_BYTES);
+    uint64_t* full_bar = bars;                   // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;         // [STAGES]
+    uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m * p.num_n;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        if (p.tma_store) tma_prefetch_desc(&tmap_d);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                int m_blk, n_blk;
+                tile_coords(t, p.num_m, p.num_n, m_blk, n_blk);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+                    uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
+                    if (!A_MN) {
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BM / 64; ++i)
+                            tma_load_2d(sa + i * (BK * 128), &tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BN / 64; ++i)
+                            tma_load_2d(sb + i * (BK * 128), &tmap_b, &full_bar[stage], n_blk * BN + i * 64, kb * BK);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, 3);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
+                    const uint32_t sb = smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // K-major: +32 B per K=16 step inside the 128 B swizzle span; SBO = 8 rows x 128 B.
+                        // MN-major: +16 K-rows x 128 B per step; LBO = next 64-wide MN chunk (BK rows x 128 B), SBO = 8 K-rows.
+                        const uint64_t adesc = A_MN ? umma_smem_desc(sa + k * 2048, BK * 128, 1024, 2)
+                                                    : umma_smem_desc(sa + k * 32, 16, 1024, 2);
+                        const uint64_t bdesc = B_MN ? umma_smem_desc(sb + k * 2048, BK * 128, 1024, 2)
+                                                    : umma_smem_desc(sb + k * 32, 16, 1024, 2);
+                        umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);  // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue (4 warps, TMEM sub-partition = warp % 4) =================
+        const int sub = warp & 3;
+        const int et = sub * 32 + lane;  // row within the tile == TMEM lane
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int epi_buf = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            int m_blk, n_blk;
+            tile_coords(t, p.num_m, p.num_n, m_blk, n_blk);
+            mbar_wait(&tmem_full[acc], acc_phase, 4);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (uint32_t(sub * 32) << 16) + uint32_t(acc * BN);
+            const int64_t row = int64_t(m_blk) * BM + et;
+            const bool row_ok = row < p.M;
+            const int col0 = n_blk * BN;
+
+            if (p.tma_store) {
+                // 4 slabs of 64 columns: regs -> swizzled smem -> TMA store
+#pragma unroll 1
+                for (int slab = 0; slab < BN / 64; ++slab) {
+                    if (col0 + slab * 64 >= p.N) break;
+                    uint8_t* buf = smem_epi + epi_buf * EPI_SLAB_BYTES;
+                    // the buffer must have been fully read by the TMA store issued two slabs ago
+                    if (et == 0) tma_store_wait_read<EPI_BUFS - 1>();
+                    named_bar_sync(1, 128);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t r[32];
+                        tmem_ld32(t_addr + slab * 64 + h * 32, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {  // 4 x 16-byte chunks (8 columns each)
+                            float f[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[c * 8 + j]) * p.alpha;
+                            if (p.bias != nullptr) {
+                                const int cb = col0 + slab * 64 + h * 32 + c * 8;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    if (cb + j < p.N) f[j] += __bfloat162float(p.bias[cb + j]);
+                            }
+                            uint4 v;
+                            v.x = pack_bf16(f[0], f[1]);
+                            v.y = pack_bf16(f[2], f[3]);
+                            v.z = pack_bf16(f[4], f[5]);
+                            v.w = pack_bf16(f[6], f[7]);
+                            const int chunk = h * 4 + c;  // logical 16-byte chunk inside the 128-byte row
+                            *reinterpret_cast<uint4*>(buf + et * 128 + ((chunk ^ (et & 7)) << 4)) = v;
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, 128);
+                    if (et == 0) {
+                        tma_store_2d(&tmap_d, buf, col0 + slab * 64, m_blk * BM);
+                        tma_store_commit();
+                    }
+                    epi_buf ^= 1;
+                }
+            } else {
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ++ch) {
+                    const int cb = col0 + ch * 32;
+                    if (cb >= p.N) break;
+                    uint32_t r[32];
+                    tmem_ld32(t_addr + ch * 32, r);
+                    tmem_ld_wait();
+                    if (!row_ok) continue;
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]) * p.alpha;
+                    if (p.bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (cb + j < p.N) f[j] += __bfloat162float(p.bias[cb + j]);
+                    }
+                    if (p.d_is_f32) {
+                        float* drow = static_cast<float*>(p.D) + row * p.ldd + cb;
+                        const float* crow = p.C ? static_cast<const float*>(p.C) + row * p.ldc + cb : nullptr;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            if (cb + q * 4 < p.N) {  // N % 8 == 0 -> whole float4 in range
+                                float4 o = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+                                if (crow) {
+                                    const float4 c4 = *reinterpret_cast<const float4*>(crow + q * 4);
+                                    o.x += p.beta * c4.x; o.y += p.beta * c4.y; o.z += p.beta * c4.z; o.w += p.beta * c4.w;
+                                }
+                                *reinterpret_cast<float4*>(drow + q * 4) = o;
+                            }
+                        }
+                    } else {
+                        __nv_bfloat16* drow = static_cast<__nv_bfloat16*>(p.D) + row * p.ldd + cb;
+                        const __nv_bfloat16* crow =
+                            p.C ? static_cast<const __nv_bfloat16*>(p.C) + row * p.ldc + cb : nullptr;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (cb + q * 8 < p.N) {
+                                if (crow) {
+                                    const uint4 cv = *reinterpret_cast<const uint4*>(crow + q * 8);
+                                    f[q * 8 + 0] += p.beta * bf16_lo(cv.x); f[q * 8 + 1] += p.beta * bf16_hi(cv.x);
+                                    f[q * 8 + 2] += p.beta * bf16_lo(cv.y); f[q * 8 + 3] += p.beta * bf16_hi(cv.y);
+                                    f[q * 8 + 4] += p.beta * bf16_lo(cv.z); f[q * 8 + 5] += p.beta * bf16_hi(cv.z);
+                                    f[q * 8 + 6] += p.beta * bf16_lo(cv.w); f[q * 8 + 7] += p.beta * bf16_hi(cv.w);
+                                }
+                                uint4 v;
+                                v.x = pack_bf16(f[q * 8 + 0], f[q * 8 + 1]);
+                                v.y = pack_bf16(f[q * 8 + 2], f[q * 8 + 3]);
+                                v.z = pack_bf16(f[q * 8 + 4], f[q * 8 + 5]);
+                                v.w = pack_bf16(f[q * 8 + 6], f[q * 8 + 7]);
+                                *reinterpret_cast<uint4*>(drow + q * 8) = v;
+                            }
+                        }
+                    }
+                }
+            }
+            // release the accumulator stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (p.tma_store && et == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+template <bool A_MN, bool B_MN>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p,
+                cudaStream_t st) {
+    auto kern = gemm_bf16_kernel<A_MN, B_MN>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        DOLO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles = p.num_m * p.num_n;
+    const int grid = tiles < dolo_num_sms() ? tiles : dolo_num_sms();
+    kern<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(ta, tb, td, p);
+    DOLO_LAUNCH_OK("gemm_bf16");
+    return DOLO_OK;
+}
+
+}  // namespace
+
+extern "C" int dolomite_b200_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
+                                       int b_mn_major, void* D, int64_t ldd, int d_is_f32, const void* C, int64_t ldc,
+                                       float alpha, float beta, const void* bias, int64_t M, int64_t N, int64_t K,
+                                       int flags, void* stream) {
+    DOLO_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative dimension");
+    if (M == 0 || N == 0) return DOLO_OK;
+    DOLO_REQUIRE(K > 0, "gemm: K must be > 0");
+    DOLO_REQUIRE(K % 8 == 0 && N % 8 == 0, "gemm: K=%lld and N=%lld must be multiples of 8", (long long)K, (long long)N);
+    DOLO_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldd % (d_is_f32 ? 4 : 8) == 0, "gemm: leading dimensions must keep 16-byte alignment");
+    DOLO_REQUIRE(!a_mn_major || M % 8 == 0, "gemm: MN-major A requires M %% 8 == 0");
+    DOLO_REQUIRE(C == nullptr || ldc % (d_is_f32 ? 4 : 8) == 0, "gemm: ldc alignment");
+    DOLO_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm: dimension too large");
+    const bool tma_store = (flags & DOLO_GEMM_FLAG_TMA_STORE) != 0;
+    DOLO_REQUIRE(!tma_store || (!d_is_f32 && C == nullptr), "gemm: TMA-store epilogue needs bf16 D and no C");
+
+    CUtensorMap ta, tb, td;
+    {
+        // K-major: dims {K, rows}, box {64, tile rows}.  MN-major: dims {rows, K}, box {64, 64}.
+        uint64_t dims[2], strides[2];
+        uint32_t box[2];
+        if (!a_mn_major) {
+            dims[0] = uint64_t(K); dims[1] = uint64_t(M); strides[0] = 2; strides[1] = uint64_t(lda) * 2;
+            box[0] = BK; box[1] = BM;
+        } else {
+            dims[0] = uint64_t(M); dims[1] = uint64_t(K); strides[0] = 2; strides[1] = uint64_t(lda) * 2;
+            box[0] = 64; box[1] = BK;
+        }
+        int rc = dolo_make_tmap(&ta, A, 2, 2, dims, strides, box, DOLO_SW_128);
+        if (rc) return rc;
+        if (!b_mn_major) {
+            dims[0] = uint64_t(K); dims[1] = uint64_t(N); strides[1] = uint64_t(ldb) * 2;
+            box[0] = BK; box[1] = BN;
+        } else {
+            dims[0] = uint64_t(N); dims[1] = uint64_t(K); strides[1] = uint64_t(ldb) * 2;
+            box[0] = 64; box[1] = BK;
+        }
+        rc = dolo_make_tmap(&tb, B, 2, 2, dims, strides, box, DOLO_SW_128);
+        if (rc) return rc;
+        if (tma_store) {
+            dims[0] = uint64_t(N); dims[1] = uint64_t(M); strides[1] = uint64_t(ldd) * 2;
+            box[0] = 64; box[1] = BM;
+            rc = dolo_make_tmap(&td, D, 2, 2, dims, strides, box, DOLO_SW_128);
+            if (rc) return rc;
+        } else {
+            td = ta;  // unused
+        }
+    }
+    GemmParams p;
+    p.D = D;
+    p.C = C;
+    p.bias = static_cast<const __nv_bfloat16*>(bias);
+    p.ldd = ldd;
+    p.ldc = ldc;
+    p.M = int(M);
+    p.N = int(N);
+    p.K = int(K);
+    p.alpha = alpha;
+    p.beta = C ? beta : 0.f;
+    p.d_is_f32 = d_is_f32;
+    p.tma_store = tma_store ? 1 : 0;
+    p.num_m = int((M + BM - 1) / BM);
+    p.num_n = int((N + BN - 1) / BN);
+    p.num_kb = int((K + BK - 1) / BK);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!a_mn_major && !b_mn_major) return launch_gemm<false, false>(ta, tb, td, p, st);
+    if (!a_mn_major && b_mn_major) return launch_gemm<false, true>(ta, tb, td, p, st);
+    if (a_mn_major && !b_mn_major) return launch_gemm<true, false>(ta, tb, td, p, st);
+    return launch_gemm<true, true>(ta, tb, td, p, st);
+}

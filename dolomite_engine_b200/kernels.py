@@ -1,0 +1,255 @@
+"""Thin torch-tensor wrappers over the C ABI (include/dolomite_b200.h).
+
+torch is used only for device memory and streams; every computation below is a hand-written sm_100a kernel.
+All functions launch on torch's current CUDA stream and never synchronise.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise _lib.DolomiteB200Error(f"{name} must be a CUDA tensor (no CPU fallback on the hot path)")
+    if t.dtype != dtype:
+        raise _lib.DolomiteB200Error(f"{name} must be {dtype}, got {t.dtype}")
+
+
+# ------------------------------------------------------------------------------------------------
+# RMSNorm (normalization/rmsnorm/base.py:18-25)
+# ------------------------------------------------------------------------------------------------
+def rmsnorm_fwd(x: torch.Tensor, w: torch.Tensor, eps: float, out: torch.Tensor | None = None):
+    _req(x, _BF16, "x"), _req(w, _BF16, "w")
+    assert x.is_contiguous() and x.dim() == 2
+    T, H = x.shape
+    y = torch.empty_like(x) if out is None else out
+    rstd = torch.empty(T, dtype=torch.float32, device=x.device)
+    _lib.call("dolomite_b200_rmsnorm_fwd", x.data_ptr(), w.data_ptr(), y.data_ptr(), rstd.data_ptr(), T, H, eps, _stream())
+    return y, rstd
+
+
+_ws_cache: dict = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device, "ws")
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def rmsnorm_bwd(dy, x, w, rstd, dw_accum: torch.Tensor | None, dx_add: torch.Tensor | None = None, out=None):
+    _req(dy, _BF16, "dy"), _req(x, _BF16, "x")
+    T, H = x.shape
+    dx = torch.empty_like(x) if out is None else out
+    ws = _workspace(_lib.load().dolomite_b200_rmsnorm_bwd_workspace_bytes(H), x.device)
+    if dw_accum is not None:
+        _req(dw_accum, torch.float32, "dw_accum")
+    _lib.call(
+        "dolomite_b200_rmsnorm_bwd", dy.data_ptr(), x.data_ptr(), w.data_ptr(), rstd.data_ptr(), _ptr(dx_add),
+        dx.data_ptr(), _ptr(dw_accum), ws.data_ptr(), T, H, _stream(),
+    )
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# RoPE (position_embedding/rope.py:104-114) in place on packed qkv
+# ------------------------------------------------------------------------------------------------
+def rope_qk_inplace(qkv, n_groups: int, q_per_group: int, head_dim: int, cos, sin, position_ids, inverse=False):
+    _req(qkv, _BF16, "qkv"), _req(cos, _BF16, "cos"), _req(sin, _BF16, "sin")
+    assert qkv.dim() == 2 and qkv.stride(1) == 1
+    assert position_ids.dtype in (torch.int32, torch.int64) and position_ids.is_contiguous()
+    T = qkv.shape[0]
+    _lib.call(
+        "dolomite_b200_rope_qk_inplace", qkv.data_ptr(), qkv.stride(0), T, n_groups, q_per_group, head_dim,
+        cos.data_ptr(), sin.data_ptr(), position_ids.data_ptr(), int(position_ids.dtype == torch.int64),
+        cos.shape[0], int(inverse), _stream(),
+    )
+    return qkv
+
+
+# ------------------------------------------------------------------------------------------------
+# SwiGLU (activations/glu.py:26-28)
+# ------------------------------------------------------------------------------------------------
+def swiglu_fwd(x, out=None):
+    _req(x, _BF16, "x")
+    T, F2 = x.shape
+    y = torch.empty(T, F2 // 2, dtype=_BF16, device=x.device) if out is None else out
+    _lib.call("dolomite_b200_swiglu_fwd", x.data_ptr(), y.data_ptr(), T, F2 // 2, _stream())
+    return y
+
+
+def swiglu_bwd(dy, x, out=None):
+    _req(dy, _BF16, "dy"), _req(x, _BF16, "x")
+    T, F2 = x.shape
+    dx = torch.empty_like(x) if out is None else out
+    _lib.call("dolomite_b200_swiglu_bwd", dy.data_ptr(), x.data_ptr(), dx.data_ptr(), T, F2 // 2, _stream())
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# Embedding (gpt_dolomite/base.py:351-372)
+# ------------------------------------------------------------------------------------------------
+def embedding_fwd(ids, wte, scale: float = 1.0, out=None):
+    _req(ids, torch.int64, "ids"), _req(wte, _BF16, "wte")
+    T = ids.numel()
+    V, H = wte.shape
+    y = torch.empty(T, H, dtype=_BF16, device=wte.device) if out is None else out
+    _lib.call("dolomite_b200_embedding_fwd", ids.data_ptr(), wte.data_ptr(), y.data_ptr(), T, H, V, scale, _stream())
+    return y
+
+
+def embedding_bwd(ids, dout, dwte_accum, scale: float = 1.0):
+    _req(ids, torch.int64, "ids"), _req(dout, _BF16, "dout"), _req(dwte_accum, torch.float32, "dwte")
+    T = ids.numel()
+    V, H = dwte_accum.shape
+    _lib.call("dolomite_b200_embedding_bwd", ids.data_ptr(), dout.data_ptr(), dwte_accum.data_ptr(), T, H, V, scale, _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# Cross entropy fwd+bwd (model_wrapper/pretraining.py:124-125)
+# ------------------------------------------------------------------------------------------------
+def cross_entropy_fwd_bwd(logits, labels, ignore_index=-100, logit_scale=1.0, grad_scale=1.0, dlogits=None):
+    _req(logits, _BF16, "logits"), _req(labels, torch.int64, "labels")
+    T, V = logits.shape
+    assert logits.stride(1) == 1
+    dl = logits if dlogits is None else dlogits
+    loss_tok = torch.empty(T, dtype=torch.float32, device=logits.device)
+    loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+    scratch = torch.empty(2, dtype=torch.float32, device=logits.device)
+    _lib.call(
+        "dolomite_b200_cross_entropy_fwd_bwd", logits.data_ptr(), logits.stride(0), labels.data_ptr(), dl.data_ptr(),
+        loss_tok.data_ptr(), loss.data_ptr(), scratch.data_ptr(), T, V, ignore_index, logit_scale, grad_scale, _stream(),
+    )
+    return loss, loss_tok, dl
+
+
+def colsum_accum(x, out):
+    _req(x, _BF16, "x"), _req(out, torch.float32, "out")
+    T, N = x.shape
+    _lib.call("dolomite_b200_colsum_accum", x.data_ptr(), x.stride(0), out.data_ptr(), T, N, _stream())
+
+
+def add_scaled(a, b, alpha: float, out=None):
+    _req(a, _BF16, "a"), _req(b, _BF16, "b")
+    o = torch.empty_like(a) if out is None else out
+    _lib.call("dolomite_b200_add_scaled", a.data_ptr(), b.data_ptr(), o.data_ptr(), alpha, a.numel(), _stream())
+    return o
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer kernels (train_utils.py:99-106)
+# ------------------------------------------------------------------------------------------------
+def sumsq_accum(g, out):
+    _req(g, torch.float32, "g")
+    _lib.call("dolomite_b200_sumsq_accum", g.data_ptr(), g.numel(), out.data_ptr(), _stream())
+
+
+def clip_coef(sumsq, max_norm: float, coef_out, norm_out=None):
+    _lib.call("dolomite_b200_clip_coef", sumsq.data_ptr(), float(max_norm), coef_out.data_ptr(), _ptr(norm_out), _stream())
+
+
+def adamw_step(p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, clip=None):
+    _req(p, torch.float32, "p"), _req(g, torch.float32, "g")
+    _lib.call(
+        "dolomite_b200_adamw_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(p_bf16), p.numel(),
+        lr, beta1, beta2, eps, weight_decay, step, _ptr(clip), _stream(),
+    )
+
+
+def cast_f32_to_bf16(src, dst):
+    _lib.call("dolomite_b200_cast_f32_to_bf16", src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
+
+
+def accum_bf16_into_f32(src, dst, scale=1.0):
+    _lib.call("dolomite_b200_accum_bf16_into_f32", src.data_ptr(), dst.data_ptr(), scale, src.numel(), _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM (nn.Linear fwd / dgrad / wgrad; linear.py:5-25)
+# ------------------------------------------------------------------------------------------------
+GEMM_TMA_STORE = 1
+_default_gemm_flags = 0
+
+
+def set_default_gemm_flags(flags: int) -> None:
+    global _default_gemm_flags
+    _default_gemm_flags = flags
+
+
+def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=_BF16, c=None, alpha=1.0, beta=0.0, bias=None, flags=None):
+    """D[M,N] = alpha * A·Bᵀ + bias + beta*C.  A logical [M,K] (stored [K,M] if a_mn), B logical [N,K] (stored [K,N] if b_mn)."""
+    _req(a, _BF16, "a"), _req(b, _BF16, "b")
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    if a_mn:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if b_mn:
+        Kb, N = b.shape
+    else:
+        N, Kb = b.shape
+    if K != Kb:
+        raise _lib.DolomiteB200Error(f"gemm: contraction mismatch {K} vs {Kb}")
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+    d_is_f32 = int(out.dtype == torch.float32)
+    assert out.stride(1) == 1 and out.shape == (M, N)
+    if c is not None:
+        assert c.dtype == out.dtype and c.stride(1) == 1
+    if flags is None:
+        flags = _default_gemm_flags
+        if d_is_f32 or c is not None:
+            flags &= ~GEMM_TMA_STORE
+    _lib.call(
+        "dolomite_b200_gemm_bf16", a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn),
+        out.data_ptr(), out.stride(0), d_is_f32, _ptr(c), 0 if c is None else c.stride(0), alpha, beta, _ptr(bias),
+        M, N, K, flags, _stream(),
+    )
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# packed var-len causal attention (attention/padding_free.py:51-62)
+# ------------------------------------------------------------------------------------------------
+def attn_varlen_fwd(qkv, cu_seqlens, max_seqlen: int, n_groups: int, q_per_group: int, head_dim: int, scale: float, out=None):
+    _req(qkv, _BF16, "qkv"), _req(cu_seqlens, torch.int32, "cu_seqlens")
+    T = qkv.shape[0]
+    nh = n_groups * q_per_group
+    o = torch.empty(T, nh * head_dim, dtype=_BF16, device=qkv.device) if out is None else out
+    lse = torch.empty(nh, T, dtype=torch.float32, device=qkv.device)
+    _lib.call(
+        "dolomite_b200_attn_varlen_fwd", qkv.data_ptr(), qkv.stride(0), o.data_ptr(), lse.data_ptr(),
+        cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, T, int(max_seqlen), n_groups, q_per_group, head_dim, scale, _stream(),
+    )
+    return o, lse
+
+
+def attn_varlen_bwd(dout, qkv, out, lse, cu_seqlens, max_seqlen, n_groups, q_per_group, head_dim, scale, dqkv=None):
+    _req(dout, _BF16, "dout"), _req(qkv, _BF16, "qkv")
+    T = qkv.shape[0]
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    ws_bytes = _lib.load().dolomite_b200_attn_varlen_bwd_workspace_bytes(T, n_groups, q_per_group, head_dim)
+    ws = _workspace(ws_bytes, qkv.device)
+    _lib.call(
+        "dolomite_b200_attn_varlen_bwd", dout.data_ptr(), qkv.data_ptr(), qkv.stride(0), out.data_ptr(), lse.data_ptr(),
+        dqkv.data_ptr(), cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, T, int(max_seqlen), n_groups, q_per_group,
+        head_dim, scale, ws.data_ptr(), _stream(),
+    )
+    return dqkv

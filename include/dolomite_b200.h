@@ -1,0 +1,153 @@
+/*
+ * dolomite_b200.h -- C ABI of the B200-native (sm_100a) hot path of dolomite-engine.
+ *
+ * Scope: the data-parallel GPTDolomite / MoEDolomite training step.  The reference
+ * (ibm-granite/dolomite-engine @ 2024_08_07) is pure Python and reaches its GPU kernels through
+ * torch / flash-attn / scattermoe; it has no FFI of its own.  Every entry point below therefore cites
+ * the reference *call site* (file:line under dolomite_engine/) whose arithmetic it replaces.  The Python
+ * host side (dolomite_engine_b200/) binds these with ctypes; INTEGRATION.md shows the stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 (DOLO_OK) or a negative error code; dolomite_b200_last_error() returns a
+ *     thread-local human readable message for the last failure on the calling thread.
+ *   - all pointers are DEVICE pointers unless the name ends in _host.  The callee never allocates, frees
+ *     or retains device memory and never synchronises the stream.
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - activations/weights are bf16 (uint16 storage), statistics / master weights / gradients-of-weights fp32.
+ *   - row-major everywhere; `ld*` are leading dimensions in ELEMENTS.
+ */
+#ifndef DOLOMITE_B200_H
+#define DOLOMITE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DOLOMITE_B200_ABI_VERSION 1
+
+#define DOLO_OK 0
+#define DOLO_ERR_INVALID (-1) /* bad argument / unsupported shape */
+#define DOLO_ERR_CUDA (-2)    /* CUDA runtime / driver error     */
+
+const char* dolomite_b200_last_error(void);
+int dolomite_b200_abi_version(void);
+int dolomite_b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * RMSNorm  -- hf_models/modeling_utils/normalization/rmsnorm/base.py:18-25
+ *   y = w * bf16( x32 * rsqrt(mean(x32^2) + eps) ), rstd saved for backward.
+ *   bwd: dx (+ optional dx_add, the residual-stream gradient), dw accumulated (+=) into fp32.
+ *   workspace for bwd: dolomite_b200_rmsnorm_bwd_workspace_bytes(H) bytes.
+ * ------------------------------------------------------------------------------------------------ */
+int dolomite_b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t T, int H, float eps,
+                              void* stream);
+int64_t dolomite_b200_rmsnorm_bwd_workspace_bytes(int H);
+int dolomite_b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dx_add,
+                              void* dx, float* dw_accum, void* workspace, int64_t T, int H, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * RoPE on the packed qkv buffer, in place -- hf_models/modeling_utils/position_embedding/rope.py:104-114,
+ *   call sites attention/padding_free.py:38-40; cos/sin gather gpt_dolomite/base.py:289-296.
+ *   qkv rows are `n_groups` groups of (q_per_group + 2) head slots of head_dim (layouts of
+ *   attention/padding_free.py:79-116: mha = nh groups x [q,k,v]; gqa = nkv groups x [q*g,k,v]; mqa = 1 group).
+ *   The first q_per_group+1 slots of each group (queries and the key) are rotated.
+ *   cos/sin: bf16 tables [n_positions, head_dim]; position_ids int32 or int64 [T].
+ *   inverse != 0 applies the transpose rotation (backward).
+ * ------------------------------------------------------------------------------------------------ */
+int dolomite_b200_rope_qk_inplace(void* qkv, int64_t row_stride, int64_t T, int n_groups, int q_per_group,
+                                  int head_dim, const void* cos_table, const void* sin_table, const void* position_ids,
+                                  int position_ids_is_int64, int64_t n_positions, int inverse, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SwiGLU -- hf_models/modeling_utils/activations/glu.py:26-28 with gpt_dolomite/mlp.py:54-55 ordering:
+ *   x = [up | gate] (first F columns up, last F gate);  y = up * silu(gate).
+ * ------------------------------------------------------------------------------------------------ */
+int dolomite_b200_swiglu_fwd(const void* x, void* y, int64_t T, int64_t F, void* stream);
+int dolomite_b200_swiglu_bwd(const void* dy, const void* x, void* dx, int64_t T, int64_t F, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Embedding -- gpt_dolomite/base.py:351-372 (wte gather, * m_emb); bwd accumulates (+=) into fp32 dwte.
+ *   ids int64 [T].  Out-of-range ids are an error on the host side (checked by the caller), the kernel clamps.
+ * ------------------------------------------------------------------------------------------------ */
+int dolomite_b200_embedding_fwd(const int64_t* ids, const void* wte, void* out, int64_t T, int H, int64_t V,
+                                float scale, void* stream);
+int dolomite_b200_embedding_bwd(const int64_t* ids, const void* dout, float* dwte, int64_t T, int H, int64_t V,
+                                float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cross entropy (mean over non-ignored tokens), fused forward + backward --
+ *   model_wrapper/pretraining.py:124-125 (F.cross_entropy on [T,V]) and gpt_dolomite/main.py:185-200.
+ *   logits bf16 [T, ldl]; labels int64 [T]; label == ignore_index contributes nothing.
+ *   Writes per-token loss (fp32, 0 for ignored), the scalar mean loss, and overwrites dlogits (may alias
+ *   logits) with (softmax - onehot) * grad_scale / n_valid in bf16.
+ *   scratch: 2 floats.  logit_scale multiplies logits before the softmax (1/m_width, gpt_dolomite/main.py:155-156).
+ * ------------------------------------------------------------------------------------------------ */
+int dolomite_b200_cross_entropy_fwd_bwd(const void* logits, int64_t ldl, const int64_t* labels, void* dlogits,
+                                        float* loss_per_token, float* loss_mean, float* scratch, int64_t T, int64_t V,
+                                        int64_t ignore_index, float logit_scale, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Column sum (bias gradient of nn.Linear, autograd of linear.py:5-25):  out[n] += sum_t x[t, n]
+ * ------------------------------------------------------------------------------------------------ */
+int dolomite_b200_colsum_accum(const void* x, int64_t ldx, float* out, int64_t T, int64_t N, void* stream);
+
+/* out = a + alpha * b  (bf16; residual adds of gpt_dolomite/layer.py:70-85), a/b/out may alias */
+int dolomite_b200_add_scaled(const void* a, const void* b, void* out, float alpha, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer-side flat-shard kernels (train_utils.py:99-106: clip_grad_norm_ + AdamW step).
+ *   sumsq: out[0] += sum(g^2)  (fp32 grads).   clip coef: coef = min(1, max_norm / (sqrt(sumsq) + 1e-6)).
+ *   adamw: torch.optim.AdamW semantics on fp32 master shard; also emits the bf16 copy that the next
+ *   all-gather ships.  `clip_coef` is a device pointer (nullable -> 1).  step >= 1.
+ * ------------------------------------------------------------------------------------------------ */
+int dolomite_b200_sumsq_accum(const float* g, int64_t n, float* out, void* stream);
+int dolomite_b200_clip_coef(const float* sumsq, float max_norm, float* coef_out, float* norm_out, void* stream);
+int dolomite_b200_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                             const float* clip_coef, void* stream);
+/* fp32 -> bf16 cast of a flat shard; bf16 grads -> fp32 accumulate */
+int dolomite_b200_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+int dolomite_b200_accum_bf16_into_f32(const void* src, float* dst, float scale, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * bf16 GEMM on tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM -> epilogue), replacing the cuBLAS
+ * calls behind nn.Linear (linear.py:5-25; call sites attention/base.py:100, padding_free.py:74,
+ * gpt_dolomite/mlp.py:46-48, gpt_dolomite/main.py:172-177) and their autograd (dgrad / wgrad).
+ *
+ *   D[M,N] = alpha * sum_k A[m,k] * B[n,k]  + bias[n] + beta * C[m,n]
+ *
+ *   A is logical [M,K]: a_mn_major == 0 -> stored row-major [M,K] (ld = lda);  1 -> stored [K,M] (ld = lda).
+ *   B is logical [N,K]: b_mn_major == 0 -> stored row-major [N,K] (ld = ldb);  1 -> stored [K,N] (ld = ldb).
+ *   D/C: row-major [M,N]; d_is_f32 selects fp32 (else bf16) for BOTH D and C.  C may be NULL (beta ignored)
+ *   or alias D.  bias: bf16 [N] or NULL.   K % 8 == 0, lds % 8 == 0, 16-byte aligned bases.
+ *   flags: bit0 = epilogue via smem staging + TMA store (bf16 D, no C), else direct vector stores.
+ * ------------------------------------------------------------------------------------------------ */
+#define DOLO_GEMM_FLAG_TMA_STORE 1
+int dolomite_b200_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
+                            void* D, int64_t ldd, int d_is_f32, const void* C, int64_t ldc, float alpha, float beta,
+                            const void* bias, int64_t M, int64_t N, int64_t K, int flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Packed var-len causal attention (replaces flash_attn_varlen_func at attention/padding_free.py:51-62).
+ *   qkv: packed projection output [T, row_stride] in the slot layout described at rope_qk_inplace.
+ *   out: [T, n_heads*head_dim] bf16; lse: fp32 [n_heads, T] (natural log-sum-exp of scale*s).
+ *   cu_seqlens int32 [B+1] (same for q and k), causal within each document.
+ *   bwd: dqkv has the same layout as qkv (dq, dk, dv written into their slots; bf16).
+ *   workspace sizes via the *_workspace_bytes helpers.
+ * ------------------------------------------------------------------------------------------------ */
+int dolomite_b200_attn_varlen_fwd(const void* qkv, int64_t row_stride, void* out, float* lse,
+                                  const int32_t* cu_seqlens, int n_docs, int64_t T, int max_seqlen, int n_groups,
+                                  int q_per_group, int head_dim, float softmax_scale, void* stream);
+int64_t dolomite_b200_attn_varlen_bwd_workspace_bytes(int64_t T, int n_groups, int q_per_group, int head_dim);
+int dolomite_b200_attn_varlen_bwd(const void* dout, const void* qkv, int64_t row_stride, const void* out,
+                                  const float* lse, void* dqkv, const int32_t* cu_seqlens, int n_docs, int64_t T,
+                                  int max_seqlen, int n_groups, int q_per_group, int head_dim, float softmax_scale,
+                                  void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOLOMITE_B200_H */

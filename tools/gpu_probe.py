@@ -1,0 +1,412 @@
+"""GPU bring-up probe: runs each kernel check in its own subprocess (a trap/hang in one cannot take the
+rest down) and writes one JSON line per case to gpurun_out/probe.jsonl.
+
+    python tools/gpu_probe.py                 # all cases
+    python tools/gpu_probe.py --only gemm     # cases whose name contains 'gemm'
+    python tools/gpu_probe.py --case NAME     # run one case in-process (used by the driver mode)
+
+References are computed with torch on the GPU (test infrastructure only).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CASES = {}
+
+
+def case(fn):
+    CASES[fn.__name__] = fn
+    return fn
+
+
+def _t():
+    import torch
+
+    return torch
+
+
+def _err(a, b):
+    a = a.float()
+    b = b.float()
+    d = (a - b).abs()
+    return {
+        "max_abs": d.max().item(),
+        "rel_l2": (d.norm() / (b.norm() + 1e-30)).item(),
+        "ref_absmax": b.abs().max().item(),
+    }
+
+
+def _time(fn, iters=20, warmup=3):
+    torch = _t()
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+# ---------------------------------------------------------------------------------------------
+def _gemm_case(M, N, K, a_mn, b_mn, flags=0, out_f32=False, with_c=False, bias=False, alpha=1.0, beta=1.0, bench=False):
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.5).bfloat16()
+    a_in = A.t().contiguous() if a_mn else A
+    b_in = B.t().contiguous() if b_mn else B
+    dt = torch.float32 if out_f32 else torch.bfloat16
+    C = (torch.randn(M, N, device="cuda", generator=g)).to(dt) if with_c else None
+    bv = (torch.randn(N, device="cuda", generator=g)).bfloat16() if bias else None
+    ref = alpha * (A.float() @ B.float().t())
+    if bias:
+        ref = ref + bv.float()
+    if with_c:
+        ref = ref + beta * C.float()
+    out = k.gemm(a_in, b_in, a_mn=a_mn, b_mn=b_mn, out_dtype=dt, c=C, alpha=alpha, beta=beta, bias=bv, flags=flags)
+    torch.cuda.synchronize()
+    res = _err(out, ref)
+    res["shape"] = [M, N, K]
+    if bench:
+        ms = _time(lambda: k.gemm(a_in, b_in, a_mn=a_mn, b_mn=b_mn, out=out, c=C, alpha=alpha, beta=beta, bias=bv, flags=flags))
+        res["ms"] = ms
+        res["tflops"] = 2.0 * M * N * K / ms / 1e9
+        ms_ref = _time(lambda: torch.matmul(A, B.t()))
+        res["cublas_ms"] = ms_ref
+        res["cublas_tflops"] = 2.0 * M * N * K / ms_ref / 1e9
+    tol = 2e-2 if not out_f32 else 1e-3
+    res["ok"] = bool(res["rel_l2"] < tol)
+    return res
+
+
+@case
+def gemm_nt_small():
+    return _gemm_case(128, 256, 64, False, False)
+
+
+@case
+def gemm_nt_k256():
+    return _gemm_case(128, 256, 256, False, False)
+
+
+@case
+def gemm_nt_multi_tile():
+    return _gemm_case(512, 1024, 512, False, False)
+
+
+@case
+def gemm_nt_ragged():
+    return _gemm_case(300, 520, 328, False, False)
+
+
+@case
+def gemm_nt_tma_store():
+    return _gemm_case(512, 1024, 512, False, False, flags=1)
+
+
+@case
+def gemm_nt_tma_store_ragged():
+    return _gemm_case(300, 520, 328, False, False, flags=1, bias=True)
+
+
+@case
+def gemm_nt_bias_c():
+    return _gemm_case(384, 512, 256, False, False, with_c=True, bias=True, alpha=0.5, beta=1.0)
+
+
+@case
+def gemm_nn_bmn():
+    return _gemm_case(512, 768, 512, False, True)
+
+
+@case
+def gemm_tn_amn():
+    return _gemm_case(512, 768, 512, True, False)
+
+
+@case
+def gemm_tt_wgrad_f32_accum():
+    return _gemm_case(640, 512, 1024, True, True, out_f32=True, with_c=True, beta=1.0)
+
+
+@case
+def gemm_many_tiles_persistent():
+    # > 148 tiles so every CTA loops; exercises accumulator double buffering and phase flips
+    return _gemm_case(4096, 4096, 1024, False, False)
+
+
+@case
+def gemm_bench_fwd_qkv():
+    return _gemm_case(8192, 7680, 2560, False, False, bench=True)
+
+
+@case
+def gemm_bench_fwd_qkv_tma_store():
+    return _gemm_case(8192, 7680, 2560, False, False, flags=1, bench=True)
+
+
+@case
+def gemm_bench_fc():
+    return _gemm_case(8192, 20480, 2560, False, False, flags=1, bench=True)
+
+
+@case
+def gemm_bench_proj():
+    return _gemm_case(8192, 2560, 10240, False, False, flags=1, bench=True)
+
+
+@case
+def gemm_bench_dgrad():
+    return _gemm_case(8192, 2560, 7680, False, True, flags=1, bench=True)
+
+
+@case
+def gemm_bench_wgrad():
+    return _gemm_case(20480, 2560, 8192, True, True, out_f32=True, with_c=True, bench=True)
+
+
+# ---------------------------------------------------------------------------------------------
+@case
+def rmsnorm():
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+
+    out = {}
+    ok = True
+    for T, H in [(256, 256), (1000, 2560), (64, 4096), (33, 8192)]:
+        g = torch.Generator(device="cuda").manual_seed(2)
+        x = torch.randn(T, H, device="cuda", generator=g).bfloat16()
+        w = (1 + 0.1 * torch.randn(H, device="cuda", generator=g)).bfloat16()
+        dy = torch.randn(T, H, device="cuda", generator=g).bfloat16()
+        dres = torch.randn(T, H, device="cuda", generator=g).bfloat16()
+        eps = 1e-5
+        y, rstd = k.rmsnorm_fwd(x, w, eps)
+        xf = x.float().requires_grad_(True)
+        wf = w.float().requires_grad_(True)
+        var = xf.pow(2).mean(-1, keepdim=True)
+        xn = xf * torch.rsqrt(var + eps)
+        yref = (w * xn.detach().to(torch.bfloat16)).float()
+        e1 = _err(y, yref)
+        yr2 = wf * xn
+        yr2.backward(dy.float())
+        dw = torch.zeros(H, device="cuda", dtype=torch.float32)
+        dx = k.rmsnorm_bwd(dy, x, w, rstd, dw, dx_add=dres)
+        e2 = _err(dx, xf.grad + dres.float())
+        e3 = _err(dw, wf.grad)
+        out[f"{T}x{H}"] = {"fwd": e1, "dx": e2, "dw": e3}
+        ok = ok and e1["rel_l2"] < 5e-3 and e2["rel_l2"] < 1e-2 and e3["rel_l2"] < 1e-2
+    # bandwidth
+    T, H = 16384, 2560
+    x = torch.randn(T, H, device="cuda").bfloat16()
+    w = torch.ones(H, device="cuda").bfloat16()
+    y = torch.empty_like(x)
+    ms = _time(lambda: k.rmsnorm_fwd(x, w, 1e-5, out=y))
+    out["fwd_GBps"] = 4.0 * T * H / ms / 1e6
+    out["ok"] = bool(ok)
+    return out
+
+
+@case
+def rope():
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+
+    out = {}
+    ok = True
+    for (T, ng, g, hd) in [(128, 4, 1, 64), (200, 32, 1, 80), (77, 8, 4, 128), (50, 1, 4, 32)]:
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        width = ng * (g + 2) * hd
+        qkv = torch.randn(T, width, device="cuda", generator=gen).bfloat16()
+        npos = 512
+        inv_freq = 1.0 / (10000 ** (torch.arange(0, hd, 2, dtype=torch.float32, device="cuda") / hd))
+        t = torch.arange(npos, dtype=torch.float32, device="cuda")
+        freqs = torch.outer(t, inv_freq)
+        emb = torch.cat((freqs, freqs), dim=-1)
+        cos = emb.cos().to(torch.bfloat16)
+        sin = emb.sin().to(torch.bfloat16)
+        pos = torch.randint(0, npos, (T,), device="cuda", generator=gen)
+        v = qkv.view(T, ng, g + 2, hd).clone()
+        c = cos[pos].unsqueeze(1).unsqueeze(1)
+        s = sin[pos].unsqueeze(1).unsqueeze(1)
+        rot = v[:, :, : g + 1]
+        x1, x2 = torch.chunk(rot, 2, dim=-1)
+        ref_rot = (rot * c) + (torch.cat((-x2, x1), dim=-1) * s)
+        ref = v.clone()
+        ref[:, :, : g + 1] = ref_rot
+        got = k.rope_qk_inplace(qkv.clone(), ng, g, hd, cos, sin, pos)
+        e = _err(got.view(T, ng, g + 2, hd), ref)
+        # inverse(forward(x)) ~= x on rotated slots (orthogonality, up to bf16 rounding)
+        back = k.rope_qk_inplace(got.clone(), ng, g, hd, cos, sin, pos.int(), inverse=True)
+        e2 = _err(back, qkv)
+        out[f"{T}_{ng}_{g}_{hd}"] = {"fwd": e, "roundtrip": e2}
+        ok = ok and e["max_abs"] <= 4e-2 and e["rel_l2"] < 3e-3 and e2["rel_l2"] < 2e-2
+    out["ok"] = bool(ok)
+    return out
+
+
+@case
+def swiglu():
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+
+    T, F = 300, 1024
+    x = torch.randn(T, 2 * F, device="cuda").bfloat16()
+    dy = torch.randn(T, F, device="cuda").bfloat16()
+    y = k.swiglu_fwd(x)
+    xf = x.float().requires_grad_(True)
+    u, g = xf.chunk(2, dim=-1)
+    yr = u * torch.nn.functional.silu(g)
+    yr.backward(dy.float())
+    dx = k.swiglu_bwd(dy, x)
+    e1, e2 = _err(y, yr), _err(dx, xf.grad)
+    T, F = 8192, 10240
+    xb = torch.randn(T, 2 * F, device="cuda").bfloat16()
+    yb = torch.empty(T, F, device="cuda", dtype=torch.bfloat16)
+    ms = _time(lambda: k.swiglu_fwd(xb, out=yb))
+    return {"fwd": e1, "bwd": e2, "fwd_GBps": 6.0 * T * F / ms / 1e6, "ok": bool(e1["rel_l2"] < 5e-3 and e2["rel_l2"] < 5e-3)}
+
+
+@case
+def embedding_ce():
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+
+    V, H, T = 2048, 256, 500
+    wte = torch.randn(V, H, device="cuda").bfloat16()
+    ids = torch.randint(0, V, (T,), device="cuda")
+    y = k.embedding_fwd(ids, wte, 1.0)
+    e1 = _err(y, wte[ids])
+    y2 = k.embedding_fwd(ids, wte, 12.0)
+    e1b = _err(y2, (wte[ids].float() * 12.0))
+    dout = torch.randn(T, H, device="cuda").bfloat16()
+    dw = torch.zeros(V, H, device="cuda")
+    k.embedding_bwd(ids, dout, dw, 1.0)
+    ref = torch.zeros(V, H, device="cuda").index_add_(0, ids, dout.float())
+    e2 = _err(dw, ref)
+    # cross entropy
+    res = {"emb_fwd": e1, "emb_fwd_scaled": e1b, "emb_bwd": e2}
+    ok = e1["max_abs"] == 0 and e1b["rel_l2"] < 4e-3 and e2["rel_l2"] < 1e-5
+    for (T, V) in [(300, 2048), (64, 49152), (17, 128256)]:
+        logits = (torch.randn(T, V, device="cuda") * 2).bfloat16()
+        labels = torch.randint(0, V, (T,), device="cuda")
+        labels[::7] = -100
+        lf = logits.float().requires_grad_(True)
+        lr = torch.nn.functional.cross_entropy(lf, labels, ignore_index=-100)
+        lr.backward()
+        loss, loss_tok, dl = k.cross_entropy_fwd_bwd(logits.clone(), labels)
+        torch.cuda.synchronize()
+        el = abs(loss.item() - lr.item()) / abs(lr.item())
+        eg = _err(dl, lf.grad)
+        res[f"ce_{T}x{V}"] = {"loss_rel": el, "grad": eg}
+        ok = ok and el < 1e-5 and eg["rel_l2"] < 5e-3
+    T, V = 8192, 49152
+    logits = torch.randn(T, V, device="cuda").bfloat16()
+    labels = torch.randint(0, V, (T,), device="cuda")
+    ms = _time(lambda: k.cross_entropy_fwd_bwd(logits, labels), iters=5)
+    res["ce_GBps_alg_4TV"] = 4.0 * T * V / ms / 1e6
+    res["ok"] = bool(ok)
+    return res
+
+
+@case
+def optimizer():
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+
+    n = 1_000_003
+    p = torch.randn(n, device="cuda")
+    g = torch.randn(n, device="cuda") * 0.1
+    p_ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([p_ref], lr=1e-3, betas=(0.9, 0.95), eps=1e-10, weight_decay=0.1)
+    m = torch.zeros(n, device="cuda")
+    v = torch.zeros(n, device="cuda")
+    pb = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    ss = torch.zeros(1, device="cuda")
+    coef = torch.empty(1, device="cuda")
+    norm = torch.empty(1, device="cuda")
+    k.sumsq_accum(g, ss)
+    k.clip_coef(ss, 1.0, coef, norm)
+    ref_norm = g.norm().item()
+    for step in (1, 2, 3):
+        p_ref.grad = g * min(1.0, 1.0 / (ref_norm + 1e-6))
+        opt.step()
+        k.adamw_step(p, g, m, v, pb, 1e-3, 0.9, 0.95, 1e-10, 0.1, step, clip=coef)
+    e = _err(p, p_ref.data)
+    eb = _err(pb, p_ref.data.bfloat16())
+    # colsum + add_scaled
+    x = torch.randn(777, 1024, device="cuda").bfloat16()
+    out = torch.zeros(1024, device="cuda")
+    k.colsum_accum(x, out)
+    ec = _err(out, x.float().sum(0))
+    a = torch.randn(4096, device="cuda").bfloat16()
+    b = torch.randn(4096, device="cuda").bfloat16()
+    ea = _err(k.add_scaled(a, b, 0.22), a + (b * 0.22))
+    ok = e["rel_l2"] < 1e-5 and abs(norm.item() - ref_norm) / ref_norm < 1e-4 and ec["rel_l2"] < 1e-4 and ea["max_abs"] < 1e-9 + 0.04
+    return {"adamw": e, "adamw_bf16": eb, "norm": [norm.item(), ref_norm], "colsum": ec, "add_scaled": ea, "ok": bool(ok)}
+
+
+@case
+def env_info():
+    torch = _t()
+    import subprocess as sp
+
+    smi = sp.run(["nvidia-smi", "--query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total", "--format=csv"], capture_output=True, text=True).stdout
+    return {"torch": torch.__version__, "device": torch.cuda.get_device_name(0), "cpu_count": os.cpu_count(), "smi": smi, "ok": True}
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case")
+    ap.add_argument("--only", default="")
+    ap.add_argument("--timeout", type=int, default=120)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "probe.jsonl"))
+    a = ap.parse_args()
+    if a.case:
+        t0 = time.time()
+        try:
+            res = CASES[a.case]()
+        except Exception as e:  # noqa
+            import traceback
+
+            res = {"ok": False, "error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-1500:]}
+        res["case"] = a.case
+        res["wall_s"] = round(time.time() - t0, 2)
+        print("PROBE_RESULT " + json.dumps(res))
+        return
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    names = [n for n in CASES if a.only in n]
+    with open(a.out, "a") as f:
+        for n in names:
+            try:
+                proc = subprocess.run([sys.executable, __file__, "--case", n], capture_output=True, text=True, timeout=a.timeout)
+                line = [l for l in proc.stdout.splitlines() if l.startswith("PROBE_RESULT ")]
+                if line:
+                    res = json.loads(line[-1][len("PROBE_RESULT "):])
+                else:
+                    res = {"case": n, "ok": False, "error": "no result", "rc": proc.returncode, "stdout": proc.stdout[-1500:], "stderr": proc.stderr[-1500:]}
+            except subprocess.TimeoutExpired as e:
+                res = {"case": n, "ok": False, "error": "timeout", "stdout": (e.stdout or b"")[-1000:].decode(errors="replace") if isinstance(e.stdout, bytes) else str(e.stdout)[-1000:]}
+            f.write(json.dumps(res) + "\n")
+            f.flush()
+            brief = {k: v for k, v in res.items() if k in ("case", "ok", "error", "rel_l2", "max_abs", "tflops", "cublas_tflops", "ms")}
+            print(json.dumps(brief), flush=True)
+
+
+if __name__ == "__main__":
+    main()
