@@ -1,0 +1,327 @@
+// Packed var-len causal attention forward on tcgen05 (replaces flash_attn_varlen_func at
+// attention/padding_free.py:51-62).
+//
+// One CTA = one 128-row query tile of one head of one document.  Warp roles:
+//   warp 0   TMA producer: Q tile once, then (K_j, V_j) tiles through a 2-stage ring
+//   warp 1   MMA issuer:   S = Q K_j^T  (SS, fp32 in TMEM)  and  O += P_j V_j  (A = P from TMEM, B = V MN-major)
+//   warps 2-5 softmax:     one query row per thread (TMEM lane == row): online max / exp2 / sum, P -> TMEM as bf16
+//                          (aliasing the S columns), O rescale in TMEM, final O / l and LSE store.
+// TMEM: S/P 128 columns + O head_dim columns  (<= 256 -> two CTAs per SM overlap each other's softmax and MMA).
+#include "attention_common.cuh"
+#include "../../include/dolomite_b200.h"
+
+using namespace dolo;
+
+namespace {
+
+constexpr int FWD_THREADS = 192;
+constexpr int KV_STAGES = 2;
+
+struct FwdParams {
+    __nv_bfloat16* out;
+    float* lse;
+    const int32_t* cu_seqlens;
+    int n_docs;
+    int64_t T;
+    int n_groups, q_per_group;
+    int n_heads;
+    float scale_log2;  // softmax_scale * log2(e)
+    float scale;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(FWD_THREADS)
+    attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap64, const __grid_constant__ CUtensorMap tmapR,
+                    const FwdParams p) {
+    using CH = HeadChunks<HD>;
+    constexpr int TILE_BYTES = CH::TILE_BYTES;
+    constexpr int TMEM_COLS = (128 + HD) <= 256 ? 256 : 512;
+    constexpr uint32_t O_COL = 128;
+
+    const int ti = int(gridDim.x) - 1 - int(blockIdx.x);  // long (late) tiles first
+    const TileLoc loc = locate_tile(p.cu_seqlens, p.n_docs, ti);
+    if (!loc.valid) return;  // uniform for the whole CTA
+    const int head = blockIdx.y;
+    const int group = head / p.q_per_group, slot = head % p.q_per_group;
+    const int q_col = (group * (p.q_per_group + 2) + slot) * HD;
+    const int k_col = (group * (p.q_per_group + 2) + p.q_per_group) * HD;
+    const int v_col = k_col + HD;
+    const int q0 = loc.tile * ATT_TILE;                       // first query (doc-relative) of this tile
+    const int n_kv = loc.tile + 1;                            // causal: key tiles 0 .. tile
+    const int row_base = loc.doc_start + q0;                  // global token row of query 0
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + TILE_BYTES;                 // [KV_STAGES]
+    uint8_t* sV = sK + KV_STAGES * TILE_BYTES;     // [KV_STAGES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * TILE_BYTES);
+    uint64_t* q_full = bars;            // 1
+    uint64_t* kv_full = bars + 1;       // [KV_STAGES]
+    uint64_t* kv_empty = bars + 3;      // [KV_STAGES]
+    uint64_t* s_full = bars + 5;        // 1
+    uint64_t* p_ready = bars + 6;       // 1 (128 arrivals)
+    uint64_t* o_full = bars + 7;        // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        if (CH::NC64 > 0) tma_prefetch_desc(&tmap64);
+        if (CH::REM > 0) tma_prefetch_desc(&tmapR);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < KV_STAGES; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(p_ready, 128);
+        mbar_init(o_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto load_tile = [&](uint8_t* dst, uint64_t* bar, int col, int row) {
+#pragma unroll
+        for (int c = 0; c < CH::NCHUNK; ++c) {
+            const CUtensorMap* m = (c < CH::NC64) ? &tmap64 : &tmapR;
+            tma_load_2d(dst + CH::offset(c), m, bar, col + CH::col(c), row);
+        }
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, TILE_BYTES);
+            load_tile(sQ, q_full, q_col, row_base);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int j = 0; j < n_kv; ++j) {
+                mbar_wait(&kv_empty[stage], phase ^ 1, 10);
+                mbar_expect_tx(&kv_full[stage], 2 * TILE_BYTES);
+                const int krow = loc.doc_start + j * ATT_TILE;
+                load_tile(sK + stage * TILE_BYTES, &kv_full[stage], k_col, krow);
+                load_tile(sV + stage * TILE_BYTES, &kv_full[stage], v_col, krow);
+                if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, false, false);
+            mbar_wait(q_full, 0, 11);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int j = 0; j < n_kv; ++j) {
+                mbar_wait(&kv_full[stage], phase, 12);
+                tc_fence_after();
+                const uint32_t q_s = smem_u32(sQ);
+                const uint32_t k_s = smem_u32(sK + stage * TILE_BYTES);
+                const uint32_t v_s = smem_u32(sV + stage * TILE_BYTES);
+                // S = Q K^T  (contraction over head_dim, chunk by chunk)
+                bool first = true;
+#pragma unroll
+                for (int c = 0; c < CH::NCHUNK; ++c) {
+                    const int w = CH::width(c);
+#pragma unroll
+                    for (int k = 0; k < w / 16; ++k) {
+                        umma_ss(tmem_base, chunk_desc_kmajor(q_s + CH::offset(c), w, k),
+                                chunk_desc_kmajor(k_s + CH::offset(c), w, k), idesc_qk, first ? 0u : 1u);
+                        first = false;
+                    }
+                }
+                umma_commit(s_full);
+                // wait for P_j (bf16, TMEM columns [0,64)) and the rescaled O
+                mbar_wait(p_ready, uint32_t(j & 1), 13);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < CH::NCHUNK; ++c) {
+                    const int w = CH::width(c);
+                    const uint32_t idesc_pv = umma_idesc_bf16(128, w, false, true);
+#pragma unroll
+                    for (int k = 0; k < ATT_TILE / 16; ++k) {
+                        umma_ts(tmem_base + O_COL + CH::col(c), tmem_base + k * 8,
+                                chunk_desc_mnmajor(v_s + CH::offset(c), w, k), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&kv_empty[stage]);
+                if (j == n_kv - 1) umma_commit(o_full);
+                if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ---------------- softmax / correction / epilogue: one query row per thread ----------------
+        const int sub = warp & 3;
+        const int r = sub * 32 + lane;                 // row in tile == TMEM lane
+        const uint32_t t_lane = tmem_base + (uint32_t(sub * 32) << 16);
+        const int qi = q0 + r;                         // doc-relative query index
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < n_kv; ++j) {
+            mbar_wait(s_full, uint32_t(j & 1), 14);
+            tc_fence_after();
+            const bool diag = (j == n_kv - 1);
+            const int kbase = j * ATT_TILE;
+            // pass 1: row max
+            float mx = m_run;
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(t_lane + ch * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float s = __uint_as_float(v[i]);
+                    if (diag && (kbase + ch * 32 + i > qi)) s = -INFINITY;
+                    mx = fmaxf(mx, s);
+                }
+            }
+            const float m_new = mx;  // finite for every valid row (the diagonal key is always visible)
+            const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
+            const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run * p.scale_log2 - m_scaled);
+            // rescale O (previous PV has completed: s_full is committed after it)
+            if (j > 0) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < HD; c0 += 16) {
+                    uint32_t o[16];
+                    tmem_ld16(t_lane + O_COL + c0, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st16(t_lane + O_COL + c0, o);
+                }
+            }
+            // pass 2: P = exp2(s*scale - m), row sum; P (bf16) overwrites the already-consumed S columns
+            float lsum = 0.f;
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(t_lane + ch * 32, v);
+                tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+                    float p0 = exp2f(s0 * p.scale_log2 - m_scaled);
+                    float p1 = exp2f(s1 * p.scale_log2 - m_scaled);
+                    if (diag) {
+                        if (kbase + ch * 32 + i > qi) p0 = 0.f;
+                        if (kbase + ch * 32 + i + 1 > qi) p1 = 0.f;
+                    }
+                    lsum += p0 + p1;
+                    pk[i >> 1] = pack_bf16(p0, p1);
+                }
+                tmem_st16(t_lane + ch * 16, pk);
+            }
+            l_run = l_run * alpha + lsum;
+            m_run = m_new;
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(p_ready);
+        }
+        // ---------------- epilogue ----------------
+        mbar_wait(o_full, 0, 15);
+        tc_fence_after();
+        const bool row_ok = qi < loc.doc_len;
+        const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
+        __nv_bfloat16* orow = p.out + int64_t(row_base + r) * (int64_t(p.n_heads) * HD) + int64_t(head) * HD;
+#pragma unroll 1
+        for (int c0 = 0; c0 < HD; c0 += 16) {
+            uint32_t o[16];
+            tmem_ld16(t_lane + O_COL + c0, o);
+            tmem_ld_wait();
+            if (row_ok) {
+                uint4 a, b;
+                a.x = pack_bf16(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l);
+                a.y = pack_bf16(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l);
+                a.z = pack_bf16(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l);
+                a.w = pack_bf16(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l);
+                b.x = pack_bf16(__uint_as_float(o[8]) * inv_l, __uint_as_float(o[9]) * inv_l);
+                b.y = pack_bf16(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l);
+                b.z = pack_bf16(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l);
+                b.w = pack_bf16(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l);
+                *reinterpret_cast<uint4*>(orow + c0) = a;
+                *reinterpret_cast<uint4*>(orow + c0 + 8) = b;
+            }
+        }
+        if (row_ok) p.lse[int64_t(head) * p.T + row_base + r] = m_run * p.scale + logf(l_run);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+template <int HD>
+int launch_fwd(const void* qkv, int64_t row_stride, const FwdParams& p, int max_seqlen, cudaStream_t st) {
+    using CH = HeadChunks<HD>;
+    CUtensorMap t64, tR;
+    uint64_t dims[2] = {uint64_t(row_stride), uint64_t(p.T)};
+    uint64_t strides[2] = {2, uint64_t(row_stride) * 2};
+    uint32_t box[2] = {64, ATT_TILE};
+    int rc;
+    if (CH::NC64 > 0) {
+        rc = dolo_make_tmap(&t64, qkv, 2, 2, dims, strides, box, DOLO_SW_128);
+        if (rc) return rc;
+    }
+    if (CH::REM > 0) {
+        box[0] = CH::REM;
+        rc = dolo_make_tmap(&tR, qkv, 2, 2, dims, strides, box, CH::REM == 32 ? DOLO_SW_64 : DOLO_SW_32);
+        if (rc) return rc;
+    }
+    if (CH::NC64 == 0) t64 = tR;
+    if (CH::REM == 0) tR = t64;
+    constexpr int smem_bytes = 1024 + (1 + 2 * KV_STAGES) * CH::TILE_BYTES + 128;
+    auto kern = attn_fwd_kernel<HD>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DOLO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        attr_set = true;
+    }
+    // upper bound on the number of q tiles without reading cu_seqlens on the host
+    const int64_t max_tiles = (p.T + ATT_TILE - 1) / ATT_TILE + p.n_docs;
+    dim3 grid((unsigned)max_tiles, (unsigned)p.n_heads);
+    kern<<<grid, FWD_THREADS, smem_bytes, st>>>(t64, tR, p);
+    DOLO_LAUNCH_OK("attn_varlen_fwd");
+    (void)max_seqlen;
+    return DOLO_OK;
+}
+
+}  // namespace
+
+extern "C" int dolomite_b200_attn_varlen_fwd(const void* qkv, int64_t row_stride, void* out, float* lse,
+                                             const int32_t* cu_seqlens, int n_docs, int64_t T, int max_seqlen,
+                                             int n_groups, int q_per_group, int head_dim, float softmax_scale,
+                                             void* stream) {
+    DOLO_REQUIRE(n_docs >= 0 && T >= 0, "attn_fwd: negative sizes");
+    if (T == 0 || n_docs == 0) return DOLO_OK;
+    DOLO_REQUIRE(n_groups > 0 && q_per_group > 0, "attn_fwd: bad head grouping");
+    DOLO_REQUIRE(row_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0, "attn_fwd: qkv alignment");
+    DOLO_REQUIRE(int64_t(n_groups) * (q_per_group + 2) * head_dim <= row_stride, "attn_fwd: slot layout exceeds row");
+    DOLO_REQUIRE(T < (1ll << 31), "attn_fwd: T too large");
+    FwdParams p;
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.lse = lse;
+    p.cu_seqlens = cu_seqlens;
+    p.n_docs = n_docs;
+    p.T = T;
+    p.n_groups = n_groups;
+    p.q_per_group = q_per_group;
+    p.n_heads = n_groups * q_per_group;
+    p.scale = softmax_scale;
+    p.scale_log2 = softmax_scale * 1.4426950408889634f;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (head_dim) {
+        case 16: return launch_fwd<16>(qkv, row_stride, p, max_seqlen, st);
+        case 32: return launch_fwd<32>(qkv, row_stride, p, max_seqlen, st);
+        case 64: return launch_fwd<64>(qkv, row_stride, p, max_seqlen, st);
+        case 80: return launch_fwd<80>(qkv, row_stride, p, max_seqlen, st);
+        case 96: return launch_fwd<96>(qkv, row_stride, p, max_seqlen, st);
+        case 128: return launch_fwd<128>(qkv, row_stride, p, max_seqlen, st);
+        default: return dolo_set_error("attn_fwd: unsupported head_dim %d (supported: 16,32,64,80,96,128)", head_dim);
+    }
+}
