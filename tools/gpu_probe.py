@@ -360,6 +360,162 @@ def optimizer():
     return {"adamw": e, "adamw_bf16": eb, "norm": [norm.item(), ref_norm], "colsum": ec, "add_scaled": ea, "ok": bool(ok)}
 
 
+# ---------------------------------------------------------------------------------------------
+def _attn_ref(qkv, cu, ng, g, hd, scale, dout=None):
+    """fp32 reference: per-document causal softmax attention on the packed slot layout."""
+    torch = _t()
+    T = qkv.shape[0]
+    x = qkv.float().view(T, ng, g + 2, hd).detach().clone().requires_grad_(True)
+    q = x[:, :, :g].reshape(T, ng * g, hd)
+    k = x[:, :, g].repeat_interleave(g, dim=1)
+    v = x[:, :, g + 1].repeat_interleave(g, dim=1)
+    outs, lses = [], []
+    cu_l = cu.tolist()
+    for d in range(len(cu_l) - 1):
+        s, e = cu_l[d], cu_l[d + 1]
+        if e == s:
+            continue
+        qd, kd, vd = q[s:e].transpose(0, 1), k[s:e].transpose(0, 1), v[s:e].transpose(0, 1)
+        sc = torch.matmul(qd, kd.transpose(1, 2)) * scale
+        mask = torch.ones(e - s, e - s, dtype=torch.bool, device=qkv.device).tril()
+        sc = sc.masked_fill(~mask, float("-inf"))
+        lses.append(torch.logsumexp(sc, dim=-1))
+        outs.append(torch.matmul(torch.softmax(sc, dim=-1), vd).transpose(0, 1))
+    out = torch.cat(outs, 0)
+    lse = torch.cat(lses, 1)
+    dx = None
+    if dout is not None:
+        out.backward(dout.float().view(T, ng * g, hd))
+        dx = x.grad.view(T, -1)
+    return out.reshape(T, -1).detach(), lse.detach(), dx
+
+
+def _attn_case(lens, ng, g, hd, bwd=True, seed=5):
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    T = sum(lens)
+    width = ng * (g + 2) * hd
+    qkv = (torch.randn(T, width, device="cuda", generator=gen)).bfloat16()
+    cu = torch.tensor([0] + list(__import__("itertools").accumulate(lens)), dtype=torch.int32, device="cuda")
+    scale = hd ** -0.5
+    dout = (torch.randn(T, ng * g * hd, device="cuda", generator=gen)).bfloat16()
+    out, lse = k.attn_varlen_fwd(qkv, cu, max(lens), ng, g, hd, scale)
+    torch.cuda.synchronize()
+    ro, rl, rdx = _attn_ref(qkv, cu, ng, g, hd, scale, dout if bwd else None)
+    res = {"fwd": _err(out, ro), "lse": _err(lse, rl), "T": T}
+    ok = res["fwd"]["rel_l2"] < 1e-2 and res["lse"]["max_abs"] < 2e-2
+    if bwd:
+        dqkv = k.attn_varlen_bwd(dout, qkv, out, lse, cu, max(lens), ng, g, hd, scale)
+        torch.cuda.synchronize()
+        d = dqkv.float().view(T, ng, g + 2, hd)
+        r = rdx.view(T, ng, g + 2, hd)
+        res["dq"] = _err(d[:, :, :g], r[:, :, :g])
+        res["dk"] = _err(d[:, :, g], r[:, :, g])
+        res["dv"] = _err(d[:, :, g + 1], r[:, :, g + 1])
+        ok = ok and all(res[x]["rel_l2"] < 2e-2 for x in ("dq", "dk", "dv"))
+    res["ok"] = bool(ok)
+    return res
+
+
+@case
+def attn_hd64_single_tile():
+    return _attn_case([128], 2, 1, 64)
+
+
+@case
+def attn_hd64_two_tiles():
+    return _attn_case([256], 2, 1, 64)
+
+
+@case
+def attn_hd64_ragged_docs():
+    return _attn_case([100, 37, 300, 1, 129], 4, 1, 64)
+
+
+@case
+def attn_hd80_ragged_docs():
+    return _attn_case([200, 130, 515], 4, 1, 80)
+
+
+@case
+def attn_hd128_gqa():
+    return _attn_case([300, 77, 260], 2, 4, 128)
+
+
+@case
+def attn_hd32_mqa():
+    return _attn_case([150, 250], 1, 4, 32)
+
+
+@case
+def attn_hd96():
+    return _attn_case([384, 100], 2, 1, 96)
+
+
+@case
+def attn_hd16():
+    return _attn_case([140], 2, 2, 16)
+
+
+def _attn_bench(S, B, nh, hd):
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+    from flash_attn.flash_attn_interface import flash_attn_varlen_func
+
+    T = S * B
+    qkv = torch.randn(T, nh * 3 * hd, device="cuda").bfloat16()
+    cu = torch.arange(0, T + 1, S, dtype=torch.int32, device="cuda")
+    scale = hd ** -0.5
+    dout = torch.randn(T, nh * hd, device="cuda").bfloat16()
+    out, lse = k.attn_varlen_fwd(qkv, cu, S, nh, 1, hd, scale)
+    v = qkv.view(T, nh, 3, hd)
+    q, kk, vv = v[:, :, 0], v[:, :, 1], v[:, :, 2]
+    fo = flash_attn_varlen_func(q, kk, vv, cu, cu, S, S, 0.0, softmax_scale=scale, causal=True)
+    res = {"vs_flash_fwd": _err(out, fo.reshape(T, -1))}
+    flops_fwd = 4.0 * S * S * hd * nh * B / 2
+    ms = _time(lambda: k.attn_varlen_fwd(qkv, cu, S, nh, 1, hd, scale, out=out), iters=10)
+    res["fwd_ms"] = ms
+    res["fwd_tflops_causal"] = flops_fwd / ms / 1e9
+    ms_f = _time(lambda: flash_attn_varlen_func(q, kk, vv, cu, cu, S, S, 0.0, softmax_scale=scale, causal=True), iters=10)
+    res["flash_fwd_ms"] = ms_f
+    res["flash_fwd_tflops_causal"] = flops_fwd / ms_f / 1e9
+    dqkv = torch.empty_like(qkv)
+    k.attn_varlen_bwd(dout, qkv, out, lse, cu, S, nh, 1, hd, scale, dqkv=dqkv)
+    qf = q.detach().clone().requires_grad_(True)
+    kf = kk.detach().clone().requires_grad_(True)
+    vf = vv.detach().clone().requires_grad_(True)
+    fo2 = flash_attn_varlen_func(qf, kf, vf, cu, cu, S, S, 0.0, softmax_scale=scale, causal=True)
+    fo2.backward(dout.view(T, nh, hd))
+    d = dqkv.view(T, nh, 3, hd)
+    res["vs_flash_dq"] = _err(d[:, :, 0], qf.grad)
+    res["vs_flash_dk"] = _err(d[:, :, 1], kf.grad)
+    res["vs_flash_dv"] = _err(d[:, :, 2], vf.grad)
+    ms_b = _time(lambda: k.attn_varlen_bwd(dout, qkv, out, lse, cu, S, nh, 1, hd, scale, dqkv=dqkv), iters=5)
+    res["bwd_ms"] = ms_b
+    res["bwd_tflops_causal"] = 2.5 * flops_fwd / ms_b / 1e9
+
+    def fb():
+        o = flash_attn_varlen_func(qf, kf, vf, cu, cu, S, S, 0.0, softmax_scale=scale, causal=True)
+        o.backward(dout.view(T, nh, hd))
+
+    ms_fb = _time(fb, iters=5)
+    res["flash_fwd_bwd_ms"] = ms_fb
+    res["ok"] = bool(res["vs_flash_fwd"]["rel_l2"] < 1e-2 and res["vs_flash_dq"]["rel_l2"] < 2e-2 and res["vs_flash_dk"]["rel_l2"] < 2e-2 and res["vs_flash_dv"]["rel_l2"] < 2e-2)
+    return res
+
+
+@case
+def attn_bench_c2():
+    return _attn_bench(4096, 2, 32, 80)
+
+
+@case
+def attn_bench_hd128():
+    return _attn_bench(4096, 2, 16, 128)
+
+
 @case
 def env_info():
     torch = _t()
