@@ -407,7 +407,7 @@ __global__ void ce_mean_kernel(const float* __restrict__ loss_tok, int64_t T, co
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
     colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t T, int64_t N,
-                  int rows_per_block) {
+                  int rows_per_block, float scale) {
     __shared__ float sm[8][256];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t col = int64_t(blockIdx.x) * 256 + lane * 8;
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += sm[w][c];
     const int64_t gc = int64_t(blockIdx.x) * 256 + c;
-    if (gc < N) atomicAdd(out + gc, s);
+    if (gc < N) atomicAdd(out + gc, s * scale);
 }
 
 __global__ void __launch_bounds__(kThreads) add_scaled_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
@@ -681,7 +681,8 @@ extern "C" int dolomite_b200_cross_entropy_fwd_bwd(const void* logits, int64_t l
     return DOLO_OK;
 }
 
-extern "C" int dolomite_b200_colsum_accum(const void* x, int64_t ldx, float* out, int64_t T, int64_t N, void* stream) {
+extern "C" int dolomite_b200_colsum_accum(const void* x, int64_t ldx, float* out, int64_t T, int64_t N, float scale,
+                                          void* stream) {
     DOLO_REQUIRE(N > 0 && N % 8 == 0 && ldx % 8 == 0, "colsum: N=%lld / ld=%lld must be multiples of 8", (long long)N,
                  (long long)ldx);
     DOLO_REQUIRE(aligned16(x), "colsum: pointer must be 16-byte aligned");
@@ -693,8 +694,34 @@ extern "C" int dolomite_b200_colsum_accum(const void* x, int64_t ldx, float* out
     const int rows_per_block = int((T + row_splits - 1) / row_splits);
     dim3 grid(col_tiles, row_splits);
     colsum_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ldx,
-                                                                            out, T, N, rows_per_block);
+                                                                            out, T, N, rows_per_block, scale);
     DOLO_LAUNCH_OK("colsum");
+    return DOLO_OK;
+}
+
+__global__ void __launch_bounds__(256) scale_by_dev_scalar_kernel(uint4* __restrict__ x, int64_t n8,
+                                                                  const float* __restrict__ scale) {
+    const float s = scale[0];
+    if (s == 1.f) return;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += int64_t(gridDim.x) * blockDim.x) {
+        uint4 v = x[i];
+        v.x = dolo::pack_bf16(dolo::bf16_lo(v.x) * s, dolo::bf16_hi(v.x) * s);
+        v.y = dolo::pack_bf16(dolo::bf16_lo(v.y) * s, dolo::bf16_hi(v.y) * s);
+        v.z = dolo::pack_bf16(dolo::bf16_lo(v.z) * s, dolo::bf16_hi(v.z) * s);
+        v.w = dolo::pack_bf16(dolo::bf16_lo(v.w) * s, dolo::bf16_hi(v.w) * s);
+        x[i] = v;
+    }
+}
+
+extern "C" int dolomite_b200_scale_bf16_by_device_scalar(void* x, int64_t n, const float* scale, void* stream) {
+    DOLO_REQUIRE(n % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "scale_bf16: n %% 8 and 16-byte alignment required");
+    if (n == 0) return DOLO_OK;
+    int64_t blocks = (n / 8 + 255) / 256;
+    const int64_t cap = int64_t(dolo_num_sms()) * 8;
+    if (blocks > cap) blocks = cap;
+    scale_by_dev_scalar_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<uint4*>(x), n / 8, scale);
+    DOLO_LAUNCH_OK("scale_bf16_by_device_scalar");
     return DOLO_OK;
 }
 

@@ -192,13 +192,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         for (int c = 0; c < 4; ++c) {  // 4 x 16-byte chunks (8 columns each)
                             float f[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[c * 8 + j]) * p.alpha;
+                            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[c * 8 + j]);
                             if (p.bias != nullptr) {
                                 const int cb = col0 + slab * 64 + h * 32 + c * 8;
 #pragma unroll
                                 for (int j = 0; j < 8; ++j)
                                     if (cb + j < p.N) f[j] += __bfloat162float(p.bias[cb + j]);
                             }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] *= p.alpha;
                             uint4 v;
                             v.x = pack_bf16(f[0], f[1]);
                             v.y = pack_bf16(f[2], f[3]);
@@ -227,12 +229,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     if (!row_ok) continue;
                     float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]) * p.alpha;
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
                     if (p.bias != nullptr) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (cb + j < p.N) f[j] += __bfloat162float(p.bias[cb + j]);
                     }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
                     if (p.d_is_f32) {
                         float* drow = static_cast<float*>(p.D) + row * p.ldd + cb;
                         const float* crow = p.C ? static_cast<const float*>(p.C) + row * p.ldc + cb : nullptr;

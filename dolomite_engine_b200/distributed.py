@@ -1,0 +1,278 @@
+"""Flat-bucket sharded data parallelism for the B200 path (replaces torch FSDP as configured by
+`wrap_model_for_distributed_training`, reference distributed/__init__.py:47-236).
+
+One FlatUnit per transformer block + one root unit (same wrapping as `transformer_auto_wrap_policy` over
+`_no_split_modules`).  Rank r owns slice r of every unit's fp32 master / optimizer state.  Per step and unit:
+
+  forward   cast own fp32 shard -> bf16 into its slice of the unit's gather buffer, in-place `ncclAllGather`
+            on the communication stream, prefetched one unit ahead of the compute stream (N1 of SURVEY 2.2)
+  backward  wgrad GEMM epilogues accumulate into the unit's full gradient buffer; when the unit's backward is
+            done (last micro-step only, i.e. outside `no_sync`) `ncclReduceScatter(AVG)` on the communication
+            stream overlaps the next unit's backward (N2)
+
+B200-first choices: the gathered bf16 parameters of a 3.5 B (8 B) model are 7 GB (16 GB) of 180 GB HBM, so units
+stay resident between forward and backward (`reshard_after_forward=False`; one all-gather per unit per optimizer
+step instead of the reference's two per micro-step) unless stage-3 resharding is requested; gather/gradient buffers
+are allocated once (no allocator churn, no record_stream); scalar collectives (loss AVG, grad-norm SUM) stay on
+the device without `.item()` until the caller asks.
+"""
+
+from __future__ import annotations
+
+import contextlib
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import kernels as K
+from .engine import DolomiteEngine, FlatUnit
+
+
+class _Comm:
+    """engine hooks: all-gather prefetch in forward, reduce-scatter in backward"""
+
+    def __init__(self, engine: DolomiteEngine, group, communication_dtype: torch.dtype, reshard_after_forward: bool):
+        self.engine = engine
+        self.group = group
+        self.ws = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.comm_dtype = communication_dtype
+        self.reshard = reshard_after_forward
+        self.stream = torch.cuda.Stream(device=engine.device, priority=-1)
+        n = len(engine.units)
+        self.ag_work: list = [None] * n
+        self.rs_work: list = [None] * n
+        self.fresh = [False] * n  # gather buffer holds the current parameters
+        self.sync_grads = True
+        if communication_dtype == torch.bfloat16:
+            biggest = max(u.padded for u in engine.units)
+            self.rs_stage = [torch.empty(biggest, dtype=torch.bfloat16, device=engine.device) for _ in range(2)]
+            self.rs_out = [torch.empty(biggest // self.ws, dtype=torch.bfloat16, device=engine.device) for _ in range(2)]
+            self.rs_stage_evt = [None, None]
+        self._rs_count = 0
+        self._pending_bf16 = []
+
+    # ---- all-gather ----
+    def invalidate(self) -> None:
+        self.fresh = [False] * len(self.fresh)
+
+    def _issue_gather(self, i: int) -> None:
+        if self.fresh[i] or self.ag_work[i] is not None:
+            return
+        u = self.engine.units[i]
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)  # previous readers of the buffer (last backward) are ordered before the overwrite
+        with torch.cuda.stream(self.stream):
+            own = u.compute[self.rank * u.shard_numel : (self.rank + 1) * u.shard_numel]
+            K.cast_f32_to_bf16(u.master.data, own)
+            self.ag_work[i] = dist.all_gather_into_tensor(u.compute, own, group=self.group, async_op=True)
+
+    def _wait_gather(self, i: int) -> None:
+        if self.ag_work[i] is not None:
+            self.ag_work[i].wait()  # compute stream waits (device side) for the collective
+            self.ag_work[i] = None
+            self.fresh[i] = True
+
+    def pre_forward_unit(self, i: int) -> None:
+        self._issue_gather(i)
+        if i + 1 < len(self.fresh):
+            self._issue_gather(i + 1)  # prefetch depth 1
+        self._wait_gather(i)
+
+    def post_forward_unit(self, i: int) -> None:
+        if self.reshard and i > 0:
+            self.fresh[i] = False  # stage-3 semantics: parameters are re-gathered for backward
+
+    def pre_backward_unit(self, i: int) -> None:
+        if self.reshard:
+            self._issue_gather(i)
+            if i - 1 >= 1:
+                self._issue_gather(i - 1)
+            self._wait_gather(i)
+
+    # ---- reduce-scatter ----
+    def post_backward_unit(self, i: int) -> None:
+        if not self.sync_grads:
+            return
+        u = self.engine.units[i]
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            if self.comm_dtype == torch.bfloat16:
+                slot = self._rs_count % 2
+                self._rs_count += 1
+                if self.rs_stage_evt[slot] is not None:
+                    self.rs_stage_evt[slot].wait()
+                stage = self.rs_stage[slot][: u.padded]
+                out = self.rs_out[slot][: u.shard_numel]
+                K.cast_f32_to_bf16(u.grad_full, stage)
+                work = dist.reduce_scatter_tensor(out, stage, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+                work.wait()  # orders the comm stream after the collective
+                u.master.grad.zero_()
+                K.accum_bf16_into_f32(out, u.master.grad, 1.0)
+                evt = torch.cuda.Event()
+                evt.record(self.stream)
+                self.rs_stage_evt[slot] = evt
+                self.rs_work[i] = evt
+            else:
+                work = dist.reduce_scatter_tensor(u.master.grad, u.grad_full, op=dist.ReduceOp.AVG, group=self.group,
+                                                  async_op=True)
+                self.rs_work[i] = work
+        if i == 0:
+            self.finish_backward()
+
+    def finish_backward(self) -> None:
+        cur = torch.cuda.current_stream()
+        for i, w in enumerate(self.rs_work):
+            if w is None:
+                continue
+            if isinstance(w, torch.cuda.Event):
+                cur.wait_event(w)
+            else:
+                w.wait()
+            self.rs_work[i] = None
+        for u in self.engine.units:
+            u.grad_full.zero_()  # consumed; next accumulation window starts from zero
+
+    def gather_master(self, unit: FlatUnit) -> torch.Tensor:
+        full = torch.empty(unit.padded, dtype=torch.float32, device=unit.master.device)
+        dist.all_gather_into_tensor(full, unit.master.data, group=self.group)
+        return full
+
+
+class ShardedDataParallel(nn.Module):
+    """What `wrap_model_for_distributed_training` returns.  Supports what train_utils.train_step needs from an
+    FSDP-1 style wrapper: `.no_sync()`, `.clip_grad_norm_(max_norm)`, `.parameters()` (flat fp32 shards with
+    `.grad`), `.train()/.eval()`, `.config`, `.tokenizer` and `forward(batch) -> loss`."""
+
+    def __init__(self, model_wrapper: nn.Module, process_group=None, communication_dtype: torch.dtype | None = None,
+                 reshard_after_forward: bool = False):
+        super().__init__()
+        self.module = model_wrapper
+        self.engine: DolomiteEngine = model_wrapper.model.engine
+        self.group = process_group
+        self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        if self.world_size > 1:
+            assert self.engine.world_size == self.world_size, "engine must be built with world_size/rank of the DP group"
+            comm_dtype = torch.bfloat16 if communication_dtype is None else communication_dtype
+            self.engine.comm = _Comm(self.engine, process_group, comm_dtype, reshard_after_forward)
+        self._sumsq = torch.zeros(1, dtype=torch.float32, device=self.engine.device)
+        self.clip_coef = torch.ones(1, dtype=torch.float32, device=self.engine.device)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=self.engine.device)
+        self._stale = True
+        self._versions = [-1] * len(self.engine.units)
+
+    # ---- attribute passthrough ----
+    @property
+    def config(self):
+        return self.module.config
+
+    @property
+    def tokenizer(self):
+        return getattr(self.module, "tokenizer", None)
+
+    def parameters(self, recurse: bool = True):
+        for u in self.engine.units:
+            yield u.master
+
+    def named_parameters(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True):
+        for u in self.engine.units:
+            yield f"{prefix}flat.{u.name}", u.master
+
+    # ---- parameter freshness ----
+    def mark_parameters_updated(self) -> None:
+        """call after the optimizer changed the fp32 masters (train_step does; torch optimizers are also detected
+        through the tensors' version counters)"""
+        self._stale = True
+
+    def _refresh_parameters_if_needed(self) -> None:
+        changed = self._stale
+        for i, u in enumerate(self.engine.units):
+            if u.master._version != self._versions[i]:
+                changed = True
+        if not changed:
+            return
+        if self.engine.comm is not None:
+            self.engine.comm.invalidate()
+        else:
+            self.engine.refresh_compute_from_master()
+        self._versions = [u.master._version for u in self.engine.units]
+        self._stale = False
+
+    def notify_fused_update(self) -> None:
+        """the fused AdamW already wrote the bf16 copies (world_size == 1) -> nothing to refresh"""
+        self._versions = [u.master._version for u in self.engine.units]
+        self._stale = self.engine.comm is not None
+        if self.engine.comm is not None:
+            self.engine.comm.invalidate()
+            self._stale = False
+
+    # ---- forward ----
+    def forward(self, batch: dict) -> torch.Tensor:
+        self._refresh_parameters_if_needed()
+        return self.module(batch)
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        comm = self.engine.comm
+        if comm is None:
+            yield
+            return
+        prev = comm.sync_grads
+        comm.sync_grads = False
+        try:
+            yield
+        finally:
+            comm.sync_grads = prev
+
+    def set_requires_gradient_sync(self, flag: bool) -> None:  # FSDP-2 style spelling
+        if self.engine.comm is not None:
+            self.engine.comm.sync_grads = bool(flag)
+
+    # ---- gradient clipping (train_utils.py:99-103) ----
+    def clip_grad_norm_(self, max_norm: float, fuse_into_optimizer: bool = False) -> torch.Tensor:
+        """total L2 norm over all ranks' shards; returns a 0-d device tensor (no host sync).  With
+        `fuse_into_optimizer` the gradients are left unscaled and the clip coefficient (device scalar
+        `self.clip_coef`) is consumed by DolomiteFusedAdamW; otherwise gradients are scaled in place."""
+        self._sumsq.zero_()
+        for u in self.engine.units:
+            K.sumsq_accum(u.master.grad, self._sumsq)
+        if self.world_size > 1:
+            dist.all_reduce(self._sumsq, op=dist.ReduceOp.SUM, group=self.group)
+        K.clip_coef(self._sumsq, max_norm, self.clip_coef, self.grad_norm)
+        if not fuse_into_optimizer:
+            for u in self.engine.units:
+                u.master.grad.mul_(self.clip_coef)
+        return self.grad_norm.reshape(())
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        self.engine.zero_grad()
+
+    def state_dict(self, *args, **kwargs):
+        return self.engine.state_dict()
+
+    def load_state_dict(self, sd, strict: bool = True, assign: bool = False):
+        self.engine.load_state_dict(sd, strict=strict)
+        self.mark_parameters_updated()
+
+
+def wrap_model_for_distributed_training(args, model: nn.Module) -> nn.Module:
+    """Reference signature (distributed/__init__.py:47).  Reads the same knobs from `args.distributed_args`:
+    `stage` (3 -> reshard parameters after forward, 0/2 -> keep them gathered), `communication_dtype`,
+    `fsdp_algorithm` (both map to the same flat-bucket runtime), and rejects what is out of scope."""
+    dargs = getattr(args, "distributed_args", None)
+    stage = getattr(dargs, "stage", 3) if dargs is not None else 3
+    comm_dtype = None
+    if dargs is not None and getattr(dargs, "communication_dtype", None) is not None:
+        comm_dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[str(dargs.communication_dtype).split(".")[-1]]
+    if dargs is not None:
+        if str(getattr(dargs, "distributed_backend", "torch")).split(".")[-1] != "torch":
+            raise NotImplementedError("only distributed_backend=torch (NCCL) exists on the B200 path; no DeepSpeed dispatch")
+        if getattr(dargs, "tensor_parallel_size", 1) != 1:
+            raise NotImplementedError("tensor parallelism is out of scope of the data-parallel B200 path")
+        if getattr(dargs, "torch_compile", False):
+            raise NotImplementedError("torch.compile is not used on the B200 path (hand-written kernels + CUDA streams)")
+    reshard = bool(getattr(dargs, "reshard_after_forward", False)) if dargs is not None else False
+    group = dist.group.WORLD if dist.is_initialized() else None
+    return ShardedDataParallel(model, group, communication_dtype=comm_dtype, reshard_after_forward=reshard and stage == 3)

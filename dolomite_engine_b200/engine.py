@@ -1,0 +1,423 @@
+"""Training engine of the B200 path: flat parameter units + explicit forward/backward over the C-ABI kernels.
+
+Replaces, for the padding-free GPTDolomite / MoEDolomite step, what the reference gets from autograd over
+`GPTDolomiteModel.forward` (gpt_dolomite/base.py:170-244), `GPTDolomiteBlock.forward` (layer.py:49-87),
+`PaddingFreeAttention.forward` (attention/padding_free.py:15-77), `MLP.forward` (mlp.py:45-50) and the tied LM head
+(main.py:172-177), and what torch FSDP does around it (distributed/__init__.py:126-230).
+
+Data layout in HBM
+  * one FlatUnit per FSDP unit (root = wte [+wpe] + ln_f [+lm_head]; one per transformer block), mirroring
+    `_no_split_modules` wrapping.  Per unit: fp32 master shard (the nn.Parameter the optimizer sees), fp32 gradient
+    shard, a full bf16 compute buffer (what the all-gather fills and the kernels read) and a full fp32 gradient
+    accumulation buffer that the wgrad GEMM epilogues add into (what the reduce-scatter consumes).
+  * activations are [T, features] bf16 row-major; attention reads q/k/v straight out of the packed c_attn output.
+No op here has a PyTorch fallback: without the CUDA library every call raises.
+"""
+
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import TYPE_CHECKING
+
+import torch
+
+from . import kernels as K
+
+if TYPE_CHECKING:  # the config module lives in hf_models, which imports this module
+    from .hf_models.config import CommonConfig
+
+_ALIGN = 64  # elements; keeps every parameter 128-byte aligned inside a flat unit (TMA needs 16 B)
+
+
+@dataclass
+class ParamSpec:
+    name: str  # reference state-dict name
+    shape: tuple
+    offset: int
+    numel: int
+    init: str  # "normal:<std>" | "ones" | "zeros"
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class FlatUnit:
+    """One FSDP unit: contiguous flat buffers + named views (reference parameter names)."""
+
+    def __init__(self, name: str, specs: list[tuple[str, tuple, str]], world_size: int = 1, rank: int = 0):
+        self.name = name
+        self.specs: list[ParamSpec] = []
+        off = 0
+        for pname, shape, init in specs:
+            n = math.prod(shape)
+            self.specs.append(ParamSpec(pname, tuple(shape), off, n, init))
+            off += _round_up(n, _ALIGN)
+        self.numel = off
+        self.world_size = world_size
+        self.rank = rank
+        self.padded = _round_up(max(off, 1), world_size * _ALIGN)
+        self.shard_numel = self.padded // world_size
+        self.master: torch.nn.Parameter | None = None  # fp32 [shard_numel]
+        self.compute: torch.Tensor | None = None  # bf16 [padded]
+        self.grad_full: torch.Tensor | None = None  # fp32 [padded]
+        self.views: dict[str, torch.Tensor] = {}
+        self.gviews: dict[str, torch.Tensor] = {}
+        self.gathered = False  # compute buffer holds current parameters
+        self.exp_avg = None
+        self.exp_avg_sq = None
+
+    # ---- allocation / init ----
+    def allocate(self, device) -> None:
+        self.master = torch.nn.Parameter(torch.zeros(self.shard_numel, dtype=torch.float32, device=device))
+        self.master.grad = torch.zeros(self.shard_numel, dtype=torch.float32, device=device)
+        self.compute = torch.zeros(self.padded, dtype=torch.bfloat16, device=device)
+        if self.world_size == 1:
+            self.grad_full = self.master.grad  # no reduce-scatter: wgrad accumulates straight into the shard grad
+        else:
+            self.grad_full = torch.zeros(self.padded, dtype=torch.float32, device=device)
+        for s in self.specs:
+            self.views[s.name] = self.compute[s.offset : s.offset + s.numel].view(s.shape)
+            self.gviews[s.name] = self.grad_full[s.offset : s.offset + s.numel].view(s.shape)
+
+    def full_master_from(self, full_fp32: torch.Tensor) -> None:
+        """install parameters from a full flat fp32 tensor (host or device)"""
+        lo = self.rank * self.shard_numel
+        with torch.no_grad():
+            self.master.copy_(full_fp32[lo : lo + self.shard_numel])
+            self.compute.copy_(full_fp32.to(self.compute.device))
+        self.gathered = True
+
+    def init_full(self, generator: torch.Generator) -> torch.Tensor:
+        """reference init rules, on the CPU in fp32 so that every rank draws the same values"""
+        full = torch.zeros(self.padded, dtype=torch.float32)
+        for s in self.specs:
+            v = full[s.offset : s.offset + s.numel].view(s.shape)
+            if s.init == "ones":
+                v.fill_(1.0)
+            elif s.init == "zeros":
+                v.zero_()
+            else:
+                std = float(s.init.split(":")[1])
+                v.copy_(torch.randn(s.shape, generator=generator) * std)
+        return full
+
+
+def _block_specs(cfg: CommonConfig, i: int) -> list[tuple[str, tuple, str]]:
+    """parameters of GPTDolomiteBlock i in registration order (layer.py:33-47, attention/base.py:73-86, mlp.py:26-41)"""
+    H, F = cfg.n_embd, cfg.n_inner
+    hd = cfg.n_embd // cfg.n_head
+    qkv = H + 2 * cfg.num_key_value_heads * hd
+    std = cfg.initializer_range
+    if cfg.init_method == "mup":
+        std /= math.sqrt(cfg.m_width)
+    std_proj = cfg.initializer_range / math.sqrt(2 * cfg.n_layer)
+    if cfg.init_method == "mup":
+        std_proj /= math.sqrt(cfg.m_width)
+    glu = cfg.activation_function.endswith("glu")
+    fc_out = 2 * F if glu else F
+    p = f"transformer.h.{i}."
+    specs = [(p + "ln_1.weight", (H,), "ones"), (p + "attn.c_attn.weight", (qkv, H), f"normal:{std}")]
+    if cfg.add_bias:
+        specs.append((p + "attn.c_attn.bias", (qkv,), "zeros"))
+    specs.append((p + "attn.c_proj.weight", (H, H), f"normal:{std_proj}"))
+    if cfg.add_bias:
+        specs.append((p + "attn.c_proj.bias", (H,), "zeros"))
+    specs.append((p + "ln_2.weight", (H,), "ones"))
+    E = getattr(cfg, "num_experts", 0) if cfg.model_type == "moe_dolomite" else 0
+    if E:
+        specs.append((p + "mlp.gate.weight", (E, H), f"normal:{std}"))
+        specs.append((p + "mlp.c_fc.weight", (E, fc_out, H), f"normal:{std}"))
+        if cfg.add_bias:
+            specs.append((p + "mlp.c_fc.bias", (E, fc_out), "zeros"))
+        specs.append((p + "mlp.c_proj.weight", (E, H, F), f"normal:{std_proj}"))
+        if cfg.add_bias:
+            specs.append((p + "mlp.c_proj.bias", (E, H), "zeros"))
+    else:
+        specs.append((p + "mlp.c_fc.weight", (fc_out, H), f"normal:{std}"))
+        if cfg.add_bias:
+            specs.append((p + "mlp.c_fc.bias", (fc_out,), "zeros"))
+        specs.append((p + "mlp.c_proj.weight", (H, F), f"normal:{std_proj}"))
+        if cfg.add_bias:
+            specs.append((p + "mlp.c_proj.bias", (H,), "zeros"))
+    return specs
+
+
+def _root_specs(cfg: CommonConfig) -> list[tuple[str, tuple, str]]:
+    H, V = cfg.n_embd, cfg.vocab_size
+    specs = [("transformer.wte.weight", (V, H), f"normal:{cfg.initializer_range}")]
+    specs.append(("transformer.ln_f.weight", (H,), "ones"))
+    if not cfg.tie_word_embeddings:
+        std = cfg.initializer_range
+        if cfg.init_method == "mup":
+            std /= math.sqrt(cfg.m_width)
+        specs.append(("lm_head.weight", (V, H), f"normal:{std}"))
+    return specs
+
+
+def check_supported(cfg: CommonConfig) -> None:
+    """The B200 hot path implements the configurations SURVEY.md section 8 puts in scope; everything else raises
+    (mirrors the reference's NotImplementedError / ValueError conventions)."""
+    if cfg.position_embedding_type not in ("rope", "nope"):
+        raise NotImplementedError(
+            f"position_embedding_type={cfg.position_embedding_type!r}: the B200 path implements rope and nope "
+            "(alibi is unsupported with flash attention in the reference too, gpt_dolomite/base.py:530)"
+        )
+    if cfg.rope_scaling is not None:
+        raise NotImplementedError("YaRN rope_scaling is out of scope of the B200 hot path (SURVEY.md section 2 #5)")
+    if cfg.normalization_function != "rmsnorm":
+        raise NotImplementedError(f"normalization_function={cfg.normalization_function!r}: only rmsnorm is on the hot path")
+    if cfg.activation_function != "swiglu":
+        raise NotImplementedError(f"activation_function={cfg.activation_function!r}: only swiglu is implemented in CUDA")
+    if cfg.resid_pdrop != 0 or cfg.embd_pdrop != 0 or cfg.attn_pdrop != 0:
+        raise NotImplementedError("dropout > 0 is not implemented on the B200 path (target configs use p=0: nn.Identity)")
+    hd = cfg.n_embd // cfg.n_head
+    if hd not in (16, 32, 64, 80, 96, 128):
+        raise NotImplementedError(f"head_dim={hd}: supported head dims are 16, 32, 64, 80, 96, 128")
+    if cfg.n_embd % 8 or cfg.n_inner % 8 or cfg.vocab_size % 8:
+        raise NotImplementedError("n_embd, n_inner and vocab_size must be multiples of 8 (16-byte vector kernels / TMA)")
+
+
+class DolomiteEngine:
+    """Owns the flat units of one model replica/shard and runs the explicit forward / backward."""
+
+    def __init__(self, cfg: CommonConfig, device, world_size: int = 1, rank: int = 0, seed: int | None = 42):
+        check_supported(cfg)
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.world_size, self.rank = world_size, rank
+        self.hd = cfg.n_embd // cfg.n_head
+        self.n_groups = cfg.num_key_value_heads
+        self.q_per_group = cfg.n_head // cfg.num_key_value_heads
+        self.qkv_dim = cfg.n_embd + 2 * cfg.num_key_value_heads * self.hd
+        self.is_moe = cfg.model_type == "moe_dolomite"
+        self.units: list[FlatUnit] = [FlatUnit("root", _root_specs(cfg), world_size, rank)]
+        for i in range(cfg.n_layer):
+            self.units.append(FlatUnit(f"h.{i}", _block_specs(cfg, i), world_size, rank))
+        for u in self.units:
+            u.allocate(self.device)
+        if seed is not None:
+            g = torch.Generator().manual_seed(seed)
+            for u in self.units:
+                u.full_master_from(u.init_full(g))
+        self._setup_rope()
+        self.comm = None  # set by distributed.ShardedDataParallel
+        self._saved = None
+        self.requires_gradient_sync = True
+        if cfg.attention_multiplier is not None:
+            self.softmax_scale = float(cfg.attention_multiplier)
+        elif cfg.scale_attn_weights:
+            self.softmax_scale = 1.0 / math.sqrt(self.hd)
+        else:
+            self.softmax_scale = 1.0
+
+    # ------------------------------------------------------------------------------------------
+    def _setup_rope(self) -> None:
+        """cos/sin cache exactly as RoPE._set_cos_sin_cache (position_embedding/rope.py:36-55) then .to(bf16) (:29-30)"""
+        self.rope_cos = self.rope_sin = None
+        if self.cfg.position_embedding_type != "rope":
+            return
+        hd = self.hd
+        inv_freq = 1.0 / (float(self.cfg.rope_theta) ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))
+        t = torch.arange(self.cfg.n_positions, dtype=torch.float32)
+        freqs = torch.outer(t, inv_freq)
+        emb = torch.cat((freqs, freqs), dim=-1)
+        self.rope_cos = emb.cos().to(torch.bfloat16).to(self.device)
+        self.rope_sin = emb.sin().to(torch.bfloat16).to(self.device)
+
+    def named_views(self):
+        for u in self.units:
+            for s in u.specs:
+                yield s.name, u, s
+
+    def num_parameters(self) -> int:
+        return sum(s.numel for u in self.units for s in u.specs)
+
+    def zero_grad(self) -> None:
+        for u in self.units:
+            u.grad_full.zero_()
+            if u.master.grad is not u.grad_full:
+                u.master.grad.zero_()
+
+    # ------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------
+    def _w(self, unit: FlatUnit, name: str):
+        return unit.views.get(name)
+
+    def forward(self, input_ids, position_ids, cu_seqlens, max_seqlen: int, labels=None, ignore_index: int = -100,
+                save_for_backward: bool = True):
+        """Returns (logits_or_None, loss_or_None).  input_ids int64 [T]; cu_seqlens int32 [B+1]."""
+        cfg = self.cfg
+        T = input_ids.numel()
+        root = self.units[0]
+        comm = self.comm
+        if comm is not None:
+            comm.pre_forward_unit(0)
+        h = K.embedding_fwd(input_ids, root.views["transformer.wte.weight"], 1.0 if cfg.m_emb is None else float(cfg.m_emb))
+        saved_layers = []
+        m_res = 1.0 if cfg.m_residual is None else float(cfg.m_residual)
+        for i in range(cfg.n_layer):
+            u = self.units[i + 1]
+            if comm is not None:
+                comm.pre_forward_unit(i + 1)
+            p = f"transformer.h.{i}."
+            x_in = h
+            ln1, rstd1 = K.rmsnorm_fwd(x_in, u.views[p + "ln_1.weight"], cfg.layer_norm_epsilon)
+            qkv = K.gemm(ln1, u.views[p + "attn.c_attn.weight"], bias=u.views.get(p + "attn.c_attn.bias"))
+            if self.rope_cos is not None:
+                K.rope_qk_inplace(qkv, self.n_groups, self.q_per_group, self.hd, self.rope_cos, self.rope_sin, position_ids)
+            attn, lse = K.attn_varlen_fwd(qkv, cu_seqlens, max_seqlen, self.n_groups, self.q_per_group, self.hd, self.softmax_scale)
+            h_mid = K.gemm(attn, u.views[p + "attn.c_proj.weight"], bias=u.views.get(p + "attn.c_proj.bias"), c=x_in,
+                           alpha=m_res, beta=1.0)
+            ln2, rstd2 = K.rmsnorm_fwd(h_mid, u.views[p + "ln_2.weight"], cfg.layer_norm_epsilon)
+            if self.is_moe:
+                from . import moe
+
+                h, moe_saved = moe.forward(self, u, p, ln2, h_mid, m_res)
+                layer = (x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, moe_saved)
+            else:
+                fc = K.gemm(ln2, u.views[p + "mlp.c_fc.weight"], bias=u.views.get(p + "mlp.c_fc.bias"))
+                act = K.swiglu_fwd(fc)
+                h = K.gemm(act, u.views[p + "mlp.c_proj.weight"], bias=u.views.get(p + "mlp.c_proj.bias"), c=h_mid,
+                           alpha=m_res, beta=1.0)
+                layer = (x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, fc, act)
+            if save_for_backward:
+                saved_layers.append(layer)
+            if comm is not None:
+                comm.post_forward_unit(i + 1)
+        hf, rstd_f = K.rmsnorm_fwd(h, root.views["transformer.ln_f.weight"], cfg.layer_norm_epsilon)
+        head = root.views["transformer.wte.weight"] if cfg.tie_word_embeddings else root.views["lm_head.weight"]
+        inv_width = 1.0 if cfg.m_width is None else 1.0 / float(cfg.m_width)
+        logits = K.gemm(hf, head, alpha=inv_width)
+        loss = None
+        if labels is not None:
+            # fused CE fwd+bwd: dlogits overwrites a copy only when the caller also wants the logits back
+            loss, _, dlogits = K.cross_entropy_fwd_bwd(logits, labels, ignore_index=ignore_index, dlogits=None)
+            logits_out = None
+        else:
+            dlogits = None
+            logits_out = logits
+        if save_for_backward:
+            self._saved = dict(input_ids=input_ids, position_ids=position_ids, cu_seqlens=cu_seqlens, max_seqlen=max_seqlen,
+                               layers=saved_layers, h_last=h, rstd_f=rstd_f, hf=hf, dlogits=dlogits, T=T)
+        return logits_out, loss
+
+    # ------------------------------------------------------------------------------------------
+    # backward
+    # ------------------------------------------------------------------------------------------
+    def _linear_bwd(self, unit: FlatUnit, wname: str, bname: str | None, x, dy, alpha: float = 1.0, need_dx: bool = True):
+        """autograd of y = alpha * (x W^T + b):  dx = alpha * dy W ; dW += alpha * dy^T x ; db += alpha * colsum(dy)"""
+        w = unit.views[wname]
+        gw = unit.gviews[wname]
+        dx = K.gemm(dy, w, b_mn=True, alpha=alpha) if need_dx else None
+        K.gemm(dy, x, a_mn=True, b_mn=True, out=gw, c=gw, alpha=alpha, beta=1.0)
+        if bname is not None and bname in unit.gviews:
+            K.colsum_accum(dy, unit.gviews[bname], alpha)
+        return dx
+
+    def backward(self, dlogits=None, grad_scale_dev=None) -> None:
+        """Backward of the last forward.  `dlogits` overrides the CE gradient (logits-mode autograd)."""
+        s = self._saved
+        if s is None:
+            raise RuntimeError("backward called without a saved forward")
+        cfg = self.cfg
+        root = self.units[0]
+        comm = self.comm
+        dl = dlogits if dlogits is not None else s["dlogits"]
+        if dl is None:
+            raise RuntimeError("no loss gradient available: forward was run without labels and no dlogits was given")
+        if grad_scale_dev is not None:
+            K.scale_by_device_scalar(dl, grad_scale_dev)
+        inv_width = 1.0 if cfg.m_width is None else 1.0 / float(cfg.m_width)
+        m_res = 1.0 if cfg.m_residual is None else float(cfg.m_residual)
+        head_name = "transformer.wte.weight" if cfg.tie_word_embeddings else "lm_head.weight"
+        if comm is not None:
+            comm.pre_backward_unit(0)
+        d_hf = self._linear_bwd(root, head_name, None, s["hf"], dl, alpha=inv_width)
+        dh = K.rmsnorm_bwd(d_hf, s["h_last"], root.views["transformer.ln_f.weight"], s["rstd_f"],
+                           root.gviews["transformer.ln_f.weight"])
+        del d_hf
+        for i in reversed(range(cfg.n_layer)):
+            u = self.units[i + 1]
+            if comm is not None:
+                comm.pre_backward_unit(i + 1)
+            p = f"transformer.h.{i}."
+            layer = s["layers"][i]
+            if self.is_moe:
+                from . import moe
+
+                x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, moe_saved = layer
+                d_ln2 = moe.backward(self, u, p, ln2, dh, m_res, moe_saved)
+            else:
+                x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, fc, act = layer
+                d_act = self._linear_bwd(u, p + "mlp.c_proj.weight", p + "mlp.c_proj.bias", act, dh, alpha=m_res)
+                d_fc = K.swiglu_bwd(d_act, fc)
+                del d_act
+                d_ln2 = self._linear_bwd(u, p + "mlp.c_fc.weight", p + "mlp.c_fc.bias", ln2, d_fc)
+                del d_fc
+            dh_mid = K.rmsnorm_bwd(d_ln2, h_mid, u.views[p + "ln_2.weight"], rstd2, u.gviews[p + "ln_2.weight"], dx_add=dh)
+            del d_ln2
+            d_attn = self._linear_bwd(u, p + "attn.c_proj.weight", p + "attn.c_proj.bias", attn, dh_mid, alpha=m_res)
+            dqkv = K.attn_varlen_bwd(d_attn, qkv, attn, lse, s["cu_seqlens"], s["max_seqlen"], self.n_groups,
+                                     self.q_per_group, self.hd, self.softmax_scale)
+            del d_attn
+            if self.rope_cos is not None:
+                K.rope_qk_inplace(dqkv, self.n_groups, self.q_per_group, self.hd, self.rope_cos, self.rope_sin,
+                                  s["position_ids"], inverse=True)
+            d_ln1 = self._linear_bwd(u, p + "attn.c_attn.weight", p + "attn.c_attn.bias", ln1, dqkv)
+            del dqkv
+            dh = K.rmsnorm_bwd(d_ln1, x_in, u.views[p + "ln_1.weight"], rstd1, u.gviews[p + "ln_1.weight"], dx_add=dh_mid)
+            del d_ln1, dh_mid
+            s["layers"][i] = None  # free this layer's activations
+            if comm is not None:
+                comm.post_backward_unit(i + 1)
+        K.embedding_bwd(s["input_ids"], dh, root.gviews["transformer.wte.weight"], 1.0 if cfg.m_emb is None else float(cfg.m_emb))
+        if comm is not None:
+            comm.post_backward_unit(0)
+        self._saved = None
+
+    # ------------------------------------------------------------------------------------------
+    # state dict (reference names)
+    # ------------------------------------------------------------------------------------------
+    def full_master(self, unit: FlatUnit) -> torch.Tensor:
+        if self.world_size == 1:
+            return unit.master.detach()
+        return self.comm.gather_master(unit)
+
+    def state_dict(self) -> dict:
+        out = {}
+        for u in self.units:
+            full = self.full_master(u)
+            for s in u.specs:
+                out[s.name] = full[s.offset : s.offset + s.numel].view(s.shape).clone()
+        if self.cfg.tie_word_embeddings:
+            pass  # lm_head.weight is tied: _tied_weights_keys (gpt_dolomite/main.py:12) -> not serialised
+        return out
+
+    def load_state_dict(self, sd: dict, strict: bool = True) -> None:
+        seen = set()
+        for u in self.units:
+            full = torch.zeros(u.padded, dtype=torch.float32)
+            for s in u.specs:
+                if s.name in sd:
+                    t = sd[s.name]
+                    if tuple(t.shape) != s.shape:
+                        raise ValueError(f"shape mismatch for {s.name}: {tuple(t.shape)} vs {s.shape}")
+                    full[s.offset : s.offset + s.numel].view(s.shape).copy_(t.detach().float().cpu())
+                    seen.add(s.name)
+                elif strict:
+                    raise KeyError(f"missing key {s.name} in state_dict")
+            u.full_master_from(full)
+        if strict:
+            extra = set(sd) - seen - ({"lm_head.weight"} if self.cfg.tie_word_embeddings else set())
+            if extra:
+                raise KeyError(f"unexpected keys in state_dict: {sorted(extra)[:5]}")
+
+    def refresh_compute_from_master(self) -> None:
+        """bf16 compute copy <- fp32 masters (world_size == 1; the sharded path all-gathers instead)"""
+        assert self.world_size == 1
+        for u in self.units:
+            K.cast_f32_to_bf16(u.master.data, u.compute)
+            u.gathered = True

@@ -1,0 +1,251 @@
+"""GPTDolomiteForCausalLM / MoEDolomiteForCausalLM behind the reference's construction + forward contract
+(hf_models/models/gpt_dolomite/{base,main}.py, hf_models/models/moe_dolomite/{base,main}.py).
+
+The module keeps the reference kwargs (`attn_implementation`, `use_padding_free_transformer`,
+`normalization_implementation`, `moe_implementation`, `torch_dtype`), input validation and state-dict names, but the
+computation is the explicit B200 engine (engine.py) -- there is no eager PyTorch path to fall back to.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+from dataclasses import dataclass
+
+import torch
+import torch.nn as nn
+
+from ..engine import DolomiteEngine
+from .config import CommonConfig, GPTDolomiteConfig, MoEDolomiteConfig, config_class_for
+from .utils import convert_padding_free_lists_to_tensors
+
+
+@dataclass
+class CausalLMOutputWithPast:
+    loss: torch.Tensor | None = None
+    logits: torch.Tensor | None = None
+    past_key_values: None = None
+    hidden_states: None = None
+    attentions: None = None
+    router_logits: None = None
+
+    def __getitem__(self, i):
+        return tuple(v for v in (self.loss, self.logits) if v is not None)[i]
+
+
+class _EngineFunction(torch.autograd.Function):
+    """Bridges autograd to the explicit engine: the only differentiable input is a dummy anchor; parameter gradients
+    are accumulated by the engine into its flat fp32 gradient buffers (exactly where FSDP would leave them)."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, input_ids, position_ids, cu_seqlens, max_seqlen, labels, ignore_index):
+        engine = model.engine
+        logits, loss = engine.forward(input_ids, position_ids, cu_seqlens, max_seqlen, labels=labels,
+                                      ignore_index=ignore_index, save_for_backward=torch.is_grad_enabled() or True)
+        ctx.model = model
+        ctx.loss_mode = labels is not None
+        return loss.reshape(()) if ctx.loss_mode else logits
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        model = ctx.model
+        engine = model.engine
+        if ctx.loss_mode:
+            # d(loss)/d(loss) arrives as a 0-d device tensor; it is 1 for `loss.backward()` (the only thing
+            # train_utils.train_step does).  Anything else is applied on the device, without a host sync.
+            scale = None if model.assume_unit_loss_grad else grad_out.reshape(1).float()
+            engine.backward(grad_scale_dev=scale)
+        else:
+            engine.backward(dlogits=grad_out.contiguous())
+        return (None,) * 8
+
+
+class DolomitePreTrainedModel(nn.Module):
+    config_class = CommonConfig
+    base_model_prefix = "transformer"
+    _no_split_modules = ["GPTDolomiteBlock"]
+    _tied_weights_keys = ["lm_head.weight"]
+
+    def __init__(self, config: CommonConfig, **kwargs) -> None:
+        super().__init__()
+        self.config = config
+        # ---- reference kwargs (gpt_dolomite/base.py:30-62, moe_dolomite/base.py:18-22) ----
+        self.attention_implementation = kwargs.pop("attn_implementation", "flash_attention_2")
+        self._use_padding_free_transformer = kwargs.pop("use_padding_free_transformer", True)
+        self.normalization_implementation = kwargs.pop("normalization_implementation", "torch")
+        self.moe_implementation = kwargs.pop("moe_implementation", "scattermoe")
+        kwargs.pop("torch_dtype", None)
+        kwargs.pop("trust_remote_code", None)
+        device = kwargs.pop("device", None)
+        world_size = kwargs.pop("world_size", 1)
+        rank = kwargs.pop("rank", 0)
+        seed = kwargs.pop("seed", 42)
+        if kwargs.pop("tensor_parallel_word_embeddings", False) or kwargs.pop("sequence_parallel", False):
+            raise NotImplementedError("tensor / sequence parallelism is out of scope of the data-parallel B200 path")
+        if kwargs:
+            raise TypeError(f"unexpected keyword arguments: {sorted(kwargs)}")
+        if self.attention_implementation not in ("flash_attention_2", "eager", "sdpa"):
+            raise ValueError(f"unexpected `attn_implementation` {self.attention_implementation}")
+        if not self._use_padding_free_transformer:
+            raise NotImplementedError(
+                "the B200 hot path is the padding-free transformer (use_padding_free_transformer=True); "
+                "padded-batch attention is a 'next' row of SURVEY.md section 8f"
+            )
+        if self.moe_implementation not in ("eager", "scattermoe"):
+            raise ValueError(f"unexpected `moe_implementation` {self.moe_implementation}")
+        if device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError(
+                    "dolomite_engine_b200 needs a CUDA device (sm_100a); there is no CPU path. "
+                    "Use oracle/ for CPU reference computations in tests."
+                )
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.engine = DolomiteEngine(config, device, world_size=world_size, rank=rank, seed=seed)
+        self.flat_params = nn.ParameterList([u.master for u in self.engine.units])
+        self._anchor = torch.zeros(1, device=device, requires_grad=True)
+        self.assume_unit_loss_grad = False
+        self.upcast_logits_for_loss = config.upcast_logits_for_loss
+        self.m_width = config.m_width
+
+    # ------------------------------------------------------------------------------------------
+    def prepare_inputs_for_model(self, input_ids, inputs_embeds, position_ids, token_type_ids, labels, cu_seqlens,
+                                 max_seqlen, past_key_values, attention_mask, use_cache, output_attentions):
+        """gpt_dolomite/base.py:68-115 (padding-free branch)"""
+        if isinstance(input_ids, list) or isinstance(inputs_embeds, list):
+            error_message = "{variable} should not be passed for flash attention when using List[List[int]] input types for input_ids"
+            assert cu_seqlens is None, error_message.format(variable="cu_seqlens")
+            assert max_seqlen is None, error_message.format(variable="max_seqlen")
+            assert attention_mask is None, error_message.format(variable="attention_mask")
+            input_ids, position_ids, token_type_ids, labels, cu_seqlens, max_seqlen = convert_padding_free_lists_to_tensors(
+                input_ids=input_ids, inputs_embeds=inputs_embeds, position_ids=position_ids,
+                token_type_ids=token_type_ids, labels=labels, device=self.engine.device,
+            )
+        else:
+            assert cu_seqlens is not None, "cu_seqlens needs to be specified when using tensor inputs with padding_free transformer"
+            assert position_ids is not None, "max_seqlen needs to be specified when specifying cu_seqlens"
+            assert max_seqlen is not None, "max_seqlen needs to be specified when specifying cu_seqlens"
+            assert attention_mask is None, "attention_mask should not be passed when specifying cu_seqlens"
+        if use_cache or past_key_values is not None:
+            raise NotImplementedError("KV caching is not supported with padding_free transformer")
+        assert not output_attentions
+        if inputs_embeds is not None:
+            raise NotImplementedError("inputs_embeds is not supported on the B200 padding-free path")
+        if token_type_ids is not None:
+            raise NotImplementedError("token_type_ids is not supported on the B200 padding-free path")
+        return input_ids, position_ids, token_type_ids, labels, cu_seqlens, max_seqlen
+
+    def forward(self, input_ids=None, past_key_values=None, attention_mask=None, token_type_ids=None, position_ids=None,
+                inputs_embeds=None, labels=None, use_cache=None, output_attentions=None, output_hidden_states=None,
+                return_dict=True, cu_seqlens=None, max_seqlen=None, output_router_logits=None):
+        if output_router_logits:
+            # moe_dolomite/main.py:47-48
+            raise NotImplementedError("router loss is not implemented with padding_free transformer")
+        assert not output_hidden_states, "output_hidden_states is not supported on the B200 path"
+        input_ids, position_ids, token_type_ids, labels, cu_seqlens, max_seqlen = self.prepare_inputs_for_model(
+            input_ids, inputs_embeds, position_ids, token_type_ids, labels, cu_seqlens, max_seqlen, past_key_values,
+            attention_mask, use_cache, output_attentions,
+        )
+        dev = self.engine.device
+        input_ids = input_ids.to(dev).reshape(-1).long().contiguous()
+        position_ids = position_ids.to(dev).reshape(-1).contiguous()
+        if position_ids.dtype not in (torch.int32, torch.int64):
+            position_ids = position_ids.long()
+        cu_seqlens = cu_seqlens.to(dev, torch.int32).contiguous()
+        if isinstance(max_seqlen, torch.Tensor):
+            max_seqlen = int(max_seqlen.item())  # the reference syncs here too (flash-attn takes a python int)
+        shift_labels = None
+        if labels is not None:
+            # gpt_dolomite/main.py:185-191 : logits[:-1] vs labels[1:], document-final positions dropped
+            labels = labels.to(dev).reshape(-1).long()
+            shift_labels = torch.full_like(labels, -100)
+            shift_labels[:-1] = labels[1:]
+            drop = (cu_seqlens[1:-1] - 1).long()
+            shift_labels[drop] = -100
+        out = _EngineFunction.apply(self._anchor, self, input_ids, position_ids, cu_seqlens, int(max_seqlen), shift_labels, -100)
+        if shift_labels is not None:
+            result = CausalLMOutputWithPast(loss=out, logits=None)
+        else:
+            result = CausalLMOutputWithPast(loss=None, logits=out)
+        if not return_dict:
+            return tuple(v for v in (result.loss, result.logits) if v is not None)
+        return result
+
+    # ---- pretraining entry: labels already aligned with positions (model_wrapper/pretraining.py:104-127) ----
+    def forward_pretraining_loss(self, input_ids, position_ids, cu_seqlens, max_seqlen: int, labels):
+        return _EngineFunction.apply(self._anchor, self, input_ids, position_ids, cu_seqlens, int(max_seqlen), labels, -100)
+
+    # ------------------------------------------------------------------------------------------
+    # state dict / (de)serialisation with the reference's names
+    # ------------------------------------------------------------------------------------------
+    def state_dict(self, *args, **kwargs):
+        return self.engine.state_dict()
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        self.engine.load_state_dict(state_dict, strict=strict)
+
+    def named_reference_parameters(self):
+        return self.engine.state_dict().items()
+
+    def get_input_embeddings(self):
+        return self.engine.units[0].views["transformer.wte.weight"]
+
+    def save_pretrained(self, path: str, safe_serialization: bool = True) -> None:
+        from safetensors.torch import save_file
+
+        os.makedirs(path, exist_ok=True)
+        self.config.save_pretrained(path)
+        sd = {k: v.contiguous().cpu() for k, v in self.engine.state_dict().items()}
+        save_file(sd, os.path.join(path, "model.safetensors"), metadata={"format": "pt"})
+
+    @classmethod
+    def from_pretrained(cls, path: str, **kwargs):
+        from ..utils.safetensors import SafeTensorsWeightsManager
+
+        with open(os.path.join(path, "config.json")) as f:
+            d = json.load(f)
+        config = config_class_for(d["model_type"]).from_dict(d)
+        model = cls(config, seed=None, **kwargs)
+        sd = SafeTensorsWeightsManager(path).state_dict()
+        model.load_state_dict(sd)
+        return model
+
+    def extra_repr(self) -> str:
+        return (
+            f"{type(self).__name__}(PaddingFreeAttention[tcgen05], RMSNorm[cuda], RoPE[cuda], "
+            f"{'ScatterMoE[tcgen05 grouped gemm]' if self.engine.is_moe else 'MLP[tcgen05 gemm]'}, "
+            f"params={self.engine.num_parameters():,})"
+        )
+
+
+class GPTDolomiteForCausalLM(DolomitePreTrainedModel):
+    config_class = GPTDolomiteConfig
+
+    def __init__(self, config: GPTDolomiteConfig, **kwargs) -> None:
+        assert config.model_type == "gpt_dolomite"
+        super().__init__(config, **kwargs)
+
+
+class MoEDolomiteForCausalLM(DolomitePreTrainedModel):
+    config_class = MoEDolomiteConfig
+    _no_split_modules = ["SparseMoEBlock"]
+
+    def __init__(self, config: MoEDolomiteConfig, **kwargs) -> None:
+        assert config.model_type == "moe_dolomite"
+        super().__init__(config, **kwargs)
+
+
+_MODEL_CLASSES = {"gpt_dolomite": GPTDolomiteForCausalLM, "moe_dolomite": MoEDolomiteForCausalLM}
+
+
+class AutoModelForCausalLM:
+    """`AutoModelForCausalLM.from_config / from_pretrained` dispatch of the reference (hf_models/register_hf.py:24-44)"""
+
+    @staticmethod
+    def from_config(config: CommonConfig, **kwargs):
+        return _MODEL_CLASSES[config.model_type](config, **kwargs)
+
+    @staticmethod
+    def from_pretrained(path: str, **kwargs):
+        with open(os.path.join(path, "config.json")) as f:
+            mt = json.load(f)["model_type"]
+        return _MODEL_CLASSES[mt].from_pretrained(path, **kwargs)

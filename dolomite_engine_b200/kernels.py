@@ -139,10 +139,15 @@ def cross_entropy_fwd_bwd(logits, labels, ignore_index=-100, logit_scale=1.0, gr
     return loss, loss_tok, dl
 
 
-def colsum_accum(x, out):
+def colsum_accum(x, out, scale: float = 1.0):
     _req(x, _BF16, "x"), _req(out, torch.float32, "out")
     T, N = x.shape
-    _lib.call("dolomite_b200_colsum_accum", x.data_ptr(), x.stride(0), out.data_ptr(), T, N, _stream())
+    _lib.call("dolomite_b200_colsum_accum", x.data_ptr(), x.stride(0), out.data_ptr(), T, N, scale, _stream())
+
+
+def scale_by_device_scalar(x, scale):
+    _req(x, _BF16, "x"), _req(scale, torch.float32, "scale")
+    _lib.call("dolomite_b200_scale_bf16_by_device_scalar", x.data_ptr(), x.numel(), scale.data_ptr(), _stream())
 
 
 def add_scaled(a, b, alpha: float, out=None):

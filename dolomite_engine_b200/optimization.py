@@ -1,0 +1,146 @@
+"""Optimizer + LR schedule of the training step (reference: optimization/optimizer.py:55-164,
+optimization/scheduler.py:50-219, defaults arguments.py:235-266).
+
+`DolomiteFusedAdamW` runs torch.optim.AdamW arithmetic as ONE hand-written kernel per flat shard
+(dolomite_b200_adamw_step): grad-clip coefficient read from a device scalar, fp32 master update and the bf16 copy
+for the next all-gather in the same pass.  `TorchAdamW` is accepted for drop-in compatibility."""
+
+from __future__ import annotations
+
+import math
+
+import torch
+from torch.optim import Optimizer
+from torch.optim.lr_scheduler import LambdaLR
+
+from . import kernels as K
+
+
+class DolomiteFusedAdamW(Optimizer):
+    def __init__(self, params, lr=1e-5, betas=(0.9, 0.95), eps=1e-10, weight_decay=0.1, model=None):
+        defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self.model = model  # ShardedDataParallel: provides the clip coefficient and the bf16 targets
+        self._step = 0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        assert closure is None
+        self._step += 1
+        sdp = self.model
+        engine = sdp.engine
+        by_ptr = {u.master.data_ptr(): u for u in engine.units}
+        clip = sdp.clip_coef
+        for group in self.param_groups:
+            b1, b2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["exp_avg"] = torch.zeros_like(p)
+                    st["exp_avg_sq"] = torch.zeros_like(p)
+                u = by_ptr[p.data_ptr()]
+                # world_size == 1: write the bf16 compute copy in the same pass; sharded: into own slice of the
+                # gather buffer is done by the all-gather prologue (cast), so skip here
+                pb = u.compute if engine.world_size == 1 else None
+                K.adamw_step(p.data, p.grad, st["exp_avg"], st["exp_avg_sq"], pb, group["lr"], b1, b2, group["eps"],
+                             group["weight_decay"], self._step, clip=clip)
+        sdp.clip_coef.fill_(1.0)
+        sdp.notify_fused_update()
+
+
+_OPTIMIZER_CLASSES = {"TorchAdamW": torch.optim.AdamW, "DolomiteFusedAdamW": DolomiteFusedAdamW}
+
+
+def get_optimizer(optimizer_class_name: str, optimizer_class_args: dict, model, params_group_method=None) -> Optimizer:
+    """optimization/optimizer.py:129-164"""
+    if optimizer_class_name not in _OPTIMIZER_CLASSES:
+        raise ValueError(
+            f"invalid class_name ({optimizer_class_name}) for optimizer; the B200 path provides {sorted(_OPTIMIZER_CLASSES)}"
+        )
+    if params_group_method is not None:
+        raise NotImplementedError("muP parameter groups are out of scope of the B200 hot path")
+    args = dict(optimizer_class_args)
+    if "betas" in args:
+        args["betas"] = tuple(args["betas"])
+    cls = _OPTIMIZER_CLASSES[optimizer_class_name]
+    params = list(model.parameters())
+    if cls is DolomiteFusedAdamW:
+        return cls(params, model=model, **args)
+    return cls(params, **args)
+
+
+def _linear(m, c, x):
+    return m * x + c
+
+
+def _cosine(a, b, t, x):
+    return a * (1 + math.cos(math.pi * x / t)) / 2 + b
+
+
+def _exponential(a, b, t, x):
+    return a * math.exp(-x / t) + b
+
+
+class _LRScheduler(LambdaLR):
+    def __init__(self, optimizer, num_warmup_steps, num_constant_steps, num_decay_steps, num_training_steps,
+                 lr_decay_factor, last_epoch=-1):
+        self.lr_warmup_boundary = num_warmup_steps
+        self.lr_constant_boundary = self.lr_warmup_boundary + num_constant_steps
+        self.lr_decay_boundary = num_training_steps
+        if num_decay_steps is not None:
+            self.lr_decay_boundary = self.lr_constant_boundary + num_decay_steps
+        self.lr_decay_factor = lr_decay_factor
+        super().__init__(optimizer, lr_lambda=self._lr_lambda, last_epoch=last_epoch)
+
+    def _decay(self, x, t):
+        raise NotImplementedError
+
+    def _lr_lambda(self, num_steps: int) -> float:
+        if self.lr_warmup_boundary > 0 and num_steps <= self.lr_warmup_boundary:
+            return _linear(m=1 / self.lr_warmup_boundary, c=0, x=num_steps)
+        if num_steps <= self.lr_constant_boundary:
+            return 1
+        if num_steps <= self.lr_decay_boundary:
+            return self._decay(num_steps - self.lr_constant_boundary, self.lr_decay_boundary - self.lr_constant_boundary)
+        return self.lr_decay_factor
+
+
+class ConstantScheduler(_LRScheduler):
+    def _lr_lambda(self, num_steps: int) -> float:
+        if self.lr_warmup_boundary > 0 and num_steps <= self.lr_warmup_boundary:
+            return _linear(m=1 / self.lr_warmup_boundary, c=0, x=num_steps)
+        return 1
+
+
+class CosineScheduler(_LRScheduler):
+    def _decay(self, x, t):
+        return _cosine(a=1 - self.lr_decay_factor, b=self.lr_decay_factor, t=t, x=x)
+
+
+class ExponentialScheduler(_LRScheduler):
+    def _decay(self, x, t):
+        return _exponential(a=1, b=0, t=t / math.log(1 / self.lr_decay_factor), x=x)
+
+
+class LinearScheduler(_LRScheduler):
+    def _decay(self, x, t):
+        return _linear(m=(self.lr_decay_factor - 1) / t, c=1, x=x)
+
+
+_LR_SCHEDULER_CLASSES = {"constant": ConstantScheduler, "cosine": CosineScheduler, "exponential": ExponentialScheduler,
+                         "linear": LinearScheduler}
+
+
+def get_scheduler(optimizer, num_warmup_steps, num_constant_steps, num_decay_steps, num_training_steps, lr_decay_style,
+                  lr_decay_factor, extra_lr_scheduler_args=None, last_epoch=-1) -> LambdaLR:
+    """optimization/scheduler.py:193-219"""
+    style = str(getattr(lr_decay_style, "value", lr_decay_style))
+    if style not in _LR_SCHEDULER_CLASSES:
+        raise ValueError(f"invalid lr_decay_style ({lr_decay_style})")
+    return _LR_SCHEDULER_CLASSES[style](
+        optimizer, num_warmup_steps=num_warmup_steps, num_constant_steps=num_constant_steps,
+        num_decay_steps=num_decay_steps, num_training_steps=num_training_steps, lr_decay_factor=lr_decay_factor,
+        **(extra_lr_scheduler_args or {}), last_epoch=last_epoch,
+    )

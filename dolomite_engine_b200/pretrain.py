@@ -1,0 +1,126 @@
+"""`python -m dolomite_engine_b200.pretrain --config <yaml>` -- the reference's pretraining entry point
+(pretrain.py:60-371) for the data-parallel hot path: args -> process group -> model wrapper -> sharded wrap ->
+optimizer / scheduler -> train loop over `train_step`.
+
+The data layer (Megatron mmap datasets) is out of scope; the loop consumes any iterator
+of `{"text": LongTensor[mbs, seq+1]}` batches -- exactly what `GPTDataset` emits (gpt_dataset.py:83-98) -- and ships
+`SyntheticPackedDataset` (class_name in the YAML) that fabricates such batches with the seeds of SURVEY section 8d.
+"""
+
+from __future__ import annotations
+
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+from .arguments import TrainingArgs, get_args
+from .distributed import wrap_model_for_distributed_training
+from .model_wrapper import get_model
+from .optimization import get_optimizer, get_scheduler
+from .train_utils import get_model_tflops, train_step
+
+
+class SyntheticPackedDataset:
+    """tokens = randint(0, V, (mbs, S+1), manual_seed(1234 + rank)), optionally with EOS injected at seeded
+    log-uniform positions (ragged packing)."""
+
+    def __init__(self, vocab_size: int, micro_batch_size: int, sequence_length: int, rank: int = 0, eos_token_id: int | None = None,
+                 ragged: bool = False, pin: bool = True):
+        self.V, self.mbs, self.S = vocab_size, micro_batch_size, sequence_length
+        self.gen = torch.Generator().manual_seed(1234 + rank)
+        self.eos = eos_token_id
+        self.ragged = ragged
+        self.pin = pin and torch.cuda.is_available()
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> dict:
+        t = torch.randint(0, self.V, (self.mbs, self.S + 1), generator=self.gen, dtype=torch.int64)
+        if self.ragged and self.eos is not None:
+            t[t == self.eos] = (self.eos + 1) % self.V
+            for r in range(self.mbs):
+                pos = 0
+                while True:
+                    u = torch.rand(1, generator=self.gen).item()
+                    step = int(64 * (self.S / 64) ** u)  # log-uniform in [64, S]
+                    pos += step
+                    if pos >= self.S:
+                        break
+                    t[r, pos] = self.eos
+        if self.pin:
+            t = t.pin_memory()
+        return {"text": t}
+
+
+def init_distributed() -> tuple[int, int, int]:
+    """utils/__init__.py:28-58 / utils/parallel.py:46-79 (DP group only)"""
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group(backend="nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def build(args: TrainingArgs):
+    rank, world, local = init_distributed()
+    torch.manual_seed(args.random_args.seed)
+    device = torch.device("cuda", local)
+    wrapper = get_model(args, device=device, world_size=world, rank=rank)
+    model = wrap_model_for_distributed_training(args, wrapper)
+    optimizer = get_optimizer(args.optimizer_args.class_name, args.optimizer_args.class_args, model,
+                              args.optimizer_args.params_group_method)
+    ls = args.lr_scheduler_args
+    scheduler = get_scheduler(optimizer, ls.num_warmup_steps, ls.num_constant_steps, ls.num_decay_steps,
+                              args.training_parameters.num_training_steps, ls.lr_decay_style, ls.lr_decay_factor,
+                              ls.extra_lr_scheduler_args)
+    return model, optimizer, scheduler, (rank, world, local)
+
+
+def make_dataloader(args: TrainingArgs, model, rank: int):
+    ds = args.datasets[0]
+    if ds.class_name != "SyntheticPackedDataset":
+        raise NotImplementedError(
+            f"dataset class {ds.class_name}: the Megatron data layer is out of scope of the B200 hot path "
+            "(SURVEY.md section 8f rank 2); use class_name: SyntheticPackedDataset or pass your own iterator to train()"
+        )
+    cfg = model.config
+    return SyntheticPackedDataset(cfg.vocab_size, args.training_parameters.micro_batch_size,
+                                  ds.class_args["sequence_length"], rank=rank, eos_token_id=cfg.eos_token_id,
+                                  ragged=bool(ds.class_args.get("ragged", False)))
+
+
+def train(args: TrainingArgs, model, optimizer, scheduler, dataloader, rank: int, world: int) -> list[float]:
+    tp = args.training_parameters
+    seq = args.datasets[0].class_args["sequence_length"]
+    tflop_per_step = get_model_tflops(model.config, tp.micro_batch_size * tp.gradient_accumulation_steps, seq)
+    losses = []
+    t0 = time.perf_counter()
+    for step in range(1, tp.num_training_steps + 1):
+        loss, grad_norm = train_step(model, optimizer, scheduler, train_dataloader=dataloader,
+                                     gradient_accumulation_steps=tp.gradient_accumulation_steps,
+                                     gradient_clipping=tp.gradient_clipping)
+        losses.append(loss)
+        if rank == 0 and step % args.logging_args.log_interval == 0:
+            dt = (time.perf_counter() - t0) / step
+            print(f"step {step}: loss {loss:.4f} grad_norm {grad_norm:.4f} lr {scheduler.get_last_lr()[0]:.3e} "
+                  f"step_time {dt:.3f}s FLOPS {tflop_per_step / dt:.1f} TFLOP/s/GPU", flush=True)
+    return losses
+
+
+def main() -> None:
+    args = get_args()
+    model, optimizer, scheduler, (rank, world, _) = build(args)
+    dl = make_dataloader(args, model, rank)
+    train(args, model, optimizer, scheduler, dl, rank, world)
+    if dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -90,9 +90,12 @@ int dolomite_b200_cross_entropy_fwd_bwd(const void* logits, int64_t ldl, const i
                                         int64_t ignore_index, float logit_scale, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Column sum (bias gradient of nn.Linear, autograd of linear.py:5-25):  out[n] += sum_t x[t, n]
+ * Column sum (bias gradient of nn.Linear, autograd of linear.py:5-25):  out[n] += scale * sum_t x[t, n]
  * ------------------------------------------------------------------------------------------------ */
-int dolomite_b200_colsum_accum(const void* x, int64_t ldx, float* out, int64_t T, int64_t N, void* stream);
+int dolomite_b200_colsum_accum(const void* x, int64_t ldx, float* out, int64_t T, int64_t N, float scale,
+                               void* stream);
+/* x[i] *= scale[0]  (bf16 in place; scale is a DEVICE scalar: upstream gradient of the loss) */
+int dolomite_b200_scale_bf16_by_device_scalar(void* x, int64_t n, const float* scale, void* stream);
 
 /* out = a + alpha * b  (bf16; residual adds of gpt_dolomite/layer.py:70-85), a/b/out may alias */
 int dolomite_b200_add_scaled(const void* a, const void* b, void* out, float alpha, int64_t n, void* stream);
@@ -117,7 +120,7 @@ int dolomite_b200_accum_bf16_into_f32(const void* src, float* dst, float scale, 
  * calls behind nn.Linear (linear.py:5-25; call sites attention/base.py:100, padding_free.py:74,
  * gpt_dolomite/mlp.py:46-48, gpt_dolomite/main.py:172-177) and their autograd (dgrad / wgrad).
  *
- *   D[M,N] = alpha * sum_k A[m,k] * B[n,k]  + bias[n] + beta * C[m,n]
+ *   D[M,N] = alpha * (sum_k A[m,k] * B[n,k] + bias[n]) + beta * C[m,n]
  *
  *   A is logical [M,K]: a_mn_major == 0 -> stored row-major [M,K] (ld = lda);  1 -> stored [K,M] (ld = lda).
  *   B is logical [N,K]: b_mn_major == 0 -> stored row-major [N,K] (ld = ldb);  1 -> stored [K,N] (ld = ldb).

@@ -1,0 +1,161 @@
+"""CPU: host-side logic of the drop-in boundary -- config surface, YAML argument tree, integer bookkeeping (bit-exact
+against the oracle), flat-unit layout, LR schedules, safetensors manager."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle.dolomite_oracle as O
+from dolomite_engine_b200.arguments import get_args_from_dict, load_yaml
+from dolomite_engine_b200.engine import FlatUnit, _block_specs, _root_specs, check_supported
+from dolomite_engine_b200.hf_models import GPTDolomiteConfig, MoEDolomiteConfig
+from dolomite_engine_b200.hf_models.config import CommonConfig
+from dolomite_engine_b200.hf_models.utils import prepare_pretraining_inputs_host
+from dolomite_engine_b200.optimization import get_scheduler
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_config_defaults_aliases_and_validation(tmp_path):
+    c = GPTDolomiteConfig()
+    assert c.n_inner == 4 * c.n_embd and c.attention_head_type == "mqa" and c.num_key_value_heads == 1
+    assert c.hidden_size == c.n_embd and c.num_hidden_layers == c.n_layer and c.max_position_embeddings == c.n_positions
+    c2 = GPTDolomiteConfig(hidden_size=128, num_attention_heads=8, attention_head_type="gqa", num_key_value_heads=2)
+    assert c2.n_embd == 128 and c2.n_head == 8
+    with pytest.raises(AssertionError):
+        GPTDolomiteConfig(attention_head_type="gqa")
+    with pytest.raises(AssertionError):
+        GPTDolomiteConfig(attention_head_type="mha", n_head=8, num_key_value_heads=2)
+    with pytest.raises(ValueError):
+        GPTDolomiteConfig(position_embedding_type="bogus")
+    c2.save_pretrained(str(tmp_path))
+    c3 = CommonConfig.from_pretrained(str(tmp_path))
+    assert isinstance(c3, GPTDolomiteConfig) and c3.to_dict() == c2.to_dict()
+    m = MoEDolomiteConfig(num_experts=4, num_experts_per_tok=1, n_embd=64, n_head=4, attention_head_type="mha")
+    assert m.model_type == "moe_dolomite" and m.to_dict()["num_experts"] == 4
+
+
+def test_unsupported_configs_fail_loudly():
+    ok = GPTDolomiteConfig(n_embd=256, n_head=4, attention_head_type="mha", position_embedding_type="rope",
+                           activation_function="swiglu", normalization_function="rmsnorm", resid_pdrop=0, embd_pdrop=0,
+                           attn_pdrop=0, vocab_size=2048)
+    check_supported(ok)
+    for kw in (dict(position_embedding_type="alibi"), dict(normalization_function="layernorm"),
+               dict(activation_function="gelu_pytorch_tanh"), dict(attn_pdrop=0.1), dict(n_head=32, num_key_value_heads=32)):
+        d = ok.to_dict()
+        d.update(kw)
+        with pytest.raises(NotImplementedError):
+            check_supported(GPTDolomiteConfig.from_dict(d))
+
+
+@pytest.mark.parametrize("ram,rpi", [(False, False), (True, False), (True, True)])
+def test_pretraining_bookkeeping_bit_exact(ram, rpi):
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        tokens = rng.integers(0, 50, size=(3, 65), dtype=np.int64)
+        eos = 7
+        inp, lab = O.split_tokens(tokens)
+        ref = O.prepare_model_inputs(inp.copy(), eos, ram, rpi)
+        got = prepare_pretraining_inputs_host(tokens, eos, ram, rpi)
+        assert np.array_equal(got["input_ids"], ref["input_ids"])
+        assert np.array_equal(got["labels"], np.ascontiguousarray(lab).reshape(-1))
+        assert np.array_equal(got["cu_seqlens"], ref["cu_seqlens"]) and got["cu_seqlens"].dtype == np.int32
+        assert np.array_equal(got["position_ids"], ref["position_ids"])
+        assert got["position_ids"].dtype == ref["position_ids"].dtype
+        assert got["max_seqlen"] == ref["max_seqlen"]
+
+
+def test_bookkeeping_edge_cases():
+    # every token is EOS -> documents of length 1; and EOS at the row boundary
+    tokens = np.full((2, 9), 7, dtype=np.int64)
+    got = prepare_pretraining_inputs_host(tokens, 7, True, True)
+    assert np.array_equal(got["cu_seqlens"], np.arange(0, 17, dtype=np.int32))
+    assert got["max_seqlen"] == 1 and np.all(got["position_ids"] == 0)
+    tokens = np.arange(18, dtype=np.int64).reshape(2, 9) + 100
+    got = prepare_pretraining_inputs_host(tokens, 7, True, True)
+    assert np.array_equal(got["cu_seqlens"], np.array([0, 8, 16], dtype=np.int32)) and got["max_seqlen"] == 8
+
+
+def test_flat_unit_layout_and_sharding():
+    cfg = GPTDolomiteConfig(n_embd=64, n_head=4, n_layer=2, n_inner=128, vocab_size=256, attention_head_type="gqa",
+                            num_key_value_heads=2, add_bias=True, activation_function="swiglu")
+    specs = _block_specs(cfg, 0)
+    names = [s[0] for s in specs]
+    assert names[0] == "transformer.h.0.ln_1.weight" and "transformer.h.0.mlp.c_fc.bias" in names
+    shapes = dict((s[0], s[1]) for s in specs)
+    assert shapes["transformer.h.0.attn.c_attn.weight"] == (64 + 2 * 2 * 16, 64)  # H + 2*nkv*hd
+    assert shapes["transformer.h.0.mlp.c_fc.weight"] == (256, 64)  # 2F for GLU
+    for ws in (1, 2, 8):
+        u = FlatUnit("h.0", specs, world_size=ws, rank=0)
+        assert u.padded % (ws * 64) == 0 and u.shard_numel * ws == u.padded
+        offs = [(s.offset, s.numel) for s in u.specs]
+        for (o1, n1), (o2, _) in zip(offs, offs[1:]):
+            assert o1 + n1 <= o2 and o2 % 64 == 0  # no overlap, 128-byte aligned
+    assert [s[0] for s in _root_specs(cfg)] == ["transformer.wte.weight", "transformer.ln_f.weight"]
+    cfg.tie_word_embeddings = False
+    assert _root_specs(cfg)[-1][0] == "lm_head.weight"
+
+
+def test_yaml_argument_tree():
+    a = get_args_from_dict(load_yaml(os.path.join(ROOT, "configs", "c2_granite3b_shape.yml")))
+    assert a.model_args.pretrained_config["n_embd"] == 2560 and a.optimizer_args.class_args["lr"] == 1e-5
+    assert a.datasets[0].class_args["sequence_length"] == 4096
+    bad = load_yaml(os.path.join(ROOT, "configs", "c1_tiny.yml"))
+    bad["model_args"]["bogus_key"] = 1
+    with pytest.raises(Exception):  # extra="forbid"
+        get_args_from_dict(bad)
+    ds = load_yaml(os.path.join(ROOT, "configs", "c1_tiny.yml"))
+    ds["distributed_args"]["distributed_backend"] = "deepspeed"
+    with pytest.raises(NotImplementedError):
+        get_args_from_dict(ds)
+
+
+def test_cosine_schedule_matches_reference_formula():
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=1.0)
+    s = get_scheduler(opt, 4, 2, None, 20, "cosine", 0.1)
+    lrs = []
+    for _ in range(22):
+        lrs.append(s.get_last_lr()[0])
+        opt.step()
+        s.step()
+    assert lrs[0] == 0 and abs(lrs[4] - 1.0) < 1e-12 and abs(lrs[6] - 1.0) < 1e-12
+    import math
+
+    x, t = 10 - 6, 20 - 6
+    assert abs(lrs[10] - (0.9 * (1 + math.cos(math.pi * x / t)) / 2 + 0.1)) < 1e-12
+    assert abs(lrs[21] - 0.1) < 1e-12
+
+
+def test_safetensors_manager_roundtrip(tmp_path):
+    from dolomite_engine_b200.utils.safetensors import SafeTensorsWeightsManager
+
+    sd = {"a.weight": torch.randn(4, 8), "b.bias": torch.arange(5, dtype=torch.float32)}
+    SafeTensorsWeightsManager.save_state_dict(sd, str(tmp_path))
+    m = SafeTensorsWeightsManager(str(tmp_path))
+    assert len(m) == 2 and m.has_tensor("a.weight") and list(m.get_shape("a.weight")) == [4, 8]
+    assert torch.equal(m.get_tensor("b.bias"), sd["b.bias"]) and m == SafeTensorsWeightsManager(str(tmp_path))
+
+
+def test_product_path_never_imports_the_oracle():
+    import subprocess
+    import sys
+
+    code = ("import sys; import dolomite_engine_b200.engine, dolomite_engine_b200.kernels, dolomite_engine_b200.distributed, "
+            "dolomite_engine_b200.model_wrapper, dolomite_engine_b200.pretrain, dolomite_engine_b200.hf_models; "
+            "assert not any(m.startswith('oracle') for m in sys.modules), 'oracle imported by the product path'")
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+
+
+def test_no_gpu_means_loud_failure():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from dolomite_engine_b200.hf_models import GPTDolomiteForCausalLM
+
+    cfg = GPTDolomiteConfig(n_embd=256, n_head=4, attention_head_type="mha", position_embedding_type="rope",
+                            activation_function="swiglu", normalization_function="rmsnorm", resid_pdrop=0, embd_pdrop=0,
+                            attn_pdrop=0, vocab_size=2048, n_layer=1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        GPTDolomiteForCausalLM(cfg)
