@@ -90,9 +90,31 @@ def check(rc: int, what: str = "") -> None:
         raise DolomiteB200Error(f"{what}: rc={rc}: {msg.decode() if msg else '?'}")
 
 
+# kernels launched per successful call of each entry point (for bench.py's `gpu_launches` accounting)
+KERNELS_PER_CALL = {
+    "dolomite_b200_rmsnorm_fwd": 1, "dolomite_b200_rmsnorm_bwd": 2, "dolomite_b200_rope_qk_inplace": 1,
+    "dolomite_b200_swiglu_fwd": 1, "dolomite_b200_swiglu_bwd": 1, "dolomite_b200_embedding_fwd": 1,
+    "dolomite_b200_embedding_bwd": 1, "dolomite_b200_cross_entropy_fwd_bwd": 3, "dolomite_b200_colsum_accum": 1,
+    "dolomite_b200_scale_bf16_by_device_scalar": 1, "dolomite_b200_add_scaled": 1, "dolomite_b200_sumsq_accum": 1,
+    "dolomite_b200_clip_coef": 1, "dolomite_b200_adamw_step": 1, "dolomite_b200_cast_f32_to_bf16": 1,
+    "dolomite_b200_accum_bf16_into_f32": 1, "dolomite_b200_gemm_bf16": 1, "dolomite_b200_attn_varlen_fwd": 1,
+    "dolomite_b200_attn_varlen_bwd": 3,
+}
+launch_counts: dict[str, int] = {}
+
+
+def reset_launch_counts() -> None:
+    launch_counts.clear()
+
+
+def total_kernel_launches() -> int:
+    return sum(KERNELS_PER_CALL.get(k, 1) * v for k, v in launch_counts.items())
+
+
 def call(name: str, *args):
     """Call an int-status entry point and raise on failure."""
     lib = load()
+    launch_counts[name] = launch_counts.get(name, 0) + 1
     rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.dolomite_b200_last_error()

@@ -90,8 +90,9 @@ class FlatUnit:
         self.gathered = True
 
     def init_full(self, generator: torch.Generator) -> torch.Tensor:
-        """reference init rules, on the CPU in fp32 so that every rank draws the same values"""
-        full = torch.zeros(self.padded, dtype=torch.float32)
+        """reference init rules in fp32; every rank draws the same values (same seed, same
+        generator device).  CPU generator = reproducible against the oracle; CUDA generator = fast for big models."""
+        full = torch.zeros(self.padded, dtype=torch.float32, device=generator.device)
         for s in self.specs:
             v = full[s.offset : s.offset + s.numel].view(s.shape)
             if s.init == "ones":
@@ -100,7 +101,7 @@ class FlatUnit:
                 v.zero_()
             else:
                 std = float(s.init.split(":")[1])
-                v.copy_(torch.randn(s.shape, generator=generator) * std)
+                v.copy_(torch.randn(s.shape, generator=generator, device=generator.device) * std)
         return full
 
 
@@ -182,7 +183,8 @@ def check_supported(cfg: CommonConfig) -> None:
 class DolomiteEngine:
     """Owns the flat units of one model replica/shard and runs the explicit forward / backward."""
 
-    def __init__(self, cfg: CommonConfig, device, world_size: int = 1, rank: int = 0, seed: int | None = 42):
+    def __init__(self, cfg: CommonConfig, device, world_size: int = 1, rank: int = 0, seed: int | None = 42,
+                 init_on_device: bool = False):
         check_supported(cfg)
         self.cfg = cfg
         self.device = torch.device(device)
@@ -198,7 +200,7 @@ class DolomiteEngine:
         for u in self.units:
             u.allocate(self.device)
         if seed is not None:
-            g = torch.Generator().manual_seed(seed)
+            g = torch.Generator(device=self.device if init_on_device else "cpu").manual_seed(seed)
             for u in self.units:
                 u.full_master_from(u.init_full(g))
         self._setup_rope()

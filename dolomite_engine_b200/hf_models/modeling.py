@@ -80,6 +80,7 @@ class DolomitePreTrainedModel(nn.Module):
         world_size = kwargs.pop("world_size", 1)
         rank = kwargs.pop("rank", 0)
         seed = kwargs.pop("seed", 42)
+        init_on_device = kwargs.pop("init_on_device", False)
         if kwargs.pop("tensor_parallel_word_embeddings", False) or kwargs.pop("sequence_parallel", False):
             raise NotImplementedError("tensor / sequence parallelism is out of scope of the data-parallel B200 path")
         if kwargs:
@@ -100,7 +101,7 @@ class DolomitePreTrainedModel(nn.Module):
                     "Use oracle/ for CPU reference computations in tests."
                 )
             device = torch.device("cuda", torch.cuda.current_device())
-        self.engine = DolomiteEngine(config, device, world_size=world_size, rank=rank, seed=seed)
+        self.engine = DolomiteEngine(config, device, world_size=world_size, rank=rank, seed=seed, init_on_device=init_on_device)
         self.flat_params = nn.ParameterList([u.master for u in self.engine.units])
         self._anchor = torch.zeros(1, device=device, requires_grad=True)
         self.assume_unit_loss_grad = False

@@ -189,7 +189,8 @@ def accum_bf16_into_f32(src, dst, scale=1.0):
 # GEMM (nn.Linear fwd / dgrad / wgrad; linear.py:5-25)
 # ------------------------------------------------------------------------------------------------
 GEMM_TMA_STORE = 1
-_default_gemm_flags = 0
+_default_gemm_flags = GEMM_TMA_STORE
+gemm_timer = None  # bench.py: list collecting (flops, start_event, end_event) per GEMM launch
 
 
 def set_default_gemm_flags(flags: int) -> None:
@@ -221,11 +222,17 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=_BF16, c=None, alp
         flags = _default_gemm_flags
         if d_is_f32 or c is not None:
             flags &= ~GEMM_TMA_STORE
+    if gemm_timer is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.call(
         "dolomite_b200_gemm_bf16", a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn),
         out.data_ptr(), out.stride(0), d_is_f32, _ptr(c), 0 if c is None else c.stride(0), alpha, beta, _ptr(bias),
         M, N, K, flags, _stream(),
     )
+    if gemm_timer is not None:
+        e1.record()
+        gemm_timer.append((2.0 * M * N * K, e0, e1))
     return out
 
 

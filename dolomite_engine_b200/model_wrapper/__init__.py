@@ -42,6 +42,7 @@ class ModelWrapper(nn.Module):
         device=None,
         world_size: int = 1,
         rank: int = 0,
+        init_on_device: bool = False,
     ) -> None:
         super().__init__()
         self.mode = mode
@@ -68,7 +69,7 @@ class ModelWrapper(nn.Module):
         self._setup_tokenizer()
         kwargs = dict(attn_implementation=self.attention_implementation,
                       use_padding_free_transformer=self.use_padding_free_transformer,
-                      device=device, world_size=world_size, rank=rank, seed=random_seed)
+                      device=device, world_size=world_size, rank=rank, seed=random_seed, init_on_device=init_on_device)
         if moe_implementation is not None:
             kwargs["moe_implementation"] = moe_implementation
         if normalization_implementation is not None:

@@ -1,0 +1,239 @@
+"""GPU parity tests of the whole hot path: GPTDolomiteForCausalLM / ModelWrapperForPretraining on the B200 kernels
+against (a) the committed golden vectors generated from the reference's leaf modules and (b) the CPU oracle, on
+identical weights and tokens.  Tolerances: loss <= 1e-3 relative (north_star); logits within the reference's own
+bf16 tolerance rtol 5e-3 / atol 5e-3 (tests/hf_models/single_gpu/hf_models/gpt_dolomite_test.py:128-136); integer
+bookkeeping bit exact."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle.dolomite_oracle as O
+from oracle.validate_against_reference import CONFIGS
+
+pytestmark = pytest.mark.gpu
+
+GPU_CONFIGS = {k: v for k, v in CONFIGS.items() if v.get("activation_function", "swiglu") == "swiglu"}
+GPU_CONFIGS["hd80_bias"] = dict(vocab_size=1024, n_positions=512, n_embd=320, n_layer=2, n_head=4, n_inner=640,
+                                attention_head_type="mha", add_bias=True)
+GPU_CONFIGS["hd128_gqa"] = dict(vocab_size=1024, n_positions=512, n_embd=512, n_layer=1, n_head=4, num_key_value_heads=2,
+                                n_inner=1024, attention_head_type="gqa", add_bias=False, tie_word_embeddings=False)
+
+
+def oracle_params(cfg):
+    p = O.init_params(cfg, seed=42)
+    if cfg.add_bias:
+        g = torch.Generator().manual_seed(7)
+        for k in p:
+            if k.endswith(".bias"):
+                p[k] = torch.randn(p[k].shape, generator=g) * 0.02
+    return p
+
+
+def gpu_config(kw):
+    from dolomite_engine_b200.hf_models import GPTDolomiteConfig
+
+    d = dict(position_embedding_type="rope", normalization_function="rmsnorm", activation_function="swiglu",
+             resid_pdrop=0, embd_pdrop=0, attn_pdrop=0, eos_token_id=7)
+    d.update(kw)
+    return GPTDolomiteConfig(**d)
+
+
+def build_model(name):
+    from dolomite_engine_b200.hf_models import GPTDolomiteForCausalLM
+
+    kw = GPU_CONFIGS[name]
+    ocfg = O.OracleConfig(**kw)
+    params = oracle_params(ocfg)
+    model = GPTDolomiteForCausalLM(gpu_config(kw), seed=None)
+    model.load_state_dict(params)
+    return model, ocfg, params
+
+
+def rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def sample_tokens(ocfg, mbs=2, seq=64, seed=1234):
+    rng = np.random.default_rng(seed)
+    t = rng.integers(0, ocfg.vocab_size, size=(mbs, seq + 1), dtype=np.int64)
+    t[0, 20] = 7
+    t[1, 5] = 7
+    t[1, 40] = 7
+    return t
+
+
+@pytest.mark.parametrize("name", list(GPU_CONFIGS))
+@pytest.mark.parametrize("ragged", [False, True])
+def test_logits_and_loss_match_oracle(name, ragged):
+    model, ocfg, params = build_model(name)
+    tokens = sample_tokens(ocfg)
+    inp, labels = O.split_tokens(tokens)
+    b = O.prepare_model_inputs(inp.copy(), 7, ragged, ragged)
+    ref32 = O.forward_logits(params, ocfg, b["input_ids"], b["position_ids"], b["cu_seqlens"])
+    ref16 = O.forward_logits(params, ocfg, b["input_ids"], b["position_ids"], b["cu_seqlens"], bf16=True)
+    out = model(input_ids=torch.from_numpy(b["input_ids"]).cuda(), position_ids=torch.from_numpy(b["position_ids"]).cuda(),
+                cu_seqlens=torch.from_numpy(b["cu_seqlens"]).cuda(), max_seqlen=b["max_seqlen"])
+    logits = out.logits.float().cpu()
+    # the reference's own bf16 tolerance for logits
+    assert torch.allclose(logits, ref32, rtol=5e-3, atol=5e-3), (logits - ref32).abs().max()
+    # against the bf16-emulated oracle the only differences are accumulation order / fused roundings
+    assert rel_l2(logits, ref16) < 6e-3
+    lab = torch.from_numpy(np.ascontiguousarray(labels).reshape(-1))
+    loss_ref = torch.nn.functional.cross_entropy(ref32, lab).item()
+    loss_gpu = torch.nn.functional.cross_entropy(logits, lab).item()
+    assert abs(loss_gpu - loss_ref) / loss_ref < 1e-3
+
+
+@pytest.mark.parametrize("mode", ["uniform", "ragged"])
+def test_pretraining_wrapper_loss_matches_golden_c1(golden_dir, mode):
+    from dolomite_engine_b200.model_wrapper import ModelWrapperForPretraining
+
+    fx = np.load(os.path.join(golden_dir, "model_c1.npz"))
+    kw = CONFIGS["c1"]
+    ocfg = O.OracleConfig(**kw)
+    cfgd = gpu_config(kw).to_dict()
+    w = ModelWrapperForPretraining(pretrained_config=cfgd, micro_batch_size=2, sequence_length=128,
+                                   reset_attention_mask=mode == "ragged", reset_position_ids=mode == "ragged")
+    w.model.load_state_dict(oracle_params(ocfg))
+    w.eos_token_id = int(fx["eos"])
+    tokens = torch.from_numpy(fx["tokens"])
+    loss = w({"text": tokens})
+    torch.cuda.synchronize()
+    golden = float(fx[f"{mode}_loss"])
+    assert abs(loss.item() - golden) / golden < 1e-3  # north_star: loss within 1e-3 relative of the reference
+    # integer bookkeeping that reached the device is bit exact with the reference-derived fixture
+    T = 2 * 128
+    nb = fx[f"{mode}_cu_seqlens"].shape[0]
+    dev = w._dev.cpu()
+    assert np.array_equal(dev[2 * T : 3 * T].numpy(), fx[f"{mode}_position_ids"].astype(np.int64))
+    cu = dev[3 * T : 3 * T + (nb + 1) // 2].view(torch.int32)[:nb].numpy()
+    assert np.array_equal(cu, fx[f"{mode}_cu_seqlens"])
+    # gradients against the reference-derived golden gradients
+    loss.backward()
+    torch.cuda.synchronize()
+    eng = w.model.engine
+    g_lnf = eng.units[0].gviews["transformer.ln_f.weight"]
+    g_attn = eng.units[1].gviews["transformer.h.0.attn.c_attn.weight"]
+    g_wte = eng.units[0].gviews["transformer.wte.weight"]
+    assert rel_l2(g_lnf, torch.from_numpy(fx[f"{mode}_grad_ln_f"])) < 2e-2
+    assert rel_l2(g_attn[::4], torch.from_numpy(fx[f"{mode}_grad_c_attn_0"])) < 2e-2
+    rows = torch.from_numpy(fx["tokens"][0, :16])
+    assert rel_l2(g_wte[rows.cuda()], torch.from_numpy(fx[f"{mode}_grad_wte_rows"])) < 2e-2
+
+
+@pytest.mark.parametrize("name", ["gqa_bias_mup", "hd80_bias"])
+def test_all_gradients_match_oracle(name):
+    model, ocfg, params = build_model(name)
+    model.assume_unit_loss_grad = True
+    tokens = sample_tokens(ocfg)
+    p_req = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    loss_ref, _ = O.pretraining_loss(p_req, ocfg, tokens, 7, True, True)
+    loss_ref.backward()
+    inp, labels = O.split_tokens(tokens)
+    b = O.prepare_model_inputs(inp.copy(), 7, True, True)
+    model.engine.zero_grad()
+    loss = model.forward_pretraining_loss(
+        torch.from_numpy(b["input_ids"]).cuda(), torch.from_numpy(b["position_ids"]).cuda(),
+        torch.from_numpy(b["cu_seqlens"]).cuda(), b["max_seqlen"], torch.from_numpy(np.ascontiguousarray(labels).reshape(-1)).cuda())
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) / loss_ref.item() < 1e-3
+    bad = []
+    for pname, unit, spec in model.engine.named_views():
+        g = unit.gviews[pname]
+        r = p_req[pname].grad
+        e = rel_l2(g, r)
+        if e > 3e-2:
+            bad.append((pname, e))
+    assert not bad, bad
+
+
+def test_list_inputs_equal_tensor_inputs_exactly():
+    """tests/hf_models/single_gpu/hf_models/gpt_dolomite_test.py:202-246 (x.equal(y))"""
+    from dolomite_engine_b200.hf_models import convert_padding_free_lists_to_tensors
+
+    model, ocfg, _ = build_model("hd80_bias")
+    ids = [[5, 6, 7, 8, 9, 1, 2, 3, 4, 5] * 3, [9, 8, 7, 6, 5] * 5]
+    a = model(input_ids=ids).logits
+    i, p, _, _, cu, ms = convert_padding_free_lists_to_tensors(input_ids=ids)
+    assert cu.dtype == torch.int32 and cu.tolist() == [0, 30, 55] and ms == 30
+    b = model(input_ids=i, position_ids=p, cu_seqlens=cu, max_seqlen=ms).logits
+    assert a.equal(b)
+
+
+def test_finetune_loss_matches_oracle():
+    model, ocfg, params = build_model("gqa_bias_mup")
+    rng = np.random.default_rng(5)
+    ids = [rng.integers(0, ocfg.vocab_size, size=n).tolist() for n in (33, 70, 1, 19)]
+    labels = [list(x) for x in ids]
+    labels[1][:10] = [-100] * 10  # masked prompt tokens
+    ref, _ = O.finetuning_loss(params, ocfg, ids, labels)
+    out = model(input_ids=ids, labels=labels)
+    assert abs(out.loss.item() - ref.item()) / ref.item() < 1e-3
+
+
+def test_typecheck_attention_mask_rejected():
+    """tests/hf_models/single_gpu/typecheck_test.py:11-23"""
+    model, _, _ = build_model("hd80_bias")
+    with pytest.raises(AssertionError):
+        model(input_ids=[[1, 2, 3]], attention_mask=torch.ones(1, 3))
+
+
+def test_state_dict_names_and_save_load_roundtrip(tmp_path):
+    from dolomite_engine_b200.hf_models import AutoModelForCausalLM
+
+    model, ocfg, params = build_model("gqa_bias_mup")
+    sd = model.state_dict()
+    assert sorted(sd) == sorted(params)
+    for k in params:
+        assert torch.equal(sd[k].cpu(), params[k]), k
+    model.save_pretrained(str(tmp_path))
+    again = AutoModelForCausalLM.from_pretrained(str(tmp_path))
+    ids = [[3, 4, 5, 6, 7, 8, 9, 10]]
+    assert model(input_ids=ids).logits.equal(again(input_ids=ids).logits)
+
+
+@pytest.mark.parametrize("opt_name", ["DolomiteFusedAdamW", "TorchAdamW"])
+def test_train_steps_reduce_loss_and_match_cpu_adamw(opt_name):
+    """a few optimizer steps on one fixed batch: loss decreases, and the trajectory follows a CPU fp32 run of the
+    oracle + torch.optim.AdamW (same arithmetic as train_utils.train_step)"""
+    from dolomite_engine_b200.distributed import ShardedDataParallel
+    from dolomite_engine_b200.model_wrapper import ModelWrapperForPretraining
+    from dolomite_engine_b200.optimization import get_optimizer
+    from dolomite_engine_b200.train_utils import train_step
+
+    kw = GPU_CONFIGS["hd80_bias"]
+    ocfg = O.OracleConfig(**kw)
+    params = oracle_params(ocfg)
+    w = ModelWrapperForPretraining(pretrained_config=gpu_config(kw).to_dict(), micro_batch_size=2, sequence_length=64)
+    w.model.load_state_dict(params)
+    sdp = ShardedDataParallel(w)
+    args = {"lr": 1e-3, "weight_decay": 0.1, "betas": [0.9, 0.95], "eps": 1e-10}
+    opt = get_optimizer(opt_name, args, sdp)
+    tokens = torch.from_numpy(sample_tokens(ocfg))
+
+    def batches():
+        while True:
+            yield {"text": tokens}
+
+    p_cpu = {k: torch.nn.Parameter(v.clone()) for k, v in params.items()}
+    opt_cpu = torch.optim.AdamW(list(p_cpu.values()), lr=1e-3, weight_decay=0.1, betas=(0.9, 0.95), eps=1e-10)
+    dl = batches()
+    losses, ref_losses = [], []
+    for _ in range(4):
+        loss, gn = train_step(sdp, opt, None, train_dataloader=dl, gradient_accumulation_steps=2, gradient_clipping=1.0)
+        losses.append(loss)
+        opt_cpu.zero_grad()
+        for _ in range(2):
+            l, _ = O.pretraining_loss(p_cpu, ocfg, tokens.numpy())
+            l.backward()
+        ref_gn = torch.nn.utils.clip_grad_norm_(list(p_cpu.values()), 1.0)
+        opt_cpu.step()
+        ref_losses.append(l.item())
+        assert abs(gn - ref_gn.item()) / ref_gn.item() < 3e-2
+    assert losses[-1] < losses[0]
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) / b < 2e-3, (losses, ref_losses)
