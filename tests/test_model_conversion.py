@@ -1,0 +1,98 @@
+"""CPU: import_from_huggingface (llama / granite) -- weight re-layout is exact, and the imported checkpoint evaluated by
+the oracle reproduces the logits of HuggingFace's own Llama implementation on the original checkpoint
+(the reference pins this in tests/hf_models/single_gpu/model_conversion_test.py)."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle.dolomite_oracle as O
+from dolomite_engine_b200.hf_models import import_from_huggingface
+from dolomite_engine_b200.hf_models.config import CommonConfig
+from dolomite_engine_b200.hf_models.model_conversion import (
+    interleave_query_key_value_tensor_for_attention,
+    split_query_key_value_tensor_for_attention,
+)
+from dolomite_engine_b200.utils.safetensors import SafeTensorsWeightsManager
+
+
+@pytest.mark.parametrize("head_type,nh,nkv", [("mha", 4, 4), ("gqa", 8, 2), ("mqa", 4, 1)])
+def test_interleave_split_roundtrip_exact(head_type, nh, nkv):
+    """tests/hf_models/single_gpu/weight_test.py:16-68"""
+    hd = 8
+    q, k, v = torch.randn(nh * hd, 32), torch.randn(nkv * hd, 32), torch.randn(nkv * hd, 32)
+    w = interleave_query_key_value_tensor_for_attention(q, k, v, nh, nkv, hd, head_type)
+    q2, k2, v2 = split_query_key_value_tensor_for_attention(w, nh, nkv, hd, head_type)
+    assert torch.equal(q, q2) and torch.equal(k, k2) and torch.equal(v, v2)
+    cfg = O.OracleConfig(n_embd=nh * hd, n_head=nh, num_key_value_heads=nkv, attention_head_type=head_type)
+    assert torch.equal(w, O.interleave_qkv(q, k, v, cfg))
+
+
+def _write_llama(path, model_type="llama", **extra):
+    cfg = dict(model_type=model_type, vocab_size=320, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+               num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=128, rms_norm_eps=1e-5,
+               hidden_act="silu", rope_theta=10000.0, tie_word_embeddings=False, attention_bias=False, mlp_bias=False,
+               bos_token_id=1, eos_token_id=2, pad_token_id=None, initializer_range=0.02)
+    cfg.update(extra)
+    g = torch.Generator().manual_seed(0)
+    H, F, V, hd, nkv = 64, 128, 320, 16, 2
+    sd = {"model.embed_tokens.weight": torch.randn(V, H, generator=g) * 0.05,
+          "model.norm.weight": 1 + 0.1 * torch.randn(H, generator=g), "lm_head.weight": torch.randn(V, H, generator=g) * 0.05}
+    for i in range(2):
+        p = f"model.layers.{i}."
+        sd[p + "input_layernorm.weight"] = 1 + 0.1 * torch.randn(H, generator=g)
+        sd[p + "post_attention_layernorm.weight"] = 1 + 0.1 * torch.randn(H, generator=g)
+        sd[p + "self_attn.q_proj.weight"] = torch.randn(H, H, generator=g) * 0.05
+        sd[p + "self_attn.k_proj.weight"] = torch.randn(nkv * hd, H, generator=g) * 0.05
+        sd[p + "self_attn.v_proj.weight"] = torch.randn(nkv * hd, H, generator=g) * 0.05
+        sd[p + "self_attn.o_proj.weight"] = torch.randn(H, H, generator=g) * 0.05
+        sd[p + "mlp.up_proj.weight"] = torch.randn(F, H, generator=g) * 0.05
+        sd[p + "mlp.gate_proj.weight"] = torch.randn(F, H, generator=g) * 0.05
+        sd[p + "mlp.down_proj.weight"] = torch.randn(H, F, generator=g) * 0.05
+    os.makedirs(path, exist_ok=True)
+    with open(os.path.join(path, "config.json"), "w") as f:
+        json.dump(cfg, f)
+    SafeTensorsWeightsManager.save_state_dict(sd, path)
+    return cfg, sd
+
+
+def test_import_llama_matches_huggingface_llama(tmp_path):
+    src, dst = str(tmp_path / "hf"), str(tmp_path / "dolomite")
+    cfg, sd = _write_llama(src)
+    import_from_huggingface(src, dst)
+    c = CommonConfig.from_pretrained(dst)
+    assert c.model_type == "gpt_dolomite" and c.attention_head_type == "gqa" and c.n_inner == 128 and not c.add_bias
+    imported = SafeTensorsWeightsManager(dst).state_dict()
+    up, gate = imported["transformer.h.0.mlp.c_fc.weight"].chunk(2)
+    assert torch.equal(up, sd["model.layers.0.mlp.up_proj.weight"]) and torch.equal(gate, sd["model.layers.0.mlp.gate_proj.weight"])
+    ocfg = O.OracleConfig(vocab_size=320, n_positions=128, n_embd=64, n_layer=2, n_head=4, num_key_value_heads=2,
+                          n_inner=128, attention_head_type="gqa", tie_word_embeddings=False)
+    ids = np.random.default_rng(0).integers(0, 320, size=40)
+    logits = O.forward_logits(imported, ocfg, ids, np.arange(40), np.array([0, 40], dtype=np.int32))
+    transformers = pytest.importorskip("transformers")
+    hf_cfg = transformers.LlamaConfig(**{k: v for k, v in cfg.items() if k != "model_type"})
+    hf = transformers.LlamaForCausalLM(hf_cfg).eval()
+    hf.load_state_dict(sd)
+    with torch.no_grad():
+        ref = hf(torch.from_numpy(ids)[None]).logits[0]
+    assert torch.allclose(logits, ref, atol=2e-5), (logits - ref).abs().max()
+
+
+def test_import_granite_multipliers(tmp_path):
+    src, dst = str(tmp_path / "hf"), str(tmp_path / "dolomite")
+    _write_llama(src, model_type="granite", embedding_multiplier=12.0, residual_multiplier=0.22, logits_scaling=8.0,
+                 attention_multiplier=0.0078125)
+    import_from_huggingface(src, dst)
+    c = CommonConfig.from_pretrained(dst)
+    assert (c.m_emb, c.m_residual, c.m_width, c.attention_multiplier) == (12.0, 0.22, 8.0, 0.0078125)
+
+
+def test_unsupported_family_raises(tmp_path):
+    src = str(tmp_path / "x")
+    os.makedirs(src)
+    json.dump({"model_type": "mixtral"}, open(os.path.join(src, "config.json"), "w"))
+    with pytest.raises(NotImplementedError):
+        import_from_huggingface(src, str(tmp_path / "y"))
