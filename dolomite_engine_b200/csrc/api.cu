@@ -59,6 +59,13 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 int dolo_make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, DoloSwizzle sw) {
+    // cuTensorMapEncodeTiled is a DRIVER call: it needs a current context on the calling thread.  The autograd
+    // backward thread has only a runtime-API device set, so bind the primary context once per thread.
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        DOLO_CUDA_OK(cudaFree(nullptr));
+        ctx_bound = true;
+    }
     auto fn = get_encode_fn();
     DOLO_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled driver entry point unavailable (no CUDA driver?)");
     DOLO_REQUIRE(rank >= 1 && rank <= 5, "tensor map rank %d out of range", rank);

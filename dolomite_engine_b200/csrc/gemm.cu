@@ -40,6 +40,22 @@ struct GemmParams {
     int d_is_f32;
     int tma_store;
     int num_m, num_n, num_kb;
+    // grouped modes (MoE experts; moe_dolomite/moe/scatter.py:38-49 parallel_linear):
+    //   1 = M-grouped: every 128-row tile of A/D belongs to one group (m_tile_group[m_blk], -1 = unused tile); B's outer
+    //       TMA coordinate is offset by group * b_group_rows (fwd / dgrad of the expert linears)
+    //   2 = K-grouped: tile index also enumerates the group; the contraction runs over rows
+    //       [group_k_offsets[g], group_k_offsets[g+1]) and D/C are offset by g * d_group_stride (expert wgrad)
+    int grouped;
+    const int* m_tile_group;
+    int b_group_rows;
+    const int* group_k_offsets;
+    int num_groups;
+    int64_t d_group_stride;
+};
+
+struct TileInfo {
+    int m_blk, n_blk, grp, kb0, kb1;
+    bool valid;
 };
 
 __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
@@ -50,6 +66,29 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_
     const int r = t - group * per_group;
     m_blk = first_m + r % gsize;
     n_blk = r / gsize;
+}
+
+__device__ __forceinline__ TileInfo tile_info(int t, const GemmParams& p) {
+    TileInfo ti;
+    ti.grp = 0;
+    ti.kb0 = 0;
+    ti.kb1 = p.num_kb;
+    ti.valid = true;
+    if (p.grouped == 2) {
+        const int per = p.num_m * p.num_n;
+        ti.grp = t / per;
+        tile_coords(t - ti.grp * per, p.num_m, p.num_n, ti.m_blk, ti.n_blk);
+        ti.kb0 = p.group_k_offsets[ti.grp] / BK;
+        ti.kb1 = p.group_k_offsets[ti.grp + 1] / BK;
+        ti.valid = ti.kb1 > ti.kb0;
+    } else {
+        tile_coords(t, p.num_m, p.num_n, ti.m_blk, ti.n_blk);
+        if (p.grouped == 1) {
+            ti.grp = p.m_tile_group[ti.m_blk];
+            ti.valid = ti.grp >= 0;
+        }
+    }
+    return ti;
 }
 
 template <bool A_MN, bool B_MN>
@@ -70,7 +109,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m * p.num_n;
+    const int num_tiles = p.num_m * p.num_n * (p.grouped == 2 ? p.num_groups : 1);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -98,9 +137,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                int m_blk, n_blk;
-                tile_coords(t, p.num_m, p.num_n, m_blk, n_blk);
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                const TileInfo ti = tile_info(t, p);
+                if (!ti.valid) continue;
+                const int m_blk = ti.m_blk, n_blk = ti.n_blk;
+                const int b_outer = (p.grouped == 1) ? ti.grp * p.b_group_rows : 0;
+                for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1, 1);
                     mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
@@ -113,11 +154,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                             tma_load_2d(sa + i * (BK * 128), &tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
                     }
                     if (!B_MN) {
-                        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+                        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, b_outer + n_blk * BN);
                     } else {
 #pragma unroll
                         for (int i = 0; i < BN / 64; ++i)
-                            tma_load_2d(sb + i * (BK * 128), &tmap_b, &full_bar[stage], n_blk * BN + i * 64, kb * BK);
+                            tma_load_2d(sb + i * (BK * 128), &tmap_b, &full_bar[stage], n_blk * BN + i * 64,
+                                        b_outer + kb * BK);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -132,10 +174,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const TileInfo ti = tile_info(t, p);
+                if (!ti.valid) continue;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase, 3);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
@@ -148,7 +192,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                                                     : umma_smem_desc(sa + k * 32, 16, 1024, 2);
                         const uint64_t bdesc = B_MN ? umma_smem_desc(sb + k * 2048, BK * 128, 1024, 2)
                                                     : umma_smem_desc(sb + k * 32, 16, 1024, 2);
-                        umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_ss(d_tmem, adesc, bdesc, idesc, (kb != ti.kb0 || k != 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -165,8 +209,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         uint32_t acc_phase = 0;
         int epi_buf = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            int m_blk, n_blk;
-            tile_coords(t, p.num_m, p.num_n, m_blk, n_blk);
+            const TileInfo ti = tile_info(t, p);
+            if (!ti.valid) continue;
+            const int m_blk = ti.m_blk, n_blk = ti.n_blk;
+            const int64_t d_off = (p.grouped == 2) ? int64_t(ti.grp) * p.d_group_stride : 0;
             mbar_wait(&tmem_full[acc], acc_phase, 4);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t(sub * 32) << 16) + uint32_t(acc * BN);
@@ -238,8 +284,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
                     if (p.d_is_f32) {
-                        float* drow = static_cast<float*>(p.D) + row * p.ldd + cb;
-                        const float* crow = p.C ? static_cast<const float*>(p.C) + row * p.ldc + cb : nullptr;
+                        float* drow = static_cast<float*>(p.D) + d_off + row * p.ldd + cb;
+                        const float* crow = p.C ? static_cast<const float*>(p.C) + d_off + row * p.ldc + cb : nullptr;
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             if (cb + q * 4 < p.N) {  // N % 8 == 0 -> whole float4 in range
@@ -252,9 +298,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                             }
                         }
                     } else {
-                        __nv_bfloat16* drow = static_cast<__nv_bfloat16*>(p.D) + row * p.ldd + cb;
+                        __nv_bfloat16* drow = static_cast<__nv_bfloat16*>(p.D) + d_off + row * p.ldd + cb;
                         const __nv_bfloat16* crow =
-                            p.C ? static_cast<const __nv_bfloat16*>(p.C) + row * p.ldc + cb : nullptr;
+                            p.C ? static_cast<const __nv_bfloat16*>(p.C) + d_off + row * p.ldc + cb : nullptr;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             if (cb + q * 8 < p.N) {
@@ -302,7 +348,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
         DOLO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    const int tiles = p.num_m * p.num_n;
+    const int tiles = p.num_m * p.num_n * (p.grouped == 2 ? p.num_groups : 1);
     const int grid = tiles < dolo_num_sms() ? tiles : dolo_num_sms();
     kern<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(ta, tb, td, p);
     DOLO_LAUNCH_OK("gemm_bf16");
@@ -311,10 +357,19 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
 
 }  // namespace
 
-extern "C" int dolomite_b200_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
-                                       int b_mn_major, void* D, int64_t ldd, int d_is_f32, const void* C, int64_t ldc,
-                                       float alpha, float beta, const void* bias, int64_t M, int64_t N, int64_t K,
-                                       int flags, void* stream) {
+struct GroupArgs {
+    int mode = 0;
+    const int* m_tile_group = nullptr;
+    int64_t b_group_rows = 0;
+    const int* group_k_offsets = nullptr;
+    int num_groups = 1;
+    int64_t d_group_stride = 0;
+    int64_t b_total_outer = 0;  // rows of B's outer TMA dimension over all groups
+};
+
+static int gemm_impl(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D,
+                     int64_t ldd, int d_is_f32, const void* C, int64_t ldc, float alpha, float beta, const void* bias,
+                     int64_t M, int64_t N, int64_t K, int flags, void* stream, const GroupArgs& ga) {
     DOLO_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative dimension");
     if (M == 0 || N == 0) return DOLO_OK;
     DOLO_REQUIRE(K > 0, "gemm: K must be > 0");
@@ -341,10 +396,10 @@ extern "C" int dolomite_b200_gemm_bf16(const void* A, int64_t lda, int a_mn_majo
         int rc = dolo_make_tmap(&ta, A, 2, 2, dims, strides, box, DOLO_SW_128);
         if (rc) return rc;
         if (!b_mn_major) {
-            dims[0] = uint64_t(K); dims[1] = uint64_t(N); strides[1] = uint64_t(ldb) * 2;
+            dims[0] = uint64_t(K); dims[1] = uint64_t(ga.mode == 1 ? ga.b_total_outer : N); strides[1] = uint64_t(ldb) * 2;
             box[0] = BK; box[1] = BN;
         } else {
-            dims[0] = uint64_t(N); dims[1] = uint64_t(K); strides[1] = uint64_t(ldb) * 2;
+            dims[0] = uint64_t(N); dims[1] = uint64_t(ga.mode == 1 ? ga.b_total_outer : K); strides[1] = uint64_t(ldb) * 2;
             box[0] = 64; box[1] = BK;
         }
         rc = dolo_make_tmap(&tb, B, 2, 2, dims, strides, box, DOLO_SW_128);
@@ -374,9 +429,55 @@ extern "C" int dolomite_b200_gemm_bf16(const void* A, int64_t lda, int a_mn_majo
     p.num_m = int((M + BM - 1) / BM);
     p.num_n = int((N + BN - 1) / BN);
     p.num_kb = int((K + BK - 1) / BK);
+    p.grouped = ga.mode;
+    p.m_tile_group = ga.m_tile_group;
+    p.b_group_rows = int(ga.b_group_rows);
+    p.group_k_offsets = ga.group_k_offsets;
+    p.num_groups = ga.num_groups;
+    p.d_group_stride = ga.d_group_stride;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!a_mn_major && !b_mn_major) return launch_gemm<false, false>(ta, tb, td, p, st);
     if (!a_mn_major && b_mn_major) return launch_gemm<false, true>(ta, tb, td, p, st);
     if (a_mn_major && !b_mn_major) return launch_gemm<true, false>(ta, tb, td, p, st);
     return launch_gemm<true, true>(ta, tb, td, p, st);
+}
+
+extern "C" int dolomite_b200_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
+                                       int b_mn_major, void* D, int64_t ldd, int d_is_f32, const void* C, int64_t ldc,
+                                       float alpha, float beta, const void* bias, int64_t M, int64_t N, int64_t K,
+                                       int flags, void* stream) {
+    return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, d_is_f32, C, ldc, alpha, beta, bias, M, N, K, flags,
+                     stream, GroupArgs());
+}
+
+extern "C" int dolomite_b200_gemm_bf16_grouped_m(const void* A, int64_t lda, const void* B, int64_t ldb, int b_mn_major,
+                                                 void* D, int64_t ldd, float alpha, int64_t M_max, int64_t N, int64_t K,
+                                                 const int32_t* m_tile_group, int num_groups, int flags, void* stream) {
+    DOLO_REQUIRE(M_max % BM == 0, "grouped gemm: M_max=%lld must be a multiple of %d (padded expert segments)",
+                 (long long)M_max, BM);
+    DOLO_REQUIRE(!b_mn_major || K % BK == 0, "grouped gemm: MN-major B needs K %% %d == 0", BK);
+    DOLO_REQUIRE(m_tile_group != nullptr && num_groups > 0, "grouped gemm: missing group table");
+    GroupArgs ga;
+    ga.mode = 1;
+    ga.m_tile_group = m_tile_group;
+    ga.num_groups = num_groups;
+    ga.b_group_rows = b_mn_major ? K : N;
+    ga.b_total_outer = ga.b_group_rows * num_groups;
+    return gemm_impl(A, lda, 0, B, ldb, b_mn_major, D, ldd, 0, nullptr, 0, alpha, 0.f, nullptr, M_max, N, K, flags, stream,
+                     ga);
+}
+
+extern "C" int dolomite_b200_gemm_bf16_grouped_k(const void* A, int64_t lda, const void* B, int64_t ldb, float* D,
+                                                 int64_t ldd, float alpha, float beta, int64_t M, int64_t N,
+                                                 int64_t K_max, const int32_t* group_k_offsets, int num_groups,
+                                                 void* stream) {
+    DOLO_REQUIRE(group_k_offsets != nullptr && num_groups > 0, "grouped wgrad: missing offsets");
+    GroupArgs ga;
+    ga.mode = 2;
+    ga.group_k_offsets = group_k_offsets;
+    ga.num_groups = num_groups;
+    ga.d_group_stride = M * ldd;
+    // A, B are both MN-major views of [K_max, M] / [K_max, N] row-major activations; D[g] (+)= A_g^T B_g in fp32
+    return gemm_impl(A, lda, 1, B, ldb, 1, D, ldd, 1, beta != 0.f ? D : nullptr, ldd, alpha, beta, nullptr, M, N, K_max, 0,
+                     stream, ga);
 }

@@ -176,6 +176,13 @@ def check_supported(cfg: CommonConfig) -> None:
     hd = cfg.n_embd // cfg.n_head
     if hd not in (16, 32, 64, 80, 96, 128):
         raise NotImplementedError(f"head_dim={hd}: supported head dims are 16, 32, 64, 80, 96, 128")
+    if cfg.model_type == "moe_dolomite":
+        if cfg.num_experts % 8 or not (1 <= cfg.num_experts_per_tok <= min(8, cfg.num_experts)):
+            raise NotImplementedError("MoE: num_experts must be a multiple of 8 (<= 256) and 1 <= top-k <= 8")
+        if cfg.add_bias:
+            raise NotImplementedError("MoE experts with bias are not supported (ScatterMoE asserts the same, moe/scatter.py:22)")
+        if cfg.n_inner % 64 or cfg.n_embd % 64:
+            raise NotImplementedError("MoE: n_embd and n_inner must be multiples of 64 (grouped GEMM K tiles)")
     if cfg.n_embd % 8 or cfg.n_inner % 8 or cfg.vocab_size % 8:
         raise NotImplementedError("n_embd, n_inner and vocab_size must be multiples of 8 (16-byte vector kernels / TMA)")
 

@@ -265,3 +265,101 @@ def attn_varlen_bwd(dout, qkv, out, lse, cu_seqlens, max_seqlen, n_groups, q_per
         head_dim, scale, ws.data_ptr(), _stream(),
     )
     return dqkv
+
+
+# ------------------------------------------------------------------------------------------------
+# MoE: routing plan, grouped expert GEMMs (moe_dolomite/moe/scatter.py:18-138)
+# ------------------------------------------------------------------------------------------------
+class MoEPlan:
+    """device-side routing state of one MoE layer invocation (no host sync anywhere)"""
+
+    __slots__ = ("T", "E", "k", "max_rows", "sel_idx", "sel_w", "counts", "offsets", "tile_group", "cursors",
+                 "row_of_slot", "slot_of_row")
+
+
+def moe_route(router_logits, k: int) -> MoEPlan:
+    _req(router_logits, _BF16, "router_logits")
+    T, E = router_logits.shape
+    dev = router_logits.device
+    p = MoEPlan()
+    p.T, p.E, p.k = T, E, k
+    p.max_rows = _lib.load().dolomite_b200_moe_max_rows(T, E, k)
+    i32 = dict(dtype=torch.int32, device=dev)
+    p.sel_idx = torch.empty(T, k, **i32)
+    p.sel_w = torch.empty(T, k, dtype=torch.float32, device=dev)
+    p.counts = torch.empty(E, **i32)
+    p.offsets = torch.empty(E + 1, **i32)
+    p.tile_group = torch.empty(p.max_rows // 128, **i32)
+    p.cursors = torch.empty(E, **i32)
+    p.row_of_slot = torch.empty(T * k, **i32)
+    p.slot_of_row = torch.empty(p.max_rows, **i32)
+    _lib.call("dolomite_b200_moe_route", router_logits.data_ptr(), T, E, k, p.sel_idx.data_ptr(), p.sel_w.data_ptr(),
+              p.counts.data_ptr(), p.offsets.data_ptr(), p.tile_group.data_ptr(), p.cursors.data_ptr(),
+              p.row_of_slot.data_ptr(), p.slot_of_row.data_ptr(), _stream())
+    return p
+
+
+def moe_gather(x, plan: MoEPlan):
+    T, H = x.shape
+    xg = torch.empty(plan.max_rows, H, dtype=_BF16, device=x.device)
+    _lib.call("dolomite_b200_moe_gather", x.data_ptr(), xg.data_ptr(), plan.slot_of_row.data_ptr(), plan.offsets.data_ptr(),
+              T, plan.E, plan.k, H, _stream())
+    return xg
+
+
+def moe_combine(yg, plan: MoEPlan, c=None, alpha: float = 1.0):
+    H = yg.shape[1]
+    out = torch.empty(plan.T, H, dtype=_BF16, device=yg.device)
+    _lib.call("dolomite_b200_moe_combine", yg.data_ptr(), plan.row_of_slot.data_ptr(), plan.sel_w.data_ptr(), _ptr(c),
+              out.data_ptr(), plan.T, plan.k, H, alpha, _stream())
+    return out
+
+
+def moe_combine_bwd(dy, yg, plan: MoEPlan, alpha: float = 1.0):
+    H = yg.shape[1]
+    dyg = torch.empty_like(yg)
+    dw = torch.zeros(plan.T, plan.k, dtype=torch.float32, device=yg.device)
+    _lib.call("dolomite_b200_moe_combine_bwd", dy.data_ptr(), yg.data_ptr(), plan.slot_of_row.data_ptr(),
+              plan.offsets.data_ptr(), plan.sel_w.data_ptr(), dyg.data_ptr(), dw.data_ptr(), plan.T, plan.E, plan.k, H,
+              alpha, _stream())
+    return dyg, dw
+
+
+def moe_token_sum(dxg, plan: MoEPlan):
+    H = dxg.shape[1]
+    dx = torch.empty(plan.T, H, dtype=_BF16, device=dxg.device)
+    _lib.call("dolomite_b200_moe_token_sum", dxg.data_ptr(), plan.row_of_slot.data_ptr(), dx.data_ptr(), plan.T, plan.k, H, _stream())
+    return dx
+
+
+def moe_router_bwd(plan: MoEPlan, dw):
+    dl = torch.empty(plan.T, plan.E, dtype=_BF16, device=dw.device)
+    _lib.call("dolomite_b200_moe_router_bwd", plan.sel_idx.data_ptr(), plan.sel_w.data_ptr(), dw.data_ptr(), dl.data_ptr(),
+              plan.T, plan.E, plan.k, _stream())
+    return dl
+
+
+def gemm_grouped_m(a, w3, plan: MoEPlan, *, b_mn: bool, alpha: float = 1.0, flags=None):
+    """rows of `a` grouped by expert.  b_mn=False: w3 [E, N, K] -> D = A W[e]^T;  b_mn=True: w3 [E, K, N] -> D = A W[e]"""
+    _req(a, _BF16, "a"), _req(w3, _BF16, "w3")
+    rows, K = a.shape
+    E = w3.shape[0]
+    N = w3.shape[2] if b_mn else w3.shape[1]
+    assert (w3.shape[1] if b_mn else w3.shape[2]) == K and rows == plan.max_rows and w3.is_contiguous()
+    out = torch.empty(rows, N, dtype=_BF16, device=a.device)
+    if flags is None:
+        flags = _default_gemm_flags
+    _lib.call("dolomite_b200_gemm_bf16_grouped_m", a.data_ptr(), a.stride(0), w3.data_ptr(), w3.shape[2], int(b_mn),
+              out.data_ptr(), N, alpha, rows, N, K, plan.tile_group.data_ptr(), E, flags, _stream())
+    return out
+
+
+def gemm_grouped_k(a, b, plan: MoEPlan, out3, alpha: float = 1.0, beta: float = 1.0):
+    """expert wgrad: out3[e] (+)= a[rows_e]^T b[rows_e]; a [rows, M], b [rows, N], out3 fp32 [E, M, N]"""
+    _req(a, _BF16, "a"), _req(b, _BF16, "b"), _req(out3, torch.float32, "out3")
+    rows, M = a.shape
+    N = b.shape[1]
+    assert out3.shape == (plan.E, M, N) and out3.is_contiguous()
+    _lib.call("dolomite_b200_gemm_bf16_grouped_k", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out3.data_ptr(), N,
+              alpha, beta, M, N, rows, plan.offsets.data_ptr(), plan.E, _stream())
+    return out3

@@ -1,0 +1,50 @@
+"""MoE MLP of MoEDolomite on the B200 kernels (reference: moe_dolomite/moe/base.py:53-181 SparseMoE, moe/scatter.py:18-138
+ScatterMoE, moe_dolomite/layer.py:51-95 SparseMoEBlock).
+
+    router logits = x gate^T -> top-k on raw logits -> fp32 softmax over the k selected -> bf16 weights
+    tokens grouped by expert (segments padded to 128 rows)  -> grouped tcgen05 GEMM c_fc -> SwiGLU
+    -> grouped GEMM c_proj -> gate-weighted combine (+ m_residual scale + residual add fused)
+
+ScatterMoE forbids biases (moe/scatter.py:22); so does this path.  Activations stay grouped between the two expert
+GEMMs exactly like `parallel_linear(grouped_out=True)` -> `parallel_linear(grouped_in=True, gates=...)`.
+"""
+
+from __future__ import annotations
+
+from . import kernels as K
+
+
+def forward(engine, unit, p: str, x, residual, m_res: float):
+    cfg = engine.cfg
+    k = cfg.num_experts_per_tok
+    if (p + "mlp.c_fc.bias") in unit.views:
+        raise NotImplementedError("expert biases are not supported by the grouped-GEMM MoE path (moe/scatter.py:22)")
+    gate = unit.views[p + "mlp.gate.weight"]
+    logits = K.gemm(x, gate, flags=0)  # [T, E] bf16 (tiny N: direct-store epilogue)
+    plan = K.moe_route(logits, k)
+    xg = K.moe_gather(x, plan)
+    fc = K.gemm_grouped_m(xg, unit.views[p + "mlp.c_fc.weight"], plan, b_mn=False)
+    act = K.swiglu_fwd(fc)
+    yg = K.gemm_grouped_m(act, unit.views[p + "mlp.c_proj.weight"], plan, b_mn=False)
+    out = K.moe_combine(yg, plan, c=residual, alpha=m_res)
+    return out, (plan, logits, xg, fc, act, yg)
+
+
+def backward(engine, unit, p: str, x, dh, m_res: float, saved):
+    """returns d(x) (gradient wrt the MoE input, i.e. the ln_2 output); accumulates expert / gate weight grads"""
+    plan, logits, xg, fc, act, yg = saved
+    dyg, dw = K.moe_combine_bwd(dh, yg, plan, alpha=m_res)
+    w_proj, w_fc = unit.views[p + "mlp.c_proj.weight"], unit.views[p + "mlp.c_fc.weight"]
+    K.gemm_grouped_k(dyg, act, plan, unit.gviews[p + "mlp.c_proj.weight"])          # dWproj[e] += dY_e^T act_e
+    d_act = K.gemm_grouped_m(dyg, w_proj, plan, b_mn=True)                            # [rows, F]
+    d_fc = K.swiglu_bwd(d_act, fc)
+    K.gemm_grouped_k(d_fc, xg, plan, unit.gviews[p + "mlp.c_fc.weight"])             # dWfc[e] += dfc_e^T x_e
+    dxg = K.gemm_grouped_m(d_fc, w_fc, plan, b_mn=True)                               # [rows, H]
+    dx = K.moe_token_sum(dxg, plan)
+    # router path: softmax-over-k backward -> dense dlogits -> gate wgrad and dx contribution
+    dlogits = K.moe_router_bwd(plan, dw)
+    gate = unit.views[p + "mlp.gate.weight"]
+    ggate = unit.gviews[p + "mlp.gate.weight"]
+    K.gemm(dlogits, x, a_mn=True, b_mn=True, out=ggate, c=ggate, beta=1.0)          # dGate += dlogits^T x
+    dx = K.gemm(dlogits, gate, b_mn=True, out=dx, c=dx, beta=1.0, flags=0)          # dx += dlogits gate
+    return dx

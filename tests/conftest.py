@@ -9,6 +9,13 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    # the GPU box has 128 host cores: torch's intra-op pool on tiny oracle tensors is slower with all of them
+    try:
+        import torch
+
+        torch.set_num_threads(min(16, os.cpu_count() or 1))
+    except Exception:
+        pass
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
