@@ -25,6 +25,18 @@ extern "C" const char* dolomite_b200_last_error() { return g_err; }
 
 extern "C" int dolomite_b200_abi_version() { return DOLOMITE_B200_ABI_VERSION; }
 
+static int g_attn_bwd_version = 1;
+int dolo_option_attn_bwd_version() { return g_attn_bwd_version; }
+
+extern "C" int dolomite_b200_set_option(const char* key, int value) {
+    if (key != nullptr && strcmp(key, "attn_bwd_version") == 0) {
+        DOLO_REQUIRE(value == 1 || value == 2, "attn_bwd_version must be 1 or 2");
+        g_attn_bwd_version = value;
+        return DOLO_OK;
+    }
+    return dolo_set_error("unknown option '%s'", key ? key : "(null)");
+}
+
 int dolo_num_sms() {
     static int cached[64] = {0};
     int dev = 0;

@@ -399,6 +399,8 @@ int make_maps(const void* base, int64_t ld, int64_t rows, CUtensorMap* m64, CUte
     return DOLO_OK;
 }
 
+#include "attention_bwd_v2.cuh"
+
 template <int HD>
 int launch_bwd(const void* dout, const void* qkv, int64_t row_stride, const BwdParams& p, cudaStream_t st) {
     using CH = HeadChunks<HD>;
@@ -478,8 +480,14 @@ extern "C" int dolomite_b200_attn_varlen_bwd(const void* dout, const void* qkv, 
     switch (head_dim) {
         case 16: rc = launch_bwd<16>(dout, qkv, row_stride, p, st); break;
         case 32: rc = launch_bwd<32>(dout, qkv, row_stride, p, st); break;
-        case 64: rc = launch_bwd<64>(dout, qkv, row_stride, p, st); break;
-        case 80: rc = launch_bwd<80>(dout, qkv, row_stride, p, st); break;
+        case 64:
+            rc = dolo_option_attn_bwd_version() >= 2 ? launch_bwd_v2<64>(dout, qkv, row_stride, p, st)
+                                                     : launch_bwd<64>(dout, qkv, row_stride, p, st);
+            break;
+        case 80:
+            rc = dolo_option_attn_bwd_version() >= 2 ? launch_bwd_v2<80>(dout, qkv, row_stride, p, st)
+                                                     : launch_bwd<80>(dout, qkv, row_stride, p, st);
+            break;
         case 96: rc = launch_bwd<96>(dout, qkv, row_stride, p, st); break;
         case 128: rc = launch_bwd<128>(dout, qkv, row_stride, p, st); break;
         default: return dolo_set_error("attn_bwd: unsupported head_dim %d (supported: 16,32,64,80,96,128)", head_dim);

@@ -36,6 +36,7 @@ int dolo_check_cuda(cudaError_t e, const char* what);
     } while (0)
 
 int dolo_num_sms();
+int dolo_option_attn_bwd_version();  // 1 = serial reference kernel, 2 = pipelined (head_dim <= 80)
 
 // TMA descriptor encode through the driver entry point (no link-time libcuda dependency).
 // rank-2 / rank-3 bf16/f32 tiled maps.  dims/strides innermost first; strides in BYTES for dims >= 1.

@@ -148,12 +148,23 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ ws, float* __restrict__ out, int parts, int H) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= H) return;
+// out[c] += sum_p ws[p, c].  Block = 32 columns x 8 part-lanes (coalesced 128-byte rows, 8-way split of the sum).
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ ws, float* __restrict__ out,
+                                                              int parts, int H) {
+    __shared__ float sm[8][33];
+    const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
     float s = 0.f;
-    for (int p = 0; p < parts; ++p) s += ws[int64_t(p) * H + c];
-    out[c] += s;
+    if (c < H)
+        for (int p = py; p < parts; p += 8) s += ws[int64_t(p) * H + c];
+    sm[py][cx] = s;
+    __syncthreads();
+    if (py == 0 && c < H) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += sm[i][cx];
+        out[c] += t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -545,7 +556,7 @@ extern "C" int dolomite_b200_rmsnorm_fwd(const void* x, const void* w, void* y, 
     return DOLO_OK;
 }
 
-static int rmsnorm_bwd_parts() { return dolo_num_sms() * 4; }
+static int rmsnorm_bwd_parts() { return dolo_num_sms() * 2; }
 
 extern "C" int64_t dolomite_b200_rmsnorm_bwd_workspace_bytes(int H) {
     return int64_t(rmsnorm_bwd_parts()) * H * sizeof(float);
@@ -581,7 +592,7 @@ extern "C" int dolomite_b200_rmsnorm_bwd(const void* dy, const void* x, const vo
     }
     DOLO_LAUNCH_OK("rmsnorm_bwd");
     if (dw_accum != nullptr) {
-        reduce_partials_kernel<<<(H + 255) / 256, 256, 0, st>>>(WS, dw_accum, parts, H);
+        reduce_partials_kernel<<<(H + 31) / 32, 256, 0, st>>>(WS, dw_accum, parts, H);
         DOLO_LAUNCH_OK("rmsnorm_bwd_reduce");
     }
     return DOLO_OK;

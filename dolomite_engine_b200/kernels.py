@@ -13,6 +13,11 @@ from . import _lib
 _BF16 = torch.bfloat16
 
 
+def set_option(key: str, value: int) -> None:
+    """process-wide tuning knobs of the CUDA library (include/dolomite_b200.h: dolomite_b200_set_option)"""
+    _lib.call("dolomite_b200_set_option", key.encode(), int(value))
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 

@@ -35,6 +35,8 @@ extern "C" {
 const char* dolomite_b200_last_error(void);
 int dolomite_b200_abi_version(void);
 int dolomite_b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* process-wide tuning knobs: "attn_bwd_version" = 1 (serial kernel, every head_dim) | 2 (pipelined, head_dim <= 80) */
+int dolomite_b200_set_option(const char* key, int value);
 
 /* ------------------------------------------------------------------------------------------------
  * RMSNorm  -- hf_models/modeling_utils/normalization/rmsnorm/base.py:18-25

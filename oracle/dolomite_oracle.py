@@ -271,10 +271,19 @@ def moe_expert_counts(idx: torch.Tensor, num_experts: int) -> np.ndarray:
     return np.bincount(idx.reshape(-1).numpy(), minlength=num_experts)
 
 
+# Tests may pin the expert choice per layer prefix ({"transformer.h.0.mlp.": LongTensor[T,k]}) so that a comparison
+# against a lower-precision implementation is not dominated by top-k flips of near-tied router logits; the routing
+# WEIGHTS are still recomputed here from the oracle's own logits.
+FORCED_ROUTING: dict = {}
+
+
 def sparse_moe(x, p: dict, prefix: str, cfg: OracleConfig, bf16: bool = False):
     """SparseMoE.forward (moe/base.py:108-173): per expert linear -> act -> linear, gate-weighted index_add"""
     T, H = x.shape
     w, idx, logits = moe_route(x, p[prefix + "gate.weight"], cfg.num_experts_per_tok, bf16)
+    if prefix in FORCED_ROUTING:
+        idx = FORCED_ROUTING[prefix]
+        w = _r(torch.softmax(logits.gather(1, idx).float(), dim=-1), bf16)
     out = torch.zeros(T, H, dtype=torch.float32)
     Wfc, Wproj = p[prefix + "c_fc.weight"], p[prefix + "c_proj.weight"]  # [E, out, in]
     bfc, bproj = p.get(prefix + "c_fc.bias"), p.get(prefix + "c_proj.bias")

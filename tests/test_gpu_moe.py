@@ -149,25 +149,34 @@ def test_moe_model_logits_loss_and_grads_match_oracle(ragged):
     tokens[1, 60] = 7
     inp, labels = O.split_tokens(tokens)
     b = O.prepare_model_inputs(inp.copy(), 7, ragged, ragged)
-    # use bf16-rounded parameters in the oracle so that both sides route on (nearly) the same router logits
-    p_req = {k: bf(v).float().requires_grad_(True) for k, v in params.items()}
-    loss_ref, logits_ref = O.pretraining_loss(p_req, ocfg, tokens, 7, ragged, ragged)
-    loss_ref.backward()
     args = (torch.from_numpy(b["input_ids"]).cuda(), torch.from_numpy(b["position_ids"]).cuda(),
             torch.from_numpy(b["cu_seqlens"]).cuda(), b["max_seqlen"])
-    out = model(input_ids=args[0], position_ids=args[1], cu_seqlens=args[2], max_seqlen=args[3])
-    logits = out.logits.float().cpu()
-    # a token whose top-k changes under bf16 rounding flips an expert: compare on the bulk, bound the outliers
-    err = (logits - logits_ref.detach()).abs().max(dim=-1).values
-    assert (err < 1e-2).float().mean() > 0.97, err.topk(5)
+    # GPU forward first; its expert choices are pinned in the oracle (near-tied bf16 router logits may flip the
+    # top-k, which is a property of the precision, not of the kernels -- the reference's own sort is unstable too)
     model.engine.zero_grad()
     lab = torch.from_numpy(np.ascontiguousarray(labels).reshape(-1)).cuda()
     loss = model.forward_pretraining_loss(*args, lab)
+    routing = {f"transformer.h.{i}.mlp.": layer[-1][0].sel_idx.long().cpu() for i, layer in enumerate(model.engine._saved["layers"])}
     loss.backward()
-    assert abs(loss.item() - loss_ref.item()) / loss_ref.item() < 2e-3
+    out = model(input_ids=args[0], position_ids=args[1], cu_seqlens=args[2], max_seqlen=args[3])
+    logits = out.logits.float().cpu().detach()
+    O.FORCED_ROUTING.clear()
+    O.FORCED_ROUTING.update(routing)
+    try:
+        p_req = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        loss_ref, logits_ref = O.pretraining_loss(p_req, ocfg, tokens, 7, ragged, ragged, bf16=True)
+        loss_ref.backward()
+        # how often does the oracle's own (unpinned) choice agree with the GPU's?
+        O.FORCED_ROUTING.clear()
+        _, free_logits = O.pretraining_loss(params, ocfg, tokens, 7, ragged, ragged)
+    finally:
+        O.FORCED_ROUTING.clear()
+    assert rel_l2(logits, logits_ref.detach()) < 1e-2
+    assert abs(loss.item() - loss_ref.item()) / loss_ref.item() < 1e-3
+    assert rel_l2(logits, free_logits.detach()) < 5e-2  # unpinned fp32 routing: only a few tokens may flip experts
     bad = []
     for pname, unit, spec in model.engine.named_views():
         e = rel_l2(unit.gviews[pname], p_req[pname].grad)
-        if e > 6e-2:
+        if e > 3e-2:
             bad.append((pname, round(e, 4)))
     assert not bad, bad
