@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const int c = ch * 32 + c2 + u;  // query column
-                        float pe = exp2f(__uint_as_float(sv[c2 + u]) * p.scale_log2 - sLSE[c]);
+                        float pe = fast_exp2(__uint_as_float(sv[c2 + u]) * p.scale_log2 - sLSE[c]);
                         if (!key_ok || (diag && r > c)) pe = 0.f;
                         pv[u] = pe;
                         dsv[u] = pe * (__uint_as_float(dv[c2 + u]) - sDelta[c]) * p.scale;

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(320, 1)
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
                             const int c = h * HALF + ch * 32 + c2 + u;  // query column inside the 128-query tile
-                            float pe = exp2f(__uint_as_float(sv[c2 + u]) * p.scale_log2 - lse_s[c]);
+                            float pe = fast_exp2(__uint_as_float(sv[c2 + u]) * p.scale_log2 - lse_s[c]);
                             if (!key_ok || (diag && r > c)) pe = 0.f;
                             pv[u] = pe;
                             dsv[u] = pe * (__uint_as_float(dv[c2 + u]) - del_s[c]) * p.scale;

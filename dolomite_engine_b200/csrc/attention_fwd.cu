@@ -179,9 +179,10 @@ __global__ void __launch_bounds__(FWD_THREADS)
             }
             const float m_new = mx;  // finite for every valid row (the diagonal key is always visible)
             const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
-            const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run * p.scale_log2 - m_scaled);
-            // rescale O (previous PV has completed: s_full is committed after it)
-            if (j > 0) {
+            const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run * p.scale_log2 - m_scaled);
+            // rescale O (previous PV has completed: s_full is committed after it); skipped when no row of this
+            // warp raised its running max (alpha == 1 everywhere), which is the common case after the first tiles
+            if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.f)) {
 #pragma unroll 1
                 for (int c0 = 0; c0 < HD; c0 += 16) {
                     uint32_t o[16];
@@ -203,8 +204,8 @@ __global__ void __launch_bounds__(FWD_THREADS)
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
                     float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-                    float p0 = exp2f(s0 * p.scale_log2 - m_scaled);
-                    float p1 = exp2f(s1 * p.scale_log2 - m_scaled);
+                    float p0 = fast_exp2(s0 * p.scale_log2 - m_scaled);
+                    float p1 = fast_exp2(s1 * p.scale_log2 - m_scaled);
                     if (diag) {
                         if (kbase + ch * 32 + i > qi) p0 = 0.f;
                         if (kbase + ch * 32 + i + 1 > qi) p1 = 0.f;

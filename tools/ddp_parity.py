@@ -1,0 +1,95 @@
+"""2+ rank check of the flat-bucket sharded data-parallel runtime against a single-rank run in the same process.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/ddp_parity.py
+
+Every rank r feeds micro-batch r to the sharded model (world_size = N); rank 0 additionally runs an unsharded copy of
+the same model over all N micro-batches with gradient accumulation.  Checks: (1) all-gathered bf16 parameters are
+identical to the unsharded model's; (2) mean of the per-rank losses == mean of the accumulated losses; (3) the
+reduce-scattered (AVG) gradient shard == slice of (accumulated gradient / N); (4) after K optimizer steps the
+fp32 master shards still agree (loss trajectory within 1e-3)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from dolomite_engine_b200.distributed import ShardedDataParallel
+from dolomite_engine_b200.model_wrapper import ModelWrapperForPretraining
+from dolomite_engine_b200.optimization import get_optimizer
+from dolomite_engine_b200.train_utils import train_step
+
+CFG = dict(model_type="gpt_dolomite", vocab_size=1024, n_positions=512, n_embd=320, n_layer=3, n_head=4, n_inner=640,
+           attention_head_type="mha", position_embedding_type="rope", activation_function="swiglu",
+           normalization_function="rmsnorm", add_bias=True, resid_pdrop=0, embd_pdrop=0, attn_pdrop=0, eos_token_id=7)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    comm_dtype = torch.float32 if os.environ.get("COMM_DTYPE", "fp32") == "fp32" else torch.bfloat16
+    mbs, seq = 2, 128
+    w = ModelWrapperForPretraining(pretrained_config=dict(CFG), micro_batch_size=mbs, sequence_length=seq, device=dev,
+                                   world_size=world, rank=rank)
+    sdp = ShardedDataParallel(w, dist.group.WORLD, communication_dtype=comm_dtype)
+    opt = get_optimizer("DolomiteFusedAdamW", {"lr": 1e-3, "weight_decay": 0.1, "betas": [0.9, 0.95], "eps": 1e-10}, sdp)
+    ref = ref_sdp = ref_opt = None
+    if rank == 0:
+        ref = ModelWrapperForPretraining(pretrained_config=dict(CFG), micro_batch_size=mbs, sequence_length=seq, device=dev)
+        ref_sdp = ShardedDataParallel(ref, None)
+        ref_opt = get_optimizer("DolomiteFusedAdamW", {"lr": 1e-3, "weight_decay": 0.1, "betas": [0.9, 0.95], "eps": 1e-10}, ref_sdp)
+    rng = np.random.default_rng(0)
+    ok = True
+    for step in range(4):
+        all_tokens = [torch.from_numpy(rng.integers(0, 1024, size=(mbs, seq + 1), dtype=np.int64)) for _ in range(world)]
+        mine = iter([{"text": all_tokens[rank]}])
+        loss, gn = train_step(sdp, opt, None, train_dataloader=mine, gradient_accumulation_steps=1, gradient_clipping=None,
+                              return_tensors=True) if False else (None, None)
+        # manual step so that gradients can be inspected before the optimizer consumes them
+        sdp.zero_grad()
+        l = sdp({"text": all_tokens[rank]})
+        l.backward()
+        torch.cuda.synchronize()
+        lsum = l.detach().clone()
+        dist.all_reduce(lsum, op=dist.ReduceOp.AVG)
+        if rank == 0:
+            ref_sdp.zero_grad()
+            rl = 0.0
+            for t in all_tokens:
+                x = ref_sdp({"text": t})
+                x.backward()
+                rl += x.item()
+            rl /= world
+            dl = abs(lsum.item() - rl) / rl
+            worst = 0.0
+            for u, ru in zip(w.model.engine.units, ref.model.engine.units):
+                assert torch.equal(u.compute[: ru.padded].cpu()[: ru.numel], ru.compute.cpu()[: ru.numel]), "gathered params differ"
+                g = u.master.grad
+                rg = (ru.master.grad / world)[rank * u.shard_numel : (rank + 1) * u.shard_numel] if ru.padded >= (rank + 1) * u.shard_numel else None
+                if rg is not None and rg.numel() == g.numel():
+                    e = ((g - rg).norm() / (rg.norm() + 1e-20)).item()
+                    worst = max(worst, e)
+            print(f"step {step}: loss {lsum.item():.6f} ref {rl:.6f} rel {dl:.2e}; worst shard-grad rel-L2 {worst:.2e}", flush=True)
+            ok = ok and dl < 1e-3 and worst < (2e-2 if comm_dtype == torch.bfloat16 else 5e-3)
+            ref_sdp.clip_grad_norm_(1.0, fuse_into_optimizer=True)
+            # the sharded run averages gradients over ranks; make the reference see the same scale
+            for ru in ref.model.engine.units:
+                ru.master.grad.div_(world)
+            ref_sdp.clip_grad_norm_(1.0, fuse_into_optimizer=True)
+            ref_opt.step()
+        sdp.clip_grad_norm_(1.0, fuse_into_optimizer=True)
+        opt.step()
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("DDP_PARITY", "OK" if ok else "FAILED", flush=True)
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
