@@ -74,7 +74,16 @@ __device__ __forceinline__ TileInfo tile_info(int t, const GemmParams& p) {
     ti.kb0 = 0;
     ti.kb1 = p.num_kb;
     ti.valid = true;
-    if (p.grouped == 2) {
+    if (p.grouped == 3) {
+        // split-K: tile index also enumerates the K split; partial products are reduced with fp32 atomics
+        const int per = p.num_m * p.num_n;
+        const int split = t / per;
+        tile_coords(t - split * per, p.num_m, p.num_n, ti.m_blk, ti.n_blk);
+        const int kb_per = (p.num_kb + p.num_groups - 1) / p.num_groups;
+        ti.kb0 = split * kb_per;
+        ti.kb1 = min(p.num_kb, ti.kb0 + kb_per);
+        ti.valid = ti.kb1 > ti.kb0;
+    } else if (p.grouped == 2) {
         const int per = p.num_m * p.num_n;
         ti.grp = t / per;
         tile_coords(t - ti.grp * per, p.num_m, p.num_n, ti.m_blk, ti.n_blk);
@@ -109,7 +118,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m * p.num_n * (p.grouped == 2 ? p.num_groups : 1);
+    const int num_tiles = p.num_m * p.num_n * (p.grouped >= 2 ? p.num_groups : 1);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -290,6 +299,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         for (int q = 0; q < 8; ++q) {
                             if (cb + q * 4 < p.N) {  // N % 8 == 0 -> whole float4 in range
                                 float4 o = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+                                if (p.grouped == 3) {  // split-K partial: D += o
+                                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + q * 4),
+                                                 "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                                                 : "memory");
+                                    continue;
+                                }
                                 if (crow) {
                                     const float4 c4 = *reinterpret_cast<const float4*>(crow + q * 4);
                                     o.x += p.beta * c4.x; o.y += p.beta * c4.y; o.z += p.beta * c4.z; o.w += p.beta * c4.w;
@@ -348,7 +363,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
         DOLO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    const int tiles = p.num_m * p.num_n * (p.grouped == 2 ? p.num_groups : 1);
+    const int tiles = p.num_m * p.num_n * (p.grouped >= 2 ? p.num_groups : 1);
     const int grid = tiles < dolo_num_sms() ? tiles : dolo_num_sms();
     kern<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(ta, tb, td, p);
     DOLO_LAUNCH_OK("gemm_bf16");
@@ -446,6 +461,27 @@ extern "C" int dolomite_b200_gemm_bf16(const void* A, int64_t lda, int a_mn_majo
                                        int b_mn_major, void* D, int64_t ldd, int d_is_f32, const void* C, int64_t ldc,
                                        float alpha, float beta, const void* bias, int64_t M, int64_t N, int64_t K,
                                        int flags, void* stream) {
+    if (flags & DOLO_GEMM_FLAG_SPLITK_ACCUMULATE) {
+        // D(fp32) += alpha * A B^T with the contraction split over several CTAs (fp32 vector atomics): removes the
+        // wave-quantisation tail of weight-gradient GEMMs (few output tiles, long K) and the read of C
+        DOLO_REQUIRE(d_is_f32 && bias == nullptr && (C == nullptr || (C == D && beta == 1.f)),
+                     "gemm: split-K accumulate needs fp32 D, no bias and C == D with beta == 1");
+        const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+        const int64_t num_kb = (K + BK - 1) / BK;
+        const int sms = dolo_num_sms();
+        int best_s = 1;
+        double best = 1e30;
+        for (int s = 1; s <= 16; ++s) {
+            if (s > 1 && num_kb / s < 8) break;
+            const double waves = double((tiles * s + sms - 1) / sms) / double(s);  // in units of one full-K tile time
+            if (waves < best - 1e-9) { best = waves; best_s = s; }
+        }
+        GroupArgs ga;
+        ga.mode = 3;
+        ga.num_groups = best_s;
+        return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, 1, nullptr, 0, alpha, 0.f, nullptr, M, N, K, 0,
+                         stream, ga);
+    }
     return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, d_is_f32, C, ldc, alpha, beta, bias, M, N, K, flags,
                      stream, GroupArgs());
 }

@@ -194,6 +194,8 @@ def accum_bf16_into_f32(src, dst, scale=1.0):
 # GEMM (nn.Linear fwd / dgrad / wgrad; linear.py:5-25)
 # ------------------------------------------------------------------------------------------------
 GEMM_TMA_STORE = 1
+GEMM_SPLITK_ACCUMULATE = 2
+wgrad_splitk = True  # route `D(fp32) += A^T B` accumulations through the split-K atomic epilogue
 _default_gemm_flags = GEMM_TMA_STORE
 gemm_timer = None  # bench.py: list collecting (flops, start_event, end_event) per GEMM launch
 
@@ -227,6 +229,8 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=_BF16, c=None, alp
         flags = _default_gemm_flags
         if d_is_f32 or c is not None:
             flags &= ~GEMM_TMA_STORE
+        if d_is_f32 and c is out and beta == 1.0 and bias is None and wgrad_splitk:
+            flags |= GEMM_SPLITK_ACCUMULATE  # weight-gradient accumulation: split-K + fp32 atomics
     if gemm_timer is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

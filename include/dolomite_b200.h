@@ -131,6 +131,9 @@ int dolomite_b200_accum_bf16_into_f32(const void* src, float* dst, float scale, 
  *   flags: bit0 = epilogue via smem staging + TMA store (bf16 D, no C), else direct vector stores.
  * ------------------------------------------------------------------------------------------------ */
 #define DOLO_GEMM_FLAG_TMA_STORE 1
+/* bit1: D(fp32) += alpha*A.B^T with split-K + fp32 vector atomics (weight gradients); C must be NULL or alias D with
+ * beta == 1, bias NULL.  Summation order over K splits is not deterministic (like FSDP's own reduce order). */
+#define DOLO_GEMM_FLAG_SPLITK_ACCUMULATE 2
 int dolomite_b200_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                             void* D, int64_t ldd, int d_is_f32, const void* C, int64_t ldc, float alpha, float beta,
                             const void* bias, int64_t M, int64_t N, int64_t K, int flags, void* stream);

@@ -180,6 +180,35 @@ def gemm_bench_wgrad():
     return _gemm_case(20480, 2560, 8192, True, True, out_f32=True, with_c=True, bench=True)
 
 
+@case
+def gemm_bench_wgrad_splitk():
+    """weight-gradient shapes of one C2 block: accumulate-in-place epilogue vs split-K atomic epilogue"""
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+
+    res = {}
+    ok = True
+    T = 8192
+    for (n_out, k_in) in [(2560, 2560), (7680, 2560), (20480, 2560), (2560, 10240)]:
+        dy = (torch.randn(T, n_out, device="cuda") * 0.1).bfloat16()
+        x = (torch.randn(T, k_in, device="cuda") * 0.1).bfloat16()
+        ref = dy.float().t() @ x.float()
+        entry = {}
+        for name, flag in (("rmw", 0), ("splitk", 2)):
+            d = torch.zeros(n_out, k_in, device="cuda")
+            k.gemm(dy, x, a_mn=True, b_mn=True, out=d, c=d, beta=1.0, flags=flag)
+            torch.cuda.synchronize()
+            e = _err(d, ref)
+            ms = _time(lambda: k.gemm(dy, x, a_mn=True, b_mn=True, out=d, c=d, beta=1.0, flags=flag), iters=10)
+            entry[name] = {"rel_l2": e["rel_l2"], "ms": ms, "tflops": 2.0 * T * n_out * k_in / ms / 1e9}
+            ok = ok and e["rel_l2"] < 1e-4
+        ms_ref = _time(lambda: torch.matmul(dy.t(), x), iters=10)
+        entry["cublas_tflops"] = 2.0 * T * n_out * k_in / ms_ref / 1e9
+        res[f"{n_out}x{k_in}"] = entry
+    res["ok"] = bool(ok)
+    return res
+
+
 # ---------------------------------------------------------------------------------------------
 @case
 def rmsnorm():
