@@ -400,6 +400,13 @@ int make_maps(const void* base, int64_t ld, int64_t rows, CUtensorMap* m64, CUte
 }
 
 #include "attention_bwd_v2.cuh"
+#include "attention_bwd_v3.cuh"
+
+template <int HD>
+int launch_bwd_pipelined(const void* dout, const void* qkv, int64_t row_stride, const BwdParams& p, cudaStream_t st) {
+    return dolo_option_attn_bwd_version() >= 3 ? launch_bwd_v3<HD>(dout, qkv, row_stride, p, st)
+                                               : launch_bwd_v2<HD>(dout, qkv, row_stride, p, st);
+}
 
 template <int HD>
 int launch_bwd(const void* dout, const void* qkv, int64_t row_stride, const BwdParams& p, cudaStream_t st) {
@@ -481,11 +488,11 @@ extern "C" int dolomite_b200_attn_varlen_bwd(const void* dout, const void* qkv, 
         case 16: rc = launch_bwd<16>(dout, qkv, row_stride, p, st); break;
         case 32: rc = launch_bwd<32>(dout, qkv, row_stride, p, st); break;
         case 64:
-            rc = dolo_option_attn_bwd_version() >= 2 ? launch_bwd_v2<64>(dout, qkv, row_stride, p, st)
+            rc = dolo_option_attn_bwd_version() >= 2 ? launch_bwd_pipelined<64>(dout, qkv, row_stride, p, st)
                                                      : launch_bwd<64>(dout, qkv, row_stride, p, st);
             break;
         case 80:
-            rc = dolo_option_attn_bwd_version() >= 2 ? launch_bwd_v2<80>(dout, qkv, row_stride, p, st)
+            rc = dolo_option_attn_bwd_version() >= 2 ? launch_bwd_pipelined<80>(dout, qkv, row_stride, p, st)
                                                      : launch_bwd<80>(dout, qkv, row_stride, p, st);
             break;
         case 96: rc = launch_bwd<96>(dout, qkv, row_stride, p, st); break;

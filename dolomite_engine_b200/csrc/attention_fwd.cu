@@ -163,18 +163,37 @@ __global__ void __launch_bounds__(FWD_THREADS)
             tc_fence_after();
             const bool diag = (j == n_kv - 1);
             const int kbase = j * ATT_TILE;
-            // pass 1: row max
+            // pass 1: row max.  Only the diagonal tile needs the causal mask; interior tiles take the mask-free path
+            // (ncu on the first version: 13.7 instructions per score, most of them per-element mask selects).
             float mx = m_run;
+            if (!diag) {
+                float mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t v[32];
-                tmem_ld32(t_lane + ch * 32, v);
-                tmem_ld_wait();
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(t_lane + ch * 32, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float s = __uint_as_float(v[i]);
-                    if (diag && (kbase + ch * 32 + i > qi)) s = -INFINITY;
-                    mx = fmaxf(mx, s);
+                    for (int i = 0; i < 32; i += 4) {
+                        mx = fmaxf(mx, __uint_as_float(v[i]));
+                        mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
+                        mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
+                        mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
+                    }
+                }
+                mx = fmaxf(fmaxf(mx, mx1), fmaxf(mx2, mx3));
+            } else {
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(t_lane + ch * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float s = __uint_as_float(v[i]);
+                        if (kbase + ch * 32 + i > qi) s = -INFINITY;
+                        mx = fmaxf(mx, s);
+                    }
                 }
             }
             const float m_new = mx;  // finite for every valid row (the diagonal key is always visible)
@@ -194,27 +213,46 @@ __global__ void __launch_bounds__(FWD_THREADS)
                 }
             }
             // pass 2: P = exp2(s*scale - m), row sum; P (bf16) overwrites the already-consumed S columns
-            float lsum = 0.f;
+            float lsum = 0.f, lsum1 = 0.f;
+            const float neg_m = -m_scaled;
+            if (!diag) {
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t v[32];
-                tmem_ld32(t_lane + ch * 32, v);
-                tmem_ld_wait();
-                uint32_t pk[16];
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(t_lane + ch * 32, v);
+                    tmem_ld_wait();
+                    uint32_t pk[16];
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-                    float p0 = fast_exp2(s0 * p.scale_log2 - m_scaled);
-                    float p1 = fast_exp2(s1 * p.scale_log2 - m_scaled);
-                    if (diag) {
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
+                        const float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, neg_m));
+                        lsum += p0;
+                        lsum1 += p1;
+                        pk[i >> 1] = pack_bf16(p0, p1);
+                    }
+                    tmem_st16(t_lane + ch * 16, pk);
+                }
+            } else {
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(t_lane + ch * 32, v);
+                    tmem_ld_wait();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
+                        float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, neg_m));
                         if (kbase + ch * 32 + i > qi) p0 = 0.f;
                         if (kbase + ch * 32 + i + 1 > qi) p1 = 0.f;
+                        lsum += p0;
+                        lsum1 += p1;
+                        pk[i >> 1] = pack_bf16(p0, p1);
                     }
-                    lsum += p0 + p1;
-                    pk[i >> 1] = pack_bf16(p0, p1);
+                    tmem_st16(t_lane + ch * 16, pk);
                 }
-                tmem_st16(t_lane + ch * 16, pk);
             }
+            lsum += lsum1;
             l_run = l_run * alpha + lsum;
             m_run = m_new;
             tmem_st_wait();

@@ -152,9 +152,12 @@ class ShardedDataParallel(nn.Module):
         self.module = model_wrapper
         self.engine: DolomiteEngine = model_wrapper.model.engine
         self.group = process_group
-        self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        # the engine was built for a given data-parallel degree; a world_size-1 engine stays unsharded even when a
+        # process group exists (e.g. an unsharded reference copy next to a sharded model)
+        self.world_size = self.engine.world_size
         if self.world_size > 1:
-            assert self.engine.world_size == self.world_size, "engine must be built with world_size/rank of the DP group"
+            assert dist.is_initialized() and dist.get_world_size(process_group) == self.world_size, \
+                "engine must be built with world_size/rank of the DP group"
             comm_dtype = torch.bfloat16 if communication_dtype is None else communication_dtype
             self.engine.comm = _Comm(self.engine, process_group, comm_dtype, reshard_after_forward)
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=self.engine.device)

@@ -195,7 +195,10 @@ def accum_bf16_into_f32(src, dst, scale=1.0):
 # ------------------------------------------------------------------------------------------------
 GEMM_TMA_STORE = 1
 GEMM_SPLITK_ACCUMULATE = 2
-wgrad_splitk = True  # route `D(fp32) += A^T B` accumulations through the split-K atomic epilogue
+# Split-K + fp32-atomic accumulation of weight gradients was measured SLOWER than read-modify-write on B200
+# (profiles/r01_probe_wgrad_splitk.json: 20480x2560x8192 2.64 ms vs 0.65 ms -- L2 atomic throughput), so it is off;
+# the entry point stays for shapes with very few output tiles.
+wgrad_splitk = False
 _default_gemm_flags = GEMM_TMA_STORE
 gemm_timer = None  # bench.py: list collecting (flops, start_event, end_event) per GEMM launch
 

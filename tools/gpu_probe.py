@@ -549,6 +549,30 @@ def attn_bench_c2_bwd_v2():
 
 
 @case
+def attn_bench_c2_bwd_v3():
+    from dolomite_engine_b200 import kernels as k
+
+    k.set_option("attn_bwd_version", 3)
+    return _attn_bench(4096, 2, 32, 80)
+
+
+@case
+def attn_v3_correctness():
+    from dolomite_engine_b200 import kernels as k
+
+    k.set_option("attn_bwd_version", 3)
+    out = {}
+    ok = True
+    for name, (lens, ng, g, hd) in {"hd80_ragged": ([200, 130, 515], 4, 1, 80), "hd64_ragged": ([100, 37, 300, 1, 129], 4, 1, 64),
+                                    "hd64_gqa_long": ([1024, 700], 2, 2, 64), "hd80_one_tile": ([77], 2, 1, 80)}.items():
+        r = _attn_case(lens, ng, g, hd)
+        out[name] = {x: r[x]["rel_l2"] for x in ("fwd", "dq", "dk", "dv")}
+        ok = ok and r["ok"]
+    out["ok"] = ok
+    return out
+
+
+@case
 def attn_v2_correctness():
     from dolomite_engine_b200 import kernels as k
 
