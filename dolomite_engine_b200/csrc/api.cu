@@ -25,7 +25,7 @@ extern "C" const char* dolomite_b200_last_error() { return g_err; }
 
 extern "C" int dolomite_b200_abi_version() { return DOLOMITE_B200_ABI_VERSION; }
 
-static int g_attn_bwd_version = 2;
+static int g_attn_bwd_version = 3;
 int dolo_option_attn_bwd_version() { return g_attn_bwd_version; }
 
 extern "C" int dolomite_b200_set_option(const char* key, int value) {

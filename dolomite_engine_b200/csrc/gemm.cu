@@ -25,7 +25,6 @@ constexpr int EPI_SLAB_BYTES = BM * 64 * 2;  // 128 rows x 64 bf16 columns, SW12
 constexpr int EPI_BUFS = 2;
 constexpr int GEMM_THREADS = 192;
 constexpr int TMEM_COLS = 512;  // 2 accumulator stages x 256 fp32 columns
-constexpr int GROUP_M = 8;
 
 constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BUFS * EPI_SLAB_BYTES + 256 /*barriers*/;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
@@ -40,6 +39,7 @@ struct GemmParams {
     int d_is_f32;
     int tma_store;
     int num_m, num_n, num_kb;
+    int group_m;  // m-blocks per rasterisation panel
     // grouped modes (MoE experts; moe_dolomite/moe/scatter.py:38-49 parallel_linear):
     //   1 = M-grouped: every 128-row tile of A/D belongs to one group (m_tile_group[m_blk], -1 = unused tile); B's outer
     //       TMA coordinate is offset by group * b_group_rows (fwd / dgrad of the expert linears)
@@ -58,11 +58,14 @@ struct TileInfo {
     bool valid;
 };
 
-__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
-    const int per_group = GROUP_M * num_n;
+// Tile rasterisation: sweep all n-blocks for a panel of `gm` m-blocks, so that the A panel (gm x 128 rows x K) stays
+// L2-resident while B streams; gm is chosen on the host so that the panel is ~24 MB (ncu on the first version with a
+// fixed panel of 8: B re-read 8x from DRAM, 870 MB of reads for 147 MB of operands).
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int gm, int& m_blk, int& n_blk) {
+    const int per_group = gm * num_n;
     const int group = t / per_group;
-    const int first_m = group * GROUP_M;
-    const int gsize = min(num_m - first_m, GROUP_M);
+    const int first_m = group * gm;
+    const int gsize = min(num_m - first_m, gm);
     const int r = t - group * per_group;
     m_blk = first_m + r % gsize;
     n_blk = r / gsize;
@@ -78,7 +81,7 @@ __device__ __forceinline__ TileInfo tile_info(int t, const GemmParams& p) {
         // split-K: tile index also enumerates the K split; partial products are reduced with fp32 atomics
         const int per = p.num_m * p.num_n;
         const int split = t / per;
-        tile_coords(t - split * per, p.num_m, p.num_n, ti.m_blk, ti.n_blk);
+        tile_coords(t - split * per, p.num_m, p.num_n, p.group_m, ti.m_blk, ti.n_blk);
         const int kb_per = (p.num_kb + p.num_groups - 1) / p.num_groups;
         ti.kb0 = split * kb_per;
         ti.kb1 = min(p.num_kb, ti.kb0 + kb_per);
@@ -86,12 +89,12 @@ __device__ __forceinline__ TileInfo tile_info(int t, const GemmParams& p) {
     } else if (p.grouped == 2) {
         const int per = p.num_m * p.num_n;
         ti.grp = t / per;
-        tile_coords(t - ti.grp * per, p.num_m, p.num_n, ti.m_blk, ti.n_blk);
+        tile_coords(t - ti.grp * per, p.num_m, p.num_n, p.group_m, ti.m_blk, ti.n_blk);
         ti.kb0 = p.group_k_offsets[ti.grp] / BK;
         ti.kb1 = p.group_k_offsets[ti.grp + 1] / BK;
         ti.valid = ti.kb1 > ti.kb0;
     } else {
-        tile_coords(t, p.num_m, p.num_n, ti.m_blk, ti.n_blk);
+        tile_coords(t, p.num_m, p.num_n, p.group_m, ti.m_blk, ti.n_blk);
         if (p.grouped == 1) {
             ti.grp = p.m_tile_group[ti.m_blk];
             ti.valid = ti.grp >= 0;
@@ -444,6 +447,14 @@ static int gemm_impl(const void* A, int64_t lda, int a_mn_major, const void* B, 
     p.num_m = int((M + BM - 1) / BM);
     p.num_n = int((N + BN - 1) / BN);
     p.num_kb = int((K + BK - 1) / BK);
+    {
+        // A panel of group_m x 128 rows x K bf16 should fit comfortably in L2 next to the streaming B tiles
+        const int64_t panel_bytes = int64_t(BM) * K * 2;
+        int64_t gm = (24ll << 20) / (panel_bytes > 0 ? panel_bytes : 1);
+        if (gm < 4) gm = 4;
+        if (gm > 64) gm = 64;
+        p.group_m = int(gm);
+    }
     p.grouped = ga.mode;
     p.m_tile_group = ga.m_tile_group;
     p.b_group_rows = int(ga.b_group_rows);

@@ -164,7 +164,7 @@ def test_attention_fwd_bwd_vs_oracle(lens, ng, g, hd):
             dqkv = K().attn_varlen_bwd(dout.cuda(), qkv.cuda(), out, lse, torch.from_numpy(cu).cuda(), max(lens), ng, g, hd, scale)
             assert rel_l2(dqkv, x.grad) < 1.2e-2, version
         finally:
-            K().set_option("attn_bwd_version", 2)  # library default
+            K().set_option("attn_bwd_version", 3)  # library default
 
 
 # ------------------------------------------------------------------------------------------------

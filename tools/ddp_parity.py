@@ -65,7 +65,10 @@ def main():
             dl = abs(lsum.item() - rl) / rl
             worst = 0.0
             for u, ru in zip(w.model.engine.units, ref.model.engine.units):
-                assert torch.equal(u.compute[: ru.padded].cpu()[: ru.numel], ru.compute.cpu()[: ru.numel]), "gathered params differ"
+                # identical at step 0; afterwards the two runs differ by the summation order of the gradient average,
+                # so compare the bf16 parameter copies to within one bf16 ulp
+                a, b = u.compute[: ru.numel].float(), ru.compute[: ru.numel].float()
+                assert torch.allclose(a, b, rtol=2.0**-7, atol=1e-6), f"gathered params differ: {(a - b).abs().max().item()}"
                 g = u.master.grad
                 rg = (ru.master.grad / world)[rank * u.shard_numel : (rank + 1) * u.shard_numel] if ru.padded >= (rank + 1) * u.shard_numel else None
                 if rg is not None and rg.numel() == g.numel():
