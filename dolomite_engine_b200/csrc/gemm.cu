@@ -103,43 +103,59 @@ __device__ __forceinline__ TileInfo tile_info(int t, const GemmParams& p) {
     return ti;
 }
 
-template <bool A_MN, bool B_MN>
+// CTA2 = CTA-pair mode: a cluster of two CTAs computes a 256 x 256 tile with tcgen05.mma.cta_group::2 (M = 256).  Each
+// CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 N rows), so a pipeline stage is 32 KB instead
+// of 48 KB (6 stages instead of 4) and B is fetched from L2 once per pair.  The MMA is issued by the leader CTA
+// (cluster rank 0); accumulator rows 0..127 land in the leader's TMEM, rows 128..255 in the peer's, and each CTA runs its
+// own epilogue.  In CTA2 mode p.num_m counts 256-row super tiles and grouped modes are not used.
+template <bool A_MN, bool B_MN, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
+    constexpr int NSTAGE = CTA2 ? 6 : STAGES;
+    constexpr int B_BYTES = CTA2 ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
+    constexpr int STG_BYTES = A_STAGE_BYTES + B_BYTES;
+    static_assert(NSTAGE * STG_BYTES == STAGES * STAGE_BYTES, "both modes use the same 192 KB operand ring");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-    uint8_t* smem_epi = smem + STAGES * STAGE_BYTES;
+    uint8_t* smem_b = smem + NSTAGE * A_STAGE_BYTES;
+    uint8_t* smem_epi = smem + NSTAGE * STG_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_BUFS * EPI_SLAB_BYTES);
-    uint64_t* full_bar = bars;                   // [STAGES]
-    uint64_t* empty_bar = bars + STAGES;         // [STAGES]
-    uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
-    uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* full_bar = bars;                   // [NSTAGE]
+    uint64_t* empty_bar = bars + NSTAGE;         // [NSTAGE]
+    uint64_t* tmem_full = bars + 2 * NSTAGE;     // [2]
+    uint64_t* tmem_empty = bars + 2 * NSTAGE + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = p.num_m * p.num_n * (p.grouped >= 2 ? p.num_groups : 1);
+    const int cta_rank = CTA2 ? int(blockIdx.x & 1) : 0;          // == %cluster_ctarank for cluster dims (2,1,1)
+    const int worker = CTA2 ? int(blockIdx.x >> 1) : int(blockIdx.x);  // persistent worker (CTA or CTA pair) index
+    const int num_workers = CTA2 ? int(gridDim.x >> 1) : int(gridDim.x);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         if (p.tma_store) tma_prefetch_desc(&tmap_d);
-        for (int i = 0; i < STAGES; ++i) {
+        for (int i = 0; i < NSTAGE; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty[i], CTA2 ? 8 : 4);  // one arrive per epilogue warp (of both CTAs in pair mode)
         }
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    if (warp == 1) {
+        if (CTA2) tmem_alloc_2cta<TMEM_COLS>(tmem_slot);
+        else tmem_alloc<TMEM_COLS>(tmem_slot);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -148,44 +164,64 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = worker; t < num_tiles; t += num_workers) {
                 const TileInfo ti = tile_info(t, p);
                 if (!ti.valid) continue;
-                const int m_blk = ti.m_blk, n_blk = ti.n_blk;
+                const int m_blk = CTA2 ? ti.m_blk * 2 + cta_rank : ti.m_blk, n_blk = ti.n_blk;
                 const int b_outer = (p.grouped == 1) ? ti.grp * p.b_group_rows : 0;
                 for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
-                    uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
-                    if (!A_MN) {
-                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
-                    } else {
+                    uint8_t* sb = smem_b + stage * B_BYTES;
+                    if constexpr (CTA2) {
+                        // the leader's barrier collects the bytes of both CTAs (its own arrive carries the expectation)
+                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STG_BYTES);
+                        const int n_row = n_blk * BN + cta_rank * (BN / 2);  // this CTA's half of the B tile
+                        if (!A_MN) {
+                            tma_load_2d_2cta(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < BM / 64; ++i)
-                            tma_load_2d(sa + i * (BK * 128), &tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
-                    }
-                    if (!B_MN) {
-                        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, b_outer + n_blk * BN);
-                    } else {
+                            for (int i = 0; i < BM / 64; ++i)
+                                tma_load_2d_2cta(sa + i * (BK * 128), &tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+                        }
+                        if (!B_MN) {
+                            tma_load_2d_2cta(sb, &tmap_b, &full_bar[stage], kb * BK, n_row);
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < BN / 64; ++i)
-                            tma_load_2d(sb + i * (BK * 128), &tmap_b, &full_bar[stage], n_blk * BN + i * 64,
-                                        b_outer + kb * BK);
+                            for (int i = 0; i < BN / 128; ++i)
+                                tma_load_2d_2cta(sb + i * (BK * 128), &tmap_b, &full_bar[stage], n_row + i * 64, kb * BK);
+                        }
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], STG_BYTES);
+                        if (!A_MN) {
+                            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < BM / 64; ++i)
+                                tma_load_2d(sa + i * (BK * 128), &tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+                        }
+                        if (!B_MN) {
+                            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, b_outer + n_blk * BN);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < BN / 64; ++i)
+                                tma_load_2d(sb + i * (BK * 128), &tmap_b, &full_bar[stage], n_blk * BN + i * 64,
+                                            b_outer + kb * BK);
+                        }
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+        if (lane == 0 && cta_rank == 0) {  // pair mode: only the leader CTA issues (for both SMs)
+            constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * BM : BM, BN, A_MN, B_MN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = worker; t < num_tiles; t += num_workers) {
                 const TileInfo ti = tile_info(t, p);
                 if (!ti.valid) continue;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
@@ -195,21 +231,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     mbar_wait(&full_bar[stage], phase, 3);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
-                    const uint32_t sb = smem_u32(smem_b + stage * B_STAGE_BYTES);
+                    const uint32_t sb = smem_u32(smem_b + stage * B_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // K-major: +32 B per K=16 step inside the 128 B swizzle span; SBO = 8 rows x 128 B.
                         // MN-major: +16 K-rows x 128 B per step; LBO = next 64-wide MN chunk (BK rows x 128 B), SBO = 8 K-rows.
+                        // (pair mode: the same descriptors address each CTA's own A rows / B half at equal smem offsets)
                         const uint64_t adesc = A_MN ? umma_smem_desc(sa + k * 2048, BK * 128, 1024, 2)
                                                     : umma_smem_desc(sa + k * 32, 16, 1024, 2);
                         const uint64_t bdesc = B_MN ? umma_smem_desc(sb + k * 2048, BK * 128, 1024, 2)
                                                     : umma_smem_desc(sb + k * 32, 16, 1024, 2);
-                        umma_ss(d_tmem, adesc, bdesc, idesc, (kb != ti.kb0 || k != 0) ? 1u : 0u);
+                        if constexpr (CTA2) umma_ss_2cta(d_tmem, adesc, bdesc, idesc, (kb != ti.kb0 || k != 0) ? 1u : 0u);
+                        else umma_ss(d_tmem, adesc, bdesc, idesc, (kb != ti.kb0 || k != 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    // smem slot reusable (in both CTAs) once these MMAs retire
+                    if constexpr (CTA2) umma_commit_2cta(&empty_bar[stage]);
+                    else umma_commit(&empty_bar[stage]);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);  // accumulator complete
+                // accumulator complete (each CTA's epilogue drains its own 128 rows)
+                if constexpr (CTA2) umma_commit_2cta(&tmem_full[acc]);
+                else umma_commit(&tmem_full[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -220,10 +262,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         int acc = 0;
         uint32_t acc_phase = 0;
         int epi_buf = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int t = worker; t < num_tiles; t += num_workers) {
             const TileInfo ti = tile_info(t, p);
             if (!ti.valid) continue;
-            const int m_blk = ti.m_blk, n_blk = ti.n_blk;
+            const int m_blk = CTA2 ? ti.m_blk * 2 + cta_rank : ti.m_blk, n_blk = ti.n_blk;
             const int64_t d_off = (p.grouped == 2) ? int64_t(ti.grp) * p.d_group_stride : 0;
             mbar_wait(&tmem_full[acc], acc_phase, 4);
             tc_fence_after();
@@ -343,30 +385,64 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             // release the accumulator stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if constexpr (CTA2) mbar_arrive_remote(&tmem_empty[acc], 0);  // the leader's MMA thread waits for both CTAs
+                else mbar_arrive(&tmem_empty[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (p.tma_store && et == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc<TMEM_COLS>(tmem_base);
+    if constexpr (CTA2) {
+        cluster_sync_all();  // the peer's smem / TMEM / barriers stay valid until both CTAs are done
+        if (warp == 1) {
+            tc_fence_after();
+            tmem_dealloc_2cta<TMEM_COLS>(tmem_base);
+        }
+    } else {
+        __syncthreads();
+        if (warp == 1) {
+            tc_fence_after();
+            tmem_dealloc<TMEM_COLS>(tmem_base);
+        }
     }
 }
 
 template <bool A_MN, bool B_MN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p,
-                cudaStream_t st) {
-    auto kern = gemm_bf16_kernel<A_MN, B_MN>;
+                cudaStream_t st, bool cta_pair) {
+    const int tiles = p.num_m * p.num_n * (p.grouped >= 2 ? p.num_groups : 1);
+    if (cta_pair) {
+        auto kern = gemm_bf16_kernel<A_MN, B_MN, true>;
+        static bool attr_set2 = false;  // per instantiation
+        if (!attr_set2) {
+            DOLO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            attr_set2 = true;
+        }
+        const int pairs = dolo_num_sms() / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(unsigned(2 * (tiles < pairs ? tiles : pairs)));
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        DOLO_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, p));
+        return DOLO_OK;
+    }
+    auto kern = gemm_bf16_kernel<A_MN, B_MN, false>;
     static bool attr_set = false;  // per instantiation
     if (!attr_set) {
         DOLO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    const int tiles = p.num_m * p.num_n * (p.grouped >= 2 ? p.num_groups : 1);
     const int grid = tiles < dolo_num_sms() ? tiles : dolo_num_sms();
     kern<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(ta, tb, td, p);
     DOLO_LAUNCH_OK("gemm_bf16");
@@ -398,6 +474,10 @@ static int gemm_impl(const void* A, int64_t lda, int a_mn_major, const void* B, 
     DOLO_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm: dimension too large");
     const bool tma_store = (flags & DOLO_GEMM_FLAG_TMA_STORE) != 0;
     DOLO_REQUIRE(!tma_store || (!d_is_f32 && C == nullptr), "gemm: TMA-store epilogue needs bf16 D and no C");
+    // CTA-pair (cta_group::2) kernel: dense mode only, at least one full 256-row super tile
+    const bool cta_pair = ga.mode == 0 && M >= 2 * BM &&
+                          ((flags & DOLO_GEMM_FLAG_CTA_PAIR) != 0 || dolo_option_gemm_cta_pair() != 0) &&
+                          (flags & DOLO_GEMM_FLAG_NO_CTA_PAIR) == 0;
 
     CUtensorMap ta, tb, td;
     {
@@ -415,7 +495,7 @@ static int gemm_impl(const void* A, int64_t lda, int a_mn_major, const void* B, 
         if (rc) return rc;
         if (!b_mn_major) {
             dims[0] = uint64_t(K); dims[1] = uint64_t(ga.mode == 1 ? ga.b_total_outer : N); strides[1] = uint64_t(ldb) * 2;
-            box[0] = BK; box[1] = BN;
+            box[0] = BK; box[1] = cta_pair ? BN / 2 : BN;  // pair mode: each CTA stages half of the B tile
         } else {
             dims[0] = uint64_t(N); dims[1] = uint64_t(ga.mode == 1 ? ga.b_total_outer : K); strides[1] = uint64_t(ldb) * 2;
             box[0] = 64; box[1] = BK;
@@ -444,12 +524,12 @@ static int gemm_impl(const void* A, int64_t lda, int a_mn_major, const void* B, 
     p.beta = C ? beta : 0.f;
     p.d_is_f32 = d_is_f32;
     p.tma_store = tma_store ? 1 : 0;
-    p.num_m = int((M + BM - 1) / BM);
+    p.num_m = cta_pair ? int((M + 2 * BM - 1) / (2 * BM)) : int((M + BM - 1) / BM);  // pair mode: 256-row super tiles
     p.num_n = int((N + BN - 1) / BN);
     p.num_kb = int((K + BK - 1) / BK);
     {
         // A panel of group_m x 128 rows x K bf16 should fit comfortably in L2 next to the streaming B tiles
-        const int64_t panel_bytes = int64_t(BM) * K * 2;
+        const int64_t panel_bytes = int64_t(cta_pair ? 2 * BM : BM) * K * 2;
         int64_t gm = (24ll << 20) / (panel_bytes > 0 ? panel_bytes : 1);
         if (gm < 4) gm = 4;
         if (gm > 64) gm = 64;
@@ -462,10 +542,10 @@ static int gemm_impl(const void* A, int64_t lda, int a_mn_major, const void* B, 
     p.num_groups = ga.num_groups;
     p.d_group_stride = ga.d_group_stride;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (!a_mn_major && !b_mn_major) return launch_gemm<false, false>(ta, tb, td, p, st);
-    if (!a_mn_major && b_mn_major) return launch_gemm<false, true>(ta, tb, td, p, st);
-    if (a_mn_major && !b_mn_major) return launch_gemm<true, false>(ta, tb, td, p, st);
-    return launch_gemm<true, true>(ta, tb, td, p, st);
+    if (!a_mn_major && !b_mn_major) return launch_gemm<false, false>(ta, tb, td, p, st, cta_pair);
+    if (!a_mn_major && b_mn_major) return launch_gemm<false, true>(ta, tb, td, p, st, cta_pair);
+    if (a_mn_major && !b_mn_major) return launch_gemm<true, false>(ta, tb, td, p, st, cta_pair);
+    return launch_gemm<true, true>(ta, tb, td, p, st, cta_pair);
 }
 
 extern "C" int dolomite_b200_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,

@@ -134,6 +134,10 @@ int dolomite_b200_accum_bf16_into_f32(const void* src, float* dst, float scale, 
 /* bit1: D(fp32) += alpha*A.B^T with split-K + fp32 vector atomics (weight gradients); C must be NULL or alias D with
  * beta == 1, bias NULL.  Summation order over K splits is not deterministic (like FSDP's own reduce order). */
 #define DOLO_GEMM_FLAG_SPLITK_ACCUMULATE 2
+/* bit2 / bit3: force / forbid the CTA-pair kernel (tcgen05.mma.cta_group::2, 256 x 256 tiles on a 2-CTA cluster);
+ * default follows the "gemm_cta_pair" option. */
+#define DOLO_GEMM_FLAG_CTA_PAIR 4
+#define DOLO_GEMM_FLAG_NO_CTA_PAIR 8
 int dolomite_b200_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                             void* D, int64_t ldd, int d_is_f32, const void* C, int64_t ldc, float alpha, float beta,
                             const void* bias, int64_t M, int64_t N, int64_t K, int flags, void* stream);

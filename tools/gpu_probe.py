@@ -181,6 +181,49 @@ def gemm_bench_wgrad():
 
 
 @case
+def gemm_pair_correctness():
+    """CTA-pair (cta_group::2) kernel: every operand layout / epilogue, ragged sizes, many tiles"""
+    out = {}
+    ok = True
+    cases = {
+        "nt_256": (256, 256, 64, False, False, dict(flags=4)),
+        "nt_tma": (512, 1024, 512, False, False, dict(flags=5)),
+        "nt_ragged_bias": (300, 520, 328, False, False, dict(flags=5, bias=True)),
+        "nt_bias_c": (384, 512, 256, False, False, dict(flags=4, with_c=True, bias=True, alpha=0.5)),
+        "nn_bmn": (512, 768, 512, False, True, dict(flags=5)),
+        "tn_amn": (512, 768, 512, True, False, dict(flags=5)),
+        "tt_wgrad": (640, 512, 1024, True, True, dict(flags=4, out_f32=True, with_c=True)),
+        "many_tiles": (4096, 4096, 1024, False, False, dict(flags=5)),
+        "odd_super_tiles": (128 * 7, 256 * 3, 192, False, False, dict(flags=5)),
+    }
+    for name, (M, N, Kd, a_mn, b_mn, kw) in cases.items():
+        r = _gemm_case(M, N, Kd, a_mn, b_mn, **kw)
+        out[name] = r["rel_l2"]
+        ok = ok and r["ok"]
+    out["ok"] = ok
+    return out
+
+
+@case
+def gemm_pair_bench():
+    out = {}
+    for name, (M, N, Kd, a_mn, b_mn, kw) in {
+        "fwd_qkv": (8192, 7680, 2560, False, False, dict(flags=5)),
+        "fwd_fc": (8192, 20480, 2560, False, False, dict(flags=5)),
+        "fwd_proj": (8192, 2560, 10240, False, False, dict(flags=5)),
+        "dgrad": (8192, 2560, 7680, False, True, dict(flags=5)),
+        "wgrad_fc": (20480, 2560, 8192, True, True, dict(flags=4, out_f32=True, with_c=True)),
+        "wgrad_qkv": (7680, 2560, 8192, True, True, dict(flags=4, out_f32=True, with_c=True)),
+    }.items():
+        r = _gemm_case(M, N, Kd, a_mn, b_mn, bench=True, **kw)
+        base = _gemm_case(M, N, Kd, a_mn, b_mn, bench=True, **{**kw, "flags": kw["flags"] & ~4 | 8})
+        out[name] = {"pair_tflops": round(r["tflops"]), "single_tflops": round(base["tflops"]), "cublas_tflops": round(r["cublas_tflops"]),
+                     "rel_l2": r["rel_l2"]}
+    out["ok"] = all(v["rel_l2"] < 2e-2 for v in out.values())
+    return out
+
+
+@case
 def gemm_bench_wgrad_splitk():
     """weight-gradient shapes of one C2 block: accumulate-in-place epilogue vs split-K atomic epilogue"""
     torch = _t()
