@@ -27,7 +27,7 @@ extern "C" int dolomite_b200_abi_version() { return DOLOMITE_B200_ABI_VERSION; }
 
 static int g_attn_bwd_version = 3;
 int dolo_option_attn_bwd_version() { return g_attn_bwd_version; }
-static int g_gemm_cta_pair = 0;
+static int g_gemm_cta_pair = 1;
 int dolo_option_gemm_cta_pair() { return g_gemm_cta_pair; }
 
 extern "C" int dolomite_b200_set_option(const char* key, int value) {

@@ -118,7 +118,8 @@ def test_gemm_vs_oracle(M, N, Kd, a_mn, b_mn):
     ref = O.linear(A.float(), B.float(), bias.float(), bf16=True)
     a = (A.t().contiguous() if a_mn else A).cuda()
     b = (B.t().contiguous() if b_mn else B).cuda()
-    for flags in (0, 1):
+    # bit0: TMA-store epilogue; bit2 / bit3: force / forbid the CTA-pair (cta_group::2) kernel
+    for flags in (0, 1, 4, 5, 8, 9):
         out = K().gemm(a, b, a_mn=a_mn, b_mn=b_mn, bias=bias.cuda(), flags=flags)
         # fp32 accumulation order differs from the CPU: allow one bf16 ulp of the result magnitude
         assert (out.float().cpu() - ref).abs().max() <= 2 * BF16_EPS * ref.abs().max()

@@ -73,9 +73,10 @@ def _gemm_case(M, N, K, a_mn, b_mn, flags=0, out_f32=False, with_c=False, bias=F
     dt = torch.float32 if out_f32 else torch.bfloat16
     C = (torch.randn(M, N, device="cuda", generator=g)).to(dt) if with_c else None
     bv = (torch.randn(N, device="cuda", generator=g)).bfloat16() if bias else None
-    ref = alpha * (A.float() @ B.float().t())
+    ref = A.float() @ B.float().t()
     if bias:
         ref = ref + bv.float()
+    ref = alpha * ref  # D = alpha * (A.B^T + bias) + beta * C
     if with_c:
         ref = ref + beta * C.float()
     out = k.gemm(a_in, b_in, a_mn=a_mn, b_mn=b_mn, out_dtype=dt, c=C, alpha=alpha, beta=beta, bias=bv, flags=flags)
