@@ -28,12 +28,19 @@ extern "C" int dolomite_b200_abi_version() { return DOLOMITE_B200_ABI_VERSION; }
 static int g_attn_bwd_version = 3;
 int dolo_option_attn_bwd_version() { return g_attn_bwd_version; }
 static int g_gemm_cta_pair = 1;
+static int g_attn_fwd_version = 1;
+int dolo_option_attn_fwd_version() { return g_attn_fwd_version; }
 int dolo_option_gemm_cta_pair() { return g_gemm_cta_pair; }
 
 extern "C" int dolomite_b200_set_option(const char* key, int value) {
     if (key != nullptr && strcmp(key, "attn_bwd_version") == 0) {
         DOLO_REQUIRE(value >= 1 && value <= 3, "attn_bwd_version must be 1, 2 or 3");
         g_attn_bwd_version = value;
+        return DOLO_OK;
+    }
+    if (key != nullptr && strcmp(key, "attn_fwd_version") == 0) {
+        DOLO_REQUIRE(value == 1 || value == 2, "attn_fwd_version must be 1 or 2");
+        g_attn_fwd_version = value;
         return DOLO_OK;
     }
     if (key != nullptr && strcmp(key, "gemm_cta_pair") == 0) {

@@ -37,6 +37,7 @@ int dolo_check_cuda(cudaError_t e, const char* what);
 
 int dolo_num_sms();
 int dolo_option_attn_bwd_version();  // 1 = serial reference kernel, 2/3 = pipelined (head_dim <= 80)
+int dolo_option_attn_fwd_version();  // 1 = one query tile per CTA, 2 = ping-pong over two query tiles
 int dolo_option_gemm_cta_pair();     // 1 = dense GEMMs use the CTA-pair (cta_group::2) kernel when M >= 256
 
 // TMA descriptor encode through the driver entry point (no link-time libcuda dependency).

@@ -67,15 +67,21 @@ def main():
             for u, ru in zip(w.model.engine.units, ref.model.engine.units):
                 # identical at step 0; afterwards the two runs differ by the summation order of the gradient average,
                 # so compare the bf16 parameter copies to within one bf16 ulp
+                # (Adam's first steps are sign-like: an element whose tiny gradient changes sign moves by 2*lr, so the
+                #  comparison is on the whole tensor, not element-wise)
                 a, b = u.compute[: ru.numel].float(), ru.compute[: ru.numel].float()
-                assert torch.allclose(a, b, rtol=2.0**-7, atol=1e-6), f"gathered params differ: {(a - b).abs().max().item()}"
+                perr = ((a - b).norm() / (b.norm() + 1e-20)).item()
+                assert perr < (1e-6 if step == 0 else 2e-2), f"gathered params differ: rel-L2 {perr}"
                 g = u.master.grad
                 rg = (ru.master.grad / world)[rank * u.shard_numel : (rank + 1) * u.shard_numel] if ru.padded >= (rank + 1) * u.shard_numel else None
                 if rg is not None and rg.numel() == g.numel():
                     e = ((g - rg).norm() / (rg.norm() + 1e-20)).item()
                     worst = max(worst, e)
             print(f"step {step}: loss {lsum.item():.6f} ref {rl:.6f} rel {dl:.2e}; worst shard-grad rel-L2 {worst:.2e}", flush=True)
-            ok = ok and dl < 1e-3 and worst < (2e-2 if comm_dtype == torch.bfloat16 else 5e-3)
+            # step 0: identical parameters -> gradients must agree to fp32 (bf16 wire: bf16) precision; later steps the
+            # parameters have drifted by the sign-noise above, so the bound is looser
+            tol = (2e-2 if comm_dtype == torch.bfloat16 else 1e-5) if step == 0 else 5e-2
+            ok = ok and dl < 1e-3 and worst < tol
             ref_sdp.clip_grad_norm_(1.0, fuse_into_optimizer=True)
             # the sharded run averages gradients over ranks; make the reference see the same scale
             for ru in ref.model.engine.units:

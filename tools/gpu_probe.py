@@ -593,6 +593,32 @@ def attn_bench_c2_bwd_v2():
 
 
 @case
+def attn_fwd_v2_correctness():
+    from dolomite_engine_b200 import kernels as k
+
+    k.set_option("attn_fwd_version", 2)
+    out = {}
+    ok = True
+    for name, (lens, ng, g, hd) in {"hd80_ragged": ([200, 130, 515], 4, 1, 80), "hd64_ragged": ([100, 37, 300, 1, 129], 4, 1, 64),
+                                    "hd64_gqa_long": ([1024, 700], 2, 2, 64), "hd80_one_tile": ([77], 2, 1, 80),
+                                    "hd128_gqa": ([300, 77, 260, 1025], 2, 4, 128), "hd80_odd_tiles": ([128 * 5], 2, 1, 80)}.items():
+        r = _attn_case(lens, ng, g, hd)
+        out[name] = {x: r[x]["rel_l2"] for x in ("fwd", "dq", "dk", "dv")}
+        out[name]["lse"] = r["lse"]["max_abs"]
+        ok = ok and r["ok"]
+    out["ok"] = ok
+    return out
+
+
+@case
+def attn_bench_c2_fwd_v2():
+    from dolomite_engine_b200 import kernels as k
+
+    k.set_option("attn_fwd_version", 2)
+    return _attn_bench(4096, 2, 32, 80)
+
+
+@case
 def attn_bench_c2_bwd_v3():
     from dolomite_engine_b200 import kernels as k
 
