@@ -204,6 +204,9 @@ def run_ours(args) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        from dolomite_engine_b200.distributed import configure_comm_ctas
+
+        configure_comm_ctas()
         dist.init_process_group(backend="nccl", rank=rank, world_size=world, device_id=dev)
     cfg = dict(C2)
     cfg["n_layer"] = args.layers

@@ -28,6 +28,8 @@ extern "C" int dolomite_b200_abi_version() { return DOLOMITE_B200_ABI_VERSION; }
 static int g_attn_bwd_version = 3;
 int dolo_option_attn_bwd_version() { return g_attn_bwd_version; }
 static int g_gemm_cta_pair = 1;
+static int g_gemm_sm_margin = 0;
+int dolo_option_gemm_sm_margin() { return g_gemm_sm_margin; }
 static int g_attn_fwd_version = 1;
 int dolo_option_attn_fwd_version() { return g_attn_fwd_version; }
 int dolo_option_gemm_cta_pair() { return g_gemm_cta_pair; }
@@ -41,6 +43,11 @@ extern "C" int dolomite_b200_set_option(const char* key, int value) {
     if (key != nullptr && strcmp(key, "attn_fwd_version") == 0) {
         DOLO_REQUIRE(value == 1 || value == 2, "attn_fwd_version must be 1 or 2");
         g_attn_fwd_version = value;
+        return DOLO_OK;
+    }
+    if (key != nullptr && strcmp(key, "gemm_sm_margin") == 0) {
+        DOLO_REQUIRE(value >= 0 && value <= 64, "gemm_sm_margin must be in [0, 64]");
+        g_gemm_sm_margin = value;
         return DOLO_OK;
     }
     if (key != nullptr && strcmp(key, "gemm_cta_pair") == 0) {

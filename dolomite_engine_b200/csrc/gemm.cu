@@ -421,7 +421,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
             DOLO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
             attr_set2 = true;
         }
-        const int pairs = dolo_num_sms() / 2;
+        const int pairs = (dolo_num_sms() - dolo_option_gemm_sm_margin()) / 2;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(unsigned(2 * (tiles < pairs ? tiles : pairs)));
         cfg.blockDim = dim3(GEMM_THREADS);
@@ -443,7 +443,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
         DOLO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    const int grid = tiles < dolo_num_sms() ? tiles : dolo_num_sms();
+    const int sms = dolo_num_sms() - dolo_option_gemm_sm_margin();
+    const int grid = tiles < sms ? tiles : sms;
     kern<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(ta, tb, td, p);
     DOLO_LAUNCH_OK("gemm_bf16");
     return DOLO_OK;

@@ -20,6 +20,7 @@ the device without `.item()` until the caller asks.
 from __future__ import annotations
 
 import contextlib
+import os
 
 import torch
 import torch.distributed as dist
@@ -27,6 +28,19 @@ import torch.nn as nn
 
 from . import kernels as K
 from .engine import DolomiteEngine, FlatUnit
+
+
+def comm_cta_budget() -> int:
+    """CTAs (= SMs) the NCCL collectives may occupy; DOLO_COMM_CTAS overrides (default 8)."""
+    return int(os.environ.get("DOLO_COMM_CTAS", "8"))
+
+
+def configure_comm_ctas() -> None:
+    """Call BEFORE `init_process_group`: caps NCCL at `comm_cta_budget()` CTAs per collective (NVLink 5 needs few
+    CTAs for the ~210 MB per-unit all-gather / reduce-scatter) so that the budget can be subtracted from the
+    persistent GEMM grids instead of letting them queue behind the communication kernels."""
+    os.environ.setdefault("NCCL_MAX_CTAS", str(comm_cta_budget()))
+    os.environ.setdefault("NCCL_MIN_CTAS", "1")
 
 
 class _Comm:
@@ -132,8 +146,7 @@ class _Comm:
             else:
                 w.wait()
             self.rs_work[i] = None
-        for u in self.engine.units:
-            u.grad_full.zero_()  # consumed; next accumulation window starts from zero
+        # (the full gradient buffers are zeroed by zero_grad() at the start of the next accumulation window)
 
     def gather_master(self, unit: FlatUnit) -> torch.Tensor:
         full = torch.empty(unit.padded, dtype=torch.float32, device=unit.master.device)
@@ -160,6 +173,8 @@ class ShardedDataParallel(nn.Module):
                 "engine must be built with world_size/rank of the DP group"
             comm_dtype = torch.bfloat16 if communication_dtype is None else communication_dtype
             self.engine.comm = _Comm(self.engine, process_group, comm_dtype, reshard_after_forward)
+            # persistent GEMM grids must not claim the SMs the NCCL kernels run on (see configure_comm_ctas)
+            K.set_option("gemm_sm_margin", comm_cta_budget())
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=self.engine.device)
         self.clip_coef = torch.ones(1, dtype=torch.float32, device=self.engine.device)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=self.engine.device)

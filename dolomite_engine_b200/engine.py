@@ -246,7 +246,8 @@ class DolomiteEngine:
     def zero_grad(self) -> None:
         for u in self.units:
             u.grad_full.zero_()
-            if u.master.grad is not u.grad_full:
+            # sharded: the shard gradient is (over)written by the reduce-scatter, no need to clear it here
+            if u.master.grad is not u.grad_full and self.comm is None:
                 u.master.grad.zero_()
 
     # ------------------------------------------------------------------------------------------

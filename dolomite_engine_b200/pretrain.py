@@ -62,6 +62,9 @@ def init_distributed() -> tuple[int, int, int]:
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1 and not dist.is_initialized():
+        from .distributed import configure_comm_ctas
+
+        configure_comm_ctas()
         dist.init_process_group(backend="nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     return rank, world, local
 

@@ -29,6 +29,9 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from dolomite_engine_b200.distributed import configure_comm_ctas
+
+    configure_comm_ctas()
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     comm_dtype = torch.float32 if os.environ.get("COMM_DTYPE", "fp32") == "fp32" else torch.bfloat16
     mbs, seq = 2, 128
