@@ -265,6 +265,29 @@ def run_ours(args) -> None:
     gemm_ms = sum(r[1].elapsed_time(r[2]) for r in gemm_records)
     last_loss = float(loss.item())
 
+    if args.profile_step and rank == 0:
+        # untimed diagnostic: per-kernel device time of ONE warm in-situ step (CUPTI via torch.profiler) -> JSON.
+        # Unlike the ncu launch list (cold caches, serialised, base clocks) this is the step as it actually runs.
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            resident_step()
+            torch.cuda.synchronize()
+        agg, first, last = {}, None, None
+        for ev in prof.events():
+            if ev.device_type.name != "CUDA" or ev.device_time_total <= 0:
+                continue
+            a = agg.setdefault(ev.name[:120], [0, 0.0])
+            a[0] += 1
+            a[1] += ev.device_time_total / 1e3
+            s0, s1 = ev.time_range.start, ev.time_range.end
+            first = s0 if first is None else min(first, s0)
+            last = s1 if last is None else max(last, s1)
+        busy = sum(v[1] for v in agg.values())
+        with open(args.profile_step, "w") as f:
+            json.dump({"span_ms": (last - first) / 1e3, "sum_kernel_ms": busy, "ms_per_step_timed": ms_resident,
+                       "kernels": sorted(([k, v[0], v[1]] for k, v in agg.items()), key=lambda r: -r[2])}, f, indent=1)
+
     # ---------------- leg 2: end to end through the wrapper call with host buffers ----------------
     def e2e_step():
         l, gn = train_step(model, opt, None, train_dataloader=data, gradient_accumulation_steps=1, gradient_clipping=1.0)
@@ -350,6 +373,8 @@ def main() -> None:
     ap.add_argument("--ragged", action="store_true")
     ap.add_argument("--comm-dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", default=None, metavar="JSON",
+                    help="diagnostic: write per-kernel device times of one extra (untimed) step to this file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -38,24 +38,39 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                  : "memory");
 }
 
-// Delta[h, t] = sum_d dO[t, h, d] * O[t, h, d]      (one warp per (t, h))
-__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
-                                  float* __restrict__ delta, int64_t T, int n_heads, int hd) {
-    const int64_t gw = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (gw >= T * n_heads) return;
-    const int64_t t = gw / n_heads;
-    const int h = int(gw - t * n_heads);
-    const __nv_bfloat16* a = dout + (t * n_heads + h) * hd;
-    const __nv_bfloat16* b = out + (t * n_heads + h) * hd;
-    float s = 0.f;
-    for (int i = lane * 2; i < hd; i += 64) {
-        const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(a + i);
-        const __nv_bfloat162 y = *reinterpret_cast<const __nv_bfloat162*>(b + i);
-        s += __bfloat162float(x.x) * __bfloat162float(y.x) + __bfloat162float(x.y) * __bfloat162float(y.y);
+// Delta[h, t] = sum_d dO[t, h, d] * O[t, h, d].  Block = DELTA_TOK tokens: every thread takes 16-byte vectors of dO and O
+// (coalesced over the whole [tokens, heads*hd] slab) and leaves its 8-product partial in shared memory; the partials of a
+// head are then summed in a fixed order (deterministic) and written token-fastest, so each head's DELTA_TOK floats fill
+// one 32-byte sector.
+constexpr int DELTA_TOK = 8;
+__global__ void __launch_bounds__(256)
+    attn_delta_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ out, float* __restrict__ delta, int64_t T,
+                      int n_heads, int vec_per_head) {
+    extern __shared__ float part[];  // [DELTA_TOK][n_heads * vec_per_head]
+    const int64_t t0 = int64_t(blockIdx.x) * DELTA_TOK;
+    const int ntok = (T - t0) < DELTA_TOK ? int(T - t0) : DELTA_TOK;
+    const int vec_per_tok = n_heads * vec_per_head;
+    const int total = ntok * vec_per_tok;
+    const uint4* a = dout + t0 * vec_per_tok;
+    const uint4* b = out + t0 * vec_per_tok;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const uint4 x = __ldg(a + i), y = __ldg(b + i);
+        float s = bf16_lo(x.x) * bf16_lo(y.x) + bf16_hi(x.x) * bf16_hi(y.x);
+        s += bf16_lo(x.y) * bf16_lo(y.y) + bf16_hi(x.y) * bf16_hi(y.y);
+        s += bf16_lo(x.z) * bf16_lo(y.z) + bf16_hi(x.z) * bf16_hi(y.z);
+        s += bf16_lo(x.w) * bf16_lo(y.w) + bf16_hi(x.w) * bf16_hi(y.w);
+        part[i] = s;
     }
-    s = warp_sum(s);
-    if (lane == 0) delta[int64_t(h) * T + t] = s;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_heads * DELTA_TOK; i += blockDim.x) {
+        const int h = i / DELTA_TOK, tl = i - h * DELTA_TOK;
+        if (tl < ntok) {
+            const float* p = part + tl * vec_per_tok + h * vec_per_head;
+            float s = 0.f;
+            for (int k = 0; k < vec_per_head; ++k) s += p[k];
+            delta[int64_t(h) * T + t0 + tl] = s;
+        }
+    }
 }
 
 // dq_accum (fp32 [T, n_heads*hd]) -> bf16 q slots of dqkv
@@ -461,12 +476,9 @@ extern "C" int dolomite_b200_attn_varlen_bwd(const void* dout, const void* qkv, 
     float* dq_accum = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align256(int64_t(nh) * T * 4));
     DOLO_CUDA_OK(cudaMemsetAsync(dq_accum, 0, size_t(T) * nh * head_dim * 4, st));
     {
-        const int64_t warps = T * nh;
-        const int threads = 256;
-        const int64_t blocks = (warps * 32 + threads - 1) / threads;
-        attn_delta_kernel<<<(unsigned)blocks, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(dout),
-                                                                static_cast<const __nv_bfloat16*>(out), delta, T, nh,
-                                                                head_dim);
+        const int64_t blocks = (T + DELTA_TOK - 1) / DELTA_TOK;
+        attn_delta_kernel<<<(unsigned)blocks, 256, size_t(nh) * (head_dim / 8) * DELTA_TOK * sizeof(float), st>>>(
+            static_cast<const uint4*>(dout), static_cast<const uint4*>(out), delta, T, nh, head_dim / 8);
         DOLO_LAUNCH_OK("attn_delta");
     }
     BwdParams p;

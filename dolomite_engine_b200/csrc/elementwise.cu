@@ -180,13 +180,17 @@ __global__ void __launch_bounds__(kThreads)
     const int vec_per_half = half >> 3;
     const int rot_slots = q_per_group + 1;
     const int items = n_groups * rot_slots * vec_per_half;
-    for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
-        int64_t pos = static_cast<int64_t>(pos_ids[t]);
+    // flat (token, item) index space: every thread of every block has work (items per token is rarely a multiple of 256)
+    const int64_t total = T * items;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t t = i / items;
+        const int it = int(i - t * items);
+        int64_t pos = static_cast<int64_t>(__ldg(pos_ids + t));
         pos = pos < 0 ? 0 : (pos >= n_pos ? n_pos - 1 : pos);
         const __nv_bfloat16* c = cos_t + pos * hd;
         const __nv_bfloat16* s = sin_t + pos * hd;
         __nv_bfloat16* row = qkv + t * row_stride;
-        for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        {
             const int v = it % vec_per_half;
             const int slot_lin = it / vec_per_half;
             const int g = slot_lin / rot_slots, sl = slot_lin % rot_slots;
@@ -215,7 +219,9 @@ __global__ void __launch_bounds__(kThreads)
 // ------------------------------------------------------------------------------------------
 // SwiGLU
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// MUFU ex2 + MUFU rcp (2 ulp fp32; the result is rounded to bf16 right after) instead of the ~10-instruction IEEE divide:
+// the kernel is otherwise issue-bound next to its HBM time (168 M elements per layer).
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 __global__ void __launch_bounds__(kThreads)
     swiglu_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t T, int64_t F8) {
@@ -491,7 +497,45 @@ __global__ void __launch_bounds__(kThreads)
                  float bc1, float bc2_sqrt, const float* __restrict__ clip) {
     const float cc = clip ? clip[0] : 1.f;
     const float step_size = lr / bc1;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float decay = 1.f - lr * wd, omb1 = 1.f - b1, omb2 = 1.f - b2;
+    // 16-byte vector body (flat shards are 128-byte aligned), scalar tail below
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                          reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
+                        (pb == nullptr || (reinterpret_cast<uintptr_t>(pb) & 7) == 0);
+    const int64_t n4 = vec_ok ? (n >> 2) : 0;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+        float4 p4 = reinterpret_cast<float4*>(p)[i];
+        float4 m4 = reinterpret_cast<float4*>(m)[i];
+        float4 v4 = reinterpret_cast<float4*>(v)[i];
+        float* pp = reinterpret_cast<float*>(&p4);
+        float* mm = reinterpret_cast<float*>(&m4);
+        float* vv = reinterpret_cast<float*>(&v4);
+        const float* gg = reinterpret_cast<const float*>(&g4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gi = gg[j] * cc;
+            float pi = pp[j] * decay;
+            const float mi = b1 * mm[j] + omb1 * gi;
+            const float vi = b2 * vv[j] + omb2 * gi * gi;
+            const float denom = sqrtf(vi) / bc2_sqrt + eps;
+            pi -= step_size * (mi / denom);
+            pp[j] = pi;
+            mm[j] = mi;
+            vv[j] = vi;
+        }
+        reinterpret_cast<float4*>(p)[i] = p4;
+        reinterpret_cast<float4*>(m)[i] = m4;
+        reinterpret_cast<float4*>(v)[i] = v4;
+        if (pb) {
+            uint2 o;
+            o.x = pack_bf16(p4.x, p4.y);
+            o.y = pack_bf16(p4.z, p4.w);
+            reinterpret_cast<uint2*>(pb)[i] = o;
+        }
+    }
+    for (int64_t i = (n4 << 2) + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += int64_t(gridDim.x) * blockDim.x) {
         const float gi = g[i] * cc;
         float pi = p[i] * (1.f - lr * wd);
         const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -556,7 +600,9 @@ extern "C" int dolomite_b200_rmsnorm_fwd(const void* x, const void* w, void* y, 
     return DOLO_OK;
 }
 
-static int rmsnorm_bwd_parts() { return dolo_num_sms() * 2; }
+// 4 resident blocks per SM at H <= 4096 (64 registers): each block alternates a load phase, a block reduction and a
+// store phase, so it takes several independent blocks per SM to keep HBM requests in flight.
+static int rmsnorm_bwd_parts() { return dolo_num_sms() * 4; }
 
 extern "C" int64_t dolomite_b200_rmsnorm_bwd_workspace_bytes(int H) {
     return int64_t(rmsnorm_bwd_parts()) * H * sizeof(float);
@@ -609,7 +655,7 @@ extern "C" int dolomite_b200_rope_qk_inplace(void* qkv, int64_t row_stride, int6
     DOLO_REQUIRE(n_positions > 0, "rope: empty cos/sin table");
     if (T == 0) return DOLO_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid = int(T < int64_t(dolo_num_sms()) * 16 ? T : int64_t(dolo_num_sms()) * 16);
+    const int grid = grid_for(T * n_groups * (q_per_group + 1) * (head_dim / 16), kThreads);
     const float sgn = inverse ? -1.f : 1.f;
     auto Q = static_cast<__nv_bfloat16*>(qkv);
     auto C = static_cast<const __nv_bfloat16*>(cos_table);

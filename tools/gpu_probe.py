@@ -433,6 +433,56 @@ def optimizer():
     return {"adamw": e, "adamw_bf16": eb, "norm": [norm.item(), ref_norm], "colsum": ec, "add_scaled": ea, "ok": bool(ok)}
 
 
+@case
+def elementwise_bench_c2():
+    """HBM-bound kernels at the C2 micro-batch-4 sizes (T=16384, H=2560, F=10240, 32 heads x hd 80): GB/s of algorithmic bytes"""
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+
+    T, H, F, nh, hd = 16384, 2560, 10240, 32, 80
+    res = {}
+    x = torch.randn(T, H, device="cuda").bfloat16()
+    dy = torch.randn(T, H, device="cuda").bfloat16()
+    dres = torch.randn(T, H, device="cuda").bfloat16()
+    w = torch.ones(H, device="cuda").bfloat16()
+    y = torch.empty_like(x)
+    dx = torch.empty_like(x)
+    dw = torch.zeros(H, device="cuda")
+    _, rstd = k.rmsnorm_fwd(x, w, 1e-5, out=y)
+
+    def rec(name, ms, nbytes):
+        res[name] = {"ms": ms, "GBps": nbytes / ms / 1e6}
+
+    rec("rmsnorm_fwd", _time(lambda: k.rmsnorm_fwd(x, w, 1e-5, out=y)), 4.0 * T * H)
+    rec("rmsnorm_bwd_fused_residual", _time(lambda: k.rmsnorm_bwd(dy, x, w, rstd, dw, dx_add=dres, out=dx)), 8.0 * T * H)
+    fc = torch.randn(T, 2 * F, device="cuda").bfloat16()
+    act = torch.empty(T, F, device="cuda", dtype=torch.bfloat16)
+    dact = torch.randn(T, F, device="cuda").bfloat16()
+    dfc = torch.empty_like(fc)
+    rec("swiglu_fwd", _time(lambda: k.swiglu_fwd(fc, out=act)), 6.0 * T * F)
+    rec("swiglu_bwd", _time(lambda: k.swiglu_bwd(dact, fc, out=dfc)), 10.0 * T * F)
+    qkv = torch.randn(T, 3 * H, device="cuda").bfloat16()
+    npos = 4096
+    cos = torch.randn(npos, hd, device="cuda").bfloat16()
+    sin = torch.randn(npos, hd, device="cuda").bfloat16()
+    pos = (torch.arange(T, device="cuda") % npos)
+    rec("rope_qk", _time(lambda: k.rope_qk_inplace(qkv, nh, 1, hd, cos, sin, pos)), 4.0 * T * 2 * nh * hd)
+    bias_g = torch.zeros(2 * F, device="cuda")
+    rec("colsum_fc", _time(lambda: k.colsum_accum(dfc, bias_g)), 2.0 * T * 2 * F)
+    n = 104_900_000
+    p = torch.randn(n, device="cuda")
+    g = torch.randn(n, device="cuda") * 0.01
+    m = torch.zeros(n, device="cuda")
+    v = torch.zeros(n, device="cuda")
+    pb = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    ss = torch.zeros(1, device="cuda")
+    rec("adamw_block", _time(lambda: k.adamw_step(p, g, m, v, pb, 1e-4, 0.9, 0.95, 1e-8, 0.1, 1), iters=10), 30.0 * n)
+    rec("sumsq_block", _time(lambda: k.sumsq_accum(g, ss), iters=10), 4.0 * n)
+    rec("zero_block(torch fill)", _time(lambda: g.zero_(), iters=10), 4.0 * n)
+    res["ok"] = True
+    return res
+
+
 # ---------------------------------------------------------------------------------------------
 def _attn_ref(qkv, cu, ng, g, hd, scale, dout=None):
     """fp32 reference: per-document causal softmax attention on the packed slot layout."""
