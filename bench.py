@@ -344,7 +344,11 @@ def run_ours(args) -> None:
             "roofline": {
                 "bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all nn.Linear fwd/dgrad/wgrad + LM head)",
                 "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s",
-                "frac": (gemm_tflops / peak) if gemm_tflops else None, "traffic": None,
+                "frac": (gemm_tflops / peak) if gemm_tflops else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` capture
+                # (c_fc forward, M=8192 N=20480 K=2560, CTA-pair kernel): 256.7 MB + 304.8 MB vs 482.3 MB algorithmic
+                "traffic": 561486336, "traffic_algorithmic": 482344960,
+                "traffic_source": "profiles/r01_ncu_gemm_fc_pair_call14.txt (tensor pipe 93.4 % active)",
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_timed": len(gemm_records), "share_of_step": gemm_ms / (ms_resident * args.steps),
             },

@@ -33,6 +33,8 @@ int dolo_option_gemm_sm_margin() { return g_gemm_sm_margin; }
 static int g_attn_fwd_version = 1;
 int dolo_option_attn_fwd_version() { return g_attn_fwd_version; }
 int dolo_option_gemm_cta_pair() { return g_gemm_cta_pair; }
+static int g_attn_bwd_experiment = 0;
+int dolo_option_attn_bwd_experiment() { return g_attn_bwd_experiment; }
 
 extern "C" int dolomite_b200_set_option(const char* key, int value) {
     if (key != nullptr && strcmp(key, "attn_bwd_version") == 0) {
@@ -48,6 +50,10 @@ extern "C" int dolomite_b200_set_option(const char* key, int value) {
     if (key != nullptr && strcmp(key, "gemm_sm_margin") == 0) {
         DOLO_REQUIRE(value >= 0 && value <= 64, "gemm_sm_margin must be in [0, 64]");
         g_gemm_sm_margin = value;
+        return DOLO_OK;
+    }
+    if (key != nullptr && strcmp(key, "attn_bwd_experiment") == 0) {
+        g_attn_bwd_experiment = value;  // diagnostic bit mask (timing experiments; results are WRONG when non-zero)
         return DOLO_OK;
     }
     if (key != nullptr && strcmp(key, "gemm_cta_pair") == 0) {

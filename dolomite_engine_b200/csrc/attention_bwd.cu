@@ -31,6 +31,7 @@ struct BwdParams {
     int64_t T;
     int n_groups, q_per_group, n_heads;
     float scale, scale_log2;
+    int experiment;  // diagnostic bit mask, 0 in production (bit 0: skip the dQ reductions, bit 1: skip exp2)
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     const int kv_row = loc.doc_start + j * ATT_TILE;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_align_1024(smem_raw);
     uint8_t* sK = smem;
     uint8_t* sV = sK + TILE_BYTES;
     uint8_t* sQ = sV + TILE_BYTES;                    // [QDO_STAGES]
@@ -495,6 +496,7 @@ extern "C" int dolomite_b200_attn_varlen_bwd(const void* dout, const void* qkv, 
     p.n_heads = nh;
     p.scale = softmax_scale;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
+    p.experiment = dolo_option_attn_bwd_experiment();
     int rc;
     switch (head_dim) {
         case 16: rc = launch_bwd<16>(dout, qkv, row_stride, p, st); break;

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(448, 1)
     const int kv_row = loc.doc_start + j * ATT_TILE;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_align_1024(smem_raw);
     uint8_t* sK = smem;
     uint8_t* sV = sK + TILE_BYTES;
     uint8_t* sQ = sV + TILE_BYTES;             // [2]
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(448, 1)
                 uint32_t o[16];
                 tmem_ld16(t_lane + DQ_COL + c0, o);
                 tmem_ld_wait();
-                if (q_ok) {
+                if (q_ok && !(p.experiment & 1)) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         red_add_v4(dst + c0 + q * 4, __uint_as_float(o[q * 4]), __uint_as_float(o[q * 4 + 1]),

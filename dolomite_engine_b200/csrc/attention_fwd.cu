@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(FWD_THREADS)
     const int row_base = loc.doc_start + q0;                  // global token row of query 0
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_align_1024(smem_raw);
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + TILE_BYTES;                 // [KV_STAGES]
     uint8_t* sV = sK + KV_STAGES * TILE_BYTES;     // [KV_STAGES]

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(320, 1)
     const int row_base_a = loc.doc_start + tile_a * ATT_TILE;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_align_1024(smem_raw);
     uint8_t* sQ = smem;                         // [2] query tiles A, B
     uint8_t* sK = sQ + 2 * TILE_BYTES;          // [2] stages
     uint8_t* sV = sK + 2 * TILE_BYTES;          // [2] stages

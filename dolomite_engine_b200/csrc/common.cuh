@@ -43,6 +43,7 @@ int dolo_option_gemm_cta_pair();     // 1 = dense GEMMs use the CTA-pair (cta_gr
 // communication kernel (NCCL all-gather / reduce-scatter, a few CTAs) occupies some SMs: the GEMM CTAs that do not fit
 // only start when a whole persistent CTA retires.  The sharded data-parallel runtime sets this to NCCL's CTA budget.
 int dolo_option_gemm_sm_margin();
+int dolo_option_attn_bwd_experiment();
 
 // TMA descriptor encode through the driver entry point (no link-time libcuda dependency).
 // rank-2 / rank-3 bf16/f32 tiled maps.  dims/strides innermost first; strides in BYTES for dims >= 1.
@@ -59,6 +60,13 @@ namespace dolo {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// 1024-byte aligned start of the dynamic shared memory window.  Pointer arithmetic on the `extern __shared__` symbol
+// itself (not a round trip through uintptr_t) keeps the shared address space visible to the compiler, so every access
+// through the result compiles to LDS/STS instead of generic LD/ST.
+__device__ __forceinline__ uint8_t* smem_align_1024(uint8_t* smem_raw) {
+    return smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 }
 
 __device__ __forceinline__ bool elect_one() {

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     constexpr int STG_BYTES = A_STAGE_BYTES + B_BYTES;
     static_assert(NSTAGE * STG_BYTES == STAGES * STAGE_BYTES, "both modes use the same 192 KB operand ring");
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_align_1024(smem_raw);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + NSTAGE * A_STAGE_BYTES;
     uint8_t* smem_epi = smem + NSTAGE * STG_BYTES;

@@ -723,6 +723,34 @@ def env_info():
 
 
 # ---------------------------------------------------------------------------------------------
+@case
+def attn_bwd_experiments():
+    """timing-only what-if runs of the attention backward (results are wrong when the mask is non-zero):
+    bit 0 = no dQ reductions, bit 1 = no exp2"""
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+
+    S, B, nh, hd = 4096, 4, 32, 80
+    T = S * B
+    qkv = torch.randn(T, nh * 3 * hd, device="cuda").bfloat16()
+    cu = torch.arange(0, T + 1, S, dtype=torch.int32, device="cuda")
+    scale = hd ** -0.5
+    dout = torch.randn(T, nh * hd, device="cuda").bfloat16()
+    out, lse = k.attn_varlen_fwd(qkv, cu, S, nh, 1, hd, scale)
+    dqkv = torch.empty_like(qkv)
+    res = {}
+    flops = 2.5 * 4.0 * S * S * hd * nh * B / 2
+    for mask in (0, 1, 2, 3, 0):
+        k.set_option("attn_bwd_experiment", mask)
+        ms = _time(lambda: k.attn_varlen_bwd(dout, qkv, out, lse, cu, S, nh, 1, hd, scale, dqkv=dqkv), iters=5)
+        res.setdefault(f"mask{mask}", []).append({"ms": ms, "tflops": flops / ms / 1e9})
+    k.set_option("attn_bwd_experiment", 0)
+    ms = _time(lambda: k.attn_varlen_fwd(qkv, cu, S, nh, 1, hd, scale, out=out), iters=10)
+    res["fwd"] = {"ms": ms, "tflops": flops / 2.5 / ms / 1e9}
+    res["ok"] = True
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case")
