@@ -23,7 +23,7 @@ constexpr int BWD_THREADS = 192;
 struct BwdParams {
     const float* lse;      // [n_heads, T]
     const float* delta;    // [n_heads, T]
-    float* dq_accum;       // [T, n_heads*HD] fp32
+    float* dq_accum;       // [n_heads, T, HD] fp32 (a query tile of one head is one contiguous slab)
     __nv_bfloat16* dqkv;   // [T, row_stride]
     int64_t row_stride;
     const int32_t* cu_seqlens;
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// dq_accum (fp32 [T, n_heads*hd]) -> bf16 q slots of dqkv
+// dq_accum (fp32 [n_heads, T, hd]) -> bf16 q slots of dqkv
 __global__ void attn_dq_finalize_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv,
                                         int64_t row_stride, int64_t T, int n_groups, int q_per_group, int hd) {
     const int n_heads = n_groups * q_per_group;
@@ -85,7 +85,7 @@ __global__ void attn_dq_finalize_kernel(const float* __restrict__ acc, __nv_bflo
         const int e = int(i - t * vec_per_row) * 4;
         const int h = e / hd, d = e - h * hd;
         const int g = h / q_per_group, s = h - g * q_per_group;
-        const float4 v = *reinterpret_cast<const float4*>(acc + t * int64_t(n_heads) * hd + e);
+        const float4 v = *reinterpret_cast<const float4*>(acc + (int64_t(h) * T + t) * hd + d);
         __nv_bfloat16* dst = dqkv + t * row_stride + int64_t(g * (q_per_group + 2) + s) * hd + d;
         uint2 o;
         o.x = pack_bf16(v.x, v.y);
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     };
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(kv_full, 2 * TILE_BYTES);
             load_tile(sK, kv_full, &tq64, &tqR, k_col, kv_row);
             load_tile(sV, kv_full, &tq64, &tqR, v_col, kv_row);
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
             mbar_wait(kv_full, 0, 21);
             const uint32_t k_s = smem_u32(sK), v_s = smem_u32(sV), ds_s = smem_u32(sDS);
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             {
                 const int qi = i * ATT_TILE + r;
                 const bool q_ok = qi < loc.doc_len;
-                float* dst = p.dq_accum + (int64_t(loc.doc_start + qi) * p.n_heads + head) * HD;
+                float* dst = p.dq_accum + (int64_t(head) * p.T + loc.doc_start + qi) * HD;
 #pragma unroll
                 for (int c = 0; c < CH::NCHUNK; ++c) {
                     const int w = CH::width(c);

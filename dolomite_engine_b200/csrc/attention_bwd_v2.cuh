@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(320, 1)
 
     if (warp == 0) {
         // ======================= TMA producer =======================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(kv_full, 2 * TILE_BYTES);
             load_tile(sK, kv_full, &tq64, &tqR, k_col, kv_row);
             load_tile(sV, kv_full, &tq64, &tqR, v_col, kv_row);
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(320, 1)
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc_s = umma_idesc_bf16(128, HALF, false, false);
             mbar_wait(kv_full, 0, 31);
             const uint32_t k_s = smem_u32(sK), v_s = smem_u32(sV);
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(320, 1)
             tc_fence_after();
             const int qi = i * ATT_TILE + r;
             const bool q_ok = qi < loc.doc_len;
-            float* dst = p.dq_accum + (int64_t(loc.doc_start + qi) * p.n_heads + head) * HD;
+            float* dst = p.dq_accum + (int64_t(head) * p.T + loc.doc_start + qi) * HD;
 #pragma unroll 1
             for (int c0 = 0; c0 < HD; c0 += 16) {
                 uint32_t o[16];

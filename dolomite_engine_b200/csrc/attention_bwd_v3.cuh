@@ -20,6 +20,12 @@
 // TMEM columns: S^T[2] 0..127, dP^T[2] 128..255, dV 256.., dK 256+HD.., dQ 256+2HD..  (<= 496 for HD = 80).
 #pragma once
 
+// K, V, 2 x (Q, dO), 2 x dS^T staging, LSE/Delta (2 x 2 x 128 floats), barriers, dQ reduce slab
+template <int HD>
+constexpr int bwd_v3_smem_need() {
+    return 6 * HeadChunks<HD>::TILE_BYTES + 2 * (2 * ATT_TILE * 128) + 4 * ATT_TILE * 4 + 160 + ATT_TILE * HD * 4;
+}
+
 template <int HD>
 __global__ void __launch_bounds__(448, 1)
     attn_bwd_kernel_v3(const __grid_constant__ CUtensorMap tq64, const __grid_constant__ CUtensorMap tqR,
@@ -45,7 +51,14 @@ __global__ void __launch_bounds__(448, 1)
     const int kv_row = loc.doc_start + j * ATT_TILE;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_align_1024(smem_raw);
+    // dQ staging slab (fp32 [128][HD], fed to the TMA reduce-add) makes head_dim 80 use the whole 227 KB: no alignment slack
+    // left, so the dynamic window itself must start 1024-byte aligned (it does: 1 KB driver reservation, no static smem)
+    constexpr bool TIGHT = bwd_v3_smem_need<HD>() + 1024 > 232448;
+    uint8_t* smem = TIGHT ? smem_raw : smem_align_1024(smem_raw);
+    if (TIGHT && (smem_u32(smem_raw) & 1023u) != 0) {
+        if (threadIdx.x == 0) printf("[dolomite_b200] attn_bwd_v3: dynamic shared memory base not 1024-byte aligned\n");
+        __trap();
+    }
     uint8_t* sK = smem;
     uint8_t* sV = sK + TILE_BYTES;
     uint8_t* sQ = sV + TILE_BYTES;             // [2]
@@ -63,6 +76,7 @@ __global__ void __launch_bounds__(448, 1)
     uint64_t* dq_done = bars + 11;       // 128 arrivals: dQ accumulator drained
     uint64_t* dkv_full = bars + 12;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    float* sDQ = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 160);  // [128][HD] fp32
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -97,7 +111,7 @@ __global__ void __launch_bounds__(448, 1)
 
     if (warp == 0) {
         // ======================= TMA producer =======================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(kv_full, 2 * TILE_BYTES);
             load_tile(sK, kv_full, &tq64, &tqR, k_col, kv_row);
             load_tile(sV, kv_full, &tq64, &tqR, v_col, kv_row);
@@ -116,7 +130,7 @@ __global__ void __launch_bounds__(448, 1)
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
-        if (lane == 0) {
+        if (elect_one()) {  // uniform single-thread region: no per-MMA R2UR waterfall loops
             constexpr uint32_t idesc_s = umma_idesc_bf16(128, HALF, false, false);
             mbar_wait(kv_full, 0, 31);
             const uint32_t k_s = smem_u32(sK), v_s = smem_u32(sV);
@@ -175,6 +189,9 @@ __global__ void __launch_bounds__(448, 1)
                                 chunk_desc_mnmajor(q_s + CH::offset(c) + h * HALF * 2 * w, w, k), idesc_ts,
                                 (s > 0 || k > 0) ? 1u : 0u);
                 }
+                // S^T / dP^T of step s+2 go first: the softmax warps are the critical path and must never wait behind the
+                // dQ drain (the dQ MMA below needs the previous tile's accumulator drained by the red.add warps)
+                if (s + 2 < n_steps) issue_A(s + 2);
                 if (h == 1) {
                     if (it > 0) {
                         mbar_wait(dq_done, uint32_t(it - 1) & 1, 34);  // dQ accumulator drained
@@ -193,7 +210,6 @@ __global__ void __launch_bounds__(448, 1)
                     umma_commit(&dq_full[it & 1]);
                     umma_commit(&qdo_empty[stage]);
                 }
-                if (s + 2 < n_steps) issue_A(s + 2);
                 if (s == n_steps - 1) umma_commit(dkv_full);
             }
         }
@@ -208,100 +224,111 @@ __global__ void __launch_bounds__(448, 1)
         const bool key_ok = kj < loc.doc_len;
         const bool tile_full = (j + 1) * ATT_TILE <= loc.doc_len;  // every key row of this CTA is inside the document
         const float LOG2E = 1.4426950408889634f;
-        for (int it = 0; it < n_it; ++it) {
+        // LSE (log2 units) / Delta of a query tile: thread t < 128 fetches lse[t], thread 128 + t fetches delta[t].  The
+        // fetch for tile it+1 is issued while tile it is processed (global latency off the critical path).
+        auto fetch_stat = [&](int it) -> float {
             const int s_head = it / n_i, i = j + (it - s_head * n_i);
             const int head = group * p.q_per_group + s_head;
+            const int qi = i * ATT_TILE + (tid256 & (ATT_TILE - 1));
+            const bool q_ok = qi < loc.doc_len;
+            const int64_t off = int64_t(head) * p.T + loc.doc_start + qi;
+            if (tid256 < ATT_TILE) return q_ok ? p.lse[off] * LOG2E : INFINITY;
+            return q_ok ? p.delta[off] : 0.f;
+        };
+        float stat_next = fetch_stat(0);
+
+        for (int it = 0; it < n_it; ++it) {
+            const int s_head = it / n_i, i = j + (it - s_head * n_i);
             float* lse_s = sLSE + (it & 1) * ATT_TILE;
             float* del_s = sDelta + (it & 1) * ATT_TILE;
-            if (tid256 < ATT_TILE) {
-                const int qi = i * ATT_TILE + tid256;
-                float l = INFINITY;
-                if (qi < loc.doc_len) l = p.lse[int64_t(head) * p.T + loc.doc_start + qi] * LOG2E;
-                lse_s[tid256] = l;
-            } else {
-                const int q = tid256 - ATT_TILE;
-                const int qi = i * ATT_TILE + q;
-                float d = 0.f;
-                if (qi < loc.doc_len) d = p.delta[int64_t(head) * p.T + loc.doc_start + qi];
-                del_s[q] = d;
-            }
+            (tid256 < ATT_TILE ? lse_s : del_s)[tid256 & (ATT_TILE - 1)] = stat_next;
             named_bar_sync(2, 256);
+            if (it + 1 < n_it) stat_next = fetch_stat(it + 1);
             if (it >= 2) mbar_wait(&dq_full[it & 1], uint32_t((it >> 1) - 1) & 1, 35);  // dS smem buffer free again
             const bool need_mask = (i == j) || !tile_full;
+            const bool diag = (i == j);
             uint8_t* ds_buf = sDS + (it & 1) * DS_BYTES;
+
+            // one 16-column sub-chunk: P^T = exp2(S^T*scale - lse), dS^T = scale * P^T o (dP^T - delta) -> bf16 pairs,
+            // written to TMEM (A operands of dV / dK) and, for dS^T, to the MN-major smem tile (A operand of dQ)
+            auto process16 = [&](const uint32_t (&sv)[16], const uint32_t (&dv)[16], int h, int b, int sc) {
+                const int cbase = h * HALF + wg * 32 + sc * 16;  // first query column (inside the 128-query tile)
+                uint32_t pp[8], dd[8];
+                if (need_mask) {
+#pragma unroll
+                    for (int c2 = 0; c2 < 16; c2 += 2) {
+                        float pv[2], dsv[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int c = cbase + c2 + u;
+                            float pe = fast_exp2(__uint_as_float(sv[c2 + u]) * p.scale_log2 - lse_s[c]);
+                            if (!key_ok || (diag && r > c)) pe = 0.f;
+                            pv[u] = pe;
+                            dsv[u] = pe * (__uint_as_float(dv[c2 + u]) - del_s[c]) * p.scale;
+                        }
+                        pp[c2 >> 1] = pack_bf16(pv[0], pv[1]);
+                        dd[c2 >> 1] = pack_bf16(dsv[0], dsv[1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int c4 = 0; c4 < 16; c4 += 4) {
+                        const float4 l4 = *reinterpret_cast<const float4*>(lse_s + cbase + c4);
+                        const float4 d4 = *reinterpret_cast<const float4*>(del_s + cbase + c4);
+                        const float p0 = fast_exp2(__uint_as_float(sv[c4]) * p.scale_log2 - l4.x);
+                        const float p1 = fast_exp2(__uint_as_float(sv[c4 + 1]) * p.scale_log2 - l4.y);
+                        const float p2 = fast_exp2(__uint_as_float(sv[c4 + 2]) * p.scale_log2 - l4.z);
+                        const float p3 = fast_exp2(__uint_as_float(sv[c4 + 3]) * p.scale_log2 - l4.w);
+                        pp[c4 >> 1] = pack_bf16(p0, p1);
+                        pp[(c4 >> 1) + 1] = pack_bf16(p2, p3);
+                        dd[c4 >> 1] = pack_bf16(p0 * p.scale * (__uint_as_float(dv[c4]) - d4.x),
+                                                p1 * p.scale * (__uint_as_float(dv[c4 + 1]) - d4.y));
+                        dd[(c4 >> 1) + 1] = pack_bf16(p2 * p.scale * (__uint_as_float(dv[c4 + 2]) - d4.z),
+                                                      p3 * p.scale * (__uint_as_float(dv[c4 + 3]) - d4.w));
+                    }
+                }
+                // bf16 P^T / dS^T alias fp32 columns this thread has already consumed: group wg reads fp32 columns
+                // [32wg + 16sc, +16) and writes bf16 columns [32wg + 8sc, +8) -- always inside its own consumed range
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::"r"(pp[0]),
+                    "r"(pp[1]), "r"(pp[2]), "r"(pp[3]), "r"(pp[4]), "r"(pp[5]), "r"(pp[6]), "r"(pp[7]),
+                    "r"(t_lane + ST_COL + b * HALF + wg * 32 + sc * 8)
+                    : "memory");
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::"r"(dd[0]),
+                    "r"(dd[1]), "r"(dd[2]), "r"(dd[3]), "r"(dd[4]), "r"(dd[5]), "r"(dd[6]), "r"(dd[7]),
+                    "r"(t_lane + DP_COL + b * HALF + wg * 32 + sc * 8)
+                    : "memory");
+                uint8_t* rowp = ds_buf + h * (ATT_TILE * 128) + r * 128;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int piece = wg * 4 + sc * 2 + q;
+                    *reinterpret_cast<uint4*>(rowp + ((piece ^ (r & 7)) << 4)) =
+                        make_uint4(dd[q * 4], dd[q * 4 + 1], dd[q * 4 + 2], dd[q * 4 + 3]);
+                }
+            };
+
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
                 const int b = h;
                 mbar_wait(&sdp_full[b], uint32_t(it) & 1, 36);
                 tc_fence_after();
-                const int cbase = h * HALF + wg * 32;  // first query column (inside the 128-query tile) of this thread
-                uint8_t* rowp = ds_buf + h * (ATT_TILE * 128) + r * 128;
-#pragma unroll
-                for (int sc = 0; sc < 2; ++sc) {  // two sub-chunks of 16 query columns
-                    uint32_t sv[16], dv[16];
-                    tmem_ld16(t_lane + ST_COL + b * HALF + wg * 32 + sc * 16, sv);
-                    tmem_ld16(t_lane + DP_COL + b * HALF + wg * 32 + sc * 16, dv);
-                    float ls[16], dl[16];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 a = *reinterpret_cast<const float4*>(lse_s + cbase + sc * 16 + q * 4);
-                        const float4 d4 = *reinterpret_cast<const float4*>(del_s + cbase + sc * 16 + q * 4);
-                        ls[q * 4] = a.x; ls[q * 4 + 1] = a.y; ls[q * 4 + 2] = a.z; ls[q * 4 + 3] = a.w;
-                        dl[q * 4] = d4.x; dl[q * 4 + 1] = d4.y; dl[q * 4 + 2] = d4.z; dl[q * 4 + 3] = d4.w;
-                    }
-                    tmem_ld_wait();
-                    uint32_t pp[8], dd[8];
-                    if (need_mask) {
-                        const bool diag = (i == j);
-#pragma unroll
-                        for (int c2 = 0; c2 < 16; c2 += 2) {
-                            float pv[2], dsv[2];
-#pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                const int c = cbase + sc * 16 + c2 + u;
-                                float pe = fast_exp2(__uint_as_float(sv[c2 + u]) * p.scale_log2 - ls[c2 + u]);
-                                if (!key_ok || (diag && r > c)) pe = 0.f;
-                                pv[u] = pe;
-                                dsv[u] = pe * (__uint_as_float(dv[c2 + u]) - dl[c2 + u]) * p.scale;
-                            }
-                            pp[c2 >> 1] = pack_bf16(pv[0], pv[1]);
-                            dd[c2 >> 1] = pack_bf16(dsv[0], dsv[1]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int c2 = 0; c2 < 16; c2 += 2) {
-                            const float p0 = fast_exp2(__uint_as_float(sv[c2]) * p.scale_log2 - ls[c2]);
-                            const float p1 = fast_exp2(__uint_as_float(sv[c2 + 1]) * p.scale_log2 - ls[c2 + 1]);
-                            const float d0 = p0 * p.scale * (__uint_as_float(dv[c2]) - dl[c2]);
-                            const float d1 = p1 * p.scale * (__uint_as_float(dv[c2 + 1]) - dl[c2 + 1]);
-                            pp[c2 >> 1] = pack_bf16(p0, p1);
-                            dd[c2 >> 1] = pack_bf16(d0, d1);
-                        }
-                    }
-                    // bf16 P^T / dS^T alias fp32 columns this thread has already consumed: group wg reads fp32 columns
-                    // [32wg + 16sc, +16) and writes bf16 columns [32wg + 8sc, +8) -- always inside its own consumed range
-                    {
-                        uint32_t p8[8], d8[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) { p8[q] = pp[q]; d8[q] = dd[q]; }
-                        asm volatile(
-                            "tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::"r"(p8[0]),
-                            "r"(p8[1]), "r"(p8[2]), "r"(p8[3]), "r"(p8[4]), "r"(p8[5]), "r"(p8[6]), "r"(p8[7]),
-                            "r"(t_lane + ST_COL + b * HALF + wg * 32 + sc * 8)
-                            : "memory");
-                        asm volatile(
-                            "tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::"r"(d8[0]),
-                            "r"(d8[1]), "r"(d8[2]), "r"(d8[3]), "r"(d8[4]), "r"(d8[5]), "r"(d8[6]), "r"(d8[7]),
-                            "r"(t_lane + DP_COL + b * HALF + wg * 32 + sc * 8)
-                            : "memory");
-                    }
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int piece = wg * 4 + sc * 2 + q;
-                        uint4 v = make_uint4(dd[q * 4], dd[q * 4 + 1], dd[q * 4 + 2], dd[q * 4 + 3]);
-                        *reinterpret_cast<uint4*>(rowp + ((piece ^ (r & 7)) << 4)) = v;
-                    }
-                }
+                // software pipeline over the two 16-column sub-chunks: the TMEM loads of sub-chunk 1 are in flight while
+                // sub-chunk 0 is computed (tcgen05.ld latency was ~20 % of the softmax warps' time in the v3 ncu capture)
+                uint32_t sv0[16], dv0[16], sv1[16], dv1[16];
+                const uint32_t s_addr = t_lane + ST_COL + b * HALF + wg * 32;
+                const uint32_t d_addr = t_lane + DP_COL + b * HALF + wg * 32;
+                tmem_ld16(s_addr, sv0);
+                tmem_ld16(d_addr, dv0);
+                tmem_ld_wait();
+                reg_fence16(sv0);
+                reg_fence16(dv0);
+                tmem_ld16(s_addr + 16, sv1);
+                tmem_ld16(d_addr + 16, dv1);
+                process16(sv0, dv0, h, b, 0);
+                tmem_ld_wait();
+                reg_fence16(sv1);
+                reg_fence16(dv1);
+                process16(sv1, dv1, h, b, 1);
                 tmem_st_wait();
                 tc_fence_before();
                 fence_proxy_async_smem();
@@ -336,32 +363,46 @@ __global__ void __launch_bounds__(448, 1)
         }
     } else {
         // ======================= dQ drain warps (2, 3, 12, 13): TMEM lane == query row =======================
+        // Each warp copies its 32 rows of the dQ accumulator to a private shared-memory slab and hands the slab to the
+        // TMA engine as ONE bulk fp32 reduce-add into dq_accum[head, q0 + 32*sub .., :] (contiguous in the [heads, T, HD]
+        // workspace).  The per-thread red.global.add.v4.f32 version spent 26 % of the kernel in L2 atomic traffic
+        // (profiles: attn_bwd_experiments, 1.88 ms -> 1.38 ms with the reductions removed).
         const int sub = warp & 3;
-        const int r = sub * 32 + lane;
         const uint32_t t_lane = tmem_base + (uint32_t(sub * 32) << 16);
+        float* slab = sDQ + (sub * 32) * HD;
+        float* my_row = slab + lane * HD;
+        const uint32_t slab_u32 = smem_u32(slab);
         for (int it = 0; it < n_it; ++it) {
             const int s_head = it / n_i, i = j + (it - s_head * n_i);
             const int head = group * p.q_per_group + s_head;
             mbar_wait(&dq_full[it & 1], uint32_t(it >> 1) & 1, 38);
             tc_fence_after();
-            const int qi = i * ATT_TILE + r;
-            const bool q_ok = qi < loc.doc_len;
-            float* dst = p.dq_accum + (int64_t(loc.doc_start + qi) * p.n_heads + head) * HD;
+            if (lane == 0) tma_store_wait_read<0>();  // the previous tile's reduce has finished reading the slab
+            __syncwarp();
 #pragma unroll 1
             for (int c0 = 0; c0 < HD; c0 += 16) {
                 uint32_t o[16];
                 tmem_ld16(t_lane + DQ_COL + c0, o);
                 tmem_ld_wait();
-                if (q_ok && !(p.experiment & 1)) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        red_add_v4(dst + c0 + q * 4, __uint_as_float(o[q * 4]), __uint_as_float(o[q * 4 + 1]),
-                                   __uint_as_float(o[q * 4 + 2]), __uint_as_float(o[q * 4 + 3]));
-                }
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4*>(my_row + c0 + q * 4) = make_uint4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
             }
             tc_fence_before();
-            mbar_arrive(dq_done);
+            mbar_arrive(dq_done);  // accumulator free for the next dQ MMA
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                const int q0 = i * ATT_TILE + sub * 32;
+                int rows = loc.doc_len - q0;
+                rows = rows > 32 ? 32 : rows;
+                if (rows > 0 && !(p.experiment & 1))
+                    bulk_reduce_add_f32(p.dq_accum + (int64_t(head) * p.T + loc.doc_start + q0) * HD, slab_u32,
+                                        uint32_t(rows) * HD * 4);
+                tma_store_commit();
+            }
         }
+        if (lane == 0) tma_store_wait_all<0>();  // shared memory must outlive the last reduce
     }
 
     tc_fence_before();
@@ -380,8 +421,9 @@ int launch_bwd_v3(const void* dout, const void* qkv, int64_t row_stride, const B
     if (rc) return rc;
     rc = make_maps<HD>(dout, int64_t(p.n_heads) * HD, p.T, &to64, &toR);
     if (rc) return rc;
-    constexpr int smem_bytes = 1024 + 6 * CH::TILE_BYTES + 2 * (2 * ATT_TILE * 128) + 4 * ATT_TILE * 4 + 160;
-    static_assert(smem_bytes <= 232448, "attention backward v2 shared memory budget exceeded");
+    constexpr int need = bwd_v3_smem_need<HD>();
+    constexpr int smem_bytes = (need + 1024 > 232448) ? need : need + 1024;
+    static_assert(smem_bytes <= 232448, "attention backward v3 shared memory budget exceeded");
     auto kern = attn_bwd_kernel_v3<HD>;
     static bool attr_set = false;
     if (!attr_set) {

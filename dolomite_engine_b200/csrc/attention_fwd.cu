@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(FWD_THREADS)
     };
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(q_full, TILE_BYTES);
             load_tile(sQ, q_full, q_col, row_base);
             int stage = 0;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(FWD_THREADS)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {  // uniform single-thread region: no per-MMA R2UR waterfall loops
             constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, false, false);
             mbar_wait(q_full, 0, 11);
             int stage = 0;
@@ -167,12 +167,11 @@ __global__ void __launch_bounds__(FWD_THREADS)
             // (ncu on the first version: 13.7 instructions per score, most of them per-element mask selects).
             float mx = m_run;
             if (!diag) {
+                // software-pipelined TMEM reads: chunk ch+1 is in flight while chunk ch is reduced (the exposed
+                // tcgen05.ld latency, not issue slots, bounded the first version: ncu issue-active 37 %)
                 float mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld32(t_lane + ch * 32, v);
-                    tmem_ld_wait();
+                uint32_t va[32], vb[32];
+                auto fold = [&](const uint32_t (&v)[32]) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
                         mx = fmaxf(mx, __uint_as_float(v[i]));
@@ -180,7 +179,23 @@ __global__ void __launch_bounds__(FWD_THREADS)
                         mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
                         mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
                     }
-                }
+                };
+                tmem_ld32(t_lane, va);
+                tmem_ld_wait();
+                reg_fence32(va);
+                tmem_ld32(t_lane + 32, vb);
+                fold(va);
+                tmem_ld_wait();
+                reg_fence32(vb);
+                tmem_ld32(t_lane + 64, va);
+                fold(vb);
+                tmem_ld_wait();
+                reg_fence32(va);
+                tmem_ld32(t_lane + 96, vb);
+                fold(va);
+                tmem_ld_wait();
+                reg_fence32(vb);
+                fold(vb);
                 mx = fmaxf(fmaxf(mx, mx1), fmaxf(mx2, mx3));
             } else {
 #pragma unroll 1
@@ -216,11 +231,8 @@ __global__ void __launch_bounds__(FWD_THREADS)
             float lsum = 0.f, lsum1 = 0.f;
             const float neg_m = -m_scaled;
             if (!diag) {
-#pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld32(t_lane + ch * 32, v);
-                    tmem_ld_wait();
+                uint32_t va[32], vb[32];
+                auto expo = [&](const uint32_t (&v)[32], int ch) {
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
@@ -230,8 +242,24 @@ __global__ void __launch_bounds__(FWD_THREADS)
                         lsum1 += p1;
                         pk[i >> 1] = pack_bf16(p0, p1);
                     }
-                    tmem_st16(t_lane + ch * 16, pk);
-                }
+                    tmem_st16(t_lane + ch * 16, pk);  // bf16 P chunk ch aliases fp32 S columns [16ch, 16ch+16): consumed
+                };
+                tmem_ld32(t_lane, va);
+                tmem_ld_wait();
+                reg_fence32(va);
+                tmem_ld32(t_lane + 32, vb);
+                expo(va, 0);
+                tmem_ld_wait();
+                reg_fence32(vb);
+                tmem_ld32(t_lane + 64, va);
+                expo(vb, 1);
+                tmem_ld_wait();
+                reg_fence32(va);
+                tmem_ld32(t_lane + 96, vb);
+                expo(va, 2);
+                tmem_ld_wait();
+                reg_fence32(vb);
+                expo(vb, 3);
             } else {
 #pragma unroll 1
                 for (int ch = 0; ch < 4; ++ch) {

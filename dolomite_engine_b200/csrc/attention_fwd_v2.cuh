@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(320, 1)
     };
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(q_full, (has_b ? 2 : 1) * TILE_BYTES);
             load_tile(sQ, q_full, q_col, row_base_a);
             if (has_b) load_tile(sQ + TILE_BYTES, q_full, q_col, row_base_a + ATT_TILE);
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(320, 1)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, false, false);
             mbar_wait(q_full, 0, 41);
             // S_x(j) = Q_x K_j^T into TMEM columns [128x, 128x+128)

@@ -169,6 +169,14 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_all() {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+// Bulk (TMA engine) fp32 reduce-add of a contiguous shared-memory slab into global memory: one instruction replaces
+// bytes/16 per-thread red.global.add.v4.f32 and is applied by the L2 in full lines.  16-byte aligned, size % 16 == 0.
+// Belongs to the thread's bulk async-group (tma_store_commit / tma_store_wait_*).
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, uint32_t smem_src, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(smem_src), "r"(bytes)
+                 : "memory");
+}
 
 // ---------------- tcgen05 ----------------
 template <int NCOLS>
@@ -314,6 +322,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Compile-time only: "redefines" the 16 registers of an earlier tcgen05.ld after its wait, so that no consumer can be
+// scheduled above the wait when several loads are kept in flight (software-pipelined TMEM reads).
+__device__ __forceinline__ void reg_fence16(uint32_t (&r)[16]) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                      "+r"(r[15]));
+}
+__device__ __forceinline__ void reg_fence32(uint32_t (&r)[32]) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                      "+r"(r[15]));
+    asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                      "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                      "+r"(r[30]), "+r"(r[31]));
+}
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(

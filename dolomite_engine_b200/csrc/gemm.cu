@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (elect_one()) {  // uniform single-thread region: ptxas keeps descriptors in uniform registers
             int stage = 0;
             uint32_t phase = 0;
             for (int t = worker; t < num_tiles; t += num_workers) {
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0 && cta_rank == 0) {  // pair mode: only the leader CTA issues (for both SMs)
+        if (cta_rank == 0 && elect_one()) {  // pair mode: only the leader CTA issues (for both SMs)
             constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * BM : BM, BN, A_MN, B_MN);
             int stage = 0;
             uint32_t phase = 0;
