@@ -38,7 +38,7 @@ int dolo_option_attn_bwd_experiment() { return g_attn_bwd_experiment; }
 
 extern "C" int dolomite_b200_set_option(const char* key, int value) {
     if (key != nullptr && strcmp(key, "attn_bwd_version") == 0) {
-        DOLO_REQUIRE(value >= 1 && value <= 3, "attn_bwd_version must be 1, 2 or 3");
+        DOLO_REQUIRE(value >= 1 && value <= 4, "attn_bwd_version must be 1, 2, 3 or 4");
         g_attn_bwd_version = value;
         return DOLO_OK;
     }

@@ -26,8 +26,11 @@ constexpr int bwd_v3_smem_need() {
     return 6 * HeadChunks<HD>::TILE_BYTES + 2 * (2 * ATT_TILE * 128) + 4 * ATT_TILE * 4 + 160 + ATT_TILE * HD * 4;
 }
 
-template <int HD>
-__global__ void __launch_bounds__(448, 1)
+// NG = number of softmax warp groups (4 warps each): every group owns 64 / NG query columns of a half step.  NG = 4
+// (704 threads, <= 88 registers) halves the dependent instruction chain per warp and doubles the warps each scheduler can
+// interleave; the softmax warps, not the tensor pipe, bound the NG = 2 version (ncu: tensor pipe 20 %, issue 25 %).
+template <int HD, int NG>
+__global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
     attn_bwd_kernel_v3(const __grid_constant__ CUtensorMap tq64, const __grid_constant__ CUtensorMap tqR,
                        const __grid_constant__ CUtensorMap to64, const __grid_constant__ CUtensorMap toR,
                        const BwdParams p) {
@@ -35,6 +38,11 @@ __global__ void __launch_bounds__(448, 1)
     static_assert(256 + 3 * HD <= 512, "v2 needs a private dQ accumulator (head_dim <= 80)");
     constexpr int TILE_BYTES = CH::TILE_BYTES;
     constexpr int HALF = 64;
+    constexpr int COLS = HALF / NG;       // query columns per softmax warp per half step
+    constexpr int NSC = COLS / 16;        // 16-column sub-chunks per warp
+    constexpr int SOFTMAX_THREADS = 128 * NG;
+    constexpr int FIRST_TAIL_WARP = 4 + 4 * NG;  // two more dQ drain warps after the softmax warps
+    static_assert(NG == 2 || NG == 4, "two or four softmax groups");
     constexpr uint32_t ST_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 256 + HD, DQ_COL = 256 + 2 * HD;
     constexpr int DS_BYTES = 2 * ATT_TILE * 128;  // 128 keys x 128 queries bf16 (two 64-query MN chunks)
 
@@ -88,7 +96,7 @@ __global__ void __launch_bounds__(448, 1)
             mbar_init(&qdo_full[i], 1);
             mbar_init(&qdo_empty[i], 1);
             mbar_init(&sdp_full[i], 1);
-            mbar_init(&pds_ready[i], 256);
+            mbar_init(&pds_ready[i], SOFTMAX_THREADS);
             mbar_init(&dq_full[i], 1);
         }
         mbar_init(dq_done, 128);
@@ -180,12 +188,12 @@ __global__ void __launch_bounds__(448, 1)
                     const uint32_t idesc_ts = umma_idesc_bf16(128, w, false, true);
 #pragma unroll
                     for (int k = 0; k < HALF / 16; ++k)  // dV += P^T dO  (contraction over the 64 queries of this half)
-                        umma_ts(tmem_base + DV_COL + CH::col(c), tmem_base + ST_COL + b * HALF + (k >> 1) * 32 + (k & 1) * 8,
+                        umma_ts(tmem_base + DV_COL + CH::col(c), tmem_base + ST_COL + b * HALF + ((16 * k) / COLS) * COLS + (((16 * k) % COLS) / 16) * 8,
                                 chunk_desc_mnmajor(do_s + CH::offset(c) + h * HALF * 2 * w, w, k), idesc_ts,
                                 (s > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
                     for (int k = 0; k < HALF / 16; ++k)  // dK += dS^T Q
-                        umma_ts(tmem_base + DK_COL + CH::col(c), tmem_base + DP_COL + b * HALF + (k >> 1) * 32 + (k & 1) * 8,
+                        umma_ts(tmem_base + DK_COL + CH::col(c), tmem_base + DP_COL + b * HALF + ((16 * k) / COLS) * COLS + (((16 * k) % COLS) / 16) * 8,
                                 chunk_desc_mnmajor(q_s + CH::offset(c) + h * HALF * 2 * w, w, k), idesc_ts,
                                 (s > 0 || k > 0) ? 1u : 0u);
                 }
@@ -213,12 +221,12 @@ __global__ void __launch_bounds__(448, 1)
                 if (s == n_steps - 1) umma_commit(dkv_full);
             }
         }
-    } else if (warp >= 4 && warp < 12) {
+    } else if (warp >= 4 && warp < FIRST_TAIL_WARP) {
         // ======================= softmax warps: 2 groups x (one key row per thread, 32 query columns) =======================
         const int wg = (warp - 4) >> 2;  // column group: query columns [32*wg, 32*wg+32) of each 64-query half
         const int sub = warp & 3;
         const int r = sub * 32 + lane;
-        const int tid256 = (warp - 4) * 32 + lane;
+        const int tidsm = (warp - 4) * 32 + lane;
         const uint32_t t_lane = tmem_base + (uint32_t(sub * 32) << 16);
         const int kj = j * ATT_TILE + r;
         const bool key_ok = kj < loc.doc_len;
@@ -229,11 +237,12 @@ __global__ void __launch_bounds__(448, 1)
         auto fetch_stat = [&](int it) -> float {
             const int s_head = it / n_i, i = j + (it - s_head * n_i);
             const int head = group * p.q_per_group + s_head;
-            const int qi = i * ATT_TILE + (tid256 & (ATT_TILE - 1));
+            const int qi = i * ATT_TILE + (tidsm & (ATT_TILE - 1));
             const bool q_ok = qi < loc.doc_len;
             const int64_t off = int64_t(head) * p.T + loc.doc_start + qi;
-            if (tid256 < ATT_TILE) return q_ok ? p.lse[off] * LOG2E : INFINITY;
-            return q_ok ? p.delta[off] : 0.f;
+            if (tidsm < ATT_TILE) return q_ok ? p.lse[off] * LOG2E : INFINITY;
+            if (tidsm < 2 * ATT_TILE) return q_ok ? p.delta[off] : 0.f;
+            return 0.f;
         };
         float stat_next = fetch_stat(0);
 
@@ -241,8 +250,8 @@ __global__ void __launch_bounds__(448, 1)
             const int s_head = it / n_i, i = j + (it - s_head * n_i);
             float* lse_s = sLSE + (it & 1) * ATT_TILE;
             float* del_s = sDelta + (it & 1) * ATT_TILE;
-            (tid256 < ATT_TILE ? lse_s : del_s)[tid256 & (ATT_TILE - 1)] = stat_next;
-            named_bar_sync(2, 256);
+            if (tidsm < 2 * ATT_TILE) (tidsm < ATT_TILE ? lse_s : del_s)[tidsm & (ATT_TILE - 1)] = stat_next;
+            named_bar_sync(2, SOFTMAX_THREADS);
             if (it + 1 < n_it) stat_next = fetch_stat(it + 1);
             if (it >= 2) mbar_wait(&dq_full[it & 1], uint32_t((it >> 1) - 1) & 1, 35);  // dS smem buffer free again
             const bool need_mask = (i == j) || !tile_full;
@@ -252,7 +261,7 @@ __global__ void __launch_bounds__(448, 1)
             // one 16-column sub-chunk: P^T = exp2(S^T*scale - lse), dS^T = scale * P^T o (dP^T - delta) -> bf16 pairs,
             // written to TMEM (A operands of dV / dK) and, for dS^T, to the MN-major smem tile (A operand of dQ)
             auto process16 = [&](const uint32_t (&sv)[16], const uint32_t (&dv)[16], int h, int b, int sc) {
-                const int cbase = h * HALF + wg * 32 + sc * 16;  // first query column (inside the 128-query tile)
+                const int cbase = h * HALF + wg * COLS + sc * 16;  // first query column (inside the 128-query tile)
                 uint32_t pp[8], dd[8];
                 if (need_mask) {
 #pragma unroll
@@ -291,17 +300,17 @@ __global__ void __launch_bounds__(448, 1)
                 asm volatile(
                     "tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::"r"(pp[0]),
                     "r"(pp[1]), "r"(pp[2]), "r"(pp[3]), "r"(pp[4]), "r"(pp[5]), "r"(pp[6]), "r"(pp[7]),
-                    "r"(t_lane + ST_COL + b * HALF + wg * 32 + sc * 8)
+                    "r"(t_lane + ST_COL + b * HALF + wg * COLS + sc * 8)
                     : "memory");
                 asm volatile(
                     "tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::"r"(dd[0]),
                     "r"(dd[1]), "r"(dd[2]), "r"(dd[3]), "r"(dd[4]), "r"(dd[5]), "r"(dd[6]), "r"(dd[7]),
-                    "r"(t_lane + DP_COL + b * HALF + wg * 32 + sc * 8)
+                    "r"(t_lane + DP_COL + b * HALF + wg * COLS + sc * 8)
                     : "memory");
                 uint8_t* rowp = ds_buf + h * (ATT_TILE * 128) + r * 128;
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    const int piece = wg * 4 + sc * 2 + q;
+                    const int piece = wg * (COLS / 8) + sc * 2 + q;
                     *reinterpret_cast<uint4*>(rowp + ((piece ^ (r & 7)) << 4)) =
                         make_uint4(dd[q * 4], dd[q * 4 + 1], dd[q * 4 + 2], dd[q * 4 + 3]);
                 }
@@ -314,21 +323,26 @@ __global__ void __launch_bounds__(448, 1)
                 tc_fence_after();
                 // software pipeline over the two 16-column sub-chunks: the TMEM loads of sub-chunk 1 are in flight while
                 // sub-chunk 0 is computed (tcgen05.ld latency was ~20 % of the softmax warps' time in the v3 ncu capture)
-                uint32_t sv0[16], dv0[16], sv1[16], dv1[16];
-                const uint32_t s_addr = t_lane + ST_COL + b * HALF + wg * 32;
-                const uint32_t d_addr = t_lane + DP_COL + b * HALF + wg * 32;
+                const uint32_t s_addr = t_lane + ST_COL + b * HALF + wg * COLS;
+                const uint32_t d_addr = t_lane + DP_COL + b * HALF + wg * COLS;
+                uint32_t sv0[16], dv0[16];
                 tmem_ld16(s_addr, sv0);
                 tmem_ld16(d_addr, dv0);
                 tmem_ld_wait();
                 reg_fence16(sv0);
                 reg_fence16(dv0);
-                tmem_ld16(s_addr + 16, sv1);
-                tmem_ld16(d_addr + 16, dv1);
-                process16(sv0, dv0, h, b, 0);
-                tmem_ld_wait();
-                reg_fence16(sv1);
-                reg_fence16(dv1);
-                process16(sv1, dv1, h, b, 1);
+                if constexpr (NSC == 2) {
+                    uint32_t sv1[16], dv1[16];
+                    tmem_ld16(s_addr + 16, sv1);
+                    tmem_ld16(d_addr + 16, dv1);
+                    process16(sv0, dv0, h, b, 0);
+                    tmem_ld_wait();
+                    reg_fence16(sv1);
+                    reg_fence16(dv1);
+                    process16(sv1, dv1, h, b, 1);
+                } else {
+                    process16(sv0, dv0, h, b, 0);
+                }
                 tmem_st_wait();
                 tc_fence_before();
                 fence_proxy_async_smem();
@@ -339,10 +353,15 @@ __global__ void __launch_bounds__(448, 1)
         mbar_wait(dkv_full, 0, 37);
         tc_fence_after();
         {
-            const uint32_t src_col = (wg == 0) ? DK_COL : DV_COL;
-            __nv_bfloat16* drow = p.dqkv + int64_t(kv_row + r) * p.row_stride + (wg == 0 ? k_col : v_col);
+            // even groups store dK_j, odd groups dV_j; with four groups each takes half of the 16-column chunks
+            const bool is_dk = (wg & 1) == 0;
+            const uint32_t src_col = is_dk ? DK_COL : DV_COL;
+            __nv_bfloat16* drow = p.dqkv + int64_t(kv_row + r) * p.row_stride + (is_dk ? k_col : v_col);
+            constexpr int NCH = HD / 16, SPLIT = (NCH + 1) / 2;
+            const int ch0 = (NG == 2) ? 0 : ((wg >> 1) == 0 ? 0 : SPLIT);
+            const int ch1 = (NG == 2) ? NCH : ((wg >> 1) == 0 ? SPLIT : NCH);
 #pragma unroll 1
-            for (int c0 = 0; c0 < HD; c0 += 16) {
+            for (int c0 = ch0 * 16; c0 < ch1 * 16; c0 += 16) {
                 uint32_t a[16];
                 tmem_ld16(t_lane + src_col + c0, a);
                 tmem_ld_wait();
@@ -413,7 +432,7 @@ __global__ void __launch_bounds__(448, 1)
     }
 }
 
-template <int HD>
+template <int HD, int NG>
 int launch_bwd_v3(const void* dout, const void* qkv, int64_t row_stride, const BwdParams& p, cudaStream_t st) {
     using CH = HeadChunks<HD>;
     CUtensorMap tq64, tqR, to64, toR;
@@ -424,7 +443,7 @@ int launch_bwd_v3(const void* dout, const void* qkv, int64_t row_stride, const B
     constexpr int need = bwd_v3_smem_need<HD>();
     constexpr int smem_bytes = (need + 1024 > 232448) ? need : need + 1024;
     static_assert(smem_bytes <= 232448, "attention backward v3 shared memory budget exceeded");
-    auto kern = attn_bwd_kernel_v3<HD>;
+    auto kern = attn_bwd_kernel_v3<HD, NG>;
     static bool attr_set = false;
     if (!attr_set) {
         DOLO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -432,7 +451,7 @@ int launch_bwd_v3(const void* dout, const void* qkv, int64_t row_stride, const B
     }
     const int64_t max_tiles = (p.T + ATT_TILE - 1) / ATT_TILE + p.n_docs;
     dim3 grid((unsigned)max_tiles, (unsigned)p.n_groups);
-    kern<<<grid, 448, smem_bytes, st>>>(tq64, tqR, to64, toR, p);
+    kern<<<grid, 32 * (6 + 4 * NG), smem_bytes, st>>>(tq64, tqR, to64, toR, p);
     DOLO_LAUNCH_OK("attn_varlen_bwd_v2");
     return DOLO_OK;
 }

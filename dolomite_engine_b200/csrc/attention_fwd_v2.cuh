@@ -33,7 +33,7 @@ __device__ __forceinline__ TilePairLoc locate_tile_pair(const int32_t* __restric
 }
 
 template <int HD>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __maxnreg__(200)
     attn_fwd_kernel_v2(const __grid_constant__ CUtensorMap tmap64, const __grid_constant__ CUtensorMap tmapR,
                        const FwdParams p) {
     using CH = HeadChunks<HD>;
@@ -199,22 +199,65 @@ __global__ void __launch_bounds__(320, 1)
                 const bool diag = (j == my_n_kv - 1);
                 const int kbase = j * ATT_TILE;
                 float mx = m_run;
-                if (!diag) {
-                    float mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+                float lsum = 0.f, lsum1 = 0.f;
+                float alpha;
+                // O *= alpha (previous PV has completed: s_full is committed after it); skipped when no row of this warp
+                // raised its running max, the common case after the first tiles
+                auto rescale_o = [&]() {
+                    if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.f)) {
 #pragma unroll 1
-                    for (int ch = 0; ch < 4; ++ch) {
-                        uint32_t v[32];
-                        tmem_ld32(t_lane + s_col + ch * 32, v);
-                        tmem_ld_wait();
+                        for (int c0 = 0; c0 < HD; c0 += 16) {
+                            uint32_t o[16];
+                            tmem_ld16(t_lane + o_col + c0, o);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            mx = fmaxf(mx, __uint_as_float(v[i]));
-                            mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
-                            mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
-                            mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
+                            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st16(t_lane + o_col + c0, o);
                         }
                     }
-                    mx = fmaxf(fmaxf(mx, mx1), fmaxf(mx2, mx3));
+                };
+                if (!diag) {
+                    // interior tile, single pass: the whole 128-score row lives in registers (one CTA per SM leaves ~200
+                    // registers per thread), so TMEM is read once; row max on FMNMX3, scale/shift on FFMA2, sums on FADD2
+                    uint32_t v0[32], v1[32], v2[32], v3[32];
+                    tmem_ld32(t_lane + s_col, v0);
+                    tmem_ld32(t_lane + s_col + 32, v1);
+                    tmem_ld32(t_lane + s_col + 64, v2);
+                    tmem_ld32(t_lane + s_col + 96, v3);
+                    tmem_ld_wait();
+                    reg_fence32(v0);
+                    reg_fence32(v1);
+                    reg_fence32(v2);
+                    reg_fence32(v3);
+                    float ma = mx, mb = -INFINITY, mc = -INFINITY, md = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        ma = fmax3(ma, __uint_as_float(v0[i]), __uint_as_float(v0[i + 1]));
+                        mb = fmax3(mb, __uint_as_float(v1[i]), __uint_as_float(v1[i + 1]));
+                        mc = fmax3(mc, __uint_as_float(v2[i]), __uint_as_float(v2[i + 1]));
+                        md = fmax3(md, __uint_as_float(v3[i]), __uint_as_float(v3[i + 1]));
+                    }
+                    mx = fmaxf(fmax3(ma, mb, mc), md);
+                    const float m_scaled = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
+                    alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run * p.scale_log2 - m_scaled);
+                    rescale_o();
+                    const float neg_m = -m_scaled;
+                    auto expo = [&](const uint32_t (&v)[32], int ch) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            float x0, x1;
+                            ffma2_bcast(x0, x1, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), p.scale_log2, neg_m);
+                            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+                            fadd2(lsum, lsum1, p0, p1);
+                            pk[i >> 1] = pack_bf16(p0, p1);
+                        }
+                        tmem_st16(t_lane + s_col + ch * 16, pk);  // bf16 P over the S columns (all of S is in registers)
+                    };
+                    expo(v0, 0);
+                    expo(v1, 1);
+                    expo(v2, 2);
+                    expo(v3, 3);
                 } else {
 #pragma unroll 1
                     for (int ch = 0; ch < 4; ++ch) {
@@ -228,41 +271,10 @@ __global__ void __launch_bounds__(320, 1)
                             mx = fmaxf(mx, s);
                         }
                     }
-                }
-                const float m_new = mx;
-                const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
-                const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run * p.scale_log2 - m_scaled);
-                if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.f)) {
-#pragma unroll 1
-                    for (int c0 = 0; c0 < HD; c0 += 16) {
-                        uint32_t o[16];
-                        tmem_ld16(t_lane + o_col + c0, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st16(t_lane + o_col + c0, o);
-                    }
-                }
-                float lsum = 0.f, lsum1 = 0.f;
-                const float neg_m = -m_scaled;
-                if (!diag) {
-#pragma unroll 1
-                    for (int ch = 0; ch < 4; ++ch) {
-                        uint32_t v[32];
-                        tmem_ld32(t_lane + s_col + ch * 32, v);
-                        tmem_ld_wait();
-                        uint32_t pk[16];
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            const float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
-                            const float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, neg_m));
-                            lsum += p0;
-                            lsum1 += p1;
-                            pk[i >> 1] = pack_bf16(p0, p1);
-                        }
-                        tmem_st16(t_lane + s_col + ch * 16, pk);
-                    }
-                } else {
+                    const float m_scaled = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
+                    alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run * p.scale_log2 - m_scaled);
+                    rescale_o();
+                    const float neg_m = -m_scaled;
 #pragma unroll 1
                     for (int ch = 0; ch < 4; ++ch) {
                         uint32_t v[32];
@@ -282,6 +294,7 @@ __global__ void __launch_bounds__(320, 1)
                         tmem_st16(t_lane + s_col + ch * 16, pk);
                     }
                 }
+                const float m_new = mx;
                 lsum += lsum1;
                 l_run = l_run * alpha + lsum;
                 m_run = m_new;

@@ -329,6 +329,28 @@ __device__ __forceinline__ void reg_fence16(uint32_t (&r)[16]) {
                       "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
                       "+r"(r[15]));
 }
+// Blackwell packed fp32 pipes: FFMA2 / FADD2 (two lanes per issue slot) and the 3-input FMNMX3.
+__device__ __forceinline__ void ffma2_bcast(float& d0, float& d1, float a0, float a1, float s, float c) {
+    uint64_t a, sb, cb, d;  // (a0, a1) * (s, s) + (c, c)
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(sb) : "f"(s));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(cb) : "f"(c));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(sb), "l"(cb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+__device__ __forceinline__ void fadd2(float& acc0, float& acc1, float b0, float b1) {
+    uint64_t a, b, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(acc0), "f"(acc1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc0), "=f"(acc1) : "l"(d));
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 __device__ __forceinline__ void reg_fence32(uint32_t (&r)[32]) {
     asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
                       "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),

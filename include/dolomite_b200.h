@@ -36,7 +36,7 @@ const char* dolomite_b200_last_error(void);
 int dolomite_b200_abi_version(void);
 int dolomite_b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* process-wide tuning knobs:
- *   "attn_bwd_version" 1 (serial kernel, every head_dim) | 2 | 3 (pipelined, head_dim <= 80; 3 = two softmax groups)
+ *   "attn_bwd_version" 1 (serial kernel, every head_dim) | 2 | 3 | 4 (pipelined, head_dim <= 80; 1 / 2 / 4 softmax groups)
  *   "attn_fwd_version" 1 (one query tile per CTA) | 2 (two query tiles per CTA, ping-pong softmax groups)
  *   "gemm_cta_pair"    0 | 1 (dense GEMMs on 2-CTA clusters with tcgen05.mma.cta_group::2)
  *   "gemm_sm_margin"   SMs the persistent GEMM grids leave free for concurrent communication kernels */

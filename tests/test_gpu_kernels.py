@@ -159,7 +159,7 @@ def test_attention_fwd_bwd_vs_oracle(lens, ng, g, hd):
     ref.backward(dout.float())
     out, lse = K().attn_varlen_fwd(qkv.cuda(), torch.from_numpy(cu).cuda(), max(lens), ng, g, hd, scale)
     assert rel_l2(out, ref) < 6e-3
-    for version in (1, 2, 3):  # serial / pipelined / pipelined with 2 softmax warp groups (2, 3: head_dim <= 80 only)
+    for version in (1, 2, 3, 4):  # serial / pipelined / pipelined with 2 softmax warp groups (2, 3: head_dim <= 80 only)
         K().set_option("attn_bwd_version", version)
         try:
             dqkv = K().attn_varlen_bwd(dout.cuda(), qkv.cuda(), out, lse, torch.from_numpy(cu).cuda(), max(lens), ng, g, hd, scale)

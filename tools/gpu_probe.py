@@ -740,11 +740,19 @@ def attn_bwd_experiments():
     dqkv = torch.empty_like(qkv)
     res = {}
     flops = 2.5 * 4.0 * S * S * hd * nh * B / 2
-    for mask in (0, 1, 2, 3, 0):
-        k.set_option("attn_bwd_experiment", mask)
-        ms = _time(lambda: k.attn_varlen_bwd(dout, qkv, out, lse, cu, S, nh, 1, hd, scale, dqkv=dqkv), iters=5)
-        res.setdefault(f"mask{mask}", []).append({"ms": ms, "tflops": flops / ms / 1e9})
+    ref = None
+    for version in (3, 4):
+        k.set_option("attn_bwd_version", version)
+        for mask in (0, 1, 0):
+            k.set_option("attn_bwd_experiment", mask)
+            ms = _time(lambda: k.attn_varlen_bwd(dout, qkv, out, lse, cu, S, nh, 1, hd, scale, dqkv=dqkv), iters=5)
+            res.setdefault(f"v{version}_mask{mask}", []).append({"ms": ms, "tflops": flops / ms / 1e9})
+        if ref is None:
+            ref = dqkv.clone()
+        else:
+            res["v4_vs_v3"] = _err(dqkv, ref)
     k.set_option("attn_bwd_experiment", 0)
+    k.set_option("attn_bwd_version", 3)
     ms = _time(lambda: k.attn_varlen_fwd(qkv, cu, S, nh, 1, hd, scale, out=out), iters=10)
     res["fwd"] = {"ms": ms, "tflops": flops / 2.5 / ms / 1e9}
     res["ok"] = True
