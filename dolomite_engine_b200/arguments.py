@@ -205,7 +205,12 @@ class DistributedArgs(BaseArgs):
         if self.tensor_parallel_size != 1:
             raise NotImplementedError("tensor parallelism is out of scope of the data-parallel B200 path")
         if self.gradient_checkpointing_method is not None:
-            raise NotImplementedError("activation checkpointing is a 'next' row (SURVEY.md section 8f rank 1)")
+            # reference enum GradientCheckpointingMethod has the single member `block` (enums.py; gradient_checkpointing/__init__.py)
+            if str(self.gradient_checkpointing_method).split(".")[-1] != "block":
+                raise ValueError(f"unexpected gradient_checkpointing_method ({self.gradient_checkpointing_method})")
+            extra = set(self.gradient_checkpointing_args) - {"checkpoint_every", "use_reentrant", "block_name"}
+            if extra:
+                raise ValueError(f"unexpected gradient_checkpointing_args {sorted(extra)}")
         if self.zero_topology.data_parallel_replication_world_size is not None:
             raise NotImplementedError("HSDP (multi-node replicate x shard) is out of scope of the single-box path")
         if self.communication_dtype is not None:

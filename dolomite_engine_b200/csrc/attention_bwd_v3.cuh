@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
             const int qi = i * ATT_TILE + (tidsm & (ATT_TILE - 1));
             const bool q_ok = qi < loc.doc_len;
             const int64_t off = int64_t(head) * p.T + loc.doc_start + qi;
-            if (tidsm < ATT_TILE) return q_ok ? p.lse[off] * LOG2E : INFINITY;
+            if (tidsm < ATT_TILE) return q_ok ? p.lse[off] : INFINITY;  // scaled to log2 units when stored (not here:
+                                                                        // the multiply would wait for the load at once)
             if (tidsm < 2 * ATT_TILE) return q_ok ? p.delta[off] : 0.f;
             return 0.f;
         };
@@ -250,7 +251,8 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
             const int s_head = it / n_i, i = j + (it - s_head * n_i);
             float* lse_s = sLSE + (it & 1) * ATT_TILE;
             float* del_s = sDelta + (it & 1) * ATT_TILE;
-            if (tidsm < 2 * ATT_TILE) (tidsm < ATT_TILE ? lse_s : del_s)[tidsm & (ATT_TILE - 1)] = stat_next;
+            if (tidsm < ATT_TILE) lse_s[tidsm] = stat_next * LOG2E;
+            else if (tidsm < 2 * ATT_TILE) del_s[tidsm - ATT_TILE] = stat_next;
             named_bar_sync(2, SOFTMAX_THREADS);
             if (it + 1 < n_it) stat_next = fetch_stat(it + 1);
             if (it >= 2) mbar_wait(&dq_full[it & 1], uint32_t((it >> 1) - 1) & 1, 35);  // dS smem buffer free again

@@ -33,7 +33,7 @@ __device__ __forceinline__ TilePairLoc locate_tile_pair(const int32_t* __restric
 }
 
 template <int HD>
-__global__ void __maxnreg__(200)
+__global__ void __launch_bounds__(320, 1)  // 10 warps = 3 per SM sub-partition -> at most 168 registers per thread
     attn_fwd_kernel_v2(const __grid_constant__ CUtensorMap tmap64, const __grid_constant__ CUtensorMap tmapR,
                        const FwdParams p) {
     using CH = HeadChunks<HD>;

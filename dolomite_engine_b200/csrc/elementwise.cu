@@ -258,6 +258,64 @@ __global__ void __launch_bounds__(kThreads) swiglu_bwd_kernel(const uint4* __res
     }
 }
 
+// SwiGLU backward that also accumulates the bias gradient of the producing linear layer (column sums of the bf16 dx it
+// writes): saves the separate pass that re-read the whole [T, 2F] tensor.  Block = 32 column vectors (256 up + 256 gate
+// columns) x 8 row lanes over `rows_per_block` rows; per-thread fp32 column sums, smem combine, one atomicAdd per column.
+__global__ void __launch_bounds__(kThreads)
+    swiglu_bwd_bias_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, uint4* __restrict__ dx,
+                           float* __restrict__ dbias, int64_t T, int64_t F8, int rows_per_block) {
+    __shared__ float sm[8][2][256];
+    const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int64_t c = int64_t(blockIdx.x) * 32 + lane;
+    const int64_t r0 = int64_t(blockIdx.y) * rows_per_block;
+    const int64_t r1 = min(T, r0 + rows_per_block);
+    float su[8], sg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) su[j] = sg[j] = 0.f;
+    if (c < F8) {
+        for (int64_t t = r0 + rl; t < r1; t += 8) {
+            float u[8], g[8], d[8], du[8], dg[8];
+            unpack8(__ldg(x + t * 2 * F8 + c), u);
+            unpack8(__ldg(x + t * 2 * F8 + F8 + c), g);
+            unpack8(__ldg(dy + t * F8 + c), d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float sgm = sigmoidf_(g[j]);
+                du[j] = d[j] * (g[j] * sgm);
+                dg[j] = d[j] * u[j] * (sgm * (1.f + g[j] * (1.f - sgm)));
+            }
+            const uint4 pu = pack8(du), pg = pack8(dg);
+            dx[t * 2 * F8 + c] = pu;
+            dx[t * 2 * F8 + F8 + c] = pg;
+            unpack8(pu, du);  // the bias gradient sums the bf16 values autograd would see
+            unpack8(pg, dg);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                su[j] += du[j];
+                sg[j] += dg[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sm[rl][0][lane * 8 + j] = su[j];
+        sm[rl][1][lane * 8 + j] = sg[j];
+    }
+    __syncthreads();
+    const int col = threadIdx.x;
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        a += sm[w][0][col];
+        b += sm[w][1][col];
+    }
+    const int64_t gc = int64_t(blockIdx.x) * 256 + col;
+    if (gc < F8 * 8) {
+        atomicAdd(dbias + gc, a);
+        atomicAdd(dbias + F8 * 8 + gc, b);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Embedding
 // ------------------------------------------------------------------------------------------
@@ -689,6 +747,27 @@ extern "C" int dolomite_b200_swiglu_bwd(const void* dy, const void* x, void* dx,
     swiglu_bwd_kernel<<<grid_for(T * F8, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const uint4*>(dy), static_cast<const uint4*>(x), static_cast<uint4*>(dx), T, F8);
     DOLO_LAUNCH_OK("swiglu_bwd");
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_swiglu_bwd_bias(const void* dy, const void* x, void* dx, float* dbias_accum, int64_t T,
+                                             int64_t F, void* stream) {
+    DOLO_REQUIRE(F > 0 && F % 8 == 0, "swiglu_bwd_bias: F=%lld must be a positive multiple of 8", (long long)F);
+    DOLO_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dx), "swiglu_bwd_bias: pointers must be 16-byte aligned");
+    DOLO_REQUIRE(dbias_accum != nullptr, "swiglu_bwd_bias: bias gradient buffer is null");
+    if (T == 0) return DOLO_OK;
+    const int64_t F8 = F / 8;
+    const int col_tiles = int((F8 + 31) / 32);
+    int row_splits = (dolo_num_sms() * 8 + col_tiles - 1) / col_tiles;
+    if (row_splits > (T + 7) / 8) row_splits = int((T + 7) / 8);
+    if (row_splits < 1) row_splits = 1;
+    if (row_splits > 65535) row_splits = 65535;
+    const int rows_per_block = int((T + row_splits - 1) / row_splits);
+    dim3 grid(col_tiles, (unsigned)((T + rows_per_block - 1) / rows_per_block));
+    swiglu_bwd_bias_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(dy), static_cast<const uint4*>(x), static_cast<uint4*>(dx), dbias_accum, T, F8,
+        rows_per_block);
+    DOLO_LAUNCH_OK("swiglu_bwd_bias");
     return DOLO_OK;
 }
 

@@ -292,5 +292,10 @@ def wrap_model_for_distributed_training(args, model: nn.Module) -> nn.Module:
         if getattr(dargs, "torch_compile", False):
             raise NotImplementedError("torch.compile is not used on the B200 path (hand-written kernels + CUDA streams)")
     reshard = bool(getattr(dargs, "reshard_after_forward", False)) if dargs is not None else False
+    if dargs is not None and getattr(dargs, "gradient_checkpointing_method", None) is not None:
+        # block_checkpointing(model, block_name, checkpoint_every=1) (distributed/__init__.py:113-121,
+        # gradient_checkpointing/block.py:13-37): blocks 0, k, 2k, ... keep only their input and are re-run in backward
+        every = int((getattr(dargs, "gradient_checkpointing_args", None) or {}).get("checkpoint_every", 1))
+        model.model.engine.checkpoint_every = every
     group = dist.group.WORLD if dist.is_initialized() else None
     return ShardedDataParallel(model, group, communication_dtype=comm_dtype, reshard_after_forward=reshard and stage == 3)

@@ -214,6 +214,8 @@ class DolomiteEngine:
         self.comm = None  # set by distributed.ShardedDataParallel
         self._saved = None
         self.requires_gradient_sync = True
+        self.checkpoint_every: int | None = None  # block activation checkpointing: re-run blocks 0, k, 2k, ... in backward
+        self._fresh_grads: set[str] = set()  # weights whose gradient buffer will be overwritten by the next wgrad GEMM
         if cfg.attention_multiplier is not None:
             self.softmax_scale = float(cfg.attention_multiplier)
         elif cfg.scale_attn_weights:
@@ -243,9 +245,26 @@ class DolomiteEngine:
     def num_parameters(self) -> int:
         return sum(s.numel for u in self.units for s in u.specs)
 
+    # parameters at least this large only ever receive their gradient from a weight-gradient GEMM first
+    _LAZY_ZERO_MIN_NUMEL = 1 << 16
+
     def zero_grad(self) -> None:
+        """Clears the fp32 gradient buffers.  Dense models do it lazily for the GEMM weights: the first weight-gradient GEMM
+        of the next backward OVERWRITES its buffer (beta = 0) instead of read-modify-writing a freshly zeroed one, which
+        saves one write and one read of every weight gradient per step (8 B / parameter); only the small tensors that are
+        accumulated by reduction kernels (norm weights, biases) are cleared here."""
+        lazy = not self.is_moe
+        self._fresh_grads = set()
         for u in self.units:
-            u.grad_full.zero_()
+            if lazy:
+                for s in u.specs:
+                    untied_wte = s.name == "transformer.wte.weight" and not self.cfg.tie_word_embeddings
+                    if s.numel >= self._LAZY_ZERO_MIN_NUMEL and s.name.endswith(".weight") and not untied_wte:
+                        self._fresh_grads.add(s.name)
+                    else:
+                        u.gviews[s.name].zero_()
+            else:
+                u.grad_full.zero_()
             # sharded: the shard gradient is (over)written by the reduce-scatter, no need to clear it here
             if u.master.grad is not u.grad_full and self.comm is None:
                 u.master.grad.zero_()
@@ -255,6 +274,35 @@ class DolomiteEngine:
     # ------------------------------------------------------------------------------------------
     def _w(self, unit: FlatUnit, name: str):
         return unit.views.get(name)
+
+    def _is_checkpointed(self, i: int) -> bool:
+        k = self.checkpoint_every
+        return k is not None and k > 0 and i % k == 0
+
+    def _block_forward(self, i: int, x_in, position_ids, cu_seqlens, max_seqlen: int):
+        """One GPTDolomiteBlock / SparseMoEBlock (gpt_dolomite/layer.py:49-87): returns (h_out, activations kept for backward)"""
+        cfg = self.cfg
+        u = self.units[i + 1]
+        p = f"transformer.h.{i}."
+        m_res = 1.0 if cfg.m_residual is None else float(cfg.m_residual)
+        ln1, rstd1 = K.rmsnorm_fwd(x_in, u.views[p + "ln_1.weight"], cfg.layer_norm_epsilon)
+        qkv = K.gemm(ln1, u.views[p + "attn.c_attn.weight"], bias=u.views.get(p + "attn.c_attn.bias"))
+        if self.rope_cos is not None:
+            K.rope_qk_inplace(qkv, self.n_groups, self.q_per_group, self.hd, self.rope_cos, self.rope_sin, position_ids)
+        attn, lse = K.attn_varlen_fwd(qkv, cu_seqlens, max_seqlen, self.n_groups, self.q_per_group, self.hd, self.softmax_scale)
+        h_mid = K.gemm(attn, u.views[p + "attn.c_proj.weight"], bias=u.views.get(p + "attn.c_proj.bias"), c=x_in,
+                       alpha=m_res, beta=1.0)
+        ln2, rstd2 = K.rmsnorm_fwd(h_mid, u.views[p + "ln_2.weight"], cfg.layer_norm_epsilon)
+        if self.is_moe:
+            from . import moe
+
+            h, moe_saved = moe.forward(self, u, p, ln2, h_mid, m_res)
+            return h, (x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, moe_saved)
+        fc = K.gemm(ln2, u.views[p + "mlp.c_fc.weight"], bias=u.views.get(p + "mlp.c_fc.bias"))
+        act = K.swiglu_fwd(fc)
+        h = K.gemm(act, u.views[p + "mlp.c_proj.weight"], bias=u.views.get(p + "mlp.c_proj.bias"), c=h_mid,
+                   alpha=m_res, beta=1.0)
+        return h, (x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, fc, act)
 
     def forward(self, input_ids, position_ids, cu_seqlens, max_seqlen: int, labels=None, ignore_index: int = -100,
                 save_for_backward: bool = True):
@@ -267,34 +315,16 @@ class DolomiteEngine:
             comm.pre_forward_unit(0)
         h = K.embedding_fwd(input_ids, root.views["transformer.wte.weight"], 1.0 if cfg.m_emb is None else float(cfg.m_emb))
         saved_layers = []
-        m_res = 1.0 if cfg.m_residual is None else float(cfg.m_residual)
         for i in range(cfg.n_layer):
-            u = self.units[i + 1]
             if comm is not None:
                 comm.pre_forward_unit(i + 1)
-            p = f"transformer.h.{i}."
             x_in = h
-            ln1, rstd1 = K.rmsnorm_fwd(x_in, u.views[p + "ln_1.weight"], cfg.layer_norm_epsilon)
-            qkv = K.gemm(ln1, u.views[p + "attn.c_attn.weight"], bias=u.views.get(p + "attn.c_attn.bias"))
-            if self.rope_cos is not None:
-                K.rope_qk_inplace(qkv, self.n_groups, self.q_per_group, self.hd, self.rope_cos, self.rope_sin, position_ids)
-            attn, lse = K.attn_varlen_fwd(qkv, cu_seqlens, max_seqlen, self.n_groups, self.q_per_group, self.hd, self.softmax_scale)
-            h_mid = K.gemm(attn, u.views[p + "attn.c_proj.weight"], bias=u.views.get(p + "attn.c_proj.bias"), c=x_in,
-                           alpha=m_res, beta=1.0)
-            ln2, rstd2 = K.rmsnorm_fwd(h_mid, u.views[p + "ln_2.weight"], cfg.layer_norm_epsilon)
-            if self.is_moe:
-                from . import moe
-
-                h, moe_saved = moe.forward(self, u, p, ln2, h_mid, m_res)
-                layer = (x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, moe_saved)
-            else:
-                fc = K.gemm(ln2, u.views[p + "mlp.c_fc.weight"], bias=u.views.get(p + "mlp.c_fc.bias"))
-                act = K.swiglu_fwd(fc)
-                h = K.gemm(act, u.views[p + "mlp.c_proj.weight"], bias=u.views.get(p + "mlp.c_proj.bias"), c=h_mid,
-                           alpha=m_res, beta=1.0)
-                layer = (x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, fc, act)
+            h, layer = self._block_forward(i, x_in, position_ids, cu_seqlens, max_seqlen)
             if save_for_backward:
-                saved_layers.append(layer)
+                # block activation checkpointing (gradient_checkpointing/block.py:13-37): every `checkpoint_every`-th
+                # block keeps only its input and is re-run in backward
+                saved_layers.append((x_in,) if self._is_checkpointed(i) else layer)
+            del layer
             if comm is not None:
                 comm.post_forward_unit(i + 1)
         hf, rstd_f = K.rmsnorm_fwd(h, root.views["transformer.ln_f.weight"], cfg.layer_norm_epsilon)
@@ -322,7 +352,11 @@ class DolomiteEngine:
         w = unit.views[wname]
         gw = unit.gviews[wname]
         dx = K.gemm(dy, w, b_mn=True, alpha=alpha) if need_dx else None
-        K.gemm(dy, x, a_mn=True, b_mn=True, out=gw, c=gw, alpha=alpha, beta=1.0)
+        if wname in self._fresh_grads:  # first gradient since zero_grad(): overwrite, the buffer was not cleared
+            self._fresh_grads.discard(wname)
+            K.gemm(dy, x, a_mn=True, b_mn=True, out=gw, alpha=alpha)
+        else:
+            K.gemm(dy, x, a_mn=True, b_mn=True, out=gw, c=gw, alpha=alpha, beta=1.0)
         if bname is not None and bname in unit.gviews:
             K.colsum_accum(dy, unit.gviews[bname], alpha)
         return dx
@@ -355,6 +389,8 @@ class DolomiteEngine:
                 comm.pre_backward_unit(i + 1)
             p = f"transformer.h.{i}."
             layer = s["layers"][i]
+            if len(layer) == 1:  # checkpointed block: re-run its forward from the saved input (MoE routing is deterministic)
+                _, layer = self._block_forward(i, layer[0], s["position_ids"], s["cu_seqlens"], s["max_seqlen"])
             if self.is_moe:
                 from . import moe
 
@@ -363,9 +399,10 @@ class DolomiteEngine:
             else:
                 x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, fc, act = layer
                 d_act = self._linear_bwd(u, p + "mlp.c_proj.weight", p + "mlp.c_proj.bias", act, dh, alpha=m_res)
-                d_fc = K.swiglu_bwd(d_act, fc)
+                # the c_fc bias gradient (column sums of d_fc) is accumulated by the SwiGLU backward while it writes d_fc
+                d_fc = K.swiglu_bwd(d_act, fc, bias_grad_accum=u.gviews.get(p + "mlp.c_fc.bias"))
                 del d_act
-                d_ln2 = self._linear_bwd(u, p + "mlp.c_fc.weight", p + "mlp.c_fc.bias", ln2, d_fc)
+                d_ln2 = self._linear_bwd(u, p + "mlp.c_fc.weight", None, ln2, d_fc)
                 del d_fc
             dh_mid = K.rmsnorm_bwd(d_ln2, h_mid, u.views[p + "ln_2.weight"], rstd2, u.gviews[p + "ln_2.weight"], dx_add=dh)
             del d_ln2
@@ -384,6 +421,11 @@ class DolomiteEngine:
             if comm is not None:
                 comm.post_backward_unit(i + 1)
         K.embedding_bwd(s["input_ids"], dh, root.gviews["transformer.wte.weight"], 1.0 if cfg.m_emb is None else float(cfg.m_emb))
+        if self._fresh_grads:  # a weight that received no gradient in this backward still has to read as zero
+            for name, unit, _ in self.named_views():
+                if name in self._fresh_grads:
+                    unit.gviews[name].zero_()
+            self._fresh_grads.clear()
         if comm is not None:
             comm.post_backward_unit(0)
         self._saved = None

@@ -99,11 +99,18 @@ def swiglu_fwd(x, out=None):
     return y
 
 
-def swiglu_bwd(dy, x, out=None):
+def swiglu_bwd(dy, x, out=None, bias_grad_accum=None):
+    """dx of y = up * silu(gate); with `bias_grad_accum` (fp32 [2F]) also += column sums of dx (bias gradient of c_fc)"""
     _req(dy, _BF16, "dy"), _req(x, _BF16, "x")
     T, F2 = x.shape
     dx = torch.empty_like(x) if out is None else out
-    _lib.call("dolomite_b200_swiglu_bwd", dy.data_ptr(), x.data_ptr(), dx.data_ptr(), T, F2 // 2, _stream())
+    if bias_grad_accum is not None:
+        _req(bias_grad_accum, torch.float32, "bias_grad_accum")
+        assert bias_grad_accum.numel() == F2
+        _lib.call("dolomite_b200_swiglu_bwd_bias", dy.data_ptr(), x.data_ptr(), dx.data_ptr(), bias_grad_accum.data_ptr(),
+                  T, F2 // 2, _stream())
+    else:
+        _lib.call("dolomite_b200_swiglu_bwd", dy.data_ptr(), x.data_ptr(), dx.data_ptr(), T, F2 // 2, _stream())
     return dx
 
 

@@ -73,6 +73,10 @@ int dolomite_b200_rope_qk_inplace(void* qkv, int64_t row_stride, int64_t T, int 
  * ------------------------------------------------------------------------------------------------ */
 int dolomite_b200_swiglu_fwd(const void* x, void* y, int64_t T, int64_t F, void* stream);
 int dolomite_b200_swiglu_bwd(const void* dy, const void* x, void* dx, int64_t T, int64_t F, void* stream);
+/* Same, and additionally accumulates the bias gradient of the linear layer that produced x (autograd of
+ * ParameterizedLinear's `+ bias`, modeling_utils/linear.py): dbias_accum[0..2F) += column sums of the bf16 dx written. */
+int dolomite_b200_swiglu_bwd_bias(const void* dy, const void* x, void* dx, float* dbias_accum, int64_t T, int64_t F,
+                                  void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Embedding -- gpt_dolomite/base.py:351-372 (wte gather, * m_emb); bwd accumulates (+=) into fp32 dwte.

@@ -74,7 +74,18 @@ def test_swiglu_fwd_bwd():
     assert (y.float().cpu() - ref).abs().max() <= 4 * BF16_EPS * ref.abs().max()
     xf = x.float().requires_grad_(True)
     O.activation(xf, "swiglu").backward(dy.float())
-    assert rel_l2(K().swiglu_bwd(dy.cuda(), x.cuda()), xf.grad) < 5e-3
+    dx = K().swiglu_bwd(dy.cuda(), x.cuda())
+    assert rel_l2(dx, xf.grad) < 5e-3
+    # fused variant: identical dx, plus the bias gradient of the producing linear (column sums of the bf16 dx),
+    # accumulated on top of what is already in the buffer; ragged row / column-tile counts
+    for T, F in [(77, 256), (1000, 328), (8, 8)]:
+        x2, dy2 = bf(torch.randn(T, 2 * F, generator=g)).cuda(), bf(torch.randn(T, F, generator=g)).cuda()
+        plain = K().swiglu_bwd(dy2, x2)
+        db = torch.full((2 * F,), 0.5, device="cuda")
+        fused = K().swiglu_bwd(dy2, x2, bias_grad_accum=db)
+        assert torch.equal(fused, plain)
+        want = 0.5 + plain.float().sum(0)
+        assert torch.allclose(db, want, rtol=1e-5, atol=1e-4), (T, F, (db - want).abs().max().item())
 
 
 def test_embedding_exact_and_grad():

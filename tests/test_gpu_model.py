@@ -246,3 +246,32 @@ def test_train_steps_reduce_loss_and_match_cpu_adamw(opt_name):
     assert losses[-1] < losses[0]
     for a, b in zip(losses, ref_losses):
         assert abs(a - b) / b < 2e-3, (losses, ref_losses)
+
+
+@pytest.mark.parametrize("every", [1, 2])
+def test_block_activation_checkpointing_gives_identical_gradients(every):
+    """gradient_checkpointing/block.py:13-37: blocks 0, k, 2k, ... are re-run in backward; the recomputation launches the
+    same kernels on the same inputs, so every gradient must be bit-identical to the non-checkpointed run (the fp32
+    atomics of the embedding gradient / dQ workspace aside, hence the tolerance on those two)."""
+    model, ocfg, params = build_model("hd80_bias")
+    model.assume_unit_loss_grad = True
+    tokens = sample_tokens(ocfg)
+    inp, labels = O.split_tokens(tokens)
+    b = O.prepare_model_inputs(inp.copy(), 7, True, True)
+    args = (torch.from_numpy(b["input_ids"]).cuda(), torch.from_numpy(b["position_ids"]).cuda(),
+            torch.from_numpy(b["cu_seqlens"]).cuda(), b["max_seqlen"],
+            torch.from_numpy(np.ascontiguousarray(labels).reshape(-1)).cuda())
+    grads = []
+    for ck in (None, every):
+        model.engine.checkpoint_every = ck
+        model.engine.zero_grad()
+        loss = model.forward_pretraining_loss(*args)
+        if ck is not None:
+            assert any(len(l) == 1 for l in model.engine._saved["layers"]), "no block was checkpointed"
+        loss.backward()
+        torch.cuda.synchronize()
+        grads.append((loss.item(), {n: u.gviews[n].clone() for n, u, _ in model.engine.named_views()}))
+    model.engine.checkpoint_every = None
+    assert grads[0][0] == grads[1][0]
+    for n, g in grads[0][1].items():
+        assert rel_l2(grads[1][1][n], g) < 1e-5, n

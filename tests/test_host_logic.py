@@ -159,3 +159,16 @@ def test_no_gpu_means_loud_failure():
                             attn_pdrop=0, vocab_size=2048, n_layer=1)
     with pytest.raises(RuntimeError, match="no CPU path"):
         GPTDolomiteForCausalLM(cfg)
+
+
+def test_gradient_checkpointing_args_follow_the_reference_surface():
+    """distributed_args.gradient_checkpointing_method: block + gradient_checkpointing_args.checkpoint_every
+    (arguments.py:312-314, gradient_checkpointing/__init__.py)"""
+    d = load_yaml(os.path.join(ROOT, "configs", "c1_tiny.yml"))
+    d["distributed_args"]["gradient_checkpointing_method"] = "block"
+    d["distributed_args"]["gradient_checkpointing_args"] = {"checkpoint_every": 2}
+    a = get_args_from_dict(d)
+    assert a.distributed_args.gradient_checkpointing_args["checkpoint_every"] == 2
+    d["distributed_args"]["gradient_checkpointing_method"] = "selective"
+    with pytest.raises(Exception):
+        get_args_from_dict(d)
