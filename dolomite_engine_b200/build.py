@@ -92,7 +92,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError(f"link failed:\n{proc.stdout}\n{proc.stderr}")
+    build_host_library(force)
     return LIB_PATH
+
+
+HOST_SRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc_host", "data_helpers.cpp")
+HOST_LIB_PATH = os.path.join(os.path.dirname(LIB_PATH), "libdolomite_data.so")
+
+
+def build_host_library(force: bool = False) -> str:
+    """the data-feed index builders (plain C++, no CUDA): lib/libdolomite_data.so"""
+    stamp = HOST_LIB_PATH + ".sha"
+    digest = _digest(HOST_SRC)
+    if not force and os.path.exists(HOST_LIB_PATH) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return HOST_LIB_PATH
+    cxx = shutil.which("g++") or "g++"
+    proc = subprocess.run([cxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-o", HOST_LIB_PATH, HOST_SRC],
+                          capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"g++ failed for {HOST_SRC}:\n{proc.stdout}\n{proc.stderr}")
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return HOST_LIB_PATH
 
 
 if __name__ == "__main__":

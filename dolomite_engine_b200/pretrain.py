@@ -84,12 +84,30 @@ def build(args: TrainingArgs):
     return model, optimizer, scheduler, (rank, world, local)
 
 
-def make_dataloader(args: TrainingArgs, model, rank: int):
+def make_megatron_dataloader(args: TrainingArgs, rank: int, world: int, consumed_samples: int = 0):
+    """get_megatron_gpt_dataloaders (data/megatron/__init__.py:18-213), train split: Megatron .bin/.idx stores named by
+    `class_args.data_path` (one prefix or [w1, prefix1, w2, prefix2, ...]) + `split`, cut into S+1-token samples, global
+    batches of mbs * world consecutive samples with rank r taking rows [r*mbs, (r+1)*mbs); resumes at `consumed_samples`."""
+    from .data import MegatronBatchSampler, PackedBatchLoader, build_gpt_datasets, get_train_val_test_samples
+
+    ds, tp = args.datasets[0], args.training_parameters
+    ca = ds.class_args
+    sizes = get_train_val_test_samples(tp.num_training_steps, tp.micro_batch_size, tp.gradient_accumulation_steps,
+                                       getattr(tp, "eval_interval", None), ca.get("eval_steps"), world)
+    train, _, _ = build_gpt_datasets(ca["data_path"], ca.get("split", "100,0,0"), sizes, ca["sequence_length"],
+                                     ca.get("seed", args.random_args.seed))
+    sampler = MegatronBatchSampler(len(train), consumed_samples, tp.micro_batch_size, world, rank)
+    return PackedBatchLoader(train, sampler, ca["sequence_length"])
+
+
+def make_dataloader(args: TrainingArgs, model, rank: int, world: int = 1, consumed_samples: int = 0):
     ds = args.datasets[0]
+    if ds.class_name == "MegatronDataset":
+        return iter(make_megatron_dataloader(args, rank, world, consumed_samples))
     if ds.class_name != "SyntheticPackedDataset":
         raise NotImplementedError(
-            f"dataset class {ds.class_name}: the Megatron data layer is out of scope of the B200 hot path "
-            "(SURVEY.md section 8f rank 2); use class_name: SyntheticPackedDataset or pass your own iterator to train()"
+            f"dataset class {ds.class_name}: only MegatronDataset (.bin/.idx token stores) and SyntheticPackedDataset feed "
+            "the pretraining hot path; pass any other iterator of {'text': LongTensor[mbs, seq+1]} batches to train()"
         )
     cfg = model.config
     return SyntheticPackedDataset(cfg.vocab_size, args.training_parameters.micro_batch_size,
@@ -118,7 +136,7 @@ def train(args: TrainingArgs, model, optimizer, scheduler, dataloader, rank: int
 def main() -> None:
     args = get_args()
     model, optimizer, scheduler, (rank, world, _) = build(args)
-    dl = make_dataloader(args, model, rank)
+    dl = make_dataloader(args, model, rank, world)
     train(args, model, optimizer, scheduler, dl, rank, world)
     if dist.is_initialized():
         dist.barrier()

@@ -1,0 +1,183 @@
+"""Data feed against fixtures PRODUCED BY THE REFERENCE ITSELF (oracle/pin_data_feed.py ran the
+reference's MMapIndexedDatasetBuilder / GPTDataset / helpers.cpp / MegatronBatchSampler in this container): the corpus
+files under tests/golden/data_feed/ were written by the reference's builder; expected.npz holds its indices and samples.
+Everything here is integer work: bit-exact."""
+import filecmp
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from dolomite_engine_b200.data import (
+    BlendedDataset,
+    GPTDataset,
+    MegatronBatchSampler,
+    MMapIndexedDataset,
+    MMapIndexedDatasetBuilder,
+    PackedBatchLoader,
+    build_blending_indices,
+    build_gpt_datasets,
+    build_sample_index,
+)
+from dolomite_engine_b200.data.gpt_dataset import get_num_epochs, get_split_indices, parse_and_normalize_split
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden", "data_feed")
+
+
+@pytest.fixture(scope="module")
+def exp():
+    return np.load(os.path.join(GOLD, "expected.npz"))
+
+
+def test_reads_reference_written_store(exp):
+    a = MMapIndexedDataset(os.path.join(GOLD, "corpus_a"))
+    b = MMapIndexedDataset(os.path.join(GOLD, "corpus_b"))
+    assert a.dtype == np.uint16 and b.dtype == np.int32
+    assert np.array_equal(a.sequence_lengths, exp["a_sequence_lengths"])
+    assert np.array_equal(a.document_indices, exp["a_document_indices"])
+    assert np.array_equal(a[5], exp["a_doc5"])
+    assert np.array_equal(b.get(3, offset=1, length=4), exp["b_doc3_slice"])
+    assert a.sequence_lengths[11] == 0 and a[11].size == 0  # the empty document
+    assert len(a[2:5]) == 3 and np.array_equal(a[2:5][1], a[3])
+
+
+def test_writer_is_byte_identical_to_the_reference_builder(tmp_path):
+    for name in ("corpus_a", "corpus_b"):
+        src = MMapIndexedDataset(os.path.join(GOLD, name))
+        out = str(tmp_path / name)
+        w = MMapIndexedDatasetBuilder(out + ".bin", dtype=src.dtype)
+        for i in range(len(src)):
+            w.add_item(src[i])
+            w.end_document()
+        w.finalize(out + ".idx")
+        assert filecmp.cmp(out + ".bin", os.path.join(GOLD, name + ".bin"), shallow=False)
+        assert filecmp.cmp(out + ".idx", os.path.join(GOLD, name + ".idx"), shallow=False)
+
+
+@pytest.mark.parametrize("ci", range(5))
+def test_gpt_dataset_indices_and_samples_match_the_reference(exp, ci):
+    lo, hi, num_samples, S, seed, n = (int(x) for x in exp[f"case{ci}_meta"])
+    ids = MMapIndexedDataset(os.path.join(GOLD, "corpus_a" if ci < 3 else "corpus_b"))
+    ds = GPTDataset(ids, np.arange(lo, hi, dtype=np.int32), num_samples, S, seed)
+    assert len(ds) == n
+    for name in ("document_index", "sample_index", "shuffle_index"):
+        got, want = getattr(ds, name), exp[f"case{ci}_{name}"]
+        assert got.dtype == want.dtype and np.array_equal(got, want), name
+    take = exp[f"case{ci}_take"]
+    got = np.stack([ds[int(i)]["text"] for i in take])
+    assert got.dtype == np.int64 and np.array_equal(got, exp[f"case{ci}_samples"])
+
+
+def test_sample_index_helper_edge_cases(exp):
+    sizes, doc_idx = exp["raw_sizes"], exp["raw_doc_idx"]
+    tpe = int(sizes.sum())
+    for S in (2, 3, 4, 8):
+        got32 = build_sample_index(sizes, doc_idx.astype(np.int32), S, 1, tpe)
+        got64 = build_sample_index(sizes, doc_idx.astype(np.int64), S, 1, tpe)
+        assert got32.dtype == np.int32 and np.array_equal(got32, exp[f"raw_S{S}_i32"])
+        assert got64.dtype == np.int64 and np.array_equal(got64, exp[f"raw_S{S}_i64"])
+    with pytest.raises(ValueError):  # claims more tokens than the document index holds
+        build_sample_index(sizes, doc_idx[:3].astype(np.int32), 4, 1, tpe)
+
+
+def test_blending_indices_match_the_reference(exp):
+    for bi in range(4):
+        w = exp[f"blend{bi}_weights"].tolist()
+        di, dsi = build_blending_indices(w, exp[f"blend{bi}_dataset_index"].size)
+        assert di.dtype == np.int16 and np.array_equal(di, exp[f"blend{bi}_dataset_index"])
+        assert np.array_equal(dsi, exp[f"blend{bi}_dataset_sample_index"])
+
+
+def test_batch_sampler_rank_assignment_and_resume(exp):
+    for si in range(3):
+        total, consumed, mbs, world, drop_last = (int(x) for x in exp[f"sampler{si}_meta"])
+        for rank in range(world):
+            rows = list(MegatronBatchSampler(total, consumed, mbs, world, rank, bool(drop_last)))
+            lens = exp[f"sampler{si}_rank{rank}_lens"]
+            flat = exp[f"sampler{si}_rank{rank}_flat"]
+            assert [len(r) for r in rows] == lens.tolist()
+            assert [x for r in rows for x in r] == (flat.tolist() if lens.size else [])
+    with pytest.raises(AssertionError):
+        MegatronBatchSampler(10, 10, 2, 1, 0)
+
+
+def test_small_helpers():
+    assert parse_and_normalize_split("98,1,1") == [0.98, 0.01, 0.01]
+    assert parse_and_normalize_split("100") == [1.0, 0.0, 0.0]
+    assert get_split_indices([0.9, 0.09, 0.01], 1000) == [0, 900, 990, 1000]
+    assert get_split_indices([0.98, 0.01, 0.01], 37)[-1] == 37
+    for tpe, S, n in [(100, 8, 5), (100, 8, 12), (100, 8, 13), (7, 3, 50), (1000, 999, 1)]:
+        e = get_num_epochs(tpe, S, n)
+        assert (e * tpe - 1) // S >= n and (e == 1 or ((e - 1) * tpe - 1) // S < n)
+
+
+def test_loader_emits_wrapper_batches_and_ranks_partition_the_global_batch():
+    S, mbs, world = 16, 3, 2
+    ids = MMapIndexedDataset(os.path.join(GOLD, "corpus_a"))
+    ds = GPTDataset(ids, np.arange(0, 37, dtype=np.int32), 60, S, 1234)
+    per_rank = []
+    for rank in range(world):
+        ld = PackedBatchLoader(ds, MegatronBatchSampler(len(ds), 6, mbs, world, rank), S, pin=False)
+        batches = [b["text"] for b in ld]
+        per_rank.append(batches)
+        assert all(b.dtype == torch.int64 and tuple(b.shape) == (mbs, S + 1) for b in batches)
+        assert ld.consumed_samples == 6 + len(batches) * mbs * world  # resume point (consumed_samples of the reference)
+    n_steps = (len(ds) - 6) // (mbs * world)
+    assert len(per_rank[0]) == len(per_rank[1]) == n_steps
+    for step in range(n_steps):
+        for rank in range(world):
+            for r in range(mbs):
+                want = ds[6 + step * mbs * world + rank * mbs + r]["text"]
+                assert np.array_equal(per_rank[rank][step][r].numpy(), want)
+    # consecutive samples of the UNSHUFFLED stream overlap by exactly one token (labels of the last position)
+    inv = np.argsort(ds.shuffle_index)
+    a, b = ds[int(inv[0])]["text"], ds[int(inv[1])]["text"]
+    assert a[-1] == b[0]
+
+
+def test_blended_dataset_and_builder(tmp_path):
+    S = 8
+    a = MMapIndexedDataset(os.path.join(GOLD, "corpus_a"))
+    b = MMapIndexedDataset(os.path.join(GOLD, "corpus_b"))
+    da = GPTDataset(a, np.arange(0, 37, dtype=np.int32), 80, S, 1)
+    db = GPTDataset(b, np.arange(0, 23, dtype=np.int32), 80, S, 1)
+    bl = BlendedDataset([da, db], [0.25, 0.75], 64)
+    counts = np.bincount(bl.dataset_index, minlength=2)
+    assert abs(counts[0] - 16) <= 1 and counts.sum() == 64
+    for i in (0, 1, 17, 63):
+        src, j = bl.locate(i)
+        assert np.array_equal(bl[i]["text"], src[j]["text"])
+    with pytest.raises(IndexError):
+        bl[64]
+    ld = PackedBatchLoader(bl, MegatronBatchSampler(len(bl), 0, 4, 1, 0), S, pin=False)
+    first = next(iter(ld))["text"]
+    assert np.array_equal(first.numpy(), np.stack([bl[i]["text"] for i in range(4)]))
+    train, val, test = build_gpt_datasets(["1", os.path.join(GOLD, "corpus_a"), "3", os.path.join(GOLD, "corpus_b")],
+                                          "90,10,0", (40, 8, 0), S, 1234)
+    assert isinstance(train, BlendedDataset) and len(train) == 40 and len(val) == 8 and test is None
+    t1, v1, _ = build_gpt_datasets(os.path.join(GOLD, "corpus_a"), "80,20,0", (30, 5, 0), S, 1234)
+    assert isinstance(t1, GPTDataset) and t1.indexed_indices[-1] + 1 == v1.indexed_indices[0]
+
+
+def test_yaml_megatron_dataset_feeds_the_training_loop_contract():
+    """class_name: MegatronDataset in the YAML -> pretrain.make_dataloader -> {"text": int64[mbs, S+1]} (pretraining.py:89)"""
+    from dolomite_engine_b200.arguments import get_args_from_dict, load_yaml
+    from dolomite_engine_b200.pretrain import make_dataloader
+
+    d = load_yaml(os.path.join(os.path.dirname(HERE), "configs", "c1_tiny.yml"))
+    d["datasets"] = [dict(class_name="MegatronDataset", data_name="Megatron",
+                          class_args=dict(data_path=[os.path.join(GOLD, "corpus_a")], split="100,0,0", sequence_length=16,
+                                          eval_steps=2, seed=7))]
+    d["training_parameters"].update(num_training_steps=4, micro_batch_size=2, gradient_accumulation_steps=1, eval_interval=2)
+    args = get_args_from_dict(d)
+    seen = []
+    for rank in range(2):
+        it = make_dataloader(args, None, rank, world=2)
+        seen.append([next(it)["text"] for _ in range(4)])
+        assert all(tuple(t.shape) == (2, 17) and t.dtype == torch.int64 for t in seen[-1])
+    assert not torch.equal(seen[0][0], seen[1][0])  # ranks read different rows of the same global batch
+    # resuming at consumed_samples = 2 steps * (mbs * world) reproduces step 2 onwards
+    it = make_dataloader(args, None, 0, world=2, consumed_samples=2 * 2 * 2)
+    assert torch.equal(next(it)["text"], seen[0][2])
