@@ -10,4 +10,4 @@ from .modeling import (
     MoEDolomiteForCausalLM,
 )
 from .utils import convert_padding_free_lists_to_tensors
-from .model_conversion import import_from_huggingface
+from .model_conversion import export_to_huggingface, import_from_huggingface

@@ -150,3 +150,94 @@ def import_from_huggingface(pretrained_model_name_or_path: str, save_path: str) 
             import shutil
 
             shutil.copy(p, os.path.join(save_path, extra))
+
+
+# ------------------------------------------------------------------------------------------------
+# export: dolomite safetensors + config  ->  HuggingFace Llama / Granite layout (weight re-layout only)
+# model_conversion/__init__.py:30-46, llama.py:152-290, granite.py:83-150
+# ------------------------------------------------------------------------------------------------
+def _export_config(config: GPTDolomiteConfig, model_type: str) -> dict:
+    assert config.activation_function == "swiglu" and config.normalization_function == "rmsnorm"
+    assert config.position_embedding_type == "rope"
+    out = dict(
+        model_type=model_type,
+        architectures=["LlamaForCausalLM" if model_type == "llama" else "GraniteForCausalLM"],
+        vocab_size=config.vocab_size,
+        max_position_embeddings=config.n_positions,
+        hidden_size=config.n_embd,
+        num_hidden_layers=config.n_layer,
+        num_attention_heads=config.n_head,
+        num_key_value_heads=config.num_key_value_heads,
+        intermediate_size=4 * config.n_embd if config.n_inner is None else config.n_inner,
+        hidden_act="silu",
+        rms_norm_eps=config.layer_norm_epsilon,
+        use_cache=config.use_cache,
+        attention_bias=config.add_bias,
+        mlp_bias=config.add_bias,
+        tie_word_embeddings=config.tie_word_embeddings,
+        initializer_range=config.initializer_range,
+        rope_theta=config.rope_theta,
+        rope_scaling=config.rope_scaling,
+        attention_dropout=config.attn_pdrop,
+        bos_token_id=config.bos_token_id,
+        eos_token_id=config.eos_token_id,
+        pad_token_id=config.pad_token_id,
+        torch_dtype="float32",
+    )
+    if model_type == "llama":
+        # a Llama checkpoint has no place for the muP multipliers (llama.py:183-186)
+        assert config.m_emb is None and config.m_residual is None and config.m_width is None
+        assert config.attention_multiplier is None
+    else:
+        one = lambda x: 1 if x is None else x  # noqa: E731
+        out.update(embedding_multiplier=one(config.m_emb), residual_multiplier=one(config.m_residual),
+                   logits_scaling=one(config.m_width),
+                   attention_multiplier=(config.n_embd // config.n_head) ** -0.5 if config.attention_multiplier is None
+                   else config.attention_multiplier)
+    return out
+
+
+def _export_state_dict(m: SafeTensorsWeightsManager, config: GPTDolomiteConfig) -> dict:
+    hd = config.n_embd // config.n_head
+    sd = {
+        "model.embed_tokens.weight": m.get_tensor("transformer.wte.weight"),
+        "model.norm.weight": m.get_tensor("transformer.ln_f.weight"),
+    }
+    if m.has_tensor("lm_head.weight"):
+        sd["lm_head.weight"] = m.get_tensor("lm_head.weight")
+    for i in range(config.n_layer):
+        src, dst = f"transformer.h.{i}.", f"model.layers.{i}."
+        sd[dst + "input_layernorm.weight"] = m.get_tensor(src + "ln_1.weight")
+        sd[dst + "post_attention_layernorm.weight"] = m.get_tensor(src + "ln_2.weight")
+        for suffix in ("weight", "bias"):
+            if not m.has_tensor(src + f"mlp.c_fc.{suffix}"):
+                continue
+            up, gate = split_up_gate_tensor_for_mlp(m.get_tensor(src + f"mlp.c_fc.{suffix}"))
+            sd[dst + f"mlp.up_proj.{suffix}"], sd[dst + f"mlp.gate_proj.{suffix}"] = up.contiguous(), gate.contiguous()
+            sd[dst + f"mlp.down_proj.{suffix}"] = m.get_tensor(src + f"mlp.c_proj.{suffix}")
+            q, k, v = split_query_key_value_tensor_for_attention(
+                m.get_tensor(src + f"attn.c_attn.{suffix}"), config.n_head, config.num_key_value_heads, hd,
+                config.attention_head_type)
+            sd[dst + f"self_attn.q_proj.{suffix}"] = q.contiguous()
+            sd[dst + f"self_attn.k_proj.{suffix}"] = k.contiguous()
+            sd[dst + f"self_attn.v_proj.{suffix}"] = v.contiguous()
+            sd[dst + f"self_attn.o_proj.{suffix}"] = m.get_tensor(src + f"attn.c_proj.{suffix}")
+    return sd
+
+
+def export_to_huggingface(pretrained_model_name_or_path: str, save_path: str, model_type: str) -> None:
+    """model_conversion/__init__.py:39-46: `model_type` in {"llama", "granite"} on this path"""
+    if model_type not in _SUPPORTED:
+        raise NotImplementedError(f"the current model_type ({model_type}) is not yet supported")
+    config = GPTDolomiteConfig.from_pretrained(pretrained_model_name_or_path)
+    sd = _export_state_dict(SafeTensorsWeightsManager(pretrained_model_name_or_path), config)
+    os.makedirs(save_path, exist_ok=True)
+    SafeTensorsWeightsManager.save_state_dict(sd, save_path)
+    with open(os.path.join(save_path, "config.json"), "w") as f:
+        json.dump(_export_config(config, model_type), f, indent=2)
+    for extra in ("tokenizer.json", "tokenizer_config.json", "special_tokens_map.json", "tokenizer.model"):
+        p = os.path.join(pretrained_model_name_or_path, extra)
+        if os.path.exists(p):
+            import shutil
+
+            shutil.copy(p, os.path.join(save_path, extra))

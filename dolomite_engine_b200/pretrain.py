@@ -115,29 +115,45 @@ def make_dataloader(args: TrainingArgs, model, rank: int, world: int = 1, consum
                                   ragged=bool(ds.class_args.get("ragged", False)))
 
 
-def train(args: TrainingArgs, model, optimizer, scheduler, dataloader, rank: int, world: int) -> list[float]:
+def train(args: TrainingArgs, model, optimizer, scheduler, dataloader, rank: int, world: int, starting_iteration: int = 0) -> list[float]:
+    """pretrain.py:60-205: the step loop; checkpoints every `save_args.save_interval` steps in the reference's layout"""
+    from .checkpointing import save_checkpoint
+
     tp = args.training_parameters
     seq = args.datasets[0].class_args["sequence_length"]
     tflop_per_step = get_model_tflops(model.config, tp.micro_batch_size * tp.gradient_accumulation_steps, seq)
+    samples_per_step = tp.micro_batch_size * tp.gradient_accumulation_steps * world
+    save_args = getattr(args, "save_args", None)
     losses = []
     t0 = time.perf_counter()
-    for step in range(1, tp.num_training_steps + 1):
+    for step in range(starting_iteration + 1, tp.num_training_steps + 1):
         loss, grad_norm = train_step(model, optimizer, scheduler, train_dataloader=dataloader,
                                      gradient_accumulation_steps=tp.gradient_accumulation_steps,
                                      gradient_clipping=tp.gradient_clipping)
         losses.append(loss)
         if rank == 0 and step % args.logging_args.log_interval == 0:
-            dt = (time.perf_counter() - t0) / step
+            dt = (time.perf_counter() - t0) / (step - starting_iteration)
             print(f"step {step}: loss {loss:.4f} grad_norm {grad_norm:.4f} lr {scheduler.get_last_lr()[0]:.3e} "
                   f"step_time {dt:.3f}s FLOPS {tflop_per_step / dt:.1f} TFLOP/s/GPU", flush=True)
+        if save_args is not None and (step % save_args.save_interval == 0 or step == tp.num_training_steps):
+            save_checkpoint(args, model, optimizer, scheduler, None, None, step,
+                            metadata={"consumed_samples": step * samples_per_step})
     return losses
 
 
 def main() -> None:
     args = get_args()
     model, optimizer, scheduler, (rank, world, _) = build(args)
-    dl = make_dataloader(args, model, rank, world)
-    train(args, model, optimizer, scheduler, dl, rank, world)
+    # resume (pretrain.py:329-343): parameters, Adam moments, scheduler, RNG; the data feed restarts at consumed_samples
+    from .checkpointing import load_checkpoint_for_training
+
+    starting_iteration, consumed_samples = 0, 0
+    loaded = load_checkpoint_for_training(args, model, optimizer, scheduler, None)
+    if loaded is not None:
+        starting_iteration, metadata, _ = loaded
+        consumed_samples = int((metadata or {}).get("consumed_samples", 0))
+    dl = make_dataloader(args, model, rank, world, consumed_samples)
+    train(args, model, optimizer, scheduler, dl, rank, world, starting_iteration)
     if dist.is_initialized():
         dist.barrier()
         dist.destroy_process_group()

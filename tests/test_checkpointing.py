@@ -1,0 +1,129 @@
+"""Reference checkpoint layout (checkpointing.py:50-263): file tree, key names, full-tensor
+round trip through the flat shards -- single process and world_size 2 (gloo, CPU)."""
+import json
+import os
+import sys
+import types
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build(world: int, rank: int, seed: int):
+    from dolomite_engine_b200.engine import DolomiteEngine
+    from dolomite_engine_b200.hf_models import GPTDolomiteConfig
+
+    cfg = GPTDolomiteConfig(n_embd=64, n_head=4, n_layer=2, n_inner=96, vocab_size=264, attention_head_type="gqa",
+                            num_key_value_heads=2, add_bias=True, activation_function="swiglu",
+                            position_embedding_type="rope", normalization_function="rmsnorm", resid_pdrop=0, embd_pdrop=0,
+                            attn_pdrop=0)
+    engine = DolomiteEngine(cfg, "cpu", world_size=world, rank=rank, seed=seed)
+    if world > 1:
+        engine.comm = types.SimpleNamespace(group=dist.group.WORLD)
+    model = types.SimpleNamespace(engine=engine)
+    opt = torch.optim.AdamW([u.master for u in engine.units], lr=1e-3, betas=(0.9, 0.95), eps=1e-10, weight_decay=0.1)
+    for ui, u in enumerate(engine.units):  # make the moments non-trivial (each rank owns a different slice of them)
+        full = torch.zeros(u.padded)  # the alignment padding never receives a gradient
+        full[: u.numel] = torch.randn(u.numel, generator=torch.Generator().manual_seed(100 + seed + ui))
+        u.master.grad = full[rank * u.shard_numel : (rank + 1) * u.shard_numel].clone()
+    opt.step()
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0 / (1 + s))
+    sched.step()
+    return engine, model, opt, sched
+
+
+def _args(path, load=False):
+    ns = types.SimpleNamespace
+    return ns(save_args=ns(save_path=path, save_optimizer=True),
+              load_args=ns(load_path=path, iteration=None, load_optimizer=True, load_lr_scheduler=True, load_rng_state=True,
+                           load_dataloader_state=True, load_experiments_tracker_state=True, load_starting_iteration=True) if load else None,
+              model_dump=lambda mode="json": {"note": "training config"})
+
+
+def _roundtrip(path, world, rank):
+    from dolomite_engine_b200 import checkpointing as C
+
+    engine, model, opt, sched = _build(world, rank, seed=1)
+    loader = types.SimpleNamespace(consumed_samples=48)
+    want_model = C.model_state_dict(model)
+    want_opt = C.optimizer_state_dict(model, opt)
+    C.save_checkpoint(_args(path), model, opt, sched, loader, None, 7, metadata={"consumed_samples": 48})
+    # a differently initialised replica restores everything
+    engine2, model2, opt2, sched2 = _build(world, rank, seed=2)
+    assert not torch.equal(engine2.units[1].master.data, engine.units[1].master.data)
+    it, meta, _ = C.load_checkpoint_for_training(_args(path, load=True), model2, opt2, sched2, None)
+    assert it == 7 and meta == {"consumed_samples": 48}
+    for u, u2 in zip(engine.units, engine2.units):
+        assert torch.equal(u.master.data, u2.master.data)
+        if world == 1:  # bf16 compute copy refreshed from the loaded masters
+            assert torch.equal(u2.compute[: u2.shard_numel], u2.master.data.bfloat16())
+        for k in ("exp_avg", "exp_avg_sq"):
+            assert torch.equal(opt.state[u.master][k], opt2.state[u2.master][k])
+        assert float(opt2.state[u2.master]["step"]) == 1.0
+    assert sched2.state_dict()["last_epoch"] == sched.state_dict()["last_epoch"]
+    got = C.model_state_dict(model2)
+    assert got.keys() == want_model.keys() and all(torch.equal(got[k], want_model[k]) for k in got)
+    return want_model, want_opt
+
+
+def test_single_process_layout_and_names(tmp_path):
+    path = str(tmp_path / "ckpt")
+    sd, osd = _roundtrip(path, 1, 0)
+    base = os.path.join(path, "global_step7")
+    for rel in ("model.pt", "optimizer.pt", "lr_scheduler.pt", "rng_state/rng_state-0.pt", "dataloader/dataloader-0.pt",
+                "metadata.json", "training_config.yml"):
+        assert os.path.isfile(os.path.join(base, rel)), rel
+    assert json.load(open(os.path.join(path, "latest_checkpointed_iteration.json"))) == {"latest_checkpointed_iteration": 7}
+    on_disk = torch.load(os.path.join(base, "model.pt"))
+    assert set(on_disk) == set(sd)
+    # reference fully-qualified names under the wrapper's "model." prefix; tied head is not serialised
+    for k in ("model.transformer.wte.weight", "model.transformer.h.0.ln_1.weight", "model.transformer.h.1.attn.c_attn.bias",
+              "model.transformer.h.1.mlp.c_proj.weight", "model.transformer.ln_f.weight"):
+        assert k in on_disk and on_disk[k].dtype == torch.float32
+    assert "model.lm_head.weight" not in on_disk
+    assert on_disk["model.transformer.h.0.attn.c_attn.weight"].shape == (64 + 2 * 2 * 16, 64)
+    o = torch.load(os.path.join(base, "optimizer.pt"))
+    assert set(o) == {"state", "param_groups"} and set(o["state"]) == set(sd)
+    e = o["state"]["model.transformer.h.0.mlp.c_fc.weight"]
+    assert set(e) == {"step", "exp_avg", "exp_avg_sq"} and e["exp_avg"].shape == (192, 64)
+    assert o["param_groups"][0]["lr"] == pytest.approx(5e-4) and o["param_groups"][0]["params"][0].startswith("model.")
+    assert torch.load(os.path.join(base, "dataloader", "dataloader-0.pt"), weights_only=False) == {"consumed_samples": 48}
+
+
+def _worker(rank, world, port, path, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sd, _ = _roundtrip(path, world, rank)
+        # the sharded save must describe the same full tensors as an unsharded replica built from the same seed
+        engine1, model1, _, _ = _build(1, 0, seed=1)
+        from dolomite_engine_b200 import checkpointing as C
+
+        ref = C.model_state_dict(model1)
+        assert all(torch.equal(ref[k], sd[k]) for k in ref)
+        q.put((rank, "ok"))
+    except Exception:  # noqa
+        import traceback
+
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_checkpoint_roundtrip(tmp_path):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path / "ckpt2"), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status in results:
+        assert status == "ok", f"rank {rank}: {status}"

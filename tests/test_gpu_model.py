@@ -275,3 +275,59 @@ def test_block_activation_checkpointing_gives_identical_gradients(every):
     assert grads[0][0] == grads[1][0]
     for n, g in grads[0][1].items():
         assert rel_l2(grads[1][1][n], g) < 1e-5, n
+
+
+def test_checkpoint_resume_continues_the_same_trajectory(tmp_path):
+    """checkpointing.py (reference layout): 2 steps, save, restore into a differently initialised model + fresh optimizer,
+    2 more steps == 4 uninterrupted steps (same kernels on the same restored fp32 masters and Adam moments; the only
+    non-determinism left is the fp32 atomics of the embedding / dQ reductions)."""
+    import types
+
+    from dolomite_engine_b200 import checkpointing as C
+    from dolomite_engine_b200.distributed import ShardedDataParallel
+    from dolomite_engine_b200.model_wrapper import ModelWrapperForPretraining
+    from dolomite_engine_b200.optimization import get_optimizer, get_scheduler
+    from dolomite_engine_b200.train_utils import train_step
+
+    kw = GPU_CONFIGS["hd80_bias"]
+    ocfg = O.OracleConfig(**kw)
+    tokens = torch.from_numpy(sample_tokens(ocfg))
+    oargs = {"lr": 1e-3, "weight_decay": 0.1, "betas": [0.9, 0.95], "eps": 1e-10}
+
+    def make(seed):
+        w = ModelWrapperForPretraining(pretrained_config=gpu_config(kw).to_dict(), micro_batch_size=2, sequence_length=64)
+        w.model.load_state_dict(oracle_params(ocfg))
+        sdp = ShardedDataParallel(w)
+        opt = get_optimizer("DolomiteFusedAdamW", oargs, sdp)
+        sched = get_scheduler(opt, 2, 0, None, 10, "cosine", 0.1)
+        return sdp, opt, sched
+
+    def batches():
+        while True:
+            yield {"text": tokens}
+
+    def run(sdp, opt, sched, n):
+        dl = batches()
+        return [train_step(sdp, opt, sched, train_dataloader=dl, gradient_accumulation_steps=1, gradient_clipping=1.0)[0]
+                for _ in range(n)]
+
+    a = make(None)
+    straight = run(*a, 4)
+    b = make(None)
+    first = run(*b, 2)
+    ns = types.SimpleNamespace
+    args = ns(save_args=ns(save_path=str(tmp_path), save_optimizer=True), model_dump=lambda mode="json": {})
+    C.save_checkpoint(args, b[0], b[1], b[2], None, None, 2, metadata={"consumed_samples": 8})
+    c = make(None)
+    for u in c[0].engine.units:  # scramble so that only the checkpoint can explain a matching trajectory
+        u.master.data.mul_(0.5)
+    largs = ns(load_args=ns(load_path=str(tmp_path), iteration=None, load_optimizer=True, load_lr_scheduler=True,
+                            load_rng_state=True, load_dataloader_state=False, load_experiments_tracker_state=False,
+                            load_starting_iteration=True))
+    it, meta, _ = C.load_checkpoint_for_training(largs, c[0], c[1], c[2], None)
+    assert it == 2 and meta["consumed_samples"] == 8 and c[1]._step == 2
+    c[0].mark_parameters_updated() if hasattr(c[0], "mark_parameters_updated") else None
+    second = run(*c, 2)
+    assert first == pytest.approx(straight[:2], rel=1e-6)
+    assert second == pytest.approx(straight[2:], rel=2e-4), (straight, first, second)
+    assert c[2].get_last_lr() == pytest.approx(a[2].get_last_lr())

@@ -96,3 +96,34 @@ def test_unsupported_family_raises(tmp_path):
     json.dump({"model_type": "mixtral"}, open(os.path.join(src, "config.json"), "w"))
     with pytest.raises(NotImplementedError):
         import_from_huggingface(src, str(tmp_path / "y"))
+
+
+@pytest.mark.parametrize("model_type", ["llama", "granite"])
+def test_export_to_huggingface_is_the_exact_inverse_of_import(tmp_path, model_type):
+    """model_conversion/__init__.py:39-46, llama.py:152-290: HF -> dolomite -> HF reproduces every tensor bit for bit, the
+    exported config carries the HF names, and HuggingFace's own LlamaForCausalLM loads the exported directory."""
+    from dolomite_engine_b200.hf_models.model_conversion import export_to_huggingface
+
+    extra = dict(embedding_multiplier=12.0, residual_multiplier=0.22, logits_scaling=8.0, attention_multiplier=0.015625) \
+        if model_type == "granite" else {}
+    src, mid, dst = str(tmp_path / "hf"), str(tmp_path / "dolomite"), str(tmp_path / "hf_again")
+    cfg, sd = _write_llama(src, model_type, **extra)
+    import_from_huggingface(src, mid)
+    export_to_huggingface(mid, dst, model_type)
+    back = SafeTensorsWeightsManager(dst).state_dict()
+    assert set(back) == set(sd)
+    for k, v in sd.items():
+        assert torch.equal(back[k], v), k
+    out_cfg = json.load(open(os.path.join(dst, "config.json")))
+    for k in ("vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads",
+              "num_key_value_heads", "max_position_embeddings", "rms_norm_eps", "rope_theta", "tie_word_embeddings",
+              "attention_bias", "mlp_bias", "bos_token_id", "eos_token_id", *extra):
+        assert out_cfg[k] == cfg[k], k
+    assert out_cfg["model_type"] == model_type
+    with pytest.raises(NotImplementedError):
+        export_to_huggingface(mid, dst, "mixtral")
+    if model_type == "llama":
+        from transformers import LlamaForCausalLM
+
+        hf = LlamaForCausalLM.from_pretrained(dst, torch_dtype=torch.float32)
+        assert torch.equal(hf.model.layers[1].self_attn.k_proj.weight.data, sd["model.layers.1.self_attn.k_proj.weight"])
