@@ -69,3 +69,19 @@ def test_sass_is_blackwell_native():
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
     assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync path found"
+
+
+def test_data_feed_library_exports_every_symbol_of_its_header():
+    """include/dolomite_data.h <-> lib/libdolomite_data.so (host C++, no CUDA)"""
+    from dolomite_engine_b200 import build
+
+    build.build()
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "dolomite_data.h")).read(), flags=re.S)
+    syms = sorted(set(re.findall(r"\b(dolomite_data_\w+)\s*\(", src)))
+    assert len(syms) == 5
+    lib = ctypes.CDLL(os.path.join(ROOT, "dolomite_engine_b200", "lib", "libdolomite_data.so"))
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in dolomite_data.h but not exported"
+    lib.dolomite_data_num_samples.restype = ctypes.c_int64
+    lib.dolomite_data_num_samples.argtypes = [ctypes.c_int64] * 3
+    assert lib.dolomite_data_num_samples(8, 2, 100) == (2 * 100 - 1) // 8
