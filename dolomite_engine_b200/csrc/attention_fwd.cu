@@ -171,13 +171,13 @@ __global__ void __launch_bounds__(FWD_THREADS)
                 // tcgen05.ld latency, not issue slots, bounded the first version: ncu issue-active 37 %)
                 float mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
                 uint32_t va[32], vb[32];
-                auto fold = [&](const uint32_t (&v)[32]) {
+                auto fold = [&](const uint32_t (&v)[32]) {  // 3-input FMNMX3: half the instructions of a max chain
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        mx = fmaxf(mx, __uint_as_float(v[i]));
-                        mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
-                        mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
-                        mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
+                    for (int i = 0; i < 32; i += 8) {
+                        mx = fmax3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                        mx1 = fmax3(mx1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                        mx2 = fmax3(mx2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+                        mx3 = fmax3(mx3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
                     }
                 };
                 tmem_ld32(t_lane, va);
@@ -235,11 +235,11 @@ __global__ void __launch_bounds__(FWD_THREADS)
                 auto expo = [&](const uint32_t (&v)[32], int ch) {
                     uint32_t pk[16];
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
-                        const float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, neg_m));
-                        lsum += p0;
-                        lsum1 += p1;
+                    for (int i = 0; i < 32; i += 2) {  // packed fp32 pipes: FFMA2 for scale/shift, FADD2 for the row sums
+                        float x0, x1;
+                        ffma2_bcast(x0, x1, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), p.scale_log2, neg_m);
+                        const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+                        fadd2(lsum, lsum1, p0, p1);
                         pk[i >> 1] = pack_bf16(p0, p1);
                     }
                     tmem_st16(t_lane + ch * 16, pk);  // bf16 P chunk ch aliases fp32 S columns [16ch, 16ch+16): consumed

@@ -47,6 +47,8 @@ def _err(a, b):
 
 def _time(fn, iters=20, warmup=3):
     torch = _t()
+    iters = int(os.environ.get("PROBE_ITERS", iters))      # ncu runs: one launch per kernel is enough
+    warmup = int(os.environ.get("PROBE_WARMUP", warmup))
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -757,6 +759,99 @@ def attn_bwd_experiments():
     res["fwd"] = {"ms": ms, "tflops": flops / 2.5 / ms / 1e9}
     res["ok"] = True
     return res
+
+
+@case
+def moe_bench_c4():
+    """MoEDolomite C4 shape (H 2048, 16 heads hd 128, 8 experts top-2, F 4096 per expert, seq 2048), 2 layers, mbs 8
+    (T = 16384): fwd+bwd step time and the rate of the grouped expert GEMMs (CUDA events around every launch)."""
+    torch = _t()
+    import numpy as np
+
+    from dolomite_engine_b200 import kernels as k
+    from dolomite_engine_b200.hf_models import MoEDolomiteConfig, MoEDolomiteForCausalLM
+
+    H, E, topk, F, S, mbs, L, V = 2048, 8, 2, 4096, 2048, 8, 2, 50304
+    cfg = MoEDolomiteConfig(vocab_size=V, n_positions=S, n_embd=H, n_layer=L, n_head=16, n_inner=F,
+                            attention_head_type="mha", add_bias=False, num_experts=E, num_experts_per_tok=topk,
+                            position_embedding_type="rope", normalization_function="rmsnorm",
+                            activation_function="swiglu", resid_pdrop=0, embd_pdrop=0, attn_pdrop=0, eos_token_id=0)
+    model = MoEDolomiteForCausalLM(cfg, seed=1)
+    model.assume_unit_loss_grad = True
+    T = S * mbs
+    g = torch.Generator(device="cuda").manual_seed(0)
+    ids = torch.randint(0, V, (T,), device="cuda", generator=g)
+    labels = torch.randint(0, V, (T,), device="cuda", generator=g)
+    pos = (torch.arange(T, device="cuda") % S)
+    cu = torch.arange(0, T + 1, S, dtype=torch.int32, device="cuda")
+
+    def step():
+        model.engine.zero_grad()
+        loss = model.forward_pretraining_loss(ids, pos, cu, S, labels)
+        loss.backward()
+        return loss
+
+    # time every grouped GEMM launch of one step
+    import dolomite_engine_b200._lib as L_
+    records = []
+    orig_call = L_.call
+
+    def timed_call(name, *a):
+        if "grouped" in name:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = orig_call(name, *a)
+            e1.record()
+            records.append((name, e0, e1))
+            return r
+        return orig_call(name, *a)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    L_.call = timed_call
+    k._lib.call = timed_call
+    try:
+        loss = step()
+        torch.cuda.synchronize()
+    finally:
+        L_.call = orig_call
+        k._lib.call = orig_call
+    grouped_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in records)
+    # expert FLOPs of one step: fwd 2 GEMMs + bwd 4 (dgrad + wgrad each); T*topk routed rows; c_fc 2F (glu), c_proj F
+    flops = L * 3 * 2.0 * (T * topk) * H * (2 * F + F)
+    ms = _time(step, iters=5)
+    return {"loss": float(loss.item()), "step_ms_fwd_bwd": ms, "tokens_per_s_fwd_bwd": T / ms * 1e3,
+            "grouped_gemm_launches": len(records), "grouped_gemm_ms": grouped_ms,
+            "grouped_gemm_tflops": flops / grouped_ms / 1e9, "ok": bool(np.isfinite(loss.item()))}
+
+
+@case
+def moe_layer_fwd_c4():
+    """only the MoE MLP forward at the C4 shape (for ncu: launch order per iteration = router gemm, route kernels, gather,
+    grouped c_fc gemm, swiglu, grouped c_proj gemm, combine)"""
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+
+    H, E, topk, F, T = 2048, 8, 2, 4096, 16384
+    x = (torch.randn(T, H, device="cuda") * 0.5).bfloat16()
+    gate = (torch.randn(E, H, device="cuda") * 0.05).bfloat16()
+    w_fc = (torch.randn(E, 2 * F, H, device="cuda") * 0.02).bfloat16()
+    w_proj = (torch.randn(E, H, F, device="cuda") * 0.02).bfloat16()
+    res = torch.zeros(T, H, device="cuda", dtype=torch.bfloat16)
+
+    def fwd():
+        logits = k.gemm(x, gate, flags=0)
+        plan = k.moe_route(logits, topk)
+        xg = k.moe_gather(x, plan)
+        fc = k.gemm_grouped_m(xg, w_fc, plan, b_mn=False)
+        act = k.swiglu_fwd(fc)
+        yg = k.gemm_grouped_m(act, w_proj, plan, b_mn=False)
+        return k.moe_combine(yg, plan, c=res, alpha=1.0)
+
+    ms = _time(fwd, iters=5, warmup=2)
+    flops = 2.0 * T * topk * H * 3 * F
+    return {"fwd_ms": ms, "expert_gemm_tflops_incl_routing_kernels": flops / ms / 1e9, "ok": True}
 
 
 def main():
