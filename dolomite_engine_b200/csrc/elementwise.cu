@@ -171,8 +171,10 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 // RoPE in place on packed qkv.  One block per token; each work item = one 8-wide vector of the first half of a
 // rotated head slot and its partner in the second half.  bf16 rounding after every op like the eager reference.
 // ------------------------------------------------------------------------------------------
+// The block is sized to the work items of ONE token (launch: round_up(items, 32) threads), so the (group, slot, vector)
+// decomposition -- integer divisions -- happens once per thread and the token loop only adds row strides.
 template <typename PosT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(1024)
     rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t row_stride, int64_t T, int n_groups, int q_per_group, int hd,
                 const __nv_bfloat16* __restrict__ cos_t, const __nv_bfloat16* __restrict__ sin_t,
                 const PosT* __restrict__ pos_ids, int64_t n_pos, float sin_sign) {
@@ -180,21 +182,17 @@ __global__ void __launch_bounds__(kThreads)
     const int vec_per_half = half >> 3;
     const int rot_slots = q_per_group + 1;
     const int items = n_groups * rot_slots * vec_per_half;
-    // flat (token, item) index space: every thread of every block has work (items per token is rarely a multiple of 256)
-    const int64_t total = T * items;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-        const int64_t t = i / items;
-        const int it = int(i - t * items);
-        int64_t pos = static_cast<int64_t>(__ldg(pos_ids + t));
-        pos = pos < 0 ? 0 : (pos >= n_pos ? n_pos - 1 : pos);
-        const __nv_bfloat16* c = cos_t + pos * hd;
-        const __nv_bfloat16* s = sin_t + pos * hd;
-        __nv_bfloat16* row = qkv + t * row_stride;
-        {
-            const int v = it % vec_per_half;
-            const int slot_lin = it / vec_per_half;
-            const int g = slot_lin / rot_slots, sl = slot_lin % rot_slots;
-            __nv_bfloat16* base = row + int64_t(g) * (q_per_group + 2) * hd + int64_t(sl) * hd + v * 8;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const int v = it % vec_per_half;
+        const int slot_lin = it / vec_per_half;
+        const int g = slot_lin / rot_slots, sl = slot_lin % rot_slots;
+        const int64_t slot_off = (int64_t(g) * (q_per_group + 2) + sl) * hd + v * 8;
+        for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
+            int64_t pos = static_cast<int64_t>(__ldg(pos_ids + t));
+            pos = pos < 0 ? 0 : (pos >= n_pos ? n_pos - 1 : pos);
+            const __nv_bfloat16* c = cos_t + pos * hd;
+            const __nv_bfloat16* s = sin_t + pos * hd;
+            __nv_bfloat16* base = qkv + t * row_stride + slot_off;
             uint4 a = *reinterpret_cast<uint4*>(base);
             uint4 b = *reinterpret_cast<uint4*>(base + half);
             float x1[8], x2[8], c1[8], c2[8], s1[8], s2[8], o1[8], o2[8];
@@ -713,16 +711,19 @@ extern "C" int dolomite_b200_rope_qk_inplace(void* qkv, int64_t row_stride, int6
     DOLO_REQUIRE(n_positions > 0, "rope: empty cos/sin table");
     if (T == 0) return DOLO_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid = grid_for(T * n_groups * (q_per_group + 1) * (head_dim / 16), kThreads);
+    const int items = n_groups * (q_per_group + 1) * (head_dim / 16);
+    const int threads = items >= 1024 ? 1024 : ((items + 31) / 32) * 32;
+    const int64_t want = int64_t(dolo_num_sms()) * (2048 / threads);
+    const int grid = int(T < want ? T : want);
     const float sgn = inverse ? -1.f : 1.f;
     auto Q = static_cast<__nv_bfloat16*>(qkv);
     auto C = static_cast<const __nv_bfloat16*>(cos_table);
     auto S = static_cast<const __nv_bfloat16*>(sin_table);
     if (position_ids_is_int64)
-        rope_kernel<int64_t><<<grid, kThreads, 0, st>>>(Q, row_stride, T, n_groups, q_per_group, head_dim, C, S,
+        rope_kernel<int64_t><<<grid, threads, 0, st>>>(Q, row_stride, T, n_groups, q_per_group, head_dim, C, S,
                                                         static_cast<const int64_t*>(position_ids), n_positions, sgn);
     else
-        rope_kernel<int32_t><<<grid, kThreads, 0, st>>>(Q, row_stride, T, n_groups, q_per_group, head_dim, C, S,
+        rope_kernel<int32_t><<<grid, threads, 0, st>>>(Q, row_stride, T, n_groups, q_per_group, head_dim, C, S,
                                                         static_cast<const int32_t*>(position_ids), n_positions, sgn);
     DOLO_LAUNCH_OK("rope");
     return DOLO_OK;

@@ -854,6 +854,12 @@ def moe_layer_fwd_c4():
     return {"fwd_ms": ms, "expert_gemm_tflops_incl_routing_kernels": flops / ms / 1e9, "ok": True}
 
 
+@case
+def attn_bench_hd128():
+    """Llama-3-8B-like attention core (C5): S=8192, 32 heads, hd 128 (MHA layout of the packed slots)"""
+    return _attn_bench(8192, 1, 32, 128)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case")
