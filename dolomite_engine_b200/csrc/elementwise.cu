@@ -150,13 +150,13 @@ __global__ void __launch_bounds__(kThreads)
 
 // out[c] += sum_p ws[p, c].  Block = 32 columns x 8 part-lanes (coalesced 128-byte rows, 8-way split of the sum).
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ ws, float* __restrict__ out,
-                                                              int parts, int H) {
+                                                              int parts, int H, int ld) {
     __shared__ float sm[8][33];
     const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cx;
     float s = 0.f;
     if (c < H)
-        for (int p = py; p < parts; p += 8) s += ws[int64_t(p) * H + c];
+        for (int p = py; p < parts; p += 8) s += ws[int64_t(p) * ld + c];
     sm[py][cx] = s;
     __syncthreads();
     if (py == 0 && c < H) {
@@ -311,6 +311,211 @@ __global__ void __launch_bounds__(kThreads)
     if (gc < F8 * 8) {
         atomicAdd(dbias + gc, a);
         atomicAdd(dbias + F8 * 8 + gc, b);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// tanh-GELU (activation_function gelu_pytorch_tanh, non-GLU MLP of the StarCoder / bigcode shape)
+//   y = 0.5 x (1 + tanh(k (x + c x^3))),  k = sqrt(2/pi), c = 0.044715
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tanh_fast(float z) {
+    // tanh(z) = 1 - 2 / (1 + e^{2z}); MUFU ex2 + MUFU rcp, saturates cleanly for |z| large
+    return 1.f - __fdividef(2.f, 1.f + __expf(2.f * z));
+}
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+    const float z = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+    return 0.5f * x * (1.f + tanh_fast(z));
+}
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+    const float z = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+    const float t = tanh_fast(z);
+    const float dz = 0.7978845608028654f * (1.f + 3.f * 0.044715f * x * x);
+    return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * dz;
+}
+
+__global__ void __launch_bounds__(kThreads) gelu_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t n8) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += int64_t(gridDim.x) * blockDim.x) {
+        float f[8];
+        unpack8(__ldg(x + i), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = gelu_tanh_f(f[j]);
+        y[i] = pack8(f);
+    }
+}
+
+// dx = dy * gelu'(x); optionally accumulates the bias gradient of the producing linear (column sums of the bf16 dx).
+// Same block shape as swiglu_bwd_bias_kernel: 32 column vectors x 8 row lanes.
+__global__ void __launch_bounds__(kThreads)
+    gelu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, uint4* __restrict__ dx,
+                    float* __restrict__ dbias, int64_t T, int64_t F8, int rows_per_block) {
+    __shared__ float sm[8][256];
+    const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int64_t c = int64_t(blockIdx.x) * 32 + lane;
+    const int64_t r0 = int64_t(blockIdx.y) * rows_per_block;
+    const int64_t r1 = min(T, r0 + rows_per_block);
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    if (c < F8) {
+        for (int64_t t = r0 + rl; t < r1; t += 8) {
+            float xf[8], d[8];
+            unpack8(__ldg(x + t * F8 + c), xf);
+            unpack8(__ldg(dy + t * F8 + c), d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[j] *= gelu_tanh_grad(xf[j]);
+            const uint4 pk = pack8(d);
+            dx[t * F8 + c] = pk;
+            if (dbias != nullptr) {
+                unpack8(pk, d);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s[j] += d[j];
+            }
+        }
+    }
+    if (dbias == nullptr) return;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[rl][lane * 8 + j] = s[j];
+    __syncthreads();
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += sm[w][threadIdx.x];
+    const int64_t gc = int64_t(blockIdx.x) * 256 + threadIdx.x;
+    if (gc < F8 * 8) atomicAdd(dbias + gc, a);
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm (normalization_function layernorm = torch.nn.LayerNorm): fp32 statistics, ONE rounding to bf16 at the end
+//   y = bf16( (x - mean) * rstd * w + b )
+// Same block-per-row structure as the RMSNorm kernels; mean and rstd are saved for backward.
+// ------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kThreads)
+    layernorm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w, const uint4* __restrict__ b,
+                         uint4* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t T, int H8,
+                         float eps, float inv_h) {
+    __shared__ float red[8];
+    for (int64_t row = blockIdx.x; row < T; row += gridDim.x) {
+        uint4 xv[NV];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int idx = threadIdx.x + i * kThreads;
+            if (idx < H8) {
+                xv[i] = __ldg(x + row * H8 + idx);
+                float f[8];
+                unpack8(xv[i], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += f[j];
+            }
+        }
+        const float mu = block_sum(s, red) * inv_h;
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int idx = threadIdx.x + i * kThreads;
+            if (idx < H8) {
+                float f[8];
+                unpack8(xv[i], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ss += (f[j] - mu) * (f[j] - mu);
+            }
+        }
+        const float r = rsqrtf(block_sum(ss, red) * inv_h + eps);
+        if (threadIdx.x == 0) {
+            mean[row] = mu;
+            rstd[row] = r;
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int idx = threadIdx.x + i * kThreads;
+            if (idx < H8) {
+                float f[8], g[8], bb[8];
+                unpack8(xv[i], f);
+                unpack8(__ldg(w + idx), g);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = (f[j] - mu) * r * g[j];
+                if (b != nullptr) {
+                    unpack8(__ldg(b + idx), bb);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] += bb[j];
+                }
+                y[row * H8 + idx] = pack8(f);
+            }
+        }
+    }
+}
+
+// dx = rstd * (g*w - mean(g*w) - xhat * mean(g*w*xhat)) [+ dx_add];  dw += sum_rows g*xhat;  db += sum_rows g.
+// Per-thread dw / db partials go to the workspace [gridDim.x][2][H] (reduced by reduce_partials_kernel).
+template <int NV>
+__global__ void __launch_bounds__(kThreads)
+    layernorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ w,
+                         const float* __restrict__ mean, const float* __restrict__ rstd, const uint4* __restrict__ dx_add,
+                         uint4* __restrict__ dx, float* __restrict__ ws, int64_t T, int H8, float inv_h) {
+    __shared__ float red[8];
+    float dwacc[NV][8], dbacc[NV][8];
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dwacc[i][j] = dbacc[i][j] = 0.f;
+    for (int64_t row = blockIdx.x; row < T; row += gridDim.x) {
+        const float mu = mean[row], r = rstd[row];
+        uint4 xv[NV], gv[NV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int idx = threadIdx.x + i * kThreads;
+            if (idx < H8) {
+                xv[i] = __ldg(x + row * H8 + idx);
+                gv[i] = __ldg(dy + row * H8 + idx);
+                float xf[8], gf[8], wf[8];
+                unpack8(xv[i], xf);
+                unpack8(gv[i], gf);
+                unpack8(__ldg(w + idx), wf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = (xf[j] - mu) * r;
+                    const float gw = gf[j] * wf[j];
+                    s1 += gw;
+                    s2 += gw * xh;
+                    dwacc[i][j] += gf[j] * xh;
+                    dbacc[i][j] += gf[j];
+                }
+            }
+        }
+        s1 = block_sum(s1, red) * inv_h;
+        s2 = block_sum(s2, red) * inv_h;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int idx = threadIdx.x + i * kThreads;
+            if (idx < H8) {
+                float xf[8], gf[8], wf[8], o[8];
+                unpack8(xv[i], xf);
+                unpack8(gv[i], gf);
+                unpack8(__ldg(w + idx), wf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = r * (gf[j] * wf[j] - s1 - (xf[j] - mu) * r * s2);
+                if (dx_add != nullptr) {
+                    float a[8];
+                    unpack8(__ldg(dx_add + row * H8 + idx), a);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] += a[j];
+                }
+                dx[row * H8 + idx] = pack8(o);
+            }
+        }
+    }
+    float* wrow = ws + int64_t(blockIdx.x) * 2 * H8 * 8;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int idx = threadIdx.x + i * kThreads;
+        if (idx < H8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                wrow[idx * 8 + j] = dwacc[i][j];
+                wrow[H8 * 8 + idx * 8 + j] = dbacc[i][j];
+            }
+        }
     }
 }
 
@@ -694,9 +899,108 @@ extern "C" int dolomite_b200_rmsnorm_bwd(const void* dy, const void* x, const vo
     }
     DOLO_LAUNCH_OK("rmsnorm_bwd");
     if (dw_accum != nullptr) {
-        reduce_partials_kernel<<<(H + 31) / 32, 256, 0, st>>>(WS, dw_accum, parts, H);
+        reduce_partials_kernel<<<(H + 31) / 32, 256, 0, st>>>(WS, dw_accum, parts, H, H);
         DOLO_LAUNCH_OK("rmsnorm_bwd_reduce");
     }
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd,
+                                           int64_t T, int H, float eps, void* stream) {
+    DOLO_REQUIRE(H > 0 && H % 8 == 0, "layernorm: H=%d must be a positive multiple of 8", H);
+    DOLO_REQUIRE(H <= 8 * kThreads * 8, "layernorm: H=%d too large (max %d)", H, 8 * kThreads * 8);
+    DOLO_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && aligned16(b), "layernorm: pointers must be 16-byte aligned");
+    if (T == 0) return DOLO_OK;
+    const int H8 = H / 8;
+    const int nv = (H8 + kThreads - 1) / kThreads;
+    const int grid = int(T < int64_t(dolo_num_sms()) * 16 ? T : int64_t(dolo_num_sms()) * 16);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto X = static_cast<const uint4*>(x);
+    auto W = static_cast<const uint4*>(w);
+    auto B = static_cast<const uint4*>(b);
+    auto Y = static_cast<uint4*>(y);
+    const float inv_h = 1.f / float(H);
+    switch (nv) {
+        case 1: layernorm_fwd_kernel<1><<<grid, kThreads, 0, st>>>(X, W, B, Y, mean, rstd, T, H8, eps, inv_h); break;
+        case 2: layernorm_fwd_kernel<2><<<grid, kThreads, 0, st>>>(X, W, B, Y, mean, rstd, T, H8, eps, inv_h); break;
+        case 3:
+        case 4: layernorm_fwd_kernel<4><<<grid, kThreads, 0, st>>>(X, W, B, Y, mean, rstd, T, H8, eps, inv_h); break;
+        default: layernorm_fwd_kernel<8><<<grid, kThreads, 0, st>>>(X, W, B, Y, mean, rstd, T, H8, eps, inv_h); break;
+    }
+    DOLO_LAUNCH_OK("layernorm_fwd");
+    return DOLO_OK;
+}
+
+extern "C" int64_t dolomite_b200_layernorm_bwd_workspace_bytes(int H) {
+    return int64_t(rmsnorm_bwd_parts()) * 2 * H * sizeof(float);
+}
+
+extern "C" int dolomite_b200_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean,
+                                           const float* rstd, const void* dx_add, void* dx, float* dw_accum,
+                                           float* db_accum, void* workspace, int64_t T, int H, void* stream) {
+    DOLO_REQUIRE(H > 0 && H % 8 == 0, "layernorm_bwd: H=%d must be a positive multiple of 8", H);
+    DOLO_REQUIRE(H <= 8 * kThreads * 8, "layernorm_bwd: H=%d too large", H);
+    DOLO_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(w) && aligned16(dx) && aligned16(workspace) &&
+                     aligned16(dx_add),
+                 "layernorm_bwd: pointers must be 16-byte aligned");
+    if (T == 0) return DOLO_OK;
+    const int H8 = H / 8;
+    const int nv = (H8 + kThreads - 1) / kThreads;
+    int parts = rmsnorm_bwd_parts();
+    if (T < parts) parts = int(T);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto DY = static_cast<const uint4*>(dy);
+    auto X = static_cast<const uint4*>(x);
+    auto W = static_cast<const uint4*>(w);
+    auto DA = static_cast<const uint4*>(dx_add);
+    auto DX = static_cast<uint4*>(dx);
+    auto WS = static_cast<float*>(workspace);
+    const float inv_h = 1.f / float(H);
+    switch (nv) {
+        case 1: layernorm_bwd_kernel<1><<<parts, kThreads, 0, st>>>(DY, X, W, mean, rstd, DA, DX, WS, T, H8, inv_h); break;
+        case 2: layernorm_bwd_kernel<2><<<parts, kThreads, 0, st>>>(DY, X, W, mean, rstd, DA, DX, WS, T, H8, inv_h); break;
+        case 3:
+        case 4: layernorm_bwd_kernel<4><<<parts, kThreads, 0, st>>>(DY, X, W, mean, rstd, DA, DX, WS, T, H8, inv_h); break;
+        default: layernorm_bwd_kernel<8><<<parts, kThreads, 0, st>>>(DY, X, W, mean, rstd, DA, DX, WS, T, H8, inv_h); break;
+    }
+    DOLO_LAUNCH_OK("layernorm_bwd");
+    if (dw_accum != nullptr) {
+        reduce_partials_kernel<<<(H + 31) / 32, 256, 0, st>>>(WS, dw_accum, parts, H, 2 * H);
+        DOLO_LAUNCH_OK("layernorm_bwd_reduce_w");
+    }
+    if (db_accum != nullptr) {
+        reduce_partials_kernel<<<(H + 31) / 32, 256, 0, st>>>(WS + H, db_accum, parts, H, 2 * H);
+        DOLO_LAUNCH_OK("layernorm_bwd_reduce_b");
+    }
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_gelu_fwd(const void* x, void* y, int64_t n, void* stream) {
+    DOLO_REQUIRE(n % 8 == 0 && aligned16(x) && aligned16(y), "gelu: n must be a multiple of 8 and pointers 16-byte aligned");
+    if (n == 0) return DOLO_OK;
+    gelu_fwd_kernel<<<grid_for(n / 8, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(x), static_cast<uint4*>(y), n / 8);
+    DOLO_LAUNCH_OK("gelu_fwd");
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_gelu_bwd(const void* dy, const void* x, void* dx, float* dbias_accum, int64_t T, int64_t F,
+                                      void* stream) {
+    DOLO_REQUIRE(F > 0 && F % 8 == 0, "gelu_bwd: F=%lld must be a positive multiple of 8", (long long)F);
+    DOLO_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dx), "gelu_bwd: pointers must be 16-byte aligned");
+    if (T == 0) return DOLO_OK;
+    const int64_t F8 = F / 8;
+    const int col_tiles = int((F8 + 31) / 32);
+    int row_splits = (dolo_num_sms() * 8 + col_tiles - 1) / col_tiles;
+    if (row_splits > (T + 7) / 8) row_splits = int((T + 7) / 8);
+    if (row_splits < 1) row_splits = 1;
+    if (row_splits > 65535) row_splits = 65535;
+    const int rows_per_block = int((T + row_splits - 1) / row_splits);
+    dim3 grid(col_tiles, (unsigned)((T + rows_per_block - 1) / rows_per_block));
+    gelu_bwd_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(dy), static_cast<const uint4*>(x), static_cast<uint4*>(dx), dbias_accum, T, F8,
+        rows_per_block);
+    DOLO_LAUNCH_OK("gelu_bwd");
     return DOLO_OK;
 }
 

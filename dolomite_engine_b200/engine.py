@@ -142,6 +142,9 @@ def _block_specs(cfg: CommonConfig, i: int) -> list[tuple[str, tuple, str]]:
         specs.append((p + "mlp.c_proj.weight", (H, F), f"normal:{std_proj}"))
         if cfg.add_bias:
             specs.append((p + "mlp.c_proj.bias", (H,), "zeros"))
+    if cfg.normalization_function == "layernorm":  # torch.nn.LayerNorm always carries a bias
+        specs.append((p + "ln_1.bias", (H,), "zeros"))
+        specs.append((p + "ln_2.bias", (H,), "zeros"))
     return specs
 
 
@@ -154,23 +157,34 @@ def _root_specs(cfg: CommonConfig) -> list[tuple[str, tuple, str]]:
         if cfg.init_method == "mup":
             std /= math.sqrt(cfg.m_width)
         specs.append(("lm_head.weight", (V, H), f"normal:{std}"))
+    # appended last: the random stream (and flat layout) of every rope / rmsnorm configuration stays what it was
+    if cfg.normalization_function == "layernorm":
+        specs.append(("transformer.ln_f.bias", (H,), "zeros"))
+    if cfg.position_embedding_type == "learned_absolute":  # ParameterizedEmbedding(n_positions, n_embd), base.py:127-134
+        specs.append(("transformer.wpe.weight", (cfg.n_positions, H), f"normal:{cfg.initializer_range}"))
     return specs
 
 
 def check_supported(cfg: CommonConfig) -> None:
     """The B200 hot path implements the configurations SURVEY.md section 8 puts in scope; everything else raises
     (mirrors the reference's NotImplementedError / ValueError conventions)."""
-    if cfg.position_embedding_type not in ("rope", "nope"):
+    if cfg.position_embedding_type not in ("rope", "nope", "learned_absolute"):
         raise NotImplementedError(
-            f"position_embedding_type={cfg.position_embedding_type!r}: the B200 path implements rope and nope "
-            "(alibi is unsupported with flash attention in the reference too, gpt_dolomite/base.py:530)"
+            f"position_embedding_type={cfg.position_embedding_type!r}: the B200 path implements rope, nope and "
+            "learned_absolute (alibi is unsupported with flash attention in the reference too, gpt_dolomite/base.py:530)"
         )
+    if cfg.position_embedding_type == "learned_absolute" and cfg.m_emb is not None:
+        raise NotImplementedError("learned_absolute positions combined with m_emb are not implemented")
     if cfg.rope_scaling is not None:
         raise NotImplementedError("YaRN rope_scaling is out of scope of the B200 hot path (SURVEY.md section 2 #5)")
-    if cfg.normalization_function != "rmsnorm":
-        raise NotImplementedError(f"normalization_function={cfg.normalization_function!r}: only rmsnorm is on the hot path")
-    if cfg.activation_function != "swiglu":
-        raise NotImplementedError(f"activation_function={cfg.activation_function!r}: only swiglu is implemented in CUDA")
+    if cfg.normalization_function not in ("rmsnorm", "layernorm"):
+        raise NotImplementedError(
+            f"normalization_function={cfg.normalization_function!r}: rmsnorm and layernorm are implemented in CUDA")
+    if cfg.activation_function not in ("swiglu", "gelu_pytorch_tanh"):
+        raise NotImplementedError(
+            f"activation_function={cfg.activation_function!r}: swiglu and gelu_pytorch_tanh are implemented in CUDA")
+    if cfg.model_type == "moe_dolomite" and (cfg.activation_function != "swiglu" or cfg.normalization_function != "rmsnorm"):
+        raise NotImplementedError("MoE blocks are implemented for swiglu + rmsnorm (the MoEDolomite / Granite-MoE shape)")
     if cfg.resid_pdrop != 0 or cfg.embd_pdrop != 0 or cfg.attn_pdrop != 0:
         raise NotImplementedError("dropout > 0 is not implemented on the B200 path (target configs use p=0: nn.Identity)")
     hd = cfg.n_embd // cfg.n_head
@@ -201,6 +215,9 @@ class DolomiteEngine:
         self.q_per_group = cfg.n_head // cfg.num_key_value_heads
         self.qkv_dim = cfg.n_embd + 2 * cfg.num_key_value_heads * self.hd
         self.is_moe = cfg.model_type == "moe_dolomite"
+        self.is_glu = cfg.activation_function.endswith("glu")
+        self.is_layernorm = cfg.normalization_function == "layernorm"
+        self.learned_positions = cfg.position_embedding_type == "learned_absolute"
         self.units: list[FlatUnit] = [FlatUnit("root", _root_specs(cfg), world_size, rank)]
         for i in range(cfg.n_layer):
             self.units.append(FlatUnit(f"h.{i}", _block_specs(cfg, i), world_size, rank))
@@ -258,7 +275,9 @@ class DolomiteEngine:
         for u in self.units:
             if lazy:
                 for s in u.specs:
-                    untied_wte = s.name == "transformer.wte.weight" and not self.cfg.tie_word_embeddings
+                    # embedding tables that only ever receive scattered atomics must start from zero
+                    untied_wte = (s.name == "transformer.wte.weight" and not self.cfg.tie_word_embeddings) or \
+                        s.name == "transformer.wpe.weight"
                     if s.numel >= self._LAZY_ZERO_MIN_NUMEL and s.name.endswith(".weight") and not untied_wte:
                         self._fresh_grads.add(s.name)
                     else:
@@ -275,6 +294,21 @@ class DolomiteEngine:
     def _w(self, unit: FlatUnit, name: str):
         return unit.views.get(name)
 
+    def _norm_fwd(self, x, unit: FlatUnit, prefix: str):
+        """RMSNorm or LayerNorm (get_normalization_function, normalization/__init__.py:13-30) -> (y, saved statistics)"""
+        eps = self.cfg.layer_norm_epsilon
+        if self.is_layernorm:
+            y, mean, rstd = K.layernorm_fwd(x, unit.views[prefix + "weight"], unit.views.get(prefix + "bias"), eps)
+            return y, (mean, rstd)
+        return K.rmsnorm_fwd(x, unit.views[prefix + "weight"], eps)
+
+    def _norm_bwd(self, dy, x, unit: FlatUnit, prefix: str, stats, dx_add=None):
+        if self.is_layernorm:
+            mean, rstd = stats
+            return K.layernorm_bwd(dy, x, unit.views[prefix + "weight"], mean, rstd, unit.gviews[prefix + "weight"],
+                                   unit.gviews.get(prefix + "bias"), dx_add=dx_add)
+        return K.rmsnorm_bwd(dy, x, unit.views[prefix + "weight"], stats, unit.gviews[prefix + "weight"], dx_add=dx_add)
+
     def _is_checkpointed(self, i: int) -> bool:
         k = self.checkpoint_every
         return k is not None and k > 0 and i % k == 0
@@ -285,21 +319,21 @@ class DolomiteEngine:
         u = self.units[i + 1]
         p = f"transformer.h.{i}."
         m_res = 1.0 if cfg.m_residual is None else float(cfg.m_residual)
-        ln1, rstd1 = K.rmsnorm_fwd(x_in, u.views[p + "ln_1.weight"], cfg.layer_norm_epsilon)
+        ln1, rstd1 = self._norm_fwd(x_in, u, p + "ln_1.")
         qkv = K.gemm(ln1, u.views[p + "attn.c_attn.weight"], bias=u.views.get(p + "attn.c_attn.bias"))
         if self.rope_cos is not None:
             K.rope_qk_inplace(qkv, self.n_groups, self.q_per_group, self.hd, self.rope_cos, self.rope_sin, position_ids)
         attn, lse = K.attn_varlen_fwd(qkv, cu_seqlens, max_seqlen, self.n_groups, self.q_per_group, self.hd, self.softmax_scale)
         h_mid = K.gemm(attn, u.views[p + "attn.c_proj.weight"], bias=u.views.get(p + "attn.c_proj.bias"), c=x_in,
                        alpha=m_res, beta=1.0)
-        ln2, rstd2 = K.rmsnorm_fwd(h_mid, u.views[p + "ln_2.weight"], cfg.layer_norm_epsilon)
+        ln2, rstd2 = self._norm_fwd(h_mid, u, p + "ln_2.")
         if self.is_moe:
             from . import moe
 
             h, moe_saved = moe.forward(self, u, p, ln2, h_mid, m_res)
             return h, (x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, moe_saved)
         fc = K.gemm(ln2, u.views[p + "mlp.c_fc.weight"], bias=u.views.get(p + "mlp.c_fc.bias"))
-        act = K.swiglu_fwd(fc)
+        act = K.swiglu_fwd(fc) if self.is_glu else K.gelu_fwd(fc)
         h = K.gemm(act, u.views[p + "mlp.c_proj.weight"], bias=u.views.get(p + "mlp.c_proj.bias"), c=h_mid,
                    alpha=m_res, beta=1.0)
         return h, (x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, fc, act)
@@ -314,6 +348,8 @@ class DolomiteEngine:
         if comm is not None:
             comm.pre_forward_unit(0)
         h = K.embedding_fwd(input_ids, root.views["transformer.wte.weight"], 1.0 if cfg.m_emb is None else float(cfg.m_emb))
+        if self.learned_positions:  # gpt_dolomite/base.py:351-372: wte(ids) + wpe(position_ids), one bf16 rounding
+            h = K.add_scaled(h, K.embedding_fwd(position_ids, root.views["transformer.wpe.weight"], 1.0), 1.0)
         saved_layers = []
         for i in range(cfg.n_layer):
             if comm is not None:
@@ -327,7 +363,7 @@ class DolomiteEngine:
             del layer
             if comm is not None:
                 comm.post_forward_unit(i + 1)
-        hf, rstd_f = K.rmsnorm_fwd(h, root.views["transformer.ln_f.weight"], cfg.layer_norm_epsilon)
+        hf, rstd_f = self._norm_fwd(h, root, "transformer.ln_f.")
         head = root.views["transformer.wte.weight"] if cfg.tie_word_embeddings else root.views["lm_head.weight"]
         inv_width = 1.0 if cfg.m_width is None else 1.0 / float(cfg.m_width)
         logits = K.gemm(hf, head, alpha=inv_width)
@@ -380,8 +416,7 @@ class DolomiteEngine:
         if comm is not None:
             comm.pre_backward_unit(0)
         d_hf = self._linear_bwd(root, head_name, None, s["hf"], dl, alpha=inv_width)
-        dh = K.rmsnorm_bwd(d_hf, s["h_last"], root.views["transformer.ln_f.weight"], s["rstd_f"],
-                           root.gviews["transformer.ln_f.weight"])
+        dh = self._norm_bwd(d_hf, s["h_last"], root, "transformer.ln_f.", s["rstd_f"])
         del d_hf
         for i in reversed(range(cfg.n_layer)):
             u = self.units[i + 1]
@@ -400,11 +435,12 @@ class DolomiteEngine:
                 x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, fc, act = layer
                 d_act = self._linear_bwd(u, p + "mlp.c_proj.weight", p + "mlp.c_proj.bias", act, dh, alpha=m_res)
                 # the c_fc bias gradient (column sums of d_fc) is accumulated by the SwiGLU backward while it writes d_fc
-                d_fc = K.swiglu_bwd(d_act, fc, bias_grad_accum=u.gviews.get(p + "mlp.c_fc.bias"))
+                act_bwd = K.swiglu_bwd if self.is_glu else K.gelu_bwd
+                d_fc = act_bwd(d_act, fc, bias_grad_accum=u.gviews.get(p + "mlp.c_fc.bias"))
                 del d_act
                 d_ln2 = self._linear_bwd(u, p + "mlp.c_fc.weight", None, ln2, d_fc)
                 del d_fc
-            dh_mid = K.rmsnorm_bwd(d_ln2, h_mid, u.views[p + "ln_2.weight"], rstd2, u.gviews[p + "ln_2.weight"], dx_add=dh)
+            dh_mid = self._norm_bwd(d_ln2, h_mid, u, p + "ln_2.", rstd2, dx_add=dh)
             del d_ln2
             d_attn = self._linear_bwd(u, p + "attn.c_proj.weight", p + "attn.c_proj.bias", attn, dh_mid, alpha=m_res)
             dqkv = K.attn_varlen_bwd(d_attn, qkv, attn, lse, s["cu_seqlens"], s["max_seqlen"], self.n_groups,
@@ -415,12 +451,14 @@ class DolomiteEngine:
                                   s["position_ids"], inverse=True)
             d_ln1 = self._linear_bwd(u, p + "attn.c_attn.weight", p + "attn.c_attn.bias", ln1, dqkv)
             del dqkv
-            dh = K.rmsnorm_bwd(d_ln1, x_in, u.views[p + "ln_1.weight"], rstd1, u.gviews[p + "ln_1.weight"], dx_add=dh_mid)
+            dh = self._norm_bwd(d_ln1, x_in, u, p + "ln_1.", rstd1, dx_add=dh_mid)
             del d_ln1, dh_mid
             s["layers"][i] = None  # free this layer's activations
             if comm is not None:
                 comm.post_backward_unit(i + 1)
         K.embedding_bwd(s["input_ids"], dh, root.gviews["transformer.wte.weight"], 1.0 if cfg.m_emb is None else float(cfg.m_emb))
+        if self.learned_positions:
+            K.embedding_bwd(s["position_ids"], dh, root.gviews["transformer.wpe.weight"], 1.0)
         if self._fresh_grads:  # a weight that received no gradient in this backward still has to read as zero
             for name, unit, _ in self.named_views():
                 if name in self._fresh_grads:

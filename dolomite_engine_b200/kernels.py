@@ -91,6 +91,43 @@ def rope_qk_inplace(qkv, n_groups: int, q_per_group: int, head_dim: int, cos, si
 # ------------------------------------------------------------------------------------------------
 # SwiGLU (activations/glu.py:26-28)
 # ------------------------------------------------------------------------------------------------
+def layernorm_fwd(x, w, b, eps: float, out=None):
+    """y = bf16((x - mean) * rstd * w + b) -> (y, mean, rstd)"""
+    _req(x, _BF16, "x"), _req(w, _BF16, "w")
+    T, H = x.shape
+    y = torch.empty_like(x) if out is None else out
+    mean = torch.empty(T, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(T, dtype=torch.float32, device=x.device)
+    _lib.call("dolomite_b200_layernorm_fwd", x.data_ptr(), w.data_ptr(), _ptr(b), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+              T, H, eps, _stream())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, w, mean, rstd, dw_accum, db_accum, dx_add=None, out=None):
+    _req(dy, _BF16, "dy"), _req(x, _BF16, "x")
+    T, H = x.shape
+    dx = torch.empty_like(x) if out is None else out
+    ws = _workspace(_lib.load().dolomite_b200_layernorm_bwd_workspace_bytes(H), x.device)
+    _lib.call("dolomite_b200_layernorm_bwd", dy.data_ptr(), x.data_ptr(), w.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+              _ptr(dx_add), dx.data_ptr(), _ptr(dw_accum), _ptr(db_accum), ws.data_ptr(), T, H, _stream())
+    return dx
+
+
+def gelu_fwd(x, out=None):
+    _req(x, _BF16, "x")
+    y = torch.empty_like(x) if out is None else out
+    _lib.call("dolomite_b200_gelu_fwd", x.data_ptr(), y.data_ptr(), x.numel(), _stream())
+    return y
+
+
+def gelu_bwd(dy, x, out=None, bias_grad_accum=None):
+    _req(dy, _BF16, "dy"), _req(x, _BF16, "x")
+    T, F = x.shape
+    dx = torch.empty_like(x) if out is None else out
+    _lib.call("dolomite_b200_gelu_bwd", dy.data_ptr(), x.data_ptr(), dx.data_ptr(), _ptr(bias_grad_accum), T, F, _stream())
+    return dx
+
+
 def swiglu_fwd(x, out=None):
     _req(x, _BF16, "x")
     T, F2 = x.shape

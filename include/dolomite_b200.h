@@ -68,6 +68,28 @@ int dolomite_b200_rope_qk_inplace(void* qkv, int64_t row_stride, int64_t T, int 
                                   int position_ids_is_int64, int64_t n_positions, int inverse, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * LayerNorm -- normalization_function "layernorm" = torch.nn.LayerNorm
+ * (hf_models/modeling_utils/normalization/layernorm/__init__.py): fp32 statistics, one rounding to bf16:
+ *   y = bf16((x - mean) * rstd * w + b);  b may be null.  mean / rstd (fp32 [T]) are saved for backward.
+ * bwd: dx = rstd * (g*w - mean(g*w) - xhat * mean(g*w*xhat)) [+ dx_add];  dw_accum += sum g*xhat;  db_accum += sum g.
+ * workspace: dolomite_b200_layernorm_bwd_workspace_bytes(H) bytes, 16-byte aligned.
+ * ------------------------------------------------------------------------------------------------ */
+int dolomite_b200_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t T,
+                                int H, float eps, void* stream);
+int64_t dolomite_b200_layernorm_bwd_workspace_bytes(int H);
+int dolomite_b200_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
+                                const void* dx_add, void* dx, float* dw_accum, float* db_accum, void* workspace, int64_t T,
+                                int H, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * tanh-GELU -- activation_function "gelu_pytorch_tanh" (hf_models/modeling_utils/activations/base.py), the non-GLU MLP
+ * of gpt_dolomite/mlp.py:45-50.  bwd: dx = dy * gelu'(x); dbias_accum (fp32 [F], may be null) += column sums of the
+ * bf16 dx (bias gradient of c_fc).
+ * ------------------------------------------------------------------------------------------------ */
+int dolomite_b200_gelu_fwd(const void* x, void* y, int64_t n, void* stream);
+int dolomite_b200_gelu_bwd(const void* dy, const void* x, void* dx, float* dbias_accum, int64_t T, int64_t F, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * SwiGLU -- hf_models/modeling_utils/activations/glu.py:26-28 with gpt_dolomite/mlp.py:54-55 ordering:
  *   x = [up | gate] (first F columns up, last F gate);  y = up * silu(gate).
  * ------------------------------------------------------------------------------------------------ */

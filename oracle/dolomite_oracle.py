@@ -173,6 +173,20 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, bf16: bool = False) ->
     return _r(w * _r(xn, bf16), bf16)
 
 
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None, eps: float, bf16: bool = False) -> torch.Tensor:
+    """normalization/layernorm/__init__.py: torch.nn.LayerNorm -- fp32 statistics, a single rounding at the output"""
+    return _r(F.layer_norm(x.float(), (x.shape[-1],), w.float(), None if b is None else b.float(), eps), bf16)
+
+
+def norm(x: torch.Tensor, p: dict, prefix: str, cfg: "OracleConfig", bf16: bool = False) -> torch.Tensor:
+    """get_normalization_function (normalization/__init__.py:13-30): rmsnorm | layernorm"""
+    if cfg.normalization_function == "rmsnorm":
+        return rmsnorm(x, p[prefix + "weight"], cfg.layer_norm_epsilon, bf16)
+    if cfg.normalization_function == "layernorm":
+        return layernorm(x, p[prefix + "weight"], p.get(prefix + "bias"), cfg.layer_norm_epsilon, bf16)
+    raise ValueError(f"oracle: unsupported normalization {cfg.normalization_function}")
+
+
 def rope_tables(head_dim: int, n_positions: int, base: float, bf16: bool = False):
     """position_embedding/rope.py:25-55"""
     inv_freq = 1.0 / (base ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
@@ -306,7 +320,7 @@ def block(h, p: dict, i: int, cfg: OracleConfig, cos, sin, cu_seqlens, bf16: boo
     (attention/padding_free.py:15-77); MoE block: moe_dolomite/layer.py:51-95."""
     pre = f"transformer.h.{i}."
     res = h
-    x = rmsnorm(h, p[pre + "ln_1.weight"], cfg.layer_norm_epsilon, bf16)
+    x = norm(h, p, pre + "ln_1.", cfg, bf16)
     qkv = linear(x, p[pre + "attn.c_attn.weight"], p.get(pre + "attn.c_attn.bias"), bf16)
     q, k, v = split_qkv_activations(qkv, cfg)
     if cfg.position_embedding_type == "rope":
@@ -318,7 +332,7 @@ def block(h, p: dict, i: int, cfg: OracleConfig, cos, sin, cu_seqlens, bf16: boo
         a = _r(a * cfg.m_residual, bf16)
     h = _r(a + res, bf16)
     res = h
-    x = rmsnorm(h, p[pre + "ln_2.weight"], cfg.layer_norm_epsilon, bf16)
+    x = norm(h, p, pre + "ln_2.", cfg, bf16)
     if cfg.num_experts > 0:
         m, _ = sparse_moe(x, p, pre + "mlp.", cfg, bf16)
     else:
@@ -337,6 +351,8 @@ def forward_logits(p: dict, cfg: OracleConfig, input_ids, position_ids, cu_seqle
     ids = torch.as_tensor(np.asarray(input_ids), dtype=torch.long)
     pos = torch.as_tensor(np.asarray(position_ids), dtype=torch.long)
     h = p["transformer.wte.weight"][ids]
+    if cfg.position_embedding_type == "learned_absolute":  # gpt_dolomite/base.py:351-372: wte(ids) + wpe(position_ids)
+        h = _r(h + p["transformer.wpe.weight"][pos], bf16)
     if cfg.m_emb is not None:
         h = _r(h * cfg.m_emb, bf16)
     cos = sin = None
@@ -347,7 +363,7 @@ def forward_logits(p: dict, cfg: OracleConfig, input_ids, position_ids, cu_seqle
     for i in range(cfg.n_layer):
         h = block(h, p, i, cfg, cos, sin, cu_seqlens, bf16)
         hidden.append(h)
-    h = rmsnorm(h, p["transformer.ln_f.weight"], cfg.layer_norm_epsilon, bf16)
+    h = norm(h, p, "transformer.ln_f.", cfg, bf16)
     head = p["transformer.wte.weight"] if cfg.tie_word_embeddings else p["lm_head.weight"]
     logits = linear(h, head, None, bf16)
     if cfg.m_width is not None:
@@ -418,6 +434,14 @@ def init_params(cfg: OracleConfig, seed: int = 42) -> dict:
     p["transformer.ln_f.weight"] = torch.ones(H)
     if not cfg.tie_word_embeddings:
         p["lm_head.weight"] = n(V, H, sd=std)
+    # drawn last so that the random stream of every earlier configuration is unchanged
+    if cfg.position_embedding_type == "learned_absolute":
+        p["transformer.wpe.weight"] = n(cfg.n_positions, H, sd=cfg.initializer_range)
+    if cfg.normalization_function == "layernorm":  # nn.LayerNorm always carries a bias (zeros at init)
+        for i in range(L):
+            p[f"transformer.h.{i}.ln_1.bias"] = torch.zeros(H)
+            p[f"transformer.h.{i}.ln_2.bias"] = torch.zeros(H)
+        p["transformer.ln_f.bias"] = torch.zeros(H)
     return p
 
 

@@ -47,12 +47,13 @@ def import_reference():
     sys.path.insert(0, REF)
     import dolomite_engine.hf_models  # noqa: F401
     from dolomite_engine.hf_models.modeling_utils import RMSNorm, RoPE, apply_rotary_pos_emb  # noqa: F401
+    from dolomite_engine.hf_models.modeling_utils import get_normalization_function
     from dolomite_engine.hf_models.models.gpt_dolomite.layer import GPTDolomiteBlock
     from dolomite_engine.hf_models.models.moe_dolomite.moe.base import SparseMoE
 
     return types.SimpleNamespace(
         GPTDolomiteBlock=GPTDolomiteBlock, RMSNorm=RMSNorm, RoPE=RoPE, apply_rotary_pos_emb=apply_rotary_pos_emb,
-        SparseMoE=SparseMoE,
+        SparseMoE=SparseMoE, get_normalization_function=get_normalization_function,
     )
 
 
@@ -82,10 +83,12 @@ def reference_forward(R, cfg, params, input_ids, position_ids, cu_seqlens):
         sd = {k[len(f"transformer.h.{i}."):]: v for k, v in params.items() if k.startswith(f"transformer.h.{i}.")}
         b.load_state_dict(sd)
         blocks.append(b)
-    ln_f = R.RMSNorm(cfg.n_embd, eps=cfg.layer_norm_epsilon)
-    ln_f.load_state_dict({"weight": params["transformer.ln_f.weight"]})
+    ln_f = R.get_normalization_function(cfg.normalization_function, cfg.n_embd, eps=cfg.layer_norm_epsilon)  # base.py:57-61
+    ln_f.load_state_dict({k[len("transformer.ln_f."):]: v for k, v in params.items() if k.startswith("transformer.ln_f.")})
     rope = R.RoPE(cfg.head_dim, max_position_embeddings=cfg.n_positions, base=cfg.rope_theta)
     wte = params["transformer.wte.weight"].clone().requires_grad_(True)
+    learned = cfg.position_embedding_type == "learned_absolute"
+    wpe = params["transformer.wpe.weight"].clone().requires_grad_(True) if learned else None
     ids = torch.as_tensor(input_ids, dtype=torch.long)
     pos = torch.as_tensor(position_ids, dtype=torch.long)
     outs = []
@@ -94,11 +97,15 @@ def reference_forward(R, cfg, params, input_ids, position_ids, cu_seqlens):
         if e == s:
             continue
         h = torch.nn.functional.embedding(ids[s:e], wte).unsqueeze(0)
+        if learned:  # base.py:351-372: inputs_embeds + wpe(position_ids)
+            h = h + torch.nn.functional.embedding(pos[s:e], wpe).unsqueeze(0)
         if cfg.m_emb is not None:
             h = h * cfg.m_emb
         n = e - s
-        cos, sin = rope(cfg.n_positions, dtype=torch.float32, device=None)
-        cs = (cos[pos[s:e]].unsqueeze(0).unsqueeze(1), sin[pos[s:e]].unsqueeze(0).unsqueeze(1))  # base.py:289-296
+        cs = None
+        if cfg.position_embedding_type == "rope":
+            cos, sin = rope(cfg.n_positions, dtype=torch.float32, device=None)
+            cs = (cos[pos[s:e]].unsqueeze(0).unsqueeze(1), sin[pos[s:e]].unsqueeze(0).unsqueeze(1))  # base.py:289-296
         causal = torch.ones(n, n, dtype=torch.bool).tril()[None, None]
         mask = torch.where(causal, torch.tensor(0.0), torch.tensor(torch.finfo(torch.float32).min))  # base.py:587-596
         for b in blocks:
@@ -109,7 +116,8 @@ def reference_forward(R, cfg, params, input_ids, position_ids, cu_seqlens):
     logits = torch.nn.functional.linear(h, head)
     if cfg.m_width is not None:
         logits = logits / cfg.m_width
-    return logits, blocks, wte
+    ln_f_grads = lambda: {"transformer.ln_f." + k: v.grad for k, v in ln_f.named_parameters()}  # noqa: E731
+    return logits, blocks, wte, wpe, ln_f_grads
 
 
 def close(a, b, atol, what):
@@ -131,6 +139,10 @@ CONFIGS = {
                          m_residual=0.22, attention_multiplier=0.015625, tie_word_embeddings=False),
     "mqa_gelu": dict(vocab_size=512, n_positions=256, n_embd=128, n_layer=1, n_head=4, n_inner=512,
                      attention_head_type="mqa", activation_function="gelu_pytorch_tanh", add_bias=True),
+    # the StarCoder / bigcode shape of configs/pretraining-examples (dropout 0): LayerNorm + tanh-GELU + learned positions + MQA
+    "bigcode": dict(vocab_size=512, n_positions=256, n_embd=128, n_layer=2, n_head=8, n_inner=512,
+                    attention_head_type="mqa", activation_function="gelu_pytorch_tanh", add_bias=True,
+                    normalization_function="layernorm", position_embedding_type="learned_absolute"),
 }
 
 
@@ -181,7 +193,8 @@ def main():
         for mode, (ram, rpi) in {"uniform": (False, False), "ragged": (True, True)}.items():
             inp, labels = O.split_tokens(tokens)
             b = O.prepare_model_inputs(inp.copy(), eos, ram, rpi)
-            logits_ref, blocks, wte = reference_forward(R, cfg, params, b["input_ids"], b["position_ids"], b["cu_seqlens"])
+            logits_ref, blocks, wte, wpe, ln_f_grads = reference_forward(R, cfg, params, b["input_ids"], b["position_ids"],
+                                                                         b["cu_seqlens"])
             lab = torch.as_tensor(np.ascontiguousarray(labels).reshape(-1))
             loss_ref = torch.nn.functional.cross_entropy(logits_ref, lab)  # model_wrapper/pretraining.py:124-125
             loss_ref.backward()
@@ -192,6 +205,9 @@ def main():
             close(loss_o.detach(), loss_ref.detach(), 1e-6, f"{mode}: loss")
             g_ref = {f"transformer.h.{i}.{k}": v.grad for i, blk in enumerate(blocks) for k, v in blk.named_parameters()}
             g_ref["transformer.wte.weight"] = wte.grad
+            g_ref.update(ln_f_grads())
+            if wpe is not None:
+                g_ref["transformer.wpe.weight"] = wpe.grad
             for k, gr in g_ref.items():
                 if k == "transformer.wte.weight" and not cfg.tie_word_embeddings:
                     pass

@@ -263,3 +263,48 @@ def test_optimizer_kernels_vs_torch():
         K().adamw_step(p, grad.cuda(), m, v, pb, 1e-3, 0.9, 0.95, 1e-10, 0.1, step, clip=coef)
     assert torch.allclose(p.cpu(), pr.data, atol=1e-6, rtol=1e-5)
     assert torch.equal(pb.cpu(), bf(p.cpu()))
+
+
+@pytest.mark.parametrize("T,H,bias", [(1, 64, True), (37, 256, True), (200, 2560, False), (5, 8192, True)])
+def test_layernorm_fwd_bwd(T, H, bias):
+    """normalization_function layernorm = torch.nn.LayerNorm: fp32 statistics, one bf16 rounding (oracle.layernorm)"""
+    g = torch.Generator().manual_seed(0)
+    x = bf(torch.randn(T, H, generator=g) + 0.5)
+    w = bf(1 + 0.1 * torch.randn(H, generator=g))
+    b = bf(0.1 * torch.randn(H, generator=g)) if bias else None
+    dy = bf(torch.randn(T, H, generator=g))
+    dres = bf(torch.randn(T, H, generator=g))
+    y, mean, rstd = K().layernorm_fwd(x.cuda(), w.cuda(), None if b is None else b.cuda(), 1e-5)
+    ref = O.layernorm(x.float(), w.float(), None if b is None else b.float(), 1e-5, bf16=True)
+    assert (y.float().cpu() - ref).abs().max() <= 2 * BF16_EPS * max(ref.abs().max().item(), 1.0)
+    assert torch.allclose(mean.cpu(), x.float().mean(-1), atol=1e-5)
+    xf = x.float().requires_grad_(True)
+    wf = w.float().requires_grad_(True)
+    bfp = b.float().requires_grad_(True) if bias else None
+    O.layernorm(xf, wf, bfp, 1e-5).backward(dy.float())
+    dw = torch.zeros(H, device="cuda")
+    db = torch.zeros(H, device="cuda") if bias else None
+    dx = K().layernorm_bwd(dy.cuda(), x.cuda(), w.cuda(), mean, rstd, dw, db, dx_add=dres.cuda())
+    assert rel_l2(dx, xf.grad + dres.float()) < 5e-3 and rel_l2(dw, wf.grad) < 5e-3
+    if bias:
+        assert rel_l2(db, bfp.grad) < 1e-4
+
+
+def test_gelu_tanh_fwd_bwd_and_fused_bias_gradient():
+    """activation_function gelu_pytorch_tanh (non-GLU MLP, gpt_dolomite/mlp.py:45-50)"""
+    g = torch.Generator().manual_seed(2)
+    for T, F in [(77, 256), (1000, 328), (8, 8)]:
+        x = bf(torch.randn(T, F, generator=g) * 2)
+        dy = bf(torch.randn(T, F, generator=g))
+        y = K().gelu_fwd(x.cuda())
+        ref = O.activation(x.float(), "gelu_pytorch_tanh", bf16=True)
+        assert (y.float().cpu() - ref).abs().max() <= 2 * BF16_EPS * max(ref.abs().max().item(), 1.0)
+        xf = x.float().requires_grad_(True)
+        O.activation(xf, "gelu_pytorch_tanh").backward(dy.float())
+        plain = K().gelu_bwd(dy.cuda(), x.cuda())
+        assert rel_l2(plain, xf.grad) < 5e-3
+        db = torch.full((F,), 0.25, device="cuda")
+        fused = K().gelu_bwd(dy.cuda(), x.cuda(), bias_grad_accum=db)
+        assert torch.equal(fused, plain)
+        want = 0.25 + plain.float().sum(0)
+        assert torch.allclose(db, want, rtol=1e-5, atol=1e-4)

@@ -15,7 +15,7 @@ from oracle.validate_against_reference import CONFIGS
 
 pytestmark = pytest.mark.gpu
 
-GPU_CONFIGS = {k: v for k, v in CONFIGS.items() if v.get("activation_function", "swiglu") == "swiglu"}
+GPU_CONFIGS = dict(CONFIGS)  # incl. mqa_gelu (tanh-GELU, non-GLU MLP) and bigcode (LayerNorm + learned positions + MQA)
 GPU_CONFIGS["hd80_bias"] = dict(vocab_size=1024, n_positions=512, n_embd=320, n_layer=2, n_head=4, n_inner=640,
                                 attention_head_type="mha", add_bias=True)
 GPU_CONFIGS["hd128_gqa"] = dict(vocab_size=1024, n_positions=512, n_embd=512, n_layer=1, n_head=4, num_key_value_heads=2,
@@ -134,7 +134,7 @@ def test_pretraining_wrapper_loss_matches_golden_c1(golden_dir, mode):
     assert rel_l2(g_wte[rows.cuda()], torch.from_numpy(fx[f"{mode}_grad_wte_rows"])) < 2e-2
 
 
-@pytest.mark.parametrize("name", ["gqa_bias_mup", "hd80_bias"])
+@pytest.mark.parametrize("name", ["gqa_bias_mup", "hd80_bias", "mqa_gelu", "bigcode"])
 def test_all_gradients_match_oracle(name):
     model, ocfg, params = build_model(name)
     model.assume_unit_loss_grad = True

@@ -42,12 +42,18 @@ def test_unsupported_configs_fail_loudly():
                            activation_function="swiglu", normalization_function="rmsnorm", resid_pdrop=0, embd_pdrop=0,
                            attn_pdrop=0, vocab_size=2048)
     check_supported(ok)
-    for kw in (dict(position_embedding_type="alibi"), dict(normalization_function="layernorm"),
-               dict(activation_function="gelu_pytorch_tanh"), dict(attn_pdrop=0.1), dict(n_head=32, num_key_value_heads=32)):
+    for kw in (dict(position_embedding_type="alibi"), dict(normalization_function="apex_layernorm"),
+               dict(activation_function="geglu"), dict(attn_pdrop=0.1), dict(n_head=32, num_key_value_heads=32),
+               dict(position_embedding_type="learned_absolute", m_emb=12.0), dict(rope_scaling={"type": "yarn", "factor": 4})):
         d = ok.to_dict()
         d.update(kw)
         with pytest.raises(NotImplementedError):
             check_supported(GPTDolomiteConfig.from_dict(d))
+    # the StarCoder / bigcode shape of the reference's example YAMLs (configs/pretraining-examples/*.yml, dropout 0)
+    d = ok.to_dict()
+    d.update(position_embedding_type="learned_absolute", normalization_function="layernorm",
+             activation_function="gelu_pytorch_tanh", attention_head_type="mqa", num_key_value_heads=1, add_bias=True)
+    check_supported(GPTDolomiteConfig.from_dict(d))
 
 
 @pytest.mark.parametrize("ram,rpi", [(False, False), (True, False), (True, True)])
@@ -80,7 +86,8 @@ def test_bookkeeping_edge_cases():
 
 def test_flat_unit_layout_and_sharding():
     cfg = GPTDolomiteConfig(n_embd=64, n_head=4, n_layer=2, n_inner=128, vocab_size=256, attention_head_type="gqa",
-                            num_key_value_heads=2, add_bias=True, activation_function="swiglu")
+                            num_key_value_heads=2, add_bias=True, activation_function="swiglu",
+                            normalization_function="rmsnorm", position_embedding_type="rope")
     specs = _block_specs(cfg, 0)
     names = [s[0] for s in specs]
     assert names[0] == "transformer.h.0.ln_1.weight" and "transformer.h.0.mlp.c_fc.bias" in names
@@ -96,6 +103,14 @@ def test_flat_unit_layout_and_sharding():
     assert [s[0] for s in _root_specs(cfg)] == ["transformer.wte.weight", "transformer.ln_f.weight"]
     cfg.tie_word_embeddings = False
     assert _root_specs(cfg)[-1][0] == "lm_head.weight"
+    # config defaults = the GPT-2 / bigcode shape: LayerNorm biases and the learned position table join the units (appended,
+    # so the layout of the rope / rmsnorm configurations above is a prefix of it)
+    big = GPTDolomiteConfig(n_embd=64, n_head=4, n_layer=2, vocab_size=256, n_positions=128, add_bias=True)
+    assert [s[0] for s in _root_specs(big)] == ["transformer.wte.weight", "transformer.ln_f.weight", "transformer.ln_f.bias",
+                                                "transformer.wpe.weight"]
+    bnames = [s[0] for s in _block_specs(big, 1)]
+    assert bnames[-2:] == ["transformer.h.1.ln_1.bias", "transformer.h.1.ln_2.bias"]
+    assert dict((s[0], s[1]) for s in _block_specs(big, 1))["transformer.h.1.mlp.c_fc.weight"] == (256, 64)  # F, not 2F
 
 
 def test_yaml_argument_tree():
