@@ -349,6 +349,8 @@ class DolomiteEngine:
             comm.pre_forward_unit(0)
         h = K.embedding_fwd(input_ids, root.views["transformer.wte.weight"], 1.0 if cfg.m_emb is None else float(cfg.m_emb))
         if self.learned_positions:  # gpt_dolomite/base.py:351-372: wte(ids) + wpe(position_ids), one bf16 rounding
+            if position_ids.dtype != torch.int64:
+                position_ids = position_ids.long()
             h = K.add_scaled(h, K.embedding_fwd(position_ids, root.views["transformer.wpe.weight"], 1.0), 1.0)
         saved_layers = []
         for i in range(cfg.n_layer):

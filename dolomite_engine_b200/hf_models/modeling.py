@@ -87,11 +87,9 @@ class DolomitePreTrainedModel(nn.Module):
             raise TypeError(f"unexpected keyword arguments: {sorted(kwargs)}")
         if self.attention_implementation not in ("flash_attention_2", "eager", "sdpa"):
             raise ValueError(f"unexpected `attn_implementation` {self.attention_implementation}")
-        if not self._use_padding_free_transformer:
-            raise NotImplementedError(
-                "the B200 hot path is the padding-free transformer (use_padding_free_transformer=True); "
-                "padded-batch attention is a 'next' row of SURVEY.md section 8f"
-            )
+        # use_padding_free_transformer=False (padded [B, S] batches + attention_mask, attention/flash.py:72-129): the reference
+        # unpads around flash attention inside every layer; here the batch is unpadded ONCE in `forward`, the packed engine
+        # runs on the valid tokens only, and the logits are scattered back to [B, S, V]
         if self.moe_implementation not in ("eager", "scattermoe"):
             raise ValueError(f"unexpected `moe_implementation` {self.moe_implementation}")
         if device is None:
@@ -142,6 +140,9 @@ class DolomitePreTrainedModel(nn.Module):
             # moe_dolomite/main.py:47-48
             raise NotImplementedError("router loss is not implemented with padding_free transformer")
         assert not output_hidden_states, "output_hidden_states is not supported on the B200 path"
+        if not self._use_padding_free_transformer:
+            return self._forward_padded(input_ids, attention_mask, position_ids, labels, return_dict, past_key_values,
+                                        use_cache, inputs_embeds, token_type_ids, cu_seqlens)
         input_ids, position_ids, token_type_ids, labels, cu_seqlens, max_seqlen = self.prepare_inputs_for_model(
             input_ids, inputs_embeds, position_ids, token_type_ids, labels, cu_seqlens, max_seqlen, past_key_values,
             attention_mask, use_cache, output_attentions,
@@ -167,6 +168,58 @@ class DolomitePreTrainedModel(nn.Module):
             result = CausalLMOutputWithPast(loss=out, logits=None)
         else:
             result = CausalLMOutputWithPast(loss=None, logits=out)
+        if not return_dict:
+            return tuple(v for v in (result.loss, result.logits) if v is not None)
+        return result
+
+    def _forward_padded(self, input_ids, attention_mask, position_ids, labels, return_dict, past_key_values, use_cache,
+                        inputs_embeds, token_type_ids, cu_seqlens):
+        """Padded batch path (gpt_dolomite/base.py:374-522 non-padding-free branch + attention/flash.py unpad/pad):
+        input_ids [B, S], attention_mask [B, S] (1 = token, left or right padding), labels [B, S] (-100 at padding).
+        position_ids default to `cumsum(mask) - 1` (base.py:524-534); loss = CE(logits[:, :-1], labels[:, 1:]) over the
+        non-ignored positions (main.py:179-202).  Every row becomes one document of the packed stream."""
+        if use_cache or past_key_values is not None:
+            raise NotImplementedError("KV caching / generation is not implemented on the B200 training path")
+        if inputs_embeds is not None or token_type_ids is not None:
+            raise NotImplementedError("inputs_embeds / token_type_ids are not supported on the B200 path")
+        assert cu_seqlens is None, "cu_seqlens belongs to the padding-free transformer"
+        dev = self.engine.device
+        input_ids = torch.as_tensor(input_ids).to(dev).long()
+        assert input_ids.dim() == 2, "padded batches are [batch, sequence]"
+        B, S = input_ids.shape
+        mask = torch.ones(B, S, dtype=torch.bool, device=dev) if attention_mask is None else attention_mask.to(dev).bool()
+        if position_ids is None:
+            position_ids = (mask.long().cumsum(-1) - 1).clamp_(min=0)
+        position_ids = position_ids.to(dev).long()
+        lens = mask.sum(1)
+        keep = mask.reshape(-1).nonzero(as_tuple=True)[0]
+        lens_host = lens.tolist()  # one host sync, like the reference's unpad (`max_seqlen_in_batch.item()`)
+        ends, total = [0], 0
+        for n in lens_host:  # empty rows contribute no document
+            if n > 0:
+                total += int(n)
+                ends.append(total)
+        cu = torch.tensor(ends, dtype=torch.int32, device=dev)
+        max_seqlen = max(lens_host) if lens_host else 0
+        ids_p = input_ids.reshape(-1)[keep].contiguous()
+        pos_p = position_ids.reshape(-1)[keep].contiguous()
+        shift_labels = None
+        if labels is not None:
+            lab = torch.as_tensor(labels).to(dev).long()
+            nxt = torch.full_like(lab, -100)
+            nxt[:, :-1] = lab[:, 1:]
+            # the successor must be a real token of the same row: drop targets that sit on padding
+            nxt_valid = torch.zeros_like(mask)
+            nxt_valid[:, :-1] = mask[:, 1:]
+            nxt = torch.where(nxt_valid & mask, nxt, torch.full_like(nxt, -100))
+            shift_labels = nxt.reshape(-1)[keep].contiguous()
+        out = _EngineFunction.apply(self._anchor, self, ids_p, pos_p, cu, int(max_seqlen), shift_labels, -100)
+        if shift_labels is not None:
+            result = CausalLMOutputWithPast(loss=out, logits=None)
+        else:
+            full = out.new_zeros(B * S, out.shape[-1])
+            full[keep] = out
+            result = CausalLMOutputWithPast(loss=None, logits=full.view(B, S, -1))
         if not return_dict:
             return tuple(v for v in (result.loss, result.logits) if v is not None)
         return result

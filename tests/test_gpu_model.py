@@ -331,3 +331,39 @@ def test_checkpoint_resume_continues_the_same_trajectory(tmp_path):
     assert first == pytest.approx(straight[:2], rel=1e-6)
     assert second == pytest.approx(straight[2:], rel=2e-4), (straight, first, second)
     assert c[2].get_last_lr() == pytest.approx(a[2].get_last_lr())
+
+
+@pytest.mark.parametrize("left_pad", [False, True])
+def test_padded_batches_match_the_unpadded_documents(left_pad):
+    """use_padding_free_transformer=False (attention/flash.py:72-129 unpad -> flash -> pad): a padded [B, S] batch with an
+    attention_mask gives the loss of its rows taken as separate documents (oracle finetuning loss on the unpadded lists),
+    and logits at the valid positions equal the packed run's; padding positions carry no loss and no gradient."""
+    from dolomite_engine_b200.hf_models import GPTDolomiteForCausalLM
+
+    kw = GPU_CONFIGS["hd80_bias"]
+    ocfg = O.OracleConfig(**kw)
+    params = oracle_params(ocfg)
+    model = GPTDolomiteForCausalLM(gpu_config(kw), seed=None, use_padding_free_transformer=False)
+    model.load_state_dict(params)
+    rng = np.random.default_rng(5)
+    lens, S = [37, 64, 1, 50], 64
+    docs = [rng.integers(8, ocfg.vocab_size, size=n).tolist() for n in lens]
+    ids = np.zeros((len(lens), S), dtype=np.int64)
+    mask = np.zeros((len(lens), S), dtype=np.int64)
+    labels = np.full((len(lens), S), -100, dtype=np.int64)
+    for r, d in enumerate(docs):
+        sl = slice(S - len(d), S) if left_pad else slice(0, len(d))
+        ids[r, sl], mask[r, sl], labels[r, sl] = d, 1, d
+    out = model(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask), labels=torch.from_numpy(labels))
+    ref = O.finetuning_loss(params, ocfg, docs, docs, bf16=True)
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    assert abs(out.loss.item() - float(ref)) / float(ref) < 2e-3
+    out.loss.backward()
+    lg = model(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask)).logits
+    assert tuple(lg.shape) == (len(lens), S, ocfg.vocab_size)
+    packed = model.__class__(gpu_config(kw), seed=None)
+    packed.load_state_dict(params)
+    lp = packed(input_ids=docs).logits  # padding-free list input: one document per row
+    flat = lg.reshape(-1, ocfg.vocab_size)[torch.from_numpy(mask.reshape(-1)).bool().cuda()]
+    assert torch.equal(flat, lp)  # same kernels on the same packed stream
+    assert float(lg[torch.from_numpy(mask).cuda() == 0].abs().max()) == 0.0

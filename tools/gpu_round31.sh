@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "=== pytest -m gpu ==="
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -12
