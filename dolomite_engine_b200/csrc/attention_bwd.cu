@@ -31,7 +31,7 @@ struct BwdParams {
     int64_t T;
     int n_groups, q_per_group, n_heads;
     float scale, scale_log2;
-    int experiment;  // diagnostic bit mask, 0 in production (bit 0: skip the dQ reductions, bit 1: skip exp2)
+    int experiment;  // diagnostic bit mask, 0 in production (bit 0: skip the dQ reductions -> timing only, dQ is wrong)
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {

@@ -39,7 +39,9 @@ int dolomite_b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   "attn_bwd_version" 1 (serial kernel, every head_dim) | 2 | 3 | 4 (pipelined, head_dim <= 80; 1 / 2 / 4 softmax groups)
  *   "attn_fwd_version" 1 (one query tile per CTA) | 2 (two query tiles per CTA, ping-pong softmax groups)
  *   "gemm_cta_pair"    0 | 1 (dense GEMMs on 2-CTA clusters with tcgen05.mma.cta_group::2)
- *   "gemm_sm_margin"   SMs the persistent GEMM grids leave free for concurrent communication kernels */
+ *   "gemm_sm_margin"   SMs the persistent GEMM grids leave free for concurrent communication kernels
+ *   "attn_bwd_experiment" diagnostic bit mask for timing what-ifs (bit 0: drop the dQ reductions); results are WRONG
+ *                      when non-zero, production callers never set it */
 int dolomite_b200_set_option(const char* key, int value);
 
 /* ------------------------------------------------------------------------------------------------
