@@ -420,7 +420,8 @@ int make_maps(const void* base, int64_t ld, int64_t rows, CUtensorMap* m64, CUte
 
 template <int HD>
 int launch_bwd_pipelined(const void* dout, const void* qkv, int64_t row_stride, const BwdParams& p, cudaStream_t st) {
-    const int v = dolo_option_attn_bwd_version();  // 2: one softmax group, 3: two groups, 4: four groups (704 threads)
+    // 2: one softmax group, 3: two groups (default), 4: four groups (704 threads; measured 4 % slower than 3)
+    const int v = dolo_option_attn_bwd_version();
     if (v >= 4) return launch_bwd_v3<HD, 4>(dout, qkv, row_stride, p, st);
     if (v == 3) return launch_bwd_v3<HD, 2>(dout, qkv, row_stride, p, st);
     return launch_bwd_v2<HD>(dout, qkv, row_stride, p, st);
