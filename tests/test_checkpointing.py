@@ -127,3 +127,24 @@ def test_world_size_2_checkpoint_roundtrip(tmp_path):
         p.join(timeout=60)
     for rank, status in results:
         assert status == "ok", f"rank {rank}: {status}"
+
+
+def test_unshard_writes_a_pretrained_directory(tmp_path):
+    """unshard.py of the reference: global_step<N>/model.pt -> safetensors + config.json with the reference's names"""
+    from dolomite_engine_b200 import checkpointing as C
+    from dolomite_engine_b200.hf_models.config import GPTDolomiteConfig
+    from dolomite_engine_b200.unshard import unshard
+    from dolomite_engine_b200.utils.safetensors import SafeTensorsWeightsManager
+
+    path = str(tmp_path / "ckpt")
+    engine, model, opt, sched = _build(1, 0, seed=3)
+    args = _args(path)
+    args.model_dump = lambda mode="json": {"model_args": {"pretrained_config": engine.cfg.to_dict()}}
+    C.save_checkpoint(args, model, opt, sched, None, None, 11)
+    out = unshard(path, str(tmp_path / "hf"), None)
+    sd = SafeTensorsWeightsManager(out).state_dict()
+    want = C.model_state_dict(model)
+    assert set(sd) == {k[len("model."):] for k in want}
+    assert all(torch.equal(sd[k[len("model."):]], v) for k, v in want.items())
+    cfg = GPTDolomiteConfig.from_pretrained(out)
+    assert cfg.n_embd == 64 and cfg.num_key_value_heads == 2 and cfg.attention_head_type == "gqa"
