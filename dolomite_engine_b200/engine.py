@@ -176,7 +176,11 @@ def check_supported(cfg: CommonConfig) -> None:
     if cfg.position_embedding_type == "learned_absolute" and cfg.m_emb is not None:
         raise NotImplementedError("learned_absolute positions combined with m_emb are not implemented")
     if cfg.rope_scaling is not None:
-        raise NotImplementedError("YaRN rope_scaling is out of scope of the B200 hot path (SURVEY.md section 2 #5)")
+        rs = cfg.rope_scaling
+        if not isinstance(rs, dict) or "factor" not in rs or "original_max_position_embeddings" not in rs:
+            raise ValueError("rope_scaling needs `factor` and `original_max_position_embeddings` (YaRN, gpt_dolomite/base.py:541-547)")
+        if rs.get("type", "yarn") not in ("yarn",):
+            raise NotImplementedError(f"rope_scaling type {rs.get('type')!r}: the reference implements YaRN only")
     if cfg.normalization_function not in ("rmsnorm", "layernorm"):
         raise NotImplementedError(
             f"normalization_function={cfg.normalization_function!r}: rmsnorm and layernorm are implemented in CUDA")
@@ -247,12 +251,32 @@ class DolomiteEngine:
         if self.cfg.position_embedding_type != "rope":
             return
         hd = self.hd
-        inv_freq = 1.0 / (float(self.cfg.rope_theta) ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))
+        base = float(self.cfg.rope_theta)
+        mscale = 1.0
+        rs = self.cfg.rope_scaling
+        if rs is None:
+            inv_freq = 1.0 / (base ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))
+        else:
+            # YaRNScaledRoPE (rope.py:56-101, :118-145; constructed in gpt_dolomite/base.py:534-547 with the class
+            # defaults extrapolation_factor = attn_factor = 1, beta_fast = 32, beta_slow = 1): only the tables change
+            scale, orig = float(rs["factor"]), int(rs["original_max_position_embeddings"])
+
+            def correction_dim(num_rotations: float) -> float:
+                return (hd * math.log(orig / (num_rotations * 2 * math.pi))) / (2 * math.log(base))
+
+            pos_freqs = base ** (torch.arange(0, hd, 2).float() / hd)
+            low = max(math.floor(correction_dim(32)), 0)
+            high = min(math.ceil(correction_dim(1)), hd - 1)
+            hi = high + 0.001 if low == high else high
+            ramp = torch.clamp((torch.arange(hd // 2, dtype=torch.float32) - low) / (hi - low), 0, 1)
+            mask = 1 - ramp
+            inv_freq = (1.0 / (scale * pos_freqs)) * (1 - mask) + (1.0 / pos_freqs) * mask
+            mscale = 1.0 if scale <= 1 else 0.1 * math.log(scale) + 1.0
         t = torch.arange(self.cfg.n_positions, dtype=torch.float32)
         freqs = torch.outer(t, inv_freq)
         emb = torch.cat((freqs, freqs), dim=-1)
-        self.rope_cos = emb.cos().to(torch.bfloat16).to(self.device)
-        self.rope_sin = emb.sin().to(torch.bfloat16).to(self.device)
+        self.rope_cos = (emb.cos() * mscale).to(torch.bfloat16).to(self.device)
+        self.rope_sin = (emb.sin() * mscale).to(torch.bfloat16).to(self.device)
 
     def named_views(self):
         for u in self.units:

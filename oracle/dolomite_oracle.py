@@ -55,6 +55,7 @@ class OracleConfig:
     # MoE (moe_dolomite/config.py:4-83)
     num_experts: int = 0
     num_experts_per_tok: int = 0
+    rope_scaling: dict | None = None  # YaRN: {"factor": s, "original_max_position_embeddings": n}
     extra: dict = field(default_factory=dict)
 
     def __post_init__(self):
@@ -187,13 +188,40 @@ def norm(x: torch.Tensor, p: dict, prefix: str, cfg: "OracleConfig", bf16: bool 
     raise ValueError(f"oracle: unsupported normalization {cfg.normalization_function}")
 
 
-def rope_tables(head_dim: int, n_positions: int, base: float, bf16: bool = False):
-    """position_embedding/rope.py:25-55"""
-    inv_freq = 1.0 / (base ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+def yarn_inv_freq_and_mscale(head_dim: int, base: float, scale: float, original_max_position_embeddings: int,
+                             extrapolation_factor: float = 1, attn_factor: float = 1, beta_fast: int = 32, beta_slow: int = 1):
+    """YaRNScaledRoPE (position_embedding/rope.py:56-101, :118-145): per-dimension blend of interpolated and extrapolated
+    frequencies + the magnitude correction `mscale` that the reference multiplies into the cos / sin tables"""
+
+    def correction_dim(num_rotations):
+        return (head_dim * math.log(original_max_position_embeddings / (num_rotations * 2 * math.pi))) / (2 * math.log(base))
+
+    pos_freqs = base ** (torch.arange(0, head_dim, 2).float() / head_dim)
+    extrapolation = 1.0 / pos_freqs
+    interpolation = 1.0 / (scale * pos_freqs)
+    low = max(math.floor(correction_dim(beta_fast)), 0)
+    high = min(math.ceil(correction_dim(beta_slow)), head_dim - 1)
+    hi = high + 0.001 if low == high else high
+    ramp = torch.clamp((torch.arange(head_dim // 2, dtype=torch.float32) - low) / (hi - low), 0, 1)
+    mask = (1 - ramp) * extrapolation_factor
+    inv_freq = interpolation * (1 - mask) + extrapolation * mask
+    mscale = (1.0 if scale <= 1 else 0.1 * math.log(scale) + 1.0) * attn_factor
+    return inv_freq, mscale
+
+
+def rope_tables(head_dim: int, n_positions: int, base: float, bf16: bool = False, rope_scaling: dict | None = None):
+    """position_embedding/rope.py:25-55; with `rope_scaling` (YaRN, gpt_dolomite/base.py:534-547) the frequencies and the
+    table magnitude change, nothing else"""
+    mscale = 1.0
+    if rope_scaling is None:
+        inv_freq = 1.0 / (base ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+    else:
+        inv_freq, mscale = yarn_inv_freq_and_mscale(head_dim, base, rope_scaling["factor"],
+                                                    rope_scaling["original_max_position_embeddings"])
     t = torch.arange(n_positions, dtype=torch.float32)
     freqs = torch.outer(t, inv_freq)
     emb = torch.cat((freqs, freqs), dim=-1)
-    return _r(emb.cos(), bf16), _r(emb.sin(), bf16)
+    return _r(emb.cos() * mscale, bf16), _r(emb.sin() * mscale, bf16)
 
 
 def apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, bf16: bool = False) -> torch.Tensor:
@@ -357,7 +385,7 @@ def forward_logits(p: dict, cfg: OracleConfig, input_ids, position_ids, cu_seqle
         h = _r(h * cfg.m_emb, bf16)
     cos = sin = None
     if cfg.position_embedding_type == "rope":
-        ct, st = rope_tables(cfg.head_dim, cfg.n_positions, cfg.rope_theta, bf16)
+        ct, st = rope_tables(cfg.head_dim, cfg.n_positions, cfg.rope_theta, bf16, cfg.rope_scaling)
         cos, sin = ct[pos].unsqueeze(1), st[pos].unsqueeze(1)
     hidden = [h]
     for i in range(cfg.n_layer):

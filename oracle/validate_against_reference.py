@@ -48,12 +48,13 @@ def import_reference():
     import dolomite_engine.hf_models  # noqa: F401
     from dolomite_engine.hf_models.modeling_utils import RMSNorm, RoPE, apply_rotary_pos_emb  # noqa: F401
     from dolomite_engine.hf_models.modeling_utils import get_normalization_function
+    from dolomite_engine.hf_models.modeling_utils.position_embedding.rope import YaRNScaledRoPE
     from dolomite_engine.hf_models.models.gpt_dolomite.layer import GPTDolomiteBlock
     from dolomite_engine.hf_models.models.moe_dolomite.moe.base import SparseMoE
 
     return types.SimpleNamespace(
         GPTDolomiteBlock=GPTDolomiteBlock, RMSNorm=RMSNorm, RoPE=RoPE, apply_rotary_pos_emb=apply_rotary_pos_emb,
-        SparseMoE=SparseMoE, get_normalization_function=get_normalization_function,
+        SparseMoE=SparseMoE, get_normalization_function=get_normalization_function, YaRNScaledRoPE=YaRNScaledRoPE,
     )
 
 
@@ -172,6 +173,13 @@ def main():
     ocb, osb = O.rope_tables(80, 128, 10000, bf16=True)
     close(O.apply_rope(q.bfloat16().float(), ocb.unsqueeze(1), osb.unsqueeze(1), bf16=True),
           R.apply_rotary_pos_emb(q.bfloat16(), (cb.unsqueeze(1), sb.unsqueeze(1))).float(), 0.0, "apply_rotary_pos_emb bf16")
+
+    for hd_, npos, base, factor, orig in [(80, 512, 10000, 4.0, 128), (128, 1024, 500000, 8.0, 256), (64, 256, 10000, 1.0, 256)]:
+        yr = R.YaRNScaledRoPE(hd_, max_position_embeddings=npos, base=base, scale=factor, original_max_position_embeddings=orig)
+        yc, ys = yr(npos, dtype=torch.float32, device=None)
+        oc2, os2 = O.rope_tables(hd_, npos, base, rope_scaling={"factor": factor, "original_max_position_embeddings": orig})
+        close(oc2, yc, 0.0, f"YaRN cos table hd{hd_} x{factor}")
+        close(os2, ys, 0.0, f"YaRN sin table hd{hd_} x{factor}")
 
     for name, kw in CONFIGS.items():
         print(f"== model {name} ==")

@@ -44,7 +44,7 @@ def test_unsupported_configs_fail_loudly():
     check_supported(ok)
     for kw in (dict(position_embedding_type="alibi"), dict(normalization_function="apex_layernorm"),
                dict(activation_function="geglu"), dict(attn_pdrop=0.1), dict(n_head=32, num_key_value_heads=32),
-               dict(position_embedding_type="learned_absolute", m_emb=12.0), dict(rope_scaling={"type": "yarn", "factor": 4})):
+               dict(position_embedding_type="learned_absolute", m_emb=12.0), dict(rope_scaling={"type": "linear", "factor": 2, "original_max_position_embeddings": 64})):
         d = ok.to_dict()
         d.update(kw)
         with pytest.raises(NotImplementedError):
@@ -187,3 +187,24 @@ def test_gradient_checkpointing_args_follow_the_reference_surface():
     d["distributed_args"]["gradient_checkpointing_method"] = "selective"
     with pytest.raises(Exception):
         get_args_from_dict(d)
+
+
+def test_rope_tables_plain_and_yarn_equal_the_pinned_oracle_tables():
+    """engine._setup_rope restates RoPE / YaRNScaledRoPE (position_embedding/rope.py:9-101); the oracle's tables are pinned
+    bit-exactly against the reference classes (oracle/validate_against_reference.py), the engine's must equal them in bf16"""
+    import torch
+
+    import oracle.dolomite_oracle as O
+    from dolomite_engine_b200.engine import DolomiteEngine
+
+    for rs, theta in [(None, 10000), ({"type": "yarn", "factor": 4.0, "original_max_position_embeddings": 64}, 10000),
+                      ({"factor": 8.0, "original_max_position_embeddings": 128}, 500000)]:
+        cfg = GPTDolomiteConfig(n_embd=320, n_head=4, n_layer=1, n_inner=640, vocab_size=256, n_positions=512,
+                                attention_head_type="mha", position_embedding_type="rope", activation_function="swiglu",
+                                normalization_function="rmsnorm", resid_pdrop=0, embd_pdrop=0, attn_pdrop=0, rope_theta=theta,
+                                rope_scaling=rs)
+        eng = DolomiteEngine(cfg, "cpu", seed=None)
+        cos, sin = O.rope_tables(80, 512, theta, bf16=True, rope_scaling=rs)
+        assert torch.equal(eng.rope_cos.float(), cos) and torch.equal(eng.rope_sin.float(), sin)
+    with pytest.raises(ValueError):
+        check_supported(GPTDolomiteConfig.from_dict({**cfg.to_dict(), "rope_scaling": {"factor": 2.0}}))
