@@ -308,3 +308,48 @@ def test_gelu_tanh_fwd_bwd_and_fused_bias_gradient():
         assert torch.equal(fused, plain)
         want = 0.25 + plain.float().sum(0)
         assert torch.allclose(db, want, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("lens,ng,g,hd", [([130, 0, 64, 0], 2, 1, 80), ([0, 5], 1, 2, 64), ([70, 200], 2, 1, 96),
+                                          ([257], 1, 1, 80), ([127, 129, 128], 2, 1, 64)])
+def test_attention_edge_cases_empty_documents_and_tile_boundaries(lens, ng, g, hd):
+    """cu_seqlens with empty documents (consecutive equal entries, what `reset_attention_mask` produces for back-to-back
+    EOS), lengths on either side of the 128-row tile boundary, head_dim 96; both forward variants, every backward variant"""
+    qkv, dout, cu = _attn_inputs(lens, ng, g, hd, seed=11)
+    scale = 1.0 / math.sqrt(hd)
+    cfg = O.OracleConfig(n_embd=ng * g * hd, n_head=ng * g, num_key_value_heads=ng,
+                         attention_head_type="mha" if g == 1 else "gqa")
+    x = qkv.float().requires_grad_(True)
+    q, k, v = O.split_qkv_activations(x, cfg)
+    ref = O.packed_causal_attention(q, k, v, cu, scale)
+    ref.backward(dout.float())
+    cu_d = torch.from_numpy(cu).cuda()
+    try:
+        for fv in (1, 2):
+            K().set_option("attn_fwd_version", fv)
+            out, lse = K().attn_varlen_fwd(qkv.cuda(), cu_d, max(lens), ng, g, hd, scale)
+            assert rel_l2(out, ref) < 6e-3, fv
+        for version in (1, 2, 3, 4):
+            K().set_option("attn_bwd_version", version)
+            dqkv = K().attn_varlen_bwd(dout.cuda(), qkv.cuda(), out, lse, cu_d, max(lens), ng, g, hd, scale)
+            assert rel_l2(dqkv, x.grad) < 1.2e-2, version
+    finally:
+        K().set_option("attn_bwd_version", 3)
+        K().set_option("attn_fwd_version", 1)
+
+
+def test_empty_and_single_row_inputs_are_accepted():
+    """T = 0 launches nothing and returns; T = 1 works for every HBM kernel"""
+    k = K()
+    for T in (0, 1):
+        x = torch.randn(T, 256, device="cuda").bfloat16()
+        w = torch.ones(256, device="cuda").bfloat16()
+        y, rstd = k.rmsnorm_fwd(x, w, 1e-5)
+        assert tuple(y.shape) == (T, 256) and tuple(rstd.shape) == (T,)
+        dw = torch.zeros(256, device="cuda")
+        assert tuple(k.rmsnorm_bwd(x, x, w, rstd, dw).shape) == (T, 256)
+        assert tuple(k.swiglu_fwd(torch.randn(T, 512, device="cuda").bfloat16()).shape) == (T, 256)
+        assert tuple(k.gelu_fwd(torch.randn(T, 512, device="cuda").bfloat16()).shape) == (T, 512)
+        ids = torch.zeros(T, dtype=torch.int64, device="cuda")
+        assert tuple(k.embedding_fwd(ids, torch.randn(16, 64, device="cuda").bfloat16()).shape) == (T, 64)
+    torch.cuda.synchronize()
