@@ -164,12 +164,17 @@ class ModelWrapperForPretraining(ModelWrapper):
 
 
 class ModelWrapperForFinetuning(ModelWrapper):
-    """model_wrapper/finetuning.py:10-99 for the padding-free list format produced by data/utils.py:8-92 collate_fn:
-    batch = {"input_ids": list[list[int]], "labels": list[list[int]]}; loss is computed inside the model
-    (gpt_dolomite/main.py:179-202)."""
+    """model_wrapper/finetuning.py:10-99.  Padding-free collate (data/utils.py:8-92): batch = {"input_ids":
+    list[list[int]], "labels": list[list[int]]}; padded collate: [B, S] tensors + "attention_mask".  The loss is computed
+    inside the model (gpt_dolomite/main.py:179-202)."""
 
     def forward(self, batch: dict) -> torch.Tensor:
-        out = self.model(input_ids=batch["input_ids"], labels=batch["labels"], position_ids=batch.get("position_ids"))
+        if "attention_mask" in batch and batch["attention_mask"] is not None:
+            # padded collate (use_padding_free_transformer: false, data/utils.py:8-92): [B, S] tensors + attention_mask
+            out = self.model(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"], labels=batch["labels"],
+                             position_ids=batch.get("position_ids"))
+        else:
+            out = self.model(input_ids=batch["input_ids"], labels=batch["labels"], position_ids=batch.get("position_ids"))
         return out.loss
 
 

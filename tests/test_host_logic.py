@@ -208,3 +208,14 @@ def test_rope_tables_plain_and_yarn_equal_the_pinned_oracle_tables():
         assert torch.equal(eng.rope_cos.float(), cos) and torch.equal(eng.rope_sin.float(), sin)
     with pytest.raises(ValueError):
         check_supported(GPTDolomiteConfig.from_dict({**cfg.to_dict(), "rope_scaling": {"factor": 2.0}}))
+
+
+def test_every_shipped_config_parses():
+    """configs/*.yml follow the reference's TrainingArgs tree (extra=forbid): C1, C2/C3, C4 (MoE), C5 (Llama-3-8B finetune)"""
+    names = sorted(f for f in os.listdir(os.path.join(ROOT, "configs")) if f.endswith(".yml"))
+    assert {"c1_tiny.yml", "c2_granite3b_shape.yml", "c4_moe_8x_top2.yml", "c5_llama3_8b_finetune.yml"} <= set(names)
+    for f in names:
+        a = get_args_from_dict(load_yaml(os.path.join(ROOT, "configs", f)))
+        assert a.training_parameters.micro_batch_size >= 1
+    a = get_args_from_dict(load_yaml(os.path.join(ROOT, "configs", "c5_llama3_8b_finetune.yml")))
+    assert a.distributed_args.gradient_checkpointing_args == {"checkpoint_every": 2} and a.model_args.model_name
