@@ -2,8 +2,9 @@
 models/moe_dolomite/config.py:4-83): same field names, defaults, aliases, validation and config.json format.
 
 The reference subclasses transformers.PretrainedConfig; that class changed incompatibly in transformers 5.x
-(SURVEY.md section 8c), so this is a small self-contained implementation of the same surface:
-`to_dict / from_dict / save_pretrained / from_pretrained`, GPT-2 style names plus the `attribute_map` aliases.
+(SURVEY.md section 8c), so this is a small self-contained, table-driven implementation of the same surface:
+every config class lists its (field, default) pairs once in `FIELDS`; construction, `to_dict / from_dict /
+save_pretrained / from_pretrained` and the `attribute_map` aliases are generic.
 """
 
 from __future__ import annotations
@@ -14,138 +15,80 @@ import os
 
 from .enums import AttentionHeadType, InitMethod, PositionEmbeddingType
 
+# HuggingFace-style aliases of the GPT-2 style names (config.py:8-13)
+_ALIASES = {"hidden_size": "n_embd", "max_position_embeddings": "n_positions", "num_attention_heads": "n_head",
+            "num_hidden_layers": "n_layer"}
+# keys HuggingFace writes into config.json that are not model hyper-parameters
+_HF_NOISE = ("model_type", "multi_query", "architectures", "transformers_version", "torch_dtype", "dtype")
+
 
 class CommonConfig:
     model_type = "common"
     keys_to_ignore_at_inference = ["past_key_values"]
-    attribute_map = {
-        "hidden_size": "n_embd",
-        "max_position_embeddings": "n_positions",
-        "num_attention_heads": "n_head",
-        "num_hidden_layers": "n_layer",
-    }
+    attribute_map = _ALIASES
 
-    def __init__(
-        self,
-        vocab_size: int = 50257,
-        n_positions: int = 1024,
-        n_embd: int = 768,
-        n_layer: int = 12,
-        n_head: int = 12,
-        num_key_value_heads: int | None = None,
-        n_inner: int | None = None,
-        activation_function: str = "gelu_pytorch_tanh",
-        attention_head_type: str = "mqa",
-        resid_pdrop: float = 0.1,
-        embd_pdrop: float = 0.1,
-        attn_pdrop: float = 0.1,
-        normalization_function: str = "layernorm",
-        layer_norm_epsilon: float = 1e-5,
-        initializer_range: float = 0.02,
-        scale_attn_weights: bool = True,
-        attention_multiplier: float | None = None,
-        use_cache: bool = True,
-        bos_token_id: int = 50256,
-        eos_token_id: int = 50256,
-        pad_token_id: int = 50256,
-        attention_softmax_in_fp32: bool = True,
-        add_bias: bool = True,
-        position_embedding_type: str = "learned_absolute",
-        rope_theta: int = 10000,
-        rope_scaling: dict | None = None,
-        m_emb: float | None = None,
-        m_width: float | None = None,
-        m_residual: float | None = None,
-        init_method: str = "normal",
-        upcast_logits_for_loss: bool = False,
-        tie_word_embeddings: bool = True,
-        **kwargs,
-    ) -> None:
-        # aliases passed as kwargs (hidden_size=..., num_hidden_layers=...) map onto the GPT-2 names
-        for alias, name in self.attribute_map.items():
-            if alias in kwargs:
-                val = kwargs.pop(alias)
-                if name == "n_embd":
-                    n_embd = val
-                elif name == "n_positions":
-                    n_positions = val
-                elif name == "n_head":
-                    n_head = val
-                elif name == "n_layer":
-                    n_layer = val
-        self.vocab_size = vocab_size
-        self.n_positions = n_positions
-        self.n_embd = n_embd
-        self.n_layer = n_layer
-        self.n_head = n_head
-        self.num_key_value_heads = num_key_value_heads
-        self.n_inner = 4 * n_embd if n_inner is None else n_inner
-        self.activation_function = activation_function
-        self.attention_head_type = attention_head_type
-        self.resid_pdrop = resid_pdrop
-        self.embd_pdrop = embd_pdrop
-        self.attn_pdrop = attn_pdrop
-        self.normalization_function = normalization_function
-        self.layer_norm_epsilon = layer_norm_epsilon
-        self.initializer_range = initializer_range
-        self.scale_attn_weights = scale_attn_weights
-        self.attention_multiplier = attention_multiplier
-        self.use_cache = use_cache
-        self.attention_softmax_in_fp32 = attention_softmax_in_fp32
-        self.position_embedding_type = position_embedding_type
-        self.add_bias = add_bias
-        self.rope_theta = rope_theta
-        self.rope_scaling = rope_scaling
-        self.m_emb = m_emb
-        self.m_width = m_width
-        self.m_residual = m_residual
-        self.init_method = init_method
-        self.upcast_logits_for_loss = upcast_logits_for_loss
-        self.tie_word_embeddings = tie_word_embeddings
-        self.bos_token_id = bos_token_id
-        self.eos_token_id = eos_token_id
-        self.pad_token_id = pad_token_id
+    # (name, default) in the reference's order; None defaults are resolved in `_finalise`
+    FIELDS: tuple[tuple[str, object], ...] = (
+        ("vocab_size", 50257), ("n_positions", 1024), ("n_embd", 768), ("n_layer", 12), ("n_head", 12),
+        ("num_key_value_heads", None), ("n_inner", None), ("activation_function", "gelu_pytorch_tanh"),
+        ("attention_head_type", "mqa"), ("resid_pdrop", 0.1), ("embd_pdrop", 0.1), ("attn_pdrop", 0.1),
+        ("normalization_function", "layernorm"), ("layer_norm_epsilon", 1e-5), ("initializer_range", 0.02),
+        ("scale_attn_weights", True), ("attention_multiplier", None), ("use_cache", True), ("bos_token_id", 50256),
+        ("eos_token_id", 50256), ("pad_token_id", 50256), ("attention_softmax_in_fp32", True), ("add_bias", True),
+        ("position_embedding_type", "learned_absolute"), ("rope_theta", 10000), ("rope_scaling", None), ("m_emb", None),
+        ("m_width", None), ("m_residual", None), ("init_method", "normal"), ("upcast_logits_for_loss", False),
+        ("tie_word_embeddings", True),
+    )
 
-        if self.attention_multiplier is not None:
-            assert self.scale_attn_weights
-
-        # check if enums are valid
-        init_method = InitMethod(init_method)
-        attention_head_type = AttentionHeadType(attention_head_type)
-        position_embedding_type = PositionEmbeddingType(position_embedding_type)
-
-        self.multi_query = attention_head_type == AttentionHeadType.mqa
-
-        if attention_head_type == AttentionHeadType.mha:
-            if self.num_key_value_heads is None:
-                self.num_key_value_heads = self.n_head
-            assert (
-                self.n_head == self.num_key_value_heads
-            ), "MultiHeadAttention should have same number of heads for query, keys and values"
-        elif attention_head_type == AttentionHeadType.mqa:
-            if self.num_key_value_heads is None:
-                self.num_key_value_heads = 1
-            assert self.num_key_value_heads == 1, "MultiQueryAttention should have 1 head for keys and values"
-        elif attention_head_type == AttentionHeadType.gqa:
-            assert (
-                self.num_key_value_heads is not None
-            ), "`num_key_value_heads` needs to be specified with GroupedQueryAttention"
-            assert (
-                self.n_head % self.num_key_value_heads == 0
-            ), "GroupedQueryAttention should have more than 1 head for keys and values"
-
+    def __init__(self, **kwargs) -> None:
+        known = dict(type(self).all_fields())
+        values = {}
+        for key in list(kwargs):
+            name = _ALIASES.get(key, key)
+            if name in known:
+                values[name] = kwargs.pop(key)
+        for name, default in known.items():
+            object.__setattr__(self, name, values.get(name, copy.deepcopy(default)))
         self._extra = dict(kwargs)  # unknown HF keys are kept so that config.json round-trips
+        self._finalise()
+
+    @classmethod
+    def all_fields(cls) -> tuple[tuple[str, object], ...]:
+        out: tuple[tuple[str, object], ...] = ()
+        for klass in reversed(cls.__mro__):
+            out += tuple(klass.__dict__.get("FIELDS", ()))
+        return out
+
+    def _finalise(self) -> None:
+        """derived defaults and the reference's consistency checks (config.py:56, :81-109)"""
+        if self.n_inner is None:
+            self.n_inner = 4 * self.n_embd
+        if self.attention_multiplier is not None and not self.scale_attn_weights:
+            raise AssertionError("attention_multiplier needs scale_attn_weights")
+        InitMethod(self.init_method)  # ValueError for unknown members, like the reference's enum casts
+        PositionEmbeddingType(self.position_embedding_type)
+        kind = AttentionHeadType(self.attention_head_type)
+        self.multi_query = kind is AttentionHeadType.mqa
+        nkv = self.num_key_value_heads
+        if kind is AttentionHeadType.mha:
+            nkv = self.n_head if nkv is None else nkv
+            assert nkv == self.n_head, "MultiHeadAttention should have same number of heads for query, keys and values"
+        elif kind is AttentionHeadType.mqa:
+            nkv = 1 if nkv is None else nkv
+            assert nkv == 1, "MultiQueryAttention should have 1 head for keys and values"
+        else:
+            assert nkv is not None, "`num_key_value_heads` needs to be specified with GroupedQueryAttention"
+            assert self.n_head % nkv == 0, "GroupedQueryAttention should have more than 1 head for keys and values"
+        self.num_key_value_heads = nkv
 
     # ---- attribute_map aliases ----
     def __getattr__(self, name):
-        amap = type(self).attribute_map
-        if name in amap:
-            return getattr(self, amap[name])
+        if name in _ALIASES:
+            return getattr(self, _ALIASES[name])
         raise AttributeError(f"{type(self).__name__} has no attribute {name!r}")
 
     def __setattr__(self, name, value):
-        amap = type(self).attribute_map
-        object.__setattr__(self, amap.get(name, name), value)
+        object.__setattr__(self, _ALIASES.get(name, name), value)
 
     @property
     def head_dim(self) -> int:
@@ -160,12 +103,7 @@ class CommonConfig:
 
     @classmethod
     def from_dict(cls, d: dict):
-        d = dict(d)
-        d.pop("model_type", None)
-        d.pop("multi_query", None)
-        for k in ("architectures", "transformers_version", "torch_dtype", "dtype"):
-            d.pop(k, None)
-        return cls(**d)
+        return cls(**{k: v for k, v in d.items() if k not in _HF_NOISE})
 
     def save_pretrained(self, path: str) -> None:
         os.makedirs(path, exist_ok=True)
@@ -190,23 +128,10 @@ class MoEDolomiteConfig(CommonConfig):
     """models/moe_dolomite/config.py:4-83"""
 
     model_type = "moe_dolomite"
-
-    def __init__(
-        self,
-        num_experts: int = 8,
-        num_experts_per_tok: int = 2,
-        output_router_logits: bool = False,
-        router_aux_loss_coef: float = 0.001,
-        **kwargs,
-    ) -> None:
-        super().__init__(**kwargs)
-        self.num_experts = num_experts
-        self.num_experts_per_tok = num_experts_per_tok
-        self.output_router_logits = output_router_logits
-        self.router_aux_loss_coef = router_aux_loss_coef
+    FIELDS = (("num_experts", 8), ("num_experts_per_tok", 2), ("output_router_logits", False), ("router_aux_loss_coef", 0.001))
 
 
-_CONFIG_CLASSES = {"gpt_dolomite": GPTDolomiteConfig, "moe_dolomite": MoEDolomiteConfig}
+_CONFIG_CLASSES = {c.model_type: c for c in (GPTDolomiteConfig, MoEDolomiteConfig)}
 
 
 def config_class_for(model_type: str):
