@@ -50,7 +50,14 @@ class DolomiteFusedAdamW(Optimizer):
         sdp.notify_fused_update()
 
 
-_OPTIMIZER_CLASSES = {"TorchAdamW": torch.optim.AdamW, "DolomiteFusedAdamW": DolomiteFusedAdamW}
+# the reference's registry (optimization/optimizer.py:55-84): every torch.optim class under its "Torch<Name>" key works on
+# the flat fp32 shards unchanged; the Apex / DeepSpeed entries are other backends' fused kernels (no multi-backend
+# dispatch here) -- DolomiteFusedAdamW is this engine's fused kernel and the default of the shipped configs
+_OPTIMIZER_CLASSES = {
+    f"Torch{name}": getattr(torch.optim, name)
+    for name in ("Adadelta", "Adagrad", "Adam", "Adamax", "AdamW", "ASGD", "NAdam", "RAdam", "RMSprop", "Rprop", "SGD")
+}
+_OPTIMIZER_CLASSES["DolomiteFusedAdamW"] = DolomiteFusedAdamW
 
 
 def get_optimizer(optimizer_class_name: str, optimizer_class_args: dict, model, params_group_method=None) -> Optimizer:
