@@ -38,10 +38,11 @@ class _EngineFunction(torch.autograd.Function):
     are accumulated by the engine into its flat fp32 gradient buffers (exactly where FSDP would leave them)."""
 
     @staticmethod
-    def forward(ctx, anchor, model, input_ids, position_ids, cu_seqlens, max_seqlen, labels, ignore_index):
+    def forward(ctx, anchor, model, input_ids, position_ids, cu_seqlens, max_seqlen, labels, ignore_index, save=True):
+        # `save`: the caller's torch.is_grad_enabled() (always False in here); under no_grad (evaluation) no activation is kept
         engine = model.engine
         logits, loss = engine.forward(input_ids, position_ids, cu_seqlens, max_seqlen, labels=labels,
-                                      ignore_index=ignore_index, save_for_backward=torch.is_grad_enabled() or True)
+                                      ignore_index=ignore_index, save_for_backward=bool(save))
         ctx.model = model
         ctx.loss_mode = labels is not None
         return loss.reshape(()) if ctx.loss_mode else logits
@@ -57,7 +58,7 @@ class _EngineFunction(torch.autograd.Function):
             engine.backward(grad_scale_dev=scale)
         else:
             engine.backward(dlogits=grad_out.contiguous())
-        return (None,) * 8
+        return (None,) * 9
 
 
 class DolomitePreTrainedModel(nn.Module):
@@ -163,7 +164,7 @@ class DolomitePreTrainedModel(nn.Module):
             shift_labels[:-1] = labels[1:]
             drop = (cu_seqlens[1:-1] - 1).long()
             shift_labels[drop] = -100
-        out = _EngineFunction.apply(self._anchor, self, input_ids, position_ids, cu_seqlens, int(max_seqlen), shift_labels, -100)
+        out = _EngineFunction.apply(self._anchor, self, input_ids, position_ids, cu_seqlens, int(max_seqlen), shift_labels, -100, torch.is_grad_enabled())
         if shift_labels is not None:
             result = CausalLMOutputWithPast(loss=out, logits=None)
         else:
@@ -213,7 +214,7 @@ class DolomitePreTrainedModel(nn.Module):
             nxt_valid[:, :-1] = mask[:, 1:]
             nxt = torch.where(nxt_valid & mask, nxt, torch.full_like(nxt, -100))
             shift_labels = nxt.reshape(-1)[keep].contiguous()
-        out = _EngineFunction.apply(self._anchor, self, ids_p, pos_p, cu, int(max_seqlen), shift_labels, -100)
+        out = _EngineFunction.apply(self._anchor, self, ids_p, pos_p, cu, int(max_seqlen), shift_labels, -100, torch.is_grad_enabled())
         if shift_labels is not None:
             result = CausalLMOutputWithPast(loss=out, logits=None)
         else:
@@ -226,7 +227,7 @@ class DolomitePreTrainedModel(nn.Module):
 
     # ---- pretraining entry: labels already aligned with positions (model_wrapper/pretraining.py:104-127) ----
     def forward_pretraining_loss(self, input_ids, position_ids, cu_seqlens, max_seqlen: int, labels):
-        return _EngineFunction.apply(self._anchor, self, input_ids, position_ids, cu_seqlens, int(max_seqlen), labels, -100)
+        return _EngineFunction.apply(self._anchor, self, input_ids, position_ids, cu_seqlens, int(max_seqlen), labels, -100, torch.is_grad_enabled())
 
     # ------------------------------------------------------------------------------------------
     # state dict / (de)serialisation with the reference's names

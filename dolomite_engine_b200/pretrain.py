@@ -100,6 +100,49 @@ def make_megatron_dataloader(args: TrainingArgs, rank: int, world: int, consumed
     return PackedBatchLoader(train, sampler, ca["sequence_length"])
 
 
+def make_megatron_val_dataloader(args: TrainingArgs, rank: int, world: int):
+    """validation split of the same stores (data/megatron/__init__.py:170-190): a fresh pass from sample 0 every evaluation"""
+    from .data import MegatronBatchSampler, PackedBatchLoader, build_gpt_datasets, get_train_val_test_samples
+
+    ds, tp = args.datasets[0], args.training_parameters
+    ca = ds.class_args
+    if ds.class_name != "MegatronDataset" or not ca.get("eval_steps") or not tp.eval_interval:
+        return None
+    sizes = get_train_val_test_samples(tp.num_training_steps, tp.micro_batch_size, tp.gradient_accumulation_steps,
+                                       tp.eval_interval, ca.get("eval_steps"), world)
+    _, val, _ = build_gpt_datasets(ca["data_path"], ca.get("split", "100,0,0"), sizes, ca["sequence_length"],
+                                   ca.get("seed", args.random_args.seed))
+    if val is None:
+        return None
+    return lambda: iter(PackedBatchLoader(val, MegatronBatchSampler(len(val), 0, tp.micro_batch_size, world, rank),
+                                          ca["sequence_length"]))
+
+
+def evaluate(val_loader_factory, model, eval_steps: int, world: int) -> float | None:
+    """pretrain.py:223-296: mean loss over `eval_steps` validation micro-batches (no activations kept), averaged over ranks"""
+    if val_loader_factory is None:
+        return None
+    model.eval()
+    it = val_loader_factory()
+    total, n = None, 0
+    with torch.no_grad():
+        for _ in range(eval_steps):
+            try:
+                batch = next(it)
+            except StopIteration:
+                break
+            loss = model(batch).detach().float()
+            total = loss if total is None else total + loss
+            n += 1
+    model.train()
+    if n == 0:
+        return None
+    mean = total / n
+    if world > 1 and dist.is_initialized():
+        dist.all_reduce(mean, op=dist.ReduceOp.AVG)
+    return float(mean.item())
+
+
 def make_dataloader(args: TrainingArgs, model, rank: int, world: int = 1, consumed_samples: int = 0):
     ds = args.datasets[0]
     if ds.class_name == "MegatronDataset":
@@ -124,6 +167,16 @@ def train(args: TrainingArgs, model, optimizer, scheduler, dataloader, rank: int
     tflop_per_step = get_model_tflops(model.config, tp.micro_batch_size * tp.gradient_accumulation_steps, seq)
     samples_per_step = tp.micro_batch_size * tp.gradient_accumulation_steps * world
     save_args = getattr(args, "save_args", None)
+    val_factory = make_megatron_val_dataloader(args, rank, world) if tp.eval_during_training else None
+    eval_steps = int(args.datasets[0].class_args.get("eval_steps") or 0)
+
+    def run_eval(at_step: int) -> None:
+        v = evaluate(val_factory, model, eval_steps, world)
+        if v is not None and rank == 0:
+            print(f"step {at_step}: val loss {v:.4f}", flush=True)
+
+    if val_factory is not None:
+        run_eval(starting_iteration)  # pretrain.py:121-122: evaluate before the first step
     losses = []
     t0 = time.perf_counter()
     for step in range(starting_iteration + 1, tp.num_training_steps + 1):
@@ -135,6 +188,8 @@ def train(args: TrainingArgs, model, optimizer, scheduler, dataloader, rank: int
             dt = (time.perf_counter() - t0) / (step - starting_iteration)
             print(f"step {step}: loss {loss:.4f} grad_norm {grad_norm:.4f} lr {scheduler.get_last_lr()[0]:.3e} "
                   f"step_time {dt:.3f}s FLOPS {tflop_per_step / dt:.1f} TFLOP/s/GPU", flush=True)
+        if val_factory is not None and step % tp.eval_interval == 0:
+            run_eval(step)
         if save_args is not None and (step % save_args.save_interval == 0 or step == tp.num_training_steps):
             save_checkpoint(args, model, optimizer, scheduler, None, None, step,
                             metadata={"consumed_samples": step * samples_per_step})

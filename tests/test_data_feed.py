@@ -181,3 +181,32 @@ def test_yaml_megatron_dataset_feeds_the_training_loop_contract():
     # resuming at consumed_samples = 2 steps * (mbs * world) reproduces step 2 onwards
     it = make_dataloader(args, None, 0, world=2, consumed_samples=2 * 2 * 2)
     assert torch.equal(next(it)["text"], seen[0][2])
+
+
+def test_validation_split_loader_and_evaluate_contract():
+    """pretrain.evaluate: mean of the per-batch losses over eval_steps batches of the validation split, model back in train mode"""
+    from dolomite_engine_b200.arguments import get_args_from_dict, load_yaml
+    from dolomite_engine_b200.pretrain import evaluate, make_megatron_val_dataloader
+
+    d = load_yaml(os.path.join(os.path.dirname(HERE), "configs", "c1_tiny.yml"))
+    d["datasets"] = [dict(class_name="MegatronDataset", data_name="Megatron",
+                          class_args=dict(data_path=[os.path.join(GOLD, "corpus_a")], split="70,30,0", sequence_length=16,
+                                          eval_steps=3, seed=7))]
+    d["training_parameters"].update(num_training_steps=4, micro_batch_size=2, gradient_accumulation_steps=1, eval_interval=2,
+                                    eval_during_training=True)
+    args = get_args_from_dict(d)
+    factory = make_megatron_val_dataloader(args, rank=0, world=1)
+    assert factory is not None
+    first = [b["text"].clone() for _, b in zip(range(3), factory())]
+    again = [b["text"].clone() for _, b in zip(range(3), factory())]
+    assert all(torch.equal(a, b) for a, b in zip(first, again))  # every evaluation restarts at sample 0
+
+    class Fake(torch.nn.Module):
+        def forward(self, batch):
+            return batch["text"].float().mean()
+
+    m = Fake()
+    v = evaluate(factory, m, 3, 1)
+    assert m.training and abs(v - float(torch.stack([t.float().mean() for t in first]).mean())) < 1e-4
+    d["datasets"][0]["class_args"]["split"] = "100,0,0"
+    assert make_megatron_val_dataloader(get_args_from_dict(d), 0, 1) is None
