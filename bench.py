@@ -199,8 +199,6 @@ def run_ours(args) -> None:
     local = int(os.environ.get("LOCAL_RANK", 0))
     if os.environ.get("DOLO_ATTN_BWD"):
         K.set_option("attn_bwd_version", int(os.environ["DOLO_ATTN_BWD"]))
-    if os.environ.get("DOLO_NO_SWIGLU_FUSION"):  # A/B switch for the fused c_fc + SwiGLU epilogue
-        K.fuse_swiglu_into_gemm = False
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)

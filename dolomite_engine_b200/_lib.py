@@ -34,7 +34,6 @@ SIGNATURES: dict[str, tuple] = {
     "dolomite_b200_rmsnorm_bwd_workspace_bytes": (_L, [_I]),
     "dolomite_b200_rmsnorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
     "dolomite_b200_rope_qk_inplace": (_I, [_P, _L, _L, _I, _I, _I, _P, _P, _P, _I, _L, _I, _P]),
-    "dolomite_b200_gemm_bf16_swiglu": (_I, [_P, _L, _P, _L, _P, _P, _L, _P, _L, _L, _L, _L, _P]),
     "dolomite_b200_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P]),
     "dolomite_b200_layernorm_bwd_workspace_bytes": (_L, [_I]),
     "dolomite_b200_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
@@ -110,7 +109,7 @@ def check(rc: int, what: str = "") -> None:
 # kernels launched per successful call of each entry point (for bench.py's `gpu_launches` accounting)
 KERNELS_PER_CALL = {
     "dolomite_b200_rmsnorm_fwd": 1, "dolomite_b200_rmsnorm_bwd": 2, "dolomite_b200_rope_qk_inplace": 1,
-    "dolomite_b200_gemm_bf16_swiglu": 1, "dolomite_b200_layernorm_fwd": 1, "dolomite_b200_layernorm_bwd": 3, "dolomite_b200_gelu_fwd": 1,
+    "dolomite_b200_layernorm_fwd": 1, "dolomite_b200_layernorm_bwd": 3, "dolomite_b200_gelu_fwd": 1,
     "dolomite_b200_gelu_bwd": 1, "dolomite_b200_swiglu_fwd": 1, "dolomite_b200_swiglu_bwd": 1, "dolomite_b200_swiglu_bwd_bias": 1,
     "dolomite_b200_embedding_fwd": 1,
     "dolomite_b200_embedding_bwd": 1, "dolomite_b200_cross_entropy_fwd_bwd": 3, "dolomite_b200_colsum_accum": 1,

@@ -30,11 +30,6 @@ constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BUF
 static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 
 struct GemmParams {
-    alignas(64) CUtensorMap tmap_e;  // second output (SwiGLU mode: act [M, F]); unused otherwise
-    // SwiGLU mode (swiglu_f = F > 0, CTA-pair kernel only): B = c_fc weight [2F, K]; the leader CTA stages the 128 "up" rows
-    // [128 n, +128) and the peer the matching "gate" rows [F + 128 n, +128), so accumulator columns 0..127 / 128..255 of a
-    // tile are up / gate of the same 128 features and the epilogue emits fc (both halves) AND act = up * silu(gate)
-    int swiglu_f;
     void* D;
     const void* C;
     const __nv_bfloat16* bias;
@@ -116,7 +111,7 @@ __device__ __forceinline__ TileInfo tile_info(int t, const GemmParams& p) {
 template <bool A_MN, bool B_MN, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ GemmParams p) {
+                     const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
     constexpr int NSTAGE = CTA2 ? 6 : STAGES;
     constexpr int B_BYTES = CTA2 ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
     constexpr int STG_BYTES = A_STAGE_BYTES + B_BYTES;
@@ -181,9 +176,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     if constexpr (CTA2) {
                         // the leader's barrier collects the bytes of both CTAs (its own arrive carries the expectation)
                         if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STG_BYTES);
-                        // this CTA's half of the B tile (SwiGLU mode: leader = up rows, peer = gate rows of the same features)
-                        const int n_row = p.swiglu_f > 0 ? (cta_rank ? p.swiglu_f : 0) + n_blk * (BN / 2)
-                                                         : n_blk * BN + cta_rank * (BN / 2);
+                        const int n_row = n_blk * BN + cta_rank * (BN / 2);  // this CTA's half of the B tile
                         if (!A_MN) {
                             tma_load_2d_2cta(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
                         } else {
@@ -281,61 +274,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const bool row_ok = row < p.M;
             const int col0 = n_blk * BN;
 
-            if (p.swiglu_f > 0) {
-                // six 64-column slabs per tile: for each half s of the 128 features: fc_up, fc_gate, act.  The arithmetic is
-                // that of the unfused path (bf16 fc = alpha * (acc + bias); act = up * bf16(gate * sigmoid(gate))): bit-identical
-                const int F = p.swiglu_f;
-                const int ucol0 = n_blk * (BN / 2);
-#pragma unroll 1
-                for (int step = 0; step < 6; ++step) {
-                    const int sl = step / 3, kind = step - sl * 3;  // kind 0: up, 1: gate, 2: act
-                    uint8_t* buf = smem_epi + epi_buf * EPI_SLAB_BYTES;
-                    if (et == 0) tma_store_wait_read<EPI_BUFS - 1>();
-                    named_bar_sync(1, 128);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint32_t ru[32], rg[32];
-                        if (kind != 1) tmem_ld32(t_addr + sl * 64 + h * 32, ru);
-                        if (kind != 0) tmem_ld32(t_addr + BN / 2 + sl * 64 + h * 32, rg);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const int cb = ucol0 + sl * 64 + h * 32 + c * 8;  // feature index of the first of 8 columns
-                            float o[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float u = 0.f, g = 0.f;
-                                if (kind != 1) {
-                                    u = __uint_as_float(ru[c * 8 + j]);
-                                    if (p.bias != nullptr) u += __bfloat162float(p.bias[cb + j]);
-                                    u = bf16_round(u * p.alpha);
-                                }
-                                if (kind != 0) {
-                                    g = __uint_as_float(rg[c * 8 + j]);
-                                    if (p.bias != nullptr) g += __bfloat162float(p.bias[F + cb + j]);
-                                    g = bf16_round(g * p.alpha);
-                                }
-                                o[j] = kind == 0 ? u : (kind == 1 ? g : u * bf16_round(g * __fdividef(1.f, 1.f + __expf(-g))));
-                            }
-                            uint4 v;
-                            v.x = pack_bf16(o[0], o[1]);
-                            v.y = pack_bf16(o[2], o[3]);
-                            v.z = pack_bf16(o[4], o[5]);
-                            v.w = pack_bf16(o[6], o[7]);
-                            const int chunk = h * 4 + c;
-                            *reinterpret_cast<uint4*>(buf + et * 128 + ((chunk ^ (et & 7)) << 4)) = v;
-                        }
-                    }
-                    fence_proxy_async_smem();
-                    named_bar_sync(1, 128);
-                    if (et == 0) {
-                        if (kind == 2) tma_store_2d(&p.tmap_e, buf, ucol0 + sl * 64, m_blk * BM);
-                        else tma_store_2d(&tmap_d, buf, (kind == 1 ? F : 0) + ucol0 + sl * 64, m_blk * BM);
-                        tma_store_commit();
-                    }
-                    epi_buf ^= 1;
-                }
-            } else if (p.tma_store) {
+            if (p.tma_store) {
                 // 4 slabs of 64 columns: regs -> swizzled smem -> TMA store
 #pragma unroll 1
                 for (int slab = 0; slab < BN / 64; ++slab) {
@@ -574,8 +513,6 @@ static int gemm_impl(const void* A, int64_t lda, int a_mn_major, const void* B, 
         }
     }
     GemmParams p;
-    p.swiglu_f = 0;
-    p.tmap_e = ta;  // unused
     p.D = D;
     p.C = C;
     p.bias = static_cast<const __nv_bfloat16*>(bias);
@@ -671,64 +608,4 @@ extern "C" int dolomite_b200_gemm_bf16_grouped_k(const void* A, int64_t lda, con
     // A, B are both MN-major views of [K_max, M] / [K_max, N] row-major activations; D[g] (+)= A_g^T B_g in fp32
     return gemm_impl(A, lda, 1, B, ldb, 1, D, ldd, 1, beta != 0.f ? D : nullptr, ldd, alpha, beta, nullptr, M, N, K_max, 0,
                      stream, ga);
-}
-
-
-// c_fc GEMM with the SwiGLU activation fused into the epilogue (gpt_dolomite/mlp.py:45-50, activations/glu.py:26-28):
-//   fc  [M, 2F] = x W^T + b            (kept: the backward needs it)
-//   act [M, F]  = fc[:, :F] * silu(fc[:, F:])
-// one pass instead of GEMM + a 6*M*F-byte elementwise kernel.  CTA-pair kernel only (M >= 256), F % 128 == 0.
-extern "C" int dolomite_b200_gemm_bf16_swiglu(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias,
-                                              void* FC, int64_t ldfc, void* ACT, int64_t ldact, int64_t M, int64_t F,
-                                              int64_t K, void* stream) {
-    DOLO_REQUIRE(M >= 2 * BM, "gemm_swiglu: needs M >= %d rows (CTA-pair kernel)", 2 * BM);
-    DOLO_REQUIRE(F > 0 && F % (BN / 2) == 0, "gemm_swiglu: F=%lld must be a positive multiple of %d", (long long)F, BN / 2);
-    DOLO_REQUIRE(K > 0 && K % 8 == 0, "gemm_swiglu: K=%lld must be a positive multiple of 8", (long long)K);
-    DOLO_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldfc % 8 == 0 && ldact % 8 == 0, "gemm_swiglu: leading dimensions must keep 16-byte alignment");
-    DOLO_REQUIRE(M < (1ll << 31) && F < (1ll << 30) && K < (1ll << 31), "gemm_swiglu: dimension too large");
-    CUtensorMap ta, tb, td;
-    GemmParams p;
-    uint64_t dims[2], strides[2];
-    uint32_t box[2];
-    strides[0] = 2;
-    dims[0] = uint64_t(K); dims[1] = uint64_t(M); strides[1] = uint64_t(lda) * 2; box[0] = BK; box[1] = BM;
-    int rc = dolo_make_tmap(&ta, A, 2, 2, dims, strides, box, DOLO_SW_128);
-    if (rc) return rc;
-    dims[0] = uint64_t(K); dims[1] = uint64_t(2 * F); strides[1] = uint64_t(ldw) * 2; box[0] = BK; box[1] = BN / 2;
-    rc = dolo_make_tmap(&tb, W, 2, 2, dims, strides, box, DOLO_SW_128);
-    if (rc) return rc;
-    dims[0] = uint64_t(2 * F); dims[1] = uint64_t(M); strides[1] = uint64_t(ldfc) * 2; box[0] = 64; box[1] = BM;
-    rc = dolo_make_tmap(&td, FC, 2, 2, dims, strides, box, DOLO_SW_128);
-    if (rc) return rc;
-    dims[0] = uint64_t(F); dims[1] = uint64_t(M); strides[1] = uint64_t(ldact) * 2; box[0] = 64; box[1] = BM;
-    rc = dolo_make_tmap(&p.tmap_e, ACT, 2, 2, dims, strides, box, DOLO_SW_128);
-    if (rc) return rc;
-    p.swiglu_f = int(F);
-    p.D = FC;
-    p.C = nullptr;
-    p.bias = static_cast<const __nv_bfloat16*>(bias);
-    p.ldd = ldfc;
-    p.ldc = 0;
-    p.M = int(M);
-    p.N = int(F);
-    p.K = int(K);
-    p.alpha = 1.f;
-    p.beta = 0.f;
-    p.d_is_f32 = 0;
-    p.tma_store = 1;
-    p.num_m = int((M + 2 * BM - 1) / (2 * BM));
-    p.num_n = int(F / (BN / 2));
-    p.num_kb = int((K + BK - 1) / BK);
-    {
-        const int64_t panel_bytes = int64_t(2 * BM) * K * 2;
-        int64_t gm = (24ll << 20) / (panel_bytes > 0 ? panel_bytes : 1);
-        p.group_m = int(gm < 4 ? 4 : (gm > 64 ? 64 : gm));
-    }
-    p.grouped = 0;
-    p.m_tile_group = nullptr;
-    p.b_group_rows = 0;
-    p.group_k_offsets = nullptr;
-    p.num_groups = 1;
-    p.d_group_stride = 0;
-    return launch_gemm<false, false>(ta, tb, td, p, static_cast<cudaStream_t>(stream), true);
 }

@@ -356,12 +356,8 @@ class DolomiteEngine:
 
             h, moe_saved = moe.forward(self, u, p, ln2, h_mid, m_res)
             return h, (x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, moe_saved)
-        w_fc, b_fc = u.views[p + "mlp.c_fc.weight"], u.views.get(p + "mlp.c_fc.bias")
-        if self.is_glu and K.gemm_swiglu_supported(ln2.shape[0], cfg.n_inner, cfg.n_embd):
-            fc, act = K.gemm_swiglu(ln2, w_fc, b_fc)  # SwiGLU in the GEMM epilogue: fc is not re-read from HBM
-        else:
-            fc = K.gemm(ln2, w_fc, bias=b_fc)
-            act = K.swiglu_fwd(fc) if self.is_glu else K.gelu_fwd(fc)
+        fc = K.gemm(ln2, u.views[p + "mlp.c_fc.weight"], bias=u.views.get(p + "mlp.c_fc.bias"))
+        act = K.swiglu_fwd(fc) if self.is_glu else K.gelu_fwd(fc)
         h = K.gemm(act, u.views[p + "mlp.c_proj.weight"], bias=u.views.get(p + "mlp.c_proj.bias"), c=h_mid,
                    alpha=m_res, beta=1.0)
         return h, (x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, fc, act)

@@ -91,32 +91,6 @@ def rope_qk_inplace(qkv, n_groups: int, q_per_group: int, head_dim: int, cos, si
 # ------------------------------------------------------------------------------------------------
 # SwiGLU (activations/glu.py:26-28)
 # ------------------------------------------------------------------------------------------------
-fuse_swiglu_into_gemm = True  # c_fc forward: GEMM epilogue emits fc and act in one pass when the shape allows it
-
-
-def gemm_swiglu_supported(M: int, F: int, K: int) -> bool:
-    return fuse_swiglu_into_gemm and M >= 256 and F % 128 == 0 and K % 8 == 0
-
-
-def gemm_swiglu(x, w, bias=None):
-    """(fc [M, 2F], act [M, F]) = c_fc + SwiGLU in one kernel; bit-identical to gemm(x, w, bias) followed by swiglu_fwd"""
-    _req(x, _BF16, "x"), _req(w, _BF16, "w")
-    M, Kd = x.shape
-    F2 = w.shape[0]
-    assert w.shape[1] == Kd and F2 % 2 == 0 and x.stride(1) == 1 and w.stride(1) == 1
-    fc = torch.empty(M, F2, dtype=_BF16, device=x.device)
-    act = torch.empty(M, F2 // 2, dtype=_BF16, device=x.device)
-    if gemm_timer is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-    _lib.call("dolomite_b200_gemm_bf16_swiglu", x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), fc.data_ptr(),
-              fc.stride(0), act.data_ptr(), act.stride(0), M, F2 // 2, Kd, _stream())
-    if gemm_timer is not None:
-        e1.record()
-        gemm_timer.append((2.0 * M * F2 * Kd, e0, e1))
-    return fc, act
-
-
 def layernorm_fwd(x, w, b, eps: float, out=None):
     """y = bf16((x - mean) * rstd * w + b) -> (y, mean, rstd)"""
     _req(x, _BF16, "x"), _req(w, _BF16, "w")

@@ -69,12 +69,6 @@ int dolomite_b200_rope_qk_inplace(void* qkv, int64_t row_stride, int64_t T, int 
                                   int head_dim, const void* cos_table, const void* sin_table, const void* position_ids,
                                   int position_ids_is_int64, int64_t n_positions, int inverse, void* stream);
 
-/* c_fc GEMM with the SwiGLU activation fused into the epilogue (gpt_dolomite/mlp.py:45-50 + activations/glu.py:26-28):
- *   fc[M, 2F] = x W^T + bias (kept for backward),  act[M, F] = fc[:, :F] * silu(fc[:, F:]); bit-identical to
- *   dolomite_b200_gemm_bf16 followed by dolomite_b200_swiglu_fwd.  x [M, K], W [2F, K] K-major bf16; M >= 256, F % 128 == 0. */
-int dolomite_b200_gemm_bf16_swiglu(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* FC,
-                                   int64_t ldfc, void* ACT, int64_t ldact, int64_t M, int64_t F, int64_t K, void* stream);
-
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm -- normalization_function "layernorm" = torch.nn.LayerNorm
  * (hf_models/modeling_utils/normalization/layernorm/__init__.py): fp32 statistics, one rounding to bf16:

@@ -353,21 +353,3 @@ def test_empty_and_single_row_inputs_are_accepted():
         ids = torch.zeros(T, dtype=torch.int64, device="cuda")
         assert tuple(k.embedding_fwd(ids, torch.randn(16, 64, device="cuda").bfloat16()).shape) == (T, 64)
     torch.cuda.synchronize()
-
-
-@pytest.mark.parametrize("M,F,Kd,bias", [(256, 128, 64, True), (1000, 384, 320, True), (4096, 1024, 2560, False), (777, 256, 72, True)])
-def test_gemm_with_fused_swiglu_epilogue_is_bit_identical_to_the_unfused_path(M, F, Kd, bias):
-    """dolomite_b200_gemm_bf16_swiglu == gemm + swiglu_fwd bit for bit (fc and act), incl. ragged M and partial K blocks"""
-    g = torch.Generator().manual_seed(4)
-    x = bf(torch.randn(M, Kd, generator=g)).cuda()
-    w = bf(torch.randn(2 * F, Kd, generator=g) * 0.1).cuda()
-    b = bf(torch.randn(2 * F, generator=g)).cuda() if bias else None
-    assert K().gemm_swiglu_supported(M, F, Kd)
-    fc, act = K().gemm_swiglu(x, w, b)
-    fc_ref = K().gemm(x, w, bias=b)
-    act_ref = K().swiglu_fwd(fc_ref)
-    assert torch.equal(fc, fc_ref)
-    assert torch.equal(act, act_ref)
-    ref = O.activation((x.float() @ w.float().T + (b.float() if bias else 0)).cpu(), "swiglu")
-    assert rel_l2(act, ref) < 1e-2
-    assert not K().gemm_swiglu_supported(128, F, Kd) and not K().gemm_swiglu_supported(M, 96, Kd)
