@@ -18,6 +18,9 @@ pytestmark = pytest.mark.gpu
 GPU_CONFIGS = dict(CONFIGS)  # incl. mqa_gelu (tanh-GELU, non-GLU MLP) and bigcode (LayerNorm + learned positions + MQA)
 GPU_CONFIGS["hd80_bias"] = dict(vocab_size=1024, n_positions=512, n_embd=320, n_layer=2, n_head=4, n_inner=640,
                                 attention_head_type="mha", add_bias=True)
+GPU_CONFIGS["yarn_rope"] = dict(vocab_size=1024, n_positions=512, n_embd=256, n_layer=2, n_head=4, n_inner=512,
+                                attention_head_type="mha", add_bias=False,
+                                rope_scaling={"type": "yarn", "factor": 4.0, "original_max_position_embeddings": 128})
 GPU_CONFIGS["hd128_gqa"] = dict(vocab_size=1024, n_positions=512, n_embd=512, n_layer=1, n_head=4, num_key_value_heads=2,
                                 n_inner=1024, attention_head_type="gqa", add_bias=False, tie_word_embeddings=False)
 
