@@ -1,0 +1,61 @@
+"""SFT feed (decoder-only) against fixtures produced by the reference's `collate_fn` (data/utils.py:8-92) and
+`BaseDataset.get_input_output_token_ids` (data/base.py:84-121) -- tests/golden/finetuning_feed.json, written by
+oracle/pin_finetuning_feed.py in the build container.  Integer work: exact."""
+import json
+import os
+
+import torch
+
+from dolomite_engine_b200.data.finetuning import JSONLinesSFTDataset, batches, build_example, collate
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def toy_tokenize(text):
+    return [3 + (sum(map(ord, w)) % 97) for w in text.split()]
+
+
+def _fx():
+    return json.load(open(os.path.join(HERE, "golden", "finetuning_feed.json")))
+
+
+def test_examples_match_reference_tokenisation_and_truncation():
+    fx = _fx()
+    for group in fx["examples"]:
+        got = [build_example(toy_tokenize, 2, i, o, group["max_input_tokens"], group["max_output_tokens"]) for i, o in fx["raw"]]
+        assert got == group["examples"]
+
+
+def test_collate_matches_reference_padding_free_and_left_padded():
+    fx = _fx()
+    by_limits = {(g["max_input_tokens"], g["max_output_tokens"]): g["examples"] for g in fx["examples"]}
+    for case in fx["collate"]:
+        exs = by_limits[(case["max_input_tokens"], case["max_output_tokens"])]
+        got = collate(exs, 2, case["padding_free"], case["loss_mask"])
+        want = case["result"]
+        assert set(got) == set(want)
+        for k, v in want.items():
+            g = got[k].tolist() if torch.is_tensor(got[k]) else got[k]
+            assert g == v, (case["padding_free"], case["loss_mask"], k)
+        if not case["padding_free"]:
+            assert got["input_ids"].dtype == torch.long and got["attention_mask"].sum(1).tolist() == [len(e["input"]) for e in exs]
+
+
+def test_jsonl_dataset_and_rank_sharded_batches(tmp_path):
+    rows = [{"input": f"question number {i} please", "output": "answer " * (1 + i % 3)} for i in range(11)]
+    with open(tmp_path / "train.jsonl", "w") as f:
+        for r in rows:
+            f.write(json.dumps(r) + "\n")
+    ds = JSONLinesSFTDataset(str(tmp_path), toy_tokenize, 2, input_format="Q: __input__\nA:", max_output_tokens=3)
+    assert len(ds) == 11 and all(len(e["output"]) <= 3 and e["output"][-1] == 2 for e in ds.examples)
+    assert ds[0]["input"][: len(toy_tokenize("Q: question number 0 please A:"))] == toy_tokenize("Q: question number 0 please\nA:")
+    seen = []
+    for rank in range(2):
+        it = batches(ds, 2, 2, True, rank=rank, world_size=2, seed=5, infinite=False)
+        got = list(it)
+        assert all(len(b["input_ids"]) == 2 and len(b["labels"]) == 2 for b in got)
+        seen.append([tuple(x) for b in got for x in b["input_ids"]])
+    assert not set(seen[0]) & set(seen[1])  # ranks see disjoint examples
+    padded = next(batches(ds, 3, 2, False, seed=5))
+    assert padded["input_ids"].shape == padded["attention_mask"].shape == padded["labels"].shape
+    assert (padded["labels"][padded["attention_mask"] == 0] == -100).all()
