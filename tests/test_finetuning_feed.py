@@ -59,3 +59,26 @@ def test_jsonl_dataset_and_rank_sharded_batches(tmp_path):
     padded = next(batches(ds, 3, 2, False, seed=5))
     assert padded["input_ids"].shape == padded["attention_mask"].shape == padded["labels"].shape
     assert (padded["labels"][padded["attention_mask"] == 0] == -100).all()
+
+
+def test_finetune_yaml_to_batches(tmp_path):
+    """finetune.make_sft_dataloader: YAML dataset entry (formats, token limits, loss mask) -> collated micro-batches"""
+    from dolomite_engine_b200.arguments import get_args_from_dict, load_yaml
+    from dolomite_engine_b200.finetune import make_sft_dataloader
+
+    with open(tmp_path / "d.jsonl", "w") as f:
+        for i in range(9):
+            f.write(json.dumps({"input": f"prompt {i} a b c d e", "output": f"reply {i} x y"}) + "\n")
+    d = load_yaml(os.path.join(os.path.dirname(HERE), "configs", "c1_tiny.yml"))
+    d["datasets"] = [dict(class_name="JSONLinesDataset", data_name="sft", class_args=dict(data_path=str(tmp_path)),
+                          input_format="Q: __input__ A:", output_format="__output__", max_input_tokens=5, max_output_tokens=3)]
+    d["tuning_args"] = dict(tuning_method="full_finetuning")
+    d["model_args"]["use_padding_free_transformer"] = False
+    d["training_parameters"].update(micro_batch_size=4, loss_mask="output_only")
+    args = get_args_from_dict(d)
+    it = make_sft_dataloader(args, toy_tokenize, 2, rank=0, world=1)
+    b = next(it)
+    assert set(b) == {"input_ids", "attention_mask", "labels"} and b["input_ids"].shape[0] == 4
+    # prompt cut to 5 tokens, reply to 2 + eos: every row has exactly 8 real tokens, labels only on the last 3
+    assert b["attention_mask"].sum(1).tolist() == [8] * 4 and ((b["labels"] != -100).sum(1) == 3).all()
+    assert (b["labels"][:, -1] == 2).all()
