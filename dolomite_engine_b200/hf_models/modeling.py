@@ -61,6 +61,24 @@ class _EngineFunction(torch.autograd.Function):
         return (None,) * 9
 
 
+def _pad_packed_stream(input_ids, position_ids, cu_seqlens, shift_labels, multiple: int = 8):
+    """The token count is the contraction length of every weight-gradient GEMM and must be a multiple of 8 (16-byte rows of
+    the MN-major operands).  Pretraining streams are (mbs * seq); finetuning streams are not, so a trailing dummy document
+    of < 8 tokens is appended: it attends only to itself and its labels are ignore_index, i.e. it adds nothing to the loss
+    or to any gradient.  Returns the padded tensors and the number of real tokens."""
+    T = int(input_ids.numel())
+    pad = (-T) % multiple
+    if pad == 0:
+        return input_ids, position_ids, cu_seqlens, shift_labels, T
+    dev = input_ids.device
+    input_ids = torch.cat([input_ids, torch.zeros(pad, dtype=input_ids.dtype, device=dev)])
+    position_ids = torch.cat([position_ids, torch.arange(pad, dtype=position_ids.dtype, device=dev)])
+    cu_seqlens = torch.cat([cu_seqlens, torch.tensor([T + pad], dtype=cu_seqlens.dtype, device=dev)])
+    if shift_labels is not None:
+        shift_labels = torch.cat([shift_labels, torch.full((pad,), -100, dtype=shift_labels.dtype, device=dev)])
+    return input_ids, position_ids, cu_seqlens, shift_labels, T
+
+
 class DolomitePreTrainedModel(nn.Module):
     config_class = CommonConfig
     base_model_prefix = "transformer"
@@ -164,11 +182,13 @@ class DolomitePreTrainedModel(nn.Module):
             shift_labels[:-1] = labels[1:]
             drop = (cu_seqlens[1:-1] - 1).long()
             shift_labels[drop] = -100
+        input_ids, position_ids, cu_seqlens, shift_labels, T_real = _pad_packed_stream(input_ids, position_ids, cu_seqlens,
+                                                                                       shift_labels)
         out = _EngineFunction.apply(self._anchor, self, input_ids, position_ids, cu_seqlens, int(max_seqlen), shift_labels, -100, torch.is_grad_enabled())
         if shift_labels is not None:
             result = CausalLMOutputWithPast(loss=out, logits=None)
         else:
-            result = CausalLMOutputWithPast(loss=None, logits=out)
+            result = CausalLMOutputWithPast(loss=None, logits=out[:T_real])
         if not return_dict:
             return tuple(v for v in (result.loss, result.logits) if v is not None)
         return result
@@ -214,12 +234,13 @@ class DolomitePreTrainedModel(nn.Module):
             nxt_valid[:, :-1] = mask[:, 1:]
             nxt = torch.where(nxt_valid & mask, nxt, torch.full_like(nxt, -100))
             shift_labels = nxt.reshape(-1)[keep].contiguous()
-        out = _EngineFunction.apply(self._anchor, self, ids_p, pos_p, cu, int(max_seqlen), shift_labels, -100, torch.is_grad_enabled())
+        ids_p, pos_p, cu, shift_labels, T_real = _pad_packed_stream(ids_p, pos_p, cu, shift_labels)
+        out = _EngineFunction.apply(self._anchor, self, ids_p, pos_p, cu, int(max(max_seqlen, 1)), shift_labels, -100, torch.is_grad_enabled())
         if shift_labels is not None:
             result = CausalLMOutputWithPast(loss=out, logits=None)
         else:
             full = out.new_zeros(B * S, out.shape[-1])
-            full[keep] = out
+            full[keep] = out[:T_real]
             result = CausalLMOutputWithPast(loss=None, logits=full.view(B, S, -1))
         if not return_dict:
             return tuple(v for v in (result.loss, result.logits) if v is not None)
