@@ -11,3 +11,4 @@ from .gpt_dataset import (
     get_train_val_test_samples,
 )
 from .indexed_dataset import MMapIndexedDataset, MMapIndexedDatasetBuilder, get_bin_path, get_idx_path, optimal_dtype
+from .fim import FIMSpec, HFTokenizerCodec, apply_fim

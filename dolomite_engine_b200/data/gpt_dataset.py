@@ -158,9 +158,10 @@ class GPTDataset:
     """Samples of S+1 tokens cut from the shuffled, epoch-repeated document stream (gpt_dataset.py:30-400)"""
 
     def __init__(self, indexed_dataset: MMapIndexedDataset, indexed_indices: np.ndarray, num_samples: int,
-                 sequence_length: int, random_seed: int = 1234, fim_rate: float = 0.0):
-        if fim_rate != 0:
-            raise NotImplementedError("fill-in-the-middle augmentation is not part of the B200 data feed")
+                 sequence_length: int, random_seed: int = 1234, fim=None):
+        # fim: data.fim.FIMSpec or None; its random stream is seeded like the reference's (gpt_dataset.py:55)
+        self.fim = fim if (fim is not None and fim.rate != 0) else None
+        self.np_rng = np.random.RandomState(seed=random_seed)
         self.indexed_dataset = indexed_dataset
         self.indexed_indices = np.asarray(indexed_indices)
         self.num_samples = int(num_samples)
@@ -214,6 +215,10 @@ class GPTDataset:
     def __getitem__(self, idx: int) -> dict[str, np.ndarray]:
         tok = self.indexed_dataset.tokens
         text = np.concatenate([tok[o : o + n] for o, n in self.sample_parts(idx)]).astype(np.int64)
+        if self.fim is not None:
+            from .fim import apply_fim
+
+            text = apply_fim(text, self.np_rng, self.fim)
         return {"text": text}
 
 
@@ -244,7 +249,7 @@ class BlendedDataset:
         return {"dataset_id": int(self.dataset_index[idx]), **ds[j]}
 
 
-def build_gpt_datasets(data_path, split: str, sizes: tuple[int, int, int], sequence_length: int, seed: int):
+def build_gpt_datasets(data_path, split: str, sizes: tuple[int, int, int], sequence_length: int, seed: int, fim=None):
     """Options 1/2 of data/megatron/__init__.py:93-101 (`data_path` = one prefix, or [w1, prefix1, w2, prefix2, ...]):
     -> (train, val, test), each a GPTDataset / BlendedDataset / None (blended_megatron_dataset_builder.py:61-226)"""
     if isinstance(data_path, str):
@@ -260,7 +265,7 @@ def build_gpt_datasets(data_path, split: str, sizes: tuple[int, int, int], seque
             if split_v[i] == 0.0 or want[i] == 0:
                 out.append(None)
             else:
-                out.append(GPTDataset(ids, np.arange(bounds[i], bounds[i + 1], dtype=dt), want[i], sequence_length, seed))
+                out.append(GPTDataset(ids, np.arange(bounds[i], bounds[i + 1], dtype=dt), want[i], sequence_length, seed, fim=fim))
         return out
 
     if len(data_path) == 1:
@@ -343,6 +348,13 @@ class PackedBatchLoader:
                 raise RuntimeError(f"gather_rows failed ({rc}): sample parts do not add up to {self.row_len} tokens")
             if tmp is not dst:
                 dst[rws] = tmp
+        # fill-in-the-middle rewrites rows on the host, in row order (each dataset owns its random stream)
+        for r, idx in enumerate(rows):
+            ds, _ = self.dataset.locate(idx) if hasattr(self.dataset, "locate") else (self.dataset, idx)
+            if getattr(ds, "fim", None) is not None:
+                from .fim import apply_fim
+
+                dst[r] = apply_fim(dst[r].copy(), ds.np_rng, ds.fim)
         return out
 
     def __iter__(self):

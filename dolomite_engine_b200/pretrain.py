@@ -2,9 +2,9 @@
 (pretrain.py:60-371) for the data-parallel hot path: args -> process group -> model wrapper -> sharded wrap ->
 optimizer / scheduler -> train loop over `train_step`.
 
-The data layer (Megatron mmap datasets) is out of scope; the loop consumes any iterator
-of `{"text": LongTensor[mbs, seq+1]}` batches -- exactly what `GPTDataset` emits (gpt_dataset.py:83-98) -- and ships
-`SyntheticPackedDataset` (class_name in the YAML) that fabricates such batches with the seeds of SURVEY section 8d.
+The loop consumes any iterator of `{"text": LongTensor[mbs, seq+1]}` batches -- exactly what `GPTDataset` emits
+(gpt_dataset.py:83-98).  `class_name: MegatronDataset` reads Megatron .bin/.idx token stores through `data/` (SURVEY.md
+section 8f rank 2); `class_name: SyntheticPackedDataset` fabricates batches with the seeds of SURVEY section 8d.
 """
 
 from __future__ import annotations
@@ -84,7 +84,26 @@ def build(args: TrainingArgs):
     return model, optimizer, scheduler, (rank, world, local)
 
 
-def make_megatron_dataloader(args: TrainingArgs, rank: int, world: int, consumed_samples: int = 0):
+def _fim_spec(args: TrainingArgs, tokenizer=None):
+    """class_args.fim_rate / fim_spm_rate (data/megatron/__init__.py:87-88); needs the tokenizer's <fim_*> ids"""
+    ca = args.datasets[0].class_args
+    rate = float(ca.get("fim_rate", 0) or 0)
+    if rate == 0:
+        return None
+    from .data import FIMSpec, HFTokenizerCodec
+
+    if tokenizer is None:
+        from transformers import AutoTokenizer
+
+        name = args.tokenizer_args.tokenizer_name or args.model_args.model_name
+        if name is None:
+            raise ValueError("fim_rate != 0 needs tokenizer_args.tokenizer_name (a tokenizer holding the <fim_*> tokens)")
+        tokenizer = AutoTokenizer.from_pretrained(name)
+    codec = tokenizer if hasattr(tokenizer, "detokenize") else HFTokenizerCodec(tokenizer)
+    return FIMSpec.from_tokenizer(codec, rate, float(ca.get("fim_spm_rate", 0.5)))
+
+
+def make_megatron_dataloader(args: TrainingArgs, rank: int, world: int, consumed_samples: int = 0, tokenizer=None):
     """get_megatron_gpt_dataloaders (data/megatron/__init__.py:18-213), train split: Megatron .bin/.idx stores named by
     `class_args.data_path` (one prefix or [w1, prefix1, w2, prefix2, ...]) + `split`, cut into S+1-token samples, global
     batches of mbs * world consecutive samples with rank r taking rows [r*mbs, (r+1)*mbs); resumes at `consumed_samples`."""
@@ -95,7 +114,7 @@ def make_megatron_dataloader(args: TrainingArgs, rank: int, world: int, consumed
     sizes = get_train_val_test_samples(tp.num_training_steps, tp.micro_batch_size, tp.gradient_accumulation_steps,
                                        getattr(tp, "eval_interval", None), ca.get("eval_steps"), world)
     train, _, _ = build_gpt_datasets(ca["data_path"], ca.get("split", "100,0,0"), sizes, ca["sequence_length"],
-                                     ca.get("seed", args.random_args.seed))
+                                     ca.get("seed", args.random_args.seed), fim=_fim_spec(args, tokenizer))
     sampler = MegatronBatchSampler(len(train), consumed_samples, tp.micro_batch_size, world, rank)
     return PackedBatchLoader(train, sampler, ca["sequence_length"])
 
