@@ -211,8 +211,9 @@ class DistributedArgs(BaseArgs):
             extra = set(self.gradient_checkpointing_args) - {"checkpoint_every", "use_reentrant", "block_name"}
             if extra:
                 raise ValueError(f"unexpected gradient_checkpointing_args {sorted(extra)}")
-        if self.zero_topology.data_parallel_replication_world_size is not None:
-            raise NotImplementedError("HSDP (multi-node replicate x shard) is out of scope of the single-box path")
+        zt = self.zero_topology
+        if (zt.data_parallel_replication_world_size is None) != (zt.data_parallel_sharding_world_size is None):
+            raise AssertionError("data_parallel_replication_world_size and data_parallel_sharding_world_size go together")
         if self.communication_dtype is not None:
             self.communication_dtype = {"bfloat16": "bf16", "float32": "fp32"}.get(self.communication_dtype, self.communication_dtype)
             assert self.communication_dtype in ("bf16", "fp32")

@@ -43,12 +43,53 @@ def configure_comm_ctas() -> None:
     os.environ.setdefault("NCCL_MIN_CTAS", "1")
 
 
-class _Comm:
-    """engine hooks: all-gather prefetch in forward, reduce-scatter in backward"""
+def hybrid_layout(world_size: int, sharding_world_size: int | None, replication_world_size: int | None):
+    """Rank lists of the 2-D data-parallel topology (`zero_topology`, reference arguments.py:283-298,
+    utils/parallel.py:59-68 and :255-266).  Returns (shard_groups, replicate_groups): parameters / optimizer state are
+    sharded inside a shard group and replicated across the groups; gradients are reduce-scattered inside the shard group
+    and then all-reduced between the ranks that own the same slice.
 
-    def __init__(self, engine: DolomiteEngine, group, communication_dtype: torch.dtype, reshard_after_forward: bool):
+    B200-first placement: a shard group is `sharding_world_size` CONSECUTIVE ranks (one NVSwitch domain), so the large
+    per-unit all-gather / reduce-scatter stay on NVLink and only the 1/S-sized shard all-reduce crosses nodes."""
+    if replication_world_size is None or sharding_world_size is None:
+        if replication_world_size is not None or sharding_world_size is not None:
+            raise ValueError("data_parallel_replication_world_size and data_parallel_sharding_world_size go together")
+        return [list(range(world_size))], [[r] for r in range(world_size)]
+    S, R = int(sharding_world_size), int(replication_world_size)
+    if S < 1 or R < 1 or S * R != world_size:
+        raise ValueError(f"replication ({R}) x sharding ({S}) world sizes must equal the data-parallel world size ({world_size})")
+    shard_groups = [[g * S + i for i in range(S)] for g in range(R)]
+    replicate_groups = [[g * S + i for g in range(R)] for i in range(S)]
+    return shard_groups, replicate_groups
+
+
+def build_data_parallel_groups(sharding_world_size: int | None = None, replication_world_size: int | None = None):
+    """-> (shard_group, replicate_group or None, shard_world_size, shard_rank).  Collective: every rank creates every
+    group, in the same order (`dist.new_group` contract)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    shard_groups, replicate_groups = hybrid_layout(world, sharding_world_size, replication_world_size)
+    if len(shard_groups) == 1:
+        return dist.group.WORLD, None, world, rank
+    mine_s = mine_r = None
+    for ranks in shard_groups:
+        g = dist.new_group(ranks)
+        if rank in ranks:
+            mine_s = (g, ranks)
+    for ranks in replicate_groups:
+        g = dist.new_group(ranks)
+        if rank in ranks:
+            mine_r = g
+    return mine_s[0], mine_r, len(mine_s[1]), mine_s[1].index(rank)
+
+
+class _Comm:
+    """engine hooks: all-gather prefetch in forward, reduce-scatter (+ replica all-reduce) in backward"""
+
+    def __init__(self, engine: DolomiteEngine, group, communication_dtype: torch.dtype, reshard_after_forward: bool,
+                 replicate_group=None):
         self.engine = engine
         self.group = group
+        self.replicate_group = replicate_group
         self.ws = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.comm_dtype = communication_dtype
@@ -123,6 +164,8 @@ class _Comm:
                 K.cast_f32_to_bf16(u.grad_full, stage)
                 work = dist.reduce_scatter_tensor(out, stage, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
                 work.wait()  # orders the comm stream after the collective
+                if self.replicate_group is not None:  # HSDP: mean over the replicas of this slice, still in bf16
+                    dist.all_reduce(out, op=dist.ReduceOp.AVG, group=self.replicate_group)
                 u.master.grad.zero_()
                 K.accum_bf16_into_f32(out, u.master.grad, 1.0)
                 evt = torch.cuda.Event()
@@ -132,6 +175,9 @@ class _Comm:
             else:
                 work = dist.reduce_scatter_tensor(u.master.grad, u.grad_full, op=dist.ReduceOp.AVG, group=self.group,
                                                   async_op=True)
+                if self.replicate_group is not None:
+                    work.wait()
+                    work = dist.all_reduce(u.master.grad, op=dist.ReduceOp.AVG, group=self.replicate_group, async_op=True)
                 self.rs_work[i] = work
         if i == 0:
             self.finish_backward()
@@ -160,19 +206,23 @@ class ShardedDataParallel(nn.Module):
     `.grad`), `.train()/.eval()`, `.config`, `.tokenizer` and `forward(batch) -> loss`."""
 
     def __init__(self, model_wrapper: nn.Module, process_group=None, communication_dtype: torch.dtype | None = None,
-                 reshard_after_forward: bool = False):
+                 reshard_after_forward: bool = False, replicate_group=None):
         super().__init__()
         self.module = model_wrapper
         self.engine: DolomiteEngine = model_wrapper.model.engine
-        self.group = process_group
+        self.group = process_group  # the SHARD group; `replicate_group` links the owners of the same slice (HSDP)
+        self.replicate_group = replicate_group
         # the engine was built for a given data-parallel degree; a world_size-1 engine stays unsharded even when a
         # process group exists (e.g. an unsharded reference copy next to a sharded model)
         self.world_size = self.engine.world_size
+        if self.world_size == 1 and replicate_group is not None and dist.get_world_size(replicate_group) > 1:
+            raise NotImplementedError("replication without sharding (data_parallel_sharding_world_size == 1) is not built: "
+                                      "shard over the box's GPUs and replicate across boxes")
         if self.world_size > 1:
             assert dist.is_initialized() and dist.get_world_size(process_group) == self.world_size, \
-                "engine must be built with world_size/rank of the DP group"
+                "engine must be built with world_size/rank of the (shard) DP group"
             comm_dtype = torch.bfloat16 if communication_dtype is None else communication_dtype
-            self.engine.comm = _Comm(self.engine, process_group, comm_dtype, reshard_after_forward)
+            self.engine.comm = _Comm(self.engine, process_group, comm_dtype, reshard_after_forward, replicate_group)
             # persistent GEMM grids must not claim the SMs the NCCL kernels run on (see configure_comm_ctas)
             K.set_option("gemm_sm_margin", comm_cta_budget())
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=self.engine.device)
@@ -297,5 +347,22 @@ def wrap_model_for_distributed_training(args, model: nn.Module) -> nn.Module:
         # gradient_checkpointing/block.py:13-37): blocks 0, k, 2k, ... keep only their input and are re-run in backward
         every = int((getattr(dargs, "gradient_checkpointing_args", None) or {}).get("checkpoint_every", 1))
         model.model.engine.checkpoint_every = every
-    group = dist.group.WORLD if dist.is_initialized() else None
-    return ShardedDataParallel(model, group, communication_dtype=comm_dtype, reshard_after_forward=reshard and stage == 3)
+    group, replicate_group = (dist.group.WORLD if dist.is_initialized() else None), None
+    topo = getattr(dargs, "zero_topology", None) if dargs is not None else None
+    if topo is not None and getattr(topo, "data_parallel_replication_world_size", None) is not None:
+        # HSDP: the engine must have been built with the SHARD group's size / rank (pretrain.build does)
+        group, replicate_group, _, _ = data_parallel_groups(topo.data_parallel_sharding_world_size,
+                                                            topo.data_parallel_replication_world_size)
+    return ShardedDataParallel(model, group, communication_dtype=comm_dtype, reshard_after_forward=reshard and stage == 3,
+                               replicate_group=replicate_group)
+
+
+_GROUP_CACHE: dict = {}
+
+
+def data_parallel_groups(sharding_world_size: int | None, replication_world_size: int | None):
+    """memoised `build_data_parallel_groups` (process groups are created once per topology)"""
+    key = (sharding_world_size, replication_world_size)
+    if key not in _GROUP_CACHE:
+        _GROUP_CACHE[key] = build_data_parallel_groups(sharding_world_size, replication_world_size)
+    return _GROUP_CACHE[key]

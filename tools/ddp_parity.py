@@ -18,7 +18,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from dolomite_engine_b200.distributed import ShardedDataParallel, configure_comm_ctas
+from dolomite_engine_b200.distributed import ShardedDataParallel, build_data_parallel_groups, configure_comm_ctas
 from dolomite_engine_b200.model_wrapper import ModelWrapperForPretraining
 from dolomite_engine_b200.optimization import get_optimizer
 
@@ -38,9 +38,13 @@ def main():
     accum = int(os.environ.get("ACCUM", "1"))
     reshard = bool(int(os.environ.get("RESHARD", "0")))
     mbs, seq = 2, 128
+    # SHARD=S: HSDP with S consecutive ranks per shard group, world / S replicas (zero_topology)
+    shard = int(os.environ.get("SHARD", "0")) or None
+    group, rep_group, s_world, s_rank = build_data_parallel_groups(shard, world // shard if shard else None)
     w = ModelWrapperForPretraining(pretrained_config=dict(CFG), micro_batch_size=mbs, sequence_length=seq, device=dev,
-                                   world_size=world, rank=rank)
-    sdp = ShardedDataParallel(w, dist.group.WORLD, communication_dtype=comm_dtype, reshard_after_forward=reshard)
+                                   world_size=s_world, rank=s_rank)
+    sdp = ShardedDataParallel(w, group, communication_dtype=comm_dtype, reshard_after_forward=reshard,
+                              replicate_group=rep_group)
     opt = get_optimizer("DolomiteFusedAdamW", OPT, sdp)
     ref = ref_sdp = ref_opt = None
     if rank == 0:
