@@ -247,6 +247,12 @@ class DolomitePreTrainedModel(nn.Module):
         return result
 
     # ---- pretraining entry: labels already aligned with positions (model_wrapper/pretraining.py:104-127) ----
+    def generate(self, input_ids=None, attention_mask=None, **generate_kwargs) -> torch.Tensor:
+        """decoder-only `generate` (model_wrapper/base.py:127): prompt + new tokens; see hf_models/generation.py"""
+        from .generation import generate
+
+        return generate(self, input_ids, attention_mask, **generate_kwargs)
+
     def forward_pretraining_loss(self, input_ids, position_ids, cu_seqlens, max_seqlen: int, labels):
         return _EngineFunction.apply(self._anchor, self, input_ids, position_ids, cu_seqlens, int(max_seqlen), labels, -100, torch.is_grad_enabled())
 

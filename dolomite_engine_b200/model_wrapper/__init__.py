@@ -105,6 +105,17 @@ class ModelWrapper(nn.Module):
     def save_pretrained(self, save_path: str) -> None:
         self.model.save_pretrained(save_path)
 
+    def generate(self, batch: dict, generate_kwargs: dict) -> tuple[list[str] | list[list[int]], list[int]]:
+        """model_wrapper/base.py:110-136: -> (generated text with the prompt trimmed, generated-token counts incl. eos).
+        Without a tokenizer (offline) the first element holds the generated token ids instead of text."""
+        out = self.model.generate(input_ids=batch["input_ids"], attention_mask=batch.get("attention_mask"),
+                                  **generate_kwargs, eos_token_id=self.eos_token_id)
+        generated = out[:, torch.as_tensor(batch["input_ids"]).shape[1] :]
+        num_generated_tokens = ((generated != self.eos_token_id).sum(dim=-1) + 1).tolist()
+        if self.tokenizer is None:
+            return generated.tolist(), num_generated_tokens
+        return self.tokenizer.batch_decode(generated, skip_special_tokens=True), num_generated_tokens
+
 
 class ModelWrapperForPretraining(ModelWrapper):
     """model_wrapper/pretraining.py:16-236"""

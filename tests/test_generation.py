@@ -1,0 +1,115 @@
+"""Decoding front end (hf_models/generation.py): the logits filters against HuggingFace's warpers on CPU; greedy / sampled
+decoding against step-by-step forward passes on the GPU."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from dolomite_engine_b200.hf_models.generation import _filter_logits
+
+
+def test_logit_filters_match_huggingface_warpers():
+    from transformers.generation.logits_process import TemperatureLogitsWarper, TopKLogitsWarper, TopPLogitsWarper
+
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(5, 97, generator=g) * 3
+    ids = torch.zeros(5, 1, dtype=torch.long)
+    for temperature, top_k, top_p in [(0.7, None, None), (None, 10, None), (None, None, 0.9), (1.3, 20, 0.8), (None, 1, None),
+                                      (None, 500, 0.999)]:
+        want = logits.clone()
+        if temperature is not None:
+            want = TemperatureLogitsWarper(temperature)(ids, want)
+        if top_k is not None:
+            want = TopKLogitsWarper(top_k)(ids, want)
+        if top_p is not None:
+            want = TopPLogitsWarper(top_p)(ids, want)
+        got = _filter_logits(logits.clone(), temperature, top_k, top_p)
+        assert torch.equal(torch.isinf(got), torch.isinf(want)), (temperature, top_k, top_p)
+        keep = ~torch.isinf(want)
+        assert torch.allclose(got[keep], want[keep])
+
+
+CFG = dict(vocab_size=512, n_positions=256, n_embd=256, n_layer=2, n_head=4, n_inner=512, attention_head_type="gqa",
+           num_key_value_heads=2, position_embedding_type="rope", activation_function="swiglu", normalization_function="rmsnorm",
+           add_bias=False, resid_pdrop=0, embd_pdrop=0, attn_pdrop=0, eos_token_id=3, bos_token_id=3, pad_token_id=3)
+
+
+def _model(padding_free: bool):
+    from dolomite_engine_b200.hf_models import GPTDolomiteConfig, GPTDolomiteForCausalLM
+
+    return GPTDolomiteForCausalLM(GPTDolomiteConfig(**CFG), device=torch.device("cuda", 0),
+                                  use_padding_free_transformer=padding_free)
+
+
+def _prompts():
+    g = torch.Generator().manual_seed(5)
+    lens = [9, 4, 13, 1]
+    L = max(lens)
+    ids = torch.full((len(lens), L), 3, dtype=torch.long)
+    mask = torch.zeros(len(lens), L, dtype=torch.long)
+    for r, n in enumerate(lens):  # left padded, like the reference's inference collate (data/utils.py)
+        ids[r, L - n :] = torch.randint(4, 512, (n,), generator=g)
+        mask[r, L - n :] = 1
+    return ids, mask
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("padding_free", [False, True])
+def test_greedy_generation_equals_stepwise_argmax(padding_free):
+    model = _model(padding_free)
+    ids, mask = _prompts()
+    out = model.generate(input_ids=ids, attention_mask=mask, max_new_tokens=6, eos_token_id=-1)  # never stops early
+    assert out.shape == (4, ids.shape[1] + 6) and torch.equal(out[:, : ids.shape[1]].cpu(), ids)
+    # replay: every generated token is the argmax of an independent forward over the row's prefix alone
+    padded = _model(False)
+    padded.load_state_dict(model.state_dict())
+    for r in range(4):
+        n0 = int(mask[r].sum())
+        row = out[r, ids.shape[1] - n0 :].cpu()
+        for t in range(6):
+            prefix = row[: n0 + t][None]
+            with torch.no_grad():
+                logits = padded(input_ids=prefix, attention_mask=torch.ones_like(prefix)).logits[0, -1].float()
+            top2 = logits.topk(2).values
+            if float(top2[0] - top2[1]) < 0.05:  # near tie: the batch composition may legitimately flip a bf16 argmax
+                break
+            assert int(logits.argmax()) == int(row[n0 + t]), (r, t)
+
+
+@pytest.mark.gpu
+def test_generation_stops_at_eos_and_pads():
+    model = _model(False)
+    ids, mask = _prompts()
+    free = model.generate(input_ids=ids, attention_mask=mask, max_new_tokens=5, eos_token_id=-1)
+    eos = int(free[0, ids.shape[1] + 1])  # make row 0's second new token the stop token
+    out = model.generate(input_ids=ids, attention_mask=mask, max_new_tokens=5, eos_token_id=eos, pad_token_id=0)
+    gen = out[:, ids.shape[1] :].cpu()
+    for r in range(4):
+        hit = (gen[r] == eos).nonzero()
+        if len(hit):
+            assert bool((gen[r, int(hit[0]) + 1 :] == 0).all())  # filled with pad after the stop token
+    # until the first row finishes both runs are the same computation
+    free_gen = free[:, ids.shape[1] :].cpu()
+    assert torch.equal(gen[:, :2], free_gen[:, :2]) and int(gen[0, 1]) == eos
+    assert bool((gen[0, 2:] == 0).all())
+    # sampling is reproducible under a seeded generator and stays inside top-k
+    g1 = torch.Generator(device="cuda").manual_seed(1)
+    g2 = torch.Generator(device="cuda").manual_seed(1)
+    a = model.generate(input_ids=ids, attention_mask=mask, max_new_tokens=4, do_sample=True, top_k=5, temperature=0.8, generator=g1)
+    b = model.generate(input_ids=ids, attention_mask=mask, max_new_tokens=4, do_sample=True, top_k=5, temperature=0.8, generator=g2)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_wrapper_generate_counts_tokens():
+    from dolomite_engine_b200.model_wrapper import ModelWrapperForFinetuning
+
+    w = ModelWrapperForFinetuning(pretrained_config=dict(model_type="gpt_dolomite", **CFG), device=torch.device("cuda", 0),
+                                  use_padding_free_transformer=False)
+    ids, mask = _prompts()
+    toks, counts = w.generate({"input_ids": ids, "attention_mask": mask}, {"max_new_tokens": 4})
+    assert len(toks) == 4 and len(counts) == 4 and all(1 <= c <= 5 for c in counts)
