@@ -85,17 +85,17 @@ def test_generation_stops_at_eos_and_pads():
     model = _model(False)
     ids, mask = _prompts()
     free = model.generate(input_ids=ids, attention_mask=mask, max_new_tokens=5, eos_token_id=-1)
-    eos = int(free[0, ids.shape[1] + 1])  # make row 0's second new token the stop token
+    free_gen = free[:, ids.shape[1] :].cpu()
+    eos = int(free_gen[0, 0])  # make row 0's first new token the stop token
     out = model.generate(input_ids=ids, attention_mask=mask, max_new_tokens=5, eos_token_id=eos, pad_token_id=0)
     gen = out[:, ids.shape[1] :].cpu()
-    for r in range(4):
+    # the first step is the same computation in both runs; row 0 stops there and is filled with the pad id
+    assert torch.equal(gen[:, 0], free_gen[:, 0]) and int(gen[0, 0]) == eos
+    assert bool((gen[0, 1:] == 0).all())
+    for r in range(4):  # any row that emitted the stop token is padded from there on
         hit = (gen[r] == eos).nonzero()
         if len(hit):
-            assert bool((gen[r, int(hit[0]) + 1 :] == 0).all())  # filled with pad after the stop token
-    # until the first row finishes both runs are the same computation
-    free_gen = free[:, ids.shape[1] :].cpu()
-    assert torch.equal(gen[:, :2], free_gen[:, :2]) and int(gen[0, 1]) == eos
-    assert bool((gen[0, 2:] == 0).all())
+            assert bool((gen[r, int(hit[0]) + 1 :] == 0).all())
     # sampling is reproducible under a seeded generator and stays inside top-k
     g1 = torch.Generator(device="cuda").manual_seed(1)
     g2 = torch.Generator(device="cuda").manual_seed(1)
