@@ -116,15 +116,24 @@ def save_checkpoint(args, model, optimizer, lr_scheduler, train_dataloader, expe
     save_root = args.save_args.save_path
     save_path = _base(save_root, iteration)
     os.makedirs(save_path, exist_ok=True)
-    sd = model_state_dict(model)
-    if rank == 0:
-        torch.save(sd, os.path.join(save_path, "model.pt"))
-    del sd
-    if getattr(args.save_args, "save_optimizer", True) and optimizer is not None:
-        osd = optimizer_state_dict(model, optimizer)
+    save_opt = getattr(args.save_args, "save_optimizer", True) and optimizer is not None
+    if int(getattr(getattr(args, "distributed_args", None), "fsdp_algorithm", 1) or 1) == 2:
+        # torch.distributed.checkpoint directories `model/`, `optimizer/` (checkpointing.py:108-113)
+        from . import checkpointing_dcp as D
+
+        D.save_model(model, os.path.join(save_path, "model"))
+        if save_opt:
+            D.save_optimizer(model, optimizer, os.path.join(save_path, "optimizer"))
+    else:
+        sd = model_state_dict(model)
         if rank == 0:
-            torch.save(osd, os.path.join(save_path, "optimizer.pt"))
-        del osd
+            torch.save(sd, os.path.join(save_path, "model.pt"))
+        del sd
+        if save_opt:
+            osd = optimizer_state_dict(model, optimizer)
+            if rank == 0:
+                torch.save(osd, os.path.join(save_path, "optimizer.pt"))
+            del osd
     if rank == 0 and lr_scheduler is not None:
         torch.save(lr_scheduler.state_dict(), os.path.join(save_path, "lr_scheduler.pt"))
     rng = {"random_rng_state": random.getstate(), "np_rng_state": np.random.get_state(), "torch_rng_state": torch.get_rng_state(),
@@ -192,9 +201,17 @@ def load_checkpoint_for_training(args, model, optimizer, lr_scheduler, train_dat
     if iteration is None:
         iteration = json.load(open(os.path.join(la.load_path, "latest_checkpointed_iteration.json")))["latest_checkpointed_iteration"]
     load_path = _base(la.load_path, iteration)
-    load_model_state_dict(model, torch.load(os.path.join(load_path, "model.pt"), map_location="cpu"))
-    if getattr(la, "load_optimizer", True) and optimizer is not None:
-        load_optimizer_state_dict(model, optimizer, torch.load(os.path.join(load_path, "optimizer.pt"), map_location="cpu"))
+    from . import checkpointing_dcp as D
+
+    want_opt = getattr(la, "load_optimizer", True) and optimizer is not None
+    if D.is_dcp_checkpoint(load_path):  # written with fsdp_algorithm: 2 (by this engine or by the reference)
+        D.load_model(model, os.path.join(load_path, "model"))
+        if want_opt:
+            D.load_optimizer(model, optimizer, os.path.join(load_path, "optimizer"))
+    else:
+        load_model_state_dict(model, torch.load(os.path.join(load_path, "model.pt"), map_location="cpu"))
+        if want_opt:
+            load_optimizer_state_dict(model, optimizer, torch.load(os.path.join(load_path, "optimizer.pt"), map_location="cpu"))
     if getattr(la, "load_lr_scheduler", True) and lr_scheduler is not None:
         assert getattr(la, "load_optimizer", True), "load_lr_scheduler requires loading of optimizer"
         lr_scheduler.load_state_dict(torch.load(os.path.join(load_path, "lr_scheduler.pt"), weights_only=False))

@@ -36,22 +36,23 @@ def _build(world: int, rank: int, seed: int):
     return engine, model, opt, sched
 
 
-def _args(path, load=False):
+def _args(path, load=False, fsdp_algorithm=1):
     ns = types.SimpleNamespace
-    return ns(save_args=ns(save_path=path, save_optimizer=True),
+    return ns(save_args=ns(save_path=path, save_optimizer=True), distributed_args=ns(fsdp_algorithm=fsdp_algorithm),
               load_args=ns(load_path=path, iteration=None, load_optimizer=True, load_lr_scheduler=True, load_rng_state=True,
                            load_dataloader_state=True, load_experiments_tracker_state=True, load_starting_iteration=True) if load else None,
               model_dump=lambda mode="json": {"note": "training config"})
 
 
-def _roundtrip(path, world, rank):
+def _roundtrip(path, world, rank, fsdp_algorithm=1):
     from dolomite_engine_b200 import checkpointing as C
 
     engine, model, opt, sched = _build(world, rank, seed=1)
     loader = types.SimpleNamespace(consumed_samples=48)
     want_model = C.model_state_dict(model)
     want_opt = C.optimizer_state_dict(model, opt)
-    C.save_checkpoint(_args(path), model, opt, sched, loader, None, 7, metadata={"consumed_samples": 48})
+    C.save_checkpoint(_args(path, fsdp_algorithm=fsdp_algorithm), model, opt, sched, loader, None, 7,
+                      metadata={"consumed_samples": 48})
     # a differently initialised replica restores everything
     engine2, model2, opt2, sched2 = _build(world, rank, seed=2)
     assert not torch.equal(engine2.units[1].master.data, engine.units[1].master.data)
@@ -94,12 +95,14 @@ def test_single_process_layout_and_names(tmp_path):
     assert torch.load(os.path.join(base, "dataloader", "dataloader-0.pt"), weights_only=False) == {"consumed_samples": 48}
 
 
-def _worker(rank, world, port, path, q):
+def _worker(rank, world, port, path, q, fsdp_algorithm=1):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        sd, _ = _roundtrip(path, world, rank)
+        sd, _ = _roundtrip(path, world, rank, fsdp_algorithm)
+        if fsdp_algorithm == 2 and rank == 0:
+            _check_dcp_directory(os.path.join(path, "global_step7"), sd, world)
         # the sharded save must describe the same full tensors as an unsharded replica built from the same seed
         engine1, model1, _, _ = _build(1, 0, seed=1)
         from dolomite_engine_b200 import checkpointing as C
@@ -115,11 +118,43 @@ def _worker(rank, world, port, path, q):
         dist.destroy_process_group()
 
 
-def test_world_size_2_checkpoint_roundtrip(tmp_path):
+def _check_dcp_directory(base, sd, world):
+    """fsdp_algorithm 2: `model/` and `optimizer/` are torch.distributed.checkpoint directories keyed by the reference's
+    names; any reader (here: a plain single-process dcp.load of full tensors) gets the same values back"""
+    import torch.distributed.checkpoint as dcp
+    from torch.distributed.checkpoint import FileSystemReader
+
+    assert not os.path.exists(os.path.join(base, "model.pt")) and not os.path.exists(os.path.join(base, "optimizer.pt"))
+    for d in ("model", "optimizer"):
+        assert os.path.isfile(os.path.join(base, d, ".metadata"))
+    files = [f for f in os.listdir(os.path.join(base, "model")) if f.endswith(".distcp")]
+    assert len(files) == world  # every rank wrote its share of the units
+    md = FileSystemReader(os.path.join(base, "model")).read_metadata()
+    assert set(md.state_dict_metadata) == set(sd)
+    omd = FileSystemReader(os.path.join(base, "optimizer")).read_metadata()
+    k = "model.transformer.h.0.mlp.c_fc.weight"
+    assert {f"state.{k}.exp_avg", f"state.{k}.exp_avg_sq", f"state.{k}.step"} <= set(omd.state_dict_metadata)
+    assert any(key.startswith("param_groups") for key in omd.state_dict_metadata)
+
+
+def test_dcp_single_process_roundtrip(tmp_path):
+    path = str(tmp_path / "ckpt_dcp")
+    sd, _ = _roundtrip(path, 1, 0, fsdp_algorithm=2)
+    _check_dcp_directory(os.path.join(path, "global_step7"), sd, 1)
+    # values: read every tensor back with plain dcp.load
+    import torch.distributed.checkpoint as dcp
+
+    got = {k: torch.zeros_like(v) for k, v in sd.items()}
+    dcp.load(got, checkpoint_id=os.path.join(path, "global_step7", "model"))
+    assert all(torch.equal(got[k], sd[k]) for k in sd)
+
+
+@pytest.mark.parametrize("fsdp_algorithm", [1, 2])
+def test_world_size_2_checkpoint_roundtrip(tmp_path, fsdp_algorithm):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path / "ckpt2"), q)) for r in range(2)]
+    port = 31500 + (os.getpid() + 7 * fsdp_algorithm) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path / "ckpt2"), q, fsdp_algorithm)) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=240) for _ in procs]
@@ -129,8 +164,10 @@ def test_world_size_2_checkpoint_roundtrip(tmp_path):
         assert status == "ok", f"rank {rank}: {status}"
 
 
-def test_unshard_writes_a_pretrained_directory(tmp_path):
-    """unshard.py of the reference: global_step<N>/model.pt -> safetensors + config.json with the reference's names"""
+@pytest.mark.parametrize("fsdp_algorithm", [1, 2])
+def test_unshard_writes_a_pretrained_directory(tmp_path, fsdp_algorithm):
+    """unshard.py of the reference: global_step<N>/model.pt (or the DCP directory model/) -> safetensors + config.json with
+    the reference's names"""
     from dolomite_engine_b200 import checkpointing as C
     from dolomite_engine_b200.hf_models.config import GPTDolomiteConfig
     from dolomite_engine_b200.unshard import unshard
@@ -138,7 +175,7 @@ def test_unshard_writes_a_pretrained_directory(tmp_path):
 
     path = str(tmp_path / "ckpt")
     engine, model, opt, sched = _build(1, 0, seed=3)
-    args = _args(path)
+    args = _args(path, fsdp_algorithm=fsdp_algorithm)
     args.model_dump = lambda mode="json": {"model_args": {"pretrained_config": engine.cfg.to_dict()}}
     C.save_checkpoint(args, model, opt, sched, None, None, 11)
     out = unshard(path, str(tmp_path / "hf"), None)
