@@ -256,13 +256,67 @@ class TrainingArgs(BaseArgs):
             raise NotImplementedError("the B200 path trains in bf16 mixed precision (mixed_precision_args.dtype: bf16)")
 
 
-def get_args_from_dict(config: dict) -> TrainingArgs:
-    return TrainingArgs(**config)
+class GenerationParameters(BaseArgs):
+    """arguments.py:449-465"""
+
+    batch_size: int = None
+    do_sample: bool | None = None
+    max_new_tokens: int = None
+    temperature: float | None = None
+    top_k: int | None = None
+    top_p: float | None = None
+
+    def model_post_init(self, __context: Any) -> None:
+        _check_not_None([(self.batch_size, "batch_size"), (self.max_new_tokens, "max_new_tokens")])
+
+    def to_dict(self) -> dict:
+        return self.model_dump()
 
 
-def get_args(mode=None) -> TrainingArgs:
-    """arguments.py:527-547"""
+class InferenceArgs(BaseArgs):
+    """arguments.py:468-503: either `model_args` (a fresh / pretrained model) or `load_args` (a training checkpoint)"""
+
+    random_args: RandomArgs = RandomArgs()
+    tokenizer_args: TokenizerArgs = TokenizerArgs()
+    model_args: ModelArgs | None = None
+    datasets: list[DatasetArgs] = []
+    load_args: LoadArgs | None = None
+    generation_parameters: GenerationParameters = None
+    mixed_precision_args: MixedPrecisionArgs = MixedPrecisionArgs()
+    logging_args: LoggingArgs = LoggingArgs()
+    output_dir: str = None
+
+    def model_post_init(self, __context: Any) -> None:
+        _check_not_None([(self.datasets, "datasets"), (self.generation_parameters, "generation_parameters"),
+                         (self.output_dir, "output_dir")])
+        if self.load_args is None:
+            assert self.model_args is not None, "model_args need to be specified if load_args are not specified"
+        else:
+            assert self.model_args is None, "model_args can't be specified with load_args"
+
+
+class UnshardingArgs(BaseArgs):
+    """arguments.py:506-517"""
+
+    load_args: LoadArgs = None
+    unsharded_path: str = None
+    mixed_precision_args: MixedPrecisionArgs = MixedPrecisionArgs()
+    logging_args: LoggingArgs = LoggingArgs()
+
+    def model_post_init(self, __context: Any) -> None:
+        _check_not_None([(self.load_args, "load_args"), (self.unsharded_path, "unsharded_path")])
+
+
+_MODE_ARGS = {"training": TrainingArgs, "inference": InferenceArgs, "unsharding": UnshardingArgs}
+
+
+def get_args_from_dict(config: dict, mode=None):
+    return _MODE_ARGS[str(getattr(mode, "value", mode) or "training")](**config)
+
+
+def get_args(mode=None):
+    """arguments.py:527-547; `mode` is "training" (default), "inference" or "unsharding" (enums.Mode values)"""
     parser = ArgumentParser()
     parser.add_argument("--config", type=str, required=True, help="path for the config")
     a = parser.parse_args()
-    return get_args_from_dict(load_yaml(a.config))
+    return get_args_from_dict(load_yaml(a.config), mode)

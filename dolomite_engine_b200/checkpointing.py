@@ -239,3 +239,35 @@ def load_checkpoint_for_training(args, model, optimizer, lr_scheduler, train_dat
     if not getattr(la, "load_starting_iteration", True):
         iteration = 0
     return iteration, metadata, tracker
+
+
+def load_checkpoint_for_inference(args, mode="inference", device=None):
+    """checkpointing.py:266-402 (distributed_backend torch, tensor_parallel_size 1): rebuild the model from the
+    `training_config.yml` stored next to the checkpoint, load `model.pt` / the DCP directory `model/` into it.
+    -> (model wrapper, training args of the checkpoint, full state dict or None for DCP)"""
+    from .arguments import get_args_from_dict, load_yaml
+    from .model_wrapper import get_model
+
+    la = args.load_args
+    iteration = la.iteration
+    if iteration is None:
+        iteration = json.load(open(os.path.join(la.load_path, "latest_checkpointed_iteration.json")))["latest_checkpointed_iteration"]
+    load_path = _base(la.load_path, iteration)
+    args_from_checkpoint = get_args_from_dict(load_yaml(os.path.join(load_path, "training_config.yml")), "training")
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    # generation runs on padded batches: the finetuning wrapper takes both layouts, the pretraining wrapper only packed text
+    args_from_checkpoint.model_args.use_padding_free_transformer = False
+    if str(getattr(args_from_checkpoint.tuning_args.tuning_method, "value", args_from_checkpoint.tuning_args.tuning_method)) == "pretraining":
+        args_from_checkpoint.tuning_args.tuning_method = "full_finetuning"
+    model = get_model(args_from_checkpoint, mode, device=device)
+    from . import checkpointing_dcp as D
+
+    state = None
+    if D.is_dcp_checkpoint(load_path):
+        D.load_model(model, os.path.join(load_path, "model"))
+    else:
+        state = torch.load(os.path.join(load_path, "model.pt"), map_location="cpu")
+        state = {k.replace("._checkpoint_wrapped_module", ""): v for k, v in state.items()}
+        load_model_state_dict(model, state)
+    return model, args_from_checkpoint, state

@@ -185,3 +185,34 @@ def test_unshard_writes_a_pretrained_directory(tmp_path, fsdp_algorithm):
     assert all(torch.equal(sd[k[len("model."):]], v) for k, v in want.items())
     cfg = GPTDolomiteConfig.from_pretrained(out)
     assert cfg.n_embd == 64 and cfg.num_key_value_heads == 2 and cfg.attention_head_type == "gqa"
+
+
+@pytest.mark.parametrize("fsdp_algorithm", [1, 2])
+def test_load_checkpoint_for_inference_rebuilds_the_model(tmp_path, fsdp_algorithm):
+    """checkpointing.py:266-402: the model is rebuilt from the training_config.yml stored with the checkpoint (as a padded-batch
+    finetuning wrapper, which generation needs) and receives the saved parameters -- from model.pt or the DCP directory"""
+    from dolomite_engine_b200 import checkpointing as C
+    from dolomite_engine_b200.arguments import get_args_from_dict
+    from dolomite_engine_b200.model_wrapper import ModelWrapperForFinetuning, get_model
+
+    d = str(tmp_path / "run")
+    pc = dict(model_type="gpt_dolomite", n_embd=64, n_head=4, n_layer=2, n_inner=96, vocab_size=264, attention_head_type="gqa",
+              num_key_value_heads=2, add_bias=True, activation_function="swiglu", position_embedding_type="rope",
+              normalization_function="rmsnorm", resid_pdrop=0, embd_pdrop=0, attn_pdrop=0)
+    targs = get_args_from_dict({
+        "model_args": {"model_class": "AutoModelForCausalLM", "pretrained_config": pc, "use_padding_free_transformer": True},
+        "tuning_args": {"tuning_method": "pretraining"},
+        "datasets": [{"class_name": "SyntheticPackedDataset", "data_name": "s", "class_args": {"sequence_length": 32}}],
+        "training_parameters": {"num_training_steps": 1, "micro_batch_size": 2, "eval_during_training": False},
+        "save_args": {"save_path": d, "save_interval": 1}, "distributed_args": {"fsdp_algorithm": fsdp_algorithm},
+        "random_args": {"seed": 5}, "mixed_precision_args": {"dtype": "bf16"}})
+    trained = get_model(targs, device=torch.device("cpu"))
+    C.save_checkpoint(targs, trained, None, None, None, None, 3)
+    iargs = get_args_from_dict({"datasets": [{"class_name": "JSONLinesDataset", "data_name": "x", "class_args": {"data_path": d}}],
+                                "load_args": {"load_path": d}, "generation_parameters": {"batch_size": 1, "max_new_tokens": 1},
+                                "output_dir": d + "/o"}, "inference")
+    model, args_ckpt, state = C.load_checkpoint_for_inference(iargs, device=torch.device("cpu"))
+    assert isinstance(model, ModelWrapperForFinetuning) and not model.use_padding_free_transformer
+    assert args_ckpt.save_args.save_path == d and (state is None) == (fsdp_algorithm == 2)
+    for u, v in zip(trained.model.engine.units, model.model.engine.units):
+        assert torch.equal(u.master.data, v.master.data) and torch.equal(u.compute, v.compute)

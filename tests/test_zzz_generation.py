@@ -113,3 +113,48 @@ def test_wrapper_generate_counts_tokens():
     ids, mask = _prompts()
     toks, counts = w.generate({"input_ids": ids, "attention_mask": mask}, {"max_new_tokens": 4})
     assert len(toks) == 4 and len(counts) == 4 and all(1 <= c <= 5 for c in counts)
+
+
+def test_generate_entry_loop_writes_jsonl(tmp_path):
+    """generate.py:14-68 with a stand-in model: batching (incl. the short last batch), left-padded inference collate,
+    one JSON line per example, generation kwargs without batch_size"""
+    import json
+    import types
+
+    from dolomite_engine_b200.arguments import get_args_from_dict
+    from dolomite_engine_b200.generate import build_datasets, generate
+
+    data = tmp_path / "d"
+    data.mkdir()
+    with open(data / "a.jsonl", "w") as f:
+        for i in range(5):
+            f.write(json.dumps({"input": "x" * (i + 1), "output": "unused"}) + "\n")
+    args = get_args_from_dict({
+        "datasets": [{"class_name": "JSONLinesDataset", "data_name": "toy", "class_args": {"data_path": str(data)},
+                      "input_format": "Q: __input__ A:", "max_input_tokens": 6}],
+        "model_args": {"model_class": "AutoModelForCausalLM", "pretrained_config": {"model_type": "gpt_dolomite"}},
+        "generation_parameters": {"batch_size": 2, "max_new_tokens": 3, "do_sample": False},
+        "output_dir": str(tmp_path / "out")}, "inference")
+    seen = []
+
+    def fake_generate(batch, kwargs):
+        assert "batch_size" not in kwargs and kwargs["max_new_tokens"] == 3
+        ids, mask = batch["input_ids"], batch["attention_mask"]
+        assert ids.shape == mask.shape and "labels" not in batch
+        assert bool((mask[:, -1] == 1).all())  # left padding
+        assert bool((ids[mask == 0] == 9).all())  # padded with eos
+        seen.append(ids.shape[0])
+        return [f"len{int(m.sum())}" for m in mask], [2] * ids.shape[0]
+
+    model = types.SimpleNamespace(eos_token_id=9, generate=fake_generate)
+    tokenize = lambda text: [ord(c) % 7 for c in text]  # noqa: E731
+    ds = build_datasets(args, tokenize, 9)
+    assert len(ds) == 1 and ds[0].data_name == "toy" and len(ds[0]) == 5
+    generate(args, model, ds)
+    assert seen == [2, 2, 1]
+    lines = [json.loads(x) for x in open(tmp_path / "out" / "output-toy.jsonl")]
+    assert len(lines) == 5 and lines[0] == {"generated_text": "len6", "num_generated_tokens": 2}  # truncated to 6 prompt tokens
+    assert os.path.isfile(tmp_path / "out" / "inference_config.yml")
+    with pytest.raises(Exception, match="model_args need to be specified"):
+        get_args_from_dict({"datasets": args.model_dump()["datasets"], "generation_parameters": {"batch_size": 1, "max_new_tokens": 1},
+                            "output_dir": "x"}, "inference")  # neither model_args nor load_args
