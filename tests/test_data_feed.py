@@ -210,3 +210,27 @@ def test_validation_split_loader_and_evaluate_contract():
     assert m.training and abs(v - float(torch.stack([t.float().mean() for t in first]).mean())) < 1e-4
     d["datasets"][0]["class_args"]["split"] = "100,0,0"
     assert make_megatron_val_dataloader(get_args_from_dict(d), 0, 1) is None
+
+
+def test_preprocess_jsonl_to_token_stores(tmp_path):
+    """data/preprocess.py (reference tool tools/megatron_dataset/preprocess_data.py): one store per JSON key, one document
+    per line, eod appended, empty documents skipped, uint16 for small vocabularies"""
+    import json
+
+    from dolomite_engine_b200.data import MMapIndexedDataset
+    from dolomite_engine_b200.data import preprocess as P
+
+    src = tmp_path / "c.jsonl"
+    rows = [{"text": "hello world", "code": "ab"}, {"text": "", "code": "xyz"}, {"text": "q", "code": ""}]
+    src.write_text("\n".join(json.dumps(r) for r in rows) + "\n\n")
+    P.configure(lambda s: [ord(c) for c in s], ["text", "code"], eod=1)
+    counts = P.write_stores(map(P.encode_line, P._lines(str(src))), str(tmp_path / "out"), ["text", "code"], vocab_size=300)
+    assert counts == {"text": 2, "code": 2}
+    text = MMapIndexedDataset(str(tmp_path / "out_text"))
+    assert text.dtype == np.uint16 and list(text.sequence_lengths) == [12, 2]
+    assert list(text[0]) == [ord(c) for c in "hello world"] + [1] and list(text[1]) == [ord("q"), 1]
+    assert list(text.document_indices) == [0, 1, 2]
+    code = MMapIndexedDataset(str(tmp_path / "out_code"))
+    assert [list(code[i]) for i in range(2)] == [[97, 98, 1], [120, 121, 122, 1]]
+    wide = P.write_stores([{"text": [70000, 5]}], str(tmp_path / "w"), ["text"], vocab_size=128000)
+    assert wide == {"text": 1} and MMapIndexedDataset(str(tmp_path / "w_text")).dtype == np.int32
