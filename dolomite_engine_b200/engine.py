@@ -189,8 +189,8 @@ def check_supported(cfg: CommonConfig) -> None:
             f"activation_function={cfg.activation_function!r}: swiglu and gelu_pytorch_tanh are implemented in CUDA")
     if cfg.model_type == "moe_dolomite" and (cfg.activation_function != "swiglu" or cfg.normalization_function != "rmsnorm"):
         raise NotImplementedError("MoE blocks are implemented for swiglu + rmsnorm (the MoEDolomite / Granite-MoE shape)")
-    if cfg.resid_pdrop != 0 or cfg.embd_pdrop != 0 or cfg.attn_pdrop != 0:
-        raise NotImplementedError("dropout > 0 is not implemented on the B200 path (target configs use p=0: nn.Identity)")
+    # dropout > 0 is accepted at construction (evaluation / generation of such checkpoints: dropout is the identity in eval
+    # mode) and rejected by `forward` in training mode, where no dropout kernel exists
     hd = cfg.n_embd // cfg.n_head
     if hd not in (16, 32, 64, 80, 96, 128):
         raise NotImplementedError(f"head_dim={hd}: supported head dims are 16, 32, 64, 80, 96, 128")
@@ -222,6 +222,8 @@ class DolomiteEngine:
         self.is_glu = cfg.activation_function.endswith("glu")
         self.is_layernorm = cfg.normalization_function == "layernorm"
         self.learned_positions = cfg.position_embedding_type == "learned_absolute"
+        self.has_dropout = bool(cfg.resid_pdrop or cfg.embd_pdrop or cfg.attn_pdrop)
+        self.training = True  # mirrors nn.Module.training of the owning model (DolomitePreTrainedModel.train)
         self.units: list[FlatUnit] = [FlatUnit("root", _root_specs(cfg), world_size, rank)]
         for i in range(cfg.n_layer):
             self.units.append(FlatUnit(f"h.{i}", _block_specs(cfg, i), world_size, rank))
@@ -366,6 +368,9 @@ class DolomiteEngine:
                 save_for_backward: bool = True):
         """Returns (logits_or_None, loss_or_None).  input_ids int64 [T]; cu_seqlens int32 [B+1]."""
         cfg = self.cfg
+        if self.has_dropout and self.training:
+            raise NotImplementedError("dropout > 0 in training mode is not implemented on the B200 path (the target configs "
+                                      "use p = 0); call .eval() for evaluation / generation, where dropout is the identity")
         T = input_ids.numel()
         root = self.units[0]
         comm = self.comm

@@ -247,6 +247,10 @@ class DolomitePreTrainedModel(nn.Module):
         return result
 
     # ---- pretraining entry: labels already aligned with positions (model_wrapper/pretraining.py:104-127) ----
+    def train(self, mode: bool = True):
+        self.engine.training = bool(mode)  # dropout > 0 is only rejected in training mode (engine.forward)
+        return super().train(mode)
+
     def generate(self, input_ids=None, attention_mask=None, **generate_kwargs) -> torch.Tensor:
         """decoder-only `generate` (model_wrapper/base.py:127): prompt + new tokens; see hf_models/generation.py"""
         from .generation import generate

@@ -43,7 +43,7 @@ def test_unsupported_configs_fail_loudly():
                            attn_pdrop=0, vocab_size=2048)
     check_supported(ok)
     for kw in (dict(position_embedding_type="alibi"), dict(normalization_function="apex_layernorm"),
-               dict(activation_function="geglu"), dict(attn_pdrop=0.1), dict(n_head=32, num_key_value_heads=32),
+               dict(activation_function="geglu"), dict(n_head=32, num_key_value_heads=32),
                dict(position_embedding_type="learned_absolute", m_emb=12.0), dict(rope_scaling={"type": "linear", "factor": 2, "original_max_position_embeddings": 64})):
         d = ok.to_dict()
         d.update(kw)
@@ -219,3 +219,21 @@ def test_every_shipped_config_parses():
         assert a.training_parameters.micro_batch_size >= 1
     a = get_args_from_dict(load_yaml(os.path.join(ROOT, "configs", "c5_llama3_8b_finetune.yml")))
     assert a.distributed_args.gradient_checkpointing_args == {"checkpoint_every": 2} and a.model_args.model_name
+
+
+def test_dropout_configs_construct_but_do_not_train():
+    """the reference's default config has dropout 0.1: such checkpoints can be loaded for evaluation / generation (dropout is
+    the identity in eval mode); a training-mode forward raises instead of silently skipping dropout"""
+    import torch
+
+    from dolomite_engine_b200.engine import DolomiteEngine
+    from dolomite_engine_b200.hf_models import GPTDolomiteConfig
+
+    cfg = GPTDolomiteConfig(n_embd=64, n_head=4, n_layer=1, vocab_size=264, n_positions=64)  # defaults: pdrop 0.1
+    engine = DolomiteEngine(cfg, "cpu", seed=1)
+    assert engine.has_dropout and engine.training
+    ids = torch.zeros(8, dtype=torch.long)
+    with pytest.raises(NotImplementedError, match="dropout > 0 in training mode"):
+        engine.forward(ids, ids, torch.tensor([0, 8], dtype=torch.int32), 8)
+    assert not DolomiteEngine(GPTDolomiteConfig(n_embd=64, n_head=4, n_layer=1, vocab_size=264, resid_pdrop=0, embd_pdrop=0,
+                                                attn_pdrop=0), "cpu", seed=1).has_dropout
