@@ -366,3 +366,15 @@ def data_parallel_groups(sharding_world_size: int | None, replication_world_size
     if key not in _GROUP_CACHE:
         _GROUP_CACHE[key] = build_data_parallel_groups(sharding_world_size, replication_world_size)
     return _GROUP_CACHE[key]
+
+
+def shard_world_and_rank(args, world: int, rank: int) -> tuple[int, int]:
+    """(world_size, rank) the ENGINE must be built with: the shard group's under `zero_topology` (HSDP), else the global ones.
+    The data feed and the loss average always use the global (rank, world)."""
+    dargs = getattr(args, "distributed_args", None)
+    topo = getattr(dargs, "zero_topology", None) if dargs is not None else None
+    if world > 1 and topo is not None and getattr(topo, "data_parallel_replication_world_size", None) is not None:
+        _, _, shard_world, shard_rank = data_parallel_groups(topo.data_parallel_sharding_world_size,
+                                                             topo.data_parallel_replication_world_size)
+        return shard_world, shard_rank
+    return world, rank

@@ -66,7 +66,10 @@ def main() -> None:
     import torch
 
     torch.manual_seed(args.random_args.seed)
-    wrapper = get_model(args, device=torch.device("cuda", local), world_size=world, rank=rank)
+    from .distributed import shard_world_and_rank
+
+    shard_world, shard_rank = shard_world_and_rank(args, world, rank)
+    wrapper = get_model(args, device=torch.device("cuda", local), world_size=shard_world, rank=shard_rank)
     if wrapper.tokenizer is None:
         raise ValueError("finetuning needs a tokenizer: set tokenizer_args.tokenizer_name (or model_args.model_name) to a local directory")
     model = wrap_model_for_distributed_training(args, wrapper)

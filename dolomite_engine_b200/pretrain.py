@@ -73,15 +73,11 @@ def build(args: TrainingArgs):
     rank, world, local = init_distributed()
     torch.manual_seed(args.random_args.seed)
     device = torch.device("cuda", local)
-    shard_world, shard_rank = world, rank
-    topo = args.distributed_args.zero_topology
-    if world > 1 and topo.data_parallel_replication_world_size is not None:
-        # HSDP (zero_topology): the engine shards over `data_parallel_sharding_world_size` consecutive ranks; the data
-        # feed and the loss average keep using the global (rank, world)
-        from .distributed import data_parallel_groups
+    # HSDP (zero_topology): the engine shards over `data_parallel_sharding_world_size` consecutive ranks; the data feed and
+    # the loss average keep using the global (rank, world)
+    from .distributed import shard_world_and_rank
 
-        _, _, shard_world, shard_rank = data_parallel_groups(topo.data_parallel_sharding_world_size,
-                                                             topo.data_parallel_replication_world_size)
+    shard_world, shard_rank = shard_world_and_rank(args, world, rank)
     wrapper = get_model(args, device=device, world_size=shard_world, rank=shard_rank)
     model = wrap_model_for_distributed_training(args, wrapper)
     optimizer = get_optimizer(args.optimizer_args.class_name, args.optimizer_args.class_args, model,
