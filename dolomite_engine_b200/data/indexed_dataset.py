@@ -18,6 +18,7 @@ as they are and files written here are readable by the reference.
 from __future__ import annotations
 
 import os
+import shutil
 import struct
 
 import numpy as np
@@ -158,6 +159,20 @@ class MMapIndexedDatasetBuilder:
 
     def end_document(self) -> None:
         self.document_indices.append(len(self.sequence_lengths))
+
+    def add_index(self, path_prefix: str) -> None:
+        """append a whole existing store (indexed_dataset.py:579-598; tools/megatron_dataset/merge_data.py): its sequences
+        and document boundaries follow the ones already written; the token bytes are streamed, not parsed"""
+        other = _Index(get_idx_path(path_prefix), multimodal=self.multimodal)
+        if other.dtype != self.dtype:
+            raise ValueError(f"cannot merge {path_prefix} ({other.dtype}) into a {self.dtype} store")
+        base = len(self.sequence_lengths)
+        self.sequence_lengths.extend(int(x) for x in other.sequence_lengths)
+        self.document_indices.extend(int(base + d) for d in other.document_indices[1:])
+        if self.multimodal:
+            self.sequence_modes.extend(int(m) for m in other.sequence_modes)
+        with open(get_bin_path(path_prefix), "rb") as f:
+            shutil.copyfileobj(f, self._file, 16 << 20)
 
     def finalize(self, idx_path: str) -> None:
         self._file.close()
