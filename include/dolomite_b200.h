@@ -32,6 +32,7 @@ extern "C" {
 #define DOLO_ERR_INVALID (-1) /* bad argument / unsupported shape */
 #define DOLO_ERR_CUDA (-2)    /* CUDA runtime / driver error     */
 
+/* library management (no reference counterpart): thread-local text of the last error, ABI version, device query */
 const char* dolomite_b200_last_error(void);
 int dolomite_b200_abi_version(void);
 int dolomite_b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
@@ -128,7 +129,8 @@ int dolomite_b200_cross_entropy_fwd_bwd(const void* logits, int64_t ldl, const i
  * ------------------------------------------------------------------------------------------------ */
 int dolomite_b200_colsum_accum(const void* x, int64_t ldx, float* out, int64_t T, int64_t N, float scale,
                                void* stream);
-/* x[i] *= scale[0]  (bf16 in place; scale is a DEVICE scalar: upstream gradient of the loss) */
+/* x[i] *= scale[0]  (bf16 in place; scale is a DEVICE scalar: the upstream gradient autograd hands to the loss when the
+ * caller does anything but `loss.backward()`, train_utils.py:61-90) */
 int dolomite_b200_scale_bf16_by_device_scalar(void* x, int64_t n, const float* scale, void* stream);
 
 /* out = a + alpha * b  (bf16; residual adds of gpt_dolomite/layer.py:70-85), a/b/out may alias */
@@ -145,7 +147,8 @@ int dolomite_b200_clip_coef(const float* sumsq, float max_norm, float* coef_out,
 int dolomite_b200_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
                              float beta1, float beta2, float eps, float weight_decay, int64_t step,
                              const float* clip_coef, void* stream);
-/* fp32 -> bf16 cast of a flat shard; bf16 grads -> fp32 accumulate */
+/* fp32 -> bf16 cast of a flat shard (FSDP MixedPrecision param_dtype = bf16, distributed/__init__.py:34-44);
+ * bf16 reduce-scatter output -> fp32 shard gradient accumulate (reduce_dtype = bf16, same table) */
 int dolomite_b200_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int dolomite_b200_accum_bf16_into_f32(const void* src, float* dst, float scale, int64_t n, void* stream);
 
