@@ -82,3 +82,28 @@ def test_finetune_yaml_to_batches(tmp_path):
     # prompt cut to 5 tokens, reply to 2 + eos: every row has exactly 8 real tokens, labels only on the last 3
     assert b["attention_mask"].sum(1).tolist() == [8] * 4 and ((b["labels"] != -100).sum(1) == 3).all()
     assert (b["labels"][:, -1] == 2).all()
+
+
+def test_eight_simulated_ranks_cover_the_dataset_once():
+    """mirrors the reference's tests/data/dataloader_test.py: 8 simulated ranks, every example is seen by exactly one rank
+    (1000 examples, micro-batch 5: 1000 / 8 = 125 per rank = 25 full batches, nothing dropped)"""
+    from dolomite_engine_b200.data.finetuning import batches
+
+    n, world, mbs = 1000, 8, 5
+    dataset = [{"input": [i, 1, 2], "output": [2]} for i in range(n)]
+    seen = {}
+    for rank in range(world):
+        ids = []
+        for batch in batches(dataset, mbs, eos_token_id=0, use_padding_free_transformer=True, rank=rank, world_size=world,
+                             seed=42, infinite=False):
+            ids += [row[0] for row in batch["input_ids"]]
+        assert len(ids) == len(set(ids)), f"rank {rank} saw an example twice"
+        seen[rank] = ids
+    flat = [i for r in range(world) for i in seen[r]]
+    assert len(flat) == n and set(flat) == set(range(n))
+    # pretraining sampler: the same property per global batch
+    from dolomite_engine_b200.data import MegatronBatchSampler
+
+    rows = {r: [i for b in MegatronBatchSampler(960, 0, 4, world, r) for i in b] for r in range(world)}
+    flat = sorted(i for r in rows for i in rows[r])
+    assert flat == list(range(960)) and all(len(rows[r]) == 120 for r in rows)
