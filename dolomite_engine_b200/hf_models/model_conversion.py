@@ -1,12 +1,12 @@
-"""`import_from_huggingface(name_or_path, save_path)` for llama / granite checkpoints (reference:
-hf_models/model_conversion/__init__.py:19-27, llama.py:13-149, granite.py:15-80).  CPU-only weight re-layout:
+"""`import_from_huggingface(name_or_path, save_path)` / `export_to_huggingface` (reference:
+hf_models/model_conversion/__init__.py:11-46).  llama / granite live here (llama.py:13-290, granite.py:15-142); gpt_bigcode,
+mixtral and granitemoe in model_conversion_families.py.  CPU-only weight re-layout:
 
   * q/k/v projections -> one `c_attn` in the per-head / per-group interleave of attention/utils.py:18-106
   * up_proj / gate_proj -> `c_fc = cat([up, gate])` (gpt_dolomite/mlp.py:54-55)
   * LlamaConfig / GraniteConfig -> GPTDolomiteConfig (llama.py:37-74, granite.py:40-79)
 
 Works on local directories (config.json + *.safetensors); there is no hub access in this environment.
-Export and the other model families are 'next' rows.
 """
 
 from __future__ import annotations
@@ -17,7 +17,8 @@ import os
 import torch
 
 from ..utils.safetensors import SafeTensorsWeightsManager
-from .config import GPTDolomiteConfig
+from . import model_conversion_families as F
+from .config import CommonConfig, GPTDolomiteConfig
 
 
 def interleave_query_key_value_tensor_for_attention(q, k, v, num_heads: int, num_key_value_heads: int, head_dim: int,
@@ -62,6 +63,21 @@ def _head_type(cfg: dict) -> str:
     return "gqa"
 
 
+def rope_fields(original: dict) -> tuple[float, dict | None]:
+    """(rope_theta, rope_scaling) from either config dialect: the top-level `rope_theta` / `rope_scaling` keys the reference
+    reads (llama.py:60-61), or the `rope_parameters` dict transformers >= 5 writes ({"rope_theta", "rope_type", ...})"""
+    rp = original.get("rope_parameters")
+    if rp is None:
+        return original.get("rope_theta", 10000), original.get("rope_scaling")
+    theta = rp.get("rope_theta", original.get("rope_theta", 10000))
+    kind = rp.get("rope_type", rp.get("type", "default"))
+    if kind == "default":
+        return theta, None
+    scaling = {k: v for k, v in rp.items() if k not in ("rope_theta", "rope_type")}
+    scaling["type"] = kind
+    return theta, scaling
+
+
 def _import_config(original: dict) -> GPTDolomiteConfig:
     assert original.get("hidden_act", "silu") == "silu"
     assert original.get("mlp_bias", False) == original.get("attention_bias", False)
@@ -82,8 +98,8 @@ def _import_config(original: dict) -> GPTDolomiteConfig:
         add_bias=original.get("attention_bias", False),
         tie_word_embeddings=original.get("tie_word_embeddings", False),
         initializer_range=original.get("initializer_range", 0.02),
-        rope_theta=original.get("rope_theta", 10000),
-        rope_scaling=original.get("rope_scaling"),
+        rope_theta=rope_fields(original)[0],
+        rope_scaling=rope_fields(original)[1],
         attn_pdrop=original.get("attention_dropout", 0.0),
         resid_pdrop=0.0,
         embd_pdrop=0.0,
@@ -128,7 +144,17 @@ def _import_state_dict(m: SafeTensorsWeightsManager, config: GPTDolomiteConfig) 
     return sd
 
 
-_SUPPORTED = ("llama", "granite")
+_SUPPORTED = ("llama", "granite", "gpt_bigcode", "mixtral", "granitemoe")
+
+
+def _copy_tokenizer_files(src: str, dst: str) -> None:
+    import shutil
+
+    for extra in ("tokenizer.json", "tokenizer_config.json", "special_tokens_map.json", "tokenizer.model", "vocab.json",
+                  "merges.txt"):
+        p = os.path.join(src, extra)
+        if os.path.exists(p):
+            shutil.copy(p, os.path.join(dst, extra))
 
 
 def import_from_huggingface(pretrained_model_name_or_path: str, save_path: str) -> None:
@@ -140,16 +166,20 @@ def import_from_huggingface(pretrained_model_name_or_path: str, save_path: str) 
     model_type = original.get("model_type")
     if model_type not in _SUPPORTED:
         raise NotImplementedError(f"the current model_type ({model_type}) is not yet supported")
-    config = _import_config(original)
-    sd = _import_state_dict(SafeTensorsWeightsManager(pretrained_model_name_or_path), config)
+    m = SafeTensorsWeightsManager(pretrained_model_name_or_path)
+    if model_type == "gpt_bigcode":
+        config = F.import_config_bigcode(original)
+        sd = F.copy_state_dict(m, config.tie_word_embeddings)
+    elif model_type in ("mixtral", "granitemoe"):
+        config = F.import_config_moe(original, _head_type(original))
+        sd = F.import_state_dict_moe(m, config, model_type, interleave_query_key_value_tensor_for_attention)
+    else:
+        config = _import_config(original)
+        sd = _import_state_dict(m, config)
+    os.makedirs(save_path, exist_ok=True)
     SafeTensorsWeightsManager.save_state_dict(sd, save_path)
     config.save_pretrained(save_path)
-    for extra in ("tokenizer.json", "tokenizer_config.json", "special_tokens_map.json", "tokenizer.model"):
-        p = os.path.join(pretrained_model_name_or_path, extra)
-        if os.path.exists(p):
-            import shutil
-
-            shutil.copy(p, os.path.join(save_path, extra))
+    _copy_tokenizer_files(pretrained_model_name_or_path, save_path)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -226,18 +256,23 @@ def _export_state_dict(m: SafeTensorsWeightsManager, config: GPTDolomiteConfig) 
 
 
 def export_to_huggingface(pretrained_model_name_or_path: str, save_path: str, model_type: str) -> None:
-    """model_conversion/__init__.py:39-46: `model_type` in {"llama", "granite"} on this path"""
+    """model_conversion/__init__.py:39-46: `model_type` in {"llama", "granite", "gpt_bigcode", "mixtral", "granitemoe"}"""
+    if model_type == "bigcode":
+        model_type = "gpt_bigcode"  # the reference's registry key (model_conversion/__init__.py:30-36)
     if model_type not in _SUPPORTED:
         raise NotImplementedError(f"the current model_type ({model_type}) is not yet supported")
-    config = GPTDolomiteConfig.from_pretrained(pretrained_model_name_or_path)
-    sd = _export_state_dict(SafeTensorsWeightsManager(pretrained_model_name_or_path), config)
+    config = CommonConfig.from_pretrained(pretrained_model_name_or_path)
+    m = SafeTensorsWeightsManager(pretrained_model_name_or_path)
+    if model_type == "gpt_bigcode":
+        out_cfg, sd = F.export_config_bigcode(config), F.copy_state_dict(m, config.tie_word_embeddings)
+    elif model_type in ("mixtral", "granitemoe"):
+        assert config.model_type == "moe_dolomite", f"{model_type} export needs a moe_dolomite checkpoint"
+        out_cfg = F.export_config_moe(config, model_type)
+        sd = F.export_state_dict_moe(m, config, model_type, split_query_key_value_tensor_for_attention)
+    else:
+        out_cfg, sd = _export_config(config, model_type), _export_state_dict(m, config)
     os.makedirs(save_path, exist_ok=True)
     SafeTensorsWeightsManager.save_state_dict(sd, save_path)
     with open(os.path.join(save_path, "config.json"), "w") as f:
-        json.dump(_export_config(config, model_type), f, indent=2)
-    for extra in ("tokenizer.json", "tokenizer_config.json", "special_tokens_map.json", "tokenizer.model"):
-        p = os.path.join(pretrained_model_name_or_path, extra)
-        if os.path.exists(p):
-            import shutil
-
-            shutil.copy(p, os.path.join(save_path, extra))
+        json.dump(out_cfg, f, indent=2)
+    _copy_tokenizer_files(pretrained_model_name_or_path, save_path)
