@@ -105,11 +105,11 @@ def load_optimizer(model, optimizer, path: str) -> None:
     else:
         for u in engine.units:
             optimizer.state[u.master]["step"] = torch.tensor(float(step))
+    stored = dcp.FileSystemReader(path).read_metadata().state_dict_metadata
+    if not any(k.startswith("param_groups") for k in stored):
+        return  # a checkpoint written without hyper-parameters keeps the YAML's values
     groups = {"param_groups": [dict(g, params=[]) for g in optimizer.param_groups]}
-    try:
-        dcp.load(groups, checkpoint_id=path)
-    except Exception:  # a checkpoint written without hyper-parameters keeps the YAML's values
-        return
+    dcp.load(groups, checkpoint_id=path)
     for g, saved in zip(optimizer.param_groups, groups["param_groups"]):
         for k, v in saved.items():
             if k != "params":
