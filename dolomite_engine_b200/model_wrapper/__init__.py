@@ -99,7 +99,11 @@ class ModelWrapper(nn.Module):
 
                 self.tokenizer = AutoTokenizer.from_pretrained(self.tokenizer_name)
                 self.eos_token_id = self.tokenizer.eos_token_id
-            except Exception:  # offline: fall back to the config's eos id
+            except (OSError, ValueError, ImportError) as e:  # not a local directory and no hub access: keep the config's eos id
+                import warnings
+
+                warnings.warn(f"tokenizer {self.tokenizer_name!r} could not be loaded ({type(e).__name__}); continuing without "
+                              "one (token-id batches only)")
                 self.tokenizer = None
 
     def save_pretrained(self, save_path: str) -> None:
