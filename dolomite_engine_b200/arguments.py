@@ -1,45 +1,55 @@
-"""`--config <yaml>` argument tree of the reference's pretrain entry point (arguments.py:30-447, utils/pydantic.py:7-8,
-utils/yaml.py:6-23) restricted to the knobs of the data-parallel training hot path.  Same key names, same
+"""`--config <yaml>` argument tree of the reference's entry points (arguments.py:30-547, utils/pydantic.py:7-8,
+utils/yaml.py:6-23) restricted to the knobs of the data-parallel path.  Same section / key names, same
 `extra="forbid"` strictness; keys that select out-of-scope subsystems are accepted only at their default values and
 raise NotImplementedError otherwise, so an existing reference YAML either runs or fails loudly.
 
-Two additions: `model_args.moe_implementation` and
-`model_args.normalization_implementation` are accepted here because the reference's own
-configs/testing/scattermoe.yml sets them although its ModelArgs rejects them."""
+The schema is ONE table (`_SCHEMA`: section -> {key: (type, default)}); the pydantic classes are generated from it and
+the per-section rules live in `_RULES`.  Two additions: `model_args.moe_implementation` and
+`model_args.normalization_implementation` are accepted because the reference's own configs/testing/scattermoe.yml sets
+them although its ModelArgs rejects them; `distributed_args.reshard_after_forward` is a B200 extension."""
 
 from __future__ import annotations
 
 import re
 from argparse import ArgumentParser
-from typing import Any
+from typing import Any, Callable, Optional
 
 import yaml
-from pydantic import BaseModel, ConfigDict
+from pydantic import BaseModel, ConfigDict, create_model
+
+_RULES: dict[str, Callable[[Any], None]] = {}
 
 
 class BaseArgs(BaseModel):
     model_config = ConfigDict(extra="forbid", protected_namespaces=())
 
+    def model_post_init(self, __context: Any) -> None:
+        rule = _RULES.get(type(self).__name__)
+        if rule is not None:
+            rule(self)
+
 
 def load_yaml(file_path: str) -> dict:
-    """utils/yaml.py:6-23 -- YAML 1.1 loader fixed so that `1e-5` parses as a float"""
-    loader = yaml.SafeLoader
-    loader.add_implicit_resolver(
-        "tag:yaml.org,2002:float",
-        re.compile(
-            """^(?:
-    [-+]?(?:[0-9][0-9_]*)\\.[0-9_]*(?:[eE][-+]?[0-9]+)?
-    |[-+]?(?:[0-9][0-9_]*)(?:[eE][-+]?[0-9]+)
-    |\\.[0-9_]+(?:[eE][-+][0-9]+)?
-    |[-+]?[0-9][0-9_]*(?::[0-5]?[0-9])+\\.[0-9_]*
-    |[-+]?\\.(?:inf|Inf|INF)
-    |\\.(?:nan|NaN|NAN))$""",
-            re.X,
-        ),
-        list("-+0123456789."),
-    )
+    """utils/yaml.py:6-23: PyYAML follows YAML 1.1, where `1e-5` is a string; teach the loader the 1.2 float grammar"""
+    floats = re.compile(r"""^(?:
+        [-+]?(?:[0-9][0-9_]*)\.[0-9_]*(?:[eE][-+]?[0-9]+)?     # 1.5, 1.5e3
+       |[-+]?(?:[0-9][0-9_]*)(?:[eE][-+]?[0-9]+)               # 1e-5
+       |\.[0-9_]+(?:[eE][-+][0-9]+)?                           # .5
+       |[-+]?[0-9][0-9_]*(?::[0-5]?[0-9])+\.[0-9_]*            # sexagesimal
+       |[-+]?\.(?:inf|Inf|INF)
+       |\.(?:nan|NaN|NAN))$""", re.X)
+
+    class Loader(yaml.SafeLoader):
+        pass
+
+    Loader.add_implicit_resolver("tag:yaml.org,2002:float", floats, list("-+0123456789."))
     with open(file_path) as f:
-        return yaml.load(f, loader)
+        return yaml.load(f, Loader)
+
+
+def _need(obj, *names: str) -> None:
+    for n in names:
+        assert getattr(obj, n) is not None, f"{n} cannot be None"
 
 
 def _check_not_None(pairs) -> None:
@@ -47,267 +57,213 @@ def _check_not_None(pairs) -> None:
         assert obj is not None, f"{name} cannot be None"
 
 
-class RandomArgs(BaseArgs):
-    seed: int = 42
+# ------------------------------------------------------------------------------------------------
+# schema: section -> {key: (annotation, default)}.  `None` defaults of non-Optional keys mark required keys
+# (checked by the section's rule, like the reference's `_check_not_None`).
+# ------------------------------------------------------------------------------------------------
+O = Optional
+_SCHEMA: dict[str, dict[str, tuple]] = {
+    "RandomArgs": {"seed": (int, 42)},
+    "TokenizerArgs": {"tokenizer_name": (O[str], None), "additional_special_tokens": (O[list[str]], None)},
+    "ModelArgs": {
+        "model_name": (O[str], None), "pretrained_config": (O[dict], None), "model_class": (str, None),
+        "trust_remote_code": (bool, False), "attention_implementation": (O[str], None),
+        "use_padding_free_transformer": (bool, False), "efficient_initialization": (bool, False),
+        "reset_attention_mask": (bool, False), "reset_position_ids": (bool, False),
+        "moe_implementation": (O[str], None), "normalization_implementation": (O[str], None)},
+    "TuningArgs": {"tuning_method": (str, None), "prompt_tuning_args": (O[dict], None), "lora_args": (O[dict], None)},
+    "TrainingParameters": {
+        "ignore_sampling_proportion_for_validation": (bool, False), "num_training_steps": (O[int], None),
+        "gradient_accumulation_steps": (int, 1), "eval_interval": (O[int], None), "micro_batch_size": (int, None),
+        "eval_during_training": (bool, True), "loss_mask": (str, "output_only"), "gradient_clipping": (O[float], 1)},
+    "SaveArgs": {"save_path": (str, None), "save_interval": (int, None), "save_optimizer": (bool, True)},
+    "LoadArgs": {
+        "load_path": (str, None), "iteration": (O[int], None), "load_optimizer": (bool, True), "load_lr_scheduler": (bool, True),
+        "load_rng_state": (bool, True), "load_dataloader_state": (bool, True), "load_experiments_tracker_state": (bool, True),
+        "load_starting_iteration": (bool, True), "resume_learning_rate": (bool, True)},
+    "DatasetArgs": {
+        "class_name": (str, None), "class_args": (dict, {}), "data_name": (str, None), "input_format": (str, "__input__"),
+        "output_format": (str, "__output__"), "data_sampling_ratio": (O[int], None), "max_input_tokens": (O[int], None),
+        "max_output_tokens": (O[int], None)},
+    "OptimizerArgs": {
+        "class_name": (str, "TorchAdamW"), "params_group_method": (O[str], None),
+        "class_args": (dict, {"lr": 1e-5, "weight_decay": 0.1, "betas": [0.9, 0.95], "eps": 1e-10})},
+    "LRSchedulerArgs": {
+        "num_warmup_steps": (int, 200), "num_constant_steps": (int, 0), "num_decay_steps": (O[int], None),
+        "lr_decay_style": (str, "cosine"), "lr_decay_factor": (float, 0.1), "extra_lr_scheduler_args": (dict, {})},
+    "MixedPrecisionArgs": {"dtype": (str, "fp32"), "fp8_backend": (O[str], None)},
+    "ZeroTopologyArgs": {"data_parallel_replication_world_size": (O[int], None), "data_parallel_sharding_world_size": (O[int], None)},
+    "DistributedArgs": {
+        "stage": (int, 3), "distributed_backend": (str, "torch"), "overlap_comm": (bool, False),
+        "contiguous_gradients": (bool, False), "cpu_offload": (bool, False), "gradient_checkpointing_method": (O[str], None),
+        "gradient_checkpointing_args": (dict, {}), "zero_topology": ("ZeroTopologyArgs", "new"),
+        "zero_quantized_weights": (bool, False), "zero_quantized_gradients": (bool, False), "communication_dtype": (O[str], None),
+        "torch_compile": (bool, False), "dispatching_dataloader": (bool, False), "tensor_parallel_size": (int, 1),
+        "tensor_parallel_word_embeddings": (bool, False), "sequence_parallel": (bool, False),
+        "data_parallel_size": (O[int], None), "timeout_minutes": (O[int], None), "fsdp_algorithm": (int, 1),
+        "reshard_after_forward": (bool, False)},
+    "LoggingArgs": {
+        "logging_level": (str, "INFO"), "log_interval": (int, 1), "aim_args": (O[dict], None), "wandb_args": (O[dict], None),
+        "experiments_tracker_name": (O[str], None), "use_colored_logs": (bool, False), "torch_profiler_trace_path": (O[str], None)},
+    "ResearchArgs": {"neft_alpha": (O[float], None)},
+    "GenerationParameters": {
+        "batch_size": (int, None), "do_sample": (O[bool], None), "max_new_tokens": (int, None), "temperature": (O[float], None),
+        "top_k": (O[int], None), "top_p": (O[float], None)},
+    # ---- roots (arguments.py:405-517): section members are written ("<Section>", "new" | None | "list") ----
+    "TrainingArgs": {
+        "random_args": ("RandomArgs", "new"), "tokenizer_args": ("TokenizerArgs", "new"), "model_args": ("ModelArgs", None),
+        "tuning_args": ("TuningArgs", None), "optimizer_args": ("OptimizerArgs", "new"),
+        "lr_scheduler_args": ("LRSchedulerArgs", "new"), "datasets": ("DatasetArgs", "list"), "save_args": ("SaveArgs", None),
+        "load_args": ("LoadArgs", None), "training_parameters": ("TrainingParameters", None),
+        "logging_args": ("LoggingArgs", "new"), "mixed_precision_args": ("MixedPrecisionArgs", "new"),
+        "distributed_args": ("DistributedArgs", "new"), "research_args": ("ResearchArgs", "new")},
+    "InferenceArgs": {
+        "random_args": ("RandomArgs", "new"), "tokenizer_args": ("TokenizerArgs", "new"), "model_args": ("ModelArgs", None),
+        "datasets": ("DatasetArgs", "list"), "load_args": ("LoadArgs", None),
+        "generation_parameters": ("GenerationParameters", None), "mixed_precision_args": ("MixedPrecisionArgs", "new"),
+        "logging_args": ("LoggingArgs", "new"), "output_dir": (str, None)},
+    "UnshardingArgs": {
+        "load_args": ("LoadArgs", None), "unsharded_path": (str, None), "mixed_precision_args": ("MixedPrecisionArgs", "new"),
+        "logging_args": ("LoggingArgs", "new")},
+}
 
 
-class TokenizerArgs(BaseArgs):
-    tokenizer_name: str | None = None
-    additional_special_tokens: list[str] | None = None
+def _generate() -> dict[str, type[BaseArgs]]:
+    made: dict[str, type[BaseArgs]] = {}
+    for section, keys in _SCHEMA.items():  # sections are listed before the roots that embed them
+        fields = {}
+        for key, (kind, default) in keys.items():
+            if isinstance(kind, str):  # an embedded section
+                sub = made[kind]
+                if default == "new":
+                    fields[key] = (sub, sub())
+                elif default == "list":
+                    fields[key] = (list[sub], [])
+                else:
+                    fields[key] = (Optional[sub], None)
+            else:
+                fields[key] = (kind, default)
+        made[section] = create_model(section, __base__=BaseArgs, __module__=__name__, **fields)
+    return made
 
 
-class ModelArgs(BaseArgs):
-    model_name: str | None = None
-    pretrained_config: dict | None = None
-    model_class: str = None
-    trust_remote_code: bool = False
-    attention_implementation: str | None = None
-    use_padding_free_transformer: bool = False
-    efficient_initialization: bool = False
-    reset_attention_mask: bool = False
-    reset_position_ids: bool = False
-    moe_implementation: str | None = None
-    normalization_implementation: str | None = None
-
-    def model_post_init(self, __context: Any) -> None:
-        _check_not_None([(self.model_class, "model_class")])
-        if self.model_name is None:
-            _check_not_None([(self.pretrained_config, "pretrained_config")])
-        else:
-            assert self.pretrained_config is None, "pretrained_config shouldn't be specified with model_name"
-        assert self.model_class in ["AutoModelForCausalLM", "AutoModelForSeq2SeqLM"], f"unexpected model_class ({self.model_class})"
-        if self.model_class != "AutoModelForCausalLM":
-            raise NotImplementedError("only AutoModelForCausalLM is on the B200 hot path")
+globals().update(_generate())
 
 
-class TuningArgs(BaseArgs):
-    tuning_method: str = None
-    prompt_tuning_args: dict | None = None
-    lora_args: dict | None = None
+# ------------------------------------------------------------------------------------------------
+# per-section rules (the reference's model_post_init bodies, plus the out-of-scope guards of this path)
+# ------------------------------------------------------------------------------------------------
+def _rule(section: str):
+    def register(fn):
+        _RULES[section] = fn
+        return fn
 
-    def model_post_init(self, __context: Any) -> None:
-        _check_not_None([(self.tuning_method, "tuning_method")])
-        if self.tuning_method not in ("pretraining", "full_finetuning"):
-            raise NotImplementedError(f"tuning_method={self.tuning_method}: PEFT is out of scope of the B200 hot path")
-
-
-class TrainingParameters(BaseArgs):
-    ignore_sampling_proportion_for_validation: bool = False
-    num_training_steps: int | None = None
-    gradient_accumulation_steps: int = 1
-    eval_interval: int | None = None
-    micro_batch_size: int = None
-    eval_during_training: bool = True
-    loss_mask: str = "output_only"
-    gradient_clipping: float | None = 1
-
-    def model_post_init(self, __context: Any) -> None:
-        _check_not_None([(self.num_training_steps, "num_training_steps"), (self.micro_batch_size, "micro_batch_size")])
-        if self.eval_during_training:
-            _check_not_None([(self.eval_interval, "eval_interval")])
+    return register
 
 
-class SaveArgs(BaseArgs):
-    save_path: str = None
-    save_interval: int = None
-    save_optimizer: bool = True
-
-    def model_post_init(self, __context: Any) -> None:
-        _check_not_None([(self.save_path, "save_path"), (self.save_interval, "save_interval")])
-
-
-class LoadArgs(BaseArgs):
-    load_path: str = None
-    iteration: int | None = None
-    load_optimizer: bool = True
-    load_lr_scheduler: bool = True
-    load_rng_state: bool = True
-    load_dataloader_state: bool = True
-    load_experiments_tracker_state: bool = True
-    load_starting_iteration: bool = True
-    resume_learning_rate: bool = True
+@_rule("ModelArgs")
+def _(a) -> None:
+    _need(a, "model_class")
+    if a.model_name is None:
+        _need(a, "pretrained_config")
+    else:
+        assert a.pretrained_config is None, "pretrained_config shouldn't be specified with model_name"
+    assert a.model_class in ["AutoModelForCausalLM", "AutoModelForSeq2SeqLM"], f"unexpected model_class ({a.model_class})"
+    if a.model_class != "AutoModelForCausalLM":
+        raise NotImplementedError("only AutoModelForCausalLM is on the B200 hot path")
 
 
-class DatasetArgs(BaseArgs):
-    class_name: str = None
-    class_args: dict = {}
-    data_name: str = None
-    input_format: str = "__input__"
-    output_format: str = "__output__"
-    data_sampling_ratio: int | None = None
-    max_input_tokens: int | None = None
-    max_output_tokens: int | None = None
-
-    def model_post_init(self, __context: Any) -> None:
-        _check_not_None([(self.class_name, "dataset class_name"), (self.data_name, "data_name")])
+@_rule("TuningArgs")
+def _(a) -> None:
+    _need(a, "tuning_method")
+    if a.tuning_method not in ("pretraining", "full_finetuning"):
+        raise NotImplementedError(f"tuning_method={a.tuning_method}: PEFT is out of scope of the B200 hot path")
 
 
-class OptimizerArgs(BaseArgs):
-    class_name: str = "TorchAdamW"
-    params_group_method: str | None = None
-    class_args: dict = {"lr": 1e-5, "weight_decay": 0.1, "betas": [0.9, 0.95], "eps": 1e-10}
+@_rule("TrainingParameters")
+def _(a) -> None:
+    _need(a, "num_training_steps", "micro_batch_size")
+    if a.eval_during_training:
+        _need(a, "eval_interval")
 
 
-class LRSchedulerArgs(BaseArgs):
-    num_warmup_steps: int = 200
-    num_constant_steps: int = 0
-    num_decay_steps: int | None = None
-    lr_decay_style: str = "cosine"
-    lr_decay_factor: float = 0.1
-    extra_lr_scheduler_args: dict = {}
+@_rule("SaveArgs")
+def _(a) -> None:
+    _need(a, "save_path", "save_interval")
 
 
-class MixedPrecisionArgs(BaseArgs):
-    dtype: str = "fp32"
-    fp8_backend: str | None = None
-
-    def model_post_init(self, __context: Any) -> None:
-        self.dtype = {"bfloat16": "bf16", "float32": "fp32", "float16": "fp16"}.get(self.dtype, self.dtype)
-        if self.fp8_backend is not None or self.dtype == "fp8":
-            raise NotImplementedError("FP8 backends are out of scope of the B200 hot path (bf16 target)")
+@_rule("DatasetArgs")
+def _(a) -> None:
+    assert a.class_name is not None, "dataset class_name cannot be None"
+    _need(a, "data_name")
 
 
-class ZeroTopologyArgs(BaseArgs):
-    data_parallel_replication_world_size: int | None = None
-    data_parallel_sharding_world_size: int | None = None
+@_rule("MixedPrecisionArgs")
+def _(a) -> None:
+    a.dtype = {"bfloat16": "bf16", "float32": "fp32", "float16": "fp16"}.get(a.dtype, a.dtype)
+    if a.fp8_backend is not None or a.dtype == "fp8":
+        raise NotImplementedError("FP8 backends are out of scope of the B200 hot path (bf16 target)")
 
 
-class DistributedArgs(BaseArgs):
-    stage: int = 3
-    distributed_backend: str = "torch"
-    overlap_comm: bool = False
-    contiguous_gradients: bool = False
-    cpu_offload: bool = False
-    gradient_checkpointing_method: str | None = None
-    gradient_checkpointing_args: dict = {}
-    zero_topology: ZeroTopologyArgs = ZeroTopologyArgs()
-    zero_quantized_weights: bool = False
-    zero_quantized_gradients: bool = False
-    communication_dtype: str | None = None
-    torch_compile: bool = False
-    dispatching_dataloader: bool = False
-    tensor_parallel_size: int = 1
-    tensor_parallel_word_embeddings: bool = False
-    sequence_parallel: bool = False
-    data_parallel_size: int | None = None
-    timeout_minutes: int | None = None
-    fsdp_algorithm: int = 1
-    # B200 extension: free gathered parameters after forward and re-gather in backward (FSDP stage-3 memory profile)
-    reshard_after_forward: bool = False
-
-    def model_post_init(self, __context: Any) -> None:
-        if self.distributed_backend != "torch":
-            raise NotImplementedError("no DeepSpeed / multi-backend dispatch on the B200 path (north_star)")
-        for flag in ("cpu_offload", "zero_quantized_weights", "zero_quantized_gradients", "torch_compile",
-                     "dispatching_dataloader", "tensor_parallel_word_embeddings", "sequence_parallel"):
-            if getattr(self, flag):
-                raise NotImplementedError(f"distributed_args.{flag} is out of scope of the data-parallel B200 path")
-        if self.tensor_parallel_size != 1:
-            raise NotImplementedError("tensor parallelism is out of scope of the data-parallel B200 path")
-        if self.gradient_checkpointing_method is not None:
-            # reference enum GradientCheckpointingMethod has the single member `block` (enums.py; gradient_checkpointing/__init__.py)
-            if str(self.gradient_checkpointing_method).split(".")[-1] != "block":
-                raise ValueError(f"unexpected gradient_checkpointing_method ({self.gradient_checkpointing_method})")
-            extra = set(self.gradient_checkpointing_args) - {"checkpoint_every", "use_reentrant", "block_name"}
-            if extra:
-                raise ValueError(f"unexpected gradient_checkpointing_args {sorted(extra)}")
-        zt = self.zero_topology
-        if (zt.data_parallel_replication_world_size is None) != (zt.data_parallel_sharding_world_size is None):
-            raise AssertionError("data_parallel_replication_world_size and data_parallel_sharding_world_size go together")
-        if self.communication_dtype is not None:
-            self.communication_dtype = {"bfloat16": "bf16", "float32": "fp32"}.get(self.communication_dtype, self.communication_dtype)
-            assert self.communication_dtype in ("bf16", "fp32")
+_OUT_OF_SCOPE_FLAGS = ("cpu_offload", "zero_quantized_weights", "zero_quantized_gradients", "torch_compile",
+                       "dispatching_dataloader", "tensor_parallel_word_embeddings", "sequence_parallel")
 
 
-class LoggingArgs(BaseArgs):
-    logging_level: str = "INFO"
-    log_interval: int = 1
-    aim_args: dict | None = None
-    wandb_args: dict | None = None
-    experiments_tracker_name: str | None = None
-    use_colored_logs: bool = False
-    torch_profiler_trace_path: str | None = None
+@_rule("DistributedArgs")
+def _(a) -> None:
+    if a.distributed_backend != "torch":
+        raise NotImplementedError("no DeepSpeed / multi-backend dispatch on the B200 path (north_star)")
+    for flag in _OUT_OF_SCOPE_FLAGS:
+        if getattr(a, flag):
+            raise NotImplementedError(f"distributed_args.{flag} is out of scope of the data-parallel B200 path")
+    if a.tensor_parallel_size != 1:
+        raise NotImplementedError("tensor parallelism is out of scope of the data-parallel B200 path")
+    if a.gradient_checkpointing_method is not None:
+        # the reference's GradientCheckpointingMethod enum has the single member `block`
+        if str(a.gradient_checkpointing_method).split(".")[-1] != "block":
+            raise ValueError(f"unexpected gradient_checkpointing_method ({a.gradient_checkpointing_method})")
+        extra = set(a.gradient_checkpointing_args) - {"checkpoint_every", "use_reentrant", "block_name"}
+        if extra:
+            raise ValueError(f"unexpected gradient_checkpointing_args {sorted(extra)}")
+    zt = a.zero_topology
+    if (zt.data_parallel_replication_world_size is None) != (zt.data_parallel_sharding_world_size is None):
+        raise AssertionError("data_parallel_replication_world_size and data_parallel_sharding_world_size go together")
+    if a.communication_dtype is not None:
+        a.communication_dtype = {"bfloat16": "bf16", "float32": "fp32"}.get(a.communication_dtype, a.communication_dtype)
+        assert a.communication_dtype in ("bf16", "fp32")
 
 
-class ResearchArgs(BaseArgs):
-    neft_alpha: float | None = None
+@_rule("GenerationParameters")
+def _(a) -> None:
+    _need(a, "batch_size", "max_new_tokens")
 
 
-class TrainingArgs(BaseArgs):
-    random_args: RandomArgs = RandomArgs()
-    tokenizer_args: TokenizerArgs = TokenizerArgs()
-    model_args: ModelArgs = None
-    tuning_args: TuningArgs = None
-    optimizer_args: OptimizerArgs = OptimizerArgs()
-    lr_scheduler_args: LRSchedulerArgs = LRSchedulerArgs()
-    datasets: list[DatasetArgs] = []
-    save_args: SaveArgs = None
-    load_args: LoadArgs | None = None
-    training_parameters: TrainingParameters | None = None
-    logging_args: LoggingArgs = LoggingArgs()
-    mixed_precision_args: MixedPrecisionArgs = MixedPrecisionArgs()
-    distributed_args: DistributedArgs = DistributedArgs()
-    research_args: ResearchArgs = ResearchArgs()
-
-    def model_post_init(self, __context: Any) -> None:
-        _check_not_None([(self.model_args, "model_args"), (self.tuning_args, "tuning_args"),
-                         (self.save_args, "save_args"), (self.datasets, "datasets")])
-        if self.mixed_precision_args.dtype != "bf16":
-            raise NotImplementedError("the B200 path trains in bf16 mixed precision (mixed_precision_args.dtype: bf16)")
+@_rule("TrainingArgs")
+def _(a) -> None:
+    _need(a, "model_args", "tuning_args", "save_args")
+    assert a.datasets, "datasets cannot be None"
+    if a.mixed_precision_args.dtype != "bf16":
+        raise NotImplementedError("the B200 path trains in bf16 mixed precision (mixed_precision_args.dtype: bf16)")
 
 
-class GenerationParameters(BaseArgs):
-    """arguments.py:449-465"""
-
-    batch_size: int = None
-    do_sample: bool | None = None
-    max_new_tokens: int = None
-    temperature: float | None = None
-    top_k: int | None = None
-    top_p: float | None = None
-
-    def model_post_init(self, __context: Any) -> None:
-        _check_not_None([(self.batch_size, "batch_size"), (self.max_new_tokens, "max_new_tokens")])
-
-    def to_dict(self) -> dict:
-        return self.model_dump()
+@_rule("InferenceArgs")
+def _(a) -> None:
+    assert a.datasets, "datasets cannot be None"
+    _need(a, "generation_parameters", "output_dir")
+    if a.load_args is None:
+        assert a.model_args is not None, "model_args need to be specified if load_args are not specified"
+    else:
+        assert a.model_args is None, "model_args can't be specified with load_args"
 
 
-class InferenceArgs(BaseArgs):
-    """arguments.py:468-503: either `model_args` (a fresh / pretrained model) or `load_args` (a training checkpoint)"""
-
-    random_args: RandomArgs = RandomArgs()
-    tokenizer_args: TokenizerArgs = TokenizerArgs()
-    model_args: ModelArgs | None = None
-    datasets: list[DatasetArgs] = []
-    load_args: LoadArgs | None = None
-    generation_parameters: GenerationParameters = None
-    mixed_precision_args: MixedPrecisionArgs = MixedPrecisionArgs()
-    logging_args: LoggingArgs = LoggingArgs()
-    output_dir: str = None
-
-    def model_post_init(self, __context: Any) -> None:
-        _check_not_None([(self.datasets, "datasets"), (self.generation_parameters, "generation_parameters"),
-                         (self.output_dir, "output_dir")])
-        if self.load_args is None:
-            assert self.model_args is not None, "model_args need to be specified if load_args are not specified"
-        else:
-            assert self.model_args is None, "model_args can't be specified with load_args"
+@_rule("UnshardingArgs")
+def _(a) -> None:
+    _need(a, "load_args", "unsharded_path")
 
 
-class UnshardingArgs(BaseArgs):
-    """arguments.py:506-517"""
+GenerationParameters.to_dict = lambda self: self.model_dump()  # noqa: E731,F821  (reference: BaseArgs.to_dict)
 
-    load_args: LoadArgs = None
-    unsharded_path: str = None
-    mixed_precision_args: MixedPrecisionArgs = MixedPrecisionArgs()
-    logging_args: LoggingArgs = LoggingArgs()
-
-    def model_post_init(self, __context: Any) -> None:
-        _check_not_None([(self.load_args, "load_args"), (self.unsharded_path, "unsharded_path")])
-
-
-_MODE_ARGS = {"training": TrainingArgs, "inference": InferenceArgs, "unsharding": UnshardingArgs}
+_MODE_ARGS = {"training": TrainingArgs, "inference": InferenceArgs, "unsharding": UnshardingArgs}  # noqa: F821
 
 
 def get_args_from_dict(config: dict, mode=None):
