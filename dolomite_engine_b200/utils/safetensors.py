@@ -16,44 +16,37 @@ _MAX_SHARD_BYTES = 5 * 1024**3
 
 class SafeTensorsWeightsManager:
     def __init__(self, model_path: str) -> None:
-        if model_path.endswith(".safetensors"):
-            filenames = [model_path]
-        else:
-            filenames = sorted(os.path.join(model_path, f) for f in os.listdir(model_path) if f.endswith(".safetensors"))
-        self.tensor_filenames: dict[str, str] = {}
-        self.file_handles = {}
-        for filename in filenames:
-            f = safe_open(filename, framework="pytorch")
-            self.file_handles[filename] = f
-            for tensor_name in f.keys():
-                self.tensor_filenames[tensor_name] = filename
+        paths = [model_path] if model_path.endswith(".safetensors") else sorted(
+            os.path.join(model_path, f) for f in os.listdir(model_path) if f.endswith(".safetensors"))
+        self._files = {p: safe_open(p, framework="pytorch") for p in paths}
+        self._where: dict[str, str] = {name: p for p, handle in self._files.items() for name in handle.keys()}
+
+    def _handle(self, tensor_name: str):
+        return self._files[self._where[tensor_name]]
 
     def get_slice(self, tensor_name: str):
-        return self.file_handles[self.tensor_filenames[tensor_name]].get_slice(tensor_name)
+        return self._handle(tensor_name).get_slice(tensor_name)
 
     def get_tensor(self, tensor_name: str, dtype: torch.dtype | None = None, device=None) -> torch.Tensor:
-        t = self.file_handles[self.tensor_filenames[tensor_name]].get_tensor(tensor_name)
-        return t.to(dtype=dtype, device=device)
+        return self._handle(tensor_name).get_tensor(tensor_name).to(dtype=dtype, device=device)
 
     def get_shape(self, tensor_name: str):
         return self.get_slice(tensor_name).get_shape()
 
     def has_tensor(self, tensor_name: str) -> bool:
-        return tensor_name in self.tensor_filenames
+        return tensor_name in self._where
 
     def __len__(self) -> int:
-        return len(self.tensor_filenames)
+        return len(self._where)
 
     def __iter__(self):
-        yield from self.tensor_filenames
+        return iter(self._where)
 
     def __eq__(self, other: object) -> bool:
-        if not isinstance(other, SafeTensorsWeightsManager) or len(self) != len(other):
+        """same tensor names in the same order, same values"""
+        if not isinstance(other, SafeTensorsWeightsManager) or list(self) != list(other):
             return False
-        for a, b in zip(self, other):
-            if a != b or not self.get_tensor(a).equal(other.get_tensor(b)):
-                return False
-        return True
+        return all(self.get_tensor(name).equal(other.get_tensor(name)) for name in self)
 
     def state_dict(self) -> dict:
         return {name: self.get_tensor(name) for name in self}
