@@ -57,15 +57,30 @@ def collate(batch: list[dict], eos_token_id: int, use_padding_free_transformer: 
     return out
 
 
+_SPLIT_PREFIXES = {"train": ("train",), "val": ("val", "validation", "dev"), "test": ("test",)}
+
+
+def split_files(data_path: str, split: str | None) -> list[str]:
+    """JSON-lines files of one split.  A directory whose files are named after splits (`train*.jsonl`, `val*` /
+    `validation*` / `dev*`, `test*` -- what `datasets.load_dataset(dir)[split]` resolves in the reference,
+    data/huggingface.py:46-47) is divided accordingly; any other directory, or a single file, is all training data."""
+    if os.path.isfile(data_path):
+        return [data_path] if split in (None, "train") else []
+    names = sorted(f for f in os.listdir(data_path) if f.endswith((".jsonl", ".json")))
+    kind = {f: next((s for s, pre in _SPLIT_PREFIXES.items() if f.lower().startswith(pre)), None) for f in names}
+    if split is None or not any(kind.values()):
+        return [os.path.join(data_path, f) for f in names] if split in (None, "train") else []
+    return [os.path.join(data_path, f) for f in names if kind[f] == split]
+
+
 class JSONLinesSFTDataset:
     """data/instruction_tuning/base.py: every line of every `*.jsonl` under `data_path` is {"input": str, "output": str};
     `input_format` / `output_format` wrap the raw strings ("__input__" / "__output__" placeholders, data/base.py:56-82)"""
 
     def __init__(self, data_path: str, tokenize: Callable[[str], list[int]], eos_token_id: int,
                  input_format: str = "__input__", output_format: str = "__output__", max_input_tokens: int | None = None,
-                 max_output_tokens: int | None = None, training: bool = True):
-        files = [data_path] if os.path.isfile(data_path) else sorted(
-            os.path.join(data_path, f) for f in os.listdir(data_path) if f.endswith((".jsonl", ".json")))
+                 max_output_tokens: int | None = None, training: bool = True, split: str | None = None):
+        files = split_files(data_path, split)
         self.examples = []
         for path in files:
             with open(path) as fh:

@@ -4,6 +4,8 @@ oracle/pin_finetuning_feed.py in the build container.  Integer work: exact."""
 import json
 import os
 
+import pytest
+
 import torch
 
 from dolomite_engine_b200.data.finetuning import JSONLinesSFTDataset, batches, build_example, collate
@@ -107,3 +109,51 @@ def test_eight_simulated_ranks_cover_the_dataset_once():
     rows = {r: [i for b in MegatronBatchSampler(960, 0, 4, world, r) for i in b] for r in range(world)}
     flat = sorted(i for r in rows for i in rows[r])
     assert flat == list(range(960)) and all(len(rows[r]) == 120 for r in rows)
+
+
+def test_split_files_and_evaluate_loop(tmp_path):
+    """validation split of the SFT feed (what `load_dataset(dir)[split]` resolves in the reference) and finetune.evaluate
+    (finetune.py:156-219: mean loss over one pass, model back in training mode)"""
+    import json
+    import types
+
+    import torch
+
+    from dolomite_engine_b200.data.finetuning import JSONLinesSFTDataset, split_files
+    from dolomite_engine_b200.finetune import evaluate, make_sft_val_batches
+
+    d = tmp_path / "sft"
+    d.mkdir()
+    for name, n in (("train.jsonl", 6), ("validation.jsonl", 4), ("test.jsonl", 1)):
+        with open(d / name, "w") as f:
+            for i in range(n):
+                f.write(json.dumps({"input": f"{name[0]}{i}", "output": "ok"}) + "\n")
+    base = lambda p: [os.path.basename(x) for x in p]  # noqa: E731
+    assert base(split_files(str(d), "train")) == ["train.jsonl"] and base(split_files(str(d), "val")) == ["validation.jsonl"]
+    assert base(split_files(str(d), None)) == ["test.jsonl", "train.jsonl", "validation.jsonl"]
+    plain = tmp_path / "plain"
+    plain.mkdir()
+    (plain / "a.jsonl").write_text(json.dumps({"input": "x", "output": "y"}) + "\n")
+    assert base(split_files(str(plain), "train")) == ["a.jsonl"] and split_files(str(plain), "val") == []
+    assert split_files(str(d / "train.jsonl"), "train") == [str(d / "train.jsonl")] and split_files(str(d / "train.jsonl"), "val") == []
+    tok = lambda s: [ord(c) % 50 + 3 for c in s]  # noqa: E731
+    assert len(JSONLinesSFTDataset(str(d), tok, 2, split="val")) == 4 and len(JSONLinesSFTDataset(str(d), tok, 2, split="train")) == 6
+
+    ns = types.SimpleNamespace
+    args = ns(datasets=[ns(class_args={"data_path": str(d)}, input_format="__input__", output_format="__output__",
+                           max_input_tokens=None, max_output_tokens=None)],
+              training_parameters=ns(eval_during_training=True, micro_batch_size=2, loss_mask="output_only"),
+              model_args=ns(use_padding_free_transformer=True), random_args=ns(seed=1))
+    val = make_sft_val_batches(args, tok, 2, rank=0, world=1)
+    seen = []
+
+    class Fake(torch.nn.Module):
+        def forward(self, batch):
+            seen.append((self.training, len(batch["input_ids"])))
+            return torch.tensor(float(len(seen)))
+
+    model = Fake()
+    assert evaluate(val, model) == pytest.approx(1.5) and seen == [(False, 2), (False, 2)] and model.training
+    assert evaluate(None, model) is None
+    args.training_parameters.eval_during_training = False
+    assert make_sft_val_batches(args, tok, 2, 0, 1) is None
