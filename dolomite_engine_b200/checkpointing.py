@@ -191,6 +191,28 @@ def load_optimizer_state_dict(model, optimizer, osd: dict) -> None:
                 g[k] = tuple(v) if k == "betas" else v
 
 
+def resume_learning_rate(args, optimizer, lr_scheduler, iteration: int | None) -> None:
+    """checkpointing.py:419-445 ("phase 2" resume, used when the stored scheduler is NOT loaded): the YAML's schedule is
+    re-created at step `iteration` on top of the learning rates the loaded optimizer currently holds (they become the
+    schedule's base rates), and its state replaces the live scheduler's"""
+    from .optimization import get_scheduler
+
+    groups = optimizer.param_groups
+    kept = [g.get("initial_lr") for g in groups]
+    for g in groups:
+        g["initial_lr"] = g["lr"]
+    ls, tp = args.lr_scheduler_args, args.training_parameters
+    fresh = get_scheduler(optimizer, ls.num_warmup_steps, ls.num_constant_steps, ls.num_decay_steps, tp.num_training_steps,
+                          ls.lr_decay_style, ls.lr_decay_factor, ls.extra_lr_scheduler_args,
+                          last_epoch=-1 if iteration is None else iteration - 1)
+    for g, value in zip(groups, kept):
+        if value is None:
+            g.pop("initial_lr", None)
+        else:
+            g["initial_lr"] = value
+    lr_scheduler.load_state_dict(fresh.state_dict())
+
+
 def load_checkpoint_for_training(args, model, optimizer, lr_scheduler, train_dataloader):
     """checkpointing.py:149-263 -> (starting iteration, metadata, experiments tracker state) or None when nothing to load"""
     la = getattr(args, "load_args", None)
@@ -215,6 +237,8 @@ def load_checkpoint_for_training(args, model, optimizer, lr_scheduler, train_dat
     if getattr(la, "load_lr_scheduler", True) and lr_scheduler is not None:
         assert getattr(la, "load_optimizer", True), "load_lr_scheduler requires loading of optimizer"
         lr_scheduler.load_state_dict(torch.load(os.path.join(load_path, "lr_scheduler.pt"), weights_only=False))
+    elif getattr(la, "resume_learning_rate", True) and lr_scheduler is not None and optimizer is not None:
+        resume_learning_rate(args, optimizer, lr_scheduler, iteration)
     if getattr(la, "load_rng_state", True):
         p = os.path.join(load_path, "rng_state", f"rng_state-{rank}.pt")
         if os.path.exists(p):

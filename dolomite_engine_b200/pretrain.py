@@ -19,7 +19,7 @@ from .arguments import TrainingArgs, get_args
 from .distributed import wrap_model_for_distributed_training
 from .model_wrapper import get_model
 from .optimization import get_optimizer, get_scheduler
-from .train_utils import get_model_tflops, train_step
+from .train_utils import billion_tokens_per_day, get_model_tflops, get_torch_profiler, train_step
 
 
 class SyntheticPackedDataset:
@@ -202,21 +202,29 @@ def train(args: TrainingArgs, model, optimizer, scheduler, dataloader, rank: int
     if val_factory is not None:
         run_eval(starting_iteration)  # pretrain.py:121-122: evaluate before the first step
     losses = []
+    profiler = get_torch_profiler(args.logging_args.torch_profiler_trace_path, rank)  # pretrain.py:138-141
+    if profiler is not None:
+        profiler.__enter__()
     t0 = time.perf_counter()
     for step in range(starting_iteration + 1, tp.num_training_steps + 1):
         loss, grad_norm = train_step(model, optimizer, scheduler, train_dataloader=dataloader,
                                      gradient_accumulation_steps=tp.gradient_accumulation_steps,
                                      gradient_clipping=tp.gradient_clipping)
         losses.append(loss)
+        if profiler is not None:
+            profiler.step()
         if rank == 0 and step % args.logging_args.log_interval == 0:
             dt = (time.perf_counter() - t0) / (step - starting_iteration)
             print(f"step {step}: loss {loss:.4f} grad_norm {grad_norm:.4f} lr {scheduler.get_last_lr()[0]:.3e} "
-                  f"step_time {dt:.3f}s FLOPS {tflop_per_step / dt:.1f} TFLOP/s/GPU", flush=True)
+                  f"step_time {dt:.3f}s FLOPS {tflop_per_step / dt:.1f} TFLOP/s/GPU "
+                  f"throughput {billion_tokens_per_day(samples_per_step * seq, dt):.2f} B tokens/day", flush=True)
         if val_factory is not None and step % tp.eval_interval == 0:
             run_eval(step)
         if save_args is not None and (step % save_args.save_interval == 0 or step == tp.num_training_steps):
             save_checkpoint(args, model, optimizer, scheduler, None, None, step,
                             metadata={"consumed_samples": step * samples_per_step})
+    if profiler is not None:
+        profiler.__exit__(None, None, None)
     return losses
 
 

@@ -75,3 +75,23 @@ def get_model_tflops(config, batch_size: int, sequence_length: int, checkpointed
     model_flops = l * (forward_flops + backward_flops)
     model_flops += 6 * b * s * h * v
     return model_flops / 10**12
+
+
+def get_torch_profiler(trace_path: str | None, rank: int = 0, wait: int = 5, warmup: int = 5):
+    """`logging_args.torch_profiler_trace_path` (train_utils.py:182-194): one traced step on rank 0 after `wait + warmup`
+    steps, written as a TensorBoard trace; other ranks never reach their window.  The kernel-level evidence of this repo
+    comes from ncu (profiles/); this is the reference's timeline view of the same loop."""
+    if trace_path is None:
+        return None
+    acts = [torch.profiler.ProfilerActivity.CPU]
+    if torch.cuda.is_available():
+        acts.append(torch.profiler.ProfilerActivity.CUDA)
+    return torch.profiler.profile(
+        activities=acts,
+        schedule=torch.profiler.schedule(wait=wait if rank == 0 else 150000, warmup=warmup, active=1, repeat=1),
+        on_trace_ready=torch.profiler.tensorboard_trace_handler(trace_path), record_shapes=True)
+
+
+def billion_tokens_per_day(tokens_per_step: int, step_seconds: float) -> float:
+    """`throughput (B tokens/day)` of track_train_metrics (train_utils.py:119-179)"""
+    return tokens_per_step * 86400.0 / step_seconds / 1e9

@@ -216,3 +216,42 @@ def test_load_checkpoint_for_inference_rebuilds_the_model(tmp_path, fsdp_algorit
     assert args_ckpt.save_args.save_path == d and (state is None) == (fsdp_algorithm == 2)
     for u, v in zip(trained.model.engine.units, model.model.engine.units):
         assert torch.equal(u.master.data, v.master.data) and torch.equal(u.compute, v.compute)
+
+
+def test_resume_learning_rate_when_the_scheduler_is_not_loaded(tmp_path):
+    """checkpointing.py:232-238, :419-445: with load_lr_scheduler false (and resume_learning_rate true) the YAML's schedule is
+    rebuilt at the loaded iteration on top of the learning rates stored in the optimizer checkpoint"""
+    from dolomite_engine_b200 import checkpointing as C
+    from dolomite_engine_b200.optimization import get_scheduler
+
+    path = str(tmp_path / "ckpt")
+    engine, model, opt, sched = _build(1, 0, seed=1)  # lr 1e-3 scheduled by 1 / (1 + s): after one step lr = 5e-4
+    C.save_checkpoint(_args(path), model, opt, sched, None, None, 7)
+    engine2, model2, opt2, _ = _build(1, 0, seed=2)
+    ns = types.SimpleNamespace
+    args = _args(path, load=True)
+    args.load_args.load_lr_scheduler = False
+    args.load_args.resume_learning_rate = True
+    args.lr_scheduler_args = ns(num_warmup_steps=2, num_constant_steps=0, num_decay_steps=None, lr_decay_style="cosine",
+                                lr_decay_factor=0.1, extra_lr_scheduler_args={})
+    args.training_parameters = ns(num_training_steps=20)
+    live = get_scheduler(opt2, 2, 0, None, 20, "cosine", 0.1)
+    it, _, _ = C.load_checkpoint_for_training(args, model2, opt2, live, None)
+    assert it == 7 and live.last_epoch == 7
+    assert live.base_lrs == [pytest.approx(5e-4)]  # the loaded optimizer's lr became the base rate of the new phase
+    # the same schedule started from scratch with base lr 5e-4 and stepped 7 times yields the same multiplier
+    probe = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=5e-4)
+    ref = get_scheduler(probe, 2, 0, None, 20, "cosine", 0.1)
+    for _ in range(7):
+        probe.step()
+        ref.step()
+    live.step()
+    ref.step()
+    assert live.get_last_lr() == pytest.approx(ref.get_last_lr())
+    assert "initial_lr" in opt2.param_groups[0]  # torch's LambdaLR set it; the temporary override was undone
+    # resume_learning_rate false: the live scheduler is left untouched
+    engine3, model3, opt3, _ = _build(1, 0, seed=3)
+    args.load_args.resume_learning_rate = False
+    untouched = get_scheduler(opt3, 2, 0, None, 20, "cosine", 0.1)
+    C.load_checkpoint_for_training(args, model3, opt3, untouched, None)
+    assert untouched.last_epoch == 0

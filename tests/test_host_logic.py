@@ -237,3 +237,18 @@ def test_dropout_configs_construct_but_do_not_train():
         engine.forward(ids, ids, torch.tensor([0, 8], dtype=torch.int32), 8)
     assert not DolomiteEngine(GPTDolomiteConfig(n_embd=64, n_head=4, n_layer=1, vocab_size=264, resid_pdrop=0, embd_pdrop=0,
                                                 attn_pdrop=0), "cpu", seed=1).has_dropout
+
+
+def test_profiler_hook_and_throughput_helper(tmp_path):
+    """logging_args.torch_profiler_trace_path (train_utils.py:182-194) and the B tokens/day figure of the step log"""
+    from dolomite_engine_b200.train_utils import billion_tokens_per_day, get_torch_profiler
+
+    assert get_torch_profiler(None) is None
+    prof = get_torch_profiler(str(tmp_path / "trace"), rank=0, wait=1, warmup=1)
+    with prof:
+        for _ in range(4):
+            sum(range(1000))
+            prof.step()
+    assert any(f.endswith(".json") or f.endswith(".json.gz") for f in os.listdir(tmp_path / "trace"))  # one traced step
+    # 6 x 4096 tokens every 0.5625 s on 8 GPUs
+    assert billion_tokens_per_day(8 * 6 * 4096, 0.5625) == pytest.approx(8 * 6 * 4096 * 86400 / 0.5625 / 1e9)
