@@ -106,8 +106,20 @@ class ModelWrapper(nn.Module):
                               "one (token-id batches only)")
                 self.tokenizer = None
 
-    def save_pretrained(self, save_path: str) -> None:
-        self.model.save_pretrained(save_path)
+    def save_pretrained(self, save_path: str, state_dict: dict | None = None) -> None:
+        """model_wrapper/base.py:138-149: tokenizer + either the live model or a given full state dict whose keys carry the
+        wrapper prefix `model.`"""
+        if self.tokenizer is not None:
+            self.tokenizer.save_pretrained(save_path)
+        if state_dict is None:
+            self.model.save_pretrained(save_path)
+            return
+        from ..utils.safetensors import SafeTensorsWeightsManager
+
+        bad = [k for k in state_dict if not k.startswith("model.")]
+        assert not bad, f"state dict keys must start with 'model.': {bad[:3]}"
+        self.config.save_pretrained(save_path)
+        SafeTensorsWeightsManager.save_state_dict({k[len("model."):]: v for k, v in state_dict.items()}, save_path)
 
     def generate(self, batch: dict, generate_kwargs: dict) -> tuple[list[str] | list[list[int]], list[int]]:
         """model_wrapper/base.py:110-136: -> (generated text with the prompt trimmed, generated-token counts incl. eos).

@@ -255,3 +255,31 @@ def test_resume_learning_rate_when_the_scheduler_is_not_loaded(tmp_path):
     untouched = get_scheduler(opt3, 2, 0, None, 20, "cosine", 0.1)
     C.load_checkpoint_for_training(args, model3, opt3, untouched, None)
     assert untouched.last_epoch == 0
+
+
+def test_wrapper_save_pretrained_from_a_full_state_dict(tmp_path):
+    """model_wrapper/base.py:138-149: `save_pretrained(path, state_dict)` strips the wrapper prefix and writes safetensors +
+    config.json that `from_pretrained`-style readers understand"""
+    from dolomite_engine_b200 import checkpointing as C
+    from dolomite_engine_b200.arguments import get_args_from_dict
+    from dolomite_engine_b200.hf_models.config import CommonConfig
+    from dolomite_engine_b200.model_wrapper import get_model
+    from dolomite_engine_b200.utils.safetensors import SafeTensorsWeightsManager
+
+    pc = dict(model_type="gpt_dolomite", n_embd=64, n_head=4, n_layer=1, n_inner=96, vocab_size=264, attention_head_type="mha",
+              add_bias=False, activation_function="swiglu", position_embedding_type="rope", normalization_function="rmsnorm",
+              resid_pdrop=0, embd_pdrop=0, attn_pdrop=0)
+    args = get_args_from_dict({
+        "model_args": {"model_class": "AutoModelForCausalLM", "pretrained_config": pc, "use_padding_free_transformer": True},
+        "tuning_args": {"tuning_method": "full_finetuning"},
+        "datasets": [{"class_name": "JSONLinesDataset", "data_name": "s", "class_args": {"data_path": "x"}}],
+        "training_parameters": {"num_training_steps": 1, "micro_batch_size": 2, "eval_during_training": False},
+        "save_args": {"save_path": str(tmp_path), "save_interval": 1}, "mixed_precision_args": {"dtype": "bf16"}})
+    w = get_model(args, device=torch.device("cpu"))
+    sd = C.model_state_dict(w)
+    w.save_pretrained(str(tmp_path / "a"), state_dict=dict(sd))
+    got = SafeTensorsWeightsManager(str(tmp_path / "a")).state_dict()
+    assert set(got) == {k[len("model."):] for k in sd} and all(torch.equal(got[k[len("model."):]], v) for k, v in sd.items())
+    assert CommonConfig.from_pretrained(str(tmp_path / "a")).n_inner == 96
+    with pytest.raises(AssertionError):
+        w.save_pretrained(str(tmp_path / "b"), state_dict={"transformer.wte.weight": torch.zeros(1)})
