@@ -115,6 +115,12 @@ class _LRScheduler(LambdaLR):
 
 
 class ConstantScheduler(_LRScheduler):
+    def __init__(self, optimizer, num_warmup_steps, num_constant_steps, num_decay_steps, num_training_steps, lr_decay_factor,
+                 last_epoch=-1):
+        assert num_decay_steps == 0, "num_decay_steps should be 0 for constant schedule"  # scheduler.py:61
+        super().__init__(optimizer, num_warmup_steps, num_constant_steps, num_decay_steps, num_training_steps, lr_decay_factor,
+                         last_epoch=last_epoch)
+
     def _lr_lambda(self, num_steps: int) -> float:
         if self.lr_warmup_boundary > 0 and num_steps <= self.lr_warmup_boundary:
             return _linear(m=1 / self.lr_warmup_boundary, c=0, x=num_steps)
@@ -127,8 +133,17 @@ class CosineScheduler(_LRScheduler):
 
 
 class ExponentialScheduler(_LRScheduler):
-    def _decay(self, x, t):
-        return _exponential(a=1, b=0, t=t / math.log(1 / self.lr_decay_factor), x=x)
+    """optimization/scheduler.py:101-116: a * exp(-x / t) + b with a, b chosen so that the multiplier is 1 at the start of the
+    decay and `lr_decay_factor` after t steps; unlike cosine / linear it keeps following the exponential afterwards"""
+
+    def _lr_lambda(self, num_steps: int) -> float:
+        if self.lr_warmup_boundary > 0 and num_steps <= self.lr_warmup_boundary:
+            return _linear(m=1 / self.lr_warmup_boundary, c=0, x=num_steps)
+        if num_steps <= self.lr_constant_boundary:
+            return 1
+        f, e = self.lr_decay_factor, math.e
+        return _exponential(a=(1 - f) * e / (e - 1), b=(f * e - 1) / (e - 1), t=self.lr_decay_boundary - self.lr_constant_boundary,
+                            x=num_steps - self.lr_constant_boundary)
 
 
 class LinearScheduler(_LRScheduler):
@@ -136,8 +151,31 @@ class LinearScheduler(_LRScheduler):
         return _linear(m=(self.lr_decay_factor - 1) / t, c=1, x=x)
 
 
+class PowerScheduler(_LRScheduler):
+    """optimization/scheduler.py:137-181 (the Granite "power" schedule): after a linear warm-up the multiplier is
+    min(1, (a / lr) * (c * step)^b) with `a, b, c` from `extra_lr_scheduler_args`; no constant phase, `lr_decay_factor` unused.
+    The warm-up ramps to the value the power law has at its last warm-up step, so the two pieces meet."""
+
+    def __init__(self, optimizer, num_warmup_steps, num_constant_steps, num_decay_steps, num_training_steps, lr_decay_factor,
+                 a: float, b: float, c: float, last_epoch=-1):
+        assert num_constant_steps == 0, "num_constant_steps should be 0 for power law scheduler"
+        self.a, self.b, self.c = a, b, c
+        self._lr0 = optimizer.param_groups[0]["lr"]  # the optimizer's configured learning rate
+        self._warmup_peak = self._law(num_warmup_steps)
+        super().__init__(optimizer, num_warmup_steps, num_constant_steps, num_decay_steps, num_training_steps, lr_decay_factor,
+                         last_epoch=last_epoch)
+
+    def _law(self, step: int) -> float:
+        return min(1, (self.a / self._lr0) * (step * self.c) ** self.b)
+
+    def _lr_lambda(self, num_steps: int) -> float:
+        if self.lr_warmup_boundary > 0 and num_steps <= self.lr_warmup_boundary:
+            return _linear(m=self._warmup_peak / self.lr_warmup_boundary, c=0, x=num_steps)
+        return self._law(num_steps)
+
+
 _LR_SCHEDULER_CLASSES = {"constant": ConstantScheduler, "cosine": CosineScheduler, "exponential": ExponentialScheduler,
-                         "linear": LinearScheduler}
+                         "linear": LinearScheduler, "power": PowerScheduler}
 
 
 def get_scheduler(optimizer, num_warmup_steps, num_constant_steps, num_decay_steps, num_training_steps, lr_decay_style,

@@ -252,3 +252,30 @@ def test_profiler_hook_and_throughput_helper(tmp_path):
     assert any(f.endswith(".json") or f.endswith(".json.gz") for f in os.listdir(tmp_path / "trace"))  # one traced step
     # 6 x 4096 tokens every 0.5625 s on 8 GPUs
     assert billion_tokens_per_day(8 * 6 * 4096, 0.5625) == pytest.approx(8 * 6 * 4096 * 86400 / 0.5625 / 1e9)
+
+
+def test_lr_schedules_match_the_reference_sequences():
+    """optimization/scheduler.py:50-219 incl. the Granite `power` schedule: learning-rate sequences produced BY THE REFERENCE's
+    module (oracle/pin_lr_schedules.py -> tests/golden/lr_schedules.json), reproduced bit for bit"""
+    import json
+
+    import torch
+
+    from dolomite_engine_b200.optimization import get_scheduler
+
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "lr_schedules.json")))
+    assert {c["style"] for c in cases} == {"constant", "cosine", "exponential", "linear", "power"}
+    for c in cases:
+        opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=c["lr"])
+        sched = get_scheduler(opt, c["warmup"], c["constant"], c["decay"], 40, c["style"], 0.1, c["extra"])
+        got = []
+        for _ in range(len(c["values"])):
+            got.append(sched.get_last_lr()[0])
+            opt.step()
+            sched.step()
+        assert got == c["values"], c["style"]
+    with pytest.raises(ValueError):
+        get_scheduler(torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0), 1, 0, None, 10, "step", 0.1)
+    with pytest.raises(AssertionError):
+        get_scheduler(torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0), 1, 2, None, 10, "power", 0.1,
+                      {"a": 1.0, "b": -0.5, "c": 1.0})
