@@ -276,3 +276,15 @@ def test_merge_matches_reference_add_index(tmp_path):
     with pytest.raises(ValueError):  # token widths must agree
         merge([os.path.join(golden, "data_feed", "corpus_a"), os.path.join(golden, "data_feed", "corpus_b")], str(tmp_path / "bad"))
     assert [os.path.basename(p) for p in prefixes_in(os.path.join(golden, "data_feed"))] == ["corpus_a", "corpus_b"]
+
+
+def test_split_arithmetic_matches_reference():
+    """`split: "969,30,1"` -> normalised weights -> document index bounds, as evaluated by the reference's own functions
+    (oracle/pin_split_logic.py -> tests/golden/split_logic.json)"""
+    import json
+
+    for case in json.load(open(os.path.join(HERE, "golden", "split_logic.json"))):
+        vec = parse_and_normalize_split(case["split"])
+        assert list(vec) == case["vector"], case["split"]
+        for n, bounds in case["bounds"].items():
+            assert list(get_split_indices(vec, int(n))) == bounds, (case["split"], n)
