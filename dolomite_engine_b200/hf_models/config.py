@@ -130,6 +130,10 @@ class MoEDolomiteConfig(CommonConfig):
     model_type = "moe_dolomite"
     FIELDS = (("num_experts", 8), ("num_experts_per_tok", 2), ("output_router_logits", False), ("router_aux_loss_coef", 0.001))
 
+    def _finalise(self) -> None:
+        super()._finalise()
+        assert self.init_method == "normal", "MoEDolomite supports the normal init method only (moe_dolomite/config.py:83)"
+
 
 _CONFIG_CLASSES = {c.model_type: c for c in (GPTDolomiteConfig, MoEDolomiteConfig)}
 

