@@ -188,7 +188,14 @@ def train(args: TrainingArgs, model, optimizer, scheduler, dataloader, rank: int
 
     tp = args.training_parameters
     seq = args.datasets[0].class_args["sequence_length"]
-    tflop_per_step = get_model_tflops(model.config, tp.micro_batch_size * tp.gradient_accumulation_steps, seq)
+    # recomputed blocks count as extra forward FLOPs, like the reference (train_utils.py:225-230)
+    dargs = args.distributed_args
+    fraction = 0.0
+    if dargs.gradient_checkpointing_method is not None:
+        every = int((dargs.gradient_checkpointing_args or {}).get("checkpoint_every", 1))
+        fraction = (model.config.n_layer // every) / model.config.n_layer
+    tflop_per_step = get_model_tflops(model.config, tp.micro_batch_size * tp.gradient_accumulation_steps, seq,
+                                      checkpointed_fraction=fraction)
     samples_per_step = tp.micro_batch_size * tp.gradient_accumulation_steps * world
     save_args = getattr(args, "save_args", None)
     val_factory = make_megatron_val_dataloader(args, rank, world) if tp.eval_during_training else None

@@ -333,3 +333,17 @@ def test_yaml_schema_matches_the_reference_sections():
             if isinstance(mine, dict) and isinstance(default, dict):  # embedded section: ignore the documented additions
                 mine = {kk: vv for kk, vv in mine.items() if kk in default}
             assert mine == default, (section, k)
+
+
+def test_model_tflops_formula_with_checkpointed_blocks():
+    """train_utils.py:197-236 (checked against the reference function on a grid while pinning): recomputed blocks add
+    `fraction` forward passes to the 2x backward"""
+    from dolomite_engine_b200.hf_models import GPTDolomiteConfig
+    from dolomite_engine_b200.train_utils import get_model_tflops
+
+    c = GPTDolomiteConfig(n_embd=2560, n_head=32, n_layer=32, n_inner=10240, vocab_size=49152, attention_head_type="mha",
+                          activation_function="swiglu")
+    b, s, h, f, v, l = 6, 4096, 2560, 10240, 49152, 32
+    fwd = 4 * b * s * h * (h * 2 + s) + 6 * b * s * h * f
+    assert get_model_tflops(c, b, s) == pytest.approx((l * 3 * fwd + 6 * b * s * h * v) / 1e12)
+    assert get_model_tflops(c, b, s, checkpointed_fraction=0.5) == pytest.approx((l * 3.5 * fwd + 6 * b * s * h * v) / 1e12)
