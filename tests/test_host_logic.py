@@ -347,3 +347,28 @@ def test_model_tflops_formula_with_checkpointed_blocks():
     fwd = 4 * b * s * h * (h * 2 + s) + 6 * b * s * h * f
     assert get_model_tflops(c, b, s) == pytest.approx((l * 3 * fwd + 6 * b * s * h * v) / 1e12)
     assert get_model_tflops(c, b, s, checkpointed_fraction=0.5) == pytest.approx((l * 3.5 * fwd + 6 * b * s * h * v) / 1e12)
+
+
+def test_init_rules_match_the_reference_block_modules():
+    """std of every weight and the shape of every block parameter as constructed by the REFERENCE's GPTDolomiteBlock
+    (oracle/pin_init_rules.py -> tests/golden/init_rules.json) == engine._block_specs"""
+    import json
+
+    from dolomite_engine_b200.engine import _block_specs
+    from dolomite_engine_b200.hf_models import GPTDolomiteConfig
+
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "init_rules.json")))
+    for name, case in gold.items():
+        kw = {"normalization_function": "rmsnorm", **case["config"]}
+        cfg = GPTDolomiteConfig(vocab_size=264, n_positions=64, position_embedding_type="rope", resid_pdrop=0, embd_pdrop=0,
+                                attn_pdrop=0, **kw)
+        specs = {n[len("transformer.h.1."):]: (shape, init) for n, shape, init in _block_specs(cfg, 1)}
+        assert {k: list(v[0]) for k, v in specs.items()} == case["shapes"], name
+        for pname, std in case["std"].items():
+            kind, _, value = specs[pname][1].partition(":")
+            assert kind == "normal" and float(value) == pytest.approx(std, rel=1e-12), (name, pname)
+        for pname, (shape, init) in specs.items():
+            if pname.endswith(".bias"):
+                assert init == "zeros", (name, pname)
+            elif pname.startswith("ln_"):
+                assert init == "ones", (name, pname)
