@@ -153,10 +153,8 @@ def _root_specs(cfg: CommonConfig) -> list[tuple[str, tuple, str]]:
     specs = [("transformer.wte.weight", (V, H), f"normal:{cfg.initializer_range}")]
     specs.append(("transformer.ln_f.weight", (H,), "ones"))
     if not cfg.tie_word_embeddings:
-        std = cfg.initializer_range
-        if cfg.init_method == "mup":
-            std /= math.sqrt(cfg.m_width)
-        specs.append(("lm_head.weight", (V, H), f"normal:{std}"))
+        # gpt_dolomite/main.py:19-21: ParameterizedLinear(..., std=initializer_range) -- no muP width scaling on the head
+        specs.append(("lm_head.weight", (V, H), f"normal:{cfg.initializer_range}"))
     # appended last: the random stream (and flat layout) of every rope / rmsnorm configuration stays what it was
     if cfg.normalization_function == "layernorm":
         specs.append(("transformer.ln_f.bias", (H,), "zeros"))

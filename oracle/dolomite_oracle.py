@@ -461,7 +461,7 @@ def init_params(cfg: OracleConfig, seed: int = 42) -> dict:
                 p[pre + "mlp.c_proj.bias"] = torch.zeros(H)
     p["transformer.ln_f.weight"] = torch.ones(H)
     if not cfg.tie_word_embeddings:
-        p["lm_head.weight"] = n(V, H, sd=std)
+        p["lm_head.weight"] = n(V, H, sd=cfg.initializer_range)  # main.py:19-21: no muP width scaling on the head
     # drawn last so that the random stream of every earlier configuration is unchanged
     if cfg.position_embedding_type == "learned_absolute":
         p["transformer.wpe.weight"] = n(cfg.n_positions, H, sd=cfg.initializer_range)

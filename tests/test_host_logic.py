@@ -372,3 +372,19 @@ def test_init_rules_match_the_reference_block_modules():
                 assert init == "zeros", (name, pname)
             elif pname.startswith("ln_"):
                 assert init == "ones", (name, pname)
+
+
+def test_root_parameter_init_rules():
+    """gpt_dolomite/base.py:136, :528 and main.py:19-21: wte, wpe and an untied lm_head are all drawn with
+    std = initializer_range -- the muP width scaling applies to the block projections only"""
+    from dolomite_engine_b200.engine import _root_specs
+    from dolomite_engine_b200.hf_models import GPTDolomiteConfig
+
+    cfg = GPTDolomiteConfig(n_embd=64, n_head=4, n_layer=2, vocab_size=264, n_positions=32, init_method="mup", m_width=4.0,
+                            initializer_range=0.1, tie_word_embeddings=False, position_embedding_type="learned_absolute",
+                            normalization_function="layernorm")
+    specs = {n: (tuple(s), i) for n, s, i in _root_specs(cfg)}
+    assert specs["transformer.wte.weight"] == ((264, 64), "normal:0.1")
+    assert specs["lm_head.weight"] == ((264, 64), "normal:0.1")
+    assert specs["transformer.wpe.weight"] == ((32, 64), "normal:0.1")
+    assert specs["transformer.ln_f.weight"][1] == "ones" and specs["transformer.ln_f.bias"][1] == "zeros"
