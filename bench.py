@@ -197,8 +197,6 @@ def run_ours(args) -> None:
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    if os.environ.get("DOLO_ATTN_BWD"):
-        K.set_option("attn_bwd_version", int(os.environ["DOLO_ATTN_BWD"]))
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)

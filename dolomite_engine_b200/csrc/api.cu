@@ -25,35 +25,15 @@ extern "C" const char* dolomite_b200_last_error() { return g_err; }
 
 extern "C" int dolomite_b200_abi_version() { return DOLOMITE_B200_ABI_VERSION; }
 
-static int g_attn_bwd_version = 3;
-int dolo_option_attn_bwd_version() { return g_attn_bwd_version; }
 static int g_gemm_cta_pair = 1;
 static int g_gemm_sm_margin = 0;
 int dolo_option_gemm_sm_margin() { return g_gemm_sm_margin; }
-static int g_attn_fwd_version = 1;
-int dolo_option_attn_fwd_version() { return g_attn_fwd_version; }
 int dolo_option_gemm_cta_pair() { return g_gemm_cta_pair; }
-static int g_attn_bwd_experiment = 0;
-int dolo_option_attn_bwd_experiment() { return g_attn_bwd_experiment; }
 
 extern "C" int dolomite_b200_set_option(const char* key, int value) {
-    if (key != nullptr && strcmp(key, "attn_bwd_version") == 0) {
-        DOLO_REQUIRE(value >= 1 && value <= 4, "attn_bwd_version must be 1, 2, 3 or 4");
-        g_attn_bwd_version = value;
-        return DOLO_OK;
-    }
-    if (key != nullptr && strcmp(key, "attn_fwd_version") == 0) {
-        DOLO_REQUIRE(value == 1 || value == 2, "attn_fwd_version must be 1 or 2");
-        g_attn_fwd_version = value;
-        return DOLO_OK;
-    }
     if (key != nullptr && strcmp(key, "gemm_sm_margin") == 0) {
         DOLO_REQUIRE(value >= 0 && value <= 64, "gemm_sm_margin must be in [0, 64]");
         g_gemm_sm_margin = value;
-        return DOLO_OK;
-    }
-    if (key != nullptr && strcmp(key, "attn_bwd_experiment") == 0) {
-        g_attn_bwd_experiment = value;  // diagnostic bit mask (timing experiments; results are WRONG when non-zero)
         return DOLO_OK;
     }
     if (key != nullptr && strcmp(key, "gemm_cta_pair") == 0) {

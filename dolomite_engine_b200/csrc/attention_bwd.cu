@@ -31,7 +31,6 @@ struct BwdParams {
     int64_t T;
     int n_groups, q_per_group, n_heads;
     float scale, scale_log2;
-    int experiment;  // diagnostic bit mask, 0 in production (bit 0: skip the dQ reductions -> timing only, dQ is wrong)
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -415,16 +414,12 @@ int make_maps(const void* base, int64_t ld, int64_t rows, CUtensorMap* m64, CUte
     return DOLO_OK;
 }
 
-#include "attention_bwd_v2.cuh"
 #include "attention_bwd_v3.cuh"
 
+// head_dim <= 80: pipelined kernel (two softmax warp groups); larger head dims: serial kernel below
 template <int HD>
 int launch_bwd_pipelined(const void* dout, const void* qkv, int64_t row_stride, const BwdParams& p, cudaStream_t st) {
-    // 2: one softmax group, 3: two groups (default), 4: four groups (704 threads; measured 4 % slower than 3)
-    const int v = dolo_option_attn_bwd_version();
-    if (v >= 4) return launch_bwd_v3<HD, 4>(dout, qkv, row_stride, p, st);
-    if (v == 3) return launch_bwd_v3<HD, 2>(dout, qkv, row_stride, p, st);
-    return launch_bwd_v2<HD>(dout, qkv, row_stride, p, st);
+    return launch_bwd_v3<HD, 2>(dout, qkv, row_stride, p, st);
 }
 
 template <int HD>
@@ -499,19 +494,12 @@ extern "C" int dolomite_b200_attn_varlen_bwd(const void* dout, const void* qkv, 
     p.n_heads = nh;
     p.scale = softmax_scale;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
-    p.experiment = dolo_option_attn_bwd_experiment();
     int rc;
     switch (head_dim) {
         case 16: rc = launch_bwd<16>(dout, qkv, row_stride, p, st); break;
         case 32: rc = launch_bwd<32>(dout, qkv, row_stride, p, st); break;
-        case 64:
-            rc = dolo_option_attn_bwd_version() >= 2 ? launch_bwd_pipelined<64>(dout, qkv, row_stride, p, st)
-                                                     : launch_bwd<64>(dout, qkv, row_stride, p, st);
-            break;
-        case 80:
-            rc = dolo_option_attn_bwd_version() >= 2 ? launch_bwd_pipelined<80>(dout, qkv, row_stride, p, st)
-                                                     : launch_bwd<80>(dout, qkv, row_stride, p, st);
-            break;
+        case 64: rc = launch_bwd_pipelined<64>(dout, qkv, row_stride, p, st); break;
+        case 80: rc = launch_bwd_pipelined<80>(dout, qkv, row_stride, p, st); break;
         case 96: rc = launch_bwd<96>(dout, qkv, row_stride, p, st); break;
         case 128: rc = launch_bwd<128>(dout, qkv, row_stride, p, st); break;
         default: return dolo_set_error("attn_bwd: unsupported head_dim %d (supported: 16,32,64,80,96,128)", head_dim);

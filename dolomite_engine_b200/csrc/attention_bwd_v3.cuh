@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
         // Each warp copies its 32 rows of the dQ accumulator to a private shared-memory slab and hands the slab to the
         // TMA engine as ONE bulk fp32 reduce-add into dq_accum[head, q0 + 32*sub .., :] (contiguous in the [heads, T, HD]
         // workspace).  The per-thread red.global.add.v4.f32 version spent 26 % of the kernel in L2 atomic traffic
-        // (profiles: attn_bwd_experiments, 1.88 ms -> 1.38 ms with the reductions removed).
+        // (profiles/r01_probe_call18_dq_bulk_reduce.jsonl: 1.88 ms -> 1.38 ms with the reductions removed).
         const int sub = warp & 3;
         const uint32_t t_lane = tmem_base + (uint32_t(sub * 32) << 16);
         float* slab = sDQ + (sub * 32) * HD;
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
                 const int q0 = i * ATT_TILE + sub * 32;
                 int rows = loc.doc_len - q0;
                 rows = rows > 32 ? 32 : rows;
-                if (rows > 0 && !(p.experiment & 1))
+                if (rows > 0)
                     bulk_reduce_add_f32(p.dq_accum + (int64_t(head) * p.T + loc.doc_start + q0) * HD, slab_u32,
                                         uint32_t(rows) * HD * 4);
                 tma_store_commit();

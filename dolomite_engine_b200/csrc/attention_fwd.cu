@@ -358,8 +358,6 @@ int launch_fwd(const void* qkv, int64_t row_stride, const FwdParams& p, int max_
     return DOLO_OK;
 }
 
-#include "attention_fwd_v2.cuh"
-
 }  // namespace
 
 extern "C" int dolomite_b200_attn_varlen_fwd(const void* qkv, int64_t row_stride, void* out, float* lse,
@@ -387,16 +385,10 @@ extern "C" int dolomite_b200_attn_varlen_fwd(const void* qkv, int64_t row_stride
     switch (head_dim) {
         case 16: return launch_fwd<16>(qkv, row_stride, p, max_seqlen, st);
         case 32: return launch_fwd<32>(qkv, row_stride, p, max_seqlen, st);
-        case 64:
-            return dolo_option_attn_fwd_version() >= 2 ? launch_fwd_v2<64>(qkv, row_stride, p, st)
-                                                       : launch_fwd<64>(qkv, row_stride, p, max_seqlen, st);
-        case 80:
-            return dolo_option_attn_fwd_version() >= 2 ? launch_fwd_v2<80>(qkv, row_stride, p, st)
-                                                       : launch_fwd<80>(qkv, row_stride, p, max_seqlen, st);
+        case 64: return launch_fwd<64>(qkv, row_stride, p, max_seqlen, st);
+        case 80: return launch_fwd<80>(qkv, row_stride, p, max_seqlen, st);
         case 96: return launch_fwd<96>(qkv, row_stride, p, max_seqlen, st);
-        case 128:
-            return dolo_option_attn_fwd_version() >= 2 ? launch_fwd_v2<128>(qkv, row_stride, p, st)
-                                                       : launch_fwd<128>(qkv, row_stride, p, max_seqlen, st);
+        case 128: return launch_fwd<128>(qkv, row_stride, p, max_seqlen, st);
         default: return dolo_set_error("attn_fwd: unsupported head_dim %d (supported: 16,32,64,80,96,128)", head_dim);
     }
 }

@@ -36,14 +36,11 @@ int dolo_check_cuda(cudaError_t e, const char* what);
     } while (0)
 
 int dolo_num_sms();
-int dolo_option_attn_bwd_version();  // 1 = serial reference kernel, 2/3 = pipelined (head_dim <= 80)
-int dolo_option_attn_fwd_version();  // 1 = one query tile per CTA, 2 = ping-pong over two query tiles
 int dolo_option_gemm_cta_pair();     // 1 = dense GEMMs use the CTA-pair (cta_group::2) kernel when M >= 256
 // SMs left free by the persistent GEMM grids.  A persistent grid sized to ALL SMs runs up to 2x longer when a
 // communication kernel (NCCL all-gather / reduce-scatter, a few CTAs) occupies some SMs: the GEMM CTAs that do not fit
 // only start when a whole persistent CTA retires.  The sharded data-parallel runtime sets this to NCCL's CTA budget.
 int dolo_option_gemm_sm_margin();
-int dolo_option_attn_bwd_experiment();
 
 // TMA descriptor encode through the driver entry point (no link-time libcuda dependency).
 // rank-2 / rank-3 bf16/f32 tiled maps.  dims/strides innermost first; strides in BYTES for dims >= 1.

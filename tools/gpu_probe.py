@@ -637,81 +637,7 @@ def attn_bench_c2():
 
 
 @case
-def attn_bench_c2_bwd_v2():
-    from dolomite_engine_b200 import kernels as k
-
-    k.set_option("attn_bwd_version", 2)
-    return _attn_bench(4096, 2, 32, 80)
-
-
-@case
-def attn_fwd_v2_correctness():
-    from dolomite_engine_b200 import kernels as k
-
-    k.set_option("attn_fwd_version", 2)
-    out = {}
-    ok = True
-    for name, (lens, ng, g, hd) in {"hd80_ragged": ([200, 130, 515], 4, 1, 80), "hd64_ragged": ([100, 37, 300, 1, 129], 4, 1, 64),
-                                    "hd64_gqa_long": ([1024, 700], 2, 2, 64), "hd80_one_tile": ([77], 2, 1, 80),
-                                    "hd128_gqa": ([300, 77, 260, 1025], 2, 4, 128), "hd80_odd_tiles": ([128 * 5], 2, 1, 80)}.items():
-        r = _attn_case(lens, ng, g, hd)
-        out[name] = {x: r[x]["rel_l2"] for x in ("fwd", "dq", "dk", "dv")}
-        out[name]["lse"] = r["lse"]["max_abs"]
-        ok = ok and r["ok"]
-    out["ok"] = ok
-    return out
-
-
-@case
-def attn_bench_c2_fwd_v2():
-    from dolomite_engine_b200 import kernels as k
-
-    k.set_option("attn_fwd_version", 2)
-    return _attn_bench(4096, 2, 32, 80)
-
-
-@case
-def attn_bench_c2_bwd_v3():
-    from dolomite_engine_b200 import kernels as k
-
-    k.set_option("attn_bwd_version", 3)
-    return _attn_bench(4096, 2, 32, 80)
-
-
-@case
-def attn_v3_correctness():
-    from dolomite_engine_b200 import kernels as k
-
-    k.set_option("attn_bwd_version", 3)
-    out = {}
-    ok = True
-    for name, (lens, ng, g, hd) in {"hd80_ragged": ([200, 130, 515], 4, 1, 80), "hd64_ragged": ([100, 37, 300, 1, 129], 4, 1, 64),
-                                    "hd64_gqa_long": ([1024, 700], 2, 2, 64), "hd80_one_tile": ([77], 2, 1, 80)}.items():
-        r = _attn_case(lens, ng, g, hd)
-        out[name] = {x: r[x]["rel_l2"] for x in ("fwd", "dq", "dk", "dv")}
-        ok = ok and r["ok"]
-    out["ok"] = ok
-    return out
-
-
-@case
-def attn_v2_correctness():
-    from dolomite_engine_b200 import kernels as k
-
-    k.set_option("attn_bwd_version", 2)
-    out = {}
-    ok = True
-    for name, (lens, ng, g, hd) in {"hd80_ragged": ([200, 130, 515], 4, 1, 80), "hd64_ragged": ([100, 37, 300, 1, 129], 4, 1, 64),
-                                    "hd64_gqa_long": ([1024, 700], 2, 2, 64), "hd80_one_tile": ([77], 2, 1, 80)}.items():
-        r = _attn_case(lens, ng, g, hd)
-        out[name] = {x: r[x]["rel_l2"] for x in ("fwd", "dq", "dk", "dv")}
-        ok = ok and r["ok"]
-    out["ok"] = ok
-    return out
-
-
-@case
-def attn_bench_hd128():
+def attn_bench_hd128_s4096():
     return _attn_bench(4096, 2, 16, 128)
 
 
@@ -725,42 +651,6 @@ def env_info():
 
 
 # ---------------------------------------------------------------------------------------------
-@case
-def attn_bwd_experiments():
-    """timing-only what-if runs of the attention backward (results are wrong when the mask is non-zero):
-    bit 0 = no dQ reductions, bit 1 = no exp2"""
-    torch = _t()
-    from dolomite_engine_b200 import kernels as k
-
-    S, B, nh, hd = 4096, 4, 32, 80
-    T = S * B
-    qkv = torch.randn(T, nh * 3 * hd, device="cuda").bfloat16()
-    cu = torch.arange(0, T + 1, S, dtype=torch.int32, device="cuda")
-    scale = hd ** -0.5
-    dout = torch.randn(T, nh * hd, device="cuda").bfloat16()
-    out, lse = k.attn_varlen_fwd(qkv, cu, S, nh, 1, hd, scale)
-    dqkv = torch.empty_like(qkv)
-    res = {}
-    flops = 2.5 * 4.0 * S * S * hd * nh * B / 2
-    ref = None
-    for version in (3, 4):
-        k.set_option("attn_bwd_version", version)
-        for mask in (0, 1, 0):
-            k.set_option("attn_bwd_experiment", mask)
-            ms = _time(lambda: k.attn_varlen_bwd(dout, qkv, out, lse, cu, S, nh, 1, hd, scale, dqkv=dqkv), iters=5)
-            res.setdefault(f"v{version}_mask{mask}", []).append({"ms": ms, "tflops": flops / ms / 1e9})
-        if ref is None:
-            ref = dqkv.clone()
-        else:
-            res["v4_vs_v3"] = _err(dqkv, ref)
-    k.set_option("attn_bwd_experiment", 0)
-    k.set_option("attn_bwd_version", 3)
-    ms = _time(lambda: k.attn_varlen_fwd(qkv, cu, S, nh, 1, hd, scale, out=out), iters=10)
-    res["fwd"] = {"ms": ms, "tflops": flops / 2.5 / ms / 1e9}
-    res["ok"] = True
-    return res
-
-
 @case
 def moe_bench_c4():
     """MoEDolomite C4 shape (H 2048, 16 heads hd 128, 8 experts top-2, F 4096 per expert, seq 2048), 2 layers, mbs 8
