@@ -45,6 +45,9 @@ SIGNATURES: dict[str, tuple] = {
     "dolomite_b200_embedding_fwd": (_I, [_P, _P, _P, _L, _I, _L, _F, _P]),
     "dolomite_b200_embedding_bwd": (_I, [_P, _P, _P, _L, _I, _L, _F, _P]),
     "dolomite_b200_cross_entropy_fwd_bwd": (_I, [_P, _L, _P, _P, _P, _P, _P, _L, _L, _L, _F, _F, _P]),
+    "dolomite_b200_cross_entropy_count": (_I, [_P, _L, _L, _P, _P]),
+    "dolomite_b200_cross_entropy_rows": (_I, [_P, _L, _P, _P, _P, _P, _L, _L, _L, _F, _F, _P]),
+    "dolomite_b200_cross_entropy_mean": (_I, [_P, _L, _P, _P, _P]),
     "dolomite_b200_colsum_accum": (_I, [_P, _L, _P, _L, _L, _F, _P]),
     "dolomite_b200_scale_bf16_by_device_scalar": (_I, [_P, _L, _P, _P]),
     "dolomite_b200_add_scaled": (_I, [_P, _P, _P, _F, _L, _P]),

@@ -101,7 +101,7 @@ _SCHEMA: dict[str, dict[str, tuple]] = {
         "torch_compile": (bool, False), "dispatching_dataloader": (bool, False), "tensor_parallel_size": (int, 1),
         "tensor_parallel_word_embeddings": (bool, False), "sequence_parallel": (bool, False),
         "data_parallel_size": (O[int], None), "timeout_minutes": (O[int], None), "fsdp_algorithm": (int, 1),
-        "reshard_after_forward": (bool, False)},
+        "reshard_after_forward": (O[bool], None)},
     "LoggingArgs": {
         "logging_level": (str, "INFO"), "log_interval": (int, 1), "aim_args": (O[dict], None), "wandb_args": (O[dict], None),
         "experiments_tracker_name": (O[str], None), "use_colored_logs": (bool, False), "torch_profiler_trace_path": (O[str], None)},

@@ -159,9 +159,16 @@ def save_checkpoint(args, model, optimizer, lr_scheduler, train_dataloader, expe
                   open(os.path.join(save_root, "latest_checkpointed_iteration.json"), "w"), indent=4)
 
 
+def _strip_wrapper(key: str) -> str:
+    """reference checkpoints written with block gradient checkpointing carry the activation-checkpoint wrapper's infix
+    (`...h.3._checkpoint_wrapped_module.attn...`, checkpointing.py:41); the engine's names do not"""
+    return key.replace("._checkpoint_wrapped_module", "")
+
+
 def load_model_state_dict(model, sd: dict[str, torch.Tensor]) -> None:
     """every rank reads the full dict and keeps its slice (+ the full bf16 compute copy), like FULL_STATE_DICT loading"""
     engine = _engine(model)
+    sd = {_strip_wrapper(k): v for k, v in sd.items()}
     bad = [k for k in sd if not k.startswith(_PREFIX)]
     if bad:
         raise KeyError(f"model checkpoint keys must start with '{_PREFIX}': {bad[:5]}")
@@ -170,7 +177,7 @@ def load_model_state_dict(model, sd: dict[str, torch.Tensor]) -> None:
 
 def load_optimizer_state_dict(model, optimizer, osd: dict) -> None:
     engine = _engine(model)
-    state = osd["state"]
+    state = {_strip_wrapper(k): v for k, v in osd["state"].items()}
     step = None
     for u in engine.units:
         st = optimizer.state[u.master]

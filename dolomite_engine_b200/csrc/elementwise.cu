@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ------------------------------------------------------------------------------------------
-// Cross entropy: one block per row.  Pass 1 online (max, sumexp); pass 2 rewrites the row as the gradient.
+// Cross entropy: one block (or cluster) per row, row held in registers between the reduction and the gradient write.
 // ------------------------------------------------------------------------------------------
 constexpr int kCeThreads = 512;
 
@@ -592,84 +592,142 @@ __global__ void ce_count_kernel(const int64_t* __restrict__ labels, int64_t T, i
     }
 }
 
-__global__ void __launch_bounds__(kCeThreads)
-    ce_fwd_bwd_kernel(const uint4* __restrict__ logits, int64_t ld8, const int64_t* __restrict__ labels,
-                      uint4* __restrict__ dlogits, float* __restrict__ loss_tok, const float* __restrict__ scratch,
-                      int64_t T, int64_t V, int64_t ignore_index, float logit_scale, float grad_scale) {
-    __shared__ float red_m[kCeThreads / 32], red_s[kCeThreads / 32];
-    __shared__ float s_lse;
+// Row-resident cross entropy: a row (or, for wide vocabularies, 1/SPLIT of a row per CTA of a SPLIT-CTA cluster) is read
+// from HBM ONCE into registers (NV 16-byte vectors per thread), max and sum-of-exponentials are reduced in the block (and
+// across the cluster through distributed shared memory), and the gradient row is written from the same registers: 4 B per
+// logit of traffic, the algorithmic minimum (the first version re-read the row: 6 B per logit, 0.58 of the copy peak in
+// profiles/r01_ncu_ce_call28.txt).  logits and dlogits may alias, hence no __restrict__ / __ldg on them.
+__device__ __forceinline__ float ce_block_reduce(float v, float* red, bool is_max) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = is_max ? warp_max(v) : warp_sum(v);
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    float t = lane < (kCeThreads / 32) ? red[lane] : (is_max ? -INFINITY : 0.f);
+    t = is_max ? warp_max(t) : warp_sum(t);
+    __syncthreads();
+    return t;
+}
+__device__ __forceinline__ void st_cluster_f32(float* local_smem, uint32_t rank, float v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem)), "r"(rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+
+template <int NV, int SPLIT>
+__global__ void __launch_bounds__(kCeThreads, 1)
+    ce_rows_kernel(const uint4* logits, int64_t ld8, const int64_t* __restrict__ labels, uint4* dlogits,
+                   float* __restrict__ loss_tok, const float* __restrict__ scratch, int64_t T, int64_t V,
+                   int64_t ignore_index, float logit_scale, float grad_scale) {
+    __shared__ float red[kCeThreads / 32];
+    __shared__ float xch[2][4];  // [max | sum][cluster rank]: written by every CTA of the cluster (DSMEM)
+    const int crank = SPLIT > 1 ? int(cluster_ctarank()) : 0;
     const int64_t V8 = V >> 3;
+    const int64_t per = (V8 + SPLIT - 1) / SPLIT;
+    const int64_t v_lo = crank * per, v_hi = min(V8, v_lo + per);
     const float n_valid = scratch[0];
     const float gs = n_valid > 0.f ? grad_scale / n_valid : 0.f;
-    for (int64_t row = blockIdx.x; row < T; row += gridDim.x) {
+    const int64_t n_clusters = gridDim.x / SPLIT;
+    for (int64_t row = blockIdx.x / SPLIT; row < T; row += n_clusters) {
         const uint4* lr = logits + row * ld8;
         uint4* dr = dlogits + row * ld8;
         const int64_t label = labels[row];
-        const bool valid = (label != ignore_index);
-        if (!valid) {
-            // uniform per block: zero gradient row
-            for (int64_t i = threadIdx.x; i < V8; i += blockDim.x) dr[i] = make_uint4(0, 0, 0, 0);
-            if (threadIdx.x == 0) loss_tok[row] = 0.f;
+        if (label == ignore_index) {  // uniform per cluster: zero gradient row
+            for (int64_t i = v_lo + threadIdx.x; i < v_hi; i += kCeThreads) dr[i] = make_uint4(0, 0, 0, 0);
+            if (crank == 0 && threadIdx.x == 0) loss_tok[row] = 0.f;
             continue;
         }
-        float m = -INFINITY, s = 0.f;
-        for (int64_t i = threadIdx.x; i < V8; i += blockDim.x) {
-            float f[8];
-            unpack8(__ldg(lr + i), f);
-            float lm = f[0] * logit_scale;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { f[j] *= logit_scale; lm = fmaxf(lm, f[j]); }
-            if (lm > m) { s *= __expf(m - lm); m = lm; }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s += __expf(f[j] - m);
+        if (label < 0 || label >= V) {  // torch's cross_entropy asserts on the device for this as well
+            if (threadIdx.x == 0 && crank == 0)
+                printf("[dolomite_b200] cross_entropy: label %lld of row %lld is outside [0, %lld)\n", (long long)label,
+                       (long long)row, (long long)V);
+            __trap();
         }
-        // warp combine
+        uint4 v[NV];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
-            const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
-            const float mn = fmaxf(m, m2);
-            s = (m == -INFINITY ? 0.f : s * __expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
-            m = mn;
+        for (int k = 0; k < NV; ++k) {
+            const int64_t i = v_lo + k * kCeThreads + threadIdx.x;
+            if (i < v_hi) v[k] = lr[i];
         }
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        if (lane == 0) { red_m[wid] = m; red_s[wid] = s; }
-        __syncthreads();
-        if (wid == 0) {
-            float mm = lane < (kCeThreads / 32) ? red_m[lane] : -INFINITY;
-            float sv = lane < (kCeThreads / 32) ? red_s[lane] : 0.f;
+        float m = -INFINITY;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float m2 = __shfl_xor_sync(0xffffffffu, mm, o);
-                const float s2 = __shfl_xor_sync(0xffffffffu, sv, o);
-                const float mn = fmaxf(mm, m2);
-                sv = (mm == -INFINITY ? 0.f : sv * __expf(mm - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
-                mm = mn;
+        for (int k = 0; k < NV; ++k) {
+            if (v_lo + k * kCeThreads + threadIdx.x < v_hi) {
+                float f[8];
+                unpack8(v[k], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m = fmaxf(m, f[j] * logit_scale);
             }
-            if (lane == 0) s_lse = mm + __logf(sv);
         }
-        __syncthreads();
-        const float lse = s_lse;
-        if (threadIdx.x == 0) {
-            const __nv_bfloat16* lrow = reinterpret_cast<const __nv_bfloat16*>(lr);
-            const float xl = __bfloat162float(lrow[label]) * logit_scale;
-            loss_tok[row] = lse - xl;
+        m = ce_block_reduce(m, red, true);
+        if (SPLIT > 1) {
+            if (threadIdx.x < SPLIT) st_cluster_f32(&xch[0][crank], threadIdx.x, m);
+            cluster_sync_all();
+#pragma unroll
+            for (int c = 0; c < SPLIT; ++c) m = fmaxf(m, xch[0][c]);
         }
-        __syncthreads();  // label logit read before the row is overwritten (dlogits may alias logits)
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            if (v_lo + k * kCeThreads + threadIdx.x < v_hi) {
+                float f[8];
+                unpack8(v[k], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += __expf(f[j] * logit_scale - m);
+            }
+        }
+        s = ce_block_reduce(s, red, false);
+        if (SPLIT > 1) {
+            if (threadIdx.x < SPLIT) st_cluster_f32(&xch[1][crank], threadIdx.x, s);
+            cluster_sync_all();
+            s = 0.f;
+#pragma unroll
+            for (int c = 0; c < SPLIT; ++c) s += xch[1][c];
+        }
+        const float lse = m + __logf(s);
         const int64_t lvec = label >> 3;
         const int lsub = int(label & 7);
-        for (int64_t i = threadIdx.x; i < V8; i += blockDim.x) {
-            float f[8];
-            unpack8(__ldg(lr + i), f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __expf(f[j] * logit_scale - lse);
-            if (i == lvec) f[lsub] -= 1.f;
+        for (int k = 0; k < NV; ++k) {
+            const int64_t i = v_lo + k * kCeThreads + threadIdx.x;
+            if (i < v_hi) {
+                float f[8];
+                unpack8(v[k], f);
+                if (i == lvec) loss_tok[row] = lse - f[lsub] * logit_scale;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] *= gs * logit_scale;
-            dr[i] = pack8(f);
+                for (int j = 0; j < 8; ++j) f[j] = __expf(f[j] * logit_scale - lse);
+                if (i == lvec) f[lsub] -= 1.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] *= gs * logit_scale;
+                dr[i] = pack8(f);
+            }
         }
-        __syncthreads();
+        // no third cluster barrier: xch[0] of this row was read before barrier 2 and is rewritten only after it; xch[1] was
+        // read before the next row's barrier 1 and is rewritten only after it
     }
+}
+
+template <int NV, int SPLIT>
+int launch_ce_rows(const void* logits, int64_t ldl, const int64_t* labels, void* dlogits, float* loss_tok,
+                   const float* scratch, int64_t T, int64_t V, int64_t ignore_index, float logit_scale, float grad_scale,
+                   cudaStream_t st) {
+    auto kern = ce_rows_kernel<NV, SPLIT>;
+    int64_t clusters = int64_t(dolo_num_sms()) / SPLIT;  // one 512-thread CTA per SM (the row lives in its registers)
+    if (clusters > T) clusters = T;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(clusters * SPLIT));
+    cfg.blockDim = dim3(kCeThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = SPLIT;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = SPLIT > 1 ? 1 : 0;
+    DOLO_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, static_cast<const uint4*>(logits), ldl / 8, labels,
+                                    static_cast<uint4*>(dlogits), loss_tok, scratch, T, V, ignore_index, logit_scale,
+                                    grad_scale));
+    return DOLO_OK;
 }
 
 __global__ void ce_mean_kernel(const float* __restrict__ loss_tok, int64_t T, const float* __restrict__ scratch,
@@ -1109,26 +1167,55 @@ extern "C" int dolomite_b200_embedding_bwd(const int64_t* ids, const void* dout,
     return DOLO_OK;
 }
 
+extern "C" int dolomite_b200_cross_entropy_count(const int64_t* labels, int64_t T, int64_t ignore_index, float* scratch,
+                                                 void* stream) {
+    ce_count_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(labels, T, ignore_index, scratch);
+    DOLO_LAUNCH_OK("ce_count");
+    return DOLO_OK;
+}
+
+extern "C" int dolomite_b200_cross_entropy_rows(const void* logits, int64_t ldl, const int64_t* labels, void* dlogits,
+                                                float* loss_per_token, const float* scratch, int64_t T, int64_t V,
+                                                int64_t ignore_index, float logit_scale, float grad_scale, void* stream) {
+    DOLO_REQUIRE(V > 0 && V % 8 == 0 && ldl % 8 == 0 && ldl >= V,
+                 "cross_entropy: V=%lld / ld=%lld must be multiples of 8", (long long)V, (long long)ldl);
+    DOLO_REQUIRE(aligned16(logits) && aligned16(dlogits), "cross_entropy: pointers must be 16-byte aligned");
+    if (T == 0) return DOLO_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // vectors per thread with 512 threads and the whole row in ONE CTA; wider rows are split over a 2- or 4-CTA cluster
+    const int64_t V8 = V / 8;
+    const int64_t nv1 = (V8 + kCeThreads - 1) / kCeThreads;
+#define DOLO_CE(NV, SPLIT)                                                                                          \
+    return launch_ce_rows<NV, SPLIT>(logits, ldl, labels, dlogits, loss_per_token, scratch, T, V, ignore_index, \
+                                     logit_scale, grad_scale, st)
+    if (nv1 <= 4) DOLO_CE(4, 1);
+    if (nv1 <= 8) DOLO_CE(8, 1);
+    if (nv1 <= 12) DOLO_CE(12, 1);
+    if (nv1 <= 16) DOLO_CE(16, 1);
+    if (nv1 <= 24) DOLO_CE(12, 2);
+    if (nv1 <= 32) DOLO_CE(16, 2);
+    if (nv1 <= 64) DOLO_CE(16, 4);
+#undef DOLO_CE
+    return dolo_set_error("cross_entropy: vocabulary %lld exceeds the 262144 columns one 4-CTA cluster holds", (long long)V);
+}
+
+extern "C" int dolomite_b200_cross_entropy_mean(const float* loss_per_token, int64_t T, const float* scratch,
+                                                float* loss_mean, void* stream) {
+    ce_mean_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(loss_per_token, T, scratch, loss_mean);
+    DOLO_LAUNCH_OK("ce_mean");
+    return DOLO_OK;
+}
+
 extern "C" int dolomite_b200_cross_entropy_fwd_bwd(const void* logits, int64_t ldl, const int64_t* labels,
                                                    void* dlogits, float* loss_per_token, float* loss_mean,
                                                    float* scratch, int64_t T, int64_t V, int64_t ignore_index,
                                                    float logit_scale, float grad_scale, void* stream) {
-    DOLO_REQUIRE(V > 0 && V % 8 == 0 && ldl % 8 == 0 && ldl >= V,
-                 "cross_entropy: V=%lld / ld=%lld must be multiples of 8", (long long)V, (long long)ldl);
-    DOLO_REQUIRE(aligned16(logits) && aligned16(dlogits), "cross_entropy: pointers must be 16-byte aligned");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    ce_count_kernel<<<1, 1024, 0, st>>>(labels, T, ignore_index, scratch);
-    DOLO_LAUNCH_OK("ce_count");
-    if (T > 0) {
-        const int grid = int(T < int64_t(dolo_num_sms()) * 4 ? T : int64_t(dolo_num_sms()) * 4);
-        ce_fwd_bwd_kernel<<<grid, kCeThreads, 0, st>>>(static_cast<const uint4*>(logits), ldl / 8, labels,
-                                                       static_cast<uint4*>(dlogits), loss_per_token, scratch, T, V,
-                                                       ignore_index, logit_scale, grad_scale);
-        DOLO_LAUNCH_OK("ce_fwd_bwd");
-    }
-    ce_mean_kernel<<<1, 1024, 0, st>>>(loss_per_token, T, scratch, loss_mean);
-    DOLO_LAUNCH_OK("ce_mean");
-    return DOLO_OK;
+    int rc = dolomite_b200_cross_entropy_count(labels, T, ignore_index, scratch, stream);
+    if (rc) return rc;
+    rc = dolomite_b200_cross_entropy_rows(logits, ldl, labels, dlogits, loss_per_token, scratch, T, V, ignore_index,
+                                          logit_scale, grad_scale, stream);
+    if (rc) return rc;
+    return dolomite_b200_cross_entropy_mean(loss_per_token, T, scratch, loss_mean, stream);
 }
 
 extern "C" int dolomite_b200_colsum_accum(const void* x, int64_t ldx, float* out, int64_t T, int64_t N, float scale,

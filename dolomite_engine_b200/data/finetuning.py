@@ -100,17 +100,58 @@ class JSONLinesSFTDataset:
         return self.examples[i]
 
 
-def batches(dataset, micro_batch_size: int, eos_token_id: int, use_padding_free_transformer: bool, rank: int = 0,
-            world_size: int = 1, seed: int = 42, loss_mask: str = "output_only", infinite: bool = True) -> Iterable[dict]:
+class ResumableBatches:
     """shuffled, rank-sharded iterator of collated micro-batches (BlendedDistributedSampler + ResumableDataLoader of the
-    reference reduced to what train_step needs): epoch e uses permutation `randperm(len, seed + e)`, rank r takes every
-    world_size-th example starting at r, incomplete trailing batches are dropped"""
-    epoch = 0
-    while True:
-        order = torch.randperm(len(dataset), generator=torch.Generator().manual_seed(seed + epoch)).tolist()[rank::world_size]
-        for lo in range(0, len(order) - micro_batch_size + 1, micro_batch_size):
-            yield collate([dataset[j] for j in order[lo : lo + micro_batch_size]], eos_token_id,
-                          use_padding_free_transformer, loss_mask)
-        epoch += 1
-        if not infinite:
-            return
+    reference, data/dataloader.py / data/sampler.py, reduced to what train_step needs): epoch e uses permutation
+    `randperm(len, seed + e)` truncated to a multiple of `world_size * micro_batch_size` (every rank yields the SAME number
+    of batches, so rank-sharded evaluation issues the same collectives everywhere), rank r takes every world_size-th example
+    starting at r.  `state_dict()` / `load_state_dict()` carry (epoch, batches consumed in the epoch): a resumed run continues
+    with the batch the interrupted run would have drawn next (finetune.py:150 / :286-305 pass the loader to the checkpoint)."""
+
+    def __init__(self, dataset, micro_batch_size: int, eos_token_id: int, use_padding_free_transformer: bool, rank: int = 0,
+                 world_size: int = 1, seed: int = 42, loss_mask: str = "output_only", infinite: bool = True):
+        self.dataset, self.mbs, self.eos = dataset, micro_batch_size, eos_token_id
+        self.padding_free, self.rank, self.world = use_padding_free_transformer, rank, world_size
+        self.seed, self.loss_mask, self.infinite = seed, loss_mask, infinite
+        self.epoch, self.offset = 0, 0  # offset: micro-batches of this rank already drawn in `epoch`
+        self._order: list[int] | None = None
+
+    def batches_per_epoch(self) -> int:
+        return len(self.dataset) // (self.world * self.mbs)
+
+    def _epoch_order(self) -> list[int]:
+        order = torch.randperm(len(self.dataset), generator=torch.Generator().manual_seed(self.seed + self.epoch)).tolist()
+        usable = self.batches_per_epoch() * self.world * self.mbs
+        return order[:usable][self.rank :: self.world]
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> dict:
+        n = self.batches_per_epoch()
+        if n == 0:
+            raise StopIteration
+        if self.offset >= n:
+            if not self.infinite:
+                raise StopIteration
+            self.epoch, self.offset, self._order = self.epoch + 1, 0, None
+        if self._order is None:
+            self._order = self._epoch_order()
+        lo = self.offset * self.mbs
+        self.offset += 1
+        return collate([self.dataset[j] for j in self._order[lo : lo + self.mbs]], self.eos, self.padding_free, self.loss_mask)
+
+    def state_dict(self) -> dict:
+        return {"epoch": self.epoch, "offset": self.offset, "seed": self.seed, "world_size": self.world,
+                "micro_batch_size": self.mbs}
+
+    def load_state_dict(self, state: dict) -> None:
+        if state.get("world_size", self.world) != self.world or state.get("micro_batch_size", self.mbs) != self.mbs:
+            raise ValueError("the finetuning feed can only be resumed with the world size / micro batch size it was saved with")
+        self.epoch, self.offset, self._order = int(state["epoch"]), int(state["offset"]), None
+
+
+def batches(dataset, micro_batch_size: int, eos_token_id: int, use_padding_free_transformer: bool, rank: int = 0,
+            world_size: int = 1, seed: int = 42, loss_mask: str = "output_only", infinite: bool = True) -> ResumableBatches:
+    return ResumableBatches(dataset, micro_batch_size, eos_token_id, use_padding_free_transformer, rank, world_size, seed,
+                            loss_mask, infinite)

@@ -82,8 +82,46 @@ def build_data_parallel_groups(sharding_world_size: int | None = None, replicati
     return mine_s[0], mine_r, len(mine_s[1]), mine_s[1].index(rank)
 
 
+class _SlotTable:
+    """Who owns which shared parameter buffer (stage-3 / pooled mode).  Unit 0 (root) and every unit of the resident mode
+    own a private buffer (slot -1); block unit i >= 1 of the pooled mode uses slot (i - 1) mod n_slots.  Pure bookkeeping,
+    no device work: `claim(i)` is called when unit i's all-gather is issued and returns the unit that loses the slot."""
+
+    def __init__(self, pooled: list[bool], n_slots: int):
+        self.pooled = list(pooled)
+        self.n_slots = n_slots
+        self.slot_of = [((i - 1) % n_slots if p else -1) for i, p in enumerate(pooled)]
+        self.owner = [-1] * n_slots
+        self.fresh = [False] * len(pooled)  # the unit's buffer holds its current parameters (once its gather is waited)
+
+    def invalidate(self) -> None:
+        self.fresh = [False] * len(self.fresh)
+
+    def is_fresh(self, i: int) -> bool:
+        return self.fresh[i] and (not self.pooled[i] or self.owner[self.slot_of[i]] == i)
+
+    def claim(self, i: int) -> int:
+        if not self.pooled[i]:
+            return -1
+        s = self.slot_of[i]
+        prev = self.owner[s]
+        self.owner[s] = i
+        if prev >= 0 and prev != i:
+            self.fresh[prev] = False
+            return prev
+        return -1
+
+
 class _Comm:
-    """engine hooks: all-gather prefetch in forward, reduce-scatter (+ replica all-reduce) in backward"""
+    """engine hooks: all-gather prefetch in forward, reduce-scatter (+ replica all-reduce) in backward.
+
+    Two memory modes.  resident (`reshard_after_forward=False`, FSDP SHARD_GRAD_OP-like and kept until the optimizer step):
+    every unit owns its gathered bf16 parameters and its full fp32 gradient buffer; one all-gather per unit per optimizer
+    step.  reshard (`reshard_after_forward=True`, what `stage: 3` means in the reference, distributed/__init__.py:205-213):
+    the block units share `engine.pool_slots` parameter buffers and as many gradient buffers (engine.convert_to_pooled);
+    a block's parameters are re-gathered for its backward and its gradients are reduce-scattered as soon as its backward
+    ends, on EVERY micro-step (FULL_SHARD never holds unsharded gradients; under `no_sync()` the reduced shards accumulate,
+    which is the same sum)."""
 
     def __init__(self, engine: DolomiteEngine, group, communication_dtype: torch.dtype, reshard_after_forward: bool,
                  replicate_group=None):
@@ -94,30 +132,47 @@ class _Comm:
         self.rank = dist.get_rank(group)
         self.comm_dtype = communication_dtype
         self.reshard = reshard_after_forward
+        if self.reshard:
+            engine.convert_to_pooled(int(os.environ.get("DOLO_POOL_SLOTS", "2")))
         self.stream = torch.cuda.Stream(device=engine.device, priority=-1)
         n = len(engine.units)
         self.ag_work: list = [None] * n
         self.rs_work: list = [None] * n
-        self.fresh = [False] * n  # gather buffer holds the current parameters
         self.sync_grads = True
+        self.pooled = [u.pooled for u in engine.units]
+        n_slots = getattr(engine, "pool_slots", 0) if any(self.pooled) else 0
+        self.slots = _SlotTable(self.pooled, max(n_slots, 1))
+        self.slot_of = self.slots.slot_of
+        self.grad_slot_free = [None] * max(n_slots, 1)  # event: the slot's gradients have left for the wire
+        self.first_rs = [True] * n                 # first reduce-scatter of the accumulation window overwrites the shard grad
+        biggest = max(u.padded for u in engine.units)
         if communication_dtype == torch.bfloat16:
-            biggest = max(u.padded for u in engine.units)
             self.rs_stage = [torch.empty(biggest, dtype=torch.bfloat16, device=engine.device) for _ in range(2)]
             self.rs_out = [torch.empty(biggest // self.ws, dtype=torch.bfloat16, device=engine.device) for _ in range(2)]
             self.rs_stage_evt = [None, None]
+        elif self.reshard:
+            self.rs_out32 = [torch.empty(biggest // self.ws, dtype=torch.float32, device=engine.device) for _ in range(2)]
+            self.rs_stage_evt = [None, None]
         self._rs_count = 0
-        self._pending_bf16 = []
 
     # ---- all-gather ----
     def invalidate(self) -> None:
-        self.fresh = [False] * len(self.fresh)
+        self.slots.invalidate()
+
+    def window_reset(self) -> None:
+        """zero_grad(): the next reduce-scatter of every unit starts a new accumulation window"""
+        self.first_rs = [True] * len(self.first_rs)
 
     def _issue_gather(self, i: int) -> None:
-        if self.fresh[i] or self.ag_work[i] is not None:
+        if self.slots.is_fresh(i) or self.ag_work[i] is not None:
             return
         u = self.engine.units[i]
         cur = torch.cuda.current_stream()
-        self.stream.wait_stream(cur)  # previous readers of the buffer (last backward) are ordered before the overwrite
+        # previous readers of the buffer (last backward; in pooled mode the block that used the slot before) are ordered
+        # before the overwrite: everything enqueued on the compute stream so far
+        self.stream.wait_stream(cur)
+        prev = self.slots.claim(i)
+        assert prev < 0 or self.ag_work[prev] is None, "parameter slot reassigned while its gather is still pending"
         with torch.cuda.stream(self.stream):
             own = u.compute[self.rank * u.shard_numel : (self.rank + 1) * u.shard_numel]
             K.cast_f32_to_bf16(u.master.data, own)
@@ -127,47 +182,81 @@ class _Comm:
         if self.ag_work[i] is not None:
             self.ag_work[i].wait()  # compute stream waits (device side) for the collective
             self.ag_work[i] = None
-            self.fresh[i] = True
+            self.slots.fresh[i] = True
 
     def pre_forward_unit(self, i: int) -> None:
         self._issue_gather(i)
-        if i + 1 < len(self.fresh):
+        if i + 1 < len(self.pooled):
             self._issue_gather(i + 1)  # prefetch depth 1
         self._wait_gather(i)
 
     def post_forward_unit(self, i: int) -> None:
-        if self.reshard and i > 0:
-            self.fresh[i] = False  # stage-3 semantics: parameters are re-gathered for backward
+        pass  # pooled mode: a block's parameters disappear when its slot is handed to the next block
 
     def pre_backward_unit(self, i: int) -> None:
-        if self.reshard:
+        if self.pooled[i]:
             self._issue_gather(i)
             if i - 1 >= 1:
                 self._issue_gather(i - 1)
             self._wait_gather(i)
+            evt = self.grad_slot_free[self.slot_of[i]]
+            if evt is not None:  # the block that used this gradient slot before has handed its gradients to the wire
+                torch.cuda.current_stream().wait_event(evt)
+                self.grad_slot_free[self.slot_of[i]] = None
+            self.engine.prepare_unit_grads(i)
 
     # ---- reduce-scatter ----
     def post_backward_unit(self, i: int) -> None:
-        if not self.sync_grads:
+        if not self.sync_grads and not self.pooled[i]:
             return
+        if not self.sync_grads and i == 0:
+            return  # the root keeps its own gradient buffer: accumulate under no_sync like the resident mode
         u = self.engine.units[i]
+        if self.pooled[i]:
+            self.engine.finish_unit_grads(i)
         cur = torch.cuda.current_stream()
         self.stream.wait_stream(cur)
+        first = self.first_rs[i]
+        self.first_rs[i] = False
         with torch.cuda.stream(self.stream):
+            slot = self._rs_count % 2
+            self._rs_count += 1
             if self.comm_dtype == torch.bfloat16:
-                slot = self._rs_count % 2
-                self._rs_count += 1
                 if self.rs_stage_evt[slot] is not None:
                     self.rs_stage_evt[slot].wait()
                 stage = self.rs_stage[slot][: u.padded]
                 out = self.rs_out[slot][: u.shard_numel]
                 K.cast_f32_to_bf16(u.grad_full, stage)
+                if self.pooled[i]:  # the fp32 gradient slot is free as soon as the bf16 wire copy exists
+                    free = torch.cuda.Event()
+                    free.record(self.stream)
+                    self.grad_slot_free[self.slot_of[i]] = free
                 work = dist.reduce_scatter_tensor(out, stage, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
                 work.wait()  # orders the comm stream after the collective
                 if self.replicate_group is not None:  # HSDP: mean over the replicas of this slice, still in bf16
                     dist.all_reduce(out, op=dist.ReduceOp.AVG, group=self.replicate_group)
-                u.master.grad.zero_()
+                if first or not self.pooled[i]:
+                    u.master.grad.zero_()
                 K.accum_bf16_into_f32(out, u.master.grad, 1.0)
+                evt = torch.cuda.Event()
+                evt.record(self.stream)
+                self.rs_stage_evt[slot] = evt
+                self.rs_work[i] = evt
+            elif self.pooled[i]:
+                if self.rs_stage_evt[slot] is not None:
+                    self.rs_stage_evt[slot].wait()
+                out = self.rs_out32[slot][: u.shard_numel]
+                work = dist.reduce_scatter_tensor(out, u.grad_full, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+                work.wait()
+                free = torch.cuda.Event()
+                free.record(self.stream)
+                self.grad_slot_free[self.slot_of[i]] = free
+                if self.replicate_group is not None:
+                    dist.all_reduce(out, op=dist.ReduceOp.AVG, group=self.replicate_group)
+                if first:
+                    u.master.grad.copy_(out)
+                else:
+                    u.master.grad.add_(out)
                 evt = torch.cuda.Event()
                 evt.record(self.stream)
                 self.rs_stage_evt[slot] = evt
@@ -206,7 +295,7 @@ class ShardedDataParallel(nn.Module):
     `.grad`), `.train()/.eval()`, `.config`, `.tokenizer` and `forward(batch) -> loss`."""
 
     def __init__(self, model_wrapper: nn.Module, process_group=None, communication_dtype: torch.dtype | None = None,
-                 reshard_after_forward: bool = False, replicate_group=None):
+                 reshard_after_forward: bool = True, replicate_group=None):
         super().__init__()
         self.module = model_wrapper
         self.engine: DolomiteEngine = model_wrapper.model.engine
@@ -327,8 +416,12 @@ class ShardedDataParallel(nn.Module):
 
 def wrap_model_for_distributed_training(args, model: nn.Module) -> nn.Module:
     """Reference signature (distributed/__init__.py:47).  Reads the same knobs from `args.distributed_args`:
-    `stage` (3 -> reshard parameters after forward, 0/2 -> keep them gathered), `communication_dtype`,
-    `fsdp_algorithm` (both map to the same flat-bucket runtime), and rejects what is out of scope."""
+    `stage` -- 3 reshards the parameters after forward and shares the gather / gradient buffers between blocks, exactly
+    what `reshard_after_forward = stage == 3` / FULL_SHARD does in the reference (distributed/__init__.py:161-176,
+    :205-213); 0 / 2 keep every unit's gathered parameters and full gradients resident (SHARD_GRAD_OP-like) --,
+    `communication_dtype`, `fsdp_algorithm` (both map to the same flat-bucket runtime), and rejects what is out of scope.
+    The one B200-specific key is `reshard_after_forward` (default None = follow `stage`): `false` together with
+    `stage: 3` opts into the resident mode, which trades ~6 B / parameter of HBM for one all-gather per unit and step."""
     dargs = getattr(args, "distributed_args", None)
     stage = getattr(dargs, "stage", 3) if dargs is not None else 3
     comm_dtype = None
@@ -341,7 +434,8 @@ def wrap_model_for_distributed_training(args, model: nn.Module) -> nn.Module:
             raise NotImplementedError("tensor parallelism is out of scope of the data-parallel B200 path")
         if getattr(dargs, "torch_compile", False):
             raise NotImplementedError("torch.compile is not used on the B200 path (hand-written kernels + CUDA streams)")
-    reshard = bool(getattr(dargs, "reshard_after_forward", False)) if dargs is not None else False
+    explicit = getattr(dargs, "reshard_after_forward", None) if dargs is not None else None
+    reshard = (stage == 3) if explicit is None else bool(explicit)
     if dargs is not None and getattr(dargs, "gradient_checkpointing_method", None) is not None:
         # block_checkpointing(model, block_name, checkpoint_every=1) (distributed/__init__.py:113-121,
         # gradient_checkpointing/block.py:13-37): blocks 0, k, 2k, ... keep only their input and are re-run in backward
@@ -353,7 +447,7 @@ def wrap_model_for_distributed_training(args, model: nn.Module) -> nn.Module:
         # HSDP: the engine must have been built with the SHARD group's size / rank (pretrain.build does)
         group, replicate_group, _, _ = data_parallel_groups(topo.data_parallel_sharding_world_size,
                                                             topo.data_parallel_replication_world_size)
-    return ShardedDataParallel(model, group, communication_dtype=comm_dtype, reshard_after_forward=reshard and stage == 3,
+    return ShardedDataParallel(model, group, communication_dtype=comm_dtype, reshard_after_forward=reshard,
                                replicate_group=replicate_group)
 
 

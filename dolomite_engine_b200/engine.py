@@ -65,6 +65,7 @@ class FlatUnit:
         self.views: dict[str, torch.Tensor] = {}
         self.gviews: dict[str, torch.Tensor] = {}
         self.gathered = False  # compute buffer holds current parameters
+        self.pooled = False  # compute / grad_full are shared with other units (stage-3 resharding)
         self.exp_avg = None
         self.exp_avg_sq = None
 
@@ -81,13 +82,25 @@ class FlatUnit:
             self.views[s.name] = self.compute[s.offset : s.offset + s.numel].view(s.shape)
             self.gviews[s.name] = self.grad_full[s.offset : s.offset + s.numel].view(s.shape)
 
+    def bind_pooled(self, compute: torch.Tensor, grad_full: torch.Tensor) -> None:
+        """stage-3 resharding: the gathered bf16 parameters and the full fp32 gradients of this unit live in a buffer that
+        several units take turns using (distributed._Comm decides who owns it when); only the shards stay per unit"""
+        assert compute.numel() == self.padded and grad_full.numel() == self.padded
+        self.compute, self.grad_full = compute, grad_full
+        self.pooled = True
+        self.gathered = False
+        for s in self.specs:
+            self.views[s.name] = compute[s.offset : s.offset + s.numel].view(s.shape)
+            self.gviews[s.name] = grad_full[s.offset : s.offset + s.numel].view(s.shape)
+
     def full_master_from(self, full_fp32: torch.Tensor) -> None:
         """install parameters from a full flat fp32 tensor (host or device)"""
         lo = self.rank * self.shard_numel
         with torch.no_grad():
             self.master.copy_(full_fp32[lo : lo + self.shard_numel])
-            self.compute.copy_(full_fp32.to(self.compute.device))
-        self.gathered = True
+            if not self.pooled:
+                self.compute.copy_(full_fp32.to(self.compute.device))
+        self.gathered = not self.pooled
 
     def init_full(self, generator: torch.Generator) -> torch.Tensor:
         """reference init rules in fp32; every rank draws the same values (same seed, same
@@ -236,6 +249,7 @@ class DolomiteEngine:
         self._saved = None
         self.requires_gradient_sync = True
         self.checkpoint_every: int | None = None  # block activation checkpointing: re-run blocks 0, k, 2k, ... in backward
+        self.head_chunk_bytes = 1 << 30  # bf16 logits of one LM-head chunk (forward(fuse_head_loss=True))
         self._fresh_grads: set[str] = set()  # weights whose gradient buffer will be overwritten by the next wgrad GEMM
         if cfg.attention_multiplier is not None:
             self.softmax_scale = float(cfg.attention_multiplier)
@@ -245,7 +259,14 @@ class DolomiteEngine:
             self.softmax_scale = 1.0
 
     # ------------------------------------------------------------------------------------------
-    def _setup_rope(self) -> None:
+    def _ensure_rope(self, max_seqlen: int) -> None:
+        """RoPE.forward regrows its cache when seq_len > max_seq_len_cached (position_embedding/rope.py:26-27, called with
+        key_length = max_seqlen, gpt_dolomite/base.py:536-557); the kernel indexes the tables by position id, so they must
+        cover the longest document of the batch (host-side check on a python int: no device sync)."""
+        if self.rope_cos is not None and max_seqlen > self.rope_cos.shape[0]:
+            self._setup_rope(n_positions=int(max_seqlen))
+
+    def _setup_rope(self, n_positions: int | None = None) -> None:
         """cos/sin cache exactly as RoPE._set_cos_sin_cache (position_embedding/rope.py:36-55) then .to(bf16) (:29-30)"""
         self.rope_cos = self.rope_sin = None
         if self.cfg.position_embedding_type != "rope":
@@ -272,7 +293,7 @@ class DolomiteEngine:
             mask = 1 - ramp
             inv_freq = (1.0 / (scale * pos_freqs)) * (1 - mask) + (1.0 / pos_freqs) * mask
             mscale = 1.0 if scale <= 1 else 0.1 * math.log(scale) + 1.0
-        t = torch.arange(self.cfg.n_positions, dtype=torch.float32)
+        t = torch.arange(self.cfg.n_positions if n_positions is None else n_positions, dtype=torch.float32)
         freqs = torch.outer(t, inv_freq)
         emb = torch.cat((freqs, freqs), dim=-1)
         self.rope_cos = (emb.cos() * mscale).to(torch.bfloat16).to(self.device)
@@ -286,6 +307,50 @@ class DolomiteEngine:
     def num_parameters(self) -> int:
         return sum(s.numel for u in self.units for s in u.specs)
 
+    def convert_to_pooled(self, n_slots: int = 2) -> None:
+        """Stage-3 memory layout (reference: FSDP FULL_SHARD, distributed/__init__.py:161-176 and :205-213): the block units
+        stop owning a full bf16 parameter buffer and a full fp32 gradient buffer each; `n_slots` buffers of each kind are
+        shared round-robin (block i uses slot i mod n_slots), so gathered parameters / unreduced gradients of at most
+        `n_slots` blocks exist at any time.  The root unit (embeddings, final norm, head) keeps its own buffers, like the
+        FSDP root.  All blocks have the same flat layout, which is what makes the slots interchangeable."""
+        blocks = self.units[1:]
+        if self.world_size == 1 or not blocks or blocks[0].pooled:
+            return
+        padded = blocks[0].padded
+        assert all(u.padded == padded for u in blocks), "block units must share one flat layout"
+        self.pool_slots = n_slots
+        self.pool_compute = [torch.zeros(padded, dtype=torch.bfloat16, device=self.device) for _ in range(n_slots)]
+        self.pool_grad = [torch.zeros(padded, dtype=torch.float32, device=self.device) for _ in range(n_slots)]
+        for i, u in enumerate(blocks):
+            u.bind_pooled(self.pool_compute[i % n_slots], self.pool_grad[i % n_slots])
+        torch.cuda.empty_cache() if self.device.type == "cuda" else None
+
+    def prepare_unit_grads(self, i: int) -> None:
+        """pooled gradients: unit i's backward starts on a buffer that held another block's gradients.  Large GEMM weights
+        are overwritten by their first weight-gradient GEMM (beta = 0); the small tensors accumulated by reduction kernels
+        (norm weights, biases) are cleared here; MoE units are cleared whole (an expert may receive no token)."""
+        u = self.units[i]
+        if not u.pooled:
+            return
+        if self.is_moe:
+            u.grad_full.zero_()
+            return
+        for s in u.specs:
+            if s.numel >= self._LAZY_ZERO_MIN_NUMEL and s.name.endswith(".weight"):
+                self._fresh_grads.add(s.name)
+            else:
+                u.gviews[s.name].zero_()
+
+    def finish_unit_grads(self, i: int) -> None:
+        """pooled gradients: a large weight that received no gradient must read as zero before the reduce-scatter"""
+        u = self.units[i]
+        if not u.pooled or not self._fresh_grads:
+            return
+        for s in u.specs:
+            if s.name in self._fresh_grads:
+                u.gviews[s.name].zero_()
+                self._fresh_grads.discard(s.name)
+
     # parameters at least this large only ever receive their gradient from a weight-gradient GEMM first
     _LAZY_ZERO_MIN_NUMEL = 1 << 16
 
@@ -296,7 +361,11 @@ class DolomiteEngine:
         accumulated by reduction kernels (norm weights, biases) are cleared here."""
         lazy = not self.is_moe
         self._fresh_grads = set()
+        if self.comm is not None:
+            self.comm.window_reset()
         for u in self.units:
+            if u.pooled:  # cleared per unit at the start of its backward (prepare_unit_grads)
+                continue
             if lazy:
                 for s in u.specs:
                     # embedding tables that only ever receive scattered atomics must start from zero
@@ -363,8 +432,10 @@ class DolomiteEngine:
         return h, (x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, fc, act)
 
     def forward(self, input_ids, position_ids, cu_seqlens, max_seqlen: int, labels=None, ignore_index: int = -100,
-                save_for_backward: bool = True):
-        """Returns (logits_or_None, loss_or_None).  input_ids int64 [T]; cu_seqlens int32 [B+1]."""
+                save_for_backward: bool = True, fuse_head_loss: bool = False):
+        """Returns (logits_or_None, loss_or_None).  input_ids int64 [T]; cu_seqlens int32 [B+1].
+        `fuse_head_loss`: the caller will backpropagate d(loss) = 1 (what train_step does), so the LM head's backward can run
+        chunk-wise inside the loss computation and the [T, V] logits are never materialised."""
         cfg = self.cfg
         if self.has_dropout and self.training:
             raise NotImplementedError("dropout > 0 in training mode is not implemented on the B200 path (the target configs "
@@ -372,6 +443,7 @@ class DolomiteEngine:
         T = input_ids.numel()
         root = self.units[0]
         comm = self.comm
+        self._ensure_rope(int(max_seqlen))
         if comm is not None:
             comm.pre_forward_unit(0)
         h = K.embedding_fwd(input_ids, root.views["transformer.wte.weight"], 1.0 if cfg.m_emb is None else float(cfg.m_emb))
@@ -393,30 +465,58 @@ class DolomiteEngine:
             if comm is not None:
                 comm.post_forward_unit(i + 1)
         hf, rstd_f = self._norm_fwd(h, root, "transformer.ln_f.")
-        head = root.views["transformer.wte.weight"] if cfg.tie_word_embeddings else root.views["lm_head.weight"]
+        head_name = "transformer.wte.weight" if cfg.tie_word_embeddings else "lm_head.weight"
+        head = root.views[head_name]
         inv_width = 1.0 if cfg.m_width is None else 1.0 / float(cfg.m_width)
-        logits = K.gemm(hf, head, alpha=inv_width)
         loss = None
-        if labels is not None:
-            # fused CE fwd+bwd: dlogits overwrites a copy only when the caller also wants the logits back
-            loss, _, dlogits = K.cross_entropy_fwd_bwd(logits, labels, ignore_index=ignore_index, dlogits=None)
-            logits_out = None
+        d_hf = dlogits = logits_out = None
+        if labels is not None and save_for_backward and fuse_head_loss:
+            # LM head + cross entropy + the head's own backward, chunk by chunk over the token rows
+            # (gpt_dolomite/main.py:172-177, model_wrapper/pretraining.py:107-127): [T, V] logits never exist -- a chunk of
+            # rows is projected, turned into its gradient in place by the row-resident CE kernel and consumed at once by
+            # the head's dgrad / wgrad GEMMs.  Valid because the caller backpropagates d(loss) = 1 (train_step).
+            scratch = K.cross_entropy_count(labels, ignore_index)
+            loss_tok = torch.empty(T, dtype=torch.float32, device=hf.device)
+            d_hf = torch.empty_like(hf)
+            rows = self._head_chunk_rows(T, head.shape[0], self.head_chunk_bytes)
+            buf = torch.empty(min(rows, T), head.shape[0], dtype=torch.bfloat16, device=hf.device)
+            for r0 in range(0, T, rows):
+                r1 = min(T, r0 + rows)
+                lg = K.gemm(hf[r0:r1], head, alpha=inv_width, out=buf[: r1 - r0])
+                K.cross_entropy_rows(lg, labels[r0:r1], loss_tok[r0:r1], scratch, ignore_index=ignore_index)
+                self._linear_bwd(root, head_name, None, hf[r0:r1], lg, alpha=inv_width, dx_out=d_hf[r0:r1])
+            loss = K.cross_entropy_mean(loss_tok, scratch)
+            del buf
         else:
-            dlogits = None
-            logits_out = logits
+            logits = K.gemm(hf, head, alpha=inv_width)
+            if labels is not None:
+                # fused CE fwd+bwd: dlogits overwrites the logits
+                loss, _, dlogits = K.cross_entropy_fwd_bwd(logits, labels, ignore_index=ignore_index, dlogits=None)
+            else:
+                logits_out = logits
         if save_for_backward:
             self._saved = dict(input_ids=input_ids, position_ids=position_ids, cu_seqlens=cu_seqlens, max_seqlen=max_seqlen,
-                               layers=saved_layers, h_last=h, rstd_f=rstd_f, hf=hf, dlogits=dlogits, T=T)
+                               layers=saved_layers, h_last=h, rstd_f=rstd_f, hf=hf, dlogits=dlogits, d_hf=d_hf, T=T)
         return logits_out, loss
+
+    @staticmethod
+    def _head_chunk_rows(T: int, V: int, budget_bytes: int = 1 << 30) -> int:
+        """token rows per LM-head chunk: equal chunks of at most `budget_bytes` of bf16 logits, multiples of 8 rows (the
+        rows of a chunk are the contraction length of its weight-gradient GEMM)"""
+        max_rows = max(8, budget_bytes // (2 * V) // 8 * 8)
+        n_chunks = -(-T // max_rows)
+        per = -(-T // n_chunks)
+        return min(T, -(-per // 8) * 8)
 
     # ------------------------------------------------------------------------------------------
     # backward
     # ------------------------------------------------------------------------------------------
-    def _linear_bwd(self, unit: FlatUnit, wname: str, bname: str | None, x, dy, alpha: float = 1.0, need_dx: bool = True):
+    def _linear_bwd(self, unit: FlatUnit, wname: str, bname: str | None, x, dy, alpha: float = 1.0, need_dx: bool = True,
+                    dx_out=None):
         """autograd of y = alpha * (x W^T + b):  dx = alpha * dy W ; dW += alpha * dy^T x ; db += alpha * colsum(dy)"""
         w = unit.views[wname]
         gw = unit.gviews[wname]
-        dx = K.gemm(dy, w, b_mn=True, alpha=alpha) if need_dx else None
+        dx = K.gemm(dy, w, b_mn=True, alpha=alpha, out=dx_out) if need_dx else None
         if wname in self._fresh_grads:  # first gradient since zero_grad(): overwrite, the buffer was not cleared
             self._fresh_grads.discard(wname)
             K.gemm(dy, x, a_mn=True, b_mn=True, out=gw, alpha=alpha)
@@ -434,17 +534,23 @@ class DolomiteEngine:
         cfg = self.cfg
         root = self.units[0]
         comm = self.comm
-        dl = dlogits if dlogits is not None else s["dlogits"]
-        if dl is None:
-            raise RuntimeError("no loss gradient available: forward was run without labels and no dlogits was given")
-        if grad_scale_dev is not None:
-            K.scale_by_device_scalar(dl, grad_scale_dev)
         inv_width = 1.0 if cfg.m_width is None else 1.0 / float(cfg.m_width)
         m_res = 1.0 if cfg.m_residual is None else float(cfg.m_residual)
         head_name = "transformer.wte.weight" if cfg.tie_word_embeddings else "lm_head.weight"
         if comm is not None:
             comm.pre_backward_unit(0)
-        d_hf = self._linear_bwd(root, head_name, None, s["hf"], dl, alpha=inv_width)
+        if dlogits is None and s.get("d_hf") is not None:
+            # the head's backward already ran chunk-wise inside the loss computation (forward(fuse_head_loss=True))
+            if grad_scale_dev is not None:
+                raise RuntimeError("forward(fuse_head_loss=True) assumed d(loss) = 1; an upstream gradient cannot be applied")
+            d_hf = s["d_hf"]
+        else:
+            dl = dlogits if dlogits is not None else s["dlogits"]
+            if dl is None:
+                raise RuntimeError("no loss gradient available: forward was run without labels and no dlogits was given")
+            if grad_scale_dev is not None:
+                K.scale_by_device_scalar(dl, grad_scale_dev)
+            d_hf = self._linear_bwd(root, head_name, None, s["hf"], dl, alpha=inv_width)
         dh = self._norm_bwd(d_hf, s["h_last"], root, "transformer.ln_f.", s["rstd_f"])
         del d_hf
         for i in reversed(range(cfg.n_layer)):

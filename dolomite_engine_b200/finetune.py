@@ -103,7 +103,7 @@ def train(args: TrainingArgs, model, optimizer, scheduler, dataloader, rank: int
         if val_batches is not None and tp.eval_interval and step % tp.eval_interval == 0:
             run_eval(step)
         if args.save_args is not None and (step % args.save_args.save_interval == 0 or step == tp.num_training_steps):
-            save_checkpoint(args, model, optimizer, scheduler, None, None, step, metadata={"iteration": step})
+            save_checkpoint(args, model, optimizer, scheduler, dataloader, None, step, metadata={"iteration": step})
     return losses
 
 
@@ -126,12 +126,12 @@ def main() -> None:
     scheduler = get_scheduler(optimizer, ls.num_warmup_steps, ls.num_constant_steps, ls.num_decay_steps,
                               args.training_parameters.num_training_steps, ls.lr_decay_style, ls.lr_decay_factor,
                               ls.extra_lr_scheduler_args)
-    start = 0
-    loaded = load_checkpoint_for_training(args, model, optimizer, scheduler, None)
-    if loaded is not None:
-        start = loaded[0]
     tokenize = lambda text: wrapper.tokenizer(text, add_special_tokens=False)["input_ids"]  # noqa: E731
     dl = make_sft_dataloader(args, tokenize, wrapper.eos_token_id, rank, world)
+    start = 0
+    loaded = load_checkpoint_for_training(args, model, optimizer, scheduler, dl)  # restores the feed position as well
+    if loaded is not None:
+        start = loaded[0]
     val = make_sft_val_batches(args, tokenize, wrapper.eos_token_id, rank, world)
     train(args, model, optimizer, scheduler, dl, rank, start, val_batches=val)
     if dist.is_initialized():

@@ -41,8 +41,11 @@ class _EngineFunction(torch.autograd.Function):
     def forward(ctx, anchor, model, input_ids, position_ids, cu_seqlens, max_seqlen, labels, ignore_index, save=True):
         # `save`: the caller's torch.is_grad_enabled() (always False in here); under no_grad (evaluation) no activation is kept
         engine = model.engine
+        # `assume_unit_loss_grad` (set by the training wrappers: train_step calls loss.backward() on the raw loss) lets the
+        # engine run the LM head's backward chunk-wise inside the loss computation without ever materialising [T, V]
         logits, loss = engine.forward(input_ids, position_ids, cu_seqlens, max_seqlen, labels=labels,
-                                      ignore_index=ignore_index, save_for_backward=bool(save))
+                                      ignore_index=ignore_index, save_for_backward=bool(save),
+                                      fuse_head_loss=bool(save) and labels is not None and model.assume_unit_loss_grad)
         ctx.model = model
         ctx.loss_mode = labels is not None
         return loss.reshape(()) if ctx.loss_mode else logits

@@ -188,6 +188,30 @@ def cross_entropy_fwd_bwd(logits, labels, ignore_index=-100, logit_scale=1.0, gr
     return loss, loss_tok, dl
 
 
+def cross_entropy_count(labels, ignore_index=-100):
+    """-> scratch (fp32 [2]); scratch[0] = number of labels != ignore_index (the divisor of the mean loss and its gradient)"""
+    _req(labels, torch.int64, "labels")
+    scratch = torch.empty(2, dtype=torch.float32, device=labels.device)
+    _lib.call("dolomite_b200_cross_entropy_count", labels.data_ptr(), labels.numel(), ignore_index, scratch.data_ptr(), _stream())
+    return scratch
+
+
+def cross_entropy_rows(logits, labels, loss_tok, scratch, ignore_index=-100, logit_scale=1.0, grad_scale=1.0):
+    """one chunk of rows: logits [t, V] are overwritten by their gradient, loss_tok [t] receives the per-token losses"""
+    _req(logits, _BF16, "logits"), _req(labels, torch.int64, "labels"), _req(loss_tok, torch.float32, "loss_tok")
+    t, V = logits.shape
+    assert logits.stride(1) == 1 and labels.numel() == t and loss_tok.numel() == t
+    _lib.call("dolomite_b200_cross_entropy_rows", logits.data_ptr(), logits.stride(0), labels.data_ptr(), logits.data_ptr(),
+              loss_tok.data_ptr(), scratch.data_ptr(), t, V, ignore_index, logit_scale, grad_scale, _stream())
+    return logits
+
+
+def cross_entropy_mean(loss_tok, scratch):
+    loss = torch.empty(1, dtype=torch.float32, device=loss_tok.device)
+    _lib.call("dolomite_b200_cross_entropy_mean", loss_tok.data_ptr(), loss_tok.numel(), scratch.data_ptr(), loss.data_ptr(), _stream())
+    return loss
+
+
 def colsum_accum(x, out, scale: float = 1.0):
     _req(x, _BF16, "x"), _req(out, torch.float32, "out")
     T, N = x.shape

@@ -195,6 +195,10 @@ class ModelWrapperForFinetuning(ModelWrapper):
     list[list[int]], "labels": list[list[int]]}; padded collate: [B, S] tensors + "attention_mask".  The loss is computed
     inside the model (gpt_dolomite/main.py:179-202)."""
 
+    def __init__(self, *args, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        self.model.assume_unit_loss_grad = True  # train_step calls loss.backward() on the raw loss (train_utils.py:61-90)
+
     def forward(self, batch: dict) -> torch.Tensor:
         if "attention_mask" in batch and batch["attention_mask"] is not None:
             # padded collate (use_padding_free_transformer: false, data/utils.py:8-92): [B, S] tensors + attention_mask

@@ -23,6 +23,12 @@ class DolomiteFusedAdamW(Optimizer):
         self.model = model  # ShardedDataParallel: provides the clip coefficient and the bf16 targets
         self._step = 0
 
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        """The reference's train_step calls `optimizer.zero_grad()` (train_utils.py:40).  The gradients this optimizer
+        consumes live in the engine's flat buffers (full fp32 accumulation buffers + shard gradients aliased by
+        `master.grad`), so clearing is the model's job; `set_to_none` would break the aliasing and is ignored."""
+        self.model.zero_grad()
+
     @torch.no_grad()
     def step(self, closure=None):
         assert closure is None

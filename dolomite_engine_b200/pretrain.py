@@ -23,13 +23,15 @@ from .train_utils import billion_tokens_per_day, get_model_tflops, get_torch_pro
 
 
 class SyntheticPackedDataset:
-    """tokens = randint(0, V, (mbs, S+1), manual_seed(1234 + rank)), optionally with EOS injected at seeded
-    log-uniform positions (ragged packing)."""
+    """batch b = randint(0, V, (mbs, S+1), manual_seed(1234 + rank + 1000003 * b)), optionally with EOS injected at seeded
+    log-uniform positions (ragged packing).  One generator per batch index makes the feed resumable
+    in O(1): `state_dict()` / `load_state_dict()` carry the number of batches drawn (`consumed_samples` / micro batch)."""
 
     def __init__(self, vocab_size: int, micro_batch_size: int, sequence_length: int, rank: int = 0, eos_token_id: int | None = None,
                  ragged: bool = False, pin: bool = True):
         self.V, self.mbs, self.S = vocab_size, micro_batch_size, sequence_length
-        self.gen = torch.Generator().manual_seed(1234 + rank)
+        self.rank = rank
+        self.index = 0  # batches drawn so far
         self.eos = eos_token_id
         self.ragged = ragged
         self.pin = pin and torch.cuda.is_available()
@@ -37,7 +39,15 @@ class SyntheticPackedDataset:
     def __iter__(self):
         return self
 
+    def state_dict(self) -> dict:
+        return {"consumed_samples": self.index * self.mbs, "batches": self.index}
+
+    def load_state_dict(self, state: dict) -> None:
+        self.index = int(state["batches"]) if "batches" in state else int(state.get("consumed_samples", 0)) // self.mbs
+
     def __next__(self) -> dict:
+        self.gen = torch.Generator().manual_seed(1234 + self.rank + 1000003 * self.index)
+        self.index += 1
         t = torch.randint(0, self.V, (self.mbs, self.S + 1), generator=self.gen, dtype=torch.int64)
         if self.ragged and self.eos is not None:
             t[t == self.eos] = (self.eos + 1) % self.V
@@ -177,9 +187,12 @@ def make_dataloader(args: TrainingArgs, model, rank: int, world: int = 1, consum
             "the pretraining hot path; pass any other iterator of {'text': LongTensor[mbs, seq+1]} batches to train()"
         )
     cfg = model.config
-    return SyntheticPackedDataset(cfg.vocab_size, args.training_parameters.micro_batch_size,
+    feed = SyntheticPackedDataset(cfg.vocab_size, args.training_parameters.micro_batch_size,
                                   ds.class_args["sequence_length"], rank=rank, eos_token_id=cfg.eos_token_id,
                                   ragged=bool(ds.class_args.get("ragged", False)))
+    # resume: skip the micro-batches this rank already drew (consumed_samples counts sequences over all ranks)
+    feed.load_state_dict({"batches": consumed_samples // (args.training_parameters.micro_batch_size * max(world, 1))})
+    return feed
 
 
 def train(args: TrainingArgs, model, optimizer, scheduler, dataloader, rank: int, world: int, starting_iteration: int = 0) -> list[float]:

@@ -123,6 +123,18 @@ int dolomite_b200_embedding_bwd(const int64_t* ids, const void* dout, float* dwt
 int dolomite_b200_cross_entropy_fwd_bwd(const void* logits, int64_t ldl, const int64_t* labels, void* dlogits,
                                         float* loss_per_token, float* loss_mean, float* scratch, int64_t T, int64_t V,
                                         int64_t ignore_index, float logit_scale, float grad_scale, void* stream);
+/* The same computation in three steps, for an LM head that never materialises [T, V] (gpt_dolomite/main.py:172-177 +
+ * model_wrapper/pretraining.py:107-127 fused): `_count` leaves the number of labels != ignore_index of the WHOLE batch in
+ * scratch[0]; `_rows` handles any chunk of rows (logits of the chunk, its labels, its slice of loss_per_token) and may be
+ * called once per chunk; `_mean` reduces loss_per_token [T] to the scalar loss.  A label outside [0, V) that is not
+ * ignore_index traps (device-side assert, like torch). */
+int dolomite_b200_cross_entropy_count(const int64_t* labels, int64_t T, int64_t ignore_index, float* scratch,
+                                      void* stream);
+int dolomite_b200_cross_entropy_rows(const void* logits, int64_t ldl, const int64_t* labels, void* dlogits,
+                                     float* loss_per_token, const float* scratch, int64_t T, int64_t V,
+                                     int64_t ignore_index, float logit_scale, float grad_scale, void* stream);
+int dolomite_b200_cross_entropy_mean(const float* loss_per_token, int64_t T, const float* scratch, float* loss_mean,
+                                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Column sum (bias gradient of nn.Linear, autograd of linear.py:5-25):  out[n] += scale * sum_t x[t, n]

@@ -157,3 +157,35 @@ def test_split_files_and_evaluate_loop(tmp_path):
     assert evaluate(None, model) is None
     args.training_parameters.eval_during_training = False
     assert make_sft_val_batches(args, tok, 2, 0, 1) is None
+
+
+def test_feed_resumes_where_it_stopped_and_ranks_draw_equal_counts():
+    """a resumed finetuning run must continue with the next unseen batch (reference finetune.py:150, :286-305 hand
+    the ResumableDataLoader to save / load), and with len(dataset) % world != 0 every rank still yields the same number of
+    batches (rank-sharded evaluation issues one collective per batch)."""
+    from dolomite_engine_b200.data.finetuning import batches
+    from dolomite_engine_b200.pretrain import SyntheticPackedDataset
+
+    ds = [{"input": [10 + i, 3], "output": [20 + i, 2]} for i in range(23)]  # 23 examples: not a multiple of 2 ranks x 2
+    counts = []
+    for rank in range(2):
+        it = batches(ds, 2, 2, True, rank=rank, world_size=2, seed=5, infinite=False)
+        counts.append(sum(1 for _ in it))
+    assert counts[0] == counts[1] == 23 // 4
+
+    a = batches(ds, 2, 2, True, rank=1, world_size=2, seed=5)
+    seen = [next(a)["input_ids"] for _ in range(8)]  # crosses an epoch boundary (5 batches per epoch)
+    state = a.state_dict()
+    assert state["epoch"] == 1 and state["offset"] == 3
+    expect = [next(a)["input_ids"] for _ in range(4)]
+    b = batches(ds, 2, 2, True, rank=1, world_size=2, seed=5)
+    b.load_state_dict(state)
+    assert [next(b)["input_ids"] for _ in range(4)] == expect
+    assert seen[0] != expect[0]
+
+    s1 = SyntheticPackedDataset(100, 2, 8, rank=3, pin=False)
+    first = [next(s1)["text"] for _ in range(5)]
+    s2 = SyntheticPackedDataset(100, 2, 8, rank=3, pin=False)
+    s2.load_state_dict({"consumed_samples": 3 * 2})
+    assert torch.equal(next(s2)["text"], first[3]) and torch.equal(next(s2)["text"], first[4])
+    assert s1.state_dict()["consumed_samples"] == 10

@@ -388,3 +388,45 @@ def test_root_parameter_init_rules():
     assert specs["lm_head.weight"] == ((264, 64), "normal:0.1")
     assert specs["transformer.wpe.weight"] == ((32, 64), "normal:0.1")
     assert specs["transformer.ln_f.weight"][1] == "ones" and specs["transformer.ln_f.bias"][1] == "zeros"
+
+
+def test_stage3_slot_table_never_hands_a_live_buffer_away():
+    """distributed._SlotTable: the ownership bookkeeping of the shared parameter buffers of the stage-3 (reshard) mode.
+    Replays the engine's hook order (forward: prefetch depth 1; backward: re-gather i and i-1) for several depths / slot
+    counts and checks that the buffer a block computes from holds that block's parameters, and that the slot given to a
+    prefetch never belongs to the block being computed."""
+    from dolomite_engine_b200.distributed import _SlotTable
+
+    for n_layer in (1, 2, 3, 4, 7):
+        for n_slots in (2, 3):
+            n = n_layer + 1
+            t = _SlotTable([False] + [True] * n_layer, n_slots)
+            gathers = []
+
+            def issue(i, busy=()):
+                if t.is_fresh(i):
+                    return
+                prev = t.claim(i)
+                assert prev not in busy, (n_layer, n_slots, i, prev, busy)
+                t.fresh[i] = True  # (the wait happens before use)
+                gathers.append(i)
+
+            for step in range(2):
+                t.invalidate()  # optimizer step: every gathered copy is stale
+                gathers.clear()
+                for i in range(n):  # forward
+                    issue(i)
+                    if i + 1 < n:
+                        issue(i + 1, busy=(i,))
+                    assert t.is_fresh(i)
+                fwd = len(gathers)
+                assert fwd == n  # one all-gather per unit
+                for i in reversed(range(1, n)):  # backward (root is not pooled and stays gathered)
+                    issue(i)
+                    if i - 1 >= 1:
+                        issue(i - 1, busy=(i,))
+                    assert t.is_fresh(i)
+                # blocks still resident at the end of forward are not gathered again
+                resident_at_end = min(n_slots, n_layer)
+                assert len(gathers) - fwd == n_layer - resident_at_end
+            assert t.is_fresh(0)

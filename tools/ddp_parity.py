@@ -3,7 +3,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/ddp_parity.py
 
 env: COMM_DTYPE=fp32|bf16 (wire dtype of the reduce-scatter), ACCUM=k (micro-steps per optimizer step, the first k-1
-under no_sync()), RESHARD=1 (stage-3 style: re-gather parameters in backward).
+under no_sync()), RESHARD=1 (what `stage: 3` means: block units share two parameter / gradient buffers, parameters are
+re-gathered in backward, gradients reduce-scattered per micro-step), CKPT=k (block activation checkpointing),
+SHARD=S (HSDP: S consecutive ranks per shard group).
 
 Every rank r feeds its own micro-batches to the sharded model (world_size = N); rank 0 additionally runs an unsharded
 copy of the same model over ALL micro-batches of all ranks.  Checks per step: (1) mean loss over ranks == mean loss
@@ -43,13 +45,15 @@ def main():
     group, rep_group, s_world, s_rank = build_data_parallel_groups(shard, world // shard if shard else None)
     w = ModelWrapperForPretraining(pretrained_config=dict(CFG), micro_batch_size=mbs, sequence_length=seq, device=dev,
                                    world_size=s_world, rank=s_rank)
+    if os.environ.get("CKPT"):
+        w.model.engine.checkpoint_every = int(os.environ["CKPT"])
     sdp = ShardedDataParallel(w, group, communication_dtype=comm_dtype, reshard_after_forward=reshard,
                               replicate_group=rep_group)
     opt = get_optimizer("DolomiteFusedAdamW", OPT, sdp)
     ref = ref_sdp = ref_opt = None
     if rank == 0:
         ref = ModelWrapperForPretraining(pretrained_config=dict(CFG), micro_batch_size=mbs, sequence_length=seq, device=dev)
-        ref_sdp = ShardedDataParallel(ref, None)
+        ref_sdp = ShardedDataParallel(ref, None, reshard_after_forward=False)
         ref_opt = get_optimizer("DolomiteFusedAdamW", OPT, ref_sdp)
     rng = np.random.default_rng(0)
     ok = True
@@ -70,6 +74,7 @@ def main():
         torch.cuda.synchronize()
         lsum /= accum
         dist.all_reduce(lsum, op=dist.ReduceOp.AVG)
+        fulls = [w.model.engine.full_master(u) for u in w.model.engine.units]  # collective: every rank
         if rank == 0:
             ref_sdp.zero_grad()
             rl = 0.0
@@ -81,11 +86,12 @@ def main():
             rl /= world * accum
             dl = abs(lsum.item() - rl) / rl
             worst, pworst = 0.0, 0.0
-            for u, ru in zip(w.model.engine.units, ref.model.engine.units):
-                a, b = u.compute[: ru.numel].float(), ru.compute[: ru.numel].float()
+            for u, ru, full in zip(w.model.engine.units, ref.model.engine.units, fulls):
+                # what the next all-gather will deliver (bf16 of the fp32 shards) vs the unsharded model's bf16 parameters
+                a, b = full[: ru.numel].bfloat16().float(), ru.compute[: ru.numel].float()
                 pworst = max(pworst, ((a - b).norm() / (b.norm() + 1e-20)).item())
                 g = u.master.grad
-                lo, hi = rank * u.shard_numel, (rank + 1) * u.shard_numel
+                lo, hi = s_rank * u.shard_numel, (s_rank + 1) * u.shard_numel
                 if hi <= ru.padded:
                     rg = (ru.master.grad / world)[lo:hi]
                     worst = max(worst, ((g - rg).norm() / (rg.norm() + 1e-20)).item())
