@@ -1,19 +1,29 @@
-"""Benchmark of the hot path: one full training step (fwd + bwd + reduce-scatter + clip + AdamW) of the
-GPTDolomite Granite-3B-code shape (BASELINE.json configs[1]: 32L / 2560d / 32 heads hd=80 / F=10240 / V=49152, bf16,
-seq 4096 padding-free, synthetic packed tokens) on N GPUs of one node.
+"""Benchmark of the hot path: one full training step (fwd + bwd + reduce-scatter + clip + AdamW) on N GPUs of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mbs 2] [--layers 32]
+    python bench.py [--config c2|c4|c5] [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|gpu_reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
+Workloads (BASELINE.json `configs`; shapes pinned by SURVEY.md section 8d):
+  c2 (default, the configuration the metric is quoted on)  GPTDolomite Granite-3B-code shape, 32L / 2560d / 32 heads hd 80 /
+      F 10240 / V 49152, bf16, seq 4096 padding-free pretraining, synthetic packed tokens
+  c4  MoEDolomite 24L / 2048d / 16 heads hd 128 / 8 experts top-2 (F 4096 each) / V 50304, seq 2048 pretraining
+  c5  Llama-3-8B shape through the `import_from_huggingface` config conversion (32L / 4096d / 32 heads, 8 KV heads, hd 128 /
+      F 14336 / V 128256, untied head, no bias), seq 8192 padding-free FINETUNING (ModelWrapperForFinetuning, ragged examples
+      with masked prompts), block activation checkpointing
+
 Prints ONE JSON line on rank 0 (contract in the task statement):
-  value      whole-job tokens/s with the batch already resident in HBM (device-timed, max over ranks)
-  e2e        the same metric through the reference-facing wrapper call `model({"text": cpu_tensor})` with pinned
-             HOST buffers: H2D of the step's tokens and D2H of the loss inside the timed region
-  roofline   dominant kernel = the tcgen05 GEMM: algorithmic FLOPs of every GEMM launch / CUDA-event time of that
-             launch, measured live inside the timed region, against the measured bf16 peak (MEASURED_PEAKS.json)
-  cpu_baseline  the oracle (CPU restatement of the reference, torch-eager fp32, eager attention) timed on the host
-             cores on a bounded sample (rank 0, N=1 only)
-`--impl reference` times that CPU implementation as its own arm (all host threads), same metric/config.
+  value        whole-job tokens/s with the batches already resident in HBM (device-timed, max over ranks)
+  e2e          the same metric through the reference-facing wrapper call (`model({"text": cpu_tensor})` /
+               `model({"input_ids": lists, "labels": lists})`) with HOST buffers: H2D of the step's tokens and D2H of the
+               loss inside the timed region
+  roofline     dominant kernel = the tcgen05 GEMM: algorithmic FLOPs of every GEMM launch / CUDA-event time of that
+               launch, measured live inside the timed region, against the measured bf16 peak (MEASURED_PEAKS.json)
+  gpu_reference  (N = 1) the reference's own PyTorch / flash-attn path (oracle/gpu_reference.py: cuBLAS nn.Linear,
+               flash_attn_varlen_func, eager RMSNorm / RoPE / SwiGLU / CE, autograd, torch AdamW) timed on the same GPU,
+               same shape -- the kernel-for-kernel baseline this engine has to beat
+  cpu_baseline the oracle (CPU restatement of the reference, torch-eager fp32, eager attention) timed on the host
+               cores on a bounded sample (rank 0, N = 1 only)
+`--impl reference` times that CPU implementation as its own arm (all host threads), same metric / config.
 """
 
 from __future__ import annotations
@@ -29,18 +39,57 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_COMMON = dict(position_embedding_type="rope", activation_function="swiglu", normalization_function="rmsnorm",
+               layer_norm_epsilon=1e-5, resid_pdrop=0, embd_pdrop=0, attn_pdrop=0, upcast_logits_for_loss=True)
 C2 = dict(model_type="gpt_dolomite", vocab_size=49152, n_positions=4096, n_embd=2560, n_layer=32, n_head=32, n_inner=10240,
-          attention_head_type="mha", position_embedding_type="rope", activation_function="swiglu",
-          normalization_function="rmsnorm", layer_norm_epsilon=1e-5, add_bias=True, resid_pdrop=0, embd_pdrop=0,
-          attn_pdrop=0, upcast_logits_for_loss=True, eos_token_id=0)
-SEQ = 4096
+          attention_head_type="mha", add_bias=True, eos_token_id=0, **_COMMON)
+C4 = dict(model_type="moe_dolomite", vocab_size=50304, n_positions=2048, n_embd=2048, n_layer=24, n_head=16, n_inner=4096,
+          num_experts=8, num_experts_per_tok=2, attention_head_type="mha", add_bias=False, eos_token_id=0, **_COMMON)
+# Meta-Llama-3-8B config.json as HuggingFace publishes it; converted by hf_models.model_conversion (llama.py:37-74)
+LLAMA3_8B_HF = dict(model_type="llama", vocab_size=128256, max_position_embeddings=8192, hidden_size=4096, num_hidden_layers=32,
+                    num_attention_heads=32, num_key_value_heads=8, intermediate_size=14336, hidden_act="silu", rms_norm_eps=1e-5,
+                    rope_theta=500000.0, attention_bias=False, mlp_bias=False, tie_word_embeddings=False, initializer_range=0.02,
+                    bos_token_id=128000, eos_token_id=128001)
+
+WORKLOADS = {
+    "c2": dict(seq=4096, mbs=6, kind="pretraining", checkpoint_every=None,
+               text="GPTDolomite Granite-3B-code shape (32L/2560d/hd80/F10240/V49152, 3.48B params) bf16 seq4096 padding-free, "
+                    "full train step (fwd+bwd+reduce-scatter+clip+AdamW)"),
+    "c4": dict(seq=2048, mbs=8, kind="pretraining", checkpoint_every=None,
+               text="MoEDolomite 8 experts top-2 (24L/2048d/hd128/F4096 per expert/V50304, 5.4B params) bf16 seq2048 "
+                    "padding-free, full train step"),
+    "c5": dict(seq=8192, mbs=1, kind="finetuning", checkpoint_every=2,
+               text="Llama-3-8B shape via the import_from_huggingface config conversion (32L/4096d/GQA 32:8 hd128/F14336/"
+                    "V128256, 8.03B params) bf16 seq8192 padding-free finetuning (4 ragged examples per micro-batch, prompts "
+                    "masked), block activation checkpointing, full train step"),
+}
 
 
-def flops_per_token(cfg: dict, seq: int) -> float:
-    """reference FLOP model, train_utils.py:197-236 (full SxS attention, no causal discount)"""
+def model_config(name: str, layers: int | None = None) -> dict:
+    if name == "c2":
+        cfg = dict(C2)
+    elif name == "c4":
+        cfg = dict(C4)
+    else:
+        from dolomite_engine_b200.hf_models.model_conversion import _import_config
+
+        cfg = _import_config(dict(LLAMA3_8B_HF)).to_dict()
+        cfg = {k: v for k, v in cfg.items() if v is not None and k not in ("transformers_version", "architectures")}
+        cfg["model_type"] = "gpt_dolomite"
+    if layers is not None:
+        cfg["n_layer"] = layers
+    return cfg
+
+
+def flops_per_token(cfg: dict, seq: int, checkpointed_fraction: float = 0.0) -> float:
+    """reference FLOP model, train_utils.py:197-236 (full SxS attention, no causal discount; recomputed blocks count)"""
     h, f, n, L, v = cfg["n_embd"], cfg["n_inner"], cfg["n_head"], cfg["n_layer"], cfg["vocab_size"]
     k = cfg.get("num_key_value_heads") or n
-    return 3 * L * (4 * h * (h * (1 + k / n) + seq) + 6 * h * f) + 6 * h * v
+    mlp = 6 * h * f
+    if cfg.get("model_type") == "moe_dolomite":
+        mlp = mlp * cfg["num_experts_per_tok"] + 2 * h * cfg["num_experts"]
+    fwd = 4 * h * (h * (1 + k / n) + seq) + mlp
+    return L * fwd * (3 + checkpointed_fraction) + 6 * h * v
 
 
 def measured_peaks() -> dict:
@@ -98,9 +147,14 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle (reference restatement) on the host cores, bounded sample, extrapolated per layer
+# CPU arm: the oracle (reference restatement) on the host cores, bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_tokens_per_s(cfg: dict, seq: int, steps: int = 1, warmup: int = 0, sample_layers: int = 1, sample_seq: int = 512):
+def cpu_reference_tokens_per_s(cfg: dict, seq: int, steps: int = 1, warmup: int = 0, sample_seq: int = 256,
+                               budget_s: float = 45.0):
+    """One full-depth (all layers) training step of the oracle -- forward, backward, clip and AdamW, fp32 torch-eager with
+    eager attention -- on ONE sequence of `sample_seq` tokens.  Nothing is extrapolated over layers; the only reduction of
+    the workload is the sequence length (attention's S^2 term is smaller than at the benchmark's S, which favours the CPU).
+    If the probe block shows that the full-depth step would blow the time budget the depth is cut and the cut is reported."""
     import numpy as np
     import torch
 
@@ -122,40 +176,54 @@ def cpu_reference_tokens_per_s(cfg: dict, seq: int, steps: int = 1, warmup: int 
         if best is None or dt < best:
             best, cores = dt, n
     torch.set_num_threads(cores)
-    small ={k: v for k, v in cfg.items() if k in O.OracleConfig.__dataclass_fields__}
-    small.update(n_layer=sample_layers, n_positions=max(sample_seq, 16))
-    ocfg = O.OracleConfig(**small)
-    params = {k: v.requires_grad_(True) for k, v in O.init_params(ocfg, seed=1).items()}
+    small = {k: v for k, v in cfg.items() if k in O.OracleConfig.__dataclass_fields__}
+    small.update(n_positions=max(sample_seq, 16))
     rng = np.random.default_rng(0)
-    tokens = rng.integers(0, ocfg.vocab_size, size=(1, sample_seq + 1), dtype=np.int64)
+    tokens = rng.integers(0, small["vocab_size"], size=(1, sample_seq + 1), dtype=np.int64)
 
-    def one(n_layer_cfg):
+    def build(n_layer):
+        ocfg = O.OracleConfig(**{**small, "n_layer": n_layer})
+        params = {k: v.requires_grad_(True) for k, v in O.init_params(ocfg, seed=1).items()}
+        opt = torch.optim.AdamW(list(params.values()), lr=1e-5, betas=(0.9, 0.95), eps=1e-10, weight_decay=0.1)
+        return ocfg, params, opt
+
+    def one(ocfg, params, opt):
         t0 = time.perf_counter()
-        loss, _ = O.pretraining_loss(params, n_layer_cfg, tokens)
+        opt.zero_grad(set_to_none=True)
+        loss, _ = O.pretraining_loss(params, ocfg, tokens)
         loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), 1.0)
+        opt.step()
         return time.perf_counter() - t0
 
-    for _ in range(max(warmup, 1)):
-        one(ocfg)
-    times = []
-    for _ in range(max(steps, 1)):
-        t_full = one(ocfg)
-        # head/embedding-only cost: zero layers
-        import dataclasses
+    # probe: one block + head, to size the depth to the budget
+    probe = build(1)
+    one(*probe)
+    t1 = one(*probe)
+    import dataclasses
 
-        t_head = one(dataclasses.replace(ocfg, n_layer=0))
-        times.append((t_full, t_head))
-    t_full = sum(t[0] for t in times) / len(times)
-    t_head = sum(t[1] for t in times) / len(times)
-    t_layer = max(t_full - t_head, 1e-9) / sample_layers
-    # attention cost grows with seq: per-token attention work at S is S/sample_seq times the sample's; the GEMM part
-    # is per token.  Keep the estimate conservative (favourable to the CPU): scale only by layer count.
-    t_token_full = (cfg["n_layer"] * t_layer + t_head) / sample_seq
-    return 1.0 / t_token_full, {
-        "value": 1.0 / t_token_full, "unit": "tokens/s", "cores": cores, "kind": "port",
-        "sample": (f"oracle (torch-eager fp32, eager attention) fwd+bwd of {sample_layers} C2 block(s) + LM head at "
-                   f"S={sample_seq}, mbs=1 ({t_full:.2f}s; head-only {t_head:.2f}s), extrapolated to {cfg['n_layer']} layers; "
-                   "attention S^2 growth to S=4096 and the optimizer step are NOT charged (favours the CPU)"),
+    probe0 = (dataclasses.replace(probe[0], n_layer=0), probe[1], probe[2])  # embedding + LM head only
+    one(*probe0)
+    t0_ = one(*probe0)
+    per_layer = max(t1 - t0_, 1e-3)
+    del probe, probe0
+    L = cfg["n_layer"]
+    runs = max(steps, 1) + max(warmup, 0)
+    depth = int(max(1, min(L, (budget_s / runs - t0_) / per_layer)))
+    state = build(depth)
+    for _ in range(max(warmup, 0)):
+        one(*state)
+    times = [one(*state) for _ in range(max(steps, 1))]
+    t_step = sum(times) / len(times)
+    if depth < L:  # depth had to be cut: charge the missing layers at the measured per-layer cost of THIS run
+        t_step = t_step + (L - depth) * (t_step - t0_) / depth
+    tps = sample_seq / t_step
+    return tps, {
+        "value": tps, "unit": "tokens/s", "cores": cores, "kind": "port",
+        "sample": (f"oracle (torch-eager fp32, eager attention): full train step (fwd+bwd+clip+AdamW) of {depth} of {L} layers + "
+                   f"LM head on 1 x {sample_seq} tokens, {t_step:.2f} s/step"
+                   + ("" if depth == L else f" after charging the {L - depth} missing layers at the measured per-layer time")
+                   + f"; the benchmark's S={seq} attention term is NOT charged (favours the CPU)"),
     }
 
 
@@ -163,17 +231,17 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    cfg = dict(C2)
-    cfg["n_layer"] = args.layers
+    wl = WORKLOADS[args.config]
+    cfg = model_config(args.config, args.layers)
     t0 = time.perf_counter()
-    tps, cb = cpu_reference_tokens_per_s(cfg, SEQ, steps=args.steps, warmup=min(args.warmup, 1))
-    tokens_per_step = args.mbs * SEQ
+    tps, cb = cpu_reference_tokens_per_s(cfg, wl["seq"], steps=args.steps, warmup=min(args.warmup, 1))
+    tokens_per_step = args.mbs * wl["seq"]
     line = {
         "impl": "reference", "metric": "tokens_per_sec", "value": tps, "unit": "tokens/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tokens_per_step / tps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "GPTDolomite Granite-3B-code shape (32L/2560d/hd80/F10240/V49152) bf16 seq4096 padding-free, "
-                               "full train step", "micro_batch_size": args.mbs, "seq_len": SEQ, "n_layer": cfg["n_layer"]},
+        "config": {"workload": wl["text"], "name": args.config, "micro_batch_size": args.mbs, "seq_len": wl["seq"],
+                   "n_layer": cfg["n_layer"]},
         "cpu_baseline": cb,
         "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
@@ -181,7 +249,62 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def run_gpu_reference(args) -> None:
+    """the reference's PyTorch / flash-attn path on cuda:0 (N = 1): own process, so its memory never coexists with the engine's"""
+    import torch
+
+    import oracle.gpu_reference as G
+
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    torch.cuda.set_device(0)
+    wl = WORKLOADS[args.config]
+    cfg = model_config(args.config, args.layers)
+    mbs = args.ref_mbs
+    out = {"impl": "gpu_reference", "metric": "tokens_per_sec", "unit": "tokens/s", "n_gpus": 1, "dtype": "bf16",
+           "config": {"workload": wl["text"], "name": args.config, "micro_batch_size": mbs, "seq_len": wl["seq"],
+                      "n_layer": cfg["n_layer"]},
+           "stack": "torch %s: F.linear (cuBLAS), flash_attn_varlen_func, eager RMSNorm/RoPE/SwiGLU/CE, autograd, torch.optim.AdamW"
+                    % torch.__version__}
+    try:
+        import flash_attn
+
+        out["flash_attn"] = flash_attn.__version__
+        r = G.time_train_steps(cfg, wl["seq"], mbs, steps=args.steps, warmup=args.warmup, device=torch.device("cuda", 0),
+                               docs_per_row=4 if wl["kind"] == "finetuning" else 1)
+        out.update(value=r["tokens_per_s"], ms_per_step=r["ms_per_step"], loss=r["loss"], peak_hbm_gb=r["peak_hbm_gb"],
+                   steps=args.steps, warmup=args.warmup)
+    except Exception as e:  # a baseline that cannot run is reported, never faked
+        out.update(value=None, error=f"{type(e).__name__}: {str(e)[:300]}")
+    print(json.dumps(out), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------
+class _FinetuneFeed:
+    """synthetic SFT micro-batches in the padding-free collate format of the reference (data/utils.py:8-92):
+    {"input_ids": list[list[int]], "labels": list[list[int]]}; every micro-batch packs `docs` examples whose lengths sum to
+    `tokens` (ragged, fixed seed); the first quarter of each example is the prompt (labels -100)."""
+
+    def __init__(self, vocab: int, tokens: int, docs: int, rank: int):
+        import numpy as np
+
+        self.rng = np.random.default_rng(4321 + rank)
+        self.vocab, self.tokens, self.docs = vocab, tokens, docs
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> dict:
+        cuts = sorted(self.rng.choice(range(64, self.tokens - 64, 8), size=self.docs - 1, replace=False).tolist())
+        lens = [b - a for a, b in zip([0] + cuts, cuts + [self.tokens])]
+        ids, labels = [], []
+        for n in lens:
+            x = self.rng.integers(0, self.vocab, size=n).tolist()
+            ids.append(x)
+            labels.append([-100] * (n // 4) + x[n // 4:])
+        return {"input_ids": ids, "labels": labels}
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
@@ -189,7 +312,7 @@ def run_ours(args) -> None:
     from dolomite_engine_b200 import _lib
     from dolomite_engine_b200 import kernels as K
     from dolomite_engine_b200.distributed import ShardedDataParallel
-    from dolomite_engine_b200.model_wrapper import ModelWrapperForPretraining
+    from dolomite_engine_b200.model_wrapper import ModelWrapperForFinetuning, ModelWrapperForPretraining
     from dolomite_engine_b200.optimization import get_optimizer
     from dolomite_engine_b200.pretrain import SyntheticPackedDataset
     from dolomite_engine_b200.train_utils import train_step
@@ -199,6 +322,22 @@ def run_ours(args) -> None:
     local = int(os.environ.get("LOCAL_RANK", 0))
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    wl = WORKLOADS[args.config]
+    cfg = model_config(args.config, args.layers)
+    mbs, seq = args.mbs, wl["seq"]
+
+    # the reference's GPU path first, in its own process (its memory is gone before the engine allocates)
+    gpu_ref = None
+    if world == 1 and not args.no_gpu_reference:
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "gpu_reference", "--config", args.config, "--steps", "4",
+               "--warmup", "2", "--ref-mbs", str(args.ref_mbs)] + (["--layers", str(args.layers)] if args.layers else [])
+        try:
+            proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+            lines = [l for l in proc.stdout.splitlines() if l.startswith("{")]
+            gpu_ref = json.loads(lines[-1]) if lines else {"value": None, "error": (proc.stderr or "no output")[-300:]}
+        except Exception as e:
+            gpu_ref = {"value": None, "error": f"{type(e).__name__}: {e}"}
+
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -206,16 +345,26 @@ def run_ours(args) -> None:
 
         configure_comm_ctas()
         dist.init_process_group(backend="nccl", rank=rank, world_size=world, device_id=dev)
-    cfg = dict(C2)
-    cfg["n_layer"] = args.layers
-    mbs, seq = args.mbs, SEQ
-    wrapper = ModelWrapperForPretraining(pretrained_config=cfg, micro_batch_size=mbs, sequence_length=seq, device=dev,
-                                         world_size=world, rank=rank, init_on_device=True,
-                                         reset_attention_mask=args.ragged, reset_position_ids=args.ragged)
+    finetune = wl["kind"] == "finetuning"
+    if finetune:
+        wrapper = ModelWrapperForFinetuning(pretrained_config=cfg, device=dev, world_size=world, rank=rank, init_on_device=True)
+    else:
+        wrapper = ModelWrapperForPretraining(pretrained_config=cfg, micro_batch_size=mbs, sequence_length=seq, device=dev,
+                                             world_size=world, rank=rank, init_on_device=True,
+                                             reset_attention_mask=args.ragged, reset_position_ids=args.ragged)
+    engine = wrapper.model.engine
+    ckpt_every = args.checkpoint_every if args.checkpoint_every is not None else wl["checkpoint_every"]
+    if ckpt_every:
+        engine.checkpoint_every = int(ckpt_every)
+    reshard = args.fsdp_mode == "reshard"
     model = ShardedDataParallel(wrapper, dist.group.WORLD if world > 1 else None,
-                                communication_dtype={"bf16": torch.bfloat16, "fp32": torch.float32}[args.comm_dtype])
+                                communication_dtype={"bf16": torch.bfloat16, "fp32": torch.float32}[args.comm_dtype],
+                                reshard_after_forward=reshard)
     opt = get_optimizer("DolomiteFusedAdamW", {"lr": 1e-5, "weight_decay": 0.1, "betas": [0.9, 0.95], "eps": 1e-10}, model)
-    data = SyntheticPackedDataset(cfg["vocab_size"], mbs, seq, rank=rank, eos_token_id=cfg["eos_token_id"], ragged=args.ragged)
+    if finetune:
+        data = _FinetuneFeed(cfg["vocab_size"], mbs * seq, 4 * mbs, rank)
+    else:
+        data = SyntheticPackedDataset(cfg["vocab_size"], mbs, seq, rank=rank, eos_token_id=cfg["eos_token_id"], ragged=args.ragged)
     tokens_per_step = mbs * seq * world
 
     def sync_all():
@@ -224,16 +373,32 @@ def run_ours(args) -> None:
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---------------- leg 1: batch resident in HBM ----------------
-    engine = wrapper.model.engine
-    batch = next(data)["text"]
-    ids, labels, pos, cu, max_seqlen = wrapper._stage(batch)
-    ids, labels, pos, cu = ids.clone(), labels.clone(), pos.clone(), cu.clone()
+    # ---------------- leg 1: batches resident in HBM (4 different batches, used in turn) ----------------
+    resident = []
+    for _ in range(4):
+        b = next(data)
+        if finetune:
+            from dolomite_engine_b200.hf_models.utils import convert_padding_free_lists_to_tensors
+
+            ids, pos, _, labels, cu, max_seqlen = convert_padding_free_lists_to_tensors(
+                input_ids=b["input_ids"], inputs_embeds=None, position_ids=None, token_type_ids=None, labels=b["labels"],
+                device=dev)
+            resident.append((ids, labels, pos, cu, max_seqlen))
+        else:
+            ids, labels, pos, cu, max_seqlen = wrapper._stage(b["text"])
+            resident.append((ids.clone(), labels.clone(), pos.clone(), cu.clone(), max_seqlen))
+    torch.cuda.synchronize()
+    turn = [0]
 
     def resident_step():
+        ids, labels, pos, cu, max_seqlen = resident[turn[0] % len(resident)]
+        turn[0] += 1
         model.zero_grad()
         model._refresh_parameters_if_needed()
-        loss = wrapper.model.forward_pretraining_loss(ids, pos, cu, max_seqlen, labels)
+        if finetune:
+            loss = wrapper.model(input_ids=ids, position_ids=pos, cu_seqlens=cu, max_seqlen=max_seqlen, labels=labels).loss
+        else:
+            loss = wrapper.model.forward_pretraining_loss(ids, pos, cu, max_seqlen, labels)
         loss.backward()
         model.clip_grad_norm_(1.0, fuse_into_optimizer=True)
         opt.step()
@@ -298,7 +463,7 @@ def run_ours(args) -> None:
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
-        e2e_step()  # includes H2D of the tokens (pinned) and D2H of loss / grad-norm (.item())
+        e2e_step()  # includes H2D of the tokens and D2H of loss / grad-norm (.item())
     t1.record()
     sync_all()
     ms_e2e = t0.elapsed_time(t1) / args.steps
@@ -312,49 +477,71 @@ def run_ours(args) -> None:
 
     if rank == 0:
         peaks = measured_peaks()
-        fpt = flops_per_token(cfg, seq)
+        frac_ckpt = 0.0
+        if ckpt_every:
+            frac_ckpt = len(range(0, cfg["n_layer"], int(ckpt_every))) / cfg["n_layer"]
+        fpt = flops_per_token(cfg, seq, frac_ckpt)
         value = tokens_per_step / (ms_resident / 1e3)
         e2e_val = tokens_per_step / (ms_e2e / 1e3)
         gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         peak = peaks["bf16_tflops_sustained"]
+        h2d = wrapper.h2d_bytes_per_step if not finetune else (3 * mbs * seq * 8 + (4 * mbs + 1) * 4)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic_table.json")
+        if os.path.exists(tpath):  # written by tools/gemm_traffic_table.py from `ncu --set full` captures of this library
+            traffic = json.load(open(tpath))
         line = {
             "metric": "tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_resident, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {
-                "workload": "GPTDolomite Granite-3B-code shape (32L/2560d/hd80/F10240/V49152, 3.48B params) bf16 seq4096 "
-                            "padding-free, full train step (fwd+bwd+reduce-scatter+clip+AdamW)",
+                "workload": wl["text"], "name": args.config,
                 "micro_batch_size": mbs, "global_batch": mbs * world, "seq_len": seq, "n_layer": cfg["n_layer"],
-                "parallelism": f"flat-bucket sharded data parallel x{world}", "packing": "ragged" if args.ragged else "uniform",
+                "parallelism": f"flat-bucket sharded data parallel x{world}" + (
+                    "" if world == 1 else (", stage 3 (parameters resharded after forward, shared gather / gradient buffers)"
+                                           if reshard else ", parameters kept gathered between forward and backward")),
+                "fsdp_mode": args.fsdp_mode if world > 1 else None,
+                "activation_checkpointing": f"every {ckpt_every} block(s)" if ckpt_every else None,
+                "packing": "ragged" if (args.ragged or finetune) else "uniform",
                 "communication_dtype": args.comm_dtype,
-                "l2": "working set (>=7 GB parameters + activations per step) far exceeds the 126 MB L2; no explicit flush",
+                "l2": "working set (parameters + activations per step, tens of GB) far exceeds the 126 MB L2; four resident "
+                      "batches are used in turn; no explicit flush",
             },
             "tokens_per_sec_per_gpu": value / world,
             "model_tflops_per_gpu": fpt * value / world / 1e12,
             "model_flops_per_token": fpt,
             "pct_of_bf16_peak_measured_sustained": 100.0 * fpt * value / world / 1e12 / peak,
             "pct_of_bf16_peak_measured_burst": 100.0 * fpt * value / world / 1e12 / peaks["bf16_tflops"],
-            "loss": last_loss, "loss_history_same_batch": [float(x) for x in torch.stack(loss_hist).tolist()],
+            "loss": last_loss, "loss_history": [float(x) for x in torch.stack(loss_hist).tolist()],
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "tokens/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": wrapper.h2d_bytes_per_step, "d2h_bytes_per_step": 8},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
             "gpu_launches": launches,
             "peak_hbm_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
             "roofline": {
-                "bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all nn.Linear fwd/dgrad/wgrad + LM head)",
+                "bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all nn.Linear fwd/dgrad/wgrad + LM head"
+                                             + (", grouped expert GEMMs)" if cfg.get("model_type") == "moe_dolomite" else ")"),
                 "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s",
                 "frac": (gemm_tflops / peak) if gemm_tflops else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` capture
-                # (c_fc forward, M=8192 N=20480 K=2560, CTA-pair kernel): 256.7 MB + 304.8 MB vs 482.3 MB algorithmic
-                "traffic": 561486336, "traffic_algorithmic": 482344960,
-                "traffic_source": "profiles/r01_ncu_gemm_fc_pair_call14.txt (tensor pipe 93.4 % active)",
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of THIS library,
+                # one row per GEMM shape of the step (null until the capture script has run for this commit)
+                "traffic": (traffic or {}).get("dominant_launch_dram_bytes"),
+                "traffic_algorithmic": (traffic or {}).get("dominant_launch_algorithmic_bytes"),
+                "traffic_source": "profiles/r02_gemm_traffic_table.json" if traffic else None,
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_timed": len(gemm_records), "share_of_step": gemm_ms / (ms_resident * args.steps),
             },
         }
+        if gpu_ref is not None:
+            line["gpu_reference"] = gpu_ref
+            if gpu_ref.get("value"):
+                line["vs_gpu_reference"] = {"resident": value / gpu_ref["value"], "e2e": e2e_val / gpu_ref["value"],
+                                            "note": "tokens/s of this engine / tokens/s of the reference's PyTorch+flash-attn "
+                                                    "path on the same GPU (its micro-batch is smaller: eager autograd keeps "
+                                                    "more activations)"}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                _, cb = cpu_reference_tokens_per_s(cfg, seq, steps=1, warmup=1)
+                _, cb = cpu_reference_tokens_per_s(cfg, seq, steps=1, warmup=0)
                 line["cpu_baseline"] = cb
             except Exception as e:  # the oracle is test infrastructure; never let it break the measurement
                 line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
@@ -370,20 +557,33 @@ def main() -> None:
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mbs", type=int, default=6,
-                    help="sequences of 4096 tokens per GPU per step, chosen to fill memory (SURVEY 8d): 4 -> 117 GB, 6 -> ~146 GB "
-                         "of 180 GB; measured 41.1 k / 42.1 k / 42.3 k tokens/s at 4 / 6 / 7")
-    ap.add_argument("--layers", type=int, default=32)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "gpu_reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--mbs", type=int, default=None,
+                    help="sequences per GPU per step; default per workload (c2: 6 x 4096 fills ~146 of 180 GB, measured 41.1 k / "
+                         "42.1 k / 42.3 k tokens/s at 4 / 6 / 7)")
+    ap.add_argument("--ref-mbs", type=int, default=None, help="micro-batch of the gpu_reference arm (eager autograd keeps more)")
+    ap.add_argument("--layers", type=int, default=None, help="override the depth (probes only: a shallower model is not the workload)")
     ap.add_argument("--ragged", action="store_true")
     ap.add_argument("--comm-dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--fsdp-mode", default="reshard", choices=["reshard", "resident"],
+                    help="N > 1: reshard = the reference's stage 3 (FULL_SHARD); resident = parameters stay gathered (B200 option)")
+    ap.add_argument("--checkpoint-every", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--profile-step", default=None, metavar="JSON",
                     help="diagnostic: write per-kernel device times of one extra (untimed) step to this file")
     args = ap.parse_args()
+    wl = WORKLOADS[args.config]
+    if args.mbs is None:
+        args.mbs = wl["mbs"]
+    if args.ref_mbs is None:
+        args.ref_mbs = {"c2": 2, "c4": 2, "c5": 1}[args.config]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "gpu_reference":
+        run_gpu_reference(args)
     else:
         run_ours(args)
 

@@ -128,8 +128,8 @@ def test_moe_layer_matches_golden(golden_dir):
     y, saved = moe.forward(eng, eng.units[1], "transformer.h.0.", x, zero, 1.0)
     torch.cuda.synchronize()
     ref = torch.from_numpy(fx["y"])
-    assert (y.float().cpu() - ref).abs().max() < 2e-3 * max(1.0, ref.abs().max().item() / 1e-2) or rel_l2(y, ref) < 2e-2
     assert rel_l2(y, ref) < 2e-2
+    assert (y.float().cpu() - ref).abs().max() < 4 * 2.0**-8 * ref.abs().max() + 5e-3  # every element within ~4 bf16 ulp of the largest
     # bf16 router logits can reorder near-ties; the histogram must still sum to T*k
     assert int(saved[0].counts.sum().item()) == x.shape[0] * 2
 
