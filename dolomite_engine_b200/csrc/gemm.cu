@@ -7,6 +7,8 @@
 //     fwd   Y[T,N]  = X[T,K]  . W[N,K]^T          A K-major,  B K-major
 //     dgrad dX[T,K] = dY[T,N] . W[N,K]            A K-major,  B MN-major (stored [N(contraction), K(out)])
 //     wgrad dW[N,K] = dY[T,N]^T . X[T,K]          A MN-major, B MN-major (contraction over T)
+#include <string.h>
+
 #include "common.cuh"
 #include "../../include/dolomite_b200.h"
 
@@ -29,17 +31,36 @@ constexpr int TMEM_COLS = 512;  // 2 accumulator stages x 256 fp32 columns
 constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BUFS * EPI_SLAB_BYTES + 256 /*barriers*/;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 
-struct GemmParams {
+constexpr int MAXP = 4;  // problems per launch (the four weight gradients of a transformer block share one launch)
+
+// Epilogue variants.  The fp32 TMA modes exist for the weight gradients: every epilogue warp stages its 32 rows x 32 fp32
+// columns in a private shared-memory slab and hands it to the TMA engine as a tile store (first gradient of a window:
+// overwrite) or a tile REDUCE-ADD performed by the L2 (accumulation) -- the first version read-modify-wrote the fp32
+// accumulator with per-thread float4 accesses, one 128-byte line per lane.
+enum EpiMode { EPI_DIRECT = 0, EPI_BF16_TMA = 1, EPI_F32_TMA_STORE = 2, EPI_F32_TMA_ADD = 3 };
+
+struct GemmMaps {
+    CUtensorMap a[MAXP], b[MAXP], d[MAXP];
+};
+
+struct Problem {
     void* D;
     const void* C;
     const __nv_bfloat16* bias;
     int64_t ldd, ldc;
-    int M, N, K;
-    float alpha, beta;
-    int d_is_f32;
-    int tma_store;
+    int M, N;
     int num_m, num_n, num_kb;
-    int group_m;  // m-blocks per rasterisation panel
+    int group_m;     // m-blocks per rasterisation panel
+    int tile_start;  // first launch-wide tile index of this problem
+    int epi;         // EpiMode
+    float alpha, beta;
+};
+
+struct GemmParams {
+    Problem pr[MAXP];
+    int n_prob;
+    int num_tiles;  // over all problems (grouped modes: single problem, includes the group factor)
+    int d_is_f32;
     // grouped modes (MoE experts; moe_dolomite/moe/scatter.py:38-49 parallel_linear):
     //   1 = M-grouped: every 128-row tile of A/D belongs to one group (m_tile_group[m_blk], -1 = unused tile); B's outer
     //       TMA coordinate is offset by group * b_group_rows (fwd / dgrad of the expert linears)
@@ -54,6 +75,7 @@ struct GemmParams {
 };
 
 struct TileInfo {
+    int q;  // problem index
     int m_blk, n_blk, grp, kb0, kb1;
     bool valid;
 };
@@ -73,28 +95,34 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int gm,
 
 __device__ __forceinline__ TileInfo tile_info(int t, const GemmParams& p) {
     TileInfo ti;
+    ti.q = 0;
+#pragma unroll
+    for (int i = 1; i < MAXP; ++i)
+        if (i < p.n_prob && t >= p.pr[i].tile_start) ti.q = i;
+    const Problem& pr = p.pr[ti.q];
+    t -= pr.tile_start;
     ti.grp = 0;
     ti.kb0 = 0;
-    ti.kb1 = p.num_kb;
+    ti.kb1 = pr.num_kb;
     ti.valid = true;
     if (p.grouped == 3) {
         // split-K: tile index also enumerates the K split; partial products are reduced with fp32 atomics
-        const int per = p.num_m * p.num_n;
+        const int per = pr.num_m * pr.num_n;
         const int split = t / per;
-        tile_coords(t - split * per, p.num_m, p.num_n, p.group_m, ti.m_blk, ti.n_blk);
-        const int kb_per = (p.num_kb + p.num_groups - 1) / p.num_groups;
+        tile_coords(t - split * per, pr.num_m, pr.num_n, pr.group_m, ti.m_blk, ti.n_blk);
+        const int kb_per = (pr.num_kb + p.num_groups - 1) / p.num_groups;
         ti.kb0 = split * kb_per;
-        ti.kb1 = min(p.num_kb, ti.kb0 + kb_per);
+        ti.kb1 = min(pr.num_kb, ti.kb0 + kb_per);
         ti.valid = ti.kb1 > ti.kb0;
     } else if (p.grouped == 2) {
-        const int per = p.num_m * p.num_n;
+        const int per = pr.num_m * pr.num_n;
         ti.grp = t / per;
-        tile_coords(t - ti.grp * per, p.num_m, p.num_n, p.group_m, ti.m_blk, ti.n_blk);
+        tile_coords(t - ti.grp * per, pr.num_m, pr.num_n, pr.group_m, ti.m_blk, ti.n_blk);
         ti.kb0 = p.group_k_offsets[ti.grp] / BK;
         ti.kb1 = p.group_k_offsets[ti.grp + 1] / BK;
         ti.valid = ti.kb1 > ti.kb0;
     } else {
-        tile_coords(t, p.num_m, p.num_n, p.group_m, ti.m_blk, ti.n_blk);
+        tile_coords(t, pr.num_m, pr.num_n, pr.group_m, ti.m_blk, ti.n_blk);
         if (p.grouped == 1) {
             ti.grp = p.m_tile_group[ti.m_blk];
             ti.valid = ti.grp >= 0;
@@ -110,8 +138,7 @@ __device__ __forceinline__ TileInfo tile_info(int t, const GemmParams& p) {
 // own epilogue.  In CTA2 mode p.num_m counts 256-row super tiles and grouped modes are not used.
 template <bool A_MN, bool B_MN, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-    gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
+    gemm_bf16_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmParams p) {
     constexpr int NSTAGE = CTA2 ? 6 : STAGES;
     constexpr int B_BYTES = CTA2 ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
     constexpr int STG_BYTES = A_STAGE_BYTES + B_BYTES;
@@ -130,15 +157,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m * p.num_n * (p.grouped >= 2 ? p.num_groups : 1);
+    const int num_tiles = p.num_tiles;
     const int cta_rank = CTA2 ? int(blockIdx.x & 1) : 0;          // == %cluster_ctarank for cluster dims (2,1,1)
     const int worker = CTA2 ? int(blockIdx.x >> 1) : int(blockIdx.x);  // persistent worker (CTA or CTA pair) index
     const int num_workers = CTA2 ? int(gridDim.x >> 1) : int(gridDim.x);
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_a);
-        tma_prefetch_desc(&tmap_b);
-        if (p.tma_store) tma_prefetch_desc(&tmap_d);
+        for (int q = 0; q < p.n_prob; ++q) {
+            tma_prefetch_desc(&maps.a[q]);
+            tma_prefetch_desc(&maps.b[q]);
+            if (p.pr[q].epi != EPI_DIRECT) tma_prefetch_desc(&maps.d[q]);
+        }
         for (int i = 0; i < NSTAGE; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -167,6 +196,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             for (int t = worker; t < num_tiles; t += num_workers) {
                 const TileInfo ti = tile_info(t, p);
                 if (!ti.valid) continue;
+                const CUtensorMap* tmap_a = &maps.a[ti.q];
+                const CUtensorMap* tmap_b = &maps.b[ti.q];
                 const int m_blk = CTA2 ? ti.m_blk * 2 + cta_rank : ti.m_blk, n_blk = ti.n_blk;
                 const int b_outer = (p.grouped == 1) ? ti.grp * p.b_group_rows : 0;
                 for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
@@ -178,34 +209,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STG_BYTES);
                         const int n_row = n_blk * BN + cta_rank * (BN / 2);  // this CTA's half of the B tile
                         if (!A_MN) {
-                            tma_load_2d_2cta(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+                            tma_load_2d_2cta(sa, tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
                         } else {
 #pragma unroll
                             for (int i = 0; i < BM / 64; ++i)
-                                tma_load_2d_2cta(sa + i * (BK * 128), &tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+                                tma_load_2d_2cta(sa + i * (BK * 128), tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
                         }
                         if (!B_MN) {
-                            tma_load_2d_2cta(sb, &tmap_b, &full_bar[stage], kb * BK, n_row);
+                            tma_load_2d_2cta(sb, tmap_b, &full_bar[stage], kb * BK, n_row);
                         } else {
 #pragma unroll
                             for (int i = 0; i < BN / 128; ++i)
-                                tma_load_2d_2cta(sb + i * (BK * 128), &tmap_b, &full_bar[stage], n_row + i * 64, kb * BK);
+                                tma_load_2d_2cta(sb + i * (BK * 128), tmap_b, &full_bar[stage], n_row + i * 64, kb * BK);
                         }
                     } else {
                         mbar_expect_tx(&full_bar[stage], STG_BYTES);
                         if (!A_MN) {
-                            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+                            tma_load_2d(sa, tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
                         } else {
 #pragma unroll
                             for (int i = 0; i < BM / 64; ++i)
-                                tma_load_2d(sa + i * (BK * 128), &tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+                                tma_load_2d(sa + i * (BK * 128), tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
                         }
                         if (!B_MN) {
-                            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, b_outer + n_blk * BN);
+                            tma_load_2d(sb, tmap_b, &full_bar[stage], kb * BK, b_outer + n_blk * BN);
                         } else {
 #pragma unroll
                             for (int i = 0; i < BN / 64; ++i)
-                                tma_load_2d(sb + i * (BK * 128), &tmap_b, &full_bar[stage], n_blk * BN + i * 64,
+                                tma_load_2d(sb + i * (BK * 128), tmap_b, &full_bar[stage], n_blk * BN + i * 64,
                                             b_outer + kb * BK);
                         }
                     }
@@ -262,23 +293,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         int acc = 0;
         uint32_t acc_phase = 0;
         int epi_buf = 0;
+        bool cta_stores = false, warp_stores = false;  // which kind of bulk group this thread may still have in flight
+        uint8_t* wslab = smem_epi + sub * (EPI_BUFS * EPI_SLAB_BYTES / 4);  // this warp's two private 4 KB slabs (fp32 modes)
+        int wbuf = 0;
         for (int t = worker; t < num_tiles; t += num_workers) {
             const TileInfo ti = tile_info(t, p);
             if (!ti.valid) continue;
+            const Problem& pr = p.pr[ti.q];
+            const CUtensorMap* tmap_d = &maps.d[ti.q];
             const int m_blk = CTA2 ? ti.m_blk * 2 + cta_rank : ti.m_blk, n_blk = ti.n_blk;
             const int64_t d_off = (p.grouped == 2) ? int64_t(ti.grp) * p.d_group_stride : 0;
             mbar_wait(&tmem_full[acc], acc_phase, 4);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t(sub * 32) << 16) + uint32_t(acc * BN);
             const int64_t row = int64_t(m_blk) * BM + et;
-            const bool row_ok = row < p.M;
+            const bool row_ok = row < pr.M;
             const int col0 = n_blk * BN;
+            const float alpha = pr.alpha, beta = pr.beta;
+            const __nv_bfloat16* bias = pr.bias;
+            const int N = pr.N;
 
-            if (p.tma_store) {
+            if (pr.epi == EPI_BF16_TMA) {
+                cta_stores = true;
                 // 4 slabs of 64 columns: regs -> swizzled smem -> TMA store
 #pragma unroll 1
                 for (int slab = 0; slab < BN / 64; ++slab) {
-                    if (col0 + slab * 64 >= p.N) break;
+                    if (col0 + slab * 64 >= N) break;
                     uint8_t* buf = smem_epi + epi_buf * EPI_SLAB_BYTES;
                     // the buffer must have been fully read by the TMA store issued two slabs ago
                     if (et == 0) tma_store_wait_read<EPI_BUFS - 1>();
@@ -293,14 +333,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                             float f[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[c * 8 + j]);
-                            if (p.bias != nullptr) {
+                            if (bias != nullptr) {
                                 const int cb = col0 + slab * 64 + h * 32 + c * 8;
 #pragma unroll
                                 for (int j = 0; j < 8; ++j)
-                                    if (cb + j < p.N) f[j] += __bfloat162float(p.bias[cb + j]);
+                                    if (cb + j < N) f[j] += __bfloat162float(bias[cb + j]);
                             }
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] *= p.alpha;
+                            for (int j = 0; j < 8; ++j) f[j] *= alpha;
                             uint4 v;
                             v.x = pack_bf16(f[0], f[1]);
                             v.y = pack_bf16(f[2], f[3]);
@@ -313,16 +353,52 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     fence_proxy_async_smem();
                     named_bar_sync(1, 128);
                     if (et == 0) {
-                        tma_store_2d(&tmap_d, buf, col0 + slab * 64, m_blk * BM);
+                        tma_store_2d(tmap_d, buf, col0 + slab * 64, m_blk * BM);
                         tma_store_commit();
                     }
                     epi_buf ^= 1;
+                }
+            } else if (pr.epi == EPI_F32_TMA_STORE || pr.epi == EPI_F32_TMA_ADD) {
+                // fp32 D (weight gradients): 8 slabs of 32 columns.  Each warp owns its 32 rows: TMEM -> registers -> a
+                // private SW128 slab (32 rows x 128 B) -> one TMA tile store / reduce-add per slab.  No CTA-wide barrier.
+                warp_stores = true;
+                const bool add = pr.epi == EPI_F32_TMA_ADD;
+                const int row0 = m_blk * BM + sub * 32;
+#pragma unroll 1
+                for (int slab = 0; slab < BN / 32; ++slab) {
+                    const int cb = col0 + slab * 32;
+                    if (cb >= N) break;
+                    uint8_t* buf = wslab + wbuf * 4096;
+                    if (lane == 0) tma_store_wait_read<1>();  // the operation issued from this slab two slabs ago has read it
+                    __syncwarp();
+                    uint32_t r[32];
+                    tmem_ld32(t_addr + slab * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint4 v;
+                        v.x = __float_as_uint(__uint_as_float(r[c * 4 + 0]) * alpha);
+                        v.y = __float_as_uint(__uint_as_float(r[c * 4 + 1]) * alpha);
+                        v.z = __float_as_uint(__uint_as_float(r[c * 4 + 2]) * alpha);
+                        v.w = __float_as_uint(__uint_as_float(r[c * 4 + 3]) * alpha);
+                        *reinterpret_cast<uint4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4)) = v;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (row0 < pr.M) {  // rows / columns beyond the tensor are clipped by the TMA unit
+                            if (add) tma_reduce_add_3d(tmap_d, buf, cb, row0, ti.grp);
+                            else tma_store_3d(tmap_d, buf, cb, row0, ti.grp);
+                        }
+                        tma_store_commit();
+                    }
+                    wbuf ^= 1;
                 }
             } else {
 #pragma unroll 1
                 for (int ch = 0; ch < BN / 32; ++ch) {
                     const int cb = col0 + ch * 32;
-                    if (cb >= p.N) break;
+                    if (cb >= N) break;
                     uint32_t r[32];
                     tmem_ld32(t_addr + ch * 32, r);
                     tmem_ld_wait();
@@ -330,19 +406,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
-                    if (p.bias != nullptr) {
+                    if (bias != nullptr) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (cb + j < p.N) f[j] += __bfloat162float(p.bias[cb + j]);
+                            if (cb + j < N) f[j] += __bfloat162float(bias[cb + j]);
                     }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
+                    for (int j = 0; j < 32; ++j) f[j] *= alpha;
                     if (p.d_is_f32) {
-                        float* drow = static_cast<float*>(p.D) + d_off + row * p.ldd + cb;
-                        const float* crow = p.C ? static_cast<const float*>(p.C) + d_off + row * p.ldc + cb : nullptr;
+                        float* drow = static_cast<float*>(pr.D) + d_off + row * pr.ldd + cb;
+                        const float* crow = pr.C ? static_cast<const float*>(pr.C) + d_off + row * pr.ldc + cb : nullptr;
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            if (cb + q * 4 < p.N) {  // N % 8 == 0 -> whole float4 in range
+                            if (cb + q * 4 < N) {  // N % 8 == 0 -> whole float4 in range
                                 float4 o = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
                                 if (p.grouped == 3) {  // split-K partial: D += o
                                     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + q * 4),
@@ -352,24 +428,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                                 }
                                 if (crow) {
                                     const float4 c4 = *reinterpret_cast<const float4*>(crow + q * 4);
-                                    o.x += p.beta * c4.x; o.y += p.beta * c4.y; o.z += p.beta * c4.z; o.w += p.beta * c4.w;
+                                    o.x += beta * c4.x; o.y += beta * c4.y; o.z += beta * c4.z; o.w += beta * c4.w;
                                 }
                                 *reinterpret_cast<float4*>(drow + q * 4) = o;
                             }
                         }
                     } else {
-                        __nv_bfloat16* drow = static_cast<__nv_bfloat16*>(p.D) + d_off + row * p.ldd + cb;
+                        __nv_bfloat16* drow = static_cast<__nv_bfloat16*>(pr.D) + d_off + row * pr.ldd + cb;
                         const __nv_bfloat16* crow =
-                            p.C ? static_cast<const __nv_bfloat16*>(p.C) + d_off + row * p.ldc + cb : nullptr;
+                            pr.C ? static_cast<const __nv_bfloat16*>(pr.C) + d_off + row * pr.ldc + cb : nullptr;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            if (cb + q * 8 < p.N) {
+                            if (cb + q * 8 < N) {
                                 if (crow) {
                                     const uint4 cv = *reinterpret_cast<const uint4*>(crow + q * 8);
-                                    f[q * 8 + 0] += p.beta * bf16_lo(cv.x); f[q * 8 + 1] += p.beta * bf16_hi(cv.x);
-                                    f[q * 8 + 2] += p.beta * bf16_lo(cv.y); f[q * 8 + 3] += p.beta * bf16_hi(cv.y);
-                                    f[q * 8 + 4] += p.beta * bf16_lo(cv.z); f[q * 8 + 5] += p.beta * bf16_hi(cv.z);
-                                    f[q * 8 + 6] += p.beta * bf16_lo(cv.w); f[q * 8 + 7] += p.beta * bf16_hi(cv.w);
+                                    f[q * 8 + 0] += beta * bf16_lo(cv.x); f[q * 8 + 1] += beta * bf16_hi(cv.x);
+                                    f[q * 8 + 2] += beta * bf16_lo(cv.y); f[q * 8 + 3] += beta * bf16_hi(cv.y);
+                                    f[q * 8 + 4] += beta * bf16_lo(cv.z); f[q * 8 + 5] += beta * bf16_hi(cv.z);
+                                    f[q * 8 + 6] += beta * bf16_lo(cv.w); f[q * 8 + 7] += beta * bf16_hi(cv.w);
                                 }
                                 uint4 v;
                                 v.x = pack_bf16(f[q * 8 + 0], f[q * 8 + 1]);
@@ -391,7 +467,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (p.tma_store && et == 0) tma_store_wait_all<0>();
+        // shared memory must outlive every bulk operation that still reads it
+        if ((cta_stores && et == 0) || (warp_stores && lane == 0)) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -411,9 +488,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 }
 
 template <bool A_MN, bool B_MN>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p,
-                cudaStream_t st, bool cta_pair) {
-    const int tiles = p.num_m * p.num_n * (p.grouped >= 2 ? p.num_groups : 1);
+int launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t st, bool cta_pair) {
+    const int tiles = p.num_tiles;
     if (cta_pair) {
         auto kern = gemm_bf16_kernel<A_MN, B_MN, true>;
         static bool attr_set2 = false;  // per instantiation
@@ -434,7 +510,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        DOLO_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, p));
+        DOLO_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, maps, p));
         return DOLO_OK;
     }
     auto kern = gemm_bf16_kernel<A_MN, B_MN, false>;
@@ -445,7 +521,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     }
     const int sms = dolo_num_sms() - dolo_option_gemm_sm_margin();
     const int grid = tiles < sms ? tiles : sms;
-    kern<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(ta, tb, td, p);
+    kern<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(maps, p);
     DOLO_LAUNCH_OK("gemm_bf16");
     return DOLO_OK;
 }
@@ -462,91 +538,173 @@ struct GroupArgs {
     int64_t b_total_outer = 0;  // rows of B's outer TMA dimension over all groups
 };
 
-static int gemm_impl(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D,
-                     int64_t ldd, int d_is_f32, const void* C, int64_t ldc, float alpha, float beta, const void* bias,
-                     int64_t M, int64_t N, int64_t K, int flags, void* stream, const GroupArgs& ga) {
-    DOLO_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative dimension");
-    if (M == 0 || N == 0) return DOLO_OK;
+// one problem of a launch
+struct GemmProblemArgs {
+    const void* A; int64_t lda;
+    const void* B; int64_t ldb;
+    void* D; int64_t ldd;
+    const void* C; int64_t ldc;
+    const void* bias;
+    float alpha, beta;
+    int64_t M, N, K;
+};
+
+// Fills maps.{a,b,d}[q] and p.pr[q] for one problem.  All problems of a launch share the operand layouts, the output type,
+// the epilogue kind and the CTA-pair decision.
+static int setup_problem(GemmMaps& maps, GemmParams& p, int q, const GemmProblemArgs& g, int a_mn_major, int b_mn_major,
+                         int d_is_f32, int epi, bool cta_pair, const GroupArgs& ga) {
+    const int64_t M = g.M, N = g.N, K = g.K;
     DOLO_REQUIRE(K > 0, "gemm: K must be > 0");
     DOLO_REQUIRE(K % 8 == 0 && N % 8 == 0, "gemm: K=%lld and N=%lld must be multiples of 8", (long long)K, (long long)N);
-    DOLO_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldd % (d_is_f32 ? 4 : 8) == 0, "gemm: leading dimensions must keep 16-byte alignment");
+    DOLO_REQUIRE(g.lda % 8 == 0 && g.ldb % 8 == 0 && g.ldd % (d_is_f32 ? 4 : 8) == 0,
+                 "gemm: leading dimensions must keep 16-byte alignment");
     DOLO_REQUIRE(!a_mn_major || M % 8 == 0, "gemm: MN-major A requires M %% 8 == 0");
-    DOLO_REQUIRE(C == nullptr || ldc % (d_is_f32 ? 4 : 8) == 0, "gemm: ldc alignment");
+    DOLO_REQUIRE(g.C == nullptr || g.ldc % (d_is_f32 ? 4 : 8) == 0, "gemm: ldc alignment");
     DOLO_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm: dimension too large");
-    const bool tma_store = (flags & DOLO_GEMM_FLAG_TMA_STORE) != 0;
-    DOLO_REQUIRE(!tma_store || (!d_is_f32 && C == nullptr), "gemm: TMA-store epilogue needs bf16 D and no C");
-    // CTA-pair (cta_group::2) kernel: dense mode only, at least one full 256-row super tile
-    const bool cta_pair = ga.mode == 0 && M >= 2 * BM &&
-                          ((flags & DOLO_GEMM_FLAG_CTA_PAIR) != 0 || dolo_option_gemm_cta_pair() != 0) &&
-                          (flags & DOLO_GEMM_FLAG_NO_CTA_PAIR) == 0;
-
-    CUtensorMap ta, tb, td;
-    {
-        // K-major: dims {K, rows}, box {64, tile rows}.  MN-major: dims {rows, K}, box {64, 64}.
-        uint64_t dims[2], strides[2];
-        uint32_t box[2];
-        if (!a_mn_major) {
-            dims[0] = uint64_t(K); dims[1] = uint64_t(M); strides[0] = 2; strides[1] = uint64_t(lda) * 2;
-            box[0] = BK; box[1] = BM;
-        } else {
-            dims[0] = uint64_t(M); dims[1] = uint64_t(K); strides[0] = 2; strides[1] = uint64_t(lda) * 2;
-            box[0] = 64; box[1] = BK;
-        }
-        int rc = dolo_make_tmap(&ta, A, 2, 2, dims, strides, box, DOLO_SW_128);
-        if (rc) return rc;
-        if (!b_mn_major) {
-            dims[0] = uint64_t(K); dims[1] = uint64_t(ga.mode == 1 ? ga.b_total_outer : N); strides[1] = uint64_t(ldb) * 2;
-            box[0] = BK; box[1] = cta_pair ? BN / 2 : BN;  // pair mode: each CTA stages half of the B tile
-        } else {
-            dims[0] = uint64_t(N); dims[1] = uint64_t(ga.mode == 1 ? ga.b_total_outer : K); strides[1] = uint64_t(ldb) * 2;
-            box[0] = 64; box[1] = BK;
-        }
-        rc = dolo_make_tmap(&tb, B, 2, 2, dims, strides, box, DOLO_SW_128);
-        if (rc) return rc;
-        if (tma_store) {
-            dims[0] = uint64_t(N); dims[1] = uint64_t(M); strides[1] = uint64_t(ldd) * 2;
-            box[0] = 64; box[1] = BM;
-            rc = dolo_make_tmap(&td, D, 2, 2, dims, strides, box, DOLO_SW_128);
-            if (rc) return rc;
-        } else {
-            td = ta;  // unused
-        }
+    // K-major: dims {K, rows}, box {64, tile rows}.  MN-major: dims {rows, K}, box {64, 64}.
+    uint64_t dims[3], strides[3];
+    uint32_t box[3];
+    if (!a_mn_major) {
+        dims[0] = uint64_t(K); dims[1] = uint64_t(M); strides[0] = 2; strides[1] = uint64_t(g.lda) * 2;
+        box[0] = BK; box[1] = BM;
+    } else {
+        dims[0] = uint64_t(M); dims[1] = uint64_t(K); strides[0] = 2; strides[1] = uint64_t(g.lda) * 2;
+        box[0] = 64; box[1] = BK;
     }
-    GemmParams p;
-    p.D = D;
-    p.C = C;
-    p.bias = static_cast<const __nv_bfloat16*>(bias);
-    p.ldd = ldd;
-    p.ldc = ldc;
-    p.M = int(M);
-    p.N = int(N);
-    p.K = int(K);
-    p.alpha = alpha;
-    p.beta = C ? beta : 0.f;
-    p.d_is_f32 = d_is_f32;
-    p.tma_store = tma_store ? 1 : 0;
-    p.num_m = cta_pair ? int((M + 2 * BM - 1) / (2 * BM)) : int((M + BM - 1) / BM);  // pair mode: 256-row super tiles
-    p.num_n = int((N + BN - 1) / BN);
-    p.num_kb = int((K + BK - 1) / BK);
+    int rc = dolo_make_tmap(&maps.a[q], g.A, 2, 2, dims, strides, box, DOLO_SW_128);
+    if (rc) return rc;
+    if (!b_mn_major) {
+        dims[0] = uint64_t(K); dims[1] = uint64_t(ga.mode == 1 ? ga.b_total_outer : N); strides[1] = uint64_t(g.ldb) * 2;
+        box[0] = BK; box[1] = cta_pair ? BN / 2 : BN;  // pair mode: each CTA stages half of the B tile
+    } else {
+        dims[0] = uint64_t(N); dims[1] = uint64_t(ga.mode == 1 ? ga.b_total_outer : K); strides[1] = uint64_t(g.ldb) * 2;
+        box[0] = 64; box[1] = BK;
+    }
+    rc = dolo_make_tmap(&maps.b[q], g.B, 2, 2, dims, strides, box, DOLO_SW_128);
+    if (rc) return rc;
+    if (epi == EPI_BF16_TMA) {
+        dims[0] = uint64_t(N); dims[1] = uint64_t(M); strides[1] = uint64_t(g.ldd) * 2;
+        box[0] = 64; box[1] = BM;
+        rc = dolo_make_tmap(&maps.d[q], g.D, 2, 2, dims, strides, box, DOLO_SW_128);
+        if (rc) return rc;
+    } else if (epi == EPI_F32_TMA_STORE || epi == EPI_F32_TMA_ADD) {
+        // fp32 [groups, M, N]: one box = 32 columns (128 B) x 32 rows, the slab of one epilogue warp
+        const int64_t groups = ga.mode == 2 ? ga.num_groups : 1;
+        dims[0] = uint64_t(N); dims[1] = uint64_t(M); dims[2] = uint64_t(groups);
+        strides[1] = uint64_t(g.ldd) * 4;
+        strides[2] = uint64_t(ga.mode == 2 ? ga.d_group_stride : M * g.ldd) * 4;
+        box[0] = 32; box[1] = 32; box[2] = 1;
+        rc = dolo_make_tmap(&maps.d[q], g.D, 4, 3, dims, strides, box, DOLO_SW_128);
+        if (rc) return rc;
+    } else {
+        maps.d[q] = maps.a[q];  // unused
+    }
+    Problem& pr = p.pr[q];
+    pr.D = g.D;
+    pr.C = g.C;
+    pr.bias = static_cast<const __nv_bfloat16*>(g.bias);
+    pr.ldd = g.ldd;
+    pr.ldc = g.ldc;
+    pr.M = int(M);
+    pr.N = int(N);
+    pr.alpha = g.alpha;
+    pr.beta = g.C ? g.beta : 0.f;
+    pr.epi = epi;
+    pr.num_m = cta_pair ? int((M + 2 * BM - 1) / (2 * BM)) : int((M + BM - 1) / BM);  // pair mode: 256-row super tiles
+    pr.num_n = int((N + BN - 1) / BN);
+    pr.num_kb = int((K + BK - 1) / BK);
     {
         // A panel of group_m x 128 rows x K bf16 should fit comfortably in L2 next to the streaming B tiles
         const int64_t panel_bytes = int64_t(cta_pair ? 2 * BM : BM) * K * 2;
         int64_t gm = (24ll << 20) / (panel_bytes > 0 ? panel_bytes : 1);
         if (gm < 4) gm = 4;
         if (gm > 64) gm = 64;
-        p.group_m = int(gm);
+        pr.group_m = int(gm);
     }
+    return DOLO_OK;
+}
+
+template <typename... Ts>
+static int dispatch_layout(int a_mn_major, int b_mn_major, Ts&&... args) {
+    if (!a_mn_major && !b_mn_major) return launch_gemm<false, false>(args...);
+    if (!a_mn_major && b_mn_major) return launch_gemm<false, true>(args...);
+    if (a_mn_major && !b_mn_major) return launch_gemm<true, false>(args...);
+    return launch_gemm<true, true>(args...);
+}
+
+// fp32 outputs go through the TMA epilogue when they are a plain overwrite (no C) or an in-place accumulation
+// (C == D, beta == 1) without bias: exactly the two forms a weight gradient takes
+static int pick_epilogue(int d_is_f32, const void* C, const void* D, float beta, const void* bias, bool tma_store,
+                         int group_mode) {
+    if (!d_is_f32) return tma_store ? EPI_BF16_TMA : EPI_DIRECT;
+    if (bias != nullptr || group_mode == 3) return EPI_DIRECT;
+    if (C == nullptr) return EPI_F32_TMA_STORE;
+    if (C == D && beta == 1.f) return EPI_F32_TMA_ADD;
+    return EPI_DIRECT;
+}
+
+static int gemm_impl(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* D,
+                     int64_t ldd, int d_is_f32, const void* C, int64_t ldc, float alpha, float beta, const void* bias,
+                     int64_t M, int64_t N, int64_t K, int flags, void* stream, const GroupArgs& ga) {
+    DOLO_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative dimension");
+    if (M == 0 || N == 0) return DOLO_OK;
+    const bool tma_store = (flags & DOLO_GEMM_FLAG_TMA_STORE) != 0;
+    DOLO_REQUIRE(!tma_store || (!d_is_f32 && C == nullptr), "gemm: TMA-store epilogue needs bf16 D and no C");
+    // CTA-pair (cta_group::2) kernel: dense mode only, at least one full 256-row super tile
+    const bool cta_pair = ga.mode == 0 && M >= 2 * BM &&
+                          ((flags & DOLO_GEMM_FLAG_CTA_PAIR) != 0 || dolo_option_gemm_cta_pair() != 0) &&
+                          (flags & DOLO_GEMM_FLAG_NO_CTA_PAIR) == 0;
+    int epi = pick_epilogue(d_is_f32, C, D, beta, bias, tma_store, ga.mode);
+    if ((flags & DOLO_GEMM_FLAG_DIRECT_EPILOGUE) != 0 && d_is_f32) epi = EPI_DIRECT;
+    GemmMaps maps;
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    GemmProblemArgs g{A, lda, B, ldb, D, ldd, C, ldc, bias, alpha, beta, M, N, K};
+    int rc = setup_problem(maps, p, 0, g, a_mn_major, b_mn_major, d_is_f32, epi, cta_pair, ga);
+    if (rc) return rc;
+    p.n_prob = 1;
+    p.pr[0].tile_start = 0;
+    p.num_tiles = p.pr[0].num_m * p.pr[0].num_n * (ga.mode >= 2 ? ga.num_groups : 1);
+    p.d_is_f32 = d_is_f32;
     p.grouped = ga.mode;
     p.m_tile_group = ga.m_tile_group;
     p.b_group_rows = int(ga.b_group_rows);
     p.group_k_offsets = ga.group_k_offsets;
     p.num_groups = ga.num_groups;
     p.d_group_stride = ga.d_group_stride;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (!a_mn_major && !b_mn_major) return launch_gemm<false, false>(ta, tb, td, p, st, cta_pair);
-    if (!a_mn_major && b_mn_major) return launch_gemm<false, true>(ta, tb, td, p, st, cta_pair);
-    if (a_mn_major && !b_mn_major) return launch_gemm<true, false>(ta, tb, td, p, st, cta_pair);
-    return launch_gemm<true, true>(ta, tb, td, p, st, cta_pair);
+    return dispatch_layout(a_mn_major, b_mn_major, maps, p, static_cast<cudaStream_t>(stream), cta_pair);
+}
+
+// The weight gradients of one transformer block in ONE persistent launch (autograd of linear.py:5-25 for c_attn, attention
+// c_proj, c_fc and mlp c_proj): dW_i[M_i, N_i] (+)= alpha_i * dY_i^T X_i with dY_i [K, M_i], X_i [K, N_i] row-major
+// activations (both operands MN-major).  Launched one by one these GEMMs lose 10-30 % to wave quantisation (c_attn: 300
+// pair tiles on 74 CTA pairs = 4.05 waves; attention c_proj: 1.35 waves); together they are 1600 tiles = 21.6 waves.
+extern "C" int dolomite_b200_gemm_bf16_wgrad_multi(int n_problems, const void* const* dY, const int64_t* ld_dy,
+                                                   const void* const* X, const int64_t* ld_x, float* const* dW,
+                                                   const int64_t* ld_dw, const int64_t* M, const int64_t* N, int64_t K,
+                                                   const float* alpha, const int* accumulate, void* stream) {
+    DOLO_REQUIRE(n_problems >= 1 && n_problems <= MAXP, "wgrad_multi: between 1 and %d problems per launch", MAXP);
+    GemmMaps maps;
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    bool pair = dolo_option_gemm_cta_pair() != 0;
+    for (int q = 0; q < n_problems; ++q) pair = pair && M[q] >= 2 * BM;
+    int tiles = 0;
+    for (int q = 0; q < n_problems; ++q) {
+        DOLO_REQUIRE(M[q] > 0 && N[q] > 0, "wgrad_multi: empty problem %d", q);
+        GemmProblemArgs g{dY[q], ld_dy[q], X[q], ld_x[q], dW[q], ld_dw[q], accumulate[q] ? dW[q] : nullptr, ld_dw[q], nullptr,
+                          alpha[q], 1.f, M[q], N[q], K};
+        int rc = setup_problem(maps, p, q, g, 1, 1, 1, accumulate[q] ? EPI_F32_TMA_ADD : EPI_F32_TMA_STORE, pair, GroupArgs());
+        if (rc) return rc;
+        p.pr[q].tile_start = tiles;
+        tiles += p.pr[q].num_m * p.pr[q].num_n;
+    }
+    p.n_prob = n_problems;
+    p.num_tiles = tiles;
+    p.d_is_f32 = 1;
+    p.grouped = 0;
+    p.num_groups = 1;
+    return launch_gemm<true, true>(maps, p, static_cast<cudaStream_t>(stream), pair);
 }
 
 extern "C" int dolomite_b200_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,

@@ -250,6 +250,8 @@ class DolomiteEngine:
         self.requires_gradient_sync = True
         self.checkpoint_every: int | None = None  # block activation checkpointing: re-run blocks 0, k, 2k, ... in backward
         self.head_chunk_bytes = 1 << 30  # bf16 logits of one LM-head chunk (forward(fuse_head_loss=True))
+        self.batch_block_wgrads = True  # the four weight gradients of a dense block in one persistent launch
+        self._deferred_wgrads: list | None = None  # list while a block's backward collects its weight gradients
         self._fresh_grads: set[str] = set()  # weights whose gradient buffer will be overwritten by the next wgrad GEMM
         if cfg.attention_multiplier is not None:
             self.softmax_scale = float(cfg.attention_multiplier)
@@ -517,14 +519,26 @@ class DolomiteEngine:
         w = unit.views[wname]
         gw = unit.gviews[wname]
         dx = K.gemm(dy, w, b_mn=True, alpha=alpha, out=dx_out) if need_dx else None
-        if wname in self._fresh_grads:  # first gradient since zero_grad(): overwrite, the buffer was not cleared
-            self._fresh_grads.discard(wname)
+        fresh = wname in self._fresh_grads  # first gradient since zero_grad(): overwrite, the buffer was not cleared
+        self._fresh_grads.discard(wname)
+        if self._deferred_wgrads is not None:
+            # weight gradients of a block are launched together at the end of the block's backward (one persistent grid
+            # over all their tiles instead of four launches with a partly filled last wave each)
+            self._deferred_wgrads.append((dy, x, gw, alpha, not fresh))
+            if len(self._deferred_wgrads) == 4:
+                self._flush_wgrads()
+        elif fresh:
             K.gemm(dy, x, a_mn=True, b_mn=True, out=gw, alpha=alpha)
         else:
             K.gemm(dy, x, a_mn=True, b_mn=True, out=gw, c=gw, alpha=alpha, beta=1.0)
         if bname is not None and bname in unit.gviews:
             K.colsum_accum(dy, unit.gviews[bname], alpha)
         return dx
+
+    def _flush_wgrads(self) -> None:
+        if self._deferred_wgrads:
+            K.gemm_wgrad_multi(self._deferred_wgrads)
+            self._deferred_wgrads.clear()
 
     def backward(self, dlogits=None, grad_scale_dev=None) -> None:
         """Backward of the last forward.  `dlogits` overrides the CE gradient (logits-mode autograd)."""
@@ -568,6 +582,8 @@ class DolomiteEngine:
                 d_ln2 = moe.backward(self, u, p, ln2, dh, m_res, moe_saved)
             else:
                 x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, fc, act = layer
+                if self.batch_block_wgrads:
+                    self._deferred_wgrads = []
                 d_act = self._linear_bwd(u, p + "mlp.c_proj.weight", p + "mlp.c_proj.bias", act, dh, alpha=m_res)
                 # the c_fc bias gradient (column sums of d_fc) is accumulated by the SwiGLU backward while it writes d_fc
                 act_bwd = K.swiglu_bwd if self.is_glu else K.gelu_bwd
@@ -588,6 +604,9 @@ class DolomiteEngine:
             del dqkv
             dh = self._norm_bwd(d_ln1, x_in, u, p + "ln_1.", rstd1, dx_add=dh_mid)
             del d_ln1, dh_mid
+            if self._deferred_wgrads is not None:
+                self._flush_wgrads()
+                self._deferred_wgrads = None
             s["layers"][i] = None  # free this layer's activations
             if comm is not None:
                 comm.post_backward_unit(i + 1)

@@ -263,6 +263,7 @@ def accum_bf16_into_f32(src, dst, scale=1.0):
 # ------------------------------------------------------------------------------------------------
 GEMM_TMA_STORE = 1
 GEMM_SPLITK_ACCUMULATE = 2
+GEMM_DIRECT_EPILOGUE = 16  # fp32 D through per-thread vector accesses instead of TMA tile store / reduce-add (A/B tests)
 # Split-K + fp32-atomic accumulation of weight gradients was measured SLOWER than read-modify-write on B200
 # (profiles/r01_probe_wgrad_splitk.json: 20480x2560x8192 2.64 ms vs 0.65 ms -- L2 atomic throughput), so it is off;
 # the entry point stays for shapes with very few output tiles.
@@ -314,6 +315,34 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=_BF16, c=None, alp
         e1.record()
         gemm_timer.append((2.0 * M * N * K, e0, e1))
     return out
+
+
+def gemm_wgrad_multi(problems: list[tuple], n_rows: int | None = None) -> None:
+    """problems: up to 4 tuples (dy [K, M] bf16, x [K, N] bf16, dw [M, N] fp32, alpha, accumulate) -> ONE persistent launch
+    computing dw (+)= alpha * dy^T x for all of them (the weight gradients of a transformer block; 21.6 waves of tiles
+    instead of four launches that each end in a partly filled wave)."""
+    import ctypes
+
+    n = len(problems)
+    assert 1 <= n <= 4
+    K = problems[0][0].shape[0] if n_rows is None else n_rows
+    P, L, F, I = ctypes.c_void_p * n, ctypes.c_int64 * n, ctypes.c_float * n, ctypes.c_int * n
+    for dy, x, dw, _, _ in problems:
+        _req(dy, _BF16, "dy"), _req(x, _BF16, "x"), _req(dw, torch.float32, "dw")
+        assert dy.shape[0] == K and x.shape[0] == K and dy.stride(1) == 1 and x.stride(1) == 1 and dw.stride(1) == 1
+        assert dw.shape == (dy.shape[1], x.shape[1])
+    if gemm_timer is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.call(
+        "dolomite_b200_gemm_bf16_wgrad_multi", n, P(*[q[0].data_ptr() for q in problems]), L(*[q[0].stride(0) for q in problems]),
+        P(*[q[1].data_ptr() for q in problems]), L(*[q[1].stride(0) for q in problems]), P(*[q[2].data_ptr() for q in problems]),
+        L(*[q[2].stride(0) for q in problems]), L(*[q[0].shape[1] for q in problems]), L(*[q[1].shape[1] for q in problems]),
+        K, F(*[float(q[3]) for q in problems]), I(*[int(bool(q[4])) for q in problems]), _stream(),
+    )
+    if gemm_timer is not None:
+        e1.record()
+        gemm_timer.append((sum(2.0 * K * q[0].shape[1] * q[1].shape[1] for q in problems), e0, e1))
 
 
 # ------------------------------------------------------------------------------------------------

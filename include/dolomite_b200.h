@@ -37,12 +37,8 @@ const char* dolomite_b200_last_error(void);
 int dolomite_b200_abi_version(void);
 int dolomite_b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* process-wide tuning knobs:
- *   "attn_bwd_version" 1 (serial kernel, every head_dim) | 2 | 3 | 4 (pipelined, head_dim <= 80; 1 / 2 / 4 softmax groups)
- *   "attn_fwd_version" 1 (one query tile per CTA) | 2 (two query tiles per CTA, ping-pong softmax groups)
  *   "gemm_cta_pair"    0 | 1 (dense GEMMs on 2-CTA clusters with tcgen05.mma.cta_group::2)
- *   "gemm_sm_margin"   SMs the persistent GEMM grids leave free for concurrent communication kernels
- *   "attn_bwd_experiment" diagnostic bit mask for timing what-ifs (bit 0: drop the dQ reductions); results are WRONG
- *                      when non-zero, production callers never set it */
+ *   "gemm_sm_margin"   SMs the persistent GEMM grids leave free for concurrent communication kernels */
 int dolomite_b200_set_option(const char* key, int value);
 
 /* ------------------------------------------------------------------------------------------------
@@ -185,9 +181,19 @@ int dolomite_b200_accum_bf16_into_f32(const void* src, float* dst, float scale, 
  * default follows the "gemm_cta_pair" option. */
 #define DOLO_GEMM_FLAG_CTA_PAIR 4
 #define DOLO_GEMM_FLAG_NO_CTA_PAIR 8
+/* bit4: fp32 D through per-thread vector accesses instead of the TMA tile store / reduce-add epilogue (A/B tests) */
+#define DOLO_GEMM_FLAG_DIRECT_EPILOGUE 16
 int dolomite_b200_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                             void* D, int64_t ldd, int d_is_f32, const void* C, int64_t ldc, float alpha, float beta,
                             const void* bias, int64_t M, int64_t N, int64_t K, int flags, void* stream);
+
+/* Up to 4 weight gradients in ONE persistent launch (the four nn.Linear of a GPTDolomiteBlock, autograd of linear.py:5-25):
+ *   dW_i[M_i, N_i] = alpha_i * dY_i^T X_i  (accumulate[i] == 0: overwrite)   or   dW_i += alpha_i * dY_i^T X_i  (!= 0)
+ * dY_i bf16 [K, M_i] (ld_dy), X_i bf16 [K, N_i] (ld_x), dW_i fp32 [M_i, N_i] (ld_dw); K = token rows, common to all. */
+int dolomite_b200_gemm_bf16_wgrad_multi(int n_problems, const void* const* dY, const int64_t* ld_dy, const void* const* X,
+                                        const int64_t* ld_x, float* const* dW, const int64_t* ld_dw, const int64_t* M,
+                                        const int64_t* N, int64_t K, const float* alpha, const int* accumulate,
+                                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Grouped GEMM for MoE experts (replaces scattermoe `parallel_linear`, moe_dolomite/moe/scatter.py:38-49, and the

@@ -203,6 +203,47 @@ def test_full_size_gemm_spot_checks():
     assert torch.allclose(once[:8, :8].double().cpu(), exact, atol=5e-2, rtol=1e-3)
 
 
+def test_block_weight_gradients_in_one_launch_and_fp32_tile_epilogues():
+    """gemm_wgrad_multi (the four weight gradients of a block in one persistent launch, TMA store / reduce-add epilogue)
+    == four separate GEMMs == fp64 products on sampled entries; overwrite and accumulate forms; ragged M / N edges.
+    Also: the fp32 TMA epilogue and the per-thread epilogue of the single-problem GEMM agree bit for bit."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    T = 2048 + 64  # not a multiple of the 64-row contraction block
+    shapes = [(2560, 1024), (520, 2560), (264, 264), (7680, 328)]  # (M = out features, N = in features)
+    probs, refs = [], []
+    for i, (M, N) in enumerate(shapes):
+        dy = bf(torch.randn(T, M, device="cuda", generator=g))
+        x = bf(torch.randn(T, N, device="cuda", generator=g))
+        acc = i % 2 == 1
+        dw = torch.randn(M, N, device="cuda", generator=g) if acc else torch.full((M, N), float("nan"), device="cuda")
+        ref = (dw.clone() if acc else torch.zeros(M, N, device="cuda"))
+        alpha = 1.0 if i != 2 else 0.5
+        probs.append((dy, x, dw, alpha, acc))
+        refs.append((ref, dy, x, alpha))
+    K().gemm_wgrad_multi(probs)
+    torch.cuda.synchronize()
+    for (dy, x, dw, alpha, acc), (ref, _, _, _) in zip(probs, refs):
+        sep = ref.clone()
+        if acc:
+            K().gemm(dy, x, a_mn=True, b_mn=True, out=sep, c=sep, alpha=alpha, beta=1.0, flags=K().GEMM_DIRECT_EPILOGUE)
+        else:
+            K().gemm(dy, x, a_mn=True, b_mn=True, out=sep, alpha=alpha, flags=K().GEMM_DIRECT_EPILOGUE)
+        assert torch.isfinite(dw).all()
+        # same tiles, same fp32 accumulation order; only the final add differs (L2 reduce-add vs register add): <= 1 ulp
+        assert torch.allclose(dw, sep, rtol=1e-6, atol=1e-5), (dw - sep).abs().max()
+        rows = torch.randint(0, dw.shape[0], (12,), generator=torch.Generator().manual_seed(3)).cuda()
+        cols = torch.randint(0, dw.shape[1], (12,), generator=torch.Generator().manual_seed(4)).cuda()
+        exact = alpha * (dy[:, rows].double().t() @ x[:, cols].double()) + ref[rows][:, cols].double()
+        assert torch.allclose(dw[rows][:, cols].double(), exact, atol=2e-2, rtol=1e-3)
+    # single-problem GEMM: TMA tile epilogue (default) vs per-thread epilogue
+    dy, x = probs[0][0], probs[0][1]
+    a = torch.empty(2560, 1024, device="cuda")
+    b = torch.empty(2560, 1024, device="cuda")
+    K().gemm(dy, x, a_mn=True, b_mn=True, out=a)
+    K().gemm(dy, x, a_mn=True, b_mn=True, out=b, flags=K().GEMM_DIRECT_EPILOGUE)
+    assert torch.equal(a, b)
+
+
 def test_full_size_attention_properties():
     S, B, nh, hd = 4096, 2, 32, 80
     T = S * B
