@@ -64,7 +64,8 @@ SIGNATURES: dict[str, tuple] = {
     "dolomite_b200_gemm_bf16_grouped_m": (_I, [_P, _L, _P, _L, _I, _P, _L, _F, _L, _L, _L, _P, _I, _I, _P]),
     "dolomite_b200_gemm_bf16_grouped_k": (_I, [_P, _L, _P, _L, _P, _L, _F, _F, _L, _L, _L, _P, _I, _P]),
     "dolomite_b200_moe_max_rows": (_L, [_L, _I, _I]),
-    "dolomite_b200_moe_route": (_I, [_P, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "dolomite_b200_moe_route": (_I, [_P, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "dolomite_b200_gemm_bf16_grouped_m_gather": (_I, [_P, _L, _L, _P, _P, _L, _P, _L, _F, _L, _L, _L, _P, _I, _I, _P]),
     "dolomite_b200_moe_gather": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _P]),
     "dolomite_b200_moe_combine": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _F, _P]),
     "dolomite_b200_moe_combine_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P]),

@@ -151,6 +151,17 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// TMA gather4 (sm_100): four rows of a rank-2 tensor, chosen by four row coordinates, land as four consecutive rows of the
+// (swizzled) shared-memory tile.  The tensor map's box is {columns, 1 row}.  The ScatterMoE gather-on-load of the grouped
+// expert GEMM (moe_dolomite/moe/scatter.py:38-49 `parallel_linear(grouped_in=False)`) is 32 of these per 128-row A tile.
+__device__ __forceinline__ void tma_gather4_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int r0, int r1,
+                                               int r2, int r3) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(r0), "r"(r1), "r"(r2),
+        "r"(r3)
+        : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(m)),
@@ -260,6 +271,16 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorM
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(c1)
+        : "memory");
+}
+// gather4 issued by either CTA of a pair; bytes are credited to the leader CTA's mbarrier (see tma_load_2d_2cta)
+__device__ __forceinline__ void tma_gather4_2d_2cta(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int r0,
+                                                    int r1, int r2, int r3) {
+    const uint32_t bar_leader = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.cta_group::2 [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(r0), "r"(r1), "r"(r2),
+        "r"(r3)
         : "memory");
 }
 __device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,

@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(kThreads)
 // ------------------------------------------------------------------------------------------
 // Cross entropy: one block (or cluster) per row, row held in registers between the reduction and the gradient write.
 // ------------------------------------------------------------------------------------------
-constexpr int kCeThreads = 512;
+constexpr int kCeThreads = 256;  // two CTAs per SM: one loads / stores its row while the other is in its reduction phases
 
 __global__ void ce_count_kernel(const int64_t* __restrict__ labels, int64_t T, int64_t ignore_index,
                                 float* __restrict__ scratch) {
@@ -614,7 +614,7 @@ __device__ __forceinline__ void st_cluster_f32(float* local_smem, uint32_t rank,
 }
 
 template <int NV, int SPLIT>
-__global__ void __launch_bounds__(kCeThreads, 1)
+__global__ void __launch_bounds__(kCeThreads, 2)
     ce_rows_kernel(const uint4* logits, int64_t ld8, const int64_t* __restrict__ labels, uint4* dlogits,
                    float* __restrict__ loss_tok, const float* __restrict__ scratch, int64_t T, int64_t V,
                    int64_t ignore_index, float logit_scale, float grad_scale) {
@@ -648,6 +648,8 @@ __global__ void __launch_bounds__(kCeThreads, 1)
             const int64_t i = v_lo + k * kCeThreads + threadIdx.x;
             if (i < v_hi) v[k] = lr[i];
         }
+        // everything in log2 units: x2 = x * (logit_scale * log2 e), so that exp() is ONE ex2.approx after one FFMA
+        const float scale2 = logit_scale * 1.4426950408889634f;
         float m = -INFINITY;
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
@@ -655,7 +657,7 @@ __global__ void __launch_bounds__(kCeThreads, 1)
                 float f[8];
                 unpack8(v[k], f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) m = fmaxf(m, f[j] * logit_scale);
+                for (int j = 0; j < 8; ++j) m = fmaxf(m, f[j] * scale2);
             }
         }
         m = ce_block_reduce(m, red, true);
@@ -672,7 +674,7 @@ __global__ void __launch_bounds__(kCeThreads, 1)
                 float f[8];
                 unpack8(v[k], f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) s += __expf(f[j] * logit_scale - m);
+                for (int j = 0; j < 8; ++j) s += fast_exp2(fmaf(f[j], scale2, -m));
             }
         }
         s = ce_block_reduce(s, red, false);
@@ -683,7 +685,8 @@ __global__ void __launch_bounds__(kCeThreads, 1)
 #pragma unroll
             for (int c = 0; c < SPLIT; ++c) s += xch[1][c];
         }
-        const float lse = m + __logf(s);
+        const float lse2 = m + __log2f(s);  // log2 units
+        const float gmul = gs * logit_scale;
         const int64_t lvec = label >> 3;
         const int lsub = int(label & 7);
 #pragma unroll
@@ -692,12 +695,12 @@ __global__ void __launch_bounds__(kCeThreads, 1)
             if (i < v_hi) {
                 float f[8];
                 unpack8(v[k], f);
-                if (i == lvec) loss_tok[row] = lse - f[lsub] * logit_scale;
+                if (i == lvec) loss_tok[row] = (lse2 - f[lsub] * scale2) * 0.6931471805599453f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = __expf(f[j] * logit_scale - lse);
+                for (int j = 0; j < 8; ++j) f[j] = fast_exp2(fmaf(f[j], scale2, -lse2));
                 if (i == lvec) f[lsub] -= 1.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] *= gs * logit_scale;
+                for (int j = 0; j < 8; ++j) f[j] *= gmul;
                 dr[i] = pack8(f);
             }
         }
@@ -711,7 +714,7 @@ int launch_ce_rows(const void* logits, int64_t ldl, const int64_t* labels, void*
                    const float* scratch, int64_t T, int64_t V, int64_t ignore_index, float logit_scale, float grad_scale,
                    cudaStream_t st) {
     auto kern = ce_rows_kernel<NV, SPLIT>;
-    int64_t clusters = int64_t(dolo_num_sms()) / SPLIT;  // one 512-thread CTA per SM (the row lives in its registers)
+    int64_t clusters = 2 * int64_t(dolo_num_sms()) / SPLIT;  // two 256-thread CTAs per SM (a row lives in a CTA's registers)
     if (clusters > T) clusters = T;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(clusters * SPLIT));
@@ -1182,7 +1185,7 @@ extern "C" int dolomite_b200_cross_entropy_rows(const void* logits, int64_t ldl,
     DOLO_REQUIRE(aligned16(logits) && aligned16(dlogits), "cross_entropy: pointers must be 16-byte aligned");
     if (T == 0) return DOLO_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // vectors per thread with 512 threads and the whole row in ONE CTA; wider rows are split over a 2- or 4-CTA cluster
+    // vectors per thread with 256 threads and the whole row in ONE CTA; wider rows are split over a 2- or 4-CTA cluster
     const int64_t V8 = V / 8;
     const int64_t nv1 = (V8 + kCeThreads - 1) / kCeThreads;
 #define DOLO_CE(NV, SPLIT)                                                                                          \
@@ -1190,13 +1193,13 @@ extern "C" int dolomite_b200_cross_entropy_rows(const void* logits, int64_t ldl,
                                      logit_scale, grad_scale, st)
     if (nv1 <= 4) DOLO_CE(4, 1);
     if (nv1 <= 8) DOLO_CE(8, 1);
-    if (nv1 <= 12) DOLO_CE(12, 1);
     if (nv1 <= 16) DOLO_CE(16, 1);
-    if (nv1 <= 24) DOLO_CE(12, 2);
+    if (nv1 <= 24) DOLO_CE(12, 2);  // (24 vectors per thread spill under the 128-register cap of two CTAs per SM)
     if (nv1 <= 32) DOLO_CE(16, 2);
+    if (nv1 <= 48) DOLO_CE(12, 4);
     if (nv1 <= 64) DOLO_CE(16, 4);
 #undef DOLO_CE
-    return dolo_set_error("cross_entropy: vocabulary %lld exceeds the 262144 columns one 4-CTA cluster holds", (long long)V);
+    return dolo_set_error("cross_entropy: vocabulary %lld exceeds the 131072 columns one 4-CTA cluster holds", (long long)V);
 }
 
 extern "C" int dolomite_b200_cross_entropy_mean(const float* loss_per_token, int64_t T, const float* scratch,

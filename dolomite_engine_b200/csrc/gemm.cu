@@ -68,6 +68,8 @@ struct GemmParams {
     //       [group_k_offsets[g], group_k_offsets[g+1]) and D/C are offset by g * d_group_stride (expert wgrad)
     int grouped;
     const int* m_tile_group;
+    int m_tile_shift;        // CTA-pair mode: a 256-row super tile covers entries 2m, 2m+1 of the 128-row tile table
+    const int* a_row_index;  // gather-on-load: source row of A for every (grouped) row of the problem, or NULL
     int b_group_rows;
     const int* group_k_offsets;
     int num_groups;
@@ -124,7 +126,7 @@ __device__ __forceinline__ TileInfo tile_info(int t, const GemmParams& p) {
     } else {
         tile_coords(t, pr.num_m, pr.num_n, pr.group_m, ti.m_blk, ti.n_blk);
         if (p.grouped == 1) {
-            ti.grp = p.m_tile_group[ti.m_blk];
+            ti.grp = p.m_tile_group[ti.m_blk << p.m_tile_shift];
             ti.valid = ti.grp >= 0;
         }
     }
@@ -190,7 +192,57 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (elect_one()) {  // uniform single-thread region: ptxas keeps descriptors in uniform registers
+        if (!A_MN && p.a_row_index != nullptr) {
+            // Gather-on-load (grouped expert GEMM reading the UNGROUPED activations): the whole warp takes part, lane l
+            // owns rows 4l .. 4l+3 of the 128-row A tile and issues one gather4 per pipeline stage for them; lane 0 also
+            // arms the barrier and loads B.
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = worker; t < num_tiles; t += num_workers) {
+                const TileInfo ti = tile_info(t, p);
+                if (!ti.valid) continue;
+                const CUtensorMap* tmap_a = &maps.a[ti.q];
+                const CUtensorMap* tmap_b = &maps.b[ti.q];
+                const int m_blk = CTA2 ? ti.m_blk * 2 + cta_rank : ti.m_blk, n_blk = ti.n_blk;
+                const int b_outer = (p.grouped == 1) ? ti.grp * p.b_group_rows : 0;
+                const int4 src = *reinterpret_cast<const int4*>(p.a_row_index + int64_t(m_blk) * BM + lane * 4);
+                for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                    uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+                    uint8_t* sb = smem_b + stage * B_BYTES;
+                    if (lane == 0) {
+                        if constexpr (CTA2) {
+                            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STG_BYTES);
+                            const int n_row = n_blk * BN + cta_rank * (BN / 2);
+                            if (!B_MN) {
+                                tma_load_2d_2cta(sb, tmap_b, &full_bar[stage], kb * BK, b_outer + n_row);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < BN / 128; ++i)
+                                    tma_load_2d_2cta(sb + i * (BK * 128), tmap_b, &full_bar[stage], n_row + i * 64,
+                                                     b_outer + kb * BK);
+                            }
+                        } else {
+                            mbar_expect_tx(&full_bar[stage], STG_BYTES);
+                            if (!B_MN) {
+                                tma_load_2d(sb, tmap_b, &full_bar[stage], kb * BK, b_outer + n_blk * BN);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < BN / 64; ++i)
+                                    tma_load_2d(sb + i * (BK * 128), tmap_b, &full_bar[stage], n_blk * BN + i * 64,
+                                                b_outer + kb * BK);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if constexpr (CTA2)
+                        tma_gather4_2d_2cta(sa + lane * 512, tmap_a, &full_bar[stage], kb * BK, src.x, src.y, src.z, src.w);
+                    else
+                        tma_gather4_2d(sa + lane * 512, tmap_a, &full_bar[stage], kb * BK, src.x, src.y, src.z, src.w);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (elect_one()) {  // uniform single-thread region: ptxas keeps descriptors in uniform registers
             int stage = 0;
             uint32_t phase = 0;
             for (int t = worker; t < num_tiles; t += num_workers) {
@@ -216,11 +268,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                                 tma_load_2d_2cta(sa + i * (BK * 128), tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
                         }
                         if (!B_MN) {
-                            tma_load_2d_2cta(sb, tmap_b, &full_bar[stage], kb * BK, n_row);
+                            tma_load_2d_2cta(sb, tmap_b, &full_bar[stage], kb * BK, b_outer + n_row);
                         } else {
 #pragma unroll
                             for (int i = 0; i < BN / 128; ++i)
-                                tma_load_2d_2cta(sb + i * (BK * 128), tmap_b, &full_bar[stage], n_row + i * 64, kb * BK);
+                                tma_load_2d_2cta(sb + i * (BK * 128), tmap_b, &full_bar[stage], n_row + i * 64,
+                                                 b_outer + kb * BK);
                         }
                     } else {
                         mbar_expect_tx(&full_bar[stage], STG_BYTES);
@@ -530,6 +583,8 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t st, bool
 
 struct GroupArgs {
     int mode = 0;
+    const int* a_row_index = nullptr;  // mode 1 only: gather the rows of A on load (A is the ungrouped matrix of a_rows rows)
+    int64_t a_rows = 0;
     const int* m_tile_group = nullptr;
     int64_t b_group_rows = 0;
     const int* group_k_offsets = nullptr;
@@ -564,7 +619,12 @@ static int setup_problem(GemmMaps& maps, GemmParams& p, int q, const GemmProblem
     // K-major: dims {K, rows}, box {64, tile rows}.  MN-major: dims {rows, K}, box {64, 64}.
     uint64_t dims[3], strides[3];
     uint32_t box[3];
-    if (!a_mn_major) {
+    if (ga.a_row_index != nullptr) {
+        // gather4: box = one row of 64 columns; the instruction names four rows of the UNGROUPED matrix
+        DOLO_REQUIRE(!a_mn_major, "gemm: gather-on-load needs a K-major A");
+        dims[0] = uint64_t(K); dims[1] = uint64_t(ga.a_rows); strides[0] = 2; strides[1] = uint64_t(g.lda) * 2;
+        box[0] = BK; box[1] = 1;
+    } else if (!a_mn_major) {
         dims[0] = uint64_t(K); dims[1] = uint64_t(M); strides[0] = 2; strides[1] = uint64_t(g.lda) * 2;
         box[0] = BK; box[1] = BM;
     } else {
@@ -650,8 +710,9 @@ static int gemm_impl(const void* A, int64_t lda, int a_mn_major, const void* B, 
     if (M == 0 || N == 0) return DOLO_OK;
     const bool tma_store = (flags & DOLO_GEMM_FLAG_TMA_STORE) != 0;
     DOLO_REQUIRE(!tma_store || (!d_is_f32 && C == nullptr), "gemm: TMA-store epilogue needs bf16 D and no C");
-    // CTA-pair (cta_group::2) kernel: dense mode only, at least one full 256-row super tile
-    const bool cta_pair = ga.mode == 0 && M >= 2 * BM &&
+    // CTA-pair (cta_group::2) kernel: at least one full 256-row super tile; M-grouped problems need their expert segments
+    // padded to 256 rows (both halves of a super tile then belong to the same expert); not for split-K
+    const bool cta_pair = (ga.mode == 0 || (ga.mode == 1 && M % (2 * BM) == 0) || ga.mode == 2) && M >= 2 * BM &&
                           ((flags & DOLO_GEMM_FLAG_CTA_PAIR) != 0 || dolo_option_gemm_cta_pair() != 0) &&
                           (flags & DOLO_GEMM_FLAG_NO_CTA_PAIR) == 0;
     int epi = pick_epilogue(d_is_f32, C, D, beta, bias, tma_store, ga.mode);
@@ -668,6 +729,8 @@ static int gemm_impl(const void* A, int64_t lda, int a_mn_major, const void* B, 
     p.d_is_f32 = d_is_f32;
     p.grouped = ga.mode;
     p.m_tile_group = ga.m_tile_group;
+    p.m_tile_shift = cta_pair ? 1 : 0;
+    p.a_row_index = ga.a_row_index;
     p.b_group_rows = int(ga.b_group_rows);
     p.group_k_offsets = ga.group_k_offsets;
     p.num_groups = ga.num_groups;
@@ -751,6 +814,29 @@ extern "C" int dolomite_b200_gemm_bf16_grouped_m(const void* A, int64_t lda, con
     ga.b_total_outer = ga.b_group_rows * num_groups;
     return gemm_impl(A, lda, 0, B, ldb, b_mn_major, D, ldd, 0, nullptr, 0, alpha, 0.f, nullptr, M_max, N, K, flags, stream,
                      ga);
+}
+
+// Same, with the ScatterMoE gather fused into the operand load: A is the UNGROUPED activation matrix [a_rows, K] and
+// a_row_index[r] names the source row of grouped row r (padding rows may name any valid row: their products are never read)
+extern "C" int dolomite_b200_gemm_bf16_grouped_m_gather(const void* A, int64_t lda, int64_t a_rows,
+                                                        const int32_t* a_row_index, const void* B, int64_t ldb, void* D,
+                                                        int64_t ldd, float alpha, int64_t M_max, int64_t N, int64_t K,
+                                                        const int32_t* m_tile_group, int num_groups, int flags,
+                                                        void* stream) {
+    DOLO_REQUIRE(M_max % BM == 0, "grouped gemm: M_max=%lld must be a multiple of %d (padded expert segments)",
+                 (long long)M_max, BM);
+    DOLO_REQUIRE(m_tile_group != nullptr && num_groups > 0 && a_row_index != nullptr && a_rows > 0,
+                 "grouped gemm (gather): missing group table / row index");
+    DOLO_REQUIRE((reinterpret_cast<uintptr_t>(a_row_index) & 15) == 0, "grouped gemm (gather): row index must be 16-byte aligned");
+    GroupArgs ga;
+    ga.mode = 1;
+    ga.a_row_index = a_row_index;
+    ga.a_rows = a_rows;
+    ga.m_tile_group = m_tile_group;
+    ga.num_groups = num_groups;
+    ga.b_group_rows = N;
+    ga.b_total_outer = N * num_groups;
+    return gemm_impl(A, lda, 0, B, ldb, 0, D, ldd, 0, nullptr, 0, alpha, 0.f, nullptr, M_max, N, K, flags, stream, ga);
 }
 
 extern "C" int dolomite_b200_gemm_bf16_grouped_k(const void* A, int64_t lda, const void* B, int64_t ldb, float* D,

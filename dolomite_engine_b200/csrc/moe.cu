@@ -4,7 +4,7 @@
 //
 // Device-side only, no host sync (the eager reference calls .tolist(), moe/base.py:33):
 //   route      : top-k on the raw router logits, fp32 softmax over the k selected, per-expert histogram
-//   plan       : expert segments padded to 128-row tiles -> offsets, tile->expert table, row assignment
+//   plan       : expert segments padded to 256 rows (CTA-pair super tiles) -> offsets, 128-row tile->expert table, row assignment
 //   gather     : X_g[row] = x[token(row)] (zero rows for padding) -- operand of the grouped c_fc GEMM
 //   combine    : y[t] = sum_j w[t,j] * Y_g[row(t,j)]            -- after the grouped c_proj GEMM
 //   backward   : dY_g rows / gate-weight grads, token-sum of dX_g rows, softmax-over-k backward to dense dlogits
@@ -16,7 +16,8 @@ using namespace dolo;
 
 namespace {
 
-constexpr int MOE_TILE = 128;
+constexpr int MOE_TILE = 128;  // granularity of the tile -> expert table (one entry per 128 grouped rows)
+constexpr int MOE_PAD = 256;   // expert segments are padded to 256 rows: one CTA-pair super tile of the grouped GEMM
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
@@ -90,7 +91,7 @@ __global__ void moe_plan_kernel(const int32_t* __restrict__ counts, int E, int32
         int acc = 0;
         for (int e = 0; e < E; ++e) {
             s_off[e] = acc;
-            acc += (counts[e] + MOE_TILE - 1) / MOE_TILE * MOE_TILE;
+            acc += (counts[e] + MOE_PAD - 1) / MOE_PAD * MOE_PAD;
         }
         s_off[E] = acc;
     }
@@ -114,7 +115,8 @@ __global__ void moe_plan_kernel(const int32_t* __restrict__ counts, int E, int32
 
 __global__ void moe_assign_kernel(const int32_t* __restrict__ sel_idx, int64_t n_slots,
                                   const int32_t* __restrict__ offsets_padded, int32_t* __restrict__ cursors,
-                                  int32_t* __restrict__ row_of_slot, int32_t* __restrict__ slot_of_row) {
+                                  int32_t* __restrict__ row_of_slot, int32_t* __restrict__ slot_of_row,
+                                  int32_t* __restrict__ token_of_row, int k) {
     const int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (s >= n_slots) return;
     const int e = sel_idx[s];
@@ -122,6 +124,7 @@ __global__ void moe_assign_kernel(const int32_t* __restrict__ sel_idx, int64_t n
     const int row = offsets_padded[e] + pos;
     row_of_slot[s] = row;
     slot_of_row[row] = int32_t(s);
+    token_of_row[row] = int32_t(s / k);
 }
 
 // X_g[row] = x[slot_of_row[row] / k]  (zeros for padding rows); one warp per row
@@ -245,11 +248,12 @@ inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
 
 }  // namespace
 
-extern "C" int64_t dolomite_b200_moe_max_rows(int64_t T, int E, int k) { return (T * k + int64_t(E) * (MOE_TILE - 1)) / MOE_TILE * MOE_TILE + MOE_TILE; }
+extern "C" int64_t dolomite_b200_moe_max_rows(int64_t T, int E, int k) { return (T * k + int64_t(E) * (MOE_PAD - 1)) / MOE_PAD * MOE_PAD + MOE_PAD; }
 
 extern "C" int dolomite_b200_moe_route(const void* router_logits, int64_t T, int E, int k, int32_t* sel_idx,
                                        float* sel_w, int32_t* counts, int32_t* offsets_padded, int32_t* m_tile_group,
-                                       int32_t* cursors, int32_t* row_of_slot, int32_t* slot_of_row, void* stream) {
+                                       int32_t* cursors, int32_t* row_of_slot, int32_t* slot_of_row,
+                                       int32_t* token_of_row, void* stream) {
     DOLO_REQUIRE(E > 0 && E <= 256, "moe_route: num_experts=%d must be in [1, 256]", E);
     DOLO_REQUIRE(k > 0 && k <= 8 && k <= E, "moe_route: top-k=%d must be in [1, min(8, E)]", k);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -257,6 +261,7 @@ extern "C" int dolomite_b200_moe_route(const void* router_logits, int64_t T, int
     const int max_tiles = int(max_rows / MOE_TILE);
     DOLO_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * E, st));
     DOLO_CUDA_OK(cudaMemsetAsync(slot_of_row, 0xFF, sizeof(int32_t) * max_rows, st));
+    DOLO_CUDA_OK(cudaMemsetAsync(token_of_row, 0, sizeof(int32_t) * max_rows, st));  // padding rows read token 0 (never used)
     if (T > 0) {
         const int64_t blocks = (T * 32 + 255) / 256;
         moe_route_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(router_logits), T, E, k,
@@ -268,7 +273,7 @@ extern "C" int dolomite_b200_moe_route(const void* router_logits, int64_t T, int
     if (T > 0) {
         const int64_t n = T * k;
         moe_assign_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sel_idx, n, offsets_padded, cursors, row_of_slot,
-                                                                       slot_of_row);
+                                                                       slot_of_row, token_of_row, k);
         DOLO_LAUNCH_OK("moe_assign");
     }
     return DOLO_OK;

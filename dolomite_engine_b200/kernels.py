@@ -383,7 +383,7 @@ class MoEPlan:
     """device-side routing state of one MoE layer invocation (no host sync anywhere)"""
 
     __slots__ = ("T", "E", "k", "max_rows", "sel_idx", "sel_w", "counts", "offsets", "tile_group", "cursors",
-                 "row_of_slot", "slot_of_row")
+                 "row_of_slot", "slot_of_row", "token_of_row")
 
 
 def moe_route(router_logits, k: int) -> MoEPlan:
@@ -402,9 +402,10 @@ def moe_route(router_logits, k: int) -> MoEPlan:
     p.cursors = torch.empty(E, **i32)
     p.row_of_slot = torch.empty(T * k, **i32)
     p.slot_of_row = torch.empty(p.max_rows, **i32)
+    p.token_of_row = torch.empty(p.max_rows, **i32)
     _lib.call("dolomite_b200_moe_route", router_logits.data_ptr(), T, E, k, p.sel_idx.data_ptr(), p.sel_w.data_ptr(),
               p.counts.data_ptr(), p.offsets.data_ptr(), p.tile_group.data_ptr(), p.cursors.data_ptr(),
-              p.row_of_slot.data_ptr(), p.slot_of_row.data_ptr(), _stream())
+              p.row_of_slot.data_ptr(), p.slot_of_row.data_ptr(), p.token_of_row.data_ptr(), _stream())
     return p
 
 
@@ -460,6 +461,28 @@ def gemm_grouped_m(a, w3, plan: MoEPlan, *, b_mn: bool, alpha: float = 1.0, flag
         flags = _default_gemm_flags
     _lib.call("dolomite_b200_gemm_bf16_grouped_m", a.data_ptr(), a.stride(0), w3.data_ptr(), w3.shape[2], int(b_mn),
               out.data_ptr(), N, alpha, rows, N, K, plan.tile_group.data_ptr(), E, flags, _stream())
+    return out
+
+
+def gemm_grouped_m_gather(x, w3, plan: MoEPlan, alpha: float = 1.0, flags=None):
+    """expert forward with the gather fused into the operand load (TMA gather4): x [T, K] UNGROUPED, w3 [E, N, K] ->
+    D[row] = x[token_of_row[row]] W[expert(row)]^T for every grouped row (moe/scatter.py:38-49 `parallel_linear`)"""
+    _req(x, _BF16, "x"), _req(w3, _BF16, "w3")
+    T, K = x.shape
+    E, N = w3.shape[0], w3.shape[1]
+    assert w3.shape[2] == K and w3.is_contiguous() and x.stride(1) == 1 and T == plan.T
+    out = torch.empty(plan.max_rows, N, dtype=_BF16, device=x.device)
+    if flags is None:
+        flags = _default_gemm_flags
+    if gemm_timer is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.call("dolomite_b200_gemm_bf16_grouped_m_gather", x.data_ptr(), x.stride(0), T, plan.token_of_row.data_ptr(),
+              w3.data_ptr(), w3.shape[2], out.data_ptr(), N, alpha, plan.max_rows, N, K, plan.tile_group.data_ptr(), E, flags,
+              _stream())
+    if gemm_timer is not None:
+        e1.record()
+        gemm_timer.append((2.0 * T * plan.k * N * K, e0, e1))
     return out
 
 

@@ -11,7 +11,12 @@ GEMMs exactly like `parallel_linear(grouped_out=True)` -> `parallel_linear(group
 
 from __future__ import annotations
 
+import os
+
 from . import kernels as K
+
+# DOLO_MOE_FUSED_GATHER=0 falls back to the separate gather pass in forward (A/B measurements)
+FUSED_GATHER = os.environ.get("DOLO_MOE_FUSED_GATHER", "1") != "0"
 
 
 def forward(engine, unit, p: str, x, residual, m_res: float):
@@ -22,23 +27,29 @@ def forward(engine, unit, p: str, x, residual, m_res: float):
     gate = unit.views[p + "mlp.gate.weight"]
     logits = K.gemm(x, gate, flags=0)  # [T, E] bf16 (tiny N: direct-store epilogue)
     plan = K.moe_route(logits, k)
-    xg = K.moe_gather(x, plan)
-    fc = K.gemm_grouped_m(xg, unit.views[p + "mlp.c_fc.weight"], plan, b_mn=False)
+    if FUSED_GATHER:
+        # scattermoe `parallel_linear(grouped_in=False, grouped_out=True)`: the expert GEMM reads the token rows straight
+        # out of x (TMA gather4 in its producer warp); no grouped copy of x is written in forward
+        fc = K.gemm_grouped_m_gather(x, unit.views[p + "mlp.c_fc.weight"], plan)
+    else:
+        fc = K.gemm_grouped_m(K.moe_gather(x, plan), unit.views[p + "mlp.c_fc.weight"], plan, b_mn=False)
     act = K.swiglu_fwd(fc)
     yg = K.gemm_grouped_m(act, unit.views[p + "mlp.c_proj.weight"], plan, b_mn=False)
     out = K.moe_combine(yg, plan, c=residual, alpha=m_res)
-    return out, (plan, logits, xg, fc, act, yg)
+    return out, (plan, logits, fc, act, yg)
 
 
 def backward(engine, unit, p: str, x, dh, m_res: float, saved):
     """returns d(x) (gradient wrt the MoE input, i.e. the ln_2 output); accumulates expert / gate weight grads"""
-    plan, logits, xg, fc, act, yg = saved
+    plan, logits, fc, act, yg = saved
     dyg, dw = K.moe_combine_bwd(dh, yg, plan, alpha=m_res)
     w_proj, w_fc = unit.views[p + "mlp.c_proj.weight"], unit.views[p + "mlp.c_fc.weight"]
     K.gemm_grouped_k(dyg, act, plan, unit.gviews[p + "mlp.c_proj.weight"])          # dWproj[e] += dY_e^T act_e
     d_act = K.gemm_grouped_m(dyg, w_proj, plan, b_mn=True)                            # [rows, F]
     d_fc = K.swiglu_bwd(d_act, fc)
+    xg = K.moe_gather(x, plan)  # grouped (zero-padded) copy of the block input: the contraction operand of the c_fc wgrad
     K.gemm_grouped_k(d_fc, xg, plan, unit.gviews[p + "mlp.c_fc.weight"])             # dWfc[e] += dfc_e^T x_e
+    del xg
     dxg = K.gemm_grouped_m(d_fc, w_fc, plan, b_mn=True)                               # [rows, H]
     dx = K.moe_token_sum(dxg, plan)
     # router path: softmax-over-k backward -> dense dlogits -> gate wgrad and dx contribution

@@ -198,7 +198,7 @@ int dolomite_b200_gemm_bf16_wgrad_multi(int n_problems, const void* const* dY, c
 /* ------------------------------------------------------------------------------------------------
  * Grouped GEMM for MoE experts (replaces scattermoe `parallel_linear`, moe_dolomite/moe/scatter.py:38-49, and the
  * per-expert F.linear loop of moe/base.py:12-50).  Token rows are grouped by expert, each segment padded to a
- * multiple of 128 rows (scattermoe `padded_block_indices`); m_tile_group[i] = expert of 128-row tile i (-1: unused).
+ * multiple of 256 rows (scattermoe `padded_block_indices`); m_tile_group[i] = expert of 128-row tile i (-1: unused).
  *   grouped_m:  D[rows, N] = alpha * A[rows, K] . W[g]^T      W stored [G, N, K] (b_mn_major = 0: expert forward)
  *                                                         or W stored [G, K, N] (b_mn_major = 1: expert dgrad)
  *   grouped_k:  D[g][M, N] = alpha * A_g^T B_g + beta * D[g]  (expert wgrad, fp32): A [K_max, M], B [K_max, N] row-major,
@@ -207,6 +207,12 @@ int dolomite_b200_gemm_bf16_wgrad_multi(int n_problems, const void* const* dY, c
 int dolomite_b200_gemm_bf16_grouped_m(const void* A, int64_t lda, const void* B, int64_t ldb, int b_mn_major, void* D,
                                       int64_t ldd, float alpha, int64_t M_max, int64_t N, int64_t K,
                                       const int32_t* m_tile_group, int num_groups, int flags, void* stream);
+/* grouped_m with the gather fused into the operand load (TMA gather4): A is the UNGROUPED [a_rows, K] activation matrix,
+ * a_row_index[r] (int32, 16-byte aligned, M_max entries) the source row of grouped row r; W stored [G, N, K]. */
+int dolomite_b200_gemm_bf16_grouped_m_gather(const void* A, int64_t lda, int64_t a_rows, const int32_t* a_row_index,
+                                             const void* B, int64_t ldb, void* D, int64_t ldd, float alpha, int64_t M_max,
+                                             int64_t N, int64_t K, const int32_t* m_tile_group, int num_groups, int flags,
+                                             void* stream);
 int dolomite_b200_gemm_bf16_grouped_k(const void* A, int64_t lda, const void* B, int64_t ldb, float* D, int64_t ldd,
                                       float alpha, float beta, int64_t M, int64_t N, int64_t K_max,
                                       const int32_t* group_k_offsets, int num_groups, void* stream);
@@ -216,14 +222,16 @@ int dolomite_b200_gemm_bf16_grouped_k(const void* A, int64_t lda, const void* B,
  *   moe_max_rows: upper bound of padded grouped rows for T tokens (buffer sizing).
  *   moe_route: router logits bf16 [T,E] -> top-k expert ids int32 [T,k] (arg-max order), fp32 softmax weights [T,k],
  *              counts[E] (== bincount, bit exact), offsets_padded[E+1], m_tile_group[max_rows/128], cursors[E] scratch,
- *              row_of_slot[T*k] (grouped row of token-slot), slot_of_row[max_rows] (-1 = padding row).
+ *              row_of_slot[T*k] (grouped row of token-slot), slot_of_row[max_rows] (-1 = padding row),
+ *              token_of_row[max_rows] (source token of a grouped row; padding rows name token 0) -- the row index of
+ *              dolomite_b200_gemm_bf16_grouped_m_gather.  Segments are padded to 256 rows (CTA-pair super tiles).
  *   moe_gather: X_g[row] = x[slot_of_row[row] / k] or 0.     moe_combine: out = c + alpha * sum_j w_j * Y_g[row_j].
  *   moe_combine_bwd / moe_token_sum / moe_router_bwd: their backward pieces.
  * ------------------------------------------------------------------------------------------------ */
 int64_t dolomite_b200_moe_max_rows(int64_t T, int E, int k);
 int dolomite_b200_moe_route(const void* router_logits, int64_t T, int E, int k, int32_t* sel_idx, float* sel_w,
                             int32_t* counts, int32_t* offsets_padded, int32_t* m_tile_group, int32_t* cursors,
-                            int32_t* row_of_slot, int32_t* slot_of_row, void* stream);
+                            int32_t* row_of_slot, int32_t* slot_of_row, int32_t* token_of_row, void* stream);
 int dolomite_b200_moe_gather(const void* x, void* xg, const int32_t* slot_of_row, const int32_t* offsets_padded,
                              int64_t T, int E, int k, int H, void* stream);
 int dolomite_b200_moe_combine(const void* yg, const int32_t* row_of_slot, const float* sel_w, const void* c, void* out,

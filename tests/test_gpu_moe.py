@@ -45,14 +45,16 @@ def test_route_and_plan_bookkeeping(T, E, k):
     counts = plan.counts.cpu().numpy()
     assert np.array_equal(counts, np.bincount(sel.reshape(-1).numpy(), minlength=E))  # bit exact (moe/base.py:158-164)
     off = plan.offsets.cpu().numpy()
-    assert off[0] == 0 and np.all(off % 128 == 0)
-    assert np.array_equal(np.diff(off), (counts + 127) // 128 * 128)
+    assert off[0] == 0 and np.all(off % 256 == 0)  # segments padded to CTA-pair super tiles
+    assert np.array_equal(np.diff(off), (counts + 255) // 256 * 256)
     ros, sor = plan.row_of_slot.cpu().numpy(), plan.slot_of_row.cpu().numpy()
     assert len(set(ros.tolist())) == T * k  # every slot has its own row
     assert np.array_equal(sor[ros], np.arange(T * k))  # inverse maps
     flat = sel.reshape(-1).numpy()
     assert np.all(ros >= off[flat]) and np.all(ros < off[flat] + counts[flat])  # row inside its expert segment
     assert (sor >= 0).sum() == T * k
+    tor = plan.token_of_row.cpu().numpy()
+    assert np.array_equal(tor[ros], np.arange(T * k) // k) and np.all(tor[sor < 0] == 0)  # gather index of the fused load
     tg = plan.tile_group.cpu().numpy()
     for i, gidx in enumerate(tg):
         row = i * 128
@@ -104,6 +106,28 @@ def _moe_cfgs():
     cfg = MoEDolomiteConfig(position_embedding_type="rope", normalization_function="rmsnorm", activation_function="swiglu",
                             resid_pdrop=0, embd_pdrop=0, attn_pdrop=0, eos_token_id=7, **kw)
     return cfg, ocfg
+
+
+@pytest.mark.parametrize("T,H,N,E,k", [(1000, 256, 512, 8, 2), (4096, 2048, 1024, 8, 2), (37, 64, 264, 16, 4)])
+def test_gather_on_load_equals_gather_then_gemm(T, H, N, E, k):
+    """grouped expert GEMM with the token gather fused into its operand load (TMA gather4) == gather kernel + grouped GEMM,
+    bit for bit on every real row; CTA-pair and single-CTA grids (the reference: scattermoe parallel_linear, moe/scatter.py:38-49)"""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = bf(torch.randn(T, H, device="cuda", generator=g))
+    w = bf(torch.randn(E, N, H, device="cuda", generator=g) * 0.05)
+    plan = K().moe_route(bf(torch.randn(T, E, device="cuda", generator=g)), k)
+    real = plan.slot_of_row >= 0
+    for flags in (K().GEMM_TMA_STORE, K().GEMM_TMA_STORE | 8):  # default (CTA pair) / single-CTA kernel
+        ref = K().gemm_grouped_m(K().moe_gather(x, plan), w, plan, b_mn=False, flags=flags)
+        got = K().gemm_grouped_m_gather(x, w, plan, flags=flags)
+        assert torch.equal(got[real], ref[real]), flags
+    # and against fp64 on a few rows
+    rows = torch.nonzero(real)[:: max(1, int(real.sum()) // 9)].flatten()[:8]
+    tg = plan.tile_group.cpu()
+    for r in rows.tolist():
+        e = int(tg[r // 128])
+        exact = x[int(plan.token_of_row[r])].double() @ w[e].double().t()
+        assert torch.allclose(got[r].double(), exact, atol=2e-2, rtol=2e-2)
 
 
 def test_moe_layer_matches_golden(golden_dir):

@@ -485,6 +485,74 @@ def elementwise_bench_c2():
     return res
 
 
+@case
+def ce_bench():
+    """row-resident cross entropy at the C2 / C5 / C4 vocabulary widths: GB/s of algorithmic bytes (4 B per logit)"""
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+
+    res = {}
+    for name, (T, V) in {"c2_V49152": (8192, 49152), "c5_V128256": (4096, 128256), "c4_V50304": (8192, 50304)}.items():
+        logits = torch.randn(T, V, device="cuda").bfloat16()
+        labels = torch.randint(0, V, (T,), device="cuda")
+        scratch = k.cross_entropy_count(labels)
+        loss_tok = torch.empty(T, device="cuda")
+        ms = _time(lambda: k.cross_entropy_rows(logits, labels, loss_tok, scratch), iters=10)
+        res[name] = {"ms": ms, "GBps": 4.0 * T * V / ms / 1e6}
+    res["ok"] = True
+    return res
+
+
+@case
+def wgrad_multi_bench():
+    """the four weight gradients of one C2 block at T = 24576 (bench micro-batch 6): four launches with the per-thread fp32
+    epilogue (round 1), four launches with the TMA tile epilogue, ONE multi-problem launch, and cuBLAS (torch.matmul)"""
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+
+    T, H, F = 24576, 2560, 10240
+    shapes = {"c_proj_mlp": (H, F), "c_fc": (2 * F, H), "c_proj_attn": (H, H), "c_attn": (3 * H, H)}
+    g = torch.Generator(device="cuda").manual_seed(0)
+    probs = []
+    for M, N in shapes.values():
+        dy = (torch.randn(T, M, device="cuda", generator=g) * 0.1).bfloat16()
+        x = (torch.randn(T, N, device="cuda", generator=g) * 0.1).bfloat16()
+        probs.append((dy, x, torch.zeros(M, N, device="cuda"), 1.0, True))
+    flops = sum(2.0 * T * M * N for M, N in shapes.values())
+
+    def separate(flags):
+        def f():
+            for dy, x, dw, a, _ in probs:
+                k.gemm(dy, x, a_mn=True, b_mn=True, out=dw, c=dw, beta=1.0, flags=flags)
+        return f
+
+    def store(flags):
+        def f():
+            for dy, x, dw, a, _ in probs:
+                k.gemm(dy, x, a_mn=True, b_mn=True, out=dw, flags=flags)
+        return f
+
+    def cublas():
+        for dy, x, dw, _, _ in probs:
+            torch.matmul(dy.t(), x)
+
+    res = {}
+    for name, fn in (("separate_direct_epilogue_accumulate", separate(k.GEMM_DIRECT_EPILOGUE)), ("separate_tma_reduce_add", separate(0)),
+                     ("separate_tma_store_overwrite", store(0)), ("multi_accumulate", lambda: k.gemm_wgrad_multi(probs)),
+                     ("multi_overwrite", lambda: k.gemm_wgrad_multi([(a, b, c, d, False) for a, b, c, d, _ in probs])),
+                     ("cublas_bf16_out", cublas)):
+        ms = _time(fn, iters=10)
+        res[name] = {"ms": ms, "tflops": flops / ms / 1e9}
+    # correctness of the multi launch against torch on one problem
+    dy, x, dw, _, _ = probs[2]
+    dw.zero_()
+    k.gemm_wgrad_multi([(p[0], p[1], p[2], 1.0, False) for p in probs])
+    ref = dy.float().t() @ x.float()
+    res["rel_l2_vs_torch"] = ((dw - ref).norm() / ref.norm()).item()
+    res["ok"] = bool(res["rel_l2_vs_torch"] < 1e-2)
+    return res
+
+
 # ---------------------------------------------------------------------------------------------
 def _attn_ref(qkv, cu, ng, g, hd, scale, dout=None):
     """fp32 reference: per-document causal softmax attention on the packed slot layout."""
@@ -730,18 +798,28 @@ def moe_layer_fwd_c4():
     w_proj = (torch.randn(E, H, F, device="cuda") * 0.02).bfloat16()
     res = torch.zeros(T, H, device="cuda", dtype=torch.bfloat16)
 
-    def fwd():
-        logits = k.gemm(x, gate, flags=0)
-        plan = k.moe_route(logits, topk)
-        xg = k.moe_gather(x, plan)
-        fc = k.gemm_grouped_m(xg, w_fc, plan, b_mn=False)
-        act = k.swiglu_fwd(fc)
-        yg = k.gemm_grouped_m(act, w_proj, plan, b_mn=False)
-        return k.moe_combine(yg, plan, c=res, alpha=1.0)
+    def make(fused: bool, flags):
+        def fwd():
+            logits = k.gemm(x, gate, flags=0)
+            plan = k.moe_route(logits, topk)
+            if fused:
+                fc = k.gemm_grouped_m_gather(x, w_fc, plan, flags=flags)
+            else:
+                fc = k.gemm_grouped_m(k.moe_gather(x, plan), w_fc, plan, b_mn=False, flags=flags)
+            act = k.swiglu_fwd(fc)
+            yg = k.gemm_grouped_m(act, w_proj, plan, b_mn=False, flags=flags)
+            return k.moe_combine(yg, plan, c=res, alpha=1.0)
+        return fwd
 
-    ms = _time(fwd, iters=5, warmup=2)
     flops = 2.0 * T * topk * H * 3 * F
-    return {"fwd_ms": ms, "expert_gemm_tflops_incl_routing_kernels": flops / ms / 1e9, "ok": True}
+    out = {}
+    for name, fused, flags in (("fused_gather_pair", True, k.GEMM_TMA_STORE), ("gather_kernel_pair", False, k.GEMM_TMA_STORE),
+                               ("gather_kernel_single_cta", False, k.GEMM_TMA_STORE | 8)):
+        ms_i = _time(make(fused, flags), iters=5, warmup=2)
+        out[name] = {"fwd_ms": ms_i, "expert_gemm_tflops_incl_routing_kernels": flops / ms_i / 1e9}
+    ms = out["fused_gather_pair"]["fwd_ms"]
+    out["ok"] = True
+    return out
 
 
 @case
