@@ -22,7 +22,6 @@ constexpr int BWD_THREADS = 192;
 
 struct BwdParams {
     const float* lse;      // [n_heads, T]
-    const float* lse2;     // [n_heads, T]  lse * log2(e), written by attn_delta_kernel (pipelined kernel: TMA-staged)
     const float* delta;    // [n_heads, T]
     float* dq_accum;       // [n_heads, T, HD] fp32 (a query tile of one head is one contiguous slab)
     __nv_bfloat16* dqkv;   // [T, row_stride]
@@ -45,8 +44,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // one 32-byte sector.
 constexpr int DELTA_TOK = 8;
 __global__ void __launch_bounds__(256)
-    attn_delta_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ out, float* __restrict__ delta,
-                      const float* __restrict__ lse, float* __restrict__ lse2, int64_t T, int n_heads, int vec_per_head) {
+    attn_delta_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ out, float* __restrict__ delta, int64_t T,
+                      int n_heads, int vec_per_head) {
     extern __shared__ float part[];  // [DELTA_TOK][n_heads * vec_per_head]
     const int64_t t0 = int64_t(blockIdx.x) * DELTA_TOK;
     const int ntok = (T - t0) < DELTA_TOK ? int(T - t0) : DELTA_TOK;
@@ -70,7 +69,6 @@ __global__ void __launch_bounds__(256)
             float s = 0.f;
             for (int k = 0; k < vec_per_head; ++k) s += p[k];
             delta[int64_t(h) * T + t0 + tl] = s;
-            lse2[int64_t(h) * T + t0 + tl] = lse[int64_t(h) * T + t0 + tl] * 1.4426950408889634f;
         }
     }
 }
@@ -456,7 +454,7 @@ inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
 extern "C" int64_t dolomite_b200_attn_varlen_bwd_workspace_bytes(int64_t T, int n_groups, int q_per_group,
                                                                  int head_dim) {
     const int64_t nh = int64_t(n_groups) * q_per_group;
-    return 2 * align256(nh * T * 4) + align256(T * nh * head_dim * 4) + 256;
+    return align256(nh * T * 4) + align256(T * nh * head_dim * 4) + 256;
 }
 
 extern "C" int dolomite_b200_attn_varlen_bwd(const void* dout, const void* qkv, int64_t row_stride, const void* out,
@@ -474,18 +472,16 @@ extern "C" int dolomite_b200_attn_varlen_bwd(const void* dout, const void* qkv, 
     const int nh = n_groups * q_per_group;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* delta = static_cast<float*>(workspace);
-    float* lse2 = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align256(int64_t(nh) * T * 4));
-    float* dq_accum = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * align256(int64_t(nh) * T * 4));
+    float* dq_accum = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align256(int64_t(nh) * T * 4));
     DOLO_CUDA_OK(cudaMemsetAsync(dq_accum, 0, size_t(T) * nh * head_dim * 4, st));
     {
         const int64_t blocks = (T + DELTA_TOK - 1) / DELTA_TOK;
         attn_delta_kernel<<<(unsigned)blocks, 256, size_t(nh) * (head_dim / 8) * DELTA_TOK * sizeof(float), st>>>(
-            static_cast<const uint4*>(dout), static_cast<const uint4*>(out), delta, lse, lse2, T, nh, head_dim / 8);
+            static_cast<const uint4*>(dout), static_cast<const uint4*>(out), delta, T, nh, head_dim / 8);
         DOLO_LAUNCH_OK("attn_delta");
     }
     BwdParams p;
     p.lse = lse;
-    p.lse2 = lse2;
     p.delta = delta;
     p.dq_accum = dq_accum;
     p.dqkv = static_cast<__nv_bfloat16*>(dqkv);

@@ -9,7 +9,7 @@
 // separate warp group draining dQ, so that the tensor pipe (S^T/dP^T of step s+1, dV/dK/dQ of step s-1) runs
 // concurrently with the softmax warps working on step s:
 //
-//   warp 0      TMA producer  (K_j,V_j once; Q_i,dO_i and the LSE / Delta rows of tile i through a 2-stage ring)
+//   warp 0      TMA producer  (K_j,V_j once; Q_i,dO_i 2-stage ring)
 //   warp 1      MMA issuer    A_s: S^T_s = K Q_h^T, dP^T_s = V dO_h^T   (128 keys x 64 queries, buffers s & 1)
 //                             C_s: dV += P^T_s dO_h, dK += dS^T_s Q_h   (A operands from TMEM)
 //                             after the second half: dQ_i = dS_i K_j    (128 queries, A = dS^T tile in smem, MN-major)
@@ -33,7 +33,6 @@ template <int HD, int NG>
 __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
     attn_bwd_kernel_v3(const __grid_constant__ CUtensorMap tq64, const __grid_constant__ CUtensorMap tqR,
                        const __grid_constant__ CUtensorMap to64, const __grid_constant__ CUtensorMap toR,
-                       const __grid_constant__ CUtensorMap tlse, const __grid_constant__ CUtensorMap tdelta,
                        const BwdParams p) {
     using CH = HeadChunks<HD>;
     static_assert(256 + 3 * HD <= 512, "v2 needs a private dQ accumulator (head_dim <= 80)");
@@ -92,8 +91,6 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tq64);
         tma_prefetch_desc(&to64);
-        tma_prefetch_desc(&tlse);
-        tma_prefetch_desc(&tdelta);
         mbar_init(kv_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&qdo_full[i], 1);
@@ -134,13 +131,9 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
                 const int q_col = (group * (p.q_per_group + 2) + s_head) * HD;
                 const int q_row = loc.doc_start + i * ATT_TILE;
                 mbar_wait(&qdo_empty[stage], phase ^ 1, 30);
-                mbar_expect_tx(&qdo_full[stage], 2 * TILE_BYTES + 2 * ATT_TILE * 4);
+                mbar_expect_tx(&qdo_full[stage], 2 * TILE_BYTES);
                 load_tile(sQ + stage * TILE_BYTES, &qdo_full[stage], &tq64, &tqR, q_col, q_row);
                 load_tile(sDO + stage * TILE_BYTES, &qdo_full[stage], &to64, &toR, head * HD, q_row);
-                // LSE (log2 units) and Delta of the 128 queries: two 512-byte TMA boxes out of the [heads, T] fp32 arrays
-                // (rows past T are zero-filled; rows of the next document are masked by the softmax warps)
-                tma_load_2d(sLSE + stage * ATT_TILE, &tlse, &qdo_full[stage], q_row, head);
-                tma_load_2d(sDelta + stage * ATT_TILE, &tdelta, &qdo_full[stage], q_row, head);
             }
         }
     } else if (warp == 1) {
@@ -233,18 +226,37 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
         const int wg = (warp - 4) >> 2;  // column group: query columns [32*wg, 32*wg+32) of each 64-query half
         const int sub = warp & 3;
         const int r = sub * 32 + lane;
+        const int tidsm = (warp - 4) * 32 + lane;
         const uint32_t t_lane = tmem_base + (uint32_t(sub * 32) << 16);
         const int kj = j * ATT_TILE + r;
         const bool key_ok = kj < loc.doc_len;
         const bool tile_full = (j + 1) * ATT_TILE <= loc.doc_len;  // every key row of this CTA is inside the document
+        const float LOG2E = 1.4426950408889634f;
+        // LSE (log2 units) / Delta of a query tile: thread t < 128 fetches lse[t], thread 128 + t fetches delta[t].  The
+        // fetch for tile it+1 is issued while tile it is processed (global latency off the critical path).
+        auto fetch_stat = [&](int it) -> float {
+            const int s_head = it / n_i, i = j + (it - s_head * n_i);
+            const int head = group * p.q_per_group + s_head;
+            const int qi = i * ATT_TILE + (tidsm & (ATT_TILE - 1));
+            const bool q_ok = qi < loc.doc_len;
+            const int64_t off = int64_t(head) * p.T + loc.doc_start + qi;
+            if (tidsm < ATT_TILE) return q_ok ? p.lse[off] : INFINITY;  // scaled to log2 units when stored (not here:
+                                                                        // the multiply would wait for the load at once)
+            if (tidsm < 2 * ATT_TILE) return q_ok ? p.delta[off] : 0.f;
+            return 0.f;
+        };
+        float stat_next = fetch_stat(0);
+
         for (int it = 0; it < n_it; ++it) {
             const int s_head = it / n_i, i = j + (it - s_head * n_i);
-            const float* lse_s = sLSE + (it & 1) * ATT_TILE;   // staged by the TMA producer together with Q_i / dO_i
-            const float* del_s = sDelta + (it & 1) * ATT_TILE;
+            float* lse_s = sLSE + (it & 1) * ATT_TILE;
+            float* del_s = sDelta + (it & 1) * ATT_TILE;
+            if (tidsm < ATT_TILE) lse_s[tidsm] = stat_next * LOG2E;
+            else if (tidsm < 2 * ATT_TILE) del_s[tidsm - ATT_TILE] = stat_next;
+            named_bar_sync(2, SOFTMAX_THREADS);
+            if (it + 1 < n_it) stat_next = fetch_stat(it + 1);
             if (it >= 2) mbar_wait(&dq_full[it & 1], uint32_t((it >> 1) - 1) & 1, 35);  // dS smem buffer free again
-            mbar_wait(&qdo_full[it & 1], uint32_t(it >> 1) & 1, 39);                    // LSE / Delta of this tile landed
-            const int q_valid = loc.doc_len - i * ATT_TILE;  // queries of this tile inside the document (>= 128: all)
-            const bool need_mask = (i == j) || !tile_full || q_valid < ATT_TILE;
+            const bool need_mask = (i == j) || !tile_full;
             const bool diag = (i == j);
             uint8_t* ds_buf = sDS + (it & 1) * DS_BYTES;
 
@@ -261,7 +273,7 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
                         for (int u = 0; u < 2; ++u) {
                             const int c = cbase + c2 + u;
                             float pe = fast_exp2(__uint_as_float(sv[c2 + u]) * p.scale_log2 - lse_s[c]);
-                            if (!key_ok || (diag && r > c) || c >= q_valid) pe = 0.f;
+                            if (!key_ok || (diag && r > c)) pe = 0.f;
                             pv[u] = pe;
                             dsv[u] = pe * (__uint_as_float(dv[c2 + u]) - del_s[c]) * p.scale;
                         }
@@ -430,17 +442,6 @@ int launch_bwd_v3(const void* dout, const void* qkv, int64_t row_stride, const B
     if (rc) return rc;
     rc = make_maps<HD>(dout, int64_t(p.n_heads) * HD, p.T, &to64, &toR);
     if (rc) return rc;
-    CUtensorMap tlse, tdelta;
-    {
-        // [heads, T] fp32, one box = the 128 values of a query tile
-        uint64_t dims[2] = {uint64_t(p.T), uint64_t(p.n_heads)};
-        uint64_t strides[2] = {4, uint64_t(p.T) * 4};
-        uint32_t box[2] = {ATT_TILE, 1};
-        rc = dolo_make_tmap(&tlse, p.lse2, 4, 2, dims, strides, box, DOLO_SW_NONE);
-        if (rc) return rc;
-        rc = dolo_make_tmap(&tdelta, p.delta, 4, 2, dims, strides, box, DOLO_SW_NONE);
-        if (rc) return rc;
-    }
     constexpr int need = bwd_v3_smem_need<HD>();
     constexpr int smem_bytes = (need + 1024 > 232448) ? need : need + 1024;
     static_assert(smem_bytes <= 232448, "attention backward v3 shared memory budget exceeded");
@@ -452,7 +453,7 @@ int launch_bwd_v3(const void* dout, const void* qkv, int64_t row_stride, const B
     }
     const int64_t max_tiles = (p.T + ATT_TILE - 1) / ATT_TILE + p.n_docs;
     dim3 grid((unsigned)max_tiles, (unsigned)p.n_groups);
-    kern<<<grid, 32 * (6 + 4 * NG), smem_bytes, st>>>(tq64, tqR, to64, toR, tlse, tdelta, p);
+    kern<<<grid, 32 * (6 + 4 * NG), smem_bytes, st>>>(tq64, tqR, to64, toR, p);
     DOLO_LAUNCH_OK("attn_varlen_bwd_v2");
     return DOLO_OK;
 }

@@ -211,7 +211,13 @@ __global__ void __launch_bounds__(FWD_THREADS)
                     }
                 }
             }
-            const float m_new = mx;  // finite for every valid row (the diagonal key is always visible)
+            // Lazy reference maximum: the exponent reference of a row only moves when the tile's maximum exceeds it by more
+            // than 2^8 (FlashAttention-4's thresholded rescale).  P then stays <= 256 (exact in bf16's exponent range, fp32
+            // sums), O and l are rescaled a handful of times per row instead of once per tile for most warps -- with random
+            // scores some row of a warp sets a new maximum in ~90 % of the tiles, so the "all alpha == 1" skip below almost
+            // never fired (ncu: the O rescale was 14 % of the softmax warps' samples).  mx is finite for every valid row.
+            const bool move_ref = (m_run == -INFINITY) || (mx * p.scale_log2 > m_run * p.scale_log2 + 8.f);
+            const float m_new = move_ref ? mx : m_run;
             const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
             const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run * p.scale_log2 - m_scaled);
             // rescale O (previous PV has completed: s_full is committed after it); skipped when no row of this

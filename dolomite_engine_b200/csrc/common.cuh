@@ -41,6 +41,10 @@ int dolo_option_gemm_cta_pair();     // 1 = dense GEMMs use the CTA-pair (cta_gr
 // communication kernel (NCCL all-gather / reduce-scatter, a few CTAs) occupies some SMs: the GEMM CTAs that do not fit
 // only start when a whole persistent CTA retires.  The sharded data-parallel runtime sets this to NCCL's CTA budget.
 int dolo_option_gemm_sm_margin();
+// 1 = fp32 outputs (weight gradients) leave through shared memory + TMA tile store / reduce-add; 0 (default) = per-thread
+// 128-byte row segments.  Measured on the four weight gradients of a C2 block (profiles/r02_probe_call70.jsonl): the TMA
+// path is 5 % (reduce-add) to 13 % (store) SLOWER -- 32 extra TMA operations per tile share the queue of the operand loads.
+int dolo_option_gemm_f32_tma_epilogue();
 
 // TMA descriptor encode through the driver entry point (no link-time libcuda dependency).
 // rank-2 / rank-3 bf16/f32 tiled maps.  dims/strides innermost first; strides in BYTES for dims >= 1.

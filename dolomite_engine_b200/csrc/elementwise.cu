@@ -695,12 +695,20 @@ __global__ void __launch_bounds__(kCeThreads, 2)
             if (i < v_hi) {
                 float f[8];
                 unpack8(v[k], f);
-                if (i == lvec) loss_tok[row] = (lse2 - f[lsub] * scale2) * 0.6931471805599453f;
+                // (compile-time indices only: a run-time index into f[] would move the array to local memory -- the ncu
+                //  capture of the first version showed two STL.128 + LDL per vector and long-scoreboard stalls on them)
+                const bool has_label = (i == lvec);
+                if (has_label) {
+                    float xl = 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fast_exp2(fmaf(f[j], scale2, -lse2));
-                if (i == lvec) f[lsub] -= 1.f;
+                    for (int j = 0; j < 8; ++j) xl = (j == lsub) ? f[j] : xl;
+                    loss_tok[row] = (lse2 - xl * scale2) * 0.6931471805599453f;
+                }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] *= gmul;
+                for (int j = 0; j < 8; ++j) {
+                    const float pj = fast_exp2(fmaf(f[j], scale2, -lse2));
+                    f[j] = ((has_label && j == lsub) ? pj - 1.f : pj) * gmul;
+                }
                 dr[i] = pack8(f);
             }
         }
@@ -1194,7 +1202,7 @@ extern "C" int dolomite_b200_cross_entropy_rows(const void* logits, int64_t ldl,
     if (nv1 <= 4) DOLO_CE(4, 1);
     if (nv1 <= 8) DOLO_CE(8, 1);
     if (nv1 <= 16) DOLO_CE(16, 1);
-    if (nv1 <= 24) DOLO_CE(12, 2);  // (24 vectors per thread spill under the 128-register cap of two CTAs per SM)
+    if (nv1 <= 24) DOLO_CE(24, 1);  // one CTA per row whenever it fits: the cluster barrier costs a GPU-scope fence per use
     if (nv1 <= 32) DOLO_CE(16, 2);
     if (nv1 <= 48) DOLO_CE(12, 4);
     if (nv1 <= 64) DOLO_CE(16, 4);

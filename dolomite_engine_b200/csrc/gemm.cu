@@ -697,7 +697,7 @@ static int dispatch_layout(int a_mn_major, int b_mn_major, Ts&&... args) {
 static int pick_epilogue(int d_is_f32, const void* C, const void* D, float beta, const void* bias, bool tma_store,
                          int group_mode) {
     if (!d_is_f32) return tma_store ? EPI_BF16_TMA : EPI_DIRECT;
-    if (bias != nullptr || group_mode == 3) return EPI_DIRECT;
+    if (bias != nullptr || group_mode == 3 || !dolo_option_gemm_f32_tma_epilogue()) return EPI_DIRECT;
     if (C == nullptr) return EPI_F32_TMA_STORE;
     if (C == D && beta == 1.f) return EPI_F32_TMA_ADD;
     return EPI_DIRECT;
@@ -717,6 +717,8 @@ static int gemm_impl(const void* A, int64_t lda, int a_mn_major, const void* B, 
                           (flags & DOLO_GEMM_FLAG_NO_CTA_PAIR) == 0;
     int epi = pick_epilogue(d_is_f32, C, D, beta, bias, tma_store, ga.mode);
     if ((flags & DOLO_GEMM_FLAG_DIRECT_EPILOGUE) != 0 && d_is_f32) epi = EPI_DIRECT;
+    if ((flags & DOLO_GEMM_FLAG_F32_TMA_EPILOGUE) != 0 && d_is_f32 && bias == nullptr && ga.mode != 3)
+        epi = C == nullptr ? EPI_F32_TMA_STORE : ((C == D && beta == 1.f) ? EPI_F32_TMA_ADD : EPI_DIRECT);
     GemmMaps maps;
     GemmParams p;
     memset(&p, 0, sizeof(p));
@@ -757,7 +759,8 @@ extern "C" int dolomite_b200_gemm_bf16_wgrad_multi(int n_problems, const void* c
         DOLO_REQUIRE(M[q] > 0 && N[q] > 0, "wgrad_multi: empty problem %d", q);
         GemmProblemArgs g{dY[q], ld_dy[q], X[q], ld_x[q], dW[q], ld_dw[q], accumulate[q] ? dW[q] : nullptr, ld_dw[q], nullptr,
                           alpha[q], 1.f, M[q], N[q], K};
-        int rc = setup_problem(maps, p, q, g, 1, 1, 1, accumulate[q] ? EPI_F32_TMA_ADD : EPI_F32_TMA_STORE, pair, GroupArgs());
+        const int epi = !dolo_option_gemm_f32_tma_epilogue() ? EPI_DIRECT : (accumulate[q] ? EPI_F32_TMA_ADD : EPI_F32_TMA_STORE);
+        int rc = setup_problem(maps, p, q, g, 1, 1, 1, epi, pair, GroupArgs());
         if (rc) return rc;
         p.pr[q].tile_start = tiles;
         tiles += p.pr[q].num_m * p.pr[q].num_n;

@@ -263,7 +263,8 @@ def accum_bf16_into_f32(src, dst, scale=1.0):
 # ------------------------------------------------------------------------------------------------
 GEMM_TMA_STORE = 1
 GEMM_SPLITK_ACCUMULATE = 2
-GEMM_DIRECT_EPILOGUE = 16  # fp32 D through per-thread vector accesses instead of TMA tile store / reduce-add (A/B tests)
+GEMM_DIRECT_EPILOGUE = 16  # fp32 D through per-thread 128-byte row segments (the default)
+GEMM_F32_TMA_EPILOGUE = 32  # fp32 D through shared memory + TMA tile store / reduce-add (measured slower; A/B tests)
 # Split-K + fp32-atomic accumulation of weight gradients was measured SLOWER than read-modify-write on B200
 # (profiles/r01_probe_wgrad_splitk.json: 20480x2560x8192 2.64 ms vs 0.65 ms -- L2 atomic throughput), so it is off;
 # the entry point stays for shapes with very few output tiles.

@@ -15,8 +15,10 @@ import os
 
 from . import kernels as K
 
-# DOLO_MOE_FUSED_GATHER=0 falls back to the separate gather pass in forward (A/B measurements)
-FUSED_GATHER = os.environ.get("DOLO_MOE_FUSED_GATHER", "1") != "0"
+# DOLO_MOE_FUSED_GATHER=1: the expert c_fc GEMM gathers its token rows itself (TMA gather4 in the producer warp).  Exact, but
+# measured 2.3x SLOWER than gather kernel + grouped GEMM on the C4 layer (3.09 vs 1.35 ms, profiles/r02_probe_call70.jsonl):
+# one gather4 moves 512 B and the operand ring needs one every 16 cycles, which the TMA unit does not sustain.  Off by default.
+FUSED_GATHER = os.environ.get("DOLO_MOE_FUSED_GATHER", "0") == "1"
 
 
 def forward(engine, unit, p: str, x, residual, m_res: float):

@@ -38,7 +38,8 @@ int dolomite_b200_abi_version(void);
 int dolomite_b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* process-wide tuning knobs:
  *   "gemm_cta_pair"    0 | 1 (dense GEMMs on 2-CTA clusters with tcgen05.mma.cta_group::2)
- *   "gemm_sm_margin"   SMs the persistent GEMM grids leave free for concurrent communication kernels */
+ *   "gemm_sm_margin"   SMs the persistent GEMM grids leave free for concurrent communication kernels
+ *   "gemm_f32_tma_epilogue" 0 | 1 (fp32 weight gradients through TMA tile store / reduce-add instead of per-thread stores) */
 int dolomite_b200_set_option(const char* key, int value);
 
 /* ------------------------------------------------------------------------------------------------
@@ -181,8 +182,10 @@ int dolomite_b200_accum_bf16_into_f32(const void* src, float* dst, float scale, 
  * default follows the "gemm_cta_pair" option. */
 #define DOLO_GEMM_FLAG_CTA_PAIR 4
 #define DOLO_GEMM_FLAG_NO_CTA_PAIR 8
-/* bit4: fp32 D through per-thread vector accesses instead of the TMA tile store / reduce-add epilogue (A/B tests) */
+/* bit4 / bit5: fp32 D through per-thread 128-byte row segments (the default) / through shared memory + TMA tile store or
+ * reduce-add (measured slower, kept for A/B tests; also the "gemm_f32_tma_epilogue" option) */
 #define DOLO_GEMM_FLAG_DIRECT_EPILOGUE 16
+#define DOLO_GEMM_FLAG_F32_TMA_EPILOGUE 32
 int dolomite_b200_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                             void* D, int64_t ldd, int d_is_f32, const void* C, int64_t ldc, float alpha, float beta,
                             const void* bias, int64_t M, int64_t N, int64_t K, int flags, void* stream);

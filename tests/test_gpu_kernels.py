@@ -203,7 +203,8 @@ def test_full_size_gemm_spot_checks():
     assert torch.allclose(once[:8, :8].double().cpu(), exact, atol=5e-2, rtol=1e-3)
 
 
-def test_block_weight_gradients_in_one_launch_and_fp32_tile_epilogues():
+@pytest.mark.parametrize("tma_epilogue", [False, True])
+def test_block_weight_gradients_in_one_launch_and_fp32_tile_epilogues(tma_epilogue):
     """gemm_wgrad_multi (the four weight gradients of a block in one persistent launch, TMA store / reduce-add epilogue)
     == four separate GEMMs == fp64 products on sampled entries; overwrite and accumulate forms; ragged M / N edges.
     Also: the fp32 TMA epilogue and the per-thread epilogue of the single-problem GEMM agree bit for bit."""
@@ -220,8 +221,12 @@ def test_block_weight_gradients_in_one_launch_and_fp32_tile_epilogues():
         alpha = 1.0 if i != 2 else 0.5
         probs.append((dy, x, dw, alpha, acc))
         refs.append((ref, dy, x, alpha))
-    K().gemm_wgrad_multi(probs)
-    torch.cuda.synchronize()
+    K().set_option("gemm_f32_tma_epilogue", int(tma_epilogue))
+    try:
+        K().gemm_wgrad_multi(probs)
+        torch.cuda.synchronize()
+    finally:
+        K().set_option("gemm_f32_tma_epilogue", 0)
     for (dy, x, dw, alpha, acc), (ref, _, _, _) in zip(probs, refs):
         sep = ref.clone()
         if acc:
@@ -239,7 +244,7 @@ def test_block_weight_gradients_in_one_launch_and_fp32_tile_epilogues():
     dy, x = probs[0][0], probs[0][1]
     a = torch.empty(2560, 1024, device="cuda")
     b = torch.empty(2560, 1024, device="cuda")
-    K().gemm(dy, x, a_mn=True, b_mn=True, out=a)
+    K().gemm(dy, x, a_mn=True, b_mn=True, out=a, flags=K().GEMM_F32_TMA_EPILOGUE)
     K().gemm(dy, x, a_mn=True, b_mn=True, out=b, flags=K().GEMM_DIRECT_EPILOGUE)
     assert torch.equal(a, b)
 

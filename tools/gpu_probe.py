@@ -537,12 +537,20 @@ def wgrad_multi_bench():
             torch.matmul(dy.t(), x)
 
     res = {}
-    for name, fn in (("separate_direct_epilogue_accumulate", separate(k.GEMM_DIRECT_EPILOGUE)), ("separate_tma_reduce_add", separate(0)),
-                     ("separate_tma_store_overwrite", store(0)), ("multi_accumulate", lambda: k.gemm_wgrad_multi(probs)),
-                     ("multi_overwrite", lambda: k.gemm_wgrad_multi([(a, b, c, d, False) for a, b, c, d, _ in probs])),
-                     ("cublas_bf16_out", cublas)):
+    def multi(acc):
+        return lambda: k.gemm_wgrad_multi([(a, b, c, d, acc) for a, b, c, d, _ in probs])
+
+    for name, fn, tma in (("separate_direct_accumulate", separate(k.GEMM_DIRECT_EPILOGUE), 0),
+                          ("separate_direct_overwrite", store(k.GEMM_DIRECT_EPILOGUE), 0),
+                          ("separate_tma_reduce_add", separate(k.GEMM_F32_TMA_EPILOGUE), 0),
+                          ("separate_tma_store_overwrite", store(k.GEMM_F32_TMA_EPILOGUE), 0),
+                          ("multi_direct_accumulate", multi(True), 0), ("multi_direct_overwrite", multi(False), 0),
+                          ("multi_tma_accumulate", multi(True), 1), ("multi_tma_overwrite", multi(False), 1),
+                          ("cublas_bf16_out", cublas, 0), ("separate_direct_accumulate_again", separate(k.GEMM_DIRECT_EPILOGUE), 0)):
+        k.set_option("gemm_f32_tma_epilogue", tma)
         ms = _time(fn, iters=10)
         res[name] = {"ms": ms, "tflops": flops / ms / 1e9}
+    k.set_option("gemm_f32_tma_epilogue", 0)
     # correctness of the multi launch against torch on one problem
     dy, x, dw, _, _ = probs[2]
     dw.zero_()
