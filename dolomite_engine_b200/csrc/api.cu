@@ -29,6 +29,8 @@ static int g_gemm_cta_pair = 1;
 static int g_gemm_sm_margin = 0;
 int dolo_option_gemm_sm_margin() { return g_gemm_sm_margin; }
 int dolo_option_gemm_cta_pair() { return g_gemm_cta_pair; }
+static int g_gemm_l2_hints = 1;
+int dolo_option_gemm_l2_hints() { return g_gemm_l2_hints; }
 static int g_gemm_f32_tma_epilogue = 0;
 int dolo_option_gemm_f32_tma_epilogue() { return g_gemm_f32_tma_epilogue; }
 
@@ -36,6 +38,10 @@ extern "C" int dolomite_b200_set_option(const char* key, int value) {
     if (key != nullptr && strcmp(key, "gemm_sm_margin") == 0) {
         DOLO_REQUIRE(value >= 0 && value <= 64, "gemm_sm_margin must be in [0, 64]");
         g_gemm_sm_margin = value;
+        return DOLO_OK;
+    }
+    if (key != nullptr && strcmp(key, "gemm_l2_hints") == 0) {
+        g_gemm_l2_hints = value != 0;
         return DOLO_OK;
     }
     if (key != nullptr && strcmp(key, "gemm_f32_tma_epilogue") == 0) {

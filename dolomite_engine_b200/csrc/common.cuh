@@ -45,6 +45,7 @@ int dolo_option_gemm_sm_margin();
 // 128-byte row segments.  Measured on the four weight gradients of a C2 block (profiles/r02_probe_call70.jsonl): the TMA
 // path is 5 % (reduce-add) to 13 % (store) SLOWER -- 32 extra TMA operations per tile share the queue of the operand loads.
 int dolo_option_gemm_f32_tma_epilogue();
+int dolo_option_gemm_l2_hints();  // 1 (default) = evict-first / evict-last operand loads for long-contraction GEMMs
 
 // TMA descriptor encode through the driver entry point (no link-time libcuda dependency).
 // rank-2 / rank-3 bf16/f32 tiled maps.  dims/strides innermost first; strides in BYTES for dims >= 1.
@@ -146,6 +147,20 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// L2 eviction-priority hints for TMA loads (the fixed policy encodings of the sm_90+ `createpolicy` instruction).  A GEMM
+// whose contraction is long streams one operand once per wave of tiles and re-uses the other in every wave: the streamed
+// operand is loaded evict-first, the re-used one evict-last, so the re-used panels survive in the 126 MB L2 (ncu before:
+// dgrad / wgrad read 2.0-2.2x their algorithmic bytes from DRAM, profiles/r02_gemm_traffic_table.json).
+constexpr uint64_t TMA_HINT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t TMA_HINT_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t TMA_HINT_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                 uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
@@ -285,6 +300,14 @@ __device__ __forceinline__ void tma_gather4_2d_2cta(void* smem_dst, const CUtens
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.cta_group::2 [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(r0), "r"(r1), "r"(r2),
         "r"(r3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                      uint64_t hint) {
+    const uint32_t bar_leader = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(c1), "l"(hint)
         : "memory");
 }
 __device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,

@@ -54,6 +54,7 @@ struct Problem {
     int tile_start;  // first launch-wide tile index of this problem
     int epi;         // EpiMode
     float alpha, beta;
+    uint64_t hint_a, hint_b;  // L2 eviction priority of the operand loads (TMA_HINT_*)
 };
 
 struct GemmParams {
@@ -250,6 +251,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 if (!ti.valid) continue;
                 const CUtensorMap* tmap_a = &maps.a[ti.q];
                 const CUtensorMap* tmap_b = &maps.b[ti.q];
+                const uint64_t ha = p.pr[ti.q].hint_a, hb = p.pr[ti.q].hint_b;
                 const int m_blk = CTA2 ? ti.m_blk * 2 + cta_rank : ti.m_blk, n_blk = ti.n_blk;
                 const int b_outer = (p.grouped == 1) ? ti.grp * p.b_group_rows : 0;
                 for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
@@ -261,36 +263,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STG_BYTES);
                         const int n_row = n_blk * BN + cta_rank * (BN / 2);  // this CTA's half of the B tile
                         if (!A_MN) {
-                            tma_load_2d_2cta(sa, tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+                            tma_load_2d_2cta_hint(sa, tmap_a, &full_bar[stage], kb * BK, m_blk * BM, ha);
                         } else {
 #pragma unroll
                             for (int i = 0; i < BM / 64; ++i)
-                                tma_load_2d_2cta(sa + i * (BK * 128), tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+                                tma_load_2d_2cta_hint(sa + i * (BK * 128), tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK, ha);
                         }
                         if (!B_MN) {
-                            tma_load_2d_2cta(sb, tmap_b, &full_bar[stage], kb * BK, b_outer + n_row);
+                            tma_load_2d_2cta_hint(sb, tmap_b, &full_bar[stage], kb * BK, b_outer + n_row, hb);
                         } else {
 #pragma unroll
                             for (int i = 0; i < BN / 128; ++i)
-                                tma_load_2d_2cta(sb + i * (BK * 128), tmap_b, &full_bar[stage], n_row + i * 64,
-                                                 b_outer + kb * BK);
+                                tma_load_2d_2cta_hint(sb + i * (BK * 128), tmap_b, &full_bar[stage], n_row + i * 64,
+                                                 b_outer + kb * BK, hb);
                         }
                     } else {
                         mbar_expect_tx(&full_bar[stage], STG_BYTES);
                         if (!A_MN) {
-                            tma_load_2d(sa, tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+                            tma_load_2d_hint(sa, tmap_a, &full_bar[stage], kb * BK, m_blk * BM, ha);
                         } else {
 #pragma unroll
                             for (int i = 0; i < BM / 64; ++i)
-                                tma_load_2d(sa + i * (BK * 128), tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+                                tma_load_2d_hint(sa + i * (BK * 128), tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK, ha);
                         }
                         if (!B_MN) {
-                            tma_load_2d(sb, tmap_b, &full_bar[stage], kb * BK, b_outer + n_blk * BN);
+                            tma_load_2d_hint(sb, tmap_b, &full_bar[stage], kb * BK, b_outer + n_blk * BN, hb);
                         } else {
 #pragma unroll
                             for (int i = 0; i < BN / 64; ++i)
-                                tma_load_2d(sb + i * (BK * 128), tmap_b, &full_bar[stage], n_blk * BN + i * 64,
-                                            b_outer + kb * BK);
+                                tma_load_2d_hint(sb + i * (BK * 128), tmap_b, &full_bar[stage], n_blk * BN + i * 64,
+                                            b_outer + kb * BK, hb);
                         }
                     }
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -670,6 +672,13 @@ static int setup_problem(GemmMaps& maps, GemmParams& p, int q, const GemmProblem
     pr.alpha = g.alpha;
     pr.beta = g.C ? g.beta : 0.f;
     pr.epi = epi;
+    pr.hint_a = pr.hint_b = TMA_HINT_NORMAL;
+    if (dolo_option_gemm_l2_hints() && ga.mode == 0 && K >= 4096 && (M + N) * K * 2 > (48ll << 20)) {
+        // long contraction, operands larger than what the L2 keeps anyway: stream the bigger one, keep the smaller one
+        const bool a_smaller = M <= N;
+        pr.hint_a = a_smaller ? TMA_HINT_EVICT_LAST : TMA_HINT_EVICT_FIRST;
+        pr.hint_b = a_smaller ? TMA_HINT_EVICT_FIRST : TMA_HINT_EVICT_LAST;
+    }
     pr.num_m = cta_pair ? int((M + 2 * BM - 1) / (2 * BM)) : int((M + BM - 1) / BM);  // pair mode: 256-row super tiles
     pr.num_n = int((N + BN - 1) / BN);
     pr.num_kb = int((K + BK - 1) / BK);

@@ -222,6 +222,21 @@ def gemm_pair_bench():
         base = _gemm_case(M, N, Kd, a_mn, b_mn, bench=True, **{**kw, "flags": kw["flags"] & ~4 | 8})
         out[name] = {"pair_tflops": round(r["tflops"]), "single_tflops": round(base["tflops"]), "cublas_tflops": round(r["cublas_tflops"]),
                      "rel_l2": r["rel_l2"]}
+    # the long-contraction shapes again without the L2 eviction hints (A/B inside one process)
+    from dolomite_engine_b200 import kernels as k_
+
+    k_.set_option("gemm_l2_hints", 0)
+    for name, (M, N, Kd, a_mn, b_mn, kw) in {
+        "dgrad_fc_T24576": (24576, 2560, 20480, False, True, dict(flags=5)),
+        "wgrad_fc_T24576": (20480, 2560, 24576, True, True, dict(flags=4, out_f32=True, with_c=True)),
+    }.items():
+        base = _gemm_case(M, N, Kd, a_mn, b_mn, bench=True, **kw)
+        k_.set_option("gemm_l2_hints", 1)
+        r = _gemm_case(M, N, Kd, a_mn, b_mn, bench=True, **kw)
+        k_.set_option("gemm_l2_hints", 0)
+        out[name] = {"hints_tflops": round(r["tflops"]), "no_hints_tflops": round(base["tflops"]), "cublas_tflops": round(r["cublas_tflops"]),
+                     "rel_l2": r["rel_l2"]}
+    k_.set_option("gemm_l2_hints", 1)
     out["ok"] = all(v["rel_l2"] < 2e-2 for v in out.values())
     return out
 
