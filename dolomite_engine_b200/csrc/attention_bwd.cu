@@ -97,13 +97,18 @@ template <int HD>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
     attn_bwd_kernel(const __grid_constant__ CUtensorMap tq64, const __grid_constant__ CUtensorMap tqR,
                     const __grid_constant__ CUtensorMap to64, const __grid_constant__ CUtensorMap toR,
-                    const BwdParams p) {
+                    const __grid_constant__ CUtensorMap tdq, const BwdParams p) {
     using CH = HeadChunks<HD>;
     constexpr int TILE_BYTES = CH::TILE_BYTES;
     constexpr int QDO_STAGES = 2;
     constexpr uint32_t ST_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 256 + HD;
     constexpr bool DQ_SEPARATE = (256 + 3 * HD) <= 512;
     static_assert(DQ_SEPARATE || CH::NCHUNK <= 2, "dQ aliasing needs at most two chunks");
+    // dQ tiles leave through shared memory + TMA tile reduce-add (one operation per warp and 32 columns, the add is done by
+    // the L2) instead of 32 per-thread red.global.add.v4.f32 per row: the per-thread atomics were 26 % of the pipelined
+    // kernel before it got the same treatment.  The staging slabs are the warp's own rows of the dS^T
+    // tile, which the dQ MMA has finished reading by the time the accumulator is drained.
+    constexpr bool DQ_TMA = (HD % 32 == 0);
 
     const TileLoc loc = locate_tile(p.cu_seqlens, p.n_docs, int(blockIdx.x));
     if (!loc.valid) return;
@@ -281,6 +286,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
                 sDelta[et] = d;
             }
             named_bar_sync(2, 128);
+            if (DQ_TMA && it > 0) {  // this warp's dS^T rows double as dQ staging slabs: the last reduces must have read them
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+            }
             mbar_wait(sdp_full, uint32_t(it & 1), 25);
             tc_fence_after();
             const bool diag = (i == j);
@@ -323,7 +332,34 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             // drain dQ_i: TMEM lane r == query row r of tile i
             mbar_wait(dq_full, uint32_t(it & 1), 26);
             tc_fence_after();
-            {
+            if constexpr (DQ_TMA) {
+                // rows past the document add zeros (their dS is zero), rows past the tensor are clipped by the TMA unit
+                const int row0 = int(int64_t(head) * p.T + loc.doc_start + i * ATT_TILE + sub * 32);
+#pragma unroll
+                for (int c = 0; c < CH::NCHUNK; ++c) {
+                    const int w = CH::width(c);
+#pragma unroll 1
+                    for (int c0 = 0; c0 < w; c0 += 32) {
+                        const int slab = ((CH::col(c) + c0) >> 5) & 1;
+                        uint8_t* buf = sDS + slab * (ATT_TILE * 128) + sub * 4096;  // this warp's 32 rows of one dS^T half
+                        if (lane == 0) tma_store_wait_read<1>();  // the reduce issued from this slab two chunks ago has read it
+                        __syncwarp();
+                        uint32_t o[32];
+                        tmem_ld32(t_lane + dq_col(c) + c0, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<uint4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                                make_uint4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_reduce_add_2d(&tdq, buf, CH::col(c) + c0, row0);
+                            tma_store_commit();
+                        }
+                    }
+                }
+            } else {
                 const int qi = i * ATT_TILE + r;
                 const bool q_ok = qi < loc.doc_len;
                 float* dst = p.dq_accum + (int64_t(head) * p.T + loc.doc_start + qi) * HD;
@@ -351,6 +387,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         // ---------------- dK_j, dV_j epilogue ----------------
         mbar_wait(dkv_full, 0, 27);
         tc_fence_after();
+        if (DQ_TMA && lane == 0) tma_store_wait_all<0>();  // shared memory must outlive the last dQ reduce
         __nv_bfloat16* krow = p.dqkv + int64_t(kv_row + r) * p.row_stride + k_col;
         __nv_bfloat16* vrow = p.dqkv + int64_t(kv_row + r) * p.row_stride + v_col;
 #pragma unroll 1
@@ -434,6 +471,15 @@ int launch_bwd(const void* dout, const void* qkv, int64_t row_stride, const BwdP
     constexpr int smem_bytes =
         1024 + (2 + 2 * QDO_STAGES) * CH::TILE_BYTES + 2 * ATT_TILE * 128 + 2 * ATT_TILE * 4 + 128;
     static_assert(smem_bytes <= 232448, "attention backward shared memory budget exceeded");
+    CUtensorMap tdq;
+    {
+        // dq_accum as [heads * T rows, HD columns] fp32; box = 32 columns x 32 rows (the staging slab of one warp)
+        uint64_t dims[2] = {uint64_t(HD), uint64_t(p.n_heads) * uint64_t(p.T)};
+        uint64_t strides[2] = {4, uint64_t(HD) * 4};
+        uint32_t box[2] = {HD >= 32 ? 32u : uint32_t(HD), 32};
+        rc = dolo_make_tmap(&tdq, p.dq_accum, 4, 2, dims, strides, box, HD >= 32 ? DOLO_SW_128 : DOLO_SW_64);
+        if (rc) return rc;
+    }
     auto kern = attn_bwd_kernel<HD>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -442,7 +488,7 @@ int launch_bwd(const void* dout, const void* qkv, int64_t row_stride, const BwdP
     }
     const int64_t max_tiles = (p.T + ATT_TILE - 1) / ATT_TILE + p.n_docs;
     dim3 grid((unsigned)max_tiles, (unsigned)p.n_groups);
-    kern<<<grid, BWD_THREADS, smem_bytes, st>>>(tq64, tqR, to64, toR, p);
+    kern<<<grid, BWD_THREADS, smem_bytes, st>>>(tq64, tqR, to64, toR, tdq, p);
     DOLO_LAUNCH_OK("attn_varlen_bwd");
     return DOLO_OK;
 }
@@ -470,6 +516,7 @@ extern "C" int dolomite_b200_attn_varlen_bwd(const void* dout, const void* qkv, 
     DOLO_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "attn_bwd: workspace must be 256-byte aligned");
     DOLO_REQUIRE(T < (1ll << 31), "attn_bwd: T too large");
     const int nh = n_groups * q_per_group;
+    DOLO_REQUIRE(int64_t(nh) * T < (1ll << 31), "attn_bwd: heads * T too large for the dQ tile reduce");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* delta = static_cast<float*>(workspace);
     float* dq_accum = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align256(int64_t(nh) * T * 4));

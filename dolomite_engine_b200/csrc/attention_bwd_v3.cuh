@@ -246,6 +246,11 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
             return 0.f;
         };
         float stat_next = fetch_stat(0);
+        uint32_t sv0[16], dv0[16];  // S^T / dP^T values of the NEXT half step's first sub-chunk (requested one step ahead)
+        mbar_wait(&sdp_full[0], 0, 36);
+        tc_fence_after();
+        tmem_ld16(t_lane + ST_COL + wg * COLS, sv0);
+        tmem_ld16(t_lane + DP_COL + wg * COLS, dv0);
 
         for (int it = 0; it < n_it; ++it) {
             const int s_head = it / n_i, i = j + (it - s_head * n_i);
@@ -321,15 +326,11 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
                 const int b = h;
-                mbar_wait(&sdp_full[b], uint32_t(it) & 1, 36);
-                tc_fence_after();
-                // software pipeline over the two 16-column sub-chunks: the TMEM loads of sub-chunk 1 are in flight while
-                // sub-chunk 0 is computed (tcgen05.ld latency was ~20 % of the softmax warps' time in the v3 ncu capture)
+                // sv0 / dv0 of this half step were requested one half step ago (or before the loop): the TMEM read latency and
+                // the wait for S^T / dP^T overlap the previous step's tcgen05.st drain, proxy fence and barrier arrive (ncu of the
+                // unpipelined loop: 10 % of the samples sat on `fence.proxy.async` + `mbarrier.arrive` behind those stores)
                 const uint32_t s_addr = t_lane + ST_COL + b * HALF + wg * COLS;
                 const uint32_t d_addr = t_lane + DP_COL + b * HALF + wg * COLS;
-                uint32_t sv0[16], dv0[16];
-                tmem_ld16(s_addr, sv0);
-                tmem_ld16(d_addr, dv0);
                 tmem_ld_wait();
                 reg_fence16(sv0);
                 reg_fence16(dv0);
@@ -344,6 +345,14 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
                     process16(sv1, dv1, h, b, 1);
                 } else {
                     process16(sv0, dv0, h, b, 0);
+                }
+                const int s_next = 2 * it + h + 1;
+                if (s_next < 2 * n_it) {  // request the first sub-chunk of the next half step (the other S^T / dP^T buffer)
+                    const int nb = s_next & 1;
+                    mbar_wait(&sdp_full[nb], uint32_t(s_next >> 1) & 1, 36);
+                    tc_fence_after();
+                    tmem_ld16(t_lane + ST_COL + nb * HALF + wg * COLS, sv0);
+                    tmem_ld16(t_lane + DP_COL + nb * HALF + wg * COLS, dv0);
                 }
                 tmem_st_wait();
                 tc_fence_before();

@@ -187,6 +187,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                  "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// rank-2 fp32 tile reduce-add (L2 performs the add; element type lives in the tensor map)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 // rank-3 tile store / fp32 reduce-add (the element type and the add live in the tensor map / the instruction): the third
 // coordinate selects the group of a grouped weight-gradient GEMM (0 for dense problems)
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
