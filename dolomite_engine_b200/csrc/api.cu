@@ -29,6 +29,8 @@ static int g_gemm_cta_pair = 1;
 static int g_gemm_sm_margin = 0;
 int dolo_option_gemm_sm_margin() { return g_gemm_sm_margin; }
 int dolo_option_gemm_cta_pair() { return g_gemm_cta_pair; }
+static int g_attn_fwd_split = 1;
+int dolo_option_attn_fwd_split() { return g_attn_fwd_split; }
 static int g_gemm_l2_hints = 1;
 int dolo_option_gemm_l2_hints() { return g_gemm_l2_hints; }
 static int g_gemm_f32_tma_epilogue = 0;
@@ -38,6 +40,10 @@ extern "C" int dolomite_b200_set_option(const char* key, int value) {
     if (key != nullptr && strcmp(key, "gemm_sm_margin") == 0) {
         DOLO_REQUIRE(value >= 0 && value <= 64, "gemm_sm_margin must be in [0, 64]");
         g_gemm_sm_margin = value;
+        return DOLO_OK;
+    }
+    if (key != nullptr && strcmp(key, "attn_fwd_split") == 0) {
+        g_attn_fwd_split = value != 0;
         return DOLO_OK;
     }
     if (key != nullptr && strcmp(key, "gemm_l2_hints") == 0) {

@@ -20,10 +20,10 @@
 // TMEM columns: S^T[2] 0..127, dP^T[2] 128..255, dV 256.., dK 256+HD.., dQ 256+2HD..  (<= 496 for HD = 80).
 #pragma once
 
-// K, V, 2 x (Q, dO), 2 x dS^T staging, LSE/Delta (2 x 2 x 128 floats), barriers, dQ reduce slab
+// K, V, 2 x (Q, dO), 2 x dS^T staging, dQ staging (4 warps x 2 swizzled 4 KB slabs), LSE/Delta (2 x 2 x 128 floats), barriers
 template <int HD>
 constexpr int bwd_v3_smem_need() {
-    return 6 * HeadChunks<HD>::TILE_BYTES + 2 * (2 * ATT_TILE * 128) + 4 * ATT_TILE * 4 + 160 + ATT_TILE * HD * 4;
+    return 6 * HeadChunks<HD>::TILE_BYTES + 2 * (2 * ATT_TILE * 128) + 4 * 2 * 4096 + 4 * ATT_TILE * 4 + 160;
 }
 
 // NG = number of softmax warp groups (4 warps each): every group owns 64 / NG query columns of a half step.  NG = 4
@@ -33,6 +33,7 @@ template <int HD, int NG>
 __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
     attn_bwd_kernel_v3(const __grid_constant__ CUtensorMap tq64, const __grid_constant__ CUtensorMap tqR,
                        const __grid_constant__ CUtensorMap to64, const __grid_constant__ CUtensorMap toR,
+                       const __grid_constant__ CUtensorMap tdq32, const __grid_constant__ CUtensorMap tdq16,
                        const BwdParams p) {
     using CH = HeadChunks<HD>;
     static_assert(256 + 3 * HD <= 512, "v2 needs a private dQ accumulator (head_dim <= 80)");
@@ -59,20 +60,14 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
     const int kv_row = loc.doc_start + j * ATT_TILE;
 
     extern __shared__ uint8_t smem_raw[];
-    // dQ staging slab (fp32 [128][HD], fed to the TMA reduce-add) makes head_dim 80 use the whole 227 KB: no alignment slack
-    // left, so the dynamic window itself must start 1024-byte aligned (it does: 1 KB driver reservation, no static smem)
-    constexpr bool TIGHT = bwd_v3_smem_need<HD>() + 1024 > 232448;
-    uint8_t* smem = TIGHT ? smem_raw : smem_align_1024(smem_raw);
-    if (TIGHT && (smem_u32(smem_raw) & 1023u) != 0) {
-        if (threadIdx.x == 0) printf("[dolomite_b200] attn_bwd_v3: dynamic shared memory base not 1024-byte aligned\n");
-        __trap();
-    }
+    uint8_t* smem = smem_align_1024(smem_raw);
     uint8_t* sK = smem;
     uint8_t* sV = sK + TILE_BYTES;
     uint8_t* sQ = sV + TILE_BYTES;             // [2]
     uint8_t* sDO = sQ + 2 * TILE_BYTES;        // [2]
     uint8_t* sDS = sDO + 2 * TILE_BYTES;       // [2] x DS_BYTES
-    float* sLSE = reinterpret_cast<float*>(sDS + 2 * DS_BYTES);  // [2][128] (log2 units)
+    uint8_t* sDQ = sDS + 2 * DS_BYTES;         // 4 drain warps x 2 slabs x 4 KB (32 rows x 32 fp32, 128B-swizzled; 1024-aligned)
+    float* sLSE = reinterpret_cast<float*>(sDQ + 4 * 2 * 4096);  // [2][128] (log2 units)
     float* sDelta = sLSE + 2 * ATT_TILE;                         // [2][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 2 * ATT_TILE);
     uint64_t* kv_full = bars;            // 1
@@ -84,13 +79,13 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
     uint64_t* dq_done = bars + 11;       // 128 arrivals: dQ accumulator drained
     uint64_t* dkv_full = bars + 12;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-    float* sDQ = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 160);  // [128][HD] fp32
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tq64);
         tma_prefetch_desc(&to64);
+        tma_prefetch_desc(&tdq32);
         mbar_init(kv_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&qdo_full[i], 1);
@@ -393,44 +388,64 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
         }
     } else {
         // ======================= dQ drain warps (2, 3, 12, 13): TMEM lane == query row =======================
-        // Each warp copies its 32 rows of the dQ accumulator to a private shared-memory slab and hands the slab to the
-        // TMA engine as ONE bulk fp32 reduce-add into dq_accum[head, q0 + 32*sub .., :] (contiguous in the [heads, T, HD]
-        // workspace).  The per-thread red.global.add.v4.f32 version spent 26 % of the kernel in L2 atomic traffic
-        // (profiles/r01_probe_call18_dq_bulk_reduce.jsonl: 1.88 ms -> 1.38 ms with the reductions removed).
+        // Each warp moves its 32 rows of the dQ accumulator through two private 4 KB slabs (32 rows x 32 fp32 columns, written
+        // in the 128-byte swizzle the TMA unit expects, so the stores are bank-conflict free) and hands every slab to the TMA
+        // engine as ONE tile reduce-add into dq_accum viewed as [heads * T, HD]; the L2 performs the adds.  History: per-thread
+        // red.global.add.v4.f32 cost 26 % of the kernel (profiles/r01_probe_call18_dq_bulk_reduce.jsonl); the first slab version
+        // was a linear [32][HD] block for a 1-D bulk reduce, whose 320-byte row pitch made every store a 4-way bank conflict
+        // (ncu call 71: 33 M of the kernel's 83 M shared-memory wavefronts were store replays).  Rows past the document add
+        // zeros (their dS is zero: lse = +inf), rows past the tensor are clipped by the TMA unit.
         const int sub = warp & 3;
         const uint32_t t_lane = tmem_base + (uint32_t(sub * 32) << 16);
-        float* slab = sDQ + (sub * 32) * HD;
-        float* my_row = slab + lane * HD;
-        const uint32_t slab_u32 = smem_u32(slab);
+        uint8_t* slab = sDQ + sub * (2 * 4096);
+        int nb = 0;
         for (int it = 0; it < n_it; ++it) {
             const int s_head = it / n_i, i = j + (it - s_head * n_i);
             const int head = group * p.q_per_group + s_head;
+            const int row0 = int(int64_t(head) * p.T + loc.doc_start + i * ATT_TILE + sub * 32);
             mbar_wait(&dq_full[it & 1], uint32_t(it >> 1) & 1, 38);
             tc_fence_after();
-            if (lane == 0) tma_store_wait_read<0>();  // the previous tile's reduce has finished reading the slab
-            __syncwarp();
 #pragma unroll 1
-            for (int c0 = 0; c0 < HD; c0 += 16) {
+            for (int c0 = 0; c0 + 32 <= HD; c0 += 32) {
+                uint8_t* buf = slab + (nb & 1) * 4096;
+                if (lane == 0) tma_store_wait_read<1>();  // the reduce issued from this slab two chunks ago has read it
+                __syncwarp();
+                uint32_t o[32];
+                tmem_ld32(t_lane + DQ_COL + c0, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<uint4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                        make_uint4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_reduce_add_2d(&tdq32, buf, c0, row0);
+                    tma_store_commit();
+                }
+                ++nb;
+            }
+            if constexpr (HD % 32 == 16) {  // last 16 columns: 64-byte rows, 64-byte swizzle
+                uint8_t* buf = slab + (nb & 1) * 4096;
+                if (lane == 0) tma_store_wait_read<1>();
+                __syncwarp();
                 uint32_t o[16];
-                tmem_ld16(t_lane + DQ_COL + c0, o);
+                tmem_ld16(t_lane + DQ_COL + (HD - 16), o);
                 tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<uint4*>(my_row + c0 + q * 4) = make_uint4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+                    *reinterpret_cast<uint4*>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+                        make_uint4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_reduce_add_2d(&tdq16, buf, HD - 16, row0);
+                    tma_store_commit();
+                }
+                ++nb;
             }
             tc_fence_before();
             mbar_arrive(dq_done);  // accumulator free for the next dQ MMA
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                const int q0 = i * ATT_TILE + sub * 32;
-                int rows = loc.doc_len - q0;
-                rows = rows > 32 ? 32 : rows;
-                if (rows > 0)
-                    bulk_reduce_add_f32(p.dq_accum + (int64_t(head) * p.T + loc.doc_start + q0) * HD, slab_u32,
-                                        uint32_t(rows) * HD * 4);
-                tma_store_commit();
-            }
         }
         if (lane == 0) tma_store_wait_all<0>();  // shared memory must outlive the last reduce
     }
@@ -451,8 +466,20 @@ int launch_bwd_v3(const void* dout, const void* qkv, int64_t row_stride, const B
     if (rc) return rc;
     rc = make_maps<HD>(dout, int64_t(p.n_heads) * HD, p.T, &to64, &toR);
     if (rc) return rc;
+    CUtensorMap tdq32, tdq16;
+    {
+        // dq_accum as [heads * T rows, HD columns] fp32; boxes = 32 rows x 32 (16) columns, the drain warps' slabs
+        uint64_t dims[2] = {uint64_t(HD), uint64_t(p.n_heads) * uint64_t(p.T)};
+        uint64_t strides[2] = {4, uint64_t(HD) * 4};
+        uint32_t box[2] = {32, 32};
+        rc = dolo_make_tmap(&tdq32, p.dq_accum, 4, 2, dims, strides, box, DOLO_SW_128);
+        if (rc) return rc;
+        box[0] = 16;
+        rc = dolo_make_tmap(&tdq16, p.dq_accum, 4, 2, dims, strides, box, DOLO_SW_64);
+        if (rc) return rc;
+    }
     constexpr int need = bwd_v3_smem_need<HD>();
-    constexpr int smem_bytes = (need + 1024 > 232448) ? need : need + 1024;
+    constexpr int smem_bytes = need + 1024;
     static_assert(smem_bytes <= 232448, "attention backward v3 shared memory budget exceeded");
     auto kern = attn_bwd_kernel_v3<HD, NG>;
     static bool attr_set = false;
@@ -462,7 +489,7 @@ int launch_bwd_v3(const void* dout, const void* qkv, int64_t row_stride, const B
     }
     const int64_t max_tiles = (p.T + ATT_TILE - 1) / ATT_TILE + p.n_docs;
     dim3 grid((unsigned)max_tiles, (unsigned)p.n_groups);
-    kern<<<grid, 32 * (6 + 4 * NG), smem_bytes, st>>>(tq64, tqR, to64, toR, p);
+    kern<<<grid, 32 * (6 + 4 * NG), smem_bytes, st>>>(tq64, tqR, to64, toR, tdq32, tdq16, p);
     DOLO_LAUNCH_OK("attn_varlen_bwd_v2");
     return DOLO_OK;
 }

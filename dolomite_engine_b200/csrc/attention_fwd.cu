@@ -329,6 +329,354 @@ __global__ void __launch_bounds__(FWD_THREADS)
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Split-softmax forward (head_dim >= 64).  ncu of the kernel above (profiles/r02_ncu_kernels_hd80_call70.txt): tensor pipe
+// 25 %, issue slots 36 %, the four softmax warps stalled on the dependent chain  S MMA -> TMEM load -> max -> exp -> TMEM
+// store -> fence -> arrive -> PV MMA -> S MMA of the next tile  (~5600 cycles per tile and CTA, hidden only by a second CTA
+// on the SM).  This kernel breaks the chain inside ONE CTA per SM:
+//   * S is double buffered in TMEM (columns 0-127 / 128-255, O behind them): the MMA warp issues S(j+1) = Q K_{j+1}^T BEFORE
+//     it waits for P(j), so the tensor pipe computes the next scores while the softmax warps work on the current ones;
+//   * EIGHT softmax warps: two threads per query row (same TMEM lanes, warps w and w+4), each owning 64 of the 128 key
+//     columns -- half the dependent work per thread and two warps per scheduler; the row maximum is exchanged through shared
+//     memory inside the warp pair (64-thread named barrier), row sums are only combined in the epilogue;
+//   * lazy reference maximum (threshold 2^8) so that O in TMEM is rescaled a handful of times per row.
+// P(j) (bf16) overwrites the S columns its own thread has consumed; the PV MMA reads it with one TMEM address per 16-key step.
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int FWD2_THREADS = 320;
+
+template <int HD>
+constexpr int fwd2_kv_stages() {
+    return (1024 + (1 + 2 * 3) * HeadChunks<HD>::TILE_BYTES + 4 * ATT_TILE * 4 + 256 <= 232448) ? 3 : 2;
+}
+
+template <int HD>
+__global__ void __launch_bounds__(FWD2_THREADS, 1)
+    attn_fwd_split_kernel(const __grid_constant__ CUtensorMap tmap64, const __grid_constant__ CUtensorMap tmapR,
+                          const FwdParams p) {
+    using CH = HeadChunks<HD>;
+    constexpr int TILE_BYTES = CH::TILE_BYTES;
+    constexpr int ST = fwd2_kv_stages<HD>();
+    constexpr uint32_t O_COL = 256;
+    constexpr int NCH16 = HD / 16;               // 16-column chunks of O
+    constexpr int CH_SPLIT = (NCH16 + 1) / 2;    // chunks [0, CH_SPLIT) belong to column group 0, the rest to group 1
+
+    const int ti = int(gridDim.x) - 1 - int(blockIdx.x);  // long (late) tiles first
+    const TileLoc loc = locate_tile(p.cu_seqlens, p.n_docs, ti);
+    if (!loc.valid) return;  // uniform for the whole CTA
+    const int head = blockIdx.y;
+    const int group = head / p.q_per_group, slot = head % p.q_per_group;
+    const int q_col = (group * (p.q_per_group + 2) + slot) * HD;
+    const int k_col = (group * (p.q_per_group + 2) + p.q_per_group) * HD;
+    const int v_col = k_col + HD;
+    const int q0 = loc.tile * ATT_TILE;
+    const int n_kv = loc.tile + 1;
+    const int row_base = loc.doc_start + q0;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_align_1024(smem_raw);
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + TILE_BYTES;            // [ST]
+    uint8_t* sV = sK + ST * TILE_BYTES;       // [ST]
+    float* xmax = reinterpret_cast<float*>(sV + ST * TILE_BYTES);  // [2 parities][2 groups][128]  row-max exchange
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xmax + 4 * ATT_TILE);
+    uint64_t* q_full = bars;                 // 1
+    uint64_t* kv_full = bars + 1;            // [ST]
+    uint64_t* kv_empty = bars + 1 + ST;      // [ST]
+    uint64_t* s_full = bars + 1 + 2 * ST;    // [2]  S buffer b holds the scores of tile j (b = j & 1)
+    uint64_t* p_ready = s_full + 2;          // [2]  256 arrivals: P written, O rescaled
+    uint64_t* pv_done = p_ready + 2;         // 1    commit after every PV: O is stable again
+    uint64_t* o_full = pv_done + 1;          // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        if (CH::NC64 > 0) tma_prefetch_desc(&tmap64);
+        if (CH::REM > 0) tma_prefetch_desc(&tmapR);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < ST; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_ready[i], 256);
+        }
+        mbar_init(pv_done, 1);
+        mbar_init(o_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto load_tile = [&](uint8_t* dst, uint64_t* bar, int col, int row) {
+#pragma unroll
+        for (int c = 0; c < CH::NCHUNK; ++c) {
+            const CUtensorMap* m = (c < CH::NC64) ? &tmap64 : &tmapR;
+            tma_load_2d(dst + CH::offset(c), m, bar, col + CH::col(c), row);
+        }
+    };
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(q_full, TILE_BYTES);
+            load_tile(sQ, q_full, q_col, row_base);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int j = 0; j < n_kv; ++j) {
+                mbar_wait(&kv_empty[stage], phase ^ 1, 50);
+                mbar_expect_tx(&kv_full[stage], 2 * TILE_BYTES);
+                const int krow = loc.doc_start + j * ATT_TILE;
+                load_tile(sK + stage * TILE_BYTES, &kv_full[stage], k_col, krow);
+                load_tile(sV + stage * TILE_BYTES, &kv_full[stage], v_col, krow);
+                if (++stage == ST) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, false, false);
+            mbar_wait(q_full, 0, 51);
+            const uint32_t q_s = smem_u32(sQ);
+            // S(jj) = Q K_jj^T into buffer jj & 1; K_jj lives in stage jj % ST (its barrier phase is (jj / ST) & 1)
+            auto issue_S = [&](int jj) {
+                const int stg = jj % ST;
+                mbar_wait(&kv_full[stg], uint32_t(jj / ST) & 1, 52);
+                tc_fence_after();
+                const uint32_t k_s = smem_u32(sK + stg * TILE_BYTES);
+                const uint32_t d = tmem_base + uint32_t(jj & 1) * 128;
+                bool first = true;
+#pragma unroll
+                for (int c = 0; c < CH::NCHUNK; ++c) {
+                    const int w = CH::width(c);
+#pragma unroll
+                    for (int k = 0; k < w / 16; ++k) {
+                        umma_ss(d, chunk_desc_kmajor(q_s + CH::offset(c), w, k), chunk_desc_kmajor(k_s + CH::offset(c), w, k),
+                                idesc_qk, first ? 0u : 1u);
+                        first = false;
+                    }
+                }
+                umma_commit(&s_full[jj & 1]);
+            };
+            issue_S(0);
+            if (n_kv > 1) issue_S(1);
+            for (int j = 0; j < n_kv; ++j) {
+                const int b = j & 1, stg = j % ST;
+                mbar_wait(&p_ready[b], uint32_t(j >> 1) & 1, 53);
+                tc_fence_after();
+                const uint32_t v_s = smem_u32(sV + stg * TILE_BYTES);
+#pragma unroll
+                for (int c = 0; c < CH::NCHUNK; ++c) {
+                    const int w = CH::width(c);
+                    const uint32_t idesc_pv = umma_idesc_bf16(128, w, false, true);
+#pragma unroll
+                    for (int k = 0; k < ATT_TILE / 16; ++k) {
+                        // P of keys [16k, 16k+16): written by column group k / 4 at its own offset (k % 4) * 8
+                        const uint32_t a_tmem = tmem_base + uint32_t(b) * 128 + uint32_t(k >> 2) * 64 + uint32_t(k & 3) * 8;
+                        umma_ts(tmem_base + O_COL + CH::col(c), a_tmem, chunk_desc_mnmajor(v_s + CH::offset(c), w, k), idesc_pv,
+                                (j > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&kv_empty[stg]);  // K_j (scores done long ago) and V_j are free
+                umma_commit(pv_done);
+                if (j == n_kv - 1) umma_commit(o_full);
+                if (j + 2 < n_kv) issue_S(j + 2);  // reuses buffer b: ordered behind PV(j) on the tensor pipe
+            }
+        }
+    } else {
+        // ---------------- softmax: two threads per query row, 64 key columns each ----------------
+        const int g = (warp - 2) >> 2;                 // column group
+        const int sub = warp & 3;                      // TMEM sub-partition of this warp (lanes 32 sub .. 32 sub + 31)
+        const int r = sub * 32 + lane;
+        const uint32_t t_lane = tmem_base + (uint32_t(sub * 32) << 16);
+        const int qi = q0 + r;
+        const uint32_t pair_bar = 1 + uint32_t(sub);   // named barrier of the two warps that share this row block
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < n_kv; ++j) {
+            const int b = j & 1;
+            const uint32_t s_col = t_lane + uint32_t(b) * 128 + uint32_t(g) * 64;
+            mbar_wait(&s_full[b], uint32_t(j >> 1) & 1, 54);
+            tc_fence_after();
+            const bool diag = (j == n_kv - 1);
+            const int kbase = j * ATT_TILE + g * 64;
+            uint32_t va[32], vb[32];
+            tmem_ld32(s_col, va);
+            tmem_ld32(s_col + 32, vb);
+            tmem_ld_wait();
+            reg_fence32(va);
+            reg_fence32(vb);
+            // ---- row maximum over my 64 columns, then over the pair ----
+            float mx = -INFINITY, mx1 = -INFINITY;
+            if (!diag) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    mx = fmax3(mx, __uint_as_float(va[i]), __uint_as_float(va[i + 1]));
+                    mx1 = fmax3(mx1, __uint_as_float(va[i + 2]), __uint_as_float(va[i + 3]));
+                    mx = fmax3(mx, __uint_as_float(vb[i]), __uint_as_float(vb[i + 1]));
+                    mx1 = fmax3(mx1, __uint_as_float(vb[i + 2]), __uint_as_float(vb[i + 3]));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (kbase + i <= qi) mx = fmaxf(mx, __uint_as_float(va[i]));
+                    if (kbase + 32 + i <= qi) mx1 = fmaxf(mx1, __uint_as_float(vb[i]));
+                }
+            }
+            mx = fmaxf(mx, mx1);
+            float* xm = xmax + (b * 2) * ATT_TILE;  // parity-buffered: the partner may still read the previous tile's value
+            xm[g * ATT_TILE + r] = mx;
+            named_bar_sync(pair_bar, 64);
+            mx = fmaxf(fmaxf(mx, xm[(1 - g) * ATT_TILE + r]), m_run);
+            // lazy reference maximum (see attn_fwd_kernel): identical in both threads of the row
+            const bool move_ref = (m_run == -INFINITY) || (mx * p.scale_log2 > m_run * p.scale_log2 + 8.f);
+            const float m_new = move_ref ? mx : m_run;
+            const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
+            const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run * p.scale_log2 - m_scaled);
+            if (j > 0) {
+                mbar_wait(pv_done, uint32_t(j - 1) & 1, 55);  // PV(j-1) has retired: O may be rescaled, P(j) may be handed over
+                tc_fence_after();
+                if (!__all_sync(0xffffffffu, alpha == 1.f)) {
+#pragma unroll 1
+                    for (int c = (g == 0 ? 0 : CH_SPLIT); c < (g == 0 ? CH_SPLIT : NCH16); ++c) {
+                        uint32_t o[16];
+                        tmem_ld16(t_lane + O_COL + c * 16, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st16(t_lane + O_COL + c * 16, o);
+                    }
+                }
+            }
+            // ---- P = exp2(s * scale - m), row sum over my columns; bf16 P overwrites my own consumed S columns ----
+            float lsum = 0.f, lsum1 = 0.f;
+            const float neg_m = -m_scaled;
+            uint32_t pk[16];
+            if (!diag) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float x0, x1;
+                    ffma2_bcast(x0, x1, __uint_as_float(va[i]), __uint_as_float(va[i + 1]), p.scale_log2, neg_m);
+                    const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+                    fadd2(lsum, lsum1, p0, p1);
+                    pk[i >> 1] = pack_bf16(p0, p1);
+                }
+                tmem_st16(s_col, pk);
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float x0, x1;
+                    ffma2_bcast(x0, x1, __uint_as_float(vb[i]), __uint_as_float(vb[i + 1]), p.scale_log2, neg_m);
+                    const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+                    fadd2(lsum, lsum1, p0, p1);
+                    pk[i >> 1] = pack_bf16(p0, p1);
+                }
+                tmem_st16(s_col + 16, pk);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float p0 = fast_exp2(fmaf(__uint_as_float(va[i]), p.scale_log2, neg_m));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(va[i + 1]), p.scale_log2, neg_m));
+                    if (kbase + i > qi) p0 = 0.f;
+                    if (kbase + i + 1 > qi) p1 = 0.f;
+                    lsum += p0;
+                    lsum1 += p1;
+                    pk[i >> 1] = pack_bf16(p0, p1);
+                }
+                tmem_st16(s_col, pk);
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float p0 = fast_exp2(fmaf(__uint_as_float(vb[i]), p.scale_log2, neg_m));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(vb[i + 1]), p.scale_log2, neg_m));
+                    if (kbase + 32 + i > qi) p0 = 0.f;
+                    if (kbase + 32 + i + 1 > qi) p1 = 0.f;
+                    lsum += p0;
+                    lsum1 += p1;
+                    pk[i >> 1] = pack_bf16(p0, p1);
+                }
+                tmem_st16(s_col + 16, pk);
+            }
+            l_run = l_run * alpha + (lsum + lsum1);
+            m_run = m_new;
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_ready[b]);
+        }
+        // ---------------- epilogue: combine the two partial row sums, each thread stores its half of the O columns ----------------
+        mbar_wait(o_full, 0, 56);
+        tc_fence_after();
+        float* xs = xmax + ((n_kv & 1) * 2) * ATT_TILE;  // the parity buffer the last tile did not use
+        xs[g * ATT_TILE + r] = l_run;
+        named_bar_sync(pair_bar, 64);
+        const float l_tot = l_run + xs[(1 - g) * ATT_TILE + r];
+        const bool row_ok = qi < loc.doc_len;
+        const float inv_l = l_tot > 0.f ? 1.f / l_tot : 0.f;
+        __nv_bfloat16* orow = p.out + int64_t(row_base + r) * (int64_t(p.n_heads) * HD) + int64_t(head) * HD;
+#pragma unroll 1
+        for (int c = (g == 0 ? 0 : CH_SPLIT); c < (g == 0 ? CH_SPLIT : NCH16); ++c) {
+            uint32_t o[16];
+            tmem_ld16(t_lane + O_COL + c * 16, o);
+            tmem_ld_wait();
+            if (row_ok) {
+                uint4 a, b4;
+                a.x = pack_bf16(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l);
+                a.y = pack_bf16(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l);
+                a.z = pack_bf16(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l);
+                a.w = pack_bf16(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l);
+                b4.x = pack_bf16(__uint_as_float(o[8]) * inv_l, __uint_as_float(o[9]) * inv_l);
+                b4.y = pack_bf16(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l);
+                b4.z = pack_bf16(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l);
+                b4.w = pack_bf16(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l);
+                *reinterpret_cast<uint4*>(orow + c * 16) = a;
+                *reinterpret_cast<uint4*>(orow + c * 16 + 8) = b4;
+            }
+        }
+        if (g == 0 && row_ok) p.lse[int64_t(head) * p.T + row_base + r] = m_run * p.scale + logf(l_tot);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+template <int HD>
+int launch_fwd_split(const void* qkv, int64_t row_stride, const FwdParams& p, cudaStream_t st) {
+    using CH = HeadChunks<HD>;
+    CUtensorMap t64, tR;
+    uint64_t dims[2] = {uint64_t(row_stride), uint64_t(p.T)};
+    uint64_t strides[2] = {2, uint64_t(row_stride) * 2};
+    uint32_t box[2] = {64, ATT_TILE};
+    int rc;
+    if (CH::NC64 > 0) {
+        rc = dolo_make_tmap(&t64, qkv, 2, 2, dims, strides, box, DOLO_SW_128);
+        if (rc) return rc;
+    }
+    if (CH::REM > 0) {
+        box[0] = CH::REM;
+        rc = dolo_make_tmap(&tR, qkv, 2, 2, dims, strides, box, CH::REM == 32 ? DOLO_SW_64 : DOLO_SW_32);
+        if (rc) return rc;
+    }
+    if (CH::NC64 == 0) t64 = tR;
+    if (CH::REM == 0) tR = t64;
+    constexpr int ST = fwd2_kv_stages<HD>();
+    constexpr int smem_bytes = 1024 + (1 + 2 * ST) * CH::TILE_BYTES + 4 * ATT_TILE * 4 + 256;
+    static_assert(smem_bytes <= 232448, "attention forward (split softmax) shared memory budget exceeded");
+    auto kern = attn_fwd_split_kernel<HD>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DOLO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        attr_set = true;
+    }
+    const int64_t max_tiles = (p.T + ATT_TILE - 1) / ATT_TILE + p.n_docs;
+    dim3 grid((unsigned)max_tiles, (unsigned)p.n_heads);
+    kern<<<grid, FWD2_THREADS, smem_bytes, st>>>(t64, tR, p);
+    DOLO_LAUNCH_OK("attn_varlen_fwd_split");
+    return DOLO_OK;
+}
+
 template <int HD>
 int launch_fwd(const void* qkv, int64_t row_stride, const FwdParams& p, int max_seqlen, cudaStream_t st) {
     using CH = HeadChunks<HD>;
@@ -388,13 +736,14 @@ extern "C" int dolomite_b200_attn_varlen_fwd(const void* qkv, int64_t row_stride
     p.scale = softmax_scale;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool split = dolo_option_attn_fwd_split() != 0;
     switch (head_dim) {
         case 16: return launch_fwd<16>(qkv, row_stride, p, max_seqlen, st);
         case 32: return launch_fwd<32>(qkv, row_stride, p, max_seqlen, st);
-        case 64: return launch_fwd<64>(qkv, row_stride, p, max_seqlen, st);
-        case 80: return launch_fwd<80>(qkv, row_stride, p, max_seqlen, st);
-        case 96: return launch_fwd<96>(qkv, row_stride, p, max_seqlen, st);
-        case 128: return launch_fwd<128>(qkv, row_stride, p, max_seqlen, st);
+        case 64: return split ? launch_fwd_split<64>(qkv, row_stride, p, st) : launch_fwd<64>(qkv, row_stride, p, max_seqlen, st);
+        case 80: return split ? launch_fwd_split<80>(qkv, row_stride, p, st) : launch_fwd<80>(qkv, row_stride, p, max_seqlen, st);
+        case 96: return split ? launch_fwd_split<96>(qkv, row_stride, p, st) : launch_fwd<96>(qkv, row_stride, p, max_seqlen, st);
+        case 128: return split ? launch_fwd_split<128>(qkv, row_stride, p, st) : launch_fwd<128>(qkv, row_stride, p, max_seqlen, st);
         default: return dolo_set_error("attn_fwd: unsupported head_dim %d (supported: 16,32,64,80,96,128)", head_dim);
     }
 }

@@ -694,6 +694,15 @@ def _attn_bench(S, B, nh, hd):
     ms = _time(lambda: k.attn_varlen_fwd(qkv, cu, S, nh, 1, hd, scale, out=out), iters=10)
     res["fwd_ms"] = ms
     res["fwd_tflops_causal"] = flops_fwd / ms / 1e9
+    if hd >= 64:  # A/B: the single-buffer forward (two CTAs per SM) against the default split-softmax forward
+        k.set_option("attn_fwd_split", 0)
+        out1, lse1 = k.attn_varlen_fwd(qkv, cu, S, nh, 1, hd, scale)
+        res["single_buffer_vs_flash_fwd"] = _err(out1, fo.reshape(T, -1))
+        res["lse_split_vs_single_max_abs"] = float((lse - lse1).abs().max())
+        ms1 = _time(lambda: k.attn_varlen_fwd(qkv, cu, S, nh, 1, hd, scale, out=out1), iters=10)
+        res["single_buffer_fwd_ms"] = ms1
+        res["single_buffer_fwd_tflops_causal"] = flops_fwd / ms1 / 1e9
+        k.set_option("attn_fwd_split", 1)
     ms_f = _time(lambda: flash_attn_varlen_func(q, kk, vv, cu, cu, S, S, 0.0, softmax_scale=scale, causal=True), iters=10)
     res["flash_fwd_ms"] = ms_f
     res["flash_fwd_tflops_causal"] = flops_fwd / ms_f / 1e9
