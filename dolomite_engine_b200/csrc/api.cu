@@ -43,7 +43,7 @@ extern "C" int dolomite_b200_set_option(const char* key, int value) {
         return DOLO_OK;
     }
     if (key != nullptr && strcmp(key, "attn_fwd_split") == 0) {
-        g_attn_fwd_split = value != 0;
+        g_attn_fwd_split = value;
         return DOLO_OK;
     }
     if (key != nullptr && strcmp(key, "gemm_l2_hints") == 0) {

@@ -219,7 +219,10 @@ __global__ void __launch_bounds__(FWD_THREADS)
             const bool move_ref = (m_run == -INFINITY) || (mx * p.scale_log2 > m_run * p.scale_log2 + 8.f);
             const float m_new = move_ref ? mx : m_run;
             const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
-            const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run * p.scale_log2 - m_scaled);
+            // (alpha must be EXACTLY 1 when the reference stays: `m_run * scale - m_scaled` contracts to an FMA whose result is the
+            //  rounding error of the product, not 0 -- the ncu capture of call 73 showed the "skipped" rescale running on 93 %
+            //  of the tiles for that reason)
+            const float alpha = !move_ref ? 1.f : ((m_run == -INFINITY) ? 0.f : fast_exp2(m_run * p.scale_log2 - m_scaled));
             // rescale O (previous PV has completed: s_full is committed after it); skipped when no row of this
             // warp raised its running max (alpha == 1 everywhere), which is the common case after the first tiles
             if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.f)) {
@@ -533,7 +536,10 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1)
             const bool move_ref = (m_run == -INFINITY) || (mx * p.scale_log2 > m_run * p.scale_log2 + 8.f);
             const float m_new = move_ref ? mx : m_run;
             const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
-            const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run * p.scale_log2 - m_scaled);
+            // (alpha must be EXACTLY 1 when the reference stays: `m_run * scale - m_scaled` contracts to an FMA whose result is the
+            //  rounding error of the product, not 0 -- the ncu capture of call 73 showed the "skipped" rescale running on 93 %
+            //  of the tiles for that reason)
+            const float alpha = !move_ref ? 1.f : ((m_run == -INFINITY) ? 0.f : fast_exp2(m_run * p.scale_log2 - m_scaled));
             if (j > 0) {
                 mbar_wait(pv_done, uint32_t(j - 1) & 1, 55);  // PV(j-1) has retired: O may be rescaled, P(j) may be handed over
                 tc_fence_after();
@@ -736,12 +742,14 @@ extern "C" int dolomite_b200_attn_varlen_fwd(const void* qkv, int64_t row_stride
     p.scale = softmax_scale;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool split = dolo_option_attn_fwd_split() != 0;
+    const int split = dolo_option_attn_fwd_split();
     switch (head_dim) {
         case 16: return launch_fwd<16>(qkv, row_stride, p, max_seqlen, st);
         case 32: return launch_fwd<32>(qkv, row_stride, p, max_seqlen, st);
-        case 64: return split ? launch_fwd_split<64>(qkv, row_stride, p, st) : launch_fwd<64>(qkv, row_stride, p, max_seqlen, st);
-        case 80: return split ? launch_fwd_split<80>(qkv, row_stride, p, st) : launch_fwd<80>(qkv, row_stride, p, max_seqlen, st);
+        // head_dim 64 / 80: the single-buffer kernel fits two CTAs per SM, which overlap each other; measured faster than the
+        // split kernel there (call 73: 0.323 vs 0.370 ms at hd 80) unless "attn_fwd_split" is set to 2
+        case 64: return split >= 2 ? launch_fwd_split<64>(qkv, row_stride, p, st) : launch_fwd<64>(qkv, row_stride, p, max_seqlen, st);
+        case 80: return split >= 2 ? launch_fwd_split<80>(qkv, row_stride, p, st) : launch_fwd<80>(qkv, row_stride, p, max_seqlen, st);
         case 96: return split ? launch_fwd_split<96>(qkv, row_stride, p, st) : launch_fwd<96>(qkv, row_stride, p, max_seqlen, st);
         case 128: return split ? launch_fwd_split<128>(qkv, row_stride, p, st) : launch_fwd<128>(qkv, row_stride, p, max_seqlen, st);
         default: return dolo_set_error("attn_fwd: unsupported head_dim %d (supported: 16,32,64,80,96,128)", head_dim);

@@ -45,7 +45,7 @@ int dolo_option_gemm_sm_margin();
 // 128-byte row segments.  Measured on the four weight gradients of a C2 block (profiles/r02_probe_call70.jsonl): the TMA
 // path is 5 % (reduce-add) to 13 % (store) SLOWER -- 32 extra TMA operations per tile share the queue of the operand loads.
 int dolo_option_gemm_f32_tma_epilogue();
-int dolo_option_attn_fwd_split();  // 1 (default) = split-softmax forward with double-buffered S for head_dim >= 64
+int dolo_option_attn_fwd_split();  // 0 never / 1 (default) head_dim >= 96 / 2 also head_dim 64, 80: split-softmax forward
 int dolo_option_gemm_l2_hints();  // 1 (default) = evict-first / evict-last operand loads for long-contraction GEMMs
 
 // TMA descriptor encode through the driver entry point (no link-time libcuda dependency).

@@ -39,8 +39,8 @@ int dolomite_b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* process-wide tuning knobs:
  *   "gemm_cta_pair"    0 | 1 (dense GEMMs on 2-CTA clusters with tcgen05.mma.cta_group::2)
  *   "gemm_sm_margin"   SMs the persistent GEMM grids leave free for concurrent communication kernels
- *   "attn_fwd_split"   1 | 0 (attention forward for head_dim >= 64: one CTA per SM with double-buffered scores in TMEM and
- *                      two threads per query row, or the single-buffer kernel with two CTAs per SM)
+ *   "attn_fwd_split"   1 | 0 | 2 (split-softmax attention forward -- one CTA per SM, double-buffered scores in TMEM, two threads
+ *                      per query row -- for head_dim >= 96 (1, default), never (0), or also for head_dim 64 / 80 (2))
  *   "gemm_l2_hints"    1 | 0 (long-contraction GEMMs load the streamed operand evict-first and the re-used one evict-last)
  *   "gemm_f32_tma_epilogue" 0 | 1 (fp32 weight gradients through TMA tile store / reduce-add instead of per-thread stores) */
 int dolomite_b200_set_option(const char* key, int value);

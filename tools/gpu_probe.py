@@ -694,7 +694,13 @@ def _attn_bench(S, B, nh, hd):
     ms = _time(lambda: k.attn_varlen_fwd(qkv, cu, S, nh, 1, hd, scale, out=out), iters=10)
     res["fwd_ms"] = ms
     res["fwd_tflops_causal"] = flops_fwd / ms / 1e9
-    if hd >= 64:  # A/B: the single-buffer forward (two CTAs per SM) against the default split-softmax forward
+    if hd >= 64:  # A/B: the single-buffer forward (two CTAs per SM) against the split-softmax forward
+        k.set_option("attn_fwd_split", 2)
+        out, lse = k.attn_varlen_fwd(qkv, cu, S, nh, 1, hd, scale)
+        res["split_vs_flash_fwd"] = _err(out, fo.reshape(T, -1))
+        ms2 = _time(lambda: k.attn_varlen_fwd(qkv, cu, S, nh, 1, hd, scale, out=out), iters=10)
+        res["split_fwd_ms"] = ms2
+        res["split_fwd_tflops_causal"] = flops_fwd / ms2 / 1e9
         k.set_option("attn_fwd_split", 0)
         out1, lse1 = k.attn_varlen_fwd(qkv, cu, S, nh, 1, hd, scale)
         res["single_buffer_vs_flash_fwd"] = _err(out1, fo.reshape(T, -1))
