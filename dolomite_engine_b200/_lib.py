@@ -72,6 +72,7 @@ SIGNATURES: dict[str, tuple] = {
     "dolomite_b200_moe_token_sum": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "dolomite_b200_moe_router_bwd": (_I, [_P, _P, _P, _P, _L, _I, _I, _P]),
     "dolomite_b200_attn_varlen_fwd": (_I, [_P, _L, _P, _P, _P, _I, _L, _I, _I, _I, _I, _F, _P]),
+    "dolomite_b200_attn_decode": (_I, [_P, _L, _P, _P, _P, _P, _I, _L, _I, _I, _I, _F, _P]),
     "dolomite_b200_attn_varlen_bwd_workspace_bytes": (_L, [_L, _I, _I, _I]),
     "dolomite_b200_attn_varlen_bwd": (
         _I,

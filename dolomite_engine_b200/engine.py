@@ -118,6 +118,18 @@ class FlatUnit:
         return full
 
 
+class KVCache:
+    """keys / values of every layer by position: k[l], v[l] bf16 [batch, max_len, n_kv_groups * head_dim]; lens int32 [batch]"""
+
+    def __init__(self, engine: "DolomiteEngine", batch: int, max_len: int):
+        dim = engine.n_groups * engine.hd
+        mk = lambda: torch.zeros(batch, max_len, dim, dtype=torch.bfloat16, device=engine.device)  # noqa: E731
+        self.k = [mk() for _ in range(engine.cfg.n_layer)]
+        self.v = [mk() for _ in range(engine.cfg.n_layer)]
+        self.lens = torch.zeros(batch, dtype=torch.int32, device=engine.device)
+        self.max_len = max_len
+
+
 def _block_specs(cfg: CommonConfig, i: int) -> list[tuple[str, tuple, str]]:
     """parameters of GPTDolomiteBlock i in registration order (layer.py:33-47, attention/base.py:73-86, mlp.py:26-41)"""
     H, F = cfg.n_embd, cfg.n_inner
@@ -252,6 +264,7 @@ class DolomiteEngine:
         self.head_chunk_bytes = 1 << 30  # bf16 logits of one LM-head chunk (forward(fuse_head_loss=True))
         self.batch_block_wgrads = True  # the four weight gradients of a dense block in one persistent launch
         self._deferred_wgrads: list | None = None  # list while a block's backward collects its weight gradients
+        self._kv_sink = None  # callable(layer, packed qkv) while a forward fills a KV cache (prefill)
         self._fresh_grads: set[str] = set()  # weights whose gradient buffer will be overwritten by the next wgrad GEMM
         if cfg.attention_multiplier is not None:
             self.softmax_scale = float(cfg.attention_multiplier)
@@ -418,6 +431,8 @@ class DolomiteEngine:
         qkv = K.gemm(ln1, u.views[p + "attn.c_attn.weight"], bias=u.views.get(p + "attn.c_attn.bias"))
         if self.rope_cos is not None:
             K.rope_qk_inplace(qkv, self.n_groups, self.q_per_group, self.hd, self.rope_cos, self.rope_sin, position_ids)
+        if self._kv_sink is not None:  # prefill of a KV cache: keys (rotated) and values of every prompt token
+            self._kv_sink(i, qkv)
         attn, lse = K.attn_varlen_fwd(qkv, cu_seqlens, max_seqlen, self.n_groups, self.q_per_group, self.hd, self.softmax_scale)
         h_mid = K.gemm(attn, u.views[p + "attn.c_proj.weight"], bias=u.views.get(p + "attn.c_proj.bias"), c=x_in,
                        alpha=m_res, beta=1.0)
@@ -509,6 +524,85 @@ class DolomiteEngine:
         n_chunks = -(-T // max_rows)
         per = -(-T // n_chunks)
         return min(T, -(-per // 8) * 8)
+
+    # ------------------------------------------------------------------------------------------
+    # decoding with a KV cache (attention/sdpa.py:11-83, attention/flash.py:16-140 `past_key_values`)
+    # ------------------------------------------------------------------------------------------
+    def kv_slices(self, qkv):
+        """(k, v) views [T, n_groups, head_dim] of a packed c_attn output (slot layout of attention/padding_free.py:79-116)"""
+        T = qkv.shape[0]
+        slots = qkv.view(T, self.n_groups, self.q_per_group + 2, self.hd)
+        return slots[:, :, self.q_per_group], slots[:, :, self.q_per_group + 1]
+
+    @torch.no_grad()
+    def prefill(self, input_ids, position_ids, cu_seqlens, max_seqlen: int, cache: "KVCache", n_sequences: int | None = None):
+        """packed forward over the prompts (document b = sequence b for b < n_sequences; later documents, e.g. the alignment
+        dummy of `_pad_packed_stream`, are run but not cached) that also fills `cache`; -> logits [T, V]"""
+        cu = cu_seqlens.tolist()
+        if n_sequences is not None:
+            cu = cu[: n_sequences + 1]
+
+        def sink(layer: int, qkv) -> None:
+            k, v = self.kv_slices(qkv)
+            for b in range(len(cu) - 1):
+                n = cu[b + 1] - cu[b]
+                cache.k[layer][b, :n].copy_(k[cu[b] : cu[b + 1]].reshape(n, -1))
+                cache.v[layer][b, :n].copy_(v[cu[b] : cu[b + 1]].reshape(n, -1))
+
+        self._kv_sink = sink
+        try:
+            logits, _ = self.forward(input_ids, position_ids, cu_seqlens, max_seqlen, save_for_backward=False)
+        finally:
+            self._kv_sink = None
+        cache.lens.copy_(torch.tensor([cu[b + 1] - cu[b] for b in range(len(cu) - 1)], dtype=torch.int32))
+        return logits
+
+    @torch.no_grad()
+    def decode_step(self, input_ids, cache: "KVCache", active=None):
+        """one new token per sequence: input_ids int64 [B]; appends its keys / values at position cache.lens[b] (sequences
+        with active[b] == False are computed but their cache does not advance) -> logits [B, V].  Every op is the training
+        kernel at T = B rows, except attention, which is the single-query cache kernel (csrc/attention_decode.cu)."""
+        cfg = self.cfg
+        if self.comm is not None:
+            raise NotImplementedError("decoding runs on an unsharded engine (world_size 1)")
+        B = input_ids.numel()
+        root = self.units[0]
+        pos = cache.lens.long()  # position of the new token = tokens already cached
+        rows = torch.arange(B, device=self.device)
+        h = K.embedding_fwd(input_ids, root.views["transformer.wte.weight"], 1.0 if cfg.m_emb is None else float(cfg.m_emb))
+        if self.learned_positions:
+            h = K.add_scaled(h, K.embedding_fwd(pos, root.views["transformer.wpe.weight"], 1.0), 1.0)
+        self._ensure_rope(int(cache.k[0].shape[1]))
+        m_res = 1.0 if cfg.m_residual is None else float(cfg.m_residual)
+        lens_incl = (cache.lens + 1).contiguous()
+        for i in range(cfg.n_layer):
+            u = self.units[i + 1]
+            p = f"transformer.h.{i}."
+            ln1, _ = self._norm_fwd(h, u, p + "ln_1.")
+            qkv = K.gemm(ln1, u.views[p + "attn.c_attn.weight"], bias=u.views.get(p + "attn.c_attn.bias"))
+            if self.rope_cos is not None:
+                K.rope_qk_inplace(qkv, self.n_groups, self.q_per_group, self.hd, self.rope_cos, self.rope_sin, pos)
+            k_new, v_new = self.kv_slices(qkv)
+            cache.k[i][rows, pos] = k_new.reshape(B, -1)
+            cache.v[i][rows, pos] = v_new.reshape(B, -1)
+            attn = K.attn_decode(qkv, cache.k[i], cache.v[i], lens_incl, self.n_groups, self.q_per_group, self.hd, self.softmax_scale)
+            h_mid = K.gemm(attn, u.views[p + "attn.c_proj.weight"], bias=u.views.get(p + "attn.c_proj.bias"), c=h, alpha=m_res,
+                           beta=1.0)
+            ln2, _ = self._norm_fwd(h_mid, u, p + "ln_2.")
+            if self.is_moe:
+                from . import moe
+
+                h, _ = moe.forward(self, u, p, ln2, h_mid, m_res)
+            else:
+                fc = K.gemm(ln2, u.views[p + "mlp.c_fc.weight"], bias=u.views.get(p + "mlp.c_fc.bias"))
+                act = K.swiglu_fwd(fc) if self.is_glu else K.gelu_fwd(fc)
+                h = K.gemm(act, u.views[p + "mlp.c_proj.weight"], bias=u.views.get(p + "mlp.c_proj.bias"), c=h_mid, alpha=m_res,
+                           beta=1.0)
+        hf, _ = self._norm_fwd(h, root, "transformer.ln_f.")
+        head = root.views["transformer.wte.weight"] if cfg.tie_word_embeddings else root.views["lm_head.weight"]
+        logits = K.gemm(hf, head, alpha=1.0 if cfg.m_width is None else 1.0 / float(cfg.m_width))
+        cache.lens.add_(1 if active is None else active.to(torch.int32))
+        return logits
 
     # ------------------------------------------------------------------------------------------
     # backward

@@ -2,10 +2,11 @@
 **generate_kwargs, eos_token_id=...)` as called by model_wrapper/base.py:110-136 with the GenerationParameters of
 arguments.py: max_new_tokens, do_sample, temperature, top_k, top_p).
 
-No KV cache: every new token re-runs the packed forward (no activations kept) over the unpadded rows and reads the
-logits of each row's last token.  That is exact -- the same kernels as training, so greedy decoding reproduces
-`argmax(forward(prefix))` token by token -- but costs O(L^2) GEMM work per sequence; a decode attention kernel with a
-paged cache is the B200-native replacement and is not built.
+`use_cache=True` (default, like HuggingFace): the prompts are packed as documents and run ONCE through the training
+forward, which also fills a KV cache (`engine.prefill`); every further token is one `engine.decode_step` -- the training
+kernels at T = batch rows plus the single-query cache attention kernel (csrc/attention_decode.cu) -- i.e. O(L) work per token.
+`use_cache=False` re-runs the packed forward over the whole prefix for every token (exact by construction, O(L^2) per sequence;
+the cached path is checked against it on the GPU).
 """
 
 from __future__ import annotations
@@ -52,6 +53,33 @@ def last_token_logits(model, input_ids: torch.Tensor, attention_mask: torch.Tens
 
 
 @torch.no_grad()
+def _prefill(model, input_ids: torch.Tensor, attention_mask: torch.Tensor, max_new_tokens: int):
+    """packed forward over the (left padded) prompts that fills a KV cache -> (fp32 [B, V] logits of the last prompt tokens, cache)"""
+    from ..engine import KVCache
+    from .modeling import _pad_packed_stream
+
+    eng = model.engine
+    dev = eng.device
+    mask = attention_mask.to(dev).bool()
+    lens = mask.sum(1)
+    lens_host = lens.tolist()
+    if min(lens_host) < 1:
+        raise ValueError("generate: every prompt needs at least one token")
+    keep = mask.reshape(-1).nonzero(as_tuple=True)[0]
+    ids = input_ids.to(dev).long().reshape(-1)[keep].contiguous()
+    pos = (mask.long().cumsum(-1) - 1).clamp_(min=0).reshape(-1)[keep].contiguous()
+    cu = torch.zeros(len(lens_host) + 1, dtype=torch.int32, device=dev)
+    cu[1:] = lens.cumsum(0)
+    last = (cu[1:] - 1).long()
+    B = len(lens_host)
+    cache = KVCache(eng, B, max(lens_host) + max_new_tokens + 8)
+    # (the packed stream may carry a trailing dummy document that rounds the token count up to 8: it is not cached)
+    ids_p, pos_p, cu_p, _, _ = _pad_packed_stream(ids, pos, cu, None)
+    logits = eng.prefill(ids_p, pos_p, cu_p, int(max(lens_host)), cache, n_sequences=B)
+    return logits[last].float(), cache
+
+
+@torch.no_grad()
 def generate(model, input_ids: torch.Tensor, attention_mask: torch.Tensor | None = None, max_new_tokens: int = 20,
              do_sample: bool = False, temperature: float | None = None, top_k: int | None = None, top_p: float | None = None,
              eos_token_id: int | None = None, pad_token_id: int | None = None, generator: torch.Generator | None = None,
@@ -70,10 +98,18 @@ def generate(model, input_ids: torch.Tensor, attention_mask: torch.Tensor | None
     B = ids.shape[0]
     finished = torch.zeros(B, dtype=torch.bool, device=dev)
     limit = getattr(model.config, "n_positions", None)
-    for _ in range(int(max_new_tokens)):
+    use_cache = unused.get("use_cache", True) is not False and model.engine.comm is None
+    cache = None
+    for step in range(int(max_new_tokens)):
         if limit is not None and model.engine.learned_positions and int(mask.sum(1).max()) >= limit:
             break  # learned absolute positions end at n_positions
-        logits = last_token_logits(model, ids, mask)
+        if not use_cache:
+            logits = last_token_logits(model, ids, mask)
+        elif cache is None:
+            logits, cache = _prefill(model, ids, mask, int(max_new_tokens))
+        else:
+            logits = model.engine.decode_step(ids[:, -1].contiguous(), cache, active=~was_finished).float()
+        was_finished = finished.clone()
         if do_sample:
             probs = _filter_logits(logits, temperature, top_k, top_p).softmax(-1)
             nxt = torch.multinomial(probs, 1, generator=generator).squeeze(1)

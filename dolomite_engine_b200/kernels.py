@@ -377,6 +377,19 @@ def attn_varlen_bwd(dout, qkv, out, lse, cu_seqlens, max_seqlen, n_groups, q_per
     return dqkv
 
 
+def attn_decode(qkv, k_cache, v_cache, lens, n_groups: int, q_per_group: int, head_dim: int, scale: float):
+    """one new token per sequence against its KV cache: qkv [B, qkv_dim] (roped), caches [B, L_max, n_groups * head_dim], lens
+    int32 [B] (valid positions including the new token) -> [B, n_heads * head_dim]"""
+    _req(qkv, _BF16, "qkv"), _req(k_cache, _BF16, "k_cache"), _req(v_cache, _BF16, "v_cache"), _req(lens, torch.int32, "lens")
+    B = qkv.shape[0]
+    assert k_cache.shape == v_cache.shape and k_cache.shape[0] == B and k_cache.shape[2] == n_groups * head_dim
+    assert k_cache.is_contiguous() and v_cache.is_contiguous() and qkv.stride(1) == 1
+    out = torch.empty(B, n_groups * q_per_group * head_dim, dtype=_BF16, device=qkv.device)
+    _lib.call("dolomite_b200_attn_decode", qkv.data_ptr(), qkv.stride(0), k_cache.data_ptr(), v_cache.data_ptr(), lens.data_ptr(),
+              out.data_ptr(), B, k_cache.shape[1], n_groups, q_per_group, head_dim, scale, _stream())
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # MoE: routing plan, grouped expert GEMMs (moe_dolomite/moe/scatter.py:18-138)
 # ------------------------------------------------------------------------------------------------

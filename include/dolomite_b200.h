@@ -165,6 +165,18 @@ int dolomite_b200_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void*
 int dolomite_b200_accum_bf16_into_f32(const void* src, float* dst, float scale, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Single-query attention over a KV cache (decoding with `past_key_values`: attention/sdpa.py:11-83, attention/flash.py:16-140;
+ * model_wrapper/base.py:110-136 `generate`).  One new token per sequence:
+ *   qkv      bf16 [batch, row_stride]: the packed c_attn output of the new tokens (RoPE applied); only the q slots are read
+ *   k_cache / v_cache  bf16 [batch, L_max, n_groups * head_dim]: keys / values by position (the new token already appended)
+ *   lens     int32 [batch]: valid positions per sequence INCLUDING the new token
+ *   out      bf16 [batch, n_heads * head_dim]
+ * ------------------------------------------------------------------------------------------------ */
+int dolomite_b200_attn_decode(const void* qkv, int64_t row_stride, const void* k_cache, const void* v_cache, const int32_t* lens,
+                              void* out, int batch, int64_t L_max, int n_groups, int q_per_group, int head_dim,
+                              float softmax_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * bf16 GEMM on tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM -> epilogue), replacing the cuBLAS
  * calls behind nn.Linear (linear.py:5-25; call sites attention/base.py:100, padding_free.py:74,
  * gpt_dolomite/mlp.py:46-48, gpt_dolomite/main.py:172-177) and their autograd (dgrad / wgrad).

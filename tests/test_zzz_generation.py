@@ -81,6 +81,58 @@ def test_greedy_generation_equals_stepwise_argmax(padding_free):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("ng,g,hd", [(2, 2, 64), (4, 1, 80), (2, 4, 128), (1, 4, 32)])
+def test_single_query_cache_attention_matches_softmax(ng, g, hd):
+    """csrc/attention_decode.cu against an fp64 softmax over the cached keys: ragged cache lengths (1 .. several 128-key chunks),
+    MHA / GQA / MQA slot layouts (attention/sdpa.py:11-83 with one query token)"""
+    from dolomite_engine_b200 import kernels as K
+
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    B, L_max = 5, 700
+    lens = torch.tensor([1, 127, 128, 129, 650], dtype=torch.int32, device="cuda")
+    qkv = torch.randn(B, ng * (g + 2) * hd, device="cuda", generator=gen).bfloat16()
+    kc = torch.randn(B, L_max, ng * hd, device="cuda", generator=gen).bfloat16()
+    vc = torch.randn(B, L_max, ng * hd, device="cuda", generator=gen).bfloat16()
+    scale = hd**-0.5
+    out = K.attn_decode(qkv, kc, vc, lens, ng, g, hd, scale).double().view(B, ng, g, hd)
+    q = qkv.view(B, ng, g + 2, hd)[:, :, :g].double()
+    for b in range(B):
+        n = int(lens[b])
+        k = kc[b, :n].view(n, ng, hd).double()
+        v = vc[b, :n].view(n, ng, hd).double()
+        p = torch.softmax(torch.einsum("ngd,lnd->ngl", q[b], k) * scale, dim=-1)
+        ref = torch.einsum("ngl,lnd->ngd", p, v)
+        assert torch.allclose(out[b], ref, atol=2e-2, rtol=2e-2), b
+
+
+@pytest.mark.gpu
+def test_cached_decoding_equals_recomputing_the_prefix():
+    """generate(use_cache=True) -- one packed prefill + one decode step per token -- against use_cache=False (the packed
+    forward over the whole prefix for every token): same greedy tokens up to bf16 near-ties, logits of a decode step close to
+    the logits of the recomputed prefix"""
+    from dolomite_engine_b200.hf_models.generation import _prefill, last_token_logits
+
+    model = _model(True)
+    ids, mask = _prompts()
+    ids, mask = ids.cuda(), mask.cuda().bool()
+    ref0 = last_token_logits(model, ids, mask)
+    got0, cache = _prefill(model, ids, mask, 8)
+    assert torch.equal(cache.lens.cpu(), mask.sum(1).int().cpu())
+    assert torch.allclose(got0, ref0, atol=2e-2, rtol=2e-2)
+    nxt = ref0.argmax(-1)
+    ids1 = torch.cat([ids, nxt[:, None]], dim=1)
+    mask1 = torch.cat([mask, torch.ones_like(mask[:, :1])], dim=1)
+    ref1 = last_token_logits(model, ids1, mask1)
+    got1 = model.engine.decode_step(nxt.contiguous(), cache).float()
+    assert torch.equal(cache.lens.cpu(), mask1.sum(1).int().cpu())
+    assert (got1 - ref1).abs().max() < 4e-2 * max(1.0, float(ref1.abs().max()))
+    a = model.generate(input_ids=ids, attention_mask=mask, max_new_tokens=6, eos_token_id=-1, use_cache=True).cpu()
+    b = model.generate(input_ids=ids, attention_mask=mask, max_new_tokens=6, eos_token_id=-1, use_cache=False).cpu()
+    agree = (a == b).float().mean().item()
+    assert agree > 0.9, agree  # a bf16 near-tie may flip one argmax and everything after it in that row
+
+
+@pytest.mark.gpu
 def test_generation_stops_at_eos_and_pads():
     model = _model(False)
     ids, mask = _prompts()
