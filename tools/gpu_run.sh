@@ -1,26 +1,25 @@
 #!/bin/bash
 # The commands of the CURRENT gpurun call (rewritten per call; git history keeps the earlier ones).
-# Call F (1 GPU): attention forward with an exact alpha == 1 when the reference maximum stays (both kernels), pipelined backward
-# with bank-conflict-free swizzled dQ slabs + TMA tile reduce, RoPE with two tokens in flight; whole suite; three bench lines.
+# Call H (1 GPU): KV-cache decoding tests, the whole suite, smoke(), and the driver's two bench arms with default flags.
 set -u
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --maxfail=30 --deselect tests/test_gpu_fullwidth.py > gpurun_out/f_pytest.log 2>&1
-echo "pytest rc=$?" >> gpurun_out/f_pytest.log
-rm -f gpurun_out/f_probe.jsonl
-for c in attn_bench_c2 attn_bench_hd128 elementwise_bench_c2; do timeout 300 python tools/gpu_probe.py --only $c --out gpurun_out/f_probe.jsonl > /dev/null 2>&1; done
-timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-gpu-reference --profile-step gpurun_out/f_step_profile_c2.json > gpurun_out/f_bench_c2.json 2> gpurun_out/f_bench_c2.err
-timeout 420 python bench.py --config c4 --steps 4 --warmup 3 --no-cpu-baseline --no-gpu-reference --profile-step gpurun_out/f_step_profile_c4.json > gpurun_out/f_bench_c4.json 2> gpurun_out/f_bench_c4.err
-timeout 420 python bench.py --config c5 --steps 3 --warmup 3 --checkpoint-every 1 --no-cpu-baseline --no-gpu-reference --profile-step gpurun_out/f_step_profile_c5.json > gpurun_out/f_bench_c5.json 2> gpurun_out/f_bench_c5.err
-timeout 900 python -m pytest tests/test_gpu_fullwidth.py -m gpu -q -s -p no:cacheprovider 2>&1 | grep -E "shape:|passed|failed|Error|error" > gpurun_out/f_fullwidth.log
-tail -c 700 gpurun_out/f_pytest.log
+timeout 900 python -m pytest tests/test_zzz_generation.py -m gpu -q > gpurun_out/h_generation.log 2>&1
+echo "rc=$?" >> gpurun_out/h_generation.log
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=30 --deselect tests/test_gpu_fullwidth.py > gpurun_out/h_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/h_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/h_smoke.log 2>&1
+echo "smoke rc=$?" >> gpurun_out/h_smoke.log
+timeout 900 python bench.py --impl reference --steps 8 --warmup 3 > gpurun_out/h_bench_reference_arm.json 2> gpurun_out/h_bench_reference_arm.err
+timeout 900 python bench.py --steps 8 --warmup 3 --profile-step gpurun_out/h_step_profile_c2.json > gpurun_out/h_bench_c2.json 2> gpurun_out/h_bench_c2.err
+tail -c 900 gpurun_out/h_generation.log
+tail -c 400 gpurun_out/h_pytest.log
+cat gpurun_out/h_smoke.log | tail -3
 python - <<'PY'
 import json
-for l in open("gpurun_out/f_probe.jsonl"):
-    d = json.loads(l); print({k: (round(v, 4) if isinstance(v, float) else v) for k, v in d.items() if k not in ("vs_flash_dk", "vs_flash_dv", "trace", "vs_flash_fwd", "single_buffer_vs_flash_fwd")})
-for c in ("c2", "c4", "c5"):
+for f in ("h_bench_reference_arm", "h_bench_c2"):
     try:
-        d = json.loads([l for l in open(f"gpurun_out/f_bench_{c}.json") if l.startswith("{")][-1]); print(c, d["value"], d["ms_per_step"], d["roofline"]["achieved"], d["peak_hbm_gb"], d["clocks"])
+        d = json.loads([l for l in open(f"gpurun_out/{f}.json") if l.startswith("{")][-1])
+        print(f, d["value"], d.get("ms_per_step"), d.get("clocks"), d.get("vs_gpu_reference"), (d.get("cpu_baseline") or {}).get("sample", "")[:160], d.get("wall_s"))
     except Exception as e:
-        print(c, "bench failed", e); print(open(f"gpurun_out/f_bench_{c}.err").read()[-1500:])
+        print(f, "failed", e); print(open(f"gpurun_out/{f}.err").read()[-1500:])
 PY
-cut -c1-260 gpurun_out/f_fullwidth.log
