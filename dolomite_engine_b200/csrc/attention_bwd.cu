@@ -74,8 +74,9 @@ __global__ void __launch_bounds__(256)
 }
 
 // dq_accum (fp32 [n_heads, T, hd]) -> bf16 q slots of dqkv
+// (`scale`: the pipelined kernel accumulates dS' K with dS' = P o (dP - delta), the softmax scale is applied here)
 __global__ void attn_dq_finalize_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv,
-                                        int64_t row_stride, int64_t T, int n_groups, int q_per_group, int hd) {
+                                        int64_t row_stride, int64_t T, int n_groups, int q_per_group, int hd, float scale) {
     const int n_heads = n_groups * q_per_group;
     const int vec_per_row = n_heads * hd / 4;
     const int64_t total = T * vec_per_row;
@@ -87,8 +88,8 @@ __global__ void attn_dq_finalize_kernel(const float* __restrict__ acc, __nv_bflo
         const float4 v = *reinterpret_cast<const float4*>(acc + (int64_t(h) * T + t) * hd + d);
         __nv_bfloat16* dst = dqkv + t * row_stride + int64_t(g * (q_per_group + 2) + s) * hd + d;
         uint2 o;
-        o.x = pack_bf16(v.x, v.y);
-        o.y = pack_bf16(v.z, v.w);
+        o.x = pack_bf16(v.x * scale, v.y * scale);
+        o.y = pack_bf16(v.z * scale, v.w * scale);
         *reinterpret_cast<uint2*>(dst) = o;
     }
 }
@@ -455,8 +456,11 @@ int make_maps(const void* base, int64_t ld, int64_t rows, CUtensorMap* m64, CUte
 
 // head_dim <= 80: pipelined kernel (two softmax warp groups); larger head dims: serial kernel below
 template <int HD>
-int launch_bwd_pipelined(const void* dout, const void* qkv, int64_t row_stride, const BwdParams& p, cudaStream_t st) {
-    return launch_bwd_v3<HD, 2>(dout, qkv, row_stride, p, st);
+int launch_bwd_pipelined(const void* dout, const void* qkv, int64_t row_stride, const BwdParams& p, cudaStream_t st,
+                         int variant) {
+    if (variant == 0) return launch_bwd_v3<HD, 2, false>(dout, qkv, row_stride, p, st);
+    if (variant == 2) return launch_bwd_v3<HD, 4, true>(dout, qkv, row_stride, p, st);
+    return launch_bwd_v3<HD, 2, true>(dout, qkv, row_stride, p, st);
 }
 
 template <int HD>
@@ -542,11 +546,14 @@ extern "C" int dolomite_b200_attn_varlen_bwd(const void* dout, const void* qkv, 
     p.scale = softmax_scale;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     int rc;
+    const int variant = dolo_option_attn_bwd_variant();
+    const bool pipelined = head_dim == 64 || head_dim == 80;
+    const float dq_scale = (pipelined && variant != 0) ? softmax_scale : 1.f;
     switch (head_dim) {
         case 16: rc = launch_bwd<16>(dout, qkv, row_stride, p, st); break;
         case 32: rc = launch_bwd<32>(dout, qkv, row_stride, p, st); break;
-        case 64: rc = launch_bwd_pipelined<64>(dout, qkv, row_stride, p, st); break;
-        case 80: rc = launch_bwd_pipelined<80>(dout, qkv, row_stride, p, st); break;
+        case 64: rc = launch_bwd_pipelined<64>(dout, qkv, row_stride, p, st, variant); break;
+        case 80: rc = launch_bwd_pipelined<80>(dout, qkv, row_stride, p, st, variant); break;
         case 96: rc = launch_bwd<96>(dout, qkv, row_stride, p, st); break;
         case 128: rc = launch_bwd<128>(dout, qkv, row_stride, p, st); break;
         default: return dolo_set_error("attn_bwd: unsupported head_dim %d (supported: 16,32,64,80,96,128)", head_dim);
@@ -558,7 +565,7 @@ extern "C" int dolomite_b200_attn_varlen_bwd(const void* dout, const void* qkv, 
         const int64_t cap = int64_t(dolo_num_sms()) * 16;
         if (blocks > cap) blocks = cap;
         attn_dq_finalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(dq_accum, static_cast<__nv_bfloat16*>(dqkv), row_stride,
-                                                                  T, n_groups, q_per_group, head_dim);
+                                                                  T, n_groups, q_per_group, head_dim, dq_scale);
         DOLO_LAUNCH_OK("attn_dq_finalize");
     }
     return DOLO_OK;

@@ -23,13 +23,13 @@
 // K, V, 2 x (Q, dO), 2 x dS^T staging, dQ staging (4 warps x 2 swizzled 4 KB slabs), LSE/Delta (2 x 2 x 128 floats), barriers
 template <int HD>
 constexpr int bwd_v3_smem_need() {
-    return 6 * HeadChunks<HD>::TILE_BYTES + 2 * (2 * ATT_TILE * 128) + 4 * 2 * 4096 + 4 * ATT_TILE * 4 + 160;
+    return 6 * HeadChunks<HD>::TILE_BYTES + 2 * (2 * ATT_TILE * 128) + 4 * 2 * 4096 + 4096 + 160;
 }
 
 // NG = number of softmax warp groups (4 warps each): every group owns 64 / NG query columns of a half step.  NG = 4
 // (704 threads, <= 88 registers) halves the dependent instruction chain per warp and doubles the warps each scheduler can
 // interleave; the softmax warps, not the tensor pipe, bound the NG = 2 version (ncu: tensor pipe 20 %, issue 25 %).
-template <int HD, int NG>
+template <int HD, int NG, bool LEAN>
 __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
     attn_bwd_kernel_v3(const __grid_constant__ CUtensorMap tq64, const __grid_constant__ CUtensorMap tqR,
                        const __grid_constant__ CUtensorMap to64, const __grid_constant__ CUtensorMap toR,
@@ -68,8 +68,8 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
     uint8_t* sDS = sDO + 2 * TILE_BYTES;       // [2] x DS_BYTES
     uint8_t* sDQ = sDS + 2 * DS_BYTES;         // 4 drain warps x 2 slabs x 4 KB (32 rows x 32 fp32, 128B-swizzled; 1024-aligned)
     float* sLSE = reinterpret_cast<float*>(sDQ + 4 * 2 * 4096);  // [2][128] (log2 units)
-    float* sDelta = sLSE + 2 * ATT_TILE;                         // [2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 2 * ATT_TILE);
+    float* sDelta = sLSE + 2 * ATT_TILE;                         // [2][128]   (LEAN: the 4 KB hold per-warp private copies)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sLSE + 1024);
     uint64_t* kv_full = bars;            // 1
     uint64_t* qdo_full = bars + 1;       // [2]
     uint64_t* qdo_empty = bars + 3;      // [2]
@@ -118,10 +118,14 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
             mbar_expect_tx(kv_full, 2 * TILE_BYTES);
             load_tile(sK, kv_full, &tq64, &tqR, k_col, kv_row);
             load_tile(sV, kv_full, &tq64, &tqR, v_col, kv_row);
+            int s_head = 0, i = j - 1;  // (head slot, query tile) of iteration `it`, tracked without a division
             for (int it = 0; it < n_it; ++it) {
                 const int stage = it & 1;
                 const uint32_t phase = uint32_t(it >> 1) & 1;
-                const int s_head = it / n_i, i = j + (it - s_head * n_i);
+                if (++i == n_q_tiles) {
+                    i = j;
+                    ++s_head;
+                }
                 const int head = group * p.q_per_group + s_head;
                 const int q_col = (group * (p.q_per_group + 2) + s_head) * HD;
                 const int q_row = loc.doc_start + i * ATT_TILE;
@@ -214,6 +218,189 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
                     umma_commit(&qdo_empty[stage]);
                 }
                 if (s == n_steps - 1) umma_commit(dkv_full);
+            }
+        }
+    } else if (LEAN && warp >= 4 && warp < FIRST_TAIL_WARP) {
+        // ======================= softmax warps, lean instruction stream =======================
+        // Same roles as the block below; what changed (ncu call 70: these warps are never waiting for the tensor pipe, they ARE
+        // the critical path at ~0.16 IPC each, 9.5 warp instructions per element):
+        //   * no integer division per tile (the (head, query tile) pair is tracked incrementally: the div's MUFU.RCP chain queued
+        //     behind the other warp's EX2 burst and cost 10 % of the samples);
+        //   * statistics are warp-private (-lse*log2e, -delta of this warp's columns; lanes fetch them one tile ahead): no
+        //     8-warp named barrier per tile, the warps drift apart and overlap each other's MUFU and FMA phases;
+        //   * packed FFMA2 / FADD2 / FMUL2 (two elements per issue slot) for the exponent argument and dS;
+        //   * the softmax scale is NOT applied here: dS' = P o (dP - delta) goes to the tensor pipe, dK is scaled in the epilogue
+        //     and dQ in attn_dq_finalize_kernel (one multiply per OUTPUT element instead of one per score);
+        //   * the generic->async proxy fence for the dS^T shared-memory tile is only needed before the second half's arrive
+        //     (the dQ MMA is the only async-proxy reader and is issued after both halves).
+        const int wg = (warp - 4) >> 2;
+        const int sub = warp & 3;
+        const int r = sub * 32 + lane;
+        const uint32_t t_lane = tmem_base + (uint32_t(sub * 32) << 16);
+        const int kj = j * ATT_TILE + r;
+        const bool key_ok = kj < loc.doc_len;
+        const bool tile_full = (j + 1) * ATT_TILE <= loc.doc_len;
+        const float LOG2E = 1.4426950408889634f;
+        // [0, COLS) -lse*log2e half 0 | [COLS, 2 COLS) half 1 | [2 COLS, 3 COLS) -delta half 0 | [3 COLS, 4 COLS) half 1
+        float* st = sLSE + (warp - 4) * (4 * COLS);
+        float l0, l1, d0, d1;  // raw statistics of the NEXT tile (lane l < COLS: query column wg * COLS + l of both halves)
+        auto fetch_raw = [&](int s_head, int i) {
+            const int head = group * p.q_per_group + s_head;
+            const int q0 = i * ATT_TILE + wg * COLS + lane;
+            const int64_t off = int64_t(head) * p.T + loc.doc_start + q0;
+            const bool ok0 = lane < COLS && q0 < loc.doc_len, ok1 = lane < COLS && q0 + HALF < loc.doc_len;
+            l0 = ok0 ? p.lse[off] : INFINITY;  // +inf -> P = 0 for query rows past the document
+            l1 = ok1 ? p.lse[off + HALF] : INFINITY;
+            d0 = ok0 ? p.delta[off] : 0.f;
+            d1 = ok1 ? p.delta[off + HALF] : 0.f;
+        };
+        int s_head = 0, i = j;
+        fetch_raw(s_head, i);
+        uint32_t sv0[16], dv0[16];
+        mbar_wait(&sdp_full[0], 0, 36);
+        tc_fence_after();
+        tmem_ld16(t_lane + ST_COL + wg * COLS, sv0);
+        tmem_ld16(t_lane + DP_COL + wg * COLS, dv0);
+
+        for (int it = 0; it < n_it; ++it) {
+            __syncwarp();  // every lane is done with the previous tile's statistics
+            if (lane < COLS) {
+                st[lane] = -LOG2E * l0;
+                st[COLS + lane] = -LOG2E * l1;
+                st[2 * COLS + lane] = -d0;
+                st[3 * COLS + lane] = -d1;
+            }
+            __syncwarp();
+            const bool diag = (i == j);
+            const bool need_mask = diag || !tile_full;
+            if (++i == n_q_tiles) {
+                i = j;
+                ++s_head;
+            }
+            if (it + 1 < n_it) fetch_raw(s_head, i);
+            if (it >= 2) mbar_wait(&dq_full[it & 1], uint32_t((it >> 1) - 1) & 1, 35);  // dS smem buffer free again
+            uint8_t* ds_buf = sDS + (it & 1) * DS_BYTES;
+
+            auto process16 = [&](const uint32_t (&sv)[16], const uint32_t (&dv)[16], int h, int b, int sc) {
+                const float* nls = st + h * COLS + sc * 16;
+                const float* nds = st + 2 * COLS + h * COLS + sc * 16;
+                uint32_t pp[8], dd[8];
+                if (need_mask) {
+                    const int cbase = h * HALF + wg * COLS + sc * 16;  // first query column (inside the 128-query tile)
+#pragma unroll
+                    for (int c2 = 0; c2 < 16; c2 += 2) {
+                        float pv[2], dsv[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            float pe = fast_exp2(fmaf(__uint_as_float(sv[c2 + u]), p.scale_log2, nls[c2 + u]));
+                            if (!key_ok || (diag && r > cbase + c2 + u)) pe = 0.f;
+                            pv[u] = pe;
+                            dsv[u] = pe * (__uint_as_float(dv[c2 + u]) + nds[c2 + u]);
+                        }
+                        pp[c2 >> 1] = pack_bf16(pv[0], pv[1]);
+                        dd[c2 >> 1] = pack_bf16(dsv[0], dsv[1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int c4 = 0; c4 < 16; c4 += 4) {
+                        const float4 l4 = *reinterpret_cast<const float4*>(nls + c4);
+                        const float4 d4 = *reinterpret_cast<const float4*>(nds + c4);
+                        float x0, x1, x2, x3, t0, t1, t2, t3, e0, e1, e2, e3;
+                        ffma2_sv(x0, x1, __uint_as_float(sv[c4]), __uint_as_float(sv[c4 + 1]), p.scale_log2, l4.x, l4.y);
+                        ffma2_sv(x2, x3, __uint_as_float(sv[c4 + 2]), __uint_as_float(sv[c4 + 3]), p.scale_log2, l4.z, l4.w);
+                        const float p0 = fast_exp2(x0), p1 = fast_exp2(x1), p2 = fast_exp2(x2), p3 = fast_exp2(x3);
+                        fadd2_v(t0, t1, __uint_as_float(dv[c4]), __uint_as_float(dv[c4 + 1]), d4.x, d4.y);
+                        fadd2_v(t2, t3, __uint_as_float(dv[c4 + 2]), __uint_as_float(dv[c4 + 3]), d4.z, d4.w);
+                        fmul2_v(e0, e1, p0, p1, t0, t1);
+                        fmul2_v(e2, e3, p2, p3, t2, t3);
+                        pp[c4 >> 1] = pack_bf16(p0, p1);
+                        pp[(c4 >> 1) + 1] = pack_bf16(p2, p3);
+                        dd[c4 >> 1] = pack_bf16(e0, e1);
+                        dd[(c4 >> 1) + 1] = pack_bf16(e2, e3);
+                    }
+                }
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::"r"(pp[0]),
+                    "r"(pp[1]), "r"(pp[2]), "r"(pp[3]), "r"(pp[4]), "r"(pp[5]), "r"(pp[6]), "r"(pp[7]),
+                    "r"(t_lane + ST_COL + b * HALF + wg * COLS + sc * 8)
+                    : "memory");
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::"r"(dd[0]),
+                    "r"(dd[1]), "r"(dd[2]), "r"(dd[3]), "r"(dd[4]), "r"(dd[5]), "r"(dd[6]), "r"(dd[7]),
+                    "r"(t_lane + DP_COL + b * HALF + wg * COLS + sc * 8)
+                    : "memory");
+                uint8_t* rowp = ds_buf + h * (ATT_TILE * 128) + r * 128;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int piece = wg * (COLS / 8) + sc * 2 + q;
+                    *reinterpret_cast<uint4*>(rowp + ((piece ^ (r & 7)) << 4)) =
+                        make_uint4(dd[q * 4], dd[q * 4 + 1], dd[q * 4 + 2], dd[q * 4 + 3]);
+                }
+            };
+
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const int b = h;
+                const uint32_t s_addr = t_lane + ST_COL + b * HALF + wg * COLS;
+                const uint32_t d_addr = t_lane + DP_COL + b * HALF + wg * COLS;
+                tmem_ld_wait();
+                reg_fence16(sv0);
+                reg_fence16(dv0);
+                if constexpr (NSC == 2) {
+                    uint32_t sv1[16], dv1[16];
+                    tmem_ld16(s_addr + 16, sv1);
+                    tmem_ld16(d_addr + 16, dv1);
+                    process16(sv0, dv0, h, b, 0);
+                    tmem_ld_wait();
+                    reg_fence16(sv1);
+                    reg_fence16(dv1);
+                    process16(sv1, dv1, h, b, 1);
+                } else {
+                    process16(sv0, dv0, h, b, 0);
+                }
+                const int s_next = 2 * it + h + 1;
+                if (s_next < 2 * n_it) {
+                    const int nb = s_next & 1;
+                    mbar_wait(&sdp_full[nb], uint32_t(s_next >> 1) & 1, 36);
+                    tc_fence_after();
+                    tmem_ld16(t_lane + ST_COL + nb * HALF + wg * COLS, sv0);
+                    tmem_ld16(t_lane + DP_COL + nb * HALF + wg * COLS, dv0);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                if (h == 1) fence_proxy_async_smem();
+                mbar_arrive(&pds_ready[b]);
+            }
+        }
+        // ---------------- epilogue: even groups store dK_j (scaled here), odd groups dV_j ----------------
+        mbar_wait(dkv_full, 0, 37);
+        tc_fence_after();
+        {
+            const bool is_dk = (wg & 1) == 0;
+            const float osc = is_dk ? p.scale : 1.f;
+            const uint32_t src_col = is_dk ? DK_COL : DV_COL;
+            __nv_bfloat16* drow = p.dqkv + int64_t(kv_row + r) * p.row_stride + (is_dk ? k_col : v_col);
+            constexpr int NCH = HD / 16, SPLIT = (NCH + 1) / 2;
+            const int ch0 = (NG == 2) ? 0 : ((wg >> 1) == 0 ? 0 : SPLIT);
+            const int ch1 = (NG == 2) ? NCH : ((wg >> 1) == 0 ? SPLIT : NCH);
+#pragma unroll 1
+            for (int c0 = ch0 * 16; c0 < ch1 * 16; c0 += 16) {
+                uint32_t a[16];
+                tmem_ld16(t_lane + src_col + c0, a);
+                tmem_ld_wait();
+                if (key_ok) {
+                    uint4 x, y;
+                    x.x = pack_bf16(__uint_as_float(a[0]) * osc, __uint_as_float(a[1]) * osc);
+                    x.y = pack_bf16(__uint_as_float(a[2]) * osc, __uint_as_float(a[3]) * osc);
+                    x.z = pack_bf16(__uint_as_float(a[4]) * osc, __uint_as_float(a[5]) * osc);
+                    x.w = pack_bf16(__uint_as_float(a[6]) * osc, __uint_as_float(a[7]) * osc);
+                    y.x = pack_bf16(__uint_as_float(a[8]) * osc, __uint_as_float(a[9]) * osc);
+                    y.y = pack_bf16(__uint_as_float(a[10]) * osc, __uint_as_float(a[11]) * osc);
+                    y.z = pack_bf16(__uint_as_float(a[12]) * osc, __uint_as_float(a[13]) * osc);
+                    y.w = pack_bf16(__uint_as_float(a[14]) * osc, __uint_as_float(a[15]) * osc);
+                    *reinterpret_cast<uint4*>(drow + c0) = x;
+                    *reinterpret_cast<uint4*>(drow + c0 + 8) = y;
+                }
             }
         }
     } else if (warp >= 4 && warp < FIRST_TAIL_WARP) {
@@ -399,8 +586,12 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
         const uint32_t t_lane = tmem_base + (uint32_t(sub * 32) << 16);
         uint8_t* slab = sDQ + sub * (2 * 4096);
         int nb = 0;
+        int s_head = 0, i = j - 1;
         for (int it = 0; it < n_it; ++it) {
-            const int s_head = it / n_i, i = j + (it - s_head * n_i);
+            if (++i == n_q_tiles) {
+                i = j;
+                ++s_head;
+            }
             const int head = group * p.q_per_group + s_head;
             const int row0 = int(int64_t(head) * p.T + loc.doc_start + i * ATT_TILE + sub * 32);
             mbar_wait(&dq_full[it & 1], uint32_t(it >> 1) & 1, 38);
@@ -458,7 +649,7 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
     }
 }
 
-template <int HD, int NG>
+template <int HD, int NG, bool LEAN>
 int launch_bwd_v3(const void* dout, const void* qkv, int64_t row_stride, const BwdParams& p, cudaStream_t st) {
     using CH = HeadChunks<HD>;
     CUtensorMap tq64, tqR, to64, toR;
@@ -481,7 +672,7 @@ int launch_bwd_v3(const void* dout, const void* qkv, int64_t row_stride, const B
     constexpr int need = bwd_v3_smem_need<HD>();
     constexpr int smem_bytes = need + 1024;
     static_assert(smem_bytes <= 232448, "attention backward v3 shared memory budget exceeded");
-    auto kern = attn_bwd_kernel_v3<HD, NG>;
+    auto kern = attn_bwd_kernel_v3<HD, NG, LEAN>;
     static bool attr_set = false;
     if (!attr_set) {
         DOLO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

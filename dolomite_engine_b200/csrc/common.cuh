@@ -46,6 +46,7 @@ int dolo_option_gemm_sm_margin();
 // path is 5 % (reduce-add) to 13 % (store) SLOWER -- 32 extra TMA operations per tile share the queue of the operand loads.
 int dolo_option_gemm_f32_tma_epilogue();
 int dolo_option_attn_fwd_split();  // 0 never / 1 (default) head_dim >= 96 / 2 also head_dim 64, 80: split-softmax forward
+int dolo_option_attn_bwd_variant();  // head_dim 64 / 80 backward: 0 = round-1 softmax warps, 1 (default) = lean, 2 = lean with 4 groups
 int dolo_option_gemm_l2_hints();  // 1 (default) = evict-first / evict-last operand loads for long-contraction GEMMs
 
 // TMA descriptor encode through the driver entry point (no link-time libcuda dependency).
@@ -403,6 +404,30 @@ __device__ __forceinline__ void ffma2_bcast(float& d0, float& d1, float a0, floa
     asm("mov.b64 %0, {%1, %1};" : "=l"(sb) : "f"(s));
     asm("mov.b64 %0, {%1, %1};" : "=l"(cb) : "f"(c));
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(sb), "l"(cb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+// (a0, a1) * (s, s) + (c0, c1)
+__device__ __forceinline__ void ffma2_sv(float& d0, float& d1, float a0, float a1, float s, float c0, float c1) {
+    uint64_t a, sb, cb, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(sb) : "f"(s));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(cb) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(sb), "l"(cb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+// (a0, a1) + (b0, b1)  and  (a0, a1) * (b0, b1)
+__device__ __forceinline__ void fadd2_v(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    uint64_t a, b, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+__device__ __forceinline__ void fmul2_v(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    uint64_t a, b, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
 }
 __device__ __forceinline__ void fadd2(float& acc0, float& acc1, float b0, float b1) {

@@ -737,6 +737,56 @@ def _attn_bench(S, B, nh, hd):
     return res
 
 
+def _attn_bwd_variants(S, B, nh, hd, rounds=3):
+    """A/B/C of the pipelined backward's softmax-warp variants, interleaved so that clock / power drift hits all alike"""
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+    from flash_attn.flash_attn_interface import flash_attn_varlen_func
+
+    T = S * B
+    qkv = torch.randn(T, nh * 3 * hd, device="cuda").bfloat16()
+    cu = torch.arange(0, T + 1, S, dtype=torch.int32, device="cuda")
+    scale = hd ** -0.5
+    dout = torch.randn(T, nh * hd, device="cuda").bfloat16()
+    out, lse = k.attn_varlen_fwd(qkv, cu, S, nh, 1, hd, scale)
+    v = qkv.view(T, nh, 3, hd)
+    qf, kf, vf = (v[:, :, i].detach().clone().requires_grad_(True) for i in range(3))
+    fo = flash_attn_varlen_func(qf, kf, vf, cu, cu, S, S, 0.0, softmax_scale=scale, causal=True)
+    fo.backward(dout.view(T, nh, hd))
+    flops = 2.5 * 4.0 * S * S * hd * nh * B / 2
+    res = {"ok": True}
+    dqkv = torch.empty_like(qkv)
+    times = {0: [], 1: [], 2: []}
+    try:
+        for variant in (0, 1, 2):
+            k.set_option("attn_bwd_variant", variant)
+            k.attn_varlen_bwd(dout, qkv, out, lse, cu, S, nh, 1, hd, scale, dqkv=dqkv)
+            d = dqkv.view(T, nh, 3, hd)
+            e = {"dq": _err(d[:, :, 0], qf.grad), "dk": _err(d[:, :, 1], kf.grad), "dv": _err(d[:, :, 2], vf.grad)}
+            res[f"variant{variant}_err"] = {n: x["rel_l2"] for n, x in e.items()}
+            res["ok"] = res["ok"] and all(x["rel_l2"] < 2e-2 for x in e.values())
+        for _ in range(rounds):
+            for variant in (0, 1, 2):
+                k.set_option("attn_bwd_variant", variant)
+                times[variant].append(_time(lambda: k.attn_varlen_bwd(dout, qkv, out, lse, cu, S, nh, 1, hd, scale, dqkv=dqkv), iters=5))
+    finally:
+        k.set_option("attn_bwd_variant", 1)
+    for variant, ts in times.items():
+        res[f"variant{variant}_ms"] = ts
+        res[f"variant{variant}_tflops_causal"] = flops / min(ts) / 1e9
+    return res
+
+
+@case
+def attn_bwd_variants_hd80():
+    return _attn_bwd_variants(4096, 2, 32, 80)
+
+
+@case
+def attn_bwd_variants_hd64():
+    return _attn_bwd_variants(4096, 2, 32, 64)
+
+
 @case
 def attn_bench_c2():
     return _attn_bench(4096, 2, 32, 80)

@@ -1,25 +1,16 @@
 #!/bin/bash
 # The commands of the CURRENT gpurun call (rewritten per call; git history keeps the earlier ones).
-# Call H (1 GPU): KV-cache decoding tests, the whole suite, smoke(), and the driver's two bench arms with default flags.
+# Call I (1 GPU): lean softmax warps of the pipelined attention backward (no division, warp-private statistics, packed
+# FFMA2 / FADD2 / FMUL2, scale folded into the dK / dQ epilogues): parity, interleaved A/B/C timing, ncu of the new kernel.
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_zzz_generation.py -m gpu -q > gpurun_out/h_generation.log 2>&1
-echo "rc=$?" >> gpurun_out/h_generation.log
-timeout 1500 python -m pytest tests -m gpu -q --maxfail=30 --deselect tests/test_gpu_fullwidth.py > gpurun_out/h_pytest.log 2>&1
-echo "pytest rc=$?" >> gpurun_out/h_pytest.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/h_smoke.log 2>&1
-echo "smoke rc=$?" >> gpurun_out/h_smoke.log
-timeout 900 python bench.py --impl reference --steps 8 --warmup 3 > gpurun_out/h_bench_reference_arm.json 2> gpurun_out/h_bench_reference_arm.err
-timeout 900 python bench.py --steps 8 --warmup 3 --profile-step gpurun_out/h_step_profile_c2.json > gpurun_out/h_bench_c2.json 2> gpurun_out/h_bench_c2.err
-tail -c 900 gpurun_out/h_generation.log
-tail -c 400 gpurun_out/h_pytest.log
-cat gpurun_out/h_smoke.log | tail -3
-python - <<'PY'
-import json
-for f in ("h_bench_reference_arm", "h_bench_c2"):
-    try:
-        d = json.loads([l for l in open(f"gpurun_out/{f}.json") if l.startswith("{")][-1])
-        print(f, d["value"], d.get("ms_per_step"), d.get("clocks"), d.get("vs_gpu_reference"), (d.get("cpu_baseline") or {}).get("sample", "")[:160], d.get("wall_s"))
-    except Exception as e:
-        print(f, "failed", e); print(open(f"gpurun_out/{f}.err").read()[-1500:])
-PY
+timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "attention or empty" > gpurun_out/i_attn_tests.log 2>&1
+echo "rc=$?" >> gpurun_out/i_attn_tests.log
+rm -f gpurun_out/i_probe.jsonl
+for c in attn_bwd_variants_hd80 attn_bwd_variants_hd64; do
+  timeout 300 python tools/gpu_probe.py --only $c --out gpurun_out/i_probe.jsonl > /dev/null 2>&1
+done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'attn_bwd_kernel_v3' --launch-skip 1 -c 1 -f -o gpurun_out/r02_attn_bwd_lean_hd80 python tools/ncu_targets.py > gpurun_out/i_ncu.log 2>&1
+tail -c 1200 gpurun_out/i_attn_tests.log
+cat gpurun_out/i_probe.jsonl | cut -c1-1800
+tail -3 gpurun_out/i_ncu.log
