@@ -33,6 +33,8 @@ static int g_attn_fwd_split = 1;
 int dolo_option_attn_fwd_split() { return g_attn_fwd_split; }
 static int g_attn_bwd_variant = 1;
 int dolo_option_attn_bwd_variant() { return g_attn_bwd_variant; }
+static int g_attn_bwd_ablate = 0;
+int dolo_option_attn_bwd_ablate() { return g_attn_bwd_ablate; }
 static int g_gemm_l2_hints = 1;
 int dolo_option_gemm_l2_hints() { return g_gemm_l2_hints; }
 static int g_gemm_f32_tma_epilogue = 0;
@@ -51,6 +53,10 @@ extern "C" int dolomite_b200_set_option(const char* key, int value) {
     if (key != nullptr && strcmp(key, "attn_bwd_variant") == 0) {
         DOLO_REQUIRE(value >= 0 && value <= 2, "attn_bwd_variant must be 0, 1 or 2");
         g_attn_bwd_variant = value;
+        return DOLO_OK;
+    }
+    if (key != nullptr && strcmp(key, "attn_bwd_ablate") == 0) {
+        g_attn_bwd_ablate = value;
         return DOLO_OK;
     }
     if (key != nullptr && strcmp(key, "gemm_l2_hints") == 0) {

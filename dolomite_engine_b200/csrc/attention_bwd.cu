@@ -31,6 +31,9 @@ struct BwdParams {
     int64_t T;
     int n_groups, q_per_group, n_heads;
     float scale, scale_log2;
+    int ablate;  // TIMING EXPERIMENTS ONLY (wrong results): see dolo_option_attn_bwd_ablate
+    unsigned long long* trace;  // DEBUG timeline buffer (5 roles x 2048 events) or nullptr
+    int trace_cta;
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -458,9 +461,11 @@ int make_maps(const void* base, int64_t ld, int64_t rows, CUtensorMap* m64, CUte
 template <int HD>
 int launch_bwd_pipelined(const void* dout, const void* qkv, int64_t row_stride, const BwdParams& p, cudaStream_t st,
                          int variant) {
-    if (variant == 0) return launch_bwd_v3<HD, 2, false>(dout, qkv, row_stride, p, st);
-    if (variant == 2) return launch_bwd_v3<HD, 4, true>(dout, qkv, row_stride, p, st);
-    return launch_bwd_v3<HD, 2, true>(dout, qkv, row_stride, p, st);
+    if (variant == 0) return launch_bwd_v3<HD, 2, false, false>(dout, qkv, row_stride, p, st);
+    if constexpr (HD % 64 != 0) {
+        if (variant == 2) return launch_bwd_v3<HD, 2, true, true>(dout, qkv, row_stride, p, st);
+    }
+    return launch_bwd_v3<HD, 2, true, false>(dout, qkv, row_stride, p, st);
 }
 
 template <int HD>
@@ -500,6 +505,16 @@ int launch_bwd(const void* dout, const void* qkv, int64_t row_stride, const BwdP
 inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
 
 }  // namespace
+
+static unsigned long long* g_bwd_trace = nullptr;
+static int g_bwd_trace_cta = 0;
+// DEBUG (not part of the ABI header): device buffer of 5 x 2048 uint64 that one CTA of the pipelined backward fills with
+// (event id << 56 | clock64) stamps; nullptr switches tracing off.
+extern "C" int dolomite_b200_debug_attn_bwd_trace(void* buf, int cta) {
+    g_bwd_trace = static_cast<unsigned long long*>(buf);
+    g_bwd_trace_cta = cta;
+    return DOLO_OK;
+}
 
 extern "C" int64_t dolomite_b200_attn_varlen_bwd_workspace_bytes(int64_t T, int n_groups, int q_per_group,
                                                                  int head_dim) {
@@ -545,6 +560,9 @@ extern "C" int dolomite_b200_attn_varlen_bwd(const void* dout, const void* qkv, 
     p.n_heads = nh;
     p.scale = softmax_scale;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
+    p.ablate = dolo_option_attn_bwd_ablate();
+    p.trace = g_bwd_trace;
+    p.trace_cta = g_bwd_trace_cta;
     int rc;
     const int variant = dolo_option_attn_bwd_variant();
     const bool pipelined = head_dim == 64 || head_dim == 80;

@@ -26,16 +26,42 @@ constexpr int bwd_v3_smem_need() {
     return 6 * HeadChunks<HD>::TILE_BYTES + 2 * (2 * ATT_TILE * 128) + 4 * 2 * 4096 + 4096 + 160;
 }
 
+// Uniform 16-column chunks (32-byte rows, SWIZZLE_32B) for head dims that are not a multiple of 64.  Every chunk is one K = 16
+// step of the K-major views (S^T, dP^T), and the MN-major views (dV, dK, dQ: head_dim = MMA N) span all chunks through ONE
+// descriptor (leading-dimension byte offset = chunk stride), so those products take one N = head_dim MMA per K step instead of
+// one per chunk.  Why it matters (ncu call 77 + the clock64 timeline of call 79): the kernel is bound by shared-memory
+// bandwidth (tensor-core operand reads 1952 + LSU 1565 wavefronts per tile of ~4700 cycles); with the 64 + 16 split every
+// dQ K step read the 4 KB dS^T slice twice.
+template <int HD>
+struct UniformChunks {
+    static constexpr int NC64 = 0;
+    static constexpr int REM = 16;
+    static constexpr int NCHUNK = HD / 16;
+    static constexpr int TILE_BYTES = ATT_TILE * HD * 2;
+    static constexpr int CHUNK_BYTES = ATT_TILE * 32;
+    __host__ __device__ static constexpr int width(int) { return 16; }
+    __host__ __device__ static constexpr int col(int c) { return c * 16; }
+    __host__ __device__ static constexpr int offset(int c) { return c * CHUNK_BYTES; }
+};
+template <int HD, bool UNI>
+struct BwdChunks {
+    using type = HeadChunks<HD>;
+};
+template <int HD>
+struct BwdChunks<HD, true> {
+    using type = UniformChunks<HD>;
+};
+
 // NG = number of softmax warp groups (4 warps each): every group owns 64 / NG query columns of a half step.  NG = 4
 // (704 threads, <= 88 registers) halves the dependent instruction chain per warp and doubles the warps each scheduler can
 // interleave; the softmax warps, not the tensor pipe, bound the NG = 2 version (ncu: tensor pipe 20 %, issue 25 %).
-template <int HD, int NG, bool LEAN>
+template <int HD, int NG, bool LEAN, bool UNI>
 __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
     attn_bwd_kernel_v3(const __grid_constant__ CUtensorMap tq64, const __grid_constant__ CUtensorMap tqR,
                        const __grid_constant__ CUtensorMap to64, const __grid_constant__ CUtensorMap toR,
                        const __grid_constant__ CUtensorMap tdq32, const __grid_constant__ CUtensorMap tdq16,
                        const BwdParams p) {
-    using CH = HeadChunks<HD>;
+    using CH = typename BwdChunks<HD, UNI>::type;
     static_assert(256 + 3 * HD <= 512, "v2 needs a private dQ accumulator (head_dim <= 80)");
     constexpr int TILE_BYTES = CH::TILE_BYTES;
     constexpr int HALF = 64;
@@ -81,6 +107,14 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // DEBUG timeline (dolomite_b200_debug_attn_bwd_trace): one thread per role of ONE CTA stamps clock64() at its events
+    constexpr int TRACE_CAP = 2048;
+    const bool tr_cta = p.trace != nullptr && int(blockIdx.x) == p.trace_cta && blockIdx.y == 0;
+    int tr_n = 0;
+    auto TR = [&](int role, int id) {
+        if (tr_cta && tr_n < TRACE_CAP)
+            p.trace[role * TRACE_CAP + tr_n++] = (static_cast<unsigned long long>(id) << 56) | (clock64() & 0xFFFFFFFFFFFFFFull);
+    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tq64);
@@ -130,9 +164,11 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
                 const int q_col = (group * (p.q_per_group + 2) + s_head) * HD;
                 const int q_row = loc.doc_start + i * ATT_TILE;
                 mbar_wait(&qdo_empty[stage], phase ^ 1, 30);
+                TR(0, 1);
                 mbar_expect_tx(&qdo_full[stage], 2 * TILE_BYTES);
                 load_tile(sQ + stage * TILE_BYTES, &qdo_full[stage], &tq64, &tqR, q_col, q_row);
                 load_tile(sDO + stage * TILE_BYTES, &qdo_full[stage], &to64, &toR, head * HD, q_row);
+                TR(0, 2);
             }
         }
     } else if (warp == 1) {
@@ -144,7 +180,11 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
 
             auto issue_A = [&](int s) {
                 const int it = s >> 1, h = s & 1, stage = it & 1, b = s & 1;
-                if (h == 0) mbar_wait(&qdo_full[stage], uint32_t(it >> 1) & 1, 32);
+                if (h == 0) {
+                    TR(1, 10);
+                    mbar_wait(&qdo_full[stage], uint32_t(it >> 1) & 1, 32);
+                    TR(1, 11);
+                }
                 tc_fence_after();
                 const uint32_t q_s = smem_u32(sQ + stage * TILE_BYTES);
                 const uint32_t do_s = smem_u32(sDO + stage * TILE_BYTES);
@@ -171,16 +211,34 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
                     }
                 }
                 umma_commit(&sdp_full[b]);
+                TR(1, 12);
             };
 
             issue_A(0);
             if (n_steps > 1) issue_A(1);
             for (int s = 0; s < n_steps; ++s) {
                 const int it = s >> 1, h = s & 1, stage = it & 1, b = s & 1;
+                TR(1, 1);
                 mbar_wait(&pds_ready[b], uint32_t(it) & 1, 33);
+                TR(1, 2);
                 tc_fence_after();
                 const uint32_t q_s = smem_u32(sQ + stage * TILE_BYTES);
                 const uint32_t do_s = smem_u32(sDO + stage * TILE_BYTES);
+                if constexpr (UNI) {
+                    constexpr uint32_t idesc_ts = umma_idesc_bf16(128, HD, false, true);
+                    if (!(p.ablate & 16)) {
+#pragma unroll
+                        for (int k = 0; k < HALF / 16; ++k)  // dV += P^T dO: one N = HD MMA per 16 queries
+                            umma_ts(tmem_base + DV_COL, tmem_base + ST_COL + b * HALF + ((16 * k) / COLS) * COLS + (((16 * k) % COLS) / 16) * 8,
+                                    umma_smem_desc(do_s + h * HALF * 32 + k * 512, CH::CHUNK_BYTES, 256, 6), idesc_ts,
+                                    (s > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < HALF / 16; ++k)  // dK += dS^T Q
+                            umma_ts(tmem_base + DK_COL, tmem_base + DP_COL + b * HALF + ((16 * k) / COLS) * COLS + (((16 * k) % COLS) / 16) * 8,
+                                    umma_smem_desc(q_s + h * HALF * 32 + k * 512, CH::CHUNK_BYTES, 256, 6), idesc_ts,
+                                    (s > 0 || k > 0) ? 1u : 0u);
+                    }
+                } else if (!(p.ablate & 16))
 #pragma unroll
                 for (int c = 0; c < CH::NCHUNK; ++c) {
                     const int w = CH::width(c);
@@ -198,13 +256,29 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
                 }
                 // S^T / dP^T of step s+2 go first: the softmax warps are the critical path and must never wait behind the
                 // dQ drain (the dQ MMA below needs the previous tile's accumulator drained by the red.add warps)
+                TR(1, 3);
+                // the dV / dK products of the second half are the last readers of this tile's Q / dO stage: hand it back to the
+                // TMA producer now (the clock64 timeline of call 79 showed the MMA thread waiting ~470 cycles per tile for the
+                // next tile's Q / dO when the release was tied to the dQ product, which does not read them)
+                if (h == 1) umma_commit(&qdo_empty[stage]);
                 if (s + 2 < n_steps) issue_A(s + 2);
                 if (h == 1) {
                     if (it > 0) {
+                        TR(1, 4);
                         mbar_wait(dq_done, uint32_t(it - 1) & 1, 34);  // dQ accumulator drained
+                        TR(1, 5);
                         tc_fence_after();
                     }
                     const uint32_t ds_s = smem_u32(sDS + (it & 1) * DS_BYTES);
+                    if constexpr (UNI) {
+                        constexpr uint32_t idesc_dq = umma_idesc_bf16(128, HD, true, true);
+                        if (!(p.ablate & 4)) {
+#pragma unroll
+                            for (int k = 0; k < ATT_TILE / 16; ++k)
+                                umma_ss(tmem_base + DQ_COL, umma_smem_desc(ds_s + k * 2048, ATT_TILE * 128, 1024, 2),
+                                        umma_smem_desc(k_s + k * 512, CH::CHUNK_BYTES, 256, 6), idesc_dq, k > 0 ? 1u : 0u);
+                        }
+                    } else if (!(p.ablate & 4))
 #pragma unroll
                     for (int c = 0; c < CH::NCHUNK; ++c) {
                         const int w = CH::width(c);
@@ -215,7 +289,7 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
                                     chunk_desc_mnmajor(k_s + CH::offset(c), w, k), idesc_dq, k > 0 ? 1u : 0u);
                     }
                     umma_commit(&dq_full[it & 1]);
-                    umma_commit(&qdo_empty[stage]);
+                    TR(1, 6);
                 }
                 if (s == n_steps - 1) umma_commit(dkv_full);
             }
@@ -262,7 +336,12 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
         tmem_ld16(t_lane + ST_COL + wg * COLS, sv0);
         tmem_ld16(t_lane + DP_COL + wg * COLS, dv0);
 
+        const int tr_role = (lane == 0 && sub == 0) ? 2 + wg : -1;
+        auto TS = [&](int id) {
+            if (tr_role >= 0) TR(tr_role, id);
+        };
         for (int it = 0; it < n_it; ++it) {
+            TS(1);
             __syncwarp();  // every lane is done with the previous tile's statistics
             if (lane < COLS) {
                 st[lane] = -LOG2E * l0;
@@ -279,13 +358,20 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
             }
             if (it + 1 < n_it) fetch_raw(s_head, i);
             if (it >= 2) mbar_wait(&dq_full[it & 1], uint32_t((it >> 1) - 1) & 1, 35);  // dS smem buffer free again
+            TS(2);
             uint8_t* ds_buf = sDS + (it & 1) * DS_BYTES;
 
             auto process16 = [&](const uint32_t (&sv)[16], const uint32_t (&dv)[16], int h, int b, int sc) {
                 const float* nls = st + h * COLS + sc * 16;
                 const float* nds = st + 2 * COLS + h * COLS + sc * 16;
                 uint32_t pp[8], dd[8];
-                if (need_mask) {
+                if (p.ablate & 8) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        pp[q] = sv[q] & 0x3f803f80u;
+                        dd[q] = dv[q] & 0x3f803f80u;
+                    }
+                } else if (need_mask) {
                     const int cbase = h * HALF + wg * COLS + sc * 16;  // first query column (inside the 128-query tile)
 #pragma unroll
                     for (int c2 = 0; c2 < 16; c2 += 2) {
@@ -330,6 +416,7 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
                     "r"(t_lane + DP_COL + b * HALF + wg * COLS + sc * 8)
                     : "memory");
                 uint8_t* rowp = ds_buf + h * (ATT_TILE * 128) + r * 128;
+                if (!(p.ablate & 32))
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const int piece = wg * (COLS / 8) + sc * 2 + q;
@@ -343,7 +430,9 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
                 const int b = h;
                 const uint32_t s_addr = t_lane + ST_COL + b * HALF + wg * COLS;
                 const uint32_t d_addr = t_lane + DP_COL + b * HALF + wg * COLS;
+                TS(3);
                 tmem_ld_wait();
+                TS(4);
                 reg_fence16(sv0);
                 reg_fence16(dv0);
                 if constexpr (NSC == 2) {
@@ -351,25 +440,31 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
                     tmem_ld16(s_addr + 16, sv1);
                     tmem_ld16(d_addr + 16, dv1);
                     process16(sv0, dv0, h, b, 0);
+                    TS(5);
                     tmem_ld_wait();
+                    TS(6);
                     reg_fence16(sv1);
                     reg_fence16(dv1);
                     process16(sv1, dv1, h, b, 1);
                 } else {
                     process16(sv0, dv0, h, b, 0);
                 }
+                TS(7);
                 const int s_next = 2 * it + h + 1;
                 if (s_next < 2 * n_it) {
                     const int nb = s_next & 1;
                     mbar_wait(&sdp_full[nb], uint32_t(s_next >> 1) & 1, 36);
+                    TS(8);
                     tc_fence_after();
                     tmem_ld16(t_lane + ST_COL + nb * HALF + wg * COLS, sv0);
                     tmem_ld16(t_lane + DP_COL + nb * HALF + wg * COLS, dv0);
                 }
                 tmem_st_wait();
+                TS(9);
                 tc_fence_before();
                 if (h == 1) fence_proxy_async_smem();
                 mbar_arrive(&pds_ready[b]);
+                TS(10);
             }
         }
         // ---------------- epilogue: even groups store dK_j (scaled here), odd groups dV_j ----------------
@@ -594,10 +689,12 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
             }
             const int head = group * p.q_per_group + s_head;
             const int row0 = int(int64_t(head) * p.T + loc.doc_start + i * ATT_TILE + sub * 32);
+            if (lane == 0 && warp == 2) TR(4, 1);
             mbar_wait(&dq_full[it & 1], uint32_t(it >> 1) & 1, 38);
+            if (lane == 0 && warp == 2) TR(4, 2);
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 + 32 <= HD; c0 += 32) {
+            for (int c0 = 0; c0 + 32 <= HD && !(p.ablate & 2); c0 += 32) {
                 uint8_t* buf = slab + (nb & 1) * 4096;
                 if (lane == 0) tma_store_wait_read<1>();  // the reduce issued from this slab two chunks ago has read it
                 __syncwarp();
@@ -610,13 +707,13 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
                         make_uint4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
+                if (lane == 0 && !(p.ablate & 1)) {
                     tma_reduce_add_2d(&tdq32, buf, c0, row0);
                     tma_store_commit();
                 }
                 ++nb;
             }
-            if constexpr (HD % 32 == 16) {  // last 16 columns: 64-byte rows, 64-byte swizzle
+            if (HD % 32 == 16 && !(p.ablate & 2)) {  // last 16 columns: 64-byte rows, 64-byte swizzle
                 uint8_t* buf = slab + (nb & 1) * 4096;
                 if (lane == 0) tma_store_wait_read<1>();
                 __syncwarp();
@@ -629,7 +726,7 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
                         make_uint4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
+                if (lane == 0 && !(p.ablate & 1)) {
                     tma_reduce_add_2d(&tdq16, buf, HD - 16, row0);
                     tma_store_commit();
                 }
@@ -637,6 +734,7 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
             }
             tc_fence_before();
             mbar_arrive(dq_done);  // accumulator free for the next dQ MMA
+            if (lane == 0 && warp == 2) TR(4, 3);
         }
         if (lane == 0) tma_store_wait_all<0>();  // shared memory must outlive the last reduce
     }
@@ -649,14 +747,28 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
     }
 }
 
-template <int HD, int NG, bool LEAN>
+template <int HD, int NG, bool LEAN, bool UNI>
 int launch_bwd_v3(const void* dout, const void* qkv, int64_t row_stride, const BwdParams& p, cudaStream_t st) {
-    using CH = HeadChunks<HD>;
     CUtensorMap tq64, tqR, to64, toR;
-    int rc = make_maps<HD>(qkv, row_stride, p.T, &tq64, &tqR);
-    if (rc) return rc;
-    rc = make_maps<HD>(dout, int64_t(p.n_heads) * HD, p.T, &to64, &toR);
-    if (rc) return rc;
+    int rc;
+    if constexpr (UNI) {  // one map per tensor: boxes of 16 columns x 128 rows, 32-byte swizzle
+        uint32_t box[2] = {16, ATT_TILE};
+        uint64_t dims[2] = {uint64_t(row_stride), uint64_t(p.T)};
+        uint64_t strides[2] = {2, uint64_t(row_stride) * 2};
+        rc = dolo_make_tmap(&tqR, qkv, 2, 2, dims, strides, box, DOLO_SW_32);
+        if (rc) return rc;
+        dims[0] = uint64_t(p.n_heads) * HD;
+        strides[1] = dims[0] * 2;
+        rc = dolo_make_tmap(&toR, dout, 2, 2, dims, strides, box, DOLO_SW_32);
+        if (rc) return rc;
+        tq64 = tqR;
+        to64 = toR;
+    } else {
+        rc = make_maps<HD>(qkv, row_stride, p.T, &tq64, &tqR);
+        if (rc) return rc;
+        rc = make_maps<HD>(dout, int64_t(p.n_heads) * HD, p.T, &to64, &toR);
+        if (rc) return rc;
+    }
     CUtensorMap tdq32, tdq16;
     {
         // dq_accum as [heads * T rows, HD columns] fp32; boxes = 32 rows x 32 (16) columns, the drain warps' slabs
@@ -672,7 +784,7 @@ int launch_bwd_v3(const void* dout, const void* qkv, int64_t row_stride, const B
     constexpr int need = bwd_v3_smem_need<HD>();
     constexpr int smem_bytes = need + 1024;
     static_assert(smem_bytes <= 232448, "attention backward v3 shared memory budget exceeded");
-    auto kern = attn_bwd_kernel_v3<HD, NG, LEAN>;
+    auto kern = attn_bwd_kernel_v3<HD, NG, LEAN, UNI>;
     static bool attr_set = false;
     if (!attr_set) {
         DOLO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

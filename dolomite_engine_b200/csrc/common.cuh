@@ -47,6 +47,7 @@ int dolo_option_gemm_sm_margin();
 int dolo_option_gemm_f32_tma_epilogue();
 int dolo_option_attn_fwd_split();  // 0 never / 1 (default) head_dim >= 96 / 2 also head_dim 64, 80: split-softmax forward
 int dolo_option_attn_bwd_variant();  // head_dim 64 / 80 backward: 0 = round-1 softmax warps, 1 (default) = lean, 2 = lean with 4 groups
+int dolo_option_attn_bwd_ablate();
 int dolo_option_gemm_l2_hints();  // 1 (default) = evict-first / evict-last operand loads for long-contraction GEMMs
 
 // TMA descriptor encode through the driver entry point (no link-time libcuda dependency).

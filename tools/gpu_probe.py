@@ -777,6 +777,89 @@ def _attn_bwd_variants(S, B, nh, hd, rounds=3):
     return res
 
 
+def _attn_bwd_ablation(S, B, nh, hd):
+    """TIMING ONLY (results are wrong by construction): which stage bounds the pipelined backward?  Bits of `attn_bwd_ablate`:
+    1 no TMA reduce-add of dQ, 2 no dQ drain at all, 4 no dQ MMAs, 8 no softmax math, 16 no dV / dK MMAs, 32 no dS^T smem stores"""
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+
+    T = S * B
+    qkv = torch.randn(T, nh * 3 * hd, device="cuda").bfloat16()
+    cu = torch.arange(0, T + 1, S, dtype=torch.int32, device="cuda")
+    scale = hd ** -0.5
+    dout = torch.randn(T, nh * hd, device="cuda").bfloat16()
+    out, lse = k.attn_varlen_fwd(qkv, cu, S, nh, 1, hd, scale)
+    dqkv = torch.empty_like(qkv)
+    flops = 2.5 * 4.0 * S * S * hd * nh * B / 2
+    res = {"ok": True}
+    masks = [0, 1, 3, 7, 8, 32, 40, 16, 47, 63]
+    times = {m: [] for m in masks}
+    try:
+        for _ in range(2):
+            for m in masks:
+                k.set_option("attn_bwd_ablate", m)
+                times[m].append(_time(lambda: k.attn_varlen_bwd(dout, qkv, out, lse, cu, S, nh, 1, hd, scale, dqkv=dqkv), iters=5))
+    finally:
+        k.set_option("attn_bwd_ablate", 0)
+    for m, ts in times.items():
+        res[f"ablate{m}_ms"] = min(ts)
+    # the small kernels around the main one (delta, memset, finalize) are inside these times: measure them alone
+    return res
+
+
+@case
+def attn_bwd_trace_hd80():
+    """clock64 timeline of ONE CTA of the pipelined backward (debug hook, not part of the ABI): gpurun_out/bwd_trace_*.npy"""
+    import ctypes
+
+    import numpy as np
+
+    torch = _t()
+    from dolomite_engine_b200 import _lib
+    from dolomite_engine_b200 import kernels as k
+
+    S, B, nh, hd = 4096, 2, 32, 80
+    T = S * B
+    qkv = torch.randn(T, nh * 3 * hd, device="cuda").bfloat16()
+    cu = torch.arange(0, T + 1, S, dtype=torch.int32, device="cuda")
+    scale = hd ** -0.5
+    dout = torch.randn(T, nh * hd, device="cuda").bfloat16()
+    out, lse = k.attn_varlen_fwd(qkv, cu, S, nh, 1, hd, scale)
+    dqkv = torch.empty_like(qkv)
+    lib = _lib.load()
+    fn = lib.dolomite_b200_debug_attn_bwd_trace
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    fn.restype = ctypes.c_int
+    res = {"ok": True}
+    os.makedirs("gpurun_out", exist_ok=True)
+    try:
+        for ablate in (0, 7, 63):
+            k.set_option("attn_bwd_ablate", ablate)
+            for _ in range(3):
+                k.attn_varlen_bwd(dout, qkv, out, lse, cu, S, nh, 1, hd, scale, dqkv=dqkv)
+            buf = torch.zeros(5 * 2048, dtype=torch.int64, device="cuda")
+            fn(buf.data_ptr(), 8)
+            k.attn_varlen_bwd(dout, qkv, out, lse, cu, S, nh, 1, hd, scale, dqkv=dqkv)
+            torch.cuda.synchronize()
+            fn(None, 0)
+            np.save(f"gpurun_out/bwd_trace_ablate{ablate}.npy", buf.cpu().numpy())
+            res[f"events_ablate{ablate}"] = int((buf != 0).sum())
+    finally:
+        fn(None, 0)
+        k.set_option("attn_bwd_ablate", 0)
+    return res
+
+
+@case
+def attn_bwd_ablation_hd80():
+    return _attn_bwd_ablation(4096, 2, 32, 80)
+
+
+@case
+def attn_bwd_ablation_hd64():
+    return _attn_bwd_ablation(4096, 2, 32, 64)
+
+
 @case
 def attn_bwd_variants_hd80():
     return _attn_bwd_variants(4096, 2, 32, 80)
