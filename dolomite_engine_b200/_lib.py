@@ -103,6 +103,11 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    # DOLO_OPTIONS="key=value,key=value": tuning knobs of dolomite_b200_set_option applied at load (A/B runs of bench.py)
+    for item in filter(None, os.environ.get("DOLO_OPTIONS", "").split(",")):
+        key, _, value = item.partition("=")
+        if lib.dolomite_b200_set_option(key.strip().encode(), int(value)) != 0:
+            raise DolomiteB200Error(f"DOLO_OPTIONS: {lib.dolomite_b200_last_error().decode()}")
     return lib
 
 

@@ -31,12 +31,14 @@ int dolo_option_gemm_sm_margin() { return g_gemm_sm_margin; }
 int dolo_option_gemm_cta_pair() { return g_gemm_cta_pair; }
 static int g_attn_fwd_split = 1;
 int dolo_option_attn_fwd_split() { return g_attn_fwd_split; }
-static int g_attn_bwd_variant = 1;
+static int g_attn_bwd_variant = 2;
 int dolo_option_attn_bwd_variant() { return g_attn_bwd_variant; }
 static int g_attn_bwd_ablate = 0;
 int dolo_option_attn_bwd_ablate() { return g_attn_bwd_ablate; }
 static int g_gemm_l2_hints = 1;
 int dolo_option_gemm_l2_hints() { return g_gemm_l2_hints; }
+static int g_gemm_dynamic = 0;
+int dolo_option_gemm_dynamic() { return g_gemm_dynamic; }
 static int g_gemm_f32_tma_epilogue = 0;
 int dolo_option_gemm_f32_tma_epilogue() { return g_gemm_f32_tma_epilogue; }
 
@@ -65,6 +67,10 @@ extern "C" int dolomite_b200_set_option(const char* key, int value) {
     }
     if (key != nullptr && strcmp(key, "gemm_f32_tma_epilogue") == 0) {
         g_gemm_f32_tma_epilogue = value != 0;
+        return DOLO_OK;
+    }
+    if (key != nullptr && strcmp(key, "gemm_dynamic") == 0) {
+        g_gemm_dynamic = value != 0;
         return DOLO_OK;
     }
     if (key != nullptr && strcmp(key, "gemm_cta_pair") == 0) {
@@ -152,5 +158,29 @@ int dolo_make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank,
             (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 1 ? strides_bytes[1] : 0), box[0],
             rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, int(sw));
     }
+    return DOLO_OK;
+}
+
+// DEBUG (not part of the ABI, used by tools/gpu_probe.py): `ctas` CTAs that each hold an SM (64 KB of shared memory: a GEMM
+// CTA does not fit next to it) and spin for `cycles` clocks -- a stand-in for a concurrent NCCL kernel on a one-GPU box.
+namespace {
+__global__ void __launch_bounds__(128, 1) debug_hold_sms_kernel(long long cycles, unsigned* sink) {
+    extern __shared__ uint8_t hold[];
+    const long long t0 = clock64();
+    unsigned acc = 0;
+    while (clock64() - t0 < cycles) acc += hold[(threadIdx.x * 37) & 0xFFFF];
+    if (acc == 0xFFFFFFFFu && sink != nullptr) *sink = acc;
+}
+}  // namespace
+
+extern "C" int dolomite_b200_debug_hold_sms(int ctas, long long cycles, void* stream) {
+    DOLO_REQUIRE(ctas >= 1 && ctas <= 148 && cycles >= 0 && cycles <= 20000000000ll, "debug_hold_sms: bad arguments");
+    static bool attr_set = false;
+    if (!attr_set) {
+        DOLO_CUDA_OK(cudaFuncSetAttribute(debug_hold_sms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        attr_set = true;
+    }
+    debug_hold_sms_kernel<<<ctas, 128, 65536, static_cast<cudaStream_t>(stream)>>>(cycles, nullptr);
+    DOLO_LAUNCH_OK("debug_hold_sms");
     return DOLO_OK;
 }

@@ -46,8 +46,11 @@ int dolo_option_gemm_sm_margin();
 // path is 5 % (reduce-add) to 13 % (store) SLOWER -- 32 extra TMA operations per tile share the queue of the operand loads.
 int dolo_option_gemm_f32_tma_epilogue();
 int dolo_option_attn_fwd_split();  // 0 never / 1 (default) head_dim >= 96 / 2 also head_dim 64, 80: split-softmax forward
-int dolo_option_attn_bwd_variant();  // head_dim 64 / 80 backward: 0 = round-1 softmax warps, 1 (default) = lean, 2 = lean with 4 groups
+int dolo_option_attn_bwd_variant();  // head_dim 64 / 80 backward: 0 = round-1 softmax warps, 1 = lean, 2 (default) = lean + uniform 16-column chunks at head_dim 80 (0.701 vs 0.752 ms, profiles/r02_probe_attn_bwd_uniform_chunks_call80.jsonl; identical to 1 at head_dim 64)
 int dolo_option_attn_bwd_ablate();
+// 1 = GEMM grids have one cluster per tile and running clusters take over pending ones through cluster launch control
+// (hardware work stealing): the grid uses every SM that is free, no margin for concurrent communication kernels needed
+int dolo_option_gemm_dynamic();
 int dolo_option_gemm_l2_hints();  // 1 (default) = evict-first / evict-last operand loads for long-contraction GEMMs
 
 // TMA descriptor encode through the driver entry point (no link-time libcuda dependency).
@@ -345,6 +348,53 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// arrive + expect `bytes` on the barrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_expect_tx_remote(uint64_t* bar, uint32_t bytes, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(remote), "r"(bytes)
+                 : "memory");
+}
+
+// ---------------- cluster launch control: work stealing over the clusters of the grid that have not started ----------------
+// A running cluster asks the hardware to CANCEL one pending cluster of its own grid and receives that cluster's first CTA
+// id (16-byte response written to shared memory, completion signalled on an mbarrier as 16 transaction bytes) -- or a
+// "nothing left" response, after which no further request may be issued.  A grid of one cluster per tile therefore
+// behaves like a persistent kernel whose workers take tiles as they get free, on however many SMs the hardware could
+// give the grid (concurrent NCCL kernels hold some).
+__device__ __forceinline__ void clc_try_cancel(void* response, uint64_t* bar) {
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(
+                     smem_u32(response)),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+// the response (and the 16 transaction bytes) go to the same shared-memory offsets in EVERY CTA of the requesting cluster
+__device__ __forceinline__ void clc_try_cancel_multicast(void* response, uint64_t* bar) {
+    asm volatile(
+        "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];" ::
+            "r"(smem_u32(response)),
+        "r"(smem_u32(bar))
+        : "memory");
+}
+// decodes a response: true + blockIdx.x of the first CTA of the cancelled cluster, or false (no pending cluster was left)
+__device__ __forceinline__ bool clc_query(const void* response, int& first_ctaid_x) {
+    uint32_t ok, x;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b128 resp;\n\t"
+        "ld.shared.b128 resp, [%2];\n\t"
+        "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p, resp;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "mov.u32 %1, 0;\n\t"
+        "@p clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %1, resp;\n\t"
+        "}\n"
+        : "=r"(ok), "=r"(x)
+        : "r"(smem_u32(response))
+        : "memory");
+    first_ctaid_x = int(x);
+    return ok != 0;
 }
 
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32

@@ -25,10 +25,11 @@ constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int EPI_SLAB_BYTES = BM * 64 * 2;  // 128 rows x 64 bf16 columns, SW128
 constexpr int EPI_BUFS = 2;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 224;  // warp 0 TMA producer, 1 MMA issuer, 2..5 epilogue, 6 tile scheduler (dynamic mode)
+constexpr int CLC_DEPTH = 4;       // tile-id responses in flight between the scheduler warp and the slowest role
 constexpr int TMEM_COLS = 512;  // 2 accumulator stages x 256 fp32 columns
 
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BUFS * EPI_SLAB_BYTES + 256 /*barriers*/;
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BUFS * EPI_SLAB_BYTES + 512 /*barriers*/;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 
 constexpr int MAXP = 4;  // problems per launch (the four weight gradients of a transformer block share one launch)
@@ -61,6 +62,7 @@ struct GemmParams {
     Problem pr[MAXP];
     int n_prob;
     int num_tiles;  // over all problems (grouped modes: single problem, includes the group factor)
+    int dynamic;    // 1 = the grid has one cluster per tile and running clusters steal pending ones (cluster launch control)
     int d_is_f32;
     // grouped modes (MoE experts; moe_dolomite/moe/scatter.py:38-49 parallel_linear):
     //   1 = M-grouped: every 128-row tile of A/D belongs to one group (m_tile_group[m_blk], -1 = unused tile); B's outer
@@ -134,6 +136,42 @@ __device__ __forceinline__ TileInfo tile_info(int t, const GemmParams& p) {
     return ti;
 }
 
+// Where a role (producer / MMA issuer / epilogue warp) gets its next tile from.  Static mode: worker w takes tiles w,
+// w + W, ...  Dynamic mode: the scheduler warp of the leader CTA keeps up to CLC_DEPTH cluster-launch-control requests
+// ahead; every role of every CTA of the cluster consumes every response (the last one says "grid exhausted") and releases
+// the slot on the LEADER's empty barrier.
+template <bool CTA2>
+struct TileFeed {
+    const uint4* resp;
+    uint64_t* full;
+    uint64_t* empty;
+    int slot;
+    uint32_t phase;
+    int step;  // static mode: number of workers
+    bool dynamic;
+    __device__ __forceinline__ TileFeed(const GemmParams& p, const uint4* r, uint64_t* f, uint64_t* e, int num_workers)
+        : resp(r), full(f), empty(e), slot(0), phase(0), step(num_workers), dynamic(p.dynamic != 0) {}
+    // `release` = this thread reports the slot as consumed for its role (one thread per role instance)
+    __device__ __forceinline__ bool next(int& t, int num_tiles, bool release, bool whole_warp, int tag) {
+        if (!dynamic) {
+            t += step;
+            return t < num_tiles;
+        }
+        mbar_wait(&full[slot], phase, tag);
+        int x;
+        const bool ok = clc_query(&resp[slot], x);
+        fence_proxy_async_smem();  // the slot's next write comes from the async proxy
+        if (whole_warp) __syncwarp();  // every lane has read the response before lane 0 hands the slot back
+        if (release) {
+            if constexpr (CTA2) mbar_arrive_remote(&empty[slot], 0);
+            else mbar_arrive(&empty[slot]);
+        }
+        if (++slot == CLC_DEPTH) { slot = 0; phase ^= 1; }
+        t = CTA2 ? (x >> 1) : x;
+        return ok;
+    }
+};
+
 // CTA2 = CTA-pair mode: a cluster of two CTAs computes a 256 x 256 tile with tcgen05.mma.cta_group::2 (M = 256).  Each
 // CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 N rows), so a pipeline stage is 32 KB instead
 // of 48 KB (6 stages instead of 4) and B is fetched from L2 once per pair.  The MMA is issued by the leader CTA
@@ -157,12 +195,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     uint64_t* tmem_full = bars + 2 * NSTAGE;     // [2]
     uint64_t* tmem_empty = bars + 2 * NSTAGE + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+    uint4* clc_resp = reinterpret_cast<uint4*>(bars + 24);  // [CLC_DEPTH] 16-byte responses (dynamic mode)
+    uint64_t* clc_full = bars + 32;                         // [CLC_DEPTH]
+    uint64_t* clc_empty = bars + 36;                        // [CLC_DEPTH] (the leader CTA's are the ones in use)
+    static_assert(2 * NSTAGE + 5 <= 24 && (36 + CLC_DEPTH) * 8 <= 512, "barrier block layout");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = p.num_tiles;
     const int cta_rank = CTA2 ? int(blockIdx.x & 1) : 0;          // == %cluster_ctarank for cluster dims (2,1,1)
     const int worker = CTA2 ? int(blockIdx.x >> 1) : int(blockIdx.x);  // persistent worker (CTA or CTA pair) index
+                                                                       // == first tile in dynamic mode
     const int num_workers = CTA2 ? int(gridDim.x >> 1) : int(gridDim.x);
 
     if (warp == 0 && lane == 0) {
@@ -178,6 +221,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], CTA2 ? 8 : 4);  // one arrive per epilogue warp (of both CTAs in pair mode)
+        }
+        for (int i = 0; i < CLC_DEPTH; ++i) {
+            mbar_init(&clc_full[i], 1);                // the scheduler's arrive.expect_tx (+ 16 response bytes)
+            mbar_init(&clc_empty[i], CTA2 ? 11 : 6);   // producer(s) + MMA issuer + epilogue warps
         }
         mbar_fence_init();
     }
@@ -246,7 +293,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         } else if (elect_one()) {  // uniform single-thread region: ptxas keeps descriptors in uniform registers
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = worker; t < num_tiles; t += num_workers) {
+            TileFeed<CTA2> feed(p, clc_resp, clc_full, clc_empty, num_workers);
+            int t = worker;
+            for (bool have = t < num_tiles; have; have = feed.next(t, num_tiles, true, false, 11)) {
                 const TileInfo ti = tile_info(t, p);
                 if (!ti.valid) continue;
                 const CUtensorMap* tmap_a = &maps.a[ti.q];
@@ -307,7 +356,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = worker; t < num_tiles; t += num_workers) {
+            TileFeed<CTA2> feed(p, clc_resp, clc_full, clc_empty, num_workers);
+            int t = worker;
+            for (bool have = t < num_tiles; have; have = feed.next(t, num_tiles, true, false, 12)) {
                 const TileInfo ti = tile_info(t, p);
                 if (!ti.valid) continue;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
@@ -341,6 +392,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
+    } else if (warp == 6) {
+        // ================= tile scheduler (dynamic mode; leader CTA only) =================
+        if (p.dynamic != 0 && cta_rank == 0 && elect_one()) {
+            int slot = 0;
+            uint32_t phase = 0;
+            for (;;) {
+                mbar_wait(&clc_empty[slot], phase ^ 1, 20);  // every role of both CTAs has read the previous response
+                mbar_expect_tx(&clc_full[slot], 16);
+                if constexpr (CTA2) {
+                    mbar_expect_tx_remote(&clc_full[slot], 16, 1);
+                    clc_try_cancel_multicast(&clc_resp[slot], &clc_full[slot]);
+                } else {
+                    clc_try_cancel(&clc_resp[slot], &clc_full[slot]);
+                }
+                mbar_wait(&clc_full[slot], phase, 21);
+                int x;
+                const bool ok = clc_query(&clc_resp[slot], x);
+                fence_proxy_async_smem();
+                if (++slot == CLC_DEPTH) { slot = 0; phase ^= 1; }
+                if (!ok) break;  // no request may follow a failed one
+            }
+        }
     } else {
         // ================= epilogue (4 warps, TMEM sub-partition = warp % 4) =================
         const int sub = warp & 3;
@@ -351,7 +424,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         bool cta_stores = false, warp_stores = false;  // which kind of bulk group this thread may still have in flight
         uint8_t* wslab = smem_epi + sub * (EPI_BUFS * EPI_SLAB_BYTES / 4);  // this warp's two private 4 KB slabs (fp32 modes)
         int wbuf = 0;
-        for (int t = worker; t < num_tiles; t += num_workers) {
+        TileFeed<CTA2> feed(p, clc_resp, clc_full, clc_empty, num_workers);
+        int t = worker;
+        for (bool have = t < num_tiles; have; have = feed.next(t, num_tiles, lane == 0, true, 13)) {
             const TileInfo ti = tile_info(t, p);
             if (!ti.valid) continue;
             const Problem& pr = p.pr[ti.q];
@@ -543,7 +618,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 }
 
 template <bool A_MN, bool B_MN>
-int launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t st, bool cta_pair) {
+int launch_gemm(const GemmMaps& maps, const GemmParams& p_in, cudaStream_t st, bool cta_pair) {
+    // Dynamic mode: one cluster per tile, running clusters cancel + take over pending ones (TileFeed).  The grid then
+    // uses whatever SMs are free when it starts -- and the ones that get free while it runs -- so gemm_sm_margin is moot.
+    GemmParams p = p_in;
+    p.dynamic = (dolo_option_gemm_dynamic() != 0 && p.a_row_index == nullptr) ? 1 : 0;
     const int tiles = p.num_tiles;
     if (cta_pair) {
         auto kern = gemm_bf16_kernel<A_MN, B_MN, true>;
@@ -554,7 +633,7 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t st, bool
         }
         const int pairs = (dolo_num_sms() - dolo_option_gemm_sm_margin()) / 2;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(unsigned(2 * (tiles < pairs ? tiles : pairs)));
+        cfg.gridDim = dim3(unsigned(2 * ((p.dynamic || tiles < pairs) ? tiles : pairs)));
         cfg.blockDim = dim3(GEMM_THREADS);
         cfg.dynamicSmemBytes = SMEM_BYTES;
         cfg.stream = st;
@@ -575,7 +654,7 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t st, bool
         attr_set = true;
     }
     const int sms = dolo_num_sms() - dolo_option_gemm_sm_margin();
-    const int grid = tiles < sms ? tiles : sms;
+    const int grid = (p.dynamic || tiles < sms) ? tiles : sms;
     kern<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(maps, p);
     DOLO_LAUNCH_OK("gemm_bf16");
     return DOLO_OK;

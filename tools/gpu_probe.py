@@ -242,6 +242,116 @@ def gemm_pair_bench():
 
 
 @case
+def gemm_dynamic():
+    """cluster-launch-control tile scheduling (gemm_dynamic = 1) against the static persistent schedule: exactness on every
+    operand layout / epilogue, interleaved timing on the C2 shapes at T = 24576, and both next to a kernel that HOLDS 8 SMs
+    (stand-in for a concurrent NCCL collective): static grid over all SMs, static grid with the 8-SM margin, dynamic"""
+    import ctypes
+
+    torch = _t()
+    from dolomite_engine_b200 import _lib
+    from dolomite_engine_b200 import kernels as k
+
+    res = {}
+    ok = True
+    shapes = {
+        "nt_256": (256, 256, 64, False, False, dict(flags=4)),
+        "nt_tma": (512, 1024, 512, False, False, dict(flags=5)),
+        "nt_ragged_bias": (300, 520, 328, False, False, dict(flags=5, bias=True)),
+        "nt_bias_c": (384, 512, 256, False, False, dict(flags=4, with_c=True, bias=True, alpha=0.5)),
+        "nn_bmn": (512, 768, 512, False, True, dict(flags=5)),
+        "tn_amn": (512, 768, 512, True, False, dict(flags=5)),
+        "tt_wgrad": (640, 512, 1024, True, True, dict(flags=4, out_f32=True, with_c=True)),
+        "many_tiles": (8192, 8192, 512, False, False, dict(flags=5)),
+        "odd_super_tiles": (128 * 7, 256 * 3, 192, False, False, dict(flags=5)),
+        "single_many_tiles": (4096 + 64, 4096, 512, False, False, dict(flags=8)),
+        "single_wgrad": (640, 512, 1024, True, True, dict(flags=8, out_f32=True, with_c=True)),
+        "single_row_tile": (100, 2560, 2560, False, False, dict(flags=0)),
+    }
+    try:
+        k.set_option("gemm_dynamic", 1)
+        for name, (M, N, Kd, a_mn, b_mn, kw) in shapes.items():
+            r = _gemm_case(M, N, Kd, a_mn, b_mn, **kw)
+            res["dyn_" + name] = r["rel_l2"]
+            ok = ok and r["ok"]
+        # bit-identical to the static schedule (same tiles, same arithmetic)
+        g = torch.Generator(device="cuda").manual_seed(3)
+        A = (torch.randn(4096, 2560, device="cuda", generator=g) * 0.5).bfloat16()
+        B = (torch.randn(7680, 2560, device="cuda", generator=g) * 0.5).bfloat16()
+        d_dyn = k.gemm(A, B, flags=5)
+        k.set_option("gemm_dynamic", 0)
+        d_sta = k.gemm(A, B, flags=5)
+        res["bit_identical"] = bool(torch.equal(d_dyn, d_sta))
+        ok = ok and res["bit_identical"]
+
+        # ---- timing, interleaved ----
+        T, H, F = 24576, 2560, 10240
+        x = (torch.randn(T, H, device="cuda", generator=g) * 0.1).bfloat16()
+        w_fc = (torch.randn(2 * F, H, device="cuda", generator=g) * 0.02).bfloat16()
+        y_fc = torch.empty(T, 2 * F, device="cuda", dtype=torch.bfloat16)
+        w_attn = (torch.randn(3 * H, H, device="cuda", generator=g) * 0.02).bfloat16()
+        y_attn = torch.empty(T, 3 * H, device="cuda", dtype=torch.bfloat16)
+        dx = torch.empty(T, H, device="cuda", dtype=torch.bfloat16)
+        a_proj = (torch.randn(T, F, device="cuda", generator=g) * 0.1).bfloat16()
+        w_proj = (torch.randn(H, F, device="cuda", generator=g) * 0.02).bfloat16()
+        probs = []
+        for M, N in ((H, F), (2 * F, H), (H, H), (3 * H, H)):
+            dy = (torch.randn(T, M, device="cuda", generator=g) * 0.1).bfloat16()
+            xx = (torch.randn(T, N, device="cuda", generator=g) * 0.1).bfloat16()
+            probs.append((dy, xx, torch.zeros(M, N, device="cuda"), 1.0, True))
+        work = {
+            "fwd_fc": (lambda: k.gemm(x, w_fc, out=y_fc, flags=5), 2.0 * T * 2 * F * H),
+            "fwd_qkv": (lambda: k.gemm(x, w_attn, out=y_attn, flags=5), 2.0 * T * 3 * H * H),
+            "fwd_proj": (lambda: k.gemm(a_proj, w_proj, out=dx, flags=5), 2.0 * T * H * F),
+            "dgrad_fc": (lambda: k.gemm(y_fc, w_fc, b_mn=True, out=dx, flags=5), 2.0 * T * 2 * F * H),
+            "wgrad_block": (lambda: k.gemm_wgrad_multi(probs), sum(2.0 * T * p[2].shape[0] * p[2].shape[1] for p in probs)),
+        }
+        for name, (fn, flops) in work.items():
+            ts = {0: [], 1: []}
+            for _ in range(3):
+                for dyn in (0, 1):
+                    k.set_option("gemm_dynamic", dyn)
+                    ts[dyn].append(_time(fn, iters=10, warmup=2))
+            res[name] = {"static_tflops": round(flops / min(ts[0]) / 1e9), "dynamic_tflops": round(flops / min(ts[1]) / 1e9),
+                         "static_ms": ts[0], "dynamic_ms": ts[1]}
+
+        # ---- next to a kernel that holds 8 SMs ----
+        lib = _lib.load()
+        hold = lib.dolomite_b200_debug_hold_sms
+        hold.argtypes = [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p]
+        hold.restype = ctypes.c_int
+        side = torch.cuda.Stream()
+        fn, flops = work["fwd_fc"]
+
+        def timed(hold_ms, n=6):
+            torch.cuda.synchronize()
+            if hold_ms > 0:
+                rc = hold(8, int(hold_ms * 1.9e6), side.cuda_stream)
+                assert rc == 0
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+
+        for label, dyn, margin in (("static_all_sms", 0, 0), ("static_margin8", 0, 8), ("dynamic", 1, 0)):
+            k.set_option("gemm_dynamic", dyn)
+            k.set_option("gemm_sm_margin", margin)
+            timed(0)
+            res["hold_" + label] = {"alone_ms": min(timed(0) for _ in range(2)),
+                                    "held_whole_time_ms": min(timed(40) for _ in range(2)),
+                                    "held_first_third_ms": min(timed(3.5) for _ in range(2))}
+    finally:
+        k.set_option("gemm_dynamic", 0)
+        k.set_option("gemm_sm_margin", 0)
+    res["ok"] = ok
+    return res
+
+
+@case
 def gemm_bench_wgrad_splitk():
     """weight-gradient shapes of one C2 block: accumulate-in-place epilogue vs split-K atomic epilogue"""
     torch = _t()
@@ -770,7 +880,7 @@ def _attn_bwd_variants(S, B, nh, hd, rounds=3):
                 k.set_option("attn_bwd_variant", variant)
                 times[variant].append(_time(lambda: k.attn_varlen_bwd(dout, qkv, out, lse, cu, S, nh, 1, hd, scale, dqkv=dqkv), iters=5))
     finally:
-        k.set_option("attn_bwd_variant", 1)
+        k.set_option("attn_bwd_variant", 2)
     for variant, ts in times.items():
         res[f"variant{variant}_ms"] = ts
         res[f"variant{variant}_tflops_causal"] = flops / min(ts) / 1e9
