@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdolomite_b200.so")
@@ -22,6 +22,7 @@ _P = c_void_p
 _I = c_int
 _L = c_int64
 _F = c_float
+_U = c_uint32
 
 # name -> (restype, argtypes).  Must list every symbol include/dolomite_b200.h declares
 # (tests/test_abi.py cross-checks this table against the header).
@@ -51,6 +52,8 @@ SIGNATURES: dict[str, tuple] = {
     "dolomite_b200_colsum_accum": (_I, [_P, _L, _P, _L, _L, _F, _P]),
     "dolomite_b200_scale_bf16_by_device_scalar": (_I, [_P, _L, _P, _P]),
     "dolomite_b200_add_scaled": (_I, [_P, _P, _P, _F, _L, _P]),
+    "dolomite_b200_dropout_fwd": (_I, [_P, _P, _P, _L, _F, _F, _U, _U, _P]),
+    "dolomite_b200_dropout_bwd": (_I, [_P, _P, _L, _F, _F, _U, _U, _P]),
     "dolomite_b200_sumsq_accum": (_I, [_P, _L, _P, _P]),
     "dolomite_b200_clip_coef": (_I, [_P, _F, _P, _P, _P]),
     "dolomite_b200_adamw_step": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _L, _P, _P]),
@@ -77,6 +80,11 @@ SIGNATURES: dict[str, tuple] = {
     "dolomite_b200_attn_varlen_bwd": (
         _I,
         [_P, _P, _L, _P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _F, _P, _P],
+    ),
+    "dolomite_b200_attn_varlen_fwd_dropout": (_I, [_P, _L, _P, _P, _P, _I, _L, _I, _I, _I, _I, _F, _F, _U, _U, _P]),
+    "dolomite_b200_attn_varlen_bwd_dropout": (
+        _I,
+        [_P, _P, _L, _P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _F, _F, _U, _U, _P, _P],
     ),
 }
 
@@ -127,7 +135,8 @@ KERNELS_PER_CALL = {
     "dolomite_b200_scale_bf16_by_device_scalar": 1, "dolomite_b200_add_scaled": 1, "dolomite_b200_sumsq_accum": 1,
     "dolomite_b200_clip_coef": 1, "dolomite_b200_adamw_step": 1, "dolomite_b200_cast_f32_to_bf16": 1,
     "dolomite_b200_accum_bf16_into_f32": 1, "dolomite_b200_gemm_bf16": 1, "dolomite_b200_attn_varlen_fwd": 1,
-    "dolomite_b200_attn_varlen_bwd": 3,
+    "dolomite_b200_attn_varlen_bwd": 3, "dolomite_b200_attn_varlen_fwd_dropout": 1, "dolomite_b200_attn_varlen_bwd_dropout": 3,
+    "dolomite_b200_dropout_fwd": 1, "dolomite_b200_dropout_bwd": 1,
 }
 launch_counts: dict[str, int] = {}
 

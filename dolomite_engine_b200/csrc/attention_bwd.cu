@@ -31,6 +31,7 @@ struct BwdParams {
     int64_t T;
     int n_groups, q_per_group, n_heads;
     float scale, scale_log2;
+    AttnDropout drop;  // attention-probability dropout of the forward being differentiated (threshold 0: none)
     int ablate;  // TIMING EXPERIMENTS ONLY (wrong results): see dolo_option_attn_bwd_ablate
     unsigned long long* trace;  // DEBUG timeline buffer (5 roles x 2048 events) or nullptr
     int trace_cta;
@@ -297,6 +298,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             mbar_wait(sdp_full, uint32_t(it & 1), 25);
             tc_fence_after();
             const bool diag = (i == j);
+            const bool drop = p.drop.threshold != 0;
+            const uint32_t head_key = dropout_head_key(uint32_t(head), p.drop.key0, p.drop.key1);
 #pragma unroll 1
             for (int ch = 0; ch < 4; ++ch) {
                 uint32_t sv[32], dv[32];
@@ -312,8 +315,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
                         const int c = ch * 32 + c2 + u;  // query column
                         float pe = fast_exp2(__uint_as_float(sv[c2 + u]) * p.scale_log2 - sLSE[c]);
                         if (!key_ok || (diag && r > c)) pe = 0.f;
+                        float dpe = __uint_as_float(dv[c2 + u]);
                         pv[u] = pe;
-                        dsv[u] = pe * (__uint_as_float(dv[c2 + u]) - sDelta[c]) * p.scale;
+                        if (drop) {  // dV takes the dropped probabilities, dP passes through the same mask; dS uses the undropped P
+                            const float ms = attn_drop_scale(p.drop, head_key, loc.doc_start + i * ATT_TILE + c, loc.doc_start + kj);
+                            pv[u] = pe * ms;
+                            dpe *= ms;
+                        }
+                        dsv[u] = pe * (dpe - sDelta[c]) * p.scale;
                     }
                     pp[c2 >> 1] = pack_bf16(pv[0], pv[1]);
                     dd[c2 >> 1] = pack_bf16(dsv[0], dsv[1]);
@@ -522,11 +531,23 @@ extern "C" int64_t dolomite_b200_attn_varlen_bwd_workspace_bytes(int64_t T, int 
     return align256(nh * T * 4) + align256(T * nh * head_dim * 4) + 256;
 }
 
+uint32_t dolo_dropout_threshold(float p);  // dropout.cu
+
 extern "C" int dolomite_b200_attn_varlen_bwd(const void* dout, const void* qkv, int64_t row_stride, const void* out,
                                              const float* lse, void* dqkv, const int32_t* cu_seqlens, int n_docs,
                                              int64_t T, int max_seqlen, int n_groups, int q_per_group, int head_dim,
                                              float softmax_scale, void* workspace, void* stream) {
+    return dolomite_b200_attn_varlen_bwd_dropout(dout, qkv, row_stride, out, lse, dqkv, cu_seqlens, n_docs, T, max_seqlen,
+                                                 n_groups, q_per_group, head_dim, softmax_scale, 0.f, 0, 0, workspace, stream);
+}
+
+extern "C" int dolomite_b200_attn_varlen_bwd_dropout(const void* dout, const void* qkv, int64_t row_stride, const void* out,
+                                                     const float* lse, void* dqkv, const int32_t* cu_seqlens, int n_docs,
+                                                     int64_t T, int max_seqlen, int n_groups, int q_per_group,
+                                                     int head_dim, float softmax_scale, float dropout_p, uint32_t key0,
+                                                     uint32_t key1, void* workspace, void* stream) {
     (void)max_seqlen;
+    DOLO_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attn_bwd: dropout_p=%f must be in [0, 1)", double(dropout_p));
     if (T == 0 || n_docs == 0) return DOLO_OK;
     DOLO_REQUIRE(n_groups > 0 && q_per_group > 0, "attn_bwd: bad head grouping");
     DOLO_REQUIRE(row_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
@@ -560,11 +581,16 @@ extern "C" int dolomite_b200_attn_varlen_bwd(const void* dout, const void* qkv, 
     p.n_heads = nh;
     p.scale = softmax_scale;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
+    p.drop.threshold = dolo_dropout_threshold(dropout_p);
+    p.drop.keep_scale = 1.f / (1.f - dropout_p);
+    p.drop.key0 = key0;
+    p.drop.key1 = key1;
     p.ablate = dolo_option_attn_bwd_ablate();
     p.trace = g_bwd_trace;
     p.trace_cta = g_bwd_trace_cta;
     int rc;
-    const int variant = dolo_option_attn_bwd_variant();
+    // dropout lives in the round-1 softmax warps of the pipelined kernel only (the lean variants have no registers to spare)
+    const int variant = p.drop.threshold != 0 ? 0 : dolo_option_attn_bwd_variant();
     const bool pipelined = head_dim == 64 || head_dim == 80;
     const float dq_scale = (pipelined && variant != 0) ? softmax_scale : 1.f;
     switch (head_dim) {

@@ -538,8 +538,11 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
             named_bar_sync(2, SOFTMAX_THREADS);
             if (it + 1 < n_it) stat_next = fetch_stat(it + 1);
             if (it >= 2) mbar_wait(&dq_full[it & 1], uint32_t((it >> 1) - 1) & 1, 35);  // dS smem buffer free again
-            const bool need_mask = (i == j) || !tile_full;
+            const bool drop = p.drop.threshold != 0;  // dropout: every tile takes the per-element path
+            const bool need_mask = (i == j) || !tile_full || drop;
             const bool diag = (i == j);
+            const int q_tok0 = loc.doc_start + i * ATT_TILE;  // global token of query column 0 of this tile
+            const uint32_t head_key = dropout_head_key(uint32_t(group * p.q_per_group + s_head), p.drop.key0, p.drop.key1);
             uint8_t* ds_buf = sDS + (it & 1) * DS_BYTES;
 
             // one 16-column sub-chunk: P^T = exp2(S^T*scale - lse), dS^T = scale * P^T o (dP^T - delta) -> bf16 pairs,
@@ -556,8 +559,14 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
                             const int c = cbase + c2 + u;
                             float pe = fast_exp2(__uint_as_float(sv[c2 + u]) * p.scale_log2 - lse_s[c]);
                             if (!key_ok || (diag && r > c)) pe = 0.f;
+                            float dpe = __uint_as_float(dv[c2 + u]);
                             pv[u] = pe;
-                            dsv[u] = pe * (__uint_as_float(dv[c2 + u]) - del_s[c]) * p.scale;
+                            if (drop) {
+                                const float ms = attn_drop_scale(p.drop, head_key, q_tok0 + c, loc.doc_start + kj);
+                                pv[u] = pe * ms;
+                                dpe *= ms;
+                            }
+                            dsv[u] = pe * (dpe - del_s[c]) * p.scale;
                         }
                         pp[c2 >> 1] = pack_bf16(pv[0], pv[1]);
                         dd[c2 >> 1] = pack_bf16(dsv[0], dsv[1]);

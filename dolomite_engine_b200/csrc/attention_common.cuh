@@ -41,6 +41,19 @@ __device__ __forceinline__ uint64_t chunk_desc_mnmajor(uint32_t chunk_saddr, int
     return umma_smem_desc(chunk_saddr + k16 * 32 * w, 16 * w, 16 * w, chunk_layout_type(w));
 }
 
+// Attention-probability dropout (attention/base.py:252 `attn_dropout`; flash_attn_varlen_func(dropout_p=...) at
+// attention/padding_free.py:49-59): P_ij is kept with probability 1 - p and scaled by 1 / (1 - p) AFTER the softmax
+// normaliser was taken over the undropped row.  The mask is a hash of (global query token, global key token, head) and the
+// keys of the call site, so the backward kernels regenerate it.  threshold == 0 <=> no dropout.
+struct AttnDropout {
+    uint32_t threshold;
+    float keep_scale;
+    uint32_t key0, key1;
+};
+__device__ __forceinline__ float attn_drop_scale(const AttnDropout& d, uint32_t head_key, int q_tok, int k_tok) {
+    return dropout_hash_qk(uint32_t(q_tok), uint32_t(k_tok), head_key) >= d.threshold ? d.keep_scale : 0.f;
+}
+
 // Locate the (document, q-tile) of a linear tile index by scanning cu_seqlens (B is small: a few docs per row).
 struct TileLoc {
     int doc_start;  // first token of the document

@@ -27,6 +27,7 @@ struct FwdParams {
     int n_heads;
     float scale_log2;  // softmax_scale * log2(e)
     float scale;
+    AttnDropout drop;  // threshold 0: none
 };
 
 template <int HD>
@@ -158,6 +159,8 @@ __global__ void __launch_bounds__(FWD_THREADS)
         const uint32_t t_lane = tmem_base + (uint32_t(sub * 32) << 16);
         const int qi = q0 + r;                         // doc-relative query index
         float m_run = -INFINITY, l_run = 0.f;
+        const bool drop = p.drop.threshold != 0;  // dropout: every tile takes the per-element path below
+        const uint32_t head_key = dropout_head_key(uint32_t(head), p.drop.key0, p.drop.key1);
         for (int j = 0; j < n_kv; ++j) {
             mbar_wait(s_full, uint32_t(j & 1), 14);
             tc_fence_after();
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(FWD_THREADS)
             // pass 2: P = exp2(s*scale - m), row sum; P (bf16) overwrites the already-consumed S columns
             float lsum = 0.f, lsum1 = 0.f;
             const float neg_m = -m_scaled;
-            if (!diag) {
+            if (!diag && !drop) {
                 uint32_t va[32], vb[32];
                 auto expo = [&](const uint32_t (&v)[32], int ch) {
                     uint32_t pk[16];
@@ -280,10 +283,15 @@ __global__ void __launch_bounds__(FWD_THREADS)
                     for (int i = 0; i < 32; i += 2) {
                         float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
                         float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, neg_m));
-                        if (kbase + ch * 32 + i > qi) p0 = 0.f;
+                        if (kbase + ch * 32 + i > qi) p0 = 0.f;  // (never true off the diagonal tile)
                         if (kbase + ch * 32 + i + 1 > qi) p1 = 0.f;
                         lsum += p0;
                         lsum1 += p1;
+                        if (drop) {  // the row sum above is that of the undropped probabilities
+                            const int kt = loc.doc_start + kbase + ch * 32 + i;
+                            p0 *= attn_drop_scale(p.drop, head_key, row_base + r, kt);
+                            p1 *= attn_drop_scale(p.drop, head_key, row_base + r, kt + 1);
+                        }
                         pk[i >> 1] = pack_bf16(p0, p1);
                     }
                     tmem_st16(t_lane + ch * 16, pk);
@@ -497,6 +505,8 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1)
         const int qi = q0 + r;
         const uint32_t pair_bar = 1 + uint32_t(sub);   // named barrier of the two warps that share this row block
         float m_run = -INFINITY, l_run = 0.f;
+        const bool drop = p.drop.threshold != 0;  // dropout: every tile takes the per-element path below
+        const uint32_t head_key = dropout_head_key(uint32_t(head), p.drop.key0, p.drop.key1);
         for (int j = 0; j < n_kv; ++j) {
             const int b = j & 1;
             const uint32_t s_col = t_lane + uint32_t(b) * 128 + uint32_t(g) * 64;
@@ -559,7 +569,7 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1)
             float lsum = 0.f, lsum1 = 0.f;
             const float neg_m = -m_scaled;
             uint32_t pk[16];
-            if (!diag) {
+            if (!diag && !drop) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
                     float x0, x1;
@@ -583,10 +593,14 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1)
                 for (int i = 0; i < 32; i += 2) {
                     float p0 = fast_exp2(fmaf(__uint_as_float(va[i]), p.scale_log2, neg_m));
                     float p1 = fast_exp2(fmaf(__uint_as_float(va[i + 1]), p.scale_log2, neg_m));
-                    if (kbase + i > qi) p0 = 0.f;
+                    if (kbase + i > qi) p0 = 0.f;  // (never true off the diagonal tile)
                     if (kbase + i + 1 > qi) p1 = 0.f;
                     lsum += p0;
                     lsum1 += p1;
+                    if (drop) {
+                        p0 *= attn_drop_scale(p.drop, head_key, row_base + r, loc.doc_start + kbase + i);
+                        p1 *= attn_drop_scale(p.drop, head_key, row_base + r, loc.doc_start + kbase + i + 1);
+                    }
                     pk[i >> 1] = pack_bf16(p0, p1);
                 }
                 tmem_st16(s_col, pk);
@@ -598,6 +612,10 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1)
                     if (kbase + 32 + i + 1 > qi) p1 = 0.f;
                     lsum += p0;
                     lsum1 += p1;
+                    if (drop) {
+                        p0 *= attn_drop_scale(p.drop, head_key, row_base + r, loc.doc_start + kbase + 32 + i);
+                        p1 *= attn_drop_scale(p.drop, head_key, row_base + r, loc.doc_start + kbase + 32 + i + 1);
+                    }
                     pk[i >> 1] = pack_bf16(p0, p1);
                 }
                 tmem_st16(s_col + 16, pk);
@@ -720,10 +738,21 @@ int launch_fwd(const void* qkv, int64_t row_stride, const FwdParams& p, int max_
 
 }  // namespace
 
+uint32_t dolo_dropout_threshold(float p);  // dropout.cu
+
 extern "C" int dolomite_b200_attn_varlen_fwd(const void* qkv, int64_t row_stride, void* out, float* lse,
                                              const int32_t* cu_seqlens, int n_docs, int64_t T, int max_seqlen,
                                              int n_groups, int q_per_group, int head_dim, float softmax_scale,
                                              void* stream) {
+    return dolomite_b200_attn_varlen_fwd_dropout(qkv, row_stride, out, lse, cu_seqlens, n_docs, T, max_seqlen, n_groups,
+                                                 q_per_group, head_dim, softmax_scale, 0.f, 0, 0, stream);
+}
+
+extern "C" int dolomite_b200_attn_varlen_fwd_dropout(const void* qkv, int64_t row_stride, void* out, float* lse,
+                                                     const int32_t* cu_seqlens, int n_docs, int64_t T, int max_seqlen,
+                                                     int n_groups, int q_per_group, int head_dim, float softmax_scale,
+                                                     float dropout_p, uint32_t key0, uint32_t key1, void* stream) {
+    DOLO_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attn_fwd: dropout_p=%f must be in [0, 1)", double(dropout_p));
     DOLO_REQUIRE(n_docs >= 0 && T >= 0, "attn_fwd: negative sizes");
     if (T == 0 || n_docs == 0) return DOLO_OK;
     DOLO_REQUIRE(n_groups > 0 && q_per_group > 0, "attn_fwd: bad head grouping");
@@ -741,6 +770,10 @@ extern "C" int dolomite_b200_attn_varlen_fwd(const void* qkv, int64_t row_stride
     p.n_heads = n_groups * q_per_group;
     p.scale = softmax_scale;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
+    p.drop.threshold = dolo_dropout_threshold(dropout_p);
+    p.drop.keep_scale = 1.f / (1.f - dropout_p);
+    p.drop.key0 = key0;
+    p.drop.key1 = key1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int split = dolo_option_attn_fwd_split();
     switch (head_dim) {

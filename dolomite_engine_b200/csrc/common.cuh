@@ -534,6 +534,32 @@ __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v 
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // 2^x on the MUFU pipe in ONE instruction (exp2f() adds range fix-ups we do not need: inputs are <= 0 or -inf)
+// ---------------- dropout masks (counter-based: the same mask is regenerated in backward and in recomputed blocks) -----------
+// keep <=> hash >= threshold with threshold = round(p * 2^32): P(keep) = 1 - p.  `lowbias32` is the 2-multiply integer
+// finaliser (xorshift-multiply chain); the generator is this library's own -- torch's Philox stream cannot be reproduced
+// by any independent kernel, the distribution (independent Bernoulli(1 - p) masks scaled by 1 / (1 - p)) is what is kept.
+// oracle/dolomite_oracle.py restates both functions in numpy (DropoutOracle), bit for bit.
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x21f0aaadu;
+    x ^= x >> 15;
+    x *= 0x735a2d97u;
+    x ^= x >> 15;
+    return x;
+}
+// element e of a flat activation tensor (site keys key0 / key1 from the host: seed and call site)
+__device__ __forceinline__ uint32_t dropout_hash_flat(uint64_t e, uint32_t key0, uint32_t key1) {
+    return lowbias32(lowbias32(uint32_t(e) ^ key0) + uint32_t(e >> 32) + key1);
+}
+// attention probability of (query token q, key token k) -- global token rows of the packed stream -- for one head;
+// head_key = dropout_head_key(head, key0, key1) is hoisted out of the loops
+__device__ __forceinline__ uint32_t dropout_head_key(uint32_t head, uint32_t key0, uint32_t key1) {
+    return lowbias32(head * 0xC2B2AE3Du + key0) ^ key1;
+}
+__device__ __forceinline__ uint32_t dropout_hash_qk(uint32_t q, uint32_t k, uint32_t head_key) {
+    return lowbias32((q * 0x9E3779B1u) ^ (k * 0x85EBCA77u) ^ head_key);
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

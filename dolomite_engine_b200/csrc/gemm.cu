@@ -26,7 +26,7 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int EPI_SLAB_BYTES = BM * 64 * 2;  // 128 rows x 64 bf16 columns, SW128
 constexpr int EPI_BUFS = 2;
 constexpr int GEMM_THREADS = 224;  // warp 0 TMA producer, 1 MMA issuer, 2..5 epilogue, 6 tile scheduler (dynamic mode)
-constexpr int CLC_DEPTH = 4;       // tile-id responses in flight between the scheduler warp and the slowest role
+constexpr int CLC_DEPTH = 8;       // tile-id responses in flight between the scheduler warp and the slowest role
 constexpr int TMEM_COLS = 512;  // 2 accumulator stages x 256 fp32 columns
 
 constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BUFS * EPI_SLAB_BYTES + 512 /*barriers*/;
@@ -196,9 +196,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     uint64_t* tmem_empty = bars + 2 * NSTAGE + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
     uint4* clc_resp = reinterpret_cast<uint4*>(bars + 24);  // [CLC_DEPTH] 16-byte responses (dynamic mode)
-    uint64_t* clc_full = bars + 32;                         // [CLC_DEPTH]
-    uint64_t* clc_empty = bars + 36;                        // [CLC_DEPTH] (the leader CTA's are the ones in use)
-    static_assert(2 * NSTAGE + 5 <= 24 && (36 + CLC_DEPTH) * 8 <= 512, "barrier block layout");
+    uint64_t* clc_full = bars + 24 + 2 * CLC_DEPTH;         // [CLC_DEPTH]
+    uint64_t* clc_empty = clc_full + CLC_DEPTH;             // [CLC_DEPTH] (the leader CTA's are the ones in use)
+    static_assert(2 * NSTAGE + 5 <= 24 && (24 + 4 * CLC_DEPTH) * 8 <= 512, "barrier block layout");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -294,8 +294,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             int stage = 0;
             uint32_t phase = 0;
             TileFeed<CTA2> feed(p, clc_resp, clc_full, clc_empty, num_workers);
-            int t = worker;
-            for (bool have = t < num_tiles; have; have = feed.next(t, num_tiles, true, false, 11)) {
+            int t = worker, t_next = 0;
+            bool have_next = false;
+            for (bool have = t < num_tiles; have; t = t_next, have = have_next) {
+                t_next = t;  // the next tile id is taken BEFORE this tile's work: its latency hides behind the pipeline waits
+                have_next = feed.next(t_next, num_tiles, true, false, 11);
                 const TileInfo ti = tile_info(t, p);
                 if (!ti.valid) continue;
                 const CUtensorMap* tmap_a = &maps.a[ti.q];
@@ -357,8 +360,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             int acc = 0;
             uint32_t acc_phase = 0;
             TileFeed<CTA2> feed(p, clc_resp, clc_full, clc_empty, num_workers);
-            int t = worker;
-            for (bool have = t < num_tiles; have; have = feed.next(t, num_tiles, true, false, 12)) {
+            int t = worker, t_next = 0;
+            bool have_next = false;
+            for (bool have = t < num_tiles; have; t = t_next, have = have_next) {
+                t_next = t;  // the next tile id is taken BEFORE this tile's work: its latency hides behind the pipeline waits
+                have_next = feed.next(t_next, num_tiles, true, false, 12);
                 const TileInfo ti = tile_info(t, p);
                 if (!ti.valid) continue;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
@@ -425,8 +431,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         uint8_t* wslab = smem_epi + sub * (EPI_BUFS * EPI_SLAB_BYTES / 4);  // this warp's two private 4 KB slabs (fp32 modes)
         int wbuf = 0;
         TileFeed<CTA2> feed(p, clc_resp, clc_full, clc_empty, num_workers);
-        int t = worker;
-        for (bool have = t < num_tiles; have; have = feed.next(t, num_tiles, lane == 0, true, 13)) {
+        int t = worker, t_next = 0;
+        bool have_next = false;
+        for (bool have = t < num_tiles; have; t = t_next, have = have_next) {
+            t_next = t;  // the next tile id is taken BEFORE this tile's work: its latency hides behind the pipeline waits
+            have_next = feed.next(t_next, num_tiles, lane == 0, true, 13);
             const TileInfo ti = tile_info(t, p);
             if (!ti.valid) continue;
             const Problem& pr = p.pr[ti.q];

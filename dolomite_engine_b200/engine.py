@@ -196,8 +196,6 @@ def check_supported(cfg: CommonConfig) -> None:
             f"position_embedding_type={cfg.position_embedding_type!r}: the B200 path implements rope, nope and "
             "learned_absolute (alibi is unsupported with flash attention in the reference too, gpt_dolomite/base.py:530)"
         )
-    if cfg.position_embedding_type == "learned_absolute" and cfg.m_emb is not None:
-        raise NotImplementedError("learned_absolute positions combined with m_emb are not implemented")
     if cfg.rope_scaling is not None:
         rs = cfg.rope_scaling
         if not isinstance(rs, dict) or "factor" not in rs or "original_max_position_embeddings" not in rs:
@@ -212,8 +210,8 @@ def check_supported(cfg: CommonConfig) -> None:
             f"activation_function={cfg.activation_function!r}: swiglu and gelu_pytorch_tanh are implemented in CUDA")
     if cfg.model_type == "moe_dolomite" and (cfg.activation_function != "swiglu" or cfg.normalization_function != "rmsnorm"):
         raise NotImplementedError("MoE blocks are implemented for swiglu + rmsnorm (the MoEDolomite / Granite-MoE shape)")
-    # dropout > 0 is accepted at construction (evaluation / generation of such checkpoints: dropout is the identity in eval
-    # mode) and rejected by `forward` in training mode, where no dropout kernel exists
+    # dropout > 0: identity in eval mode; in training mode the residual / embedding dropouts are elementwise kernels
+    # (csrc/dropout.cu) and the attention-probability dropout lives inside the attention kernels
     hd = cfg.n_embd // cfg.n_head
     if hd not in (16, 32, 64, 80, 96, 128):
         raise NotImplementedError(f"head_dim={hd}: supported head dims are 16, 32, 64, 80, 96, 128")
@@ -247,6 +245,11 @@ class DolomiteEngine:
         self.learned_positions = cfg.position_embedding_type == "learned_absolute"
         self.has_dropout = bool(cfg.resid_pdrop or cfg.embd_pdrop or cfg.attn_pdrop)
         self.training = True  # mirrors nn.Module.training of the owning model (DolomitePreTrainedModel.train)
+        # Dropout masks are counter-based (kernels.dropout_keys): seed of the pass = dropout_seed + passes so far; backward
+        # and re-computed (checkpointed) blocks regenerate the masks of their forward from the seed kept in `_saved`.
+        self.dropout_seed: int | None = None  # None: torch.initial_seed() mixed with the rank on first use
+        self._dropout_passes = 0
+        self._dropout_now: int | None = None  # seed of the pass being run / backpropagated; None = no dropout (eval)
         self.units: list[FlatUnit] = [FlatUnit("root", _root_specs(cfg), world_size, rank)]
         for i in range(cfg.n_layer):
             self.units.append(FlatUnit(f"h.{i}", _block_specs(cfg, i), world_size, rank))
@@ -417,6 +420,25 @@ class DolomiteEngine:
                                    unit.gviews.get(prefix + "bias"), dx_add=dx_add)
         return K.rmsnorm_bwd(dy, x, unit.views[prefix + "weight"], stats, unit.gviews[prefix + "weight"], dx_add=dx_add)
 
+    # dropout call sites of one pass: 0 = embeddings, 4 i + 1 / + 2 / + 3 = block i attention residual / MLP residual /
+    # attention probabilities
+    def _drop_p(self, kind: str) -> float:
+        if self._dropout_now is None:
+            return 0.0
+        return float(getattr(self.cfg, kind) or 0.0)
+
+    def _drop_keys(self, site: int) -> tuple[int, int]:
+        return K.dropout_keys(self._dropout_now, site)
+
+    def _begin_dropout_pass(self) -> None:
+        if not (self.has_dropout and self.training):
+            self._dropout_now = None
+            return
+        if self.dropout_seed is None:
+            self.dropout_seed = (int(torch.initial_seed()) + 0x632BE59BD9B4E019 * (self.rank + 1)) & ((1 << 63) - 1)
+        self._dropout_now = (self.dropout_seed + self._dropout_passes) & ((1 << 63) - 1)
+        self._dropout_passes += 1
+
     def _is_checkpointed(self, i: int) -> bool:
         k = self.checkpoint_every
         return k is not None and k > 0 and i % k == 0
@@ -433,19 +455,30 @@ class DolomiteEngine:
             K.rope_qk_inplace(qkv, self.n_groups, self.q_per_group, self.hd, self.rope_cos, self.rope_sin, position_ids)
         if self._kv_sink is not None:  # prefill of a KV cache: keys (rotated) and values of every prompt token
             self._kv_sink(i, qkv)
-        attn, lse = K.attn_varlen_fwd(qkv, cu_seqlens, max_seqlen, self.n_groups, self.q_per_group, self.hd, self.softmax_scale)
-        h_mid = K.gemm(attn, u.views[p + "attn.c_proj.weight"], bias=u.views.get(p + "attn.c_proj.bias"), c=x_in,
-                       alpha=m_res, beta=1.0)
+        p_att = self._drop_p("attn_pdrop")
+        attn, lse = K.attn_varlen_fwd(qkv, cu_seqlens, max_seqlen, self.n_groups, self.q_per_group, self.hd, self.softmax_scale,
+                                      dropout_p=p_att, dropout_keys=self._drop_keys(4 * i + 3) if p_att > 0 else (0, 0))
+        p_res = self._drop_p("resid_pdrop")
+        if p_res > 0:  # resid_dropout sits between c_proj and `* m_residual` / `+ residual` (padding_free.py:75, layer.py:73-77)
+            y = K.gemm(attn, u.views[p + "attn.c_proj.weight"], bias=u.views.get(p + "attn.c_proj.bias"))
+            h_mid = K.dropout_fwd(y, p_res, self._drop_keys(4 * i + 1), residual=x_in, post_mul=m_res, out=y)
+        else:
+            h_mid = K.gemm(attn, u.views[p + "attn.c_proj.weight"], bias=u.views.get(p + "attn.c_proj.bias"), c=x_in,
+                           alpha=m_res, beta=1.0)
         ln2, rstd2 = self._norm_fwd(h_mid, u, p + "ln_2.")
         if self.is_moe:
             from . import moe
 
-            h, moe_saved = moe.forward(self, u, p, ln2, h_mid, m_res)
+            h, moe_saved = moe.forward(self, u, p, ln2, h_mid, m_res, layer=i)
             return h, (x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, moe_saved)
         fc = K.gemm(ln2, u.views[p + "mlp.c_fc.weight"], bias=u.views.get(p + "mlp.c_fc.bias"))
         act = K.swiglu_fwd(fc) if self.is_glu else K.gelu_fwd(fc)
-        h = K.gemm(act, u.views[p + "mlp.c_proj.weight"], bias=u.views.get(p + "mlp.c_proj.bias"), c=h_mid,
-                   alpha=m_res, beta=1.0)
+        if p_res > 0:  # gpt_dolomite/mlp.py:45-50 then layer.py:82-86
+            y = K.gemm(act, u.views[p + "mlp.c_proj.weight"], bias=u.views.get(p + "mlp.c_proj.bias"))
+            h = K.dropout_fwd(y, p_res, self._drop_keys(4 * i + 2), residual=h_mid, post_mul=m_res, out=y)
+        else:
+            h = K.gemm(act, u.views[p + "mlp.c_proj.weight"], bias=u.views.get(p + "mlp.c_proj.bias"), c=h_mid,
+                       alpha=m_res, beta=1.0)
         return h, (x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, fc, act)
 
     def forward(self, input_ids, position_ids, cu_seqlens, max_seqlen: int, labels=None, ignore_index: int = -100,
@@ -454,20 +487,25 @@ class DolomiteEngine:
         `fuse_head_loss`: the caller will backpropagate d(loss) = 1 (what train_step does), so the LM head's backward can run
         chunk-wise inside the loss computation and the [T, V] logits are never materialised."""
         cfg = self.cfg
-        if self.has_dropout and self.training:
-            raise NotImplementedError("dropout > 0 in training mode is not implemented on the B200 path (the target configs "
-                                      "use p = 0); call .eval() for evaluation / generation, where dropout is the identity")
+        self._begin_dropout_pass()
         T = input_ids.numel()
         root = self.units[0]
         comm = self.comm
         self._ensure_rope(int(max_seqlen))
         if comm is not None:
             comm.pre_forward_unit(0)
-        h = K.embedding_fwd(input_ids, root.views["transformer.wte.weight"], 1.0 if cfg.m_emb is None else float(cfg.m_emb))
-        if self.learned_positions:  # gpt_dolomite/base.py:351-372: wte(ids) + wpe(position_ids), one bf16 rounding
+        m_emb = 1.0 if cfg.m_emb is None else float(cfg.m_emb)
+        p_emb = self._drop_p("embd_pdrop")
+        # gpt_dolomite/base.py:351-372: drop(wte(ids) [+ wpe(position_ids)]) * m_emb.  Without dropout and learned positions the
+        # scale rides on the gather; otherwise it is a separate bf16 multiply after the sum / the mask (p = 0: all kept).
+        post_scale = p_emb > 0 or (self.learned_positions and m_emb != 1.0)
+        h = K.embedding_fwd(input_ids, root.views["transformer.wte.weight"], 1.0 if post_scale else m_emb)
+        if self.learned_positions:  # wte(ids) + wpe(position_ids), one bf16 rounding
             if position_ids.dtype != torch.int64:
                 position_ids = position_ids.long()
             h = K.add_scaled(h, K.embedding_fwd(position_ids, root.views["transformer.wpe.weight"], 1.0), 1.0)
+        if post_scale:
+            h = K.dropout_fwd(h, p_emb, self._drop_keys(0) if p_emb > 0 else (0, 0), post_mul=m_emb, out=h)
         saved_layers = []
         for i in range(cfg.n_layer):
             if comm is not None:
@@ -513,7 +551,8 @@ class DolomiteEngine:
                 logits_out = logits
         if save_for_backward:
             self._saved = dict(input_ids=input_ids, position_ids=position_ids, cu_seqlens=cu_seqlens, max_seqlen=max_seqlen,
-                               layers=saved_layers, h_last=h, rstd_f=rstd_f, hf=hf, dlogits=dlogits, d_hf=d_hf, T=T)
+                               layers=saved_layers, h_last=h, rstd_f=rstd_f, hf=hf, dlogits=dlogits, d_hf=d_hf, T=T,
+                               dropout_seed=self._dropout_now)
         return logits_out, loss
 
     @staticmethod
@@ -645,6 +684,8 @@ class DolomiteEngine:
         inv_width = 1.0 if cfg.m_width is None else 1.0 / float(cfg.m_width)
         m_res = 1.0 if cfg.m_residual is None else float(cfg.m_residual)
         head_name = "transformer.wte.weight" if cfg.tie_word_embeddings else "lm_head.weight"
+        self._dropout_now = s.get("dropout_seed")  # the masks of the forward being backpropagated
+        p_res = self._drop_p("resid_pdrop")
         if comm is not None:
             comm.pre_backward_unit(0)
         if dlogits is None and s.get("d_hf") is not None:
@@ -673,12 +714,17 @@ class DolomiteEngine:
                 from . import moe
 
                 x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, moe_saved = layer
-                d_ln2 = moe.backward(self, u, p, ln2, dh, m_res, moe_saved)
+                d_ln2 = moe.backward(self, u, p, ln2, dh, m_res, moe_saved, layer=i)
             else:
                 x_in, rstd1, ln1, qkv, attn, lse, h_mid, rstd2, ln2, fc, act = layer
                 if self.batch_block_wgrads:
                     self._deferred_wgrads = []
-                d_act = self._linear_bwd(u, p + "mlp.c_proj.weight", p + "mlp.c_proj.bias", act, dh, alpha=m_res)
+                if p_res > 0:
+                    d_y = K.dropout_bwd(dh, p_res, self._drop_keys(4 * i + 2), pre_mul=m_res)
+                    d_act = self._linear_bwd(u, p + "mlp.c_proj.weight", p + "mlp.c_proj.bias", act, d_y)
+                    del d_y
+                else:
+                    d_act = self._linear_bwd(u, p + "mlp.c_proj.weight", p + "mlp.c_proj.bias", act, dh, alpha=m_res)
                 # the c_fc bias gradient (column sums of d_fc) is accumulated by the SwiGLU backward while it writes d_fc
                 act_bwd = K.swiglu_bwd if self.is_glu else K.gelu_bwd
                 d_fc = act_bwd(d_act, fc, bias_grad_accum=u.gviews.get(p + "mlp.c_fc.bias"))
@@ -687,9 +733,16 @@ class DolomiteEngine:
                 del d_fc
             dh_mid = self._norm_bwd(d_ln2, h_mid, u, p + "ln_2.", rstd2, dx_add=dh)
             del d_ln2
-            d_attn = self._linear_bwd(u, p + "attn.c_proj.weight", p + "attn.c_proj.bias", attn, dh_mid, alpha=m_res)
+            if p_res > 0:
+                d_y = K.dropout_bwd(dh_mid, p_res, self._drop_keys(4 * i + 1), pre_mul=m_res)
+                d_attn = self._linear_bwd(u, p + "attn.c_proj.weight", p + "attn.c_proj.bias", attn, d_y)
+                del d_y
+            else:
+                d_attn = self._linear_bwd(u, p + "attn.c_proj.weight", p + "attn.c_proj.bias", attn, dh_mid, alpha=m_res)
+            p_att = self._drop_p("attn_pdrop")
             dqkv = K.attn_varlen_bwd(d_attn, qkv, attn, lse, s["cu_seqlens"], s["max_seqlen"], self.n_groups,
-                                     self.q_per_group, self.hd, self.softmax_scale)
+                                     self.q_per_group, self.hd, self.softmax_scale, dropout_p=p_att,
+                                     dropout_keys=self._drop_keys(4 * i + 3) if p_att > 0 else (0, 0))
             del d_attn
             if self.rope_cos is not None:
                 K.rope_qk_inplace(dqkv, self.n_groups, self.q_per_group, self.hd, self.rope_cos, self.rope_sin,
@@ -704,7 +757,12 @@ class DolomiteEngine:
             s["layers"][i] = None  # free this layer's activations
             if comm is not None:
                 comm.post_backward_unit(i + 1)
-        K.embedding_bwd(s["input_ids"], dh, root.gviews["transformer.wte.weight"], 1.0 if cfg.m_emb is None else float(cfg.m_emb))
+        m_emb = 1.0 if cfg.m_emb is None else float(cfg.m_emb)
+        p_emb = self._drop_p("embd_pdrop")
+        if p_emb > 0 or (self.learned_positions and m_emb != 1.0):
+            dh = K.dropout_bwd(dh, p_emb, self._drop_keys(0) if p_emb > 0 else (0, 0), pre_mul=m_emb, out=dh)
+            m_emb = 1.0
+        K.embedding_bwd(s["input_ids"], dh, root.gviews["transformer.wte.weight"], m_emb)
         if self.learned_positions:
             K.embedding_bwd(s["position_ids"], dh, root.gviews["transformer.wpe.weight"], 1.0)
         if self._fresh_grads:  # a weight that received no gradient in this backward still has to read as zero

@@ -231,6 +231,42 @@ def add_scaled(a, b, alpha: float, out=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# dropout (nn.Dropout after the embeddings / attention c_proj / MLP c_proj; attention-probability dropout lives in the
+# attention kernels).  Masks are counter-based: (seed, site) -> two 32-bit keys on the host, element index on the device.
+# ------------------------------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+
+
+def dropout_keys(seed: int, site: int) -> tuple[int, int]:
+    """two 32-bit keys of one dropout call site of one forward pass: splitmix64 of (seed, site)"""
+    z = (int(seed) * 0x9E3779B97F4A7C15 + (int(site) + 1) * 0xD1B54A32D192ED03) & _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    z ^= z >> 31
+    return int(z & 0xFFFFFFFF), int(z >> 32)
+
+
+def dropout_fwd(x, p: float, keys: tuple[int, int], residual=None, post_mul: float = 1.0, out=None):
+    """[residual +] bf16(bf16(x * mask / (1 - p)) * post_mul)"""
+    _req(x, _BF16, "x")
+    assert x.is_contiguous() and (residual is None or (residual.is_contiguous() and residual.shape == x.shape))
+    o = torch.empty_like(x) if out is None else out
+    _lib.call("dolomite_b200_dropout_fwd", x.data_ptr(), _ptr(residual), o.data_ptr(), x.numel(), float(p), float(post_mul),
+              keys[0], keys[1], _stream())
+    return o
+
+
+def dropout_bwd(dy, p: float, keys: tuple[int, int], pre_mul: float = 1.0, out=None):
+    """bf16(bf16(dy * pre_mul) * mask / (1 - p))"""
+    _req(dy, _BF16, "dy")
+    assert dy.is_contiguous()
+    o = torch.empty_like(dy) if out is None else out
+    _lib.call("dolomite_b200_dropout_bwd", dy.data_ptr(), o.data_ptr(), dy.numel(), float(p), float(pre_mul), keys[0], keys[1],
+              _stream())
+    return o
+
+
+# ------------------------------------------------------------------------------------------------
 # optimizer kernels (train_utils.py:99-106)
 # ------------------------------------------------------------------------------------------------
 def sumsq_accum(g, out):
@@ -349,12 +385,22 @@ def gemm_wgrad_multi(problems: list[tuple], n_rows: int | None = None) -> None:
 # ------------------------------------------------------------------------------------------------
 # packed var-len causal attention (attention/padding_free.py:51-62)
 # ------------------------------------------------------------------------------------------------
-def attn_varlen_fwd(qkv, cu_seqlens, max_seqlen: int, n_groups: int, q_per_group: int, head_dim: int, scale: float, out=None):
+def attn_varlen_fwd(qkv, cu_seqlens, max_seqlen: int, n_groups: int, q_per_group: int, head_dim: int, scale: float, out=None,
+                    dropout_p: float = 0.0, dropout_keys: tuple[int, int] = (0, 0)):
+    """`dropout_p` > 0: attention-probability dropout (training mode; attention/padding_free.py:49-59), masks from
+    `dropout_keys` (kernels.dropout_keys); the backward call must be given the same p and keys"""
     _req(qkv, _BF16, "qkv"), _req(cu_seqlens, torch.int32, "cu_seqlens")
     T = qkv.shape[0]
     nh = n_groups * q_per_group
     o = torch.empty(T, nh * head_dim, dtype=_BF16, device=qkv.device) if out is None else out
     lse = torch.empty(nh, T, dtype=torch.float32, device=qkv.device)
+    if dropout_p:
+        _lib.call(
+            "dolomite_b200_attn_varlen_fwd_dropout", qkv.data_ptr(), qkv.stride(0), o.data_ptr(), lse.data_ptr(),
+            cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, T, int(max_seqlen), n_groups, q_per_group, head_dim, scale,
+            float(dropout_p), dropout_keys[0], dropout_keys[1], _stream(),
+        )
+        return o, lse
     _lib.call(
         "dolomite_b200_attn_varlen_fwd", qkv.data_ptr(), qkv.stride(0), o.data_ptr(), lse.data_ptr(),
         cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, T, int(max_seqlen), n_groups, q_per_group, head_dim, scale, _stream(),
@@ -362,13 +408,21 @@ def attn_varlen_fwd(qkv, cu_seqlens, max_seqlen: int, n_groups: int, q_per_group
     return o, lse
 
 
-def attn_varlen_bwd(dout, qkv, out, lse, cu_seqlens, max_seqlen, n_groups, q_per_group, head_dim, scale, dqkv=None):
+def attn_varlen_bwd(dout, qkv, out, lse, cu_seqlens, max_seqlen, n_groups, q_per_group, head_dim, scale, dqkv=None,
+                    dropout_p: float = 0.0, dropout_keys: tuple[int, int] = (0, 0)):
     _req(dout, _BF16, "dout"), _req(qkv, _BF16, "qkv")
     T = qkv.shape[0]
     if dqkv is None:
         dqkv = torch.empty_like(qkv)
     ws_bytes = _lib.load().dolomite_b200_attn_varlen_bwd_workspace_bytes(T, n_groups, q_per_group, head_dim)
     ws = _workspace(ws_bytes, qkv.device)
+    if dropout_p:
+        _lib.call(
+            "dolomite_b200_attn_varlen_bwd_dropout", dout.data_ptr(), qkv.data_ptr(), qkv.stride(0), out.data_ptr(),
+            lse.data_ptr(), dqkv.data_ptr(), cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, T, int(max_seqlen), n_groups,
+            q_per_group, head_dim, scale, float(dropout_p), dropout_keys[0], dropout_keys[1], ws.data_ptr(), _stream(),
+        )
+        return dqkv
     _lib.call(
         "dolomite_b200_attn_varlen_bwd", dout.data_ptr(), qkv.data_ptr(), qkv.stride(0), out.data_ptr(), lse.data_ptr(),
         dqkv.data_ptr(), cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, T, int(max_seqlen), n_groups, q_per_group,

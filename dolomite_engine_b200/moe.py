@@ -21,7 +21,7 @@ from . import kernels as K
 FUSED_GATHER = os.environ.get("DOLO_MOE_FUSED_GATHER", "0") == "1"
 
 
-def forward(engine, unit, p: str, x, residual, m_res: float):
+def forward(engine, unit, p: str, x, residual, m_res: float, layer: int = 0):
     cfg = engine.cfg
     k = cfg.num_experts_per_tok
     if (p + "mlp.c_fc.bias") in unit.views:
@@ -37,14 +37,23 @@ def forward(engine, unit, p: str, x, residual, m_res: float):
         fc = K.gemm_grouped_m(K.moe_gather(x, plan), unit.views[p + "mlp.c_fc.weight"], plan, b_mn=False)
     act = K.swiglu_fwd(fc)
     yg = K.gemm_grouped_m(act, unit.views[p + "mlp.c_proj.weight"], plan, b_mn=False)
-    out = K.moe_combine(yg, plan, c=residual, alpha=m_res)
+    p_res = engine._drop_p("resid_pdrop")
+    if p_res > 0:  # moe/base.py:106-120: dropout on the combined expert output, then layer.py's `* m_residual` / `+ residual`
+        y = K.moe_combine(yg, plan)
+        out = K.dropout_fwd(y, p_res, engine._drop_keys(4 * layer + 2), residual=residual, post_mul=m_res, out=y)
+    else:
+        out = K.moe_combine(yg, plan, c=residual, alpha=m_res)
     return out, (plan, logits, fc, act, yg)
 
 
-def backward(engine, unit, p: str, x, dh, m_res: float, saved):
+def backward(engine, unit, p: str, x, dh, m_res: float, saved, layer: int = 0):
     """returns d(x) (gradient wrt the MoE input, i.e. the ln_2 output); accumulates expert / gate weight grads"""
     plan, logits, fc, act, yg = saved
-    dyg, dw = K.moe_combine_bwd(dh, yg, plan, alpha=m_res)
+    p_res = engine._drop_p("resid_pdrop")
+    if p_res > 0:
+        dyg, dw = K.moe_combine_bwd(K.dropout_bwd(dh, p_res, engine._drop_keys(4 * layer + 2), pre_mul=m_res), yg, plan)
+    else:
+        dyg, dw = K.moe_combine_bwd(dh, yg, plan, alpha=m_res)
     w_proj, w_fc = unit.views[p + "mlp.c_proj.weight"], unit.views[p + "mlp.c_fc.weight"]
     K.gemm_grouped_k(dyg, act, plan, unit.gviews[p + "mlp.c_proj.weight"])          # dWproj[e] += dY_e^T act_e
     d_act = K.gemm_grouped_m(dyg, w_proj, plan, b_mn=True)                            # [rows, F]

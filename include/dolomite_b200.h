@@ -151,6 +151,21 @@ int dolomite_b200_scale_bf16_by_device_scalar(void* x, int64_t n, const float* s
 int dolomite_b200_add_scaled(const void* a, const void* b, void* out, float alpha, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Training-mode dropout on flat bf16 activations -- nn.Dropout at gpt_dolomite/base.py:138 (after the embeddings),
+ * attention/base.py:92 + padding_free.py:75 (after the attention c_proj), gpt_dolomite/mlp.py:43-49 (after the MLP c_proj),
+ * moe_dolomite/moe/base.py:106-120 -- fused with the `* m_residual` / `* m_emb` and `+ residual` that follow it
+ * (gpt_dolomite/layer.py:73-86, base.py:368-371), each with the reference's own bf16 rounding:
+ *   fwd: out = [residual +] bf16(bf16(x * s) * post_mul)      s = 1 / (1 - p) on kept elements, 0 on dropped ones
+ *   bwd: dx  = bf16(bf16(dy * pre_mul) * s)
+ * The mask is a counter-based hash of (element index, key0, key1): backward and re-computed (checkpointed) blocks regenerate
+ * it from the same keys.  p in [0, 1); n % 8 == 0; residual may be NULL; out may alias x / residual, dx may alias dy.
+ * ------------------------------------------------------------------------------------------------ */
+int dolomite_b200_dropout_fwd(const void* x, const void* residual, void* out, int64_t n, float p, float post_mul,
+                              uint32_t key0, uint32_t key1, void* stream);
+int dolomite_b200_dropout_bwd(const void* dy, void* dx, int64_t n, float p, float pre_mul, uint32_t key0, uint32_t key1,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Optimizer-side flat-shard kernels (train_utils.py:99-106: clip_grad_norm_ + AdamW step).
  *   sumsq: out[0] += sum(g^2)  (fp32 grads).   clip coef: coef = min(1, max_norm / (sqrt(sumsq) + 1e-6)).
  *   adamw: torch.optim.AdamW semantics on fp32 master shard; also emits the bf16 copy that the next
@@ -280,6 +295,20 @@ int dolomite_b200_attn_varlen_bwd(const void* dout, const void* qkv, int64_t row
                                   const float* lse, void* dqkv, const int32_t* cu_seqlens, int n_docs, int64_t T,
                                   int max_seqlen, int n_groups, int q_per_group, int head_dim, float softmax_scale,
                                   void* workspace, void* stream);
+/* The same with attention-probability dropout (attention/base.py:252 `attn_dropout`; `dropout_p` of flash_attn_varlen_func,
+ * attention/padding_free.py:49-59, training mode only): P_ij is kept with probability 1 - dropout_p and scaled by
+ * 1 / (1 - dropout_p) after the softmax normaliser was taken over the undropped row.  The mask is a hash of (global query
+ * token, global key token, head, key0, key1); backward must be given the keys of its forward.  dropout_p == 0: identical
+ * to the functions above. */
+int dolomite_b200_attn_varlen_fwd_dropout(const void* qkv, int64_t row_stride, void* out, float* lse,
+                                          const int32_t* cu_seqlens, int n_docs, int64_t T, int max_seqlen, int n_groups,
+                                          int q_per_group, int head_dim, float softmax_scale, float dropout_p,
+                                          uint32_t key0, uint32_t key1, void* stream);
+int dolomite_b200_attn_varlen_bwd_dropout(const void* dout, const void* qkv, int64_t row_stride, const void* out,
+                                          const float* lse, void* dqkv, const int32_t* cu_seqlens, int n_docs, int64_t T,
+                                          int max_seqlen, int n_groups, int q_per_group, int head_dim,
+                                          float softmax_scale, float dropout_p, uint32_t key0, uint32_t key1,
+                                          void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,10 @@ class OracleConfig:
     num_experts: int = 0
     num_experts_per_tok: int = 0
     rope_scaling: dict | None = None  # YaRN: {"factor": s, "original_max_position_embeddings": n}
+    # dropout probabilities (config.py:6-111); only applied while a DropoutOracle is installed in DROPOUT (training mode)
+    resid_pdrop: float = 0.0
+    embd_pdrop: float = 0.0
+    attn_pdrop: float = 0.0
     extra: dict = field(default_factory=dict)
 
     def __post_init__(self):
@@ -82,6 +86,78 @@ class OracleConfig:
 def _r(x: torch.Tensor, bf16: bool) -> torch.Tensor:
     """round to bf16 and back when emulating the mixed-precision path"""
     return x.to(torch.bfloat16).to(torch.float32) if bf16 else x
+
+
+# ------------------------------------------------------------------------------------------------
+# dropout masks -- integer arithmetic, bit exact with the kernels (csrc/common.cuh: lowbias32, dropout_hash_flat,
+# dropout_hash_qk; kernels.dropout_keys).  The reference draws its masks from torch's Philox stream (nn.Dropout,
+# flash-attn's dropout_p), which no independent implementation reproduces; what is restated is the distribution
+# (independent Bernoulli(1 - p) keeps, kept values scaled by 1 / (1 - p)) and where the masks enter the arithmetic.
+# ------------------------------------------------------------------------------------------------
+_U32 = np.uint32
+
+
+def _lowbias32(x: np.ndarray) -> np.ndarray:
+    x = x.astype(_U32)
+    x ^= x >> _U32(16)
+    x *= _U32(0x21F0AAAD)
+    x ^= x >> _U32(15)
+    x *= _U32(0x735A2D97)
+    x ^= x >> _U32(15)
+    return x
+
+
+class DropoutOracle:
+    """masks of ONE training pass with seed `seed` (the engine's `_dropout_now`); call sites: 0 = embeddings,
+    4 i + 1 / + 2 / + 3 = block i attention residual / MLP residual / attention probabilities"""
+
+    def __init__(self, seed: int):
+        self.seed = int(seed)
+
+    def keys(self, site: int) -> tuple[int, int]:
+        m = (1 << 64) - 1
+        z = (self.seed * 0x9E3779B97F4A7C15 + (int(site) + 1) * 0xD1B54A32D192ED03) & m
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+        z ^= z >> 31
+        return int(z & 0xFFFFFFFF), int(z >> 32)
+
+    @staticmethod
+    def threshold(p: float) -> int:
+        return int(min(math.floor(float(np.float32(p)) * 4294967296.0 + 0.5), 4294967295))
+
+    def flat_scale(self, site: int, shape, p: float) -> torch.Tensor:
+        """1 / (1 - p) where element e (row-major index) is kept, 0 where it is dropped"""
+        k0, k1 = self.keys(site)
+        with np.errstate(over="ignore"):
+            e = np.arange(int(np.prod(shape)), dtype=np.uint64)
+            h = _lowbias32(_lowbias32((e & np.uint64(0xFFFFFFFF)).astype(_U32) ^ _U32(k0)) + (e >> np.uint64(32)).astype(_U32) + _U32(k1))
+        keep = h >= _U32(self.threshold(p))
+        ks = float(np.float32(1.0) / (np.float32(1.0) - np.float32(p)))
+        return torch.from_numpy(np.where(keep, np.float32(ks), np.float32(0.0)).reshape(shape))
+
+    def attn_scale(self, site: int, head: int, q_tok: np.ndarray, k_tok: np.ndarray, p: float) -> torch.Tensor:
+        """[len(q_tok), len(k_tok)] keep scales of one head; q_tok / k_tok are GLOBAL token rows of the packed stream"""
+        k0, k1 = self.keys(site)
+        with np.errstate(over="ignore"):
+            hk = _lowbias32(np.asarray([head], dtype=_U32) * _U32(0xC2B2AE3D) + _U32(k0)) ^ _U32(k1)
+            q = np.asarray(q_tok, dtype=_U32)[:, None] * _U32(0x9E3779B1)
+            k = np.asarray(k_tok, dtype=_U32)[None, :] * _U32(0x85EBCA77)
+            h = _lowbias32(q ^ k ^ hk)
+        keep = h >= _U32(self.threshold(p))
+        ks = float(np.float32(1.0) / (np.float32(1.0) - np.float32(p)))
+        return torch.from_numpy(np.where(keep, np.float32(ks), np.float32(0.0)))
+
+
+# installed by a test for the duration of one training pass (None = evaluation mode: dropout is the identity)
+DROPOUT: DropoutOracle | None = None
+
+
+def _drop(x: torch.Tensor, site: int, p: float, bf16: bool) -> torch.Tensor:
+    """nn.Dropout in training mode: bf16(x * mask / (1 - p))"""
+    if DROPOUT is None or not p:
+        return x
+    return _r(x * DROPOUT.flat_scale(site, tuple(x.shape), p), bf16)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -256,7 +332,8 @@ def split_qkv_activations(qkv: torch.Tensor, cfg: OracleConfig):
     return q.reshape(T, nh, hd), k, v
 
 
-def packed_causal_attention(q, k, v, cu_seqlens: np.ndarray, scale: float, bf16: bool = False) -> torch.Tensor:
+def packed_causal_attention(q, k, v, cu_seqlens: np.ndarray, scale: float, bf16: bool = False, dropout_site: int | None = None,
+                            dropout_p: float = 0.0) -> torch.Tensor:
     """Block-diagonal (per document) causal softmax attention = flash_attn_varlen_func(causal=True) at
     attention/padding_free.py:51-62; arithmetic follows the eager Attention (attention/base.py:171-275) with fp32
     softmax (attention_softmax_in_fp32).  q [T,nh,hd]; k,v [T,nkv,hd].  Returns [T, nh*hd]."""
@@ -275,6 +352,11 @@ def packed_causal_attention(q, k, v, cu_seqlens: np.ndarray, scale: float, bf16:
         mask = torch.ones(e - s, e - s, dtype=torch.bool).tril()
         sc = sc.masked_fill(~mask, float("-inf"))
         p = torch.softmax(sc.float(), dim=-1)
+        if DROPOUT is not None and dropout_p and dropout_site is not None:
+            # attention-probability dropout (attention/base.py:252 attn_dropout; flash_attn_varlen_func(dropout_p) at
+            # padding_free.py:49-59): the softmax normaliser is that of the UNdropped row
+            tok = np.arange(s, e)
+            p = p * torch.stack([DROPOUT.attn_scale(dropout_site, h, tok, tok, dropout_p) for h in range(nh)])
         out[s:e] = torch.matmul(_r(p, bf16), vd).transpose(0, 1)
     return _r(out.reshape(T, nh * hd), bf16)
 
@@ -354,8 +436,9 @@ def block(h, p: dict, i: int, cfg: OracleConfig, cos, sin, cu_seqlens, bf16: boo
     if cfg.position_embedding_type == "rope":
         q = apply_rope(q, cos, sin, bf16)
         k = apply_rope(k, cos, sin, bf16)
-    a = packed_causal_attention(q, k, v, cu_seqlens, softmax_scale(cfg), bf16)
+    a = packed_causal_attention(q, k, v, cu_seqlens, softmax_scale(cfg), bf16, dropout_site=4 * i + 3, dropout_p=cfg.attn_pdrop)
     a = linear(a, p[pre + "attn.c_proj.weight"], p.get(pre + "attn.c_proj.bias"), bf16)
+    a = _drop(a, 4 * i + 1, cfg.resid_pdrop, bf16)  # resid_dropout (attention/padding_free.py:75)
     if cfg.m_residual is not None:
         a = _r(a * cfg.m_residual, bf16)
     h = _r(a + res, bf16)
@@ -365,6 +448,7 @@ def block(h, p: dict, i: int, cfg: OracleConfig, cos, sin, cu_seqlens, bf16: boo
         m, _ = sparse_moe(x, p, pre + "mlp.", cfg, bf16)
     else:
         m = mlp(x, p, pre + "mlp.", cfg, bf16)
+    m = _drop(m, 4 * i + 2, cfg.resid_pdrop, bf16)  # gpt_dolomite/mlp.py:49, moe/base.py:120
     if cfg.m_residual is not None:
         m = _r(m * cfg.m_residual, bf16)
     return _r(res + m, bf16)
@@ -381,6 +465,7 @@ def forward_logits(p: dict, cfg: OracleConfig, input_ids, position_ids, cu_seqle
     h = p["transformer.wte.weight"][ids]
     if cfg.position_embedding_type == "learned_absolute":  # gpt_dolomite/base.py:351-372: wte(ids) + wpe(position_ids)
         h = _r(h + p["transformer.wpe.weight"][pos], bf16)
+    h = _drop(h, 0, cfg.embd_pdrop, bf16)  # gpt_dolomite/base.py:368 `self.drop`
     if cfg.m_emb is not None:
         h = _r(h * cfg.m_emb, bf16)
     cos = sin = None

@@ -44,7 +44,7 @@ def test_unsupported_configs_fail_loudly():
     check_supported(ok)
     for kw in (dict(position_embedding_type="alibi"), dict(normalization_function="apex_layernorm"),
                dict(activation_function="geglu"), dict(n_head=32, num_key_value_heads=32),
-               dict(position_embedding_type="learned_absolute", m_emb=12.0), dict(rope_scaling={"type": "linear", "factor": 2, "original_max_position_embeddings": 64})):
+               dict(rope_scaling={"type": "linear", "factor": 2, "original_max_position_embeddings": 64})):
         d = ok.to_dict()
         d.update(kw)
         with pytest.raises(NotImplementedError):
@@ -53,6 +53,8 @@ def test_unsupported_configs_fail_loudly():
     d = ok.to_dict()
     d.update(position_embedding_type="learned_absolute", normalization_function="layernorm",
              activation_function="gelu_pytorch_tanh", attention_head_type="mqa", num_key_value_heads=1, add_bias=True)
+    check_supported(GPTDolomiteConfig.from_dict(d))
+    d.update(m_emb=12.0)  # (wte + wpe) * m_emb: the scale is a separate pass after the sum (tests/test_gpu_dropout.py "bigcode")
     check_supported(GPTDolomiteConfig.from_dict(d))
 
 
@@ -221,20 +223,43 @@ def test_every_shipped_config_parses():
     assert a.distributed_args.gradient_checkpointing_args == {"checkpoint_every": 2} and a.model_args.model_name
 
 
-def test_dropout_configs_construct_but_do_not_train():
-    """the reference's default config has dropout 0.1: such checkpoints can be loaded for evaluation / generation (dropout is
-    the identity in eval mode); a training-mode forward raises instead of silently skipping dropout"""
+def test_dropout_mask_generator_host_side():
+    """dropout masks are counter-based: (pass seed, call site) -> two 32-bit keys (kernels.dropout_keys, restated by the
+    oracle's DropoutOracle), element index -> keep bit.  Host-side properties: the keys of the product and of the oracle agree,
+    sites / passes give different masks, the keep rate is 1 - p, the kept scale is 1 / (1 - p); eval mode draws no seed."""
+    import numpy as np
     import torch
 
+    import oracle.dolomite_oracle as O
     from dolomite_engine_b200.engine import DolomiteEngine
     from dolomite_engine_b200.hf_models import GPTDolomiteConfig
+    from dolomite_engine_b200.kernels import dropout_keys
 
-    cfg = GPTDolomiteConfig(n_embd=64, n_head=4, n_layer=1, vocab_size=264, n_positions=64)  # defaults: pdrop 0.1
+    for seed in (0, 1, 12345678901234567):
+        for site in (0, 1, 7, 130):
+            assert O.DropoutOracle(seed).keys(site) == dropout_keys(seed, site)
+    d = O.DropoutOracle(99)
+    m1, m2 = d.flat_scale(1, (4096, 64), 0.1), d.flat_scale(2, (4096, 64), 0.1)
+    assert abs(float((m1 > 0).float().mean()) - 0.9) < 5e-3 and abs(float(m1.max()) - 1 / 0.9) < 1e-6
+    assert 0.75 < float(((m1 > 0) == (m2 > 0)).float().mean()) < 0.89  # independent masks agree on 0.9^2 + 0.1^2 = 0.82
+    assert not torch.equal(O.DropoutOracle(100).flat_scale(1, (4096, 64), 0.1), m1)
+    a = d.attn_scale(3, 5, np.arange(1000, 1400), np.arange(1000, 1400), 0.25)
+    assert abs(float((a > 0).float().mean()) - 0.75) < 1e-2
+    assert not torch.equal(a, d.attn_scale(3, 6, np.arange(1000, 1400), np.arange(1000, 1400), 0.25))  # per head
+    assert torch.equal(a[10:20, 30:50], d.attn_scale(3, 5, np.arange(1010, 1020), np.arange(1030, 1050), 0.25))  # position based
+    assert d.threshold(0.0) == 0 and float((d.flat_scale(0, (1000,), 0.0) == 1.0).float().mean()) == 1.0
+
+    cfg = GPTDolomiteConfig(n_embd=64, n_head=4, n_layer=1, vocab_size=264, n_positions=64)  # the reference's defaults: pdrop 0.1
     engine = DolomiteEngine(cfg, "cpu", seed=1)
     assert engine.has_dropout and engine.training
-    ids = torch.zeros(8, dtype=torch.long)
-    with pytest.raises(NotImplementedError, match="dropout > 0 in training mode"):
-        engine.forward(ids, ids, torch.tensor([0, 8], dtype=torch.int32), 8)
+    engine.dropout_seed = 7
+    engine._begin_dropout_pass()
+    first = engine._dropout_now
+    engine._begin_dropout_pass()
+    assert first == 7 and engine._dropout_now == 8 and engine._drop_p("attn_pdrop") == pytest.approx(0.1)
+    engine.training = False
+    engine._begin_dropout_pass()
+    assert engine._dropout_now is None and engine._drop_p("resid_pdrop") == 0.0
     assert not DolomiteEngine(GPTDolomiteConfig(n_embd=64, n_head=4, n_layer=1, vocab_size=264, resid_pdrop=0, embd_pdrop=0,
                                                 attn_pdrop=0), "cpu", seed=1).has_dropout
 
