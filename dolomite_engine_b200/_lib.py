@@ -31,6 +31,7 @@ SIGNATURES: dict[str, tuple] = {
     "dolomite_b200_abi_version": (_I, []),
     "dolomite_b200_device_info": (_I, [_P, _P, _P]),
     "dolomite_b200_set_option": (_I, [c_char_p, _I]),
+    "dolomite_b200_get_option": (_I, [c_char_p, _P]),
     "dolomite_b200_rmsnorm_fwd": (_I, [_P, _P, _P, _P, _L, _I, _F, _P]),
     "dolomite_b200_rmsnorm_bwd_workspace_bytes": (_L, [_I]),
     "dolomite_b200_rmsnorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),

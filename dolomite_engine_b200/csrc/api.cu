@@ -80,6 +80,20 @@ extern "C" int dolomite_b200_set_option(const char* key, int value) {
     return dolo_set_error("unknown option '%s'", key ? key : "(null)");
 }
 
+extern "C" int dolomite_b200_get_option(const char* key, int* value) {
+    DOLO_REQUIRE(key != nullptr && value != nullptr, "get_option: null argument");
+    if (strcmp(key, "gemm_sm_margin") == 0) *value = g_gemm_sm_margin;
+    else if (strcmp(key, "attn_fwd_split") == 0) *value = g_attn_fwd_split;
+    else if (strcmp(key, "attn_bwd_variant") == 0) *value = g_attn_bwd_variant;
+    else if (strcmp(key, "attn_bwd_ablate") == 0) *value = g_attn_bwd_ablate;
+    else if (strcmp(key, "gemm_l2_hints") == 0) *value = g_gemm_l2_hints;
+    else if (strcmp(key, "gemm_f32_tma_epilogue") == 0) *value = g_gemm_f32_tma_epilogue;
+    else if (strcmp(key, "gemm_dynamic") == 0) *value = g_gemm_dynamic;
+    else if (strcmp(key, "gemm_cta_pair") == 0) *value = g_gemm_cta_pair;
+    else return dolo_set_error("unknown option '%s'", key);
+    return DOLO_OK;
+}
+
 int dolo_num_sms() {
     static int cached[64] = {0};
     int dev = 0;

@@ -79,6 +79,54 @@ __global__ void __launch_bounds__(kThreads) rmsnorm_fwd_kernel(const uint4* __re
     }
 }
 
+// RMSNorm forward, one WARP per row (H <= 4096): lane l holds vectors l, l + 32, ... of the row in registers, all of them
+// requested before the first use; the sum of squares is a warp reduction -- no shared memory, no block barrier.  The
+// block-per-row kernel above keeps 8 CTAs x 5 KB = 40 KB of loads in flight per SM at H = 2560 (8 of its 32 registers hold
+// data) and measured 4.6-4.9 TB/s; here 40 of ~64 registers hold data and 32 resident warps keep 160 KB in flight.
+template <int NVW>
+__global__ void __launch_bounds__(kThreads) rmsnorm_fwd_warp_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w,
+                                                                    uint4* __restrict__ y, float* __restrict__ rstd,
+                                                                    int64_t T, int H8, float eps, float inv_h) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = int64_t(blockIdx.x) * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = int64_t(gridDim.x) * (kThreads / 32);
+    for (int64_t row = warp0; row < T; row += nwarps) {
+        const uint4* xr = x + row * H8;
+        uint4 xv[NVW];
+#pragma unroll
+        for (int i = 0; i < NVW; ++i) {
+            const int idx = lane + i * 32;
+            if (idx < H8) xv[i] = __ldg(xr + idx);
+        }
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < NVW; ++i) {
+            if (lane + i * 32 < H8) {
+                float f[8];
+                unpack8(xv[i], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+            }
+        }
+        ss = warp_sum(ss);
+        const float r = rsqrtf(ss * inv_h + eps);
+        if (lane == 0) rstd[row] = r;
+        uint4* yr = y + row * H8;
+#pragma unroll
+        for (int i = 0; i < NVW; ++i) {
+            const int idx = lane + i * 32;
+            if (idx < H8) {
+                float f[8], g[8];
+                unpack8(xv[i], f);
+                unpack8(__ldg(w + idx), g);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = g[j] * bf16_round(f[j] * r);  // weight * bf16(normalised)
+                yr[idx] = pack8(f);
+            }
+        }
+    }
+}
+
 // RMSNorm backward.  dx = r * (dy*w - xn * mean(dy*w*xn)),  dw += sum_rows dy * bf16(xn).
 // Persistent blocks; per-thread dw partials in registers, written to workspace [gridDim.x, H].
 template <int NV>
@@ -101,7 +149,7 @@ __global__ void __launch_bounds__(kThreads)
         // exposed (the residual gradient used to be fetched after the reduction: 3.3 TB/s -> see profiles)
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-            const int idx = threadIdx.x + i * kThreads;
+            const int idx = threadIdx.x + i * int(blockDim.x);
             if (idx < H8) {
                 xv[i] = __ldg(x + row * H8 + idx);
                 gv[i] = __ldg(dy + row * H8 + idx);
@@ -110,7 +158,7 @@ __global__ void __launch_bounds__(kThreads)
         }
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-            const int idx = threadIdx.x + i * kThreads;
+            const int idx = threadIdx.x + i * int(blockDim.x);
             if (idx < H8) {
                 float xf[8], gf[8], wf[8];
                 unpack8(xv[i], xf);
@@ -127,7 +175,7 @@ __global__ void __launch_bounds__(kThreads)
         dot = block_sum(dot, red) * inv_h;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-            const int idx = threadIdx.x + i * kThreads;
+            const int idx = threadIdx.x + i * int(blockDim.x);
             if (idx < H8) {
                 float xf[8], gf[8], wf[8], o[8];
                 unpack8(xv[i], xf);
@@ -148,7 +196,7 @@ __global__ void __launch_bounds__(kThreads)
     float* wrow = ws + int64_t(blockIdx.x) * H8 * 8;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-        const int idx = threadIdx.x + i * kThreads;
+        const int idx = threadIdx.x + i * int(blockDim.x);
         if (idx < H8) {
             float4* p = reinterpret_cast<float4*>(wrow + idx * 8);
             p[0] = make_float4(dwacc[i][0], dwacc[i][1], dwacc[i][2], dwacc[i][3]);
@@ -957,6 +1005,17 @@ extern "C" int dolomite_b200_rmsnorm_fwd(const void* x, const void* w, void* y, 
     auto W = static_cast<const uint4*>(w);
     auto Y = static_cast<uint4*>(y);
     const float inv_h = 1.f / float(H);
+    if (H8 <= 16 * 32 && T >= 64) {  // one warp per row
+        const int64_t want = (T + kThreads / 32 - 1) / (kThreads / 32);
+        const int wgrid = int(want < int64_t(dolo_num_sms()) * 8 ? want : int64_t(dolo_num_sms()) * 8);
+        const int nvw = (H8 + 31) / 32;
+        if (nvw <= 4) rmsnorm_fwd_warp_kernel<4><<<wgrid, kThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h);
+        else if (nvw <= 8) rmsnorm_fwd_warp_kernel<8><<<wgrid, kThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h);
+        else if (nvw <= 10) rmsnorm_fwd_warp_kernel<10><<<wgrid, kThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h);
+        else rmsnorm_fwd_warp_kernel<16><<<wgrid, kThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h);
+        DOLO_LAUNCH_OK("rmsnorm_fwd");
+        return DOLO_OK;
+    }
     switch (nv) {
         case 1: rmsnorm_fwd_kernel<1><<<grid, kThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h); break;
         case 2: rmsnorm_fwd_kernel<2><<<grid, kThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h); break;
@@ -968,9 +1027,10 @@ extern "C" int dolomite_b200_rmsnorm_fwd(const void* x, const void* w, void* y, 
     return DOLO_OK;
 }
 
-// 4 resident blocks per SM at H <= 4096 (64 registers): each block alternates a load phase, a block reduction and a
-// store phase, so it takes several independent blocks per SM to keep HBM requests in flight.
-static int rmsnorm_bwd_parts() { return dolo_num_sms() * 4; }
+// Each block alternates a load phase, a block reduction and a store phase, so it takes several independent blocks per SM to
+// keep HBM requests in flight.  The RMSNorm backward sizes its blocks to the row (H = 2560: 160 threads x 2 vectors -- with 256
+// threads 192 of them held one vector in two vectors' worth of registers), which fits 6 blocks of 64 registers per SM.
+static int rmsnorm_bwd_parts() { return dolo_num_sms() * 6; }
 
 extern "C" int64_t dolomite_b200_rmsnorm_bwd_workspace_bytes(int H) {
     return int64_t(rmsnorm_bwd_parts()) * H * sizeof(float);
@@ -997,12 +1057,14 @@ extern "C" int dolomite_b200_rmsnorm_bwd(const void* dy, const void* x, const vo
     auto DX = static_cast<uint4*>(dx);
     auto WS = static_cast<float*>(workspace);
     const float inv_h = 1.f / float(H);
-    switch (nv) {
-        case 1: rmsnorm_bwd_kernel<1><<<parts, kThreads, 0, st>>>(DY, X, W, rstd, DA, DX, WS, T, H8, inv_h); break;
-        case 2: rmsnorm_bwd_kernel<2><<<parts, kThreads, 0, st>>>(DY, X, W, rstd, DA, DX, WS, T, H8, inv_h); break;
-        case 3:
-        case 4: rmsnorm_bwd_kernel<4><<<parts, kThreads, 0, st>>>(DY, X, W, rstd, DA, DX, WS, T, H8, inv_h); break;
-        default: rmsnorm_bwd_kernel<8><<<parts, kThreads, 0, st>>>(DY, X, W, rstd, DA, DX, WS, T, H8, inv_h); break;
+    const int nvk = nv <= 2 ? nv : (nv <= 4 ? 4 : 8);                    // vectors per thread of the instantiation used
+    int threads = ((H8 + nvk - 1) / nvk + 31) / 32 * 32;                  // just enough warps for the row
+    if (threads > kThreads) threads = kThreads;
+    switch (nvk) {
+        case 1: rmsnorm_bwd_kernel<1><<<parts, threads, 0, st>>>(DY, X, W, rstd, DA, DX, WS, T, H8, inv_h); break;
+        case 2: rmsnorm_bwd_kernel<2><<<parts, threads, 0, st>>>(DY, X, W, rstd, DA, DX, WS, T, H8, inv_h); break;
+        case 4: rmsnorm_bwd_kernel<4><<<parts, threads, 0, st>>>(DY, X, W, rstd, DA, DX, WS, T, H8, inv_h); break;
+        default: rmsnorm_bwd_kernel<8><<<parts, threads, 0, st>>>(DY, X, W, rstd, DA, DX, WS, T, H8, inv_h); break;
     }
     DOLO_LAUNCH_OK("rmsnorm_bwd");
     if (dw_accum != nullptr) {

@@ -18,6 +18,14 @@ def set_option(key: str, value: int) -> None:
     _lib.call("dolomite_b200_set_option", key.encode(), int(value))
 
 
+def get_option(key: str) -> int:
+    import ctypes
+
+    v = ctypes.c_int(0)
+    _lib.call("dolomite_b200_get_option", key.encode(), ctypes.addressof(v))
+    return int(v.value)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 

@@ -67,6 +67,8 @@ def backward(engine, unit, p: str, x, dh, m_res: float, saved, layer: int = 0):
     dlogits = K.moe_router_bwd(plan, dw)
     gate = unit.views[p + "mlp.gate.weight"]
     ggate = unit.gviews[p + "mlp.gate.weight"]
-    K.gemm(dlogits, x, a_mn=True, b_mn=True, out=ggate, c=ggate, beta=1.0)          # dGate += dlogits^T x
+    # dGate[E, H] += dlogits^T x: E = 8 rows are ONE row of output tiles (8 tiles at H = 2048) with the whole token stream as
+    # contraction -- split-K over the SMs (fp32 atomics on 8 valid rows per tile) instead of 8 busy SMs for 70 us per layer
+    K.gemm(dlogits, x, a_mn=True, b_mn=True, out=ggate, c=ggate, beta=1.0, flags=K.GEMM_SPLITK_ACCUMULATE)
     dx = K.gemm(dlogits, gate, b_mn=True, out=dx, c=dx, beta=1.0, flags=0)          # dx += dlogits gate
     return dx

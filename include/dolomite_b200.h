@@ -46,6 +46,7 @@ int dolomite_b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   "gemm_l2_hints"    1 | 0 (long-contraction GEMMs load the streamed operand evict-first and the re-used one evict-last)
  *   "gemm_f32_tma_epilogue" 0 | 1 (fp32 weight gradients through TMA tile store / reduce-add instead of per-thread stores) */
 int dolomite_b200_set_option(const char* key, int value);
+int dolomite_b200_get_option(const char* key, int* value);
 
 /* ------------------------------------------------------------------------------------------------
  * RMSNorm  -- hf_models/modeling_utils/normalization/rmsnorm/base.py:18-25

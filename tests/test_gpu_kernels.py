@@ -147,6 +147,24 @@ def test_gemm_epilogue_alpha_beta_accumulate():
     assert torch.allclose(d.cpu(), C + 0.5 * (A.float() @ B.float().t()), atol=1e-3, rtol=1e-4)
 
 
+@pytest.mark.parametrize("M,N,Kd", [(8, 2048, 4096), (264, 520, 1024)])
+def test_gemm_split_k_accumulate(M, N, Kd):
+    """D (fp32) += A^T B with the contraction split over several CTAs (fp32 vector atomics): the MoE gate weight gradient
+    (E = 8 output rows, the whole token stream as contraction; moe.py backward)"""
+    g = torch.Generator().manual_seed(11)
+    A, B = bf(torch.randn(Kd, M, generator=g) * 0.1), bf(torch.randn(Kd, N, generator=g) * 0.1)
+    C = torch.randn(M, N, generator=g)
+    for dyn in (0, 1):
+        try:
+            K().set_option("gemm_dynamic", dyn)
+            d = C.cuda().clone()
+            K().gemm(A.cuda(), B.cuda(), a_mn=True, b_mn=True, out=d, c=d, beta=1.0, flags=K().GEMM_SPLITK_ACCUMULATE)
+        finally:
+            K().set_option("gemm_dynamic", 0)
+        ref = C + A.float().t() @ B.float()
+        assert torch.allclose(d.cpu(), ref, atol=2e-3, rtol=1e-4), dyn
+
+
 def _attn_inputs(lens, ng, g, hd, seed=7):
     gen = torch.Generator().manual_seed(seed)
     T = sum(lens)
