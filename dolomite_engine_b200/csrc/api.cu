@@ -33,6 +33,8 @@ static int g_attn_fwd_split = 1;
 int dolo_option_attn_fwd_split() { return g_attn_fwd_split; }
 static int g_attn_bwd_variant = 2;
 int dolo_option_attn_bwd_variant() { return g_attn_bwd_variant; }
+static int g_attn_head_fastest = 1;
+int dolo_option_attn_head_fastest() { return g_attn_head_fastest; }
 static int g_attn_bwd_ablate = 0;
 int dolo_option_attn_bwd_ablate() { return g_attn_bwd_ablate; }
 static int g_gemm_l2_hints = 1;
@@ -55,6 +57,10 @@ extern "C" int dolomite_b200_set_option(const char* key, int value) {
     if (key != nullptr && strcmp(key, "attn_bwd_variant") == 0) {
         DOLO_REQUIRE(value >= 0 && value <= 2, "attn_bwd_variant must be 0, 1 or 2");
         g_attn_bwd_variant = value;
+        return DOLO_OK;
+    }
+    if (key != nullptr && strcmp(key, "attn_head_fastest") == 0) {
+        g_attn_head_fastest = value != 0;
         return DOLO_OK;
     }
     if (key != nullptr && strcmp(key, "attn_bwd_ablate") == 0) {
@@ -86,6 +92,7 @@ extern "C" int dolomite_b200_get_option(const char* key, int* value) {
     else if (strcmp(key, "attn_fwd_split") == 0) *value = g_attn_fwd_split;
     else if (strcmp(key, "attn_bwd_variant") == 0) *value = g_attn_bwd_variant;
     else if (strcmp(key, "attn_bwd_ablate") == 0) *value = g_attn_bwd_ablate;
+    else if (strcmp(key, "attn_head_fastest") == 0) *value = g_attn_head_fastest;
     else if (strcmp(key, "gemm_l2_hints") == 0) *value = g_gemm_l2_hints;
     else if (strcmp(key, "gemm_f32_tma_epilogue") == 0) *value = g_gemm_f32_tma_epilogue;
     else if (strcmp(key, "gemm_dynamic") == 0) *value = g_gemm_dynamic;

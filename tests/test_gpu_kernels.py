@@ -147,6 +147,31 @@ def test_gemm_epilogue_alpha_beta_accumulate():
     assert torch.allclose(d.cpu(), C + 0.5 * (A.float() @ B.float().t()), atol=1e-3, rtol=1e-4)
 
 
+def test_gemm_tile_schedules_are_bit_identical():
+    """`gemm_dynamic` = 1 (one cluster per tile, running clusters take over pending ones through cluster launch control) and
+    = 0 (static persistent workers) compute the same tiles with the same arithmetic: outputs are bit-identical for every
+    operand layout / epilogue, in the CTA-pair and the single-CTA kernel, with many more tiles than SMs"""
+    g = torch.Generator().manual_seed(12)
+    default = K().get_option("gemm_dynamic")
+    cases = [(4096, 4096, 512, False, False, 5, torch.bfloat16), (1024, 3072, 1024, False, True, 5, torch.bfloat16),
+             (640, 512, 2048, True, True, 4, torch.float32), (4096 + 64, 2048, 256, False, False, 8, torch.bfloat16),
+             (300, 520, 328, False, False, 5, torch.bfloat16), (100, 2560, 2560, False, False, 0, torch.bfloat16)]
+    try:
+        for M, N, Kd, a_mn, b_mn, flags, dt in cases:
+            A, B = bf(torch.randn(M, Kd, generator=g)), bf(torch.randn(N, Kd, generator=g))
+            a = (A.t().contiguous() if a_mn else A).cuda()
+            b = (B.t().contiguous() if b_mn else B).cuda()
+            outs = []
+            for dyn in (0, 1):
+                K().set_option("gemm_dynamic", dyn)
+                outs.append(K().gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=dt, flags=flags if dt == torch.bfloat16 else flags & ~1))
+            assert torch.equal(outs[0], outs[1]), (M, N, Kd, a_mn, b_mn, flags)
+            ref = A.float() @ B.float().t()
+            assert rel_l2(outs[1], ref) < 5e-3
+    finally:
+        K().set_option("gemm_dynamic", default)
+
+
 @pytest.mark.parametrize("M,N,Kd", [(8, 2048, 4096), (264, 520, 1024)])
 def test_gemm_split_k_accumulate(M, N, Kd):
     """D (fp32) += A^T B with the contraction split over several CTAs (fp32 vector atomics): the MoE gate weight gradient
@@ -154,13 +179,14 @@ def test_gemm_split_k_accumulate(M, N, Kd):
     g = torch.Generator().manual_seed(11)
     A, B = bf(torch.randn(Kd, M, generator=g) * 0.1), bf(torch.randn(Kd, N, generator=g) * 0.1)
     C = torch.randn(M, N, generator=g)
-    for dyn in (0, 1):
+    default = K().get_option("gemm_dynamic")
+    for dyn in (0, 1):  # static persistent schedule / cluster-launch-control schedule
         try:
             K().set_option("gemm_dynamic", dyn)
             d = C.cuda().clone()
             K().gemm(A.cuda(), B.cuda(), a_mn=True, b_mn=True, out=d, c=d, beta=1.0, flags=K().GEMM_SPLITK_ACCUMULATE)
         finally:
-            K().set_option("gemm_dynamic", 0)
+            K().set_option("gemm_dynamic", default)
         ref = C + A.float().t() @ B.float()
         assert torch.allclose(d.cpu(), ref, atol=2e-3, rtol=1e-4), dyn
 

@@ -254,6 +254,7 @@ def gemm_dynamic():
 
     res = {}
     ok = True
+    default_dynamic = k.get_option("gemm_dynamic")
     shapes = {
         "nt_256": (256, 256, 64, False, False, dict(flags=4)),
         "nt_tma": (512, 1024, 512, False, False, dict(flags=5)),
@@ -345,7 +346,7 @@ def gemm_dynamic():
                                     "held_whole_time_ms": min(timed(40) for _ in range(2)),
                                     "held_first_third_ms": min(timed(3.5) for _ in range(2))}
     finally:
-        k.set_option("gemm_dynamic", 0)
+        k.set_option("gemm_dynamic", default_dynamic)
         k.set_option("gemm_sm_margin", 0)
     res["ok"] = ok
     return res
@@ -845,6 +846,61 @@ def _attn_bench(S, B, nh, hd):
     res["flash_fwd_bwd_ms"] = ms_fb
     res["ok"] = bool(res["vs_flash_fwd"]["rel_l2"] < 1e-2 and res["vs_flash_dq"]["rel_l2"] < 2e-2 and res["vs_flash_dk"]["rel_l2"] < 2e-2 and res["vs_flash_dv"]["rel_l2"] < 2e-2)
     return res
+
+
+def _attn_order_ab(S, B, ng, g, hd, rounds=3):
+    """CTA order of the attention kernels: heads fastest + longest tiles first (attn_head_fastest = 1) against round 1's tiles
+    fastest (0); forward and backward, interleaved; results must be bit-identical (the order changes nothing but timing -- the
+    backward's dQ reduction order aside)"""
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+
+    T, nh = S * B, ng * g
+    qkv = torch.randn(T, ng * (g + 2) * hd, device="cuda").bfloat16()
+    cu = torch.arange(0, T + 1, S, dtype=torch.int32, device="cuda")
+    scale = hd ** -0.5
+    dout = torch.randn(T, nh * hd, device="cuda").bfloat16()
+    flops_fwd = 4.0 * S * S * hd * nh * B / 2
+    res = {"shape": [S, B, ng, g, hd]}
+    default = k.get_option("attn_head_fastest")
+    outs = {}
+    try:
+        tf = {0: [], 1: []}
+        tb = {0: [], 1: []}
+        for _ in range(rounds):
+            for order in (0, 1):
+                k.set_option("attn_head_fastest", order)
+                out, lse = k.attn_varlen_fwd(qkv, cu, S, ng, g, hd, scale)
+                dqkv = k.attn_varlen_bwd(dout, qkv, out, lse, cu, S, ng, g, hd, scale)
+                outs[order] = (out.clone(), dqkv.clone())
+                tf[order].append(_time(lambda: k.attn_varlen_fwd(qkv, cu, S, ng, g, hd, scale, out=out), iters=10))
+                tb[order].append(_time(lambda: k.attn_varlen_bwd(dout, qkv, out, lse, cu, S, ng, g, hd, scale, dqkv=dqkv), iters=5))
+    finally:
+        k.set_option("attn_head_fastest", default)
+    res["fwd_bit_identical"] = bool(torch.equal(outs[0][0], outs[1][0]))
+    res["bwd_rel_l2_between_orders"] = _err(outs[1][1], outs[0][1])["rel_l2"]
+    for order in (0, 1):
+        res[f"order{order}_fwd_ms"] = tf[order]
+        res[f"order{order}_bwd_ms"] = tb[order]
+        res[f"order{order}_fwd_tflops_causal"] = flops_fwd / min(tf[order]) / 1e9
+        res[f"order{order}_bwd_tflops_causal"] = 2.5 * flops_fwd / min(tb[order]) / 1e9
+    res["ok"] = bool(res["fwd_bit_identical"] and res["bwd_rel_l2_between_orders"] < 1e-3)
+    return res
+
+
+@case
+def attn_order_c2():
+    return _attn_order_ab(4096, 6, 32, 1, 80)
+
+
+@case
+def attn_order_c5():
+    return _attn_order_ab(8192, 1, 8, 4, 128)
+
+
+@case
+def attn_order_c4():
+    return _attn_order_ab(2048, 8, 16, 1, 128)
 
 
 def _attn_bwd_variants(S, B, nh, hd, rounds=3):

@@ -16,8 +16,13 @@ run() {  # name, env assignments..., -- bench args
 # one-GPU checks of what changed since call 85 (RMSNorm kernels, split-K gate gradient, get_option)
 timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_moe.py -m gpu -q -x -k "rmsnorm or split_k or moe or layernorm" > gpurun_out/h_kernel_tests.log 2>&1
 echo "kernel tests rc=$?"; tail -3 gpurun_out/h_kernel_tests.log
-timeout 300 python tools/gpu_probe.py --only elementwise_bench_c2 --out gpurun_out/h_probe.jsonl > gpurun_out/h_probe.log 2>&1
-echo "probe rc=$?"; cut -c1-1800 gpurun_out/h_probe.jsonl
+timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "attention or empty or schedules" > gpurun_out/h_attn_tests.log 2>&1
+echo "attention tests (head-fastest CTA order) rc=$?"; tail -3 gpurun_out/h_attn_tests.log
+rm -f gpurun_out/h_probe.jsonl
+for c in elementwise_bench_c2 attn_order_c2 attn_order_c5 attn_order_c4; do
+  timeout 300 python tools/gpu_probe.py --only $c --out gpurun_out/h_probe.jsonl > gpurun_out/h_probe.log 2>&1
+done
+echo "probe rc=$?"; cut -c1-1500 gpurun_out/h_probe.jsonl
 DOLO_OPTIONS=gemm_dynamic=1 timeout 900 python -m pytest tests/test_nccl_parity.py -m gpu -q > gpurun_out/h_nccl_parity_dynamic.log 2>&1
 echo "nccl parity (dynamic) rc=$?"; tail -3 gpurun_out/h_nccl_parity_dynamic.log
 run c2_static_a DOLO_OPTIONS=gemm_dynamic=0 -- --fsdp-mode reshard
