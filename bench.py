@@ -504,6 +504,9 @@ def run_ours(args) -> None:
                 "activation_checkpointing": f"every {ckpt_every} block(s)" if ckpt_every else None,
                 "packing": "ragged" if (args.ragged or finetune) else "uniform",
                 "communication_dtype": args.comm_dtype,
+                "gemm_schedule": ("cluster launch control (one cluster per tile, work stealing)" if K.get_option("gemm_dynamic")
+                                  else f"static persistent workers, {K.get_option('gemm_sm_margin')} SMs left to NCCL"),
+                "attention_cta_order": "heads fastest, longest tiles first" if K.get_option("attn_head_fastest") else "tiles fastest",
                 "l2": "working set (parameters + activations per step, tens of GB) far exceeds the 126 MB L2; four resident "
                       "batches are used in turn; no explicit flush",
             },

@@ -39,7 +39,7 @@ static int g_attn_bwd_ablate = 0;
 int dolo_option_attn_bwd_ablate() { return g_attn_bwd_ablate; }
 static int g_gemm_l2_hints = 1;
 int dolo_option_gemm_l2_hints() { return g_gemm_l2_hints; }
-static int g_gemm_dynamic = 0;
+static int g_gemm_dynamic = 1;  // default since call 85: +1.4 ... +2.1 % on the C2 step, no SM margin next to NCCL
 int dolo_option_gemm_dynamic() { return g_gemm_dynamic; }
 static int g_gemm_f32_tma_epilogue = 0;
 int dolo_option_gemm_f32_tma_epilogue() { return g_gemm_f32_tma_epilogue; }

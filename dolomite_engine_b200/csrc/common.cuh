@@ -51,8 +51,9 @@ int dolo_option_attn_bwd_ablate();
 // attention CTA order: 1 (default) = heads fastest and, inside a document, the longest tiles first: the last wave holds short
 // tiles only; 0 = round 1's order (tiles fastest), which starts the long tiles of the last heads in the last wave
 int dolo_option_attn_head_fastest();
-// 1 = GEMM grids have one cluster per tile and running clusters take over pending ones through cluster launch control
-// (hardware work stealing): the grid uses every SM that is free, no margin for concurrent communication kernels needed
+// 1 (default) = GEMM grids have one cluster per tile and running clusters take over pending ones through cluster launch
+// control (hardware work stealing): the grid uses every SM that is free, no margin for concurrent communication kernels
+// needed; 0 = static persistent workers (tile w, w + W, ...) on `SMs - gemm_sm_margin` SMs
 int dolo_option_gemm_dynamic();
 int dolo_option_gemm_l2_hints();  // 1 (default) = evict-first / evict-last operand loads for long-contraction GEMMs
 

@@ -312,7 +312,9 @@ class ShardedDataParallel(nn.Module):
                 "engine must be built with world_size/rank of the (shard) DP group"
             comm_dtype = torch.bfloat16 if communication_dtype is None else communication_dtype
             self.engine.comm = _Comm(self.engine, process_group, comm_dtype, reshard_after_forward, replicate_group)
-            # persistent GEMM grids must not claim the SMs the NCCL kernels run on (see configure_comm_ctas)
+            # STATIC persistent GEMM grids (gemm_dynamic = 0) must not claim the SMs the NCCL kernels run on (see
+            # configure_comm_ctas); the default cluster-launch-control grids ignore the margin: they run on whatever SMs are
+            # free and pick up the ones a collective releases
             K.set_option("gemm_sm_margin", comm_cta_budget())
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=self.engine.device)
         self.clip_coef = torch.ones(1, dtype=torch.float32, device=self.engine.device)

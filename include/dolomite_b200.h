@@ -39,7 +39,7 @@ int dolomite_b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* process-wide tuning knobs:
  *   "gemm_cta_pair"    0 | 1 (dense GEMMs on 2-CTA clusters with tcgen05.mma.cta_group::2)
  *   "gemm_sm_margin"   SMs the persistent GEMM grids leave free for concurrent communication kernels (static schedule only)
- *   "gemm_dynamic"     0 | 1 (one cluster per output tile; running clusters take over pending ones through cluster launch
+ *   "gemm_dynamic"     1 | 0 (default 1: one cluster per output tile; running clusters take over pending ones through cluster launch
  *                      control, so the grid uses every SM that is or becomes free -- no margin needed next to NCCL kernels)
  *   "attn_fwd_split"   1 | 0 | 2 (split-softmax attention forward -- one CTA per SM, double-buffered scores in TMEM, two threads
  *                      per query row -- for head_dim >= 96 (1, default), never (0), or also for head_dim 64 / 80 (2))
