@@ -216,6 +216,7 @@ class _Comm:
             self.engine.finish_unit_grads(i)
         cur = torch.cuda.current_stream()
         self.stream.wait_stream(cur)
+        self.engine.join_wgrad_stream(self.stream)  # weight gradients launched on the engine's second stream
         first = self.first_rs[i]
         self.first_rs[i] = False
         with torch.cuda.stream(self.stream):

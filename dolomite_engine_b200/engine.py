@@ -17,6 +17,7 @@ No op here has a PyTorch fallback: without the CUDA library every call raises.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import TYPE_CHECKING
 
@@ -267,6 +268,11 @@ class DolomiteEngine:
         self.head_chunk_bytes = 1 << 30  # bf16 logits of one LM-head chunk (forward(fuse_head_loss=True))
         self.batch_block_wgrads = True  # the four weight gradients of a dense block in one persistent launch
         self._deferred_wgrads: list | None = None  # list while a block's backward collects its weight gradients
+        # Weight gradients on a second stream: nothing in a block's backward chain waits for them, so the launch of block i
+        # runs next to block i - 1's chain -- whose HBM-bound kernels (SwiGLU / norm / RoPE backward, column sums) fit on the SMs
+        # NEXT TO a GEMM CTA (it leaves 1.5 KB of shared memory, 39 K registers and 1800 thread slots free) and hide behind it.
+        self.overlap_wgrads = os.environ.get("DOLO_OVERLAP_WGRADS", "0") == "1"
+        self._wgrad_stream = None  # created on first use
         self._kv_sink = None  # callable(layer, packed qkv) while a forward fills a KV cache (prefill)
         self._fresh_grads: set[str] = set()  # weights whose gradient buffer will be overwritten by the next wgrad GEMM
         if cfg.attention_multiplier is not None:
@@ -669,9 +675,26 @@ class DolomiteEngine:
         return dx
 
     def _flush_wgrads(self) -> None:
-        if self._deferred_wgrads:
+        if not self._deferred_wgrads:
+            return
+        if self.overlap_wgrads and self.device.type == "cuda":
+            if self._wgrad_stream is None:
+                self._wgrad_stream = torch.cuda.Stream(device=self.device)
+            side, main = self._wgrad_stream, torch.cuda.current_stream()
+            side.wait_stream(main)  # every (dy, x) pair of the list has been produced on the main stream
+            with torch.cuda.stream(side):
+                K.gemm_wgrad_multi(self._deferred_wgrads)
+            for dy, x, _, _, _ in self._deferred_wgrads:  # the allocator must not hand these blocks out before the launch has read them
+                dy.record_stream(side)
+                x.record_stream(side)
+        else:
             K.gemm_wgrad_multi(self._deferred_wgrads)
-            self._deferred_wgrads.clear()
+        self._deferred_wgrads.clear()
+
+    def join_wgrad_stream(self, stream=None) -> None:
+        """orders `stream` (default: the current one) after every weight-gradient launch issued so far"""
+        if self._wgrad_stream is not None:
+            (torch.cuda.current_stream() if stream is None else stream).wait_stream(self._wgrad_stream)
 
     def backward(self, dlogits=None, grad_scale_dev=None) -> None:
         """Backward of the last forward.  `dlogits` overrides the CE gradient (logits-mode autograd)."""
@@ -772,6 +795,7 @@ class DolomiteEngine:
             self._fresh_grads.clear()
         if comm is not None:
             comm.post_backward_unit(0)
+        self.join_wgrad_stream()  # optimizer / gradient norm / the next zero_grad run on the main stream
         self._saved = None
 
     # ------------------------------------------------------------------------------------------

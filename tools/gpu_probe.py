@@ -353,6 +353,68 @@ def gemm_dynamic():
 
 
 @case
+def overlap_wgrad_elementwise():
+    """Can the HBM-bound kernels of a block's backward hide behind the block's weight-gradient GEMMs?  A GEMM CTA leaves ~1.5 KB
+    of shared memory, 39 K registers and 1800 thread slots of its SM free, so an elementwise CTA can be CO-RESIDENT with it.
+    Serial (one stream) against concurrent (weight gradients on a second stream) time of: the four weight gradients of a C2
+    block (one launch) + the block's elementwise backward kernels (SwiGLU bwd, 2 x RMSNorm bwd, RoPE bwd) at T = 24576."""
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+
+    T, H, F, nh, hd = 24576, 2560, 10240, 32, 80
+    g = torch.Generator(device="cuda").manual_seed(0)
+    probs = []
+    for M, N in ((H, F), (2 * F, H), (H, H), (3 * H, H)):
+        dy = (torch.randn(T, M, device="cuda", generator=g) * 0.1).bfloat16()
+        xx = (torch.randn(T, N, device="cuda", generator=g) * 0.1).bfloat16()
+        probs.append((dy, xx, torch.zeros(M, N, device="cuda"), 1.0, True))
+    fc = (torch.randn(T, 2 * F, device="cuda", generator=g)).bfloat16()
+    d_act = (torch.randn(T, F, device="cuda", generator=g)).bfloat16()
+    x = (torch.randn(T, H, device="cuda", generator=g)).bfloat16()
+    dy = (torch.randn(T, H, device="cuda", generator=g)).bfloat16()
+    w = torch.ones(H, device="cuda").bfloat16()
+    rstd = torch.ones(T, device="cuda")
+    dw = torch.zeros(H, device="cuda")
+    qkv = (torch.randn(T, 3 * H, device="cuda", generator=g)).bfloat16()
+    cos = torch.ones(4096, hd, device="cuda").bfloat16()
+    sin = torch.zeros(4096, hd, device="cuda").bfloat16()
+    pos = (torch.arange(T, device="cuda") % 4096).long()
+    d_fc = torch.empty_like(fc)
+    dx = torch.empty_like(x)
+
+    def elementwise():
+        k.swiglu_bwd(d_act, fc, out=d_fc)
+        k.rmsnorm_bwd(dy, x, w, rstd, dw, dx_add=dy, out=dx)
+        k.rope_qk_inplace(qkv, nh, 1, hd, cos, sin, pos, inverse=True)
+        k.rmsnorm_bwd(dy, x, w, rstd, dw, dx_add=dy, out=dx)
+
+    def wgrad():
+        k.gemm_wgrad_multi(probs)
+
+    side = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+
+    def serial():
+        wgrad()
+        elementwise()
+
+    def concurrent():
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            wgrad()
+        elementwise()
+        main.wait_stream(side)
+
+    res = {}
+    for name, fn in (("wgrad_only", wgrad), ("elementwise_only", elementwise), ("serial", serial), ("concurrent", concurrent),
+                     ("serial_again", serial), ("concurrent_again", concurrent)):
+        res[name + "_ms"] = _time(fn, iters=10, warmup=3)
+    res["hidden_fraction_of_elementwise"] = (res["serial_ms"] - res["concurrent_ms"]) / res["elementwise_only_ms"]
+    res["ok"] = True
+    return res
+
+
+@case
 def gemm_bench_wgrad_splitk():
     """weight-gradient shapes of one C2 block: accumulate-in-place epilogue vs split-K atomic epilogue"""
     torch = _t()

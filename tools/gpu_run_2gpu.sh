@@ -19,10 +19,10 @@ echo "kernel tests rc=$?"; tail -3 gpurun_out/h_kernel_tests.log
 timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "attention or empty or schedules" > gpurun_out/h_attn_tests.log 2>&1
 echo "attention tests (head-fastest CTA order) rc=$?"; tail -3 gpurun_out/h_attn_tests.log
 rm -f gpurun_out/h_probe.jsonl
-for c in elementwise_bench_c2 attn_order_c2 attn_order_c5 attn_order_c4; do
+for c in elementwise_bench_c2 attn_order_c2 attn_order_c5 attn_order_c4 overlap_wgrad_elementwise; do
   timeout 300 python tools/gpu_probe.py --only $c --out gpurun_out/h_probe.jsonl > gpurun_out/h_probe.log 2>&1
 done
-echo "probe rc=$?"; cut -c1-1500 gpurun_out/h_probe.jsonl
+echo "probe rc=$?"; cut -c1-1700 gpurun_out/h_probe.jsonl
 DOLO_OPTIONS=gemm_dynamic=1 timeout 900 python -m pytest tests/test_nccl_parity.py -m gpu -q > gpurun_out/h_nccl_parity_dynamic.log 2>&1
 echo "nccl parity (dynamic) rc=$?"; tail -3 gpurun_out/h_nccl_parity_dynamic.log
 run c2_static_a DOLO_OPTIONS=gemm_dynamic=0 -- --fsdp-mode reshard
