@@ -33,7 +33,7 @@ static int g_attn_fwd_split = 1;
 int dolo_option_attn_fwd_split() { return g_attn_fwd_split; }
 static int g_attn_bwd_variant = 2;
 int dolo_option_attn_bwd_variant() { return g_attn_bwd_variant; }
-static int g_attn_head_fastest = 1;
+static int g_attn_head_fastest = 8;
 int dolo_option_attn_head_fastest() { return g_attn_head_fastest; }
 static int g_attn_bwd_ablate = 0;
 int dolo_option_attn_bwd_ablate() { return g_attn_bwd_ablate; }
@@ -60,7 +60,8 @@ extern "C" int dolomite_b200_set_option(const char* key, int value) {
         return DOLO_OK;
     }
     if (key != nullptr && strcmp(key, "attn_head_fastest") == 0) {
-        g_attn_head_fastest = value != 0;
+        DOLO_REQUIRE(value >= 0 && value <= 1024, "attn_head_fastest must be in [0, 1024]");
+        g_attn_head_fastest = value;
         return DOLO_OK;
     }
     if (key != nullptr && strcmp(key, "attn_bwd_ablate") == 0) {

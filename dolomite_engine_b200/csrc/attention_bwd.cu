@@ -31,7 +31,8 @@ struct BwdParams {
     int64_t T;
     int n_groups, q_per_group, n_heads;
     float scale, scale_log2;
-    int head_fastest;  // CTA order: 1 = kv groups fastest, key tiles of a document longest-first (default); 0 = tiles fastest
+    int head_chunk;    // CTA order (attention_common.cuh: attn_cta_order): kv groups per chunk, 0 = tiles fastest (round 1)
+    int n_tile_slots;  // upper bound of the number of key tiles (the grid has n_tile_slots x n_groups CTAs)
     AttnDropout drop;  // attention-probability dropout of the forward being differentiated (threshold 0: none)
     int ablate;  // TIMING EXPERIMENTS ONLY (wrong results): see dolo_option_attn_bwd_ablate
     unsigned long long* trace;  // DEBUG timeline buffer (5 roles x 2048 events) or nullptr
@@ -116,9 +117,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     // tile, which the dQ MMA has finished reading by the time the accumulator is drained.
     constexpr bool DQ_TMA = (HD % 32 == 0);
 
-    const TileLoc loc = locate_tile(p.cu_seqlens, p.n_docs, p.head_fastest ? int(blockIdx.y) : int(blockIdx.x));
+    int cta_tile, group;  // key tiles of a document in natural order = longest first
+    attn_cta_order(p.head_chunk, p.n_tile_slots, cta_tile, group);
+    const TileLoc loc = locate_tile(p.cu_seqlens, p.n_docs, cta_tile);
     if (!loc.valid) return;
-    const int group = p.head_fastest ? blockIdx.x : blockIdx.y;  // (CTA order: see attn_fwd_kernel)
     const int j = loc.tile;                                      // kv tile
     const int n_q_tiles = (loc.doc_len + ATT_TILE - 1) / ATT_TILE;
     const int n_i = n_q_tiles - j;                               // q tiles j .. n_q_tiles-1
@@ -506,7 +508,8 @@ int launch_bwd(const void* dout, const void* qkv, int64_t row_stride, const BwdP
         attr_set = true;
     }
     const int64_t max_tiles = (p.T + ATT_TILE - 1) / ATT_TILE + p.n_docs;
-    dim3 grid = p.head_fastest ? dim3((unsigned)p.n_groups, (unsigned)max_tiles) : dim3((unsigned)max_tiles, (unsigned)p.n_groups);
+    DOLO_REQUIRE(max_tiles == p.n_tile_slots && max_tiles * p.n_groups < (1ll << 31), "attn_bwd: grid too large");
+    dim3 grid((unsigned)(max_tiles * p.n_groups));
     kern<<<grid, BWD_THREADS, smem_bytes, st>>>(tq64, tqR, to64, toR, tdq, p);
     DOLO_LAUNCH_OK("attn_varlen_bwd");
     return DOLO_OK;
@@ -582,7 +585,8 @@ extern "C" int dolomite_b200_attn_varlen_bwd_dropout(const void* dout, const voi
     p.n_heads = nh;
     p.scale = softmax_scale;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
-    p.head_fastest = (dolo_option_attn_head_fastest() != 0 && (T + ATT_TILE - 1) / ATT_TILE + n_docs <= 65535) ? 1 : 0;
+    p.n_tile_slots = int((T + ATT_TILE - 1) / ATT_TILE + n_docs);
+    p.head_chunk = attn_head_chunk(dolo_option_attn_head_fastest(), n_groups, 1);
     p.drop.threshold = dolo_dropout_threshold(dropout_p);
     p.drop.keep_scale = 1.f / (1.f - dropout_p);
     p.drop.key0 = key0;

@@ -73,9 +73,10 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
     constexpr uint32_t ST_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 256 + HD, DQ_COL = 256 + 2 * HD;
     constexpr int DS_BYTES = 2 * ATT_TILE * 128;  // 128 keys x 128 queries bf16 (two 64-query MN chunks)
 
-    const TileLoc loc = locate_tile(p.cu_seqlens, p.n_docs, p.head_fastest ? int(blockIdx.y) : int(blockIdx.x));
+    int cta_tile, group;  // key tiles of a document in natural order = longest first
+    attn_cta_order(p.head_chunk, p.n_tile_slots, cta_tile, group);
+    const TileLoc loc = locate_tile(p.cu_seqlens, p.n_docs, cta_tile);
     if (!loc.valid) return;
-    const int group = p.head_fastest ? blockIdx.x : blockIdx.y;  // (CTA order: see attn_fwd_kernel)
     const int j = loc.tile;
     const int n_q_tiles = (loc.doc_len + ATT_TILE - 1) / ATT_TILE;
     const int n_i = n_q_tiles - j;
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(32 * (6 + 4 * NG), 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // DEBUG timeline (dolomite_b200_debug_attn_bwd_trace): one thread per role of ONE CTA stamps clock64() at its events
     constexpr int TRACE_CAP = 2048;
-    const bool tr_cta = p.trace != nullptr && (p.head_fastest ? int(blockIdx.y) : int(blockIdx.x)) == p.trace_cta && group == 0;
+    const bool tr_cta = p.trace != nullptr && cta_tile == p.trace_cta && group == 0;
     int tr_n = 0;
     auto TR = [&](int role, int id) {
         if (tr_cta && tr_n < TRACE_CAP)
@@ -800,7 +801,8 @@ int launch_bwd_v3(const void* dout, const void* qkv, int64_t row_stride, const B
         attr_set = true;
     }
     const int64_t max_tiles = (p.T + ATT_TILE - 1) / ATT_TILE + p.n_docs;
-    dim3 grid = p.head_fastest ? dim3((unsigned)p.n_groups, (unsigned)max_tiles) : dim3((unsigned)max_tiles, (unsigned)p.n_groups);
+    DOLO_REQUIRE(max_tiles == p.n_tile_slots && max_tiles * p.n_groups < (1ll << 31), "attn_bwd: grid too large");
+    dim3 grid((unsigned)(max_tiles * p.n_groups));
     kern<<<grid, 32 * (6 + 4 * NG), smem_bytes, st>>>(tq64, tqR, to64, toR, tdq32, tdq16, p);
     DOLO_LAUNCH_OK("attn_varlen_bwd_v2");
     return DOLO_OK;

@@ -28,7 +28,8 @@ struct FwdParams {
     float scale_log2;  // softmax_scale * log2(e)
     float scale;
     AttnDropout drop;  // threshold 0: none
-    int head_fastest;  // CTA order: 1 = heads fastest, tiles longest-first (default); 0 = tiles fastest (round 1)
+    int head_chunk;    // CTA order (attention_common.cuh: attn_cta_order): heads per chunk, 0 = tiles fastest (round 1)
+    int n_tile_slots;  // upper bound of the number of query tiles (the grid has n_tile_slots x n_heads CTAs)
 };
 
 template <int HD>
@@ -40,14 +41,11 @@ __global__ void __launch_bounds__(FWD_THREADS)
     constexpr int TMEM_COLS = (128 + HD) <= 256 ? 256 : 512;
     constexpr uint32_t O_COL = 128;
 
-    // CTA order (dispatch = x fastest).  head_fastest: x = head, y = tile, long (late) tiles first -- all heads of the longest
-    // tile start first and the last wave holds only short tiles.  The round-1 order (x = tile, y = head) started the LONG tiles
-    // of the last heads in the last wave: a list-scheduling model of S = 4096 x 2 docs x 32 heads on 148 SMs loses 7 % (one CTA
-    // per SM) to 14 % (two per SM) to that tail.
-    const int ti = p.head_fastest ? int(gridDim.y) - 1 - int(blockIdx.y) : int(gridDim.x) - 1 - int(blockIdx.x);
+    int ti, head;
+    attn_cta_order(p.head_chunk, p.n_tile_slots, ti, head);
+    ti = p.n_tile_slots - 1 - ti;  // long (late) tiles first
     const TileLoc loc = locate_tile(p.cu_seqlens, p.n_docs, ti);
     if (!loc.valid) return;  // uniform for the whole CTA
-    const int head = p.head_fastest ? blockIdx.x : blockIdx.y;
     const int group = head / p.q_per_group, slot = head % p.q_per_group;
     const int q_col = (group * (p.q_per_group + 2) + slot) * HD;
     const int k_col = (group * (p.q_per_group + 2) + p.q_per_group) * HD;
@@ -376,10 +374,11 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1)
     constexpr int NCH16 = HD / 16;               // 16-column chunks of O
     constexpr int CH_SPLIT = (NCH16 + 1) / 2;    // chunks [0, CH_SPLIT) belong to column group 0, the rest to group 1
 
-    const int ti = p.head_fastest ? int(gridDim.y) - 1 - int(blockIdx.y) : int(gridDim.x) - 1 - int(blockIdx.x);  // see attn_fwd_kernel
+    int ti, head;
+    attn_cta_order(p.head_chunk, p.n_tile_slots, ti, head);
+    ti = p.n_tile_slots - 1 - ti;  // long (late) tiles first
     const TileLoc loc = locate_tile(p.cu_seqlens, p.n_docs, ti);
     if (!loc.valid) return;  // uniform for the whole CTA
-    const int head = p.head_fastest ? blockIdx.x : blockIdx.y;
     const int group = head / p.q_per_group, slot = head % p.q_per_group;
     const int q_col = (group * (p.q_per_group + 2) + slot) * HD;
     const int k_col = (group * (p.q_per_group + 2) + p.q_per_group) * HD;
@@ -700,8 +699,8 @@ int launch_fwd_split(const void* qkv, int64_t row_stride, const FwdParams& p, cu
         attr_set = true;
     }
     const int64_t max_tiles = (p.T + ATT_TILE - 1) / ATT_TILE + p.n_docs;
-    DOLO_REQUIRE(!p.head_fastest || max_tiles <= 65535, "attn_fwd: too many query tiles for grid.y");
-    dim3 grid = p.head_fastest ? dim3((unsigned)p.n_heads, (unsigned)max_tiles) : dim3((unsigned)max_tiles, (unsigned)p.n_heads);
+    DOLO_REQUIRE(max_tiles == p.n_tile_slots && max_tiles * p.n_heads < (1ll << 31), "attn_fwd: grid too large");
+    dim3 grid((unsigned)(max_tiles * p.n_heads));
     kern<<<grid, FWD2_THREADS, smem_bytes, st>>>(t64, tR, p);
     DOLO_LAUNCH_OK("attn_varlen_fwd_split");
     return DOLO_OK;
@@ -735,8 +734,8 @@ int launch_fwd(const void* qkv, int64_t row_stride, const FwdParams& p, int max_
     }
     // upper bound on the number of q tiles without reading cu_seqlens on the host
     const int64_t max_tiles = (p.T + ATT_TILE - 1) / ATT_TILE + p.n_docs;
-    DOLO_REQUIRE(!p.head_fastest || max_tiles <= 65535, "attn_fwd: too many query tiles for grid.y");
-    dim3 grid = p.head_fastest ? dim3((unsigned)p.n_heads, (unsigned)max_tiles) : dim3((unsigned)max_tiles, (unsigned)p.n_heads);
+    DOLO_REQUIRE(max_tiles == p.n_tile_slots && max_tiles * p.n_heads < (1ll << 31), "attn_fwd: grid too large");
+    dim3 grid((unsigned)(max_tiles * p.n_heads));
     kern<<<grid, FWD_THREADS, smem_bytes, st>>>(t64, tR, p);
     DOLO_LAUNCH_OK("attn_varlen_fwd");
     (void)max_seqlen;
@@ -781,7 +780,8 @@ extern "C" int dolomite_b200_attn_varlen_fwd_dropout(const void* qkv, int64_t ro
     p.drop.keep_scale = 1.f / (1.f - dropout_p);
     p.drop.key0 = key0;
     p.drop.key1 = key1;
-    p.head_fastest = (dolo_option_attn_head_fastest() != 0 && (T + ATT_TILE - 1) / ATT_TILE + n_docs <= 65535) ? 1 : 0;
+    p.n_tile_slots = int((T + ATT_TILE - 1) / ATT_TILE + n_docs);
+    p.head_chunk = attn_head_chunk(dolo_option_attn_head_fastest(), p.n_heads, q_per_group);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int split = dolo_option_attn_fwd_split();
     switch (head_dim) {

@@ -48,8 +48,8 @@ int dolo_option_gemm_f32_tma_epilogue();
 int dolo_option_attn_fwd_split();  // 0 never / 1 (default) head_dim >= 96 / 2 also head_dim 64, 80: split-softmax forward
 int dolo_option_attn_bwd_variant();  // head_dim 64 / 80 backward: 0 = round-1 softmax warps, 1 = lean, 2 (default) = lean + uniform 16-column chunks at head_dim 80 (0.701 vs 0.752 ms, profiles/r02_probe_attn_bwd_uniform_chunks_call80.jsonl; identical to 1 at head_dim 64)
 int dolo_option_attn_bwd_ablate();
-// attention CTA order: 1 (default) = heads fastest and, inside a document, the longest tiles first: the last wave holds short
-// tiles only; 0 = round 1's order (tiles fastest), which starts the long tiles of the last heads in the last wave
+// attention CTA order (attention_common.cuh: attn_cta_order): heads per chunk (default 8; heads fastest inside a chunk, the
+// longest tiles of a document first, so that the last wave holds short tiles only); 0 = round 1's order (tiles fastest)
 int dolo_option_attn_head_fastest();
 // 1 (default) = GEMM grids have one cluster per tile and running clusters take over pending ones through cluster launch
 // control (hardware work stealing): the grid uses every SM that is free, no margin for concurrent communication kernels

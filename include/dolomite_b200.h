@@ -43,8 +43,8 @@ int dolomite_b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *                      control, so the grid uses every SM that is or becomes free -- no margin needed next to NCCL kernels)
  *   "attn_fwd_split"   1 | 0 | 2 (split-softmax attention forward -- one CTA per SM, double-buffered scores in TMEM, two threads
  *                      per query row -- for head_dim >= 96 (1, default), never (0), or also for head_dim 64 / 80 (2))
- *   "attn_head_fastest" 1 | 0 (attention CTA order: heads fastest + longest tiles first, so that the last wave is short tiles;
- *                      0 = tiles fastest, round 1's order)
+ *   "attn_head_fastest" heads per chunk of the attention CTA order (default 8: inside a chunk heads fastest + longest tiles
+ *                      first, so that the last wave is short tiles; 0 = tiles fastest, round 1's order)
  *   "gemm_l2_hints"    1 | 0 (long-contraction GEMMs load the streamed operand evict-first and the re-used one evict-last)
  *   "gemm_f32_tma_epilogue" 0 | 1 (fp32 weight gradients through TMA tile store / reduce-add instead of per-thread stores) */
 int dolomite_b200_set_option(const char* key, int value);

@@ -910,10 +910,10 @@ def _attn_bench(S, B, nh, hd):
     return res
 
 
-def _attn_order_ab(S, B, ng, g, hd, rounds=3):
-    """CTA order of the attention kernels: heads fastest + longest tiles first (attn_head_fastest = 1) against round 1's tiles
-    fastest (0); forward and backward, interleaved; results must be bit-identical (the order changes nothing but timing -- the
-    backward's dQ reduction order aside)"""
+def _attn_order_ab(S, B, ng, g, hd, rounds=3, orders=(0, 8, 1024)):
+    """CTA order of the attention kernels (`attn_head_fastest`): round 1's tiles fastest (0), chunks of 8 heads (default) and
+    all heads in one chunk (1024); forward and backward, interleaved; the forward must be bit-identical (the order changes
+    nothing but timing -- the order of the backward's dQ reduction aside)"""
     torch = _t()
     from dolomite_engine_b200 import kernels as k
 
@@ -926,11 +926,11 @@ def _attn_order_ab(S, B, ng, g, hd, rounds=3):
     res = {"shape": [S, B, ng, g, hd]}
     default = k.get_option("attn_head_fastest")
     outs = {}
+    tf = {o: [] for o in orders}
+    tb = {o: [] for o in orders}
     try:
-        tf = {0: [], 1: []}
-        tb = {0: [], 1: []}
         for _ in range(rounds):
-            for order in (0, 1):
+            for order in orders:
                 k.set_option("attn_head_fastest", order)
                 out, lse = k.attn_varlen_fwd(qkv, cu, S, ng, g, hd, scale)
                 dqkv = k.attn_varlen_bwd(dout, qkv, out, lse, cu, S, ng, g, hd, scale)
@@ -939,13 +939,12 @@ def _attn_order_ab(S, B, ng, g, hd, rounds=3):
                 tb[order].append(_time(lambda: k.attn_varlen_bwd(dout, qkv, out, lse, cu, S, ng, g, hd, scale, dqkv=dqkv), iters=5))
     finally:
         k.set_option("attn_head_fastest", default)
-    res["fwd_bit_identical"] = bool(torch.equal(outs[0][0], outs[1][0]))
-    res["bwd_rel_l2_between_orders"] = _err(outs[1][1], outs[0][1])["rel_l2"]
-    for order in (0, 1):
-        res[f"order{order}_fwd_ms"] = tf[order]
-        res[f"order{order}_bwd_ms"] = tb[order]
-        res[f"order{order}_fwd_tflops_causal"] = flops_fwd / min(tf[order]) / 1e9
-        res[f"order{order}_bwd_tflops_causal"] = 2.5 * flops_fwd / min(tb[order]) / 1e9
+    res["fwd_bit_identical"] = bool(all(torch.equal(outs[orders[0]][0], outs[o][0]) for o in orders))
+    res["bwd_rel_l2_between_orders"] = max(_err(outs[o][1], outs[orders[0]][1])["rel_l2"] for o in orders)
+    for order in orders:
+        res[f"order{order}"] = {"fwd_ms": round(min(tf[order]), 4), "bwd_ms": round(min(tb[order]), 4),
+                                "fwd_tflops_causal": round(flops_fwd / min(tf[order]) / 1e9),
+                                "bwd_tflops_causal": round(2.5 * flops_fwd / min(tb[order]) / 1e9)}
     res["ok"] = bool(res["fwd_bit_identical"] and res["bwd_rel_l2_between_orders"] < 1e-3)
     return res
 

@@ -4,10 +4,12 @@
 # C2 bench A/B; attention CTA order A/B and the overlap probe if the 2-GPU call did not run them.
 set -u
 mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "attention or empty" > gpurun_out/c87_attn_tests.log 2>&1
+echo "attention tests (chunked CTA order) rc=$?"; tail -n 2 gpurun_out/c87_attn_tests.log
 DOLO_OVERLAP_WGRADS=1 timeout 900 python -m pytest tests/test_gpu_model.py tests/test_gpu_dropout.py -m gpu -q -x > gpurun_out/c87_overlap_tests.log 2>&1
 echo "model tests with overlapped wgrads rc=$?"; tail -n 4 gpurun_out/c87_overlap_tests.log | cut -c1-400
 rm -f gpurun_out/c87_probe.jsonl
-for c in overlap_wgrad_elementwise attn_order_c2 attn_order_c5 elementwise_bench_c2; do
+for c in attn_order_c2 attn_order_c5 attn_order_c4; do
   timeout 300 python tools/gpu_probe.py --only $c --out gpurun_out/c87_probe.jsonl > gpurun_out/c87_probe.log 2>&1
 done
 cut -c1-1600 gpurun_out/c87_probe.jsonl
