@@ -782,6 +782,9 @@ extern "C" int dolomite_b200_attn_varlen_fwd_dropout(const void* qkv, int64_t ro
     p.drop.key1 = key1;
     p.n_tile_slots = int((T + ATT_TILE - 1) / ATT_TILE + n_docs);
     p.head_chunk = attn_head_chunk(dolo_option_attn_head_fastest(), p.n_heads, q_per_group);
+    // all heads in one chunk when the K / V of the whole batch stay in L2 anyway (GQA / short batches): nothing to lose to
+    // re-reads, and the longest-first order then spans every head (Llama-3-8B shape: 0.707 -> 0.666 ms, call 87)
+    if (p.head_chunk > 0 && T * int64_t(n_groups) * head_dim * 4 <= (64ll << 20)) p.head_chunk = p.n_heads;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int split = dolo_option_attn_fwd_split();
     switch (head_dim) {

@@ -83,13 +83,14 @@ __global__ void __launch_bounds__(kThreads) rmsnorm_fwd_kernel(const uint4* __re
 // requested before the first use; the sum of squares is a warp reduction -- no shared memory, no block barrier.  The
 // block-per-row kernel above keeps 8 CTAs x 5 KB = 40 KB of loads in flight per SM at H = 2560 (8 of its 32 registers hold
 // data) and measured 4.6-4.9 TB/s; here 40 of ~64 registers hold data and 32 resident warps keep 160 KB in flight.
+constexpr int kWarpRowThreads = 128;  // 4 rows per CTA, one CTA per 4 rows: no row loop, hence no imbalance between warps
 template <int NVW>
-__global__ void __launch_bounds__(kThreads) rmsnorm_fwd_warp_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w,
-                                                                    uint4* __restrict__ y, float* __restrict__ rstd,
-                                                                    int64_t T, int H8, float eps, float inv_h) {
+__global__ void __launch_bounds__(kWarpRowThreads)
+    rmsnorm_fwd_warp_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w, uint4* __restrict__ y,
+                            float* __restrict__ rstd, int64_t T, int H8, float eps, float inv_h) {
     const int lane = threadIdx.x & 31;
-    const int64_t warp0 = int64_t(blockIdx.x) * (kThreads / 32) + (threadIdx.x >> 5);
-    const int64_t nwarps = int64_t(gridDim.x) * (kThreads / 32);
+    const int64_t warp0 = int64_t(blockIdx.x) * (kWarpRowThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = int64_t(gridDim.x) * (kWarpRowThreads / 32);
     for (int64_t row = warp0; row < T; row += nwarps) {
         const uint4* xr = x + row * H8;
         uint4 xv[NVW];
@@ -1006,13 +1007,13 @@ extern "C" int dolomite_b200_rmsnorm_fwd(const void* x, const void* w, void* y, 
     auto Y = static_cast<uint4*>(y);
     const float inv_h = 1.f / float(H);
     if (H8 <= 16 * 32 && T >= 64) {  // one warp per row
-        const int64_t want = (T + kThreads / 32 - 1) / (kThreads / 32);
-        const int wgrid = int(want < int64_t(dolo_num_sms()) * 8 ? want : int64_t(dolo_num_sms()) * 8);
+        const int64_t want = (T + kWarpRowThreads / 32 - 1) / (kWarpRowThreads / 32);
+        const int wgrid = int(want < (1ll << 30) ? want : (1ll << 30));
         const int nvw = (H8 + 31) / 32;
-        if (nvw <= 4) rmsnorm_fwd_warp_kernel<4><<<wgrid, kThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h);
-        else if (nvw <= 8) rmsnorm_fwd_warp_kernel<8><<<wgrid, kThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h);
-        else if (nvw <= 10) rmsnorm_fwd_warp_kernel<10><<<wgrid, kThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h);
-        else rmsnorm_fwd_warp_kernel<16><<<wgrid, kThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h);
+        if (nvw <= 4) rmsnorm_fwd_warp_kernel<4><<<wgrid, kWarpRowThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h);
+        else if (nvw <= 8) rmsnorm_fwd_warp_kernel<8><<<wgrid, kWarpRowThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h);
+        else if (nvw <= 10) rmsnorm_fwd_warp_kernel<10><<<wgrid, kWarpRowThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h);
+        else rmsnorm_fwd_warp_kernel<16><<<wgrid, kWarpRowThreads, 0, st>>>(X, W, Y, rstd, T, H8, eps, inv_h);
         DOLO_LAUNCH_OK("rmsnorm_fwd");
         return DOLO_OK;
     }
