@@ -356,23 +356,32 @@ __global__ void __launch_bounds__(FWD_THREADS)
 //   * lazy reference maximum (threshold 2^8) so that O in TMEM is rescaled a handful of times per row.
 // P(j) (bf16) overwrites the S columns its own thread has consumed; the PV MMA reads it with one TMEM address per 16-key step.
 // ------------------------------------------------------------------------------------------------------------------------
-constexpr int FWD2_THREADS = 320;
-
-template <int HD>
-constexpr int fwd2_kv_stages() {
-    return (1024 + (1 + 2 * 3) * HeadChunks<HD>::TILE_BYTES + 4 * ATT_TILE * 4 + 256 <= 232448) ? 3 : 2;
+// NT = threads per query row (2 or 4): 4 NT softmax warps, thread g of a row owns the 128 / NT key columns [g 128 / NT, ...).
+// NT = 4 halves the dependent chain per thread again and puts four softmax warps on every scheduler.
+template <int NT>
+constexpr int fwd2_threads() {
+    return 64 + 128 * NT;
 }
 
 template <int HD>
-__global__ void __launch_bounds__(FWD2_THREADS, 1)
+constexpr int fwd2_kv_stages() {
+    return (1024 + (1 + 2 * 3) * HeadChunks<HD>::TILE_BYTES + 8 * ATT_TILE * 4 + 256 <= 232448) ? 3 : 2;
+}
+
+template <int HD, int NT>
+__global__ void __launch_bounds__(fwd2_threads<NT>(), 1)
     attn_fwd_split_kernel(const __grid_constant__ CUtensorMap tmap64, const __grid_constant__ CUtensorMap tmapR,
                           const FwdParams p) {
+    static_assert(NT == 2 || NT == 4, "two or four threads per query row");
     using CH = HeadChunks<HD>;
     constexpr int TILE_BYTES = CH::TILE_BYTES;
     constexpr int ST = fwd2_kv_stages<HD>();
+    constexpr int GCOLS = ATT_TILE / NT;  // key columns per thread
+    constexpr int NV = GCOLS / 32;        // 32-column register blocks per thread
     constexpr uint32_t O_COL = 256;
     constexpr int NCH16 = HD / 16;               // 16-column chunks of O
-    constexpr int CH_SPLIT = (NCH16 + 1) / 2;    // chunks [0, CH_SPLIT) belong to column group 0, the rest to group 1
+    // O chunks [chunk_lo(g), chunk_lo(g + 1)) belong to column group g (rescale and epilogue)
+    auto chunk_lo = [](int gg) { return (gg * NCH16 + NT - 1) / NT; };
 
     int ti, head;
     attn_cta_order(p.head_chunk, p.n_tile_slots, ti, head);
@@ -392,8 +401,8 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1)
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + TILE_BYTES;            // [ST]
     uint8_t* sV = sK + ST * TILE_BYTES;       // [ST]
-    float* xmax = reinterpret_cast<float*>(sV + ST * TILE_BYTES);  // [2 parities][2 groups][128]  row-max exchange
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xmax + 4 * ATT_TILE);
+    float* xmax = reinterpret_cast<float*>(sV + ST * TILE_BYTES);  // [2 parities][NT groups][128]  row-max exchange
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xmax + 8 * ATT_TILE);
     uint64_t* q_full = bars;                 // 1
     uint64_t* kv_full = bars + 1;            // [ST]
     uint64_t* kv_empty = bars + 1 + ST;      // [ST]
@@ -415,7 +424,7 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1)
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1);
-            mbar_init(&p_ready[i], 256);
+            mbar_init(&p_ready[i], 128 * NT);
         }
         mbar_init(pv_done, 1);
         mbar_init(o_full, 1);
@@ -488,8 +497,9 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1)
                     const uint32_t idesc_pv = umma_idesc_bf16(128, w, false, true);
 #pragma unroll
                     for (int k = 0; k < ATT_TILE / 16; ++k) {
-                        // P of keys [16k, 16k+16): written by column group k / 4 at its own offset (k % 4) * 8
-                        const uint32_t a_tmem = tmem_base + uint32_t(b) * 128 + uint32_t(k >> 2) * 64 + uint32_t(k & 3) * 8;
+                        // P of keys [16k, 16k+16): written by the column group that owns them, at the start of its own columns
+                        constexpr int KPG = GCOLS / 16;  // 16-key steps per column group
+                        const uint32_t a_tmem = tmem_base + uint32_t(b) * 128 + uint32_t(k / KPG) * GCOLS + uint32_t(k % KPG) * 8;
                         umma_ts(tmem_base + O_COL + CH::col(c), a_tmem, chunk_desc_mnmajor(v_s + CH::offset(c), w, k), idesc_pv,
                                 (j > 0 || k > 0) ? 1u : 0u);
                     }
@@ -501,52 +511,56 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1)
             }
         }
     } else {
-        // ---------------- softmax: two threads per query row, 64 key columns each ----------------
+        // ---------------- softmax: NT threads per query row, 128 / NT key columns each ----------------
         const int g = (warp - 2) >> 2;                 // column group
         const int sub = warp & 3;                      // TMEM sub-partition of this warp (lanes 32 sub .. 32 sub + 31)
         const int r = sub * 32 + lane;
         const uint32_t t_lane = tmem_base + (uint32_t(sub * 32) << 16);
         const int qi = q0 + r;
-        const uint32_t pair_bar = 1 + uint32_t(sub);   // named barrier of the two warps that share this row block
+        const uint32_t pair_bar = 1 + uint32_t(sub);   // named barrier of the NT warps that share this row block
         float m_run = -INFINITY, l_run = 0.f;
         const bool drop = p.drop.threshold != 0;  // dropout: every tile takes the per-element path below
         const uint32_t head_key = dropout_head_key(uint32_t(head), p.drop.key0, p.drop.key1);
         for (int j = 0; j < n_kv; ++j) {
             const int b = j & 1;
-            const uint32_t s_col = t_lane + uint32_t(b) * 128 + uint32_t(g) * 64;
+            const uint32_t s_col = t_lane + uint32_t(b) * 128 + uint32_t(g) * GCOLS;
             mbar_wait(&s_full[b], uint32_t(j >> 1) & 1, 54);
             tc_fence_after();
             const bool diag = (j == n_kv - 1);
-            const int kbase = j * ATT_TILE + g * 64;
-            uint32_t va[32], vb[32];
-            tmem_ld32(s_col, va);
-            tmem_ld32(s_col + 32, vb);
+            const int kbase = j * ATT_TILE + g * GCOLS;
+            uint32_t v[NV][32];
+#pragma unroll
+            for (int h = 0; h < NV; ++h) tmem_ld32(s_col + h * 32, v[h]);
             tmem_ld_wait();
-            reg_fence32(va);
-            reg_fence32(vb);
-            // ---- row maximum over my 64 columns, then over the pair ----
+#pragma unroll
+            for (int h = 0; h < NV; ++h) reg_fence32(v[h]);
+            // ---- row maximum over my columns, then over the threads of the row ----
             float mx = -INFINITY, mx1 = -INFINITY;
             if (!diag) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    mx = fmax3(mx, __uint_as_float(va[i]), __uint_as_float(va[i + 1]));
-                    mx1 = fmax3(mx1, __uint_as_float(va[i + 2]), __uint_as_float(va[i + 3]));
-                    mx = fmax3(mx, __uint_as_float(vb[i]), __uint_as_float(vb[i + 1]));
-                    mx1 = fmax3(mx1, __uint_as_float(vb[i + 2]), __uint_as_float(vb[i + 3]));
-                }
+                for (int h = 0; h < NV; ++h)
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        mx = fmax3(mx, __uint_as_float(v[h][i]), __uint_as_float(v[h][i + 1]));
+                        mx1 = fmax3(mx1, __uint_as_float(v[h][i + 2]), __uint_as_float(v[h][i + 3]));
+                    }
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (kbase + i <= qi) mx = fmaxf(mx, __uint_as_float(va[i]));
-                    if (kbase + 32 + i <= qi) mx1 = fmaxf(mx1, __uint_as_float(vb[i]));
-                }
+                for (int h = 0; h < NV; ++h)
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        if (kbase + h * 32 + i <= qi) mx = fmaxf(mx, __uint_as_float(v[h][i]));
+                        if (kbase + h * 32 + i + 1 <= qi) mx1 = fmaxf(mx1, __uint_as_float(v[h][i + 1]));
+                    }
             }
             mx = fmaxf(mx, mx1);
-            float* xm = xmax + (b * 2) * ATT_TILE;  // parity-buffered: the partner may still read the previous tile's value
+            float* xm = xmax + (b * NT) * ATT_TILE;  // parity-buffered: a partner may still read the previous tile's value
             xm[g * ATT_TILE + r] = mx;
-            named_bar_sync(pair_bar, 64);
-            mx = fmaxf(fmaxf(mx, xm[(1 - g) * ATT_TILE + r]), m_run);
-            // lazy reference maximum (see attn_fwd_kernel): identical in both threads of the row
+            named_bar_sync(pair_bar, 32 * NT);
+#pragma unroll
+            for (int o = 1; o < NT; ++o) mx = fmaxf(mx, xm[((g + o) % NT) * ATT_TILE + r]);
+            mx = fmaxf(mx, m_run);
+            // lazy reference maximum (see attn_fwd_kernel): identical in all threads of the row
             const bool move_ref = (m_run == -INFINITY) || (mx * p.scale_log2 > m_run * p.scale_log2 + 8.f);
             const float m_new = move_ref ? mx : m_run;
             const float m_scaled = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
@@ -559,7 +573,7 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1)
                 tc_fence_after();
                 if (!__all_sync(0xffffffffu, alpha == 1.f)) {
 #pragma unroll 1
-                    for (int c = (g == 0 ? 0 : CH_SPLIT); c < (g == 0 ? CH_SPLIT : NCH16); ++c) {
+                    for (int c = chunk_lo(g); c < chunk_lo(g + 1); ++c) {
                         uint32_t o[16];
                         tmem_ld16(t_lane + O_COL + c * 16, o);
                         tmem_ld_wait();
@@ -575,54 +589,36 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1)
             uint32_t pk[16];
             if (!diag && !drop) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float x0, x1;
-                    ffma2_bcast(x0, x1, __uint_as_float(va[i]), __uint_as_float(va[i + 1]), p.scale_log2, neg_m);
-                    const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
-                    fadd2(lsum, lsum1, p0, p1);
-                    pk[i >> 1] = pack_bf16(p0, p1);
-                }
-                tmem_st16(s_col, pk);
+                for (int h = 0; h < NV; ++h) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float x0, x1;
-                    ffma2_bcast(x0, x1, __uint_as_float(vb[i]), __uint_as_float(vb[i + 1]), p.scale_log2, neg_m);
-                    const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
-                    fadd2(lsum, lsum1, p0, p1);
-                    pk[i >> 1] = pack_bf16(p0, p1);
+                    for (int i = 0; i < 32; i += 2) {
+                        float x0, x1;
+                        ffma2_bcast(x0, x1, __uint_as_float(v[h][i]), __uint_as_float(v[h][i + 1]), p.scale_log2, neg_m);
+                        const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+                        fadd2(lsum, lsum1, p0, p1);
+                        pk[i >> 1] = pack_bf16(p0, p1);
+                    }
+                    tmem_st16(s_col + h * 16, pk);
                 }
-                tmem_st16(s_col + 16, pk);
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float p0 = fast_exp2(fmaf(__uint_as_float(va[i]), p.scale_log2, neg_m));
-                    float p1 = fast_exp2(fmaf(__uint_as_float(va[i + 1]), p.scale_log2, neg_m));
-                    if (kbase + i > qi) p0 = 0.f;  // (never true off the diagonal tile)
-                    if (kbase + i + 1 > qi) p1 = 0.f;
-                    lsum += p0;
-                    lsum1 += p1;
-                    if (drop) {
-                        p0 *= attn_drop_scale(p.drop, head_key, row_base + r, loc.doc_start + kbase + i);
-                        p1 *= attn_drop_scale(p.drop, head_key, row_base + r, loc.doc_start + kbase + i + 1);
-                    }
-                    pk[i >> 1] = pack_bf16(p0, p1);
-                }
-                tmem_st16(s_col, pk);
+                for (int h = 0; h < NV; ++h) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float p0 = fast_exp2(fmaf(__uint_as_float(vb[i]), p.scale_log2, neg_m));
-                    float p1 = fast_exp2(fmaf(__uint_as_float(vb[i + 1]), p.scale_log2, neg_m));
-                    if (kbase + 32 + i > qi) p0 = 0.f;
-                    if (kbase + 32 + i + 1 > qi) p1 = 0.f;
-                    lsum += p0;
-                    lsum1 += p1;
-                    if (drop) {
-                        p0 *= attn_drop_scale(p.drop, head_key, row_base + r, loc.doc_start + kbase + 32 + i);
-                        p1 *= attn_drop_scale(p.drop, head_key, row_base + r, loc.doc_start + kbase + 32 + i + 1);
+                    for (int i = 0; i < 32; i += 2) {
+                        float p0 = fast_exp2(fmaf(__uint_as_float(v[h][i]), p.scale_log2, neg_m));
+                        float p1 = fast_exp2(fmaf(__uint_as_float(v[h][i + 1]), p.scale_log2, neg_m));
+                        if (kbase + h * 32 + i > qi) p0 = 0.f;  // (never true off the diagonal tile)
+                        if (kbase + h * 32 + i + 1 > qi) p1 = 0.f;
+                        lsum += p0;
+                        lsum1 += p1;
+                        if (drop) {
+                            p0 *= attn_drop_scale(p.drop, head_key, row_base + r, loc.doc_start + kbase + h * 32 + i);
+                            p1 *= attn_drop_scale(p.drop, head_key, row_base + r, loc.doc_start + kbase + h * 32 + i + 1);
+                        }
+                        pk[i >> 1] = pack_bf16(p0, p1);
                     }
-                    pk[i >> 1] = pack_bf16(p0, p1);
+                    tmem_st16(s_col + h * 16, pk);
                 }
-                tmem_st16(s_col + 16, pk);
             }
             l_run = l_run * alpha + (lsum + lsum1);
             m_run = m_new;
@@ -630,18 +626,20 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1)
             tc_fence_before();
             mbar_arrive(&p_ready[b]);
         }
-        // ---------------- epilogue: combine the two partial row sums, each thread stores its half of the O columns ----------------
+        // ---------------- epilogue: combine the partial row sums, each thread stores its share of the O columns ----------------
         mbar_wait(o_full, 0, 56);
         tc_fence_after();
-        float* xs = xmax + ((n_kv & 1) * 2) * ATT_TILE;  // the parity buffer the last tile did not use
+        float* xs = xmax + ((n_kv & 1) * NT) * ATT_TILE;  // the parity buffer the last tile did not use
         xs[g * ATT_TILE + r] = l_run;
-        named_bar_sync(pair_bar, 64);
-        const float l_tot = l_run + xs[(1 - g) * ATT_TILE + r];
+        named_bar_sync(pair_bar, 32 * NT);
+        float l_tot = 0.f;
+#pragma unroll
+        for (int o = 0; o < NT; ++o) l_tot += xs[o * ATT_TILE + r];  // same order in every thread of the row
         const bool row_ok = qi < loc.doc_len;
         const float inv_l = l_tot > 0.f ? 1.f / l_tot : 0.f;
         __nv_bfloat16* orow = p.out + int64_t(row_base + r) * (int64_t(p.n_heads) * HD) + int64_t(head) * HD;
 #pragma unroll 1
-        for (int c = (g == 0 ? 0 : CH_SPLIT); c < (g == 0 ? CH_SPLIT : NCH16); ++c) {
+        for (int c = chunk_lo(g); c < chunk_lo(g + 1); ++c) {
             uint32_t o[16];
             tmem_ld16(t_lane + O_COL + c * 16, o);
             tmem_ld_wait();
@@ -670,7 +668,7 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1)
     }
 }
 
-template <int HD>
+template <int HD, int NT>
 int launch_fwd_split(const void* qkv, int64_t row_stride, const FwdParams& p, cudaStream_t st) {
     using CH = HeadChunks<HD>;
     CUtensorMap t64, tR;
@@ -690,9 +688,9 @@ int launch_fwd_split(const void* qkv, int64_t row_stride, const FwdParams& p, cu
     if (CH::NC64 == 0) t64 = tR;
     if (CH::REM == 0) tR = t64;
     constexpr int ST = fwd2_kv_stages<HD>();
-    constexpr int smem_bytes = 1024 + (1 + 2 * ST) * CH::TILE_BYTES + 4 * ATT_TILE * 4 + 256;
+    constexpr int smem_bytes = 1024 + (1 + 2 * ST) * CH::TILE_BYTES + 8 * ATT_TILE * 4 + 256;
     static_assert(smem_bytes <= 232448, "attention forward (split softmax) shared memory budget exceeded");
-    auto kern = attn_fwd_split_kernel<HD>;
+    auto kern = attn_fwd_split_kernel<HD, NT>;
     static bool attr_set = false;
     if (!attr_set) {
         DOLO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -701,7 +699,7 @@ int launch_fwd_split(const void* qkv, int64_t row_stride, const FwdParams& p, cu
     const int64_t max_tiles = (p.T + ATT_TILE - 1) / ATT_TILE + p.n_docs;
     DOLO_REQUIRE(max_tiles == p.n_tile_slots && max_tiles * p.n_heads < (1ll << 31), "attn_fwd: grid too large");
     dim3 grid((unsigned)(max_tiles * p.n_heads));
-    kern<<<grid, FWD2_THREADS, smem_bytes, st>>>(t64, tR, p);
+    kern<<<grid, fwd2_threads<NT>(), smem_bytes, st>>>(t64, tR, p);
     DOLO_LAUNCH_OK("attn_varlen_fwd_split");
     return DOLO_OK;
 }
@@ -792,10 +790,19 @@ extern "C" int dolomite_b200_attn_varlen_fwd_dropout(const void* qkv, int64_t ro
         case 32: return launch_fwd<32>(qkv, row_stride, p, max_seqlen, st);
         // head_dim 64 / 80: the single-buffer kernel fits two CTAs per SM, which overlap each other; measured faster than the
         // split kernel there (call 73: 0.323 vs 0.370 ms at hd 80) unless "attn_fwd_split" is set to 2
-        case 64: return split >= 2 ? launch_fwd_split<64>(qkv, row_stride, p, st) : launch_fwd<64>(qkv, row_stride, p, max_seqlen, st);
-        case 80: return split >= 2 ? launch_fwd_split<80>(qkv, row_stride, p, st) : launch_fwd<80>(qkv, row_stride, p, max_seqlen, st);
-        case 96: return split ? launch_fwd_split<96>(qkv, row_stride, p, st) : launch_fwd<96>(qkv, row_stride, p, max_seqlen, st);
-        case 128: return split ? launch_fwd_split<128>(qkv, row_stride, p, st) : launch_fwd<128>(qkv, row_stride, p, max_seqlen, st);
+        // (split: 0 never / 1 head_dim >= 96 / 2 also 64, 80 -- two threads per row; 3 = like 2 with FOUR threads per row)
+        case 64:
+            if (split >= 3) return launch_fwd_split<64, 4>(qkv, row_stride, p, st);
+            return split >= 2 ? launch_fwd_split<64, 2>(qkv, row_stride, p, st) : launch_fwd<64>(qkv, row_stride, p, max_seqlen, st);
+        case 80:
+            if (split >= 3) return launch_fwd_split<80, 4>(qkv, row_stride, p, st);
+            return split >= 2 ? launch_fwd_split<80, 2>(qkv, row_stride, p, st) : launch_fwd<80>(qkv, row_stride, p, max_seqlen, st);
+        case 96:
+            if (split >= 3) return launch_fwd_split<96, 4>(qkv, row_stride, p, st);
+            return split ? launch_fwd_split<96, 2>(qkv, row_stride, p, st) : launch_fwd<96>(qkv, row_stride, p, max_seqlen, st);
+        case 128:
+            if (split >= 3) return launch_fwd_split<128, 4>(qkv, row_stride, p, st);
+            return split ? launch_fwd_split<128, 2>(qkv, row_stride, p, st) : launch_fwd<128>(qkv, row_stride, p, max_seqlen, st);
         default: return dolo_set_error("attn_fwd: unsupported head_dim %d (supported: 16,32,64,80,96,128)", head_dim);
     }
 }

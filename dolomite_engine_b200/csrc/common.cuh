@@ -45,7 +45,7 @@ int dolo_option_gemm_sm_margin();
 // 128-byte row segments.  Measured on the four weight gradients of a C2 block (profiles/r02_probe_call70.jsonl): the TMA
 // path is 5 % (reduce-add) to 13 % (store) SLOWER -- 32 extra TMA operations per tile share the queue of the operand loads.
 int dolo_option_gemm_f32_tma_epilogue();
-int dolo_option_attn_fwd_split();  // 0 never / 1 (default) head_dim >= 96 / 2 also head_dim 64, 80: split-softmax forward
+int dolo_option_attn_fwd_split();  // 0 never / 1 (default) head_dim >= 96 / 2 also head_dim 64, 80: split-softmax forward (two threads per query row); 3 = every head_dim >= 64 with four threads per row
 int dolo_option_attn_bwd_variant();  // head_dim 64 / 80 backward: 0 = round-1 softmax warps, 1 = lean, 2 (default) = lean + uniform 16-column chunks at head_dim 80 (0.701 vs 0.752 ms, profiles/r02_probe_attn_bwd_uniform_chunks_call80.jsonl; identical to 1 at head_dim 64)
 int dolo_option_attn_bwd_ablate();
 // attention CTA order (attention_common.cuh: attn_cta_order): heads per chunk (default 8; heads fastest inside a chunk, the

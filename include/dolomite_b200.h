@@ -41,8 +41,9 @@ int dolomite_b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   "gemm_sm_margin"   SMs the persistent GEMM grids leave free for concurrent communication kernels (static schedule only)
  *   "gemm_dynamic"     1 | 0 (default 1: one cluster per output tile; running clusters take over pending ones through cluster launch
  *                      control, so the grid uses every SM that is or becomes free -- no margin needed next to NCCL kernels)
- *   "attn_fwd_split"   1 | 0 | 2 (split-softmax attention forward -- one CTA per SM, double-buffered scores in TMEM, two threads
- *                      per query row -- for head_dim >= 96 (1, default), never (0), or also for head_dim 64 / 80 (2))
+ *   "attn_fwd_split"   1 | 0 | 2 | 3 (split-softmax attention forward -- one CTA per SM, double-buffered scores in TMEM, several
+ *                      threads per query row -- for head_dim >= 96 (1, default), never (0), also for head_dim 64 / 80 (2);
+ *                      3 = like 2 with FOUR instead of two threads per query row)
  *   "attn_head_fastest" heads per chunk of the attention CTA order (default 8: inside a chunk heads fastest + longest tiles
  *                      first, so that the last wave is short tiles; 0 = tiles fastest, round 1's order)
  *   "gemm_l2_hints"    1 | 0 (long-contraction GEMMs load the streamed operand evict-first and the re-used one evict-last)

@@ -214,14 +214,16 @@ def test_attention_fwd_bwd_vs_oracle(lens, ng, g, hd):
     ref.backward(dout.float())
     out, lse = K().attn_varlen_fwd(qkv.cuda(), torch.from_numpy(cu).cuda(), max(lens), ng, g, hd, scale)
     assert rel_l2(out, ref) < 6e-3
-    if hd >= 64:  # both forward kernels (single-buffer / split softmax) for every head_dim that has both
-        try:
-            K().set_option("attn_fwd_split", 2 if hd < 96 else 0)
-            out2, lse2 = K().attn_varlen_fwd(qkv.cuda(), torch.from_numpy(cu).cuda(), max(lens), ng, g, hd, scale)
-        finally:
-            K().set_option("attn_fwd_split", 1)
-        assert rel_l2(out2, ref) < 6e-3
-        assert torch.allclose(lse2, lse, atol=2e-3, rtol=1e-4)
+    if hd >= 64:  # every forward kernel (single-buffer / split softmax with two or four threads per row) of the head_dim
+        default_split = K().get_option("attn_fwd_split")
+        for split in (0, 2, 3):
+            try:
+                K().set_option("attn_fwd_split", split)
+                out2, lse2 = K().attn_varlen_fwd(qkv.cuda(), torch.from_numpy(cu).cuda(), max(lens), ng, g, hd, scale)
+            finally:
+                K().set_option("attn_fwd_split", default_split)
+            assert rel_l2(out2, ref) < 6e-3, split
+            assert torch.allclose(lse2, lse, atol=2e-3, rtol=1e-4), split
     # head_dim <= 80 runs the pipelined backward, larger head dims the serial one: both are covered by the parameter list
     dqkv = K().attn_varlen_bwd(dout.cuda(), qkv.cuda(), out, lse, torch.from_numpy(cu).cuda(), max(lens), ng, g, hd, scale)
     assert rel_l2(dqkv, x.grad) < 1.2e-2

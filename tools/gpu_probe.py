@@ -949,6 +949,52 @@ def _attn_order_ab(S, B, ng, g, hd, rounds=3, orders=(0, 8, 1024)):
     return res
 
 
+def _attn_fwd_kernels_ab(S, B, ng, g, hd, rounds=3, splits=(0, 2, 3)):
+    """forward kernels of one head_dim, interleaved: single buffer (attn_fwd_split = 0; two CTAs per SM at head_dim <= 80),
+    split softmax with two (2) and with four (3) threads per query row"""
+    torch = _t()
+    from dolomite_engine_b200 import kernels as k
+
+    T, nh = S * B, ng * g
+    qkv = torch.randn(T, ng * (g + 2) * hd, device="cuda").bfloat16()
+    cu = torch.arange(0, T + 1, S, dtype=torch.int32, device="cuda")
+    scale = hd ** -0.5
+    flops_fwd = 4.0 * S * S * hd * nh * B / 2
+    res = {"shape": [S, B, ng, g, hd]}
+    default = k.get_option("attn_fwd_split")
+    outs, ts = {}, {sp: [] for sp in splits}
+    try:
+        for _ in range(rounds):
+            for sp in splits:
+                k.set_option("attn_fwd_split", sp)
+                out, lse = k.attn_varlen_fwd(qkv, cu, S, ng, g, hd, scale)
+                outs[sp] = (out.clone(), lse.clone())
+                ts[sp].append(_time(lambda: k.attn_varlen_fwd(qkv, cu, S, ng, g, hd, scale, out=out), iters=10))
+    finally:
+        k.set_option("attn_fwd_split", default)
+    for sp in splits:
+        res[f"split{sp}"] = {"fwd_ms": round(min(ts[sp]), 4), "fwd_tflops_causal": round(flops_fwd / min(ts[sp]) / 1e9),
+                             "rel_l2_vs_split0": _err(outs[sp][0], outs[splits[0]][0])["rel_l2"],
+                             "lse_max_abs_vs_split0": float((outs[sp][1] - outs[splits[0]][1]).abs().max())}
+    res["ok"] = bool(all(res[f"split{sp}"]["rel_l2_vs_split0"] < 5e-3 for sp in splits))
+    return res
+
+
+@case
+def attn_fwd_kernels_c2():
+    return _attn_fwd_kernels_ab(4096, 6, 32, 1, 80)
+
+
+@case
+def attn_fwd_kernels_c5():
+    return _attn_fwd_kernels_ab(8192, 1, 8, 4, 128)
+
+
+@case
+def attn_fwd_kernels_c4():
+    return _attn_fwd_kernels_ab(2048, 8, 16, 1, 128)
+
+
 @case
 def attn_order_c2():
     return _attn_order_ab(4096, 6, 32, 1, 80)
