@@ -138,6 +138,9 @@ def save_checkpoint(args, model, optimizer, lr_scheduler, train_dataloader, expe
         torch.save(lr_scheduler.state_dict(), os.path.join(save_path, "lr_scheduler.pt"))
     rng = {"random_rng_state": random.getstate(), "np_rng_state": np.random.get_state(), "torch_rng_state": torch.get_rng_state(),
            "cuda_rng_state": torch.cuda.get_rng_state() if torch.cuda.is_available() else None}
+    eng = _engine(model)
+    if getattr(eng, "has_dropout", False):  # counter-based dropout masks: (seed, passes so far) is the whole generator state
+        rng["dolomite_b200_dropout_state"] = (eng.dropout_seed, eng._dropout_passes)
     os.makedirs(os.path.join(save_path, "rng_state"), exist_ok=True)
     torch.save(rng, os.path.join(save_path, "rng_state", f"rng_state-{rank}.pt"))
     if train_dataloader is not None:
@@ -255,6 +258,9 @@ def load_checkpoint_for_training(args, model, optimizer, lr_scheduler, train_dat
             torch.set_rng_state(rng["torch_rng_state"])
             if rng.get("cuda_rng_state") is not None and torch.cuda.is_available():
                 torch.cuda.set_rng_state(rng["cuda_rng_state"])
+            if rng.get("dolomite_b200_dropout_state") is not None:
+                eng = _engine(model)
+                eng.dropout_seed, eng._dropout_passes = rng["dolomite_b200_dropout_state"]
     metadata = None
     if os.path.isfile(os.path.join(load_path, "metadata.json")):
         metadata = json.load(open(os.path.join(load_path, "metadata.json")))

@@ -95,6 +95,25 @@ def test_single_process_layout_and_names(tmp_path):
     assert torch.load(os.path.join(base, "dataloader", "dataloader-0.pt"), weights_only=False) == {"consumed_samples": 48}
 
 
+def test_dropout_generator_state_travels_with_the_rng_state(tmp_path):
+    """dropout masks are counter-based: (seed, passes so far) is the generator state; it is stored next to the torch / numpy /
+    python RNG states (rng_state-<rank>.pt; the reference stores its Philox state there) so that a resumed run continues the mask
+    sequence instead of repeating it"""
+    from dolomite_engine_b200 import checkpointing as C
+
+    path = str(tmp_path / "ckpt")
+    engine, model, opt, sched = _build(1, 0, seed=1)
+    engine.has_dropout, engine.dropout_seed, engine._dropout_passes = True, 4242, 17
+    C.save_checkpoint(_args(path), model, opt, sched, None, None, 3, metadata={})
+    engine2, model2, opt2, sched2 = _build(1, 0, seed=2)
+    engine2.has_dropout = True
+    C.load_checkpoint_for_training(_args(path, load=True), model2, opt2, sched2, None)
+    assert (engine2.dropout_seed, engine2._dropout_passes) == (4242, 17)
+    engine2.training = True
+    engine2._begin_dropout_pass()
+    assert engine2._dropout_now == 4242 + 17
+
+
 def _worker(rank, world, port, path, q, fsdp_algorithm=1):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
