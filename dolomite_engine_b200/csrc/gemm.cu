@@ -437,7 +437,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             t_next = t;  // the next tile id is taken BEFORE this tile's work: its latency hides behind the pipeline waits
             have_next = feed.next(t_next, num_tiles, lane == 0, true, 13);
             const TileInfo ti = tile_info(t, p);
-            if (!ti.valid) continue;
+            if (!ti.valid) {
+                // K-grouped launch (expert weight gradients) and this expert received NO rows: its product is zero.  A launch
+                // that OVERWRITES (beta = 0, no C) must still write the tile -- the caller did not clear the buffer -- so the
+                // epilogue warps store zeros themselves; no MMA ran and no accumulator stage is involved.
+                const Problem& pz = p.pr[ti.q];
+                if (p.grouped == 2 && p.d_is_f32 && pz.C == nullptr) {
+                    const int64_t zrow = int64_t(CTA2 ? ti.m_blk * 2 + cta_rank : ti.m_blk) * BM + et;
+                    if (zrow < pz.M) {
+                        float* zr = static_cast<float*>(pz.D) + int64_t(ti.grp) * p.d_group_stride + zrow * pz.ldd;
+                        const int c1 = min(pz.N, (ti.n_blk + 1) * BN);
+                        for (int c = ti.n_blk * BN; c < c1; c += 4)  // N % 8 == 0: whole float4 in range
+                            *reinterpret_cast<float4*>(zr + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                continue;
+            }
             const Problem& pr = p.pr[ti.q];
             const CUtensorMap* tmap_d = &maps.d[ti.q];
             const int m_blk = CTA2 ? ti.m_blk * 2 + cta_rank : ti.m_blk, n_blk = ti.n_blk;

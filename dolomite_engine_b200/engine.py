@@ -351,16 +351,13 @@ class DolomiteEngine:
 
     def prepare_unit_grads(self, i: int) -> None:
         """pooled gradients: unit i's backward starts on a buffer that held another block's gradients.  Large GEMM weights
-        are overwritten by their first weight-gradient GEMM (beta = 0); the small tensors accumulated by reduction kernels
-        (norm weights, biases) are cleared here; MoE units are cleared whole (an expert may receive no token)."""
+        are overwritten by their first weight-gradient GEMM (beta = 0, `_lazy_zero`); the tensors accumulated by reduction
+        kernels or atomics (norm weights, biases, the MoE router) are cleared here."""
         u = self.units[i]
         if not u.pooled:
             return
-        if self.is_moe:
-            u.grad_full.zero_()
-            return
         for s in u.specs:
-            if s.numel >= self._LAZY_ZERO_MIN_NUMEL and s.name.endswith(".weight"):
+            if self._lazy_zero(s):
                 self._fresh_grads.add(s.name)
             else:
                 u.gviews[s.name].zero_()
@@ -378,29 +375,39 @@ class DolomiteEngine:
     # parameters at least this large only ever receive their gradient from a weight-gradient GEMM first
     _LAZY_ZERO_MIN_NUMEL = 1 << 16
 
+    def _lazy_zero(self, s: ParamSpec) -> bool:
+        """True when the first gradient of `s` in a window comes from a weight-gradient GEMM that can OVERWRITE its buffer
+        (beta = 0): the dense linears, and the 3-D expert weights (the K-grouped GEMM writes zeros for an expert without
+        tokens).  Not the MoE router (split-K partial sums are atomically ADDED into a cleared buffer), not embedding tables
+        that only receive scattered atomics (untied wte, wpe)."""
+        if s.numel < self._LAZY_ZERO_MIN_NUMEL or not s.name.endswith(".weight") or s.name.endswith("mlp.gate.weight"):
+            return False
+        if s.name == "transformer.wpe.weight" or (s.name == "transformer.wte.weight" and not self.cfg.tie_word_embeddings):
+            return False
+        return True
+
+    def take_fresh(self, wname: str) -> bool:
+        """True exactly once per accumulation window and weight: its first weight-gradient GEMM must overwrite"""
+        fresh = wname in self._fresh_grads
+        self._fresh_grads.discard(wname)
+        return fresh
+
     def zero_grad(self) -> None:
-        """Clears the fp32 gradient buffers.  Dense models do it lazily for the GEMM weights: the first weight-gradient GEMM
-        of the next backward OVERWRITES its buffer (beta = 0) instead of read-modify-writing a freshly zeroed one, which
-        saves one write and one read of every weight gradient per step (8 B / parameter); only the small tensors that are
-        accumulated by reduction kernels (norm weights, biases) are cleared here."""
-        lazy = not self.is_moe
+        """Clears the fp32 gradient buffers, lazily for the GEMM weights: the first weight-gradient GEMM of the next backward
+        OVERWRITES its buffer (beta = 0) instead of read-modify-writing a freshly zeroed one, which saves one write and one
+        read of every weight gradient per step (8 B / parameter); only the tensors that are accumulated by reduction kernels
+        or atomics (norm weights, biases, the MoE router, scatter-only embedding tables) are cleared here."""
         self._fresh_grads = set()
         if self.comm is not None:
             self.comm.window_reset()
         for u in self.units:
             if u.pooled:  # cleared per unit at the start of its backward (prepare_unit_grads)
                 continue
-            if lazy:
-                for s in u.specs:
-                    # embedding tables that only ever receive scattered atomics must start from zero
-                    untied_wte = (s.name == "transformer.wte.weight" and not self.cfg.tie_word_embeddings) or \
-                        s.name == "transformer.wpe.weight"
-                    if s.numel >= self._LAZY_ZERO_MIN_NUMEL and s.name.endswith(".weight") and not untied_wte:
-                        self._fresh_grads.add(s.name)
-                    else:
-                        u.gviews[s.name].zero_()
-            else:
-                u.grad_full.zero_()
+            for s in u.specs:
+                if self._lazy_zero(s):
+                    self._fresh_grads.add(s.name)
+                else:
+                    u.gviews[s.name].zero_()
             # sharded: the shard gradient is (over)written by the reduce-scatter, no need to clear it here
             if u.master.grad is not u.grad_full and self.comm is None:
                 u.master.grad.zero_()
@@ -658,8 +665,7 @@ class DolomiteEngine:
         w = unit.views[wname]
         gw = unit.gviews[wname]
         dx = K.gemm(dy, w, b_mn=True, alpha=alpha, out=dx_out) if need_dx else None
-        fresh = wname in self._fresh_grads  # first gradient since zero_grad(): overwrite, the buffer was not cleared
-        self._fresh_grads.discard(wname)
+        fresh = self.take_fresh(wname)  # first gradient since zero_grad(): overwrite, the buffer was not cleared
         if self._deferred_wgrads is not None:
             # weight gradients of a block are launched together at the end of the block's backward (one persistent grid
             # over all their tiles instead of four launches with a partly filled last wave each)

@@ -55,11 +55,15 @@ def backward(engine, unit, p: str, x, dh, m_res: float, saved, layer: int = 0):
     else:
         dyg, dw = K.moe_combine_bwd(dh, yg, plan, alpha=m_res)
     w_proj, w_fc = unit.views[p + "mlp.c_proj.weight"], unit.views[p + "mlp.c_fc.weight"]
-    K.gemm_grouped_k(dyg, act, plan, unit.gviews[p + "mlp.c_proj.weight"])          # dWproj[e] += dY_e^T act_e
+    # the first expert weight gradient of an accumulation window OVERWRITES its buffer (engine.zero_grad is lazy); an expert
+    # without tokens is written as zeros by the K-grouped GEMM itself
+    beta_proj = 0.0 if engine.take_fresh(p + "mlp.c_proj.weight") else 1.0
+    beta_fc = 0.0 if engine.take_fresh(p + "mlp.c_fc.weight") else 1.0
+    K.gemm_grouped_k(dyg, act, plan, unit.gviews[p + "mlp.c_proj.weight"], beta=beta_proj)  # dWproj[e] (+)= dY_e^T act_e
     d_act = K.gemm_grouped_m(dyg, w_proj, plan, b_mn=True)                            # [rows, F]
     d_fc = K.swiglu_bwd(d_act, fc)
     xg = K.moe_gather(x, plan)  # grouped (zero-padded) copy of the block input: the contraction operand of the c_fc wgrad
-    K.gemm_grouped_k(d_fc, xg, plan, unit.gviews[p + "mlp.c_fc.weight"])             # dWfc[e] += dfc_e^T x_e
+    K.gemm_grouped_k(d_fc, xg, plan, unit.gviews[p + "mlp.c_fc.weight"], beta=beta_fc)  # dWfc[e] (+)= dfc_e^T x_e
     del xg
     dxg = K.gemm_grouped_m(d_fc, w_fc, plan, b_mn=True)                               # [rows, H]
     dx = K.moe_token_sum(dxg, plan)

@@ -97,6 +97,33 @@ def test_grouped_gemms_vs_per_expert_matmul():
         assert rel_l2(once[e], y_c[rows].t() @ xg_c[rows]) < 1e-4
 
 
+@pytest.mark.parametrize("F,H", [(256, 128), (512, 384)])  # one CTA-pair super tile / several tiles with a ragged last column block
+def test_expert_wgrad_overwrite_writes_zeros_for_experts_without_tokens(F, H):
+    """engine.zero_grad() does not clear the expert weight gradients: the first K-grouped GEMM of a window runs with beta = 0
+    and must define EVERY expert's slice -- also of experts that received no token (empty contraction range)"""
+    g = torch.Generator().manual_seed(3)
+    T, E, k = 600, 8, 2
+    logits = torch.randn(T, E, generator=g)
+    logits[:, 3] = -1e4  # never among the top-2
+    logits[:, 6] = -2e4
+    plan = K().moe_route(bf(logits).cuda(), k)
+    cnt = plan.counts.cpu().numpy()
+    assert cnt[3] == 0 and cnt[6] == 0 and cnt.sum() == T * k
+    x = bf(torch.randn(T, H, generator=g))
+    xg = K().moe_gather(x.cuda(), plan)
+    y = bf(torch.randn(plan.max_rows, F, generator=g)).cuda()
+    acc = torch.zeros(E, F, H, device="cuda")
+    K().gemm_grouped_k(y, xg, plan, acc)  # accumulate form into a cleared buffer = the reference result
+    dw = torch.full((E, F, H), float("nan"), device="cuda")
+    K().gemm_grouped_k(y, xg, plan, dw, beta=0.0)
+    torch.cuda.synchronize()
+    assert torch.equal(dw, acc)  # same tiles, same arithmetic; no stale value (NaN) survives
+    assert torch.all(dw[3] == 0) and torch.all(dw[6] == 0)
+    # accumulate form leaves the slices of the empty experts alone
+    K().gemm_grouped_k(y, xg, plan, dw)
+    assert torch.all(dw[3] == 0) and torch.allclose(dw, 2 * acc, rtol=1e-5, atol=1e-4)
+
+
 def _moe_cfgs():
     from dolomite_engine_b200.hf_models import MoEDolomiteConfig
 
@@ -204,3 +231,37 @@ def test_moe_model_logits_loss_and_grads_match_oracle(ragged):
         if e > 3e-2:
             bad.append((pname, round(e, 4)))
     assert not bad, bad
+
+
+def test_lazy_gradient_clearing_leaves_no_stale_expert_gradients():
+    """zero_grad() does not touch the big weight-gradient buffers (the first wgrad GEMM of the window overwrites them): the
+    gradients of batch B must not depend on what an earlier window (batch A) left in the buffers"""
+    from dolomite_engine_b200.hf_models import MoEDolomiteForCausalLM
+
+    cfg, ocfg = _moe_cfgs()
+    model = MoEDolomiteForCausalLM(cfg, seed=None)
+    model.load_state_dict(O.init_params(ocfg, seed=42))
+    model.assume_unit_loss_grad = True
+    eng = model.engine
+    rng = np.random.default_rng(11)
+
+    def run(tokens):
+        inp, labels = O.split_tokens(tokens)
+        b = O.prepare_model_inputs(inp.copy(), 7, False, False)
+        eng.zero_grad()
+        loss = model.forward_pretraining_loss(torch.from_numpy(b["input_ids"]).cuda(), torch.from_numpy(b["position_ids"]).cuda(),
+                                              torch.from_numpy(b["cu_seqlens"]).cuda(), b["max_seqlen"],
+                                              torch.from_numpy(np.ascontiguousarray(labels).reshape(-1)).cuda())
+        loss.backward()
+        torch.cuda.synchronize()
+        return {n: u.gviews[n].clone() for n, u, _ in eng.named_views()}
+
+    tok_a = rng.integers(0, ocfg.vocab_size, size=(2, 97), dtype=np.int64)
+    tok_b = rng.integers(0, ocfg.vocab_size, size=(2, 97), dtype=np.int64)
+    g1 = run(tok_b)  # buffers still hold the zeros of their allocation
+    run(tok_a)
+    g2 = run(tok_b)  # buffers hold batch A's gradients
+    # not bit-equal: dQ tiles, router split-K partials and embedding rows are reduced with fp32 atomics (order-dependent
+    # rounding); a stale buffer would show up as an O(1) relative difference
+    for n in g1:
+        assert rel_l2(g1[n], g2[n]) < 1e-4, n
