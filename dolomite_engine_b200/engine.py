@@ -275,6 +275,8 @@ class DolomiteEngine:
         self._wgrad_stream = None  # created on first use
         self._kv_sink = None  # callable(layer, packed qkv) while a forward fills a KV cache (prefill)
         self._fresh_grads: set[str] = set()  # weights whose gradient buffer will be overwritten by the next wgrad GEMM
+        # DOLO_EAGER_GRAD_ZERO=1: zero_grad() clears every gradient buffer (A/B switch for the lazy clearing, `_lazy_zero`)
+        self.lazy_grad_zero = os.environ.get("DOLO_EAGER_GRAD_ZERO", "0") != "1"
         if cfg.attention_multiplier is not None:
             self.softmax_scale = float(cfg.attention_multiplier)
         elif cfg.scale_attn_weights:
@@ -380,6 +382,8 @@ class DolomiteEngine:
         (beta = 0): the dense linears, and the 3-D expert weights (the K-grouped GEMM writes zeros for an expert without
         tokens).  Not the MoE router (split-K partial sums are atomically ADDED into a cleared buffer), not embedding tables
         that only receive scattered atomics (untied wte, wpe)."""
+        if not self.lazy_grad_zero:
+            return False
         if s.numel < self._LAZY_ZERO_MIN_NUMEL or not s.name.endswith(".weight") or s.name.endswith("mlp.gate.weight"):
             return False
         if s.name == "transformer.wpe.weight" or (s.name == "transformer.wte.weight" and not self.cfg.tie_word_embeddings):

@@ -1,22 +1,28 @@
 #!/bin/bash
 # The commands of the CURRENT gpurun call (rewritten per call; git history keeps the earlier ones).
-# Call 92 (1 GPU): final state -- the whole GPU suite, smoke(), and the driver's two bench arms with default flags.
+# Call 93 (1 GPU): HEAD with the lazily cleared MoE expert gradients -- whole GPU suite, smoke(), C4 with and without the lazy
+# clearing on the same box, C2 line.
 set -u
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --maxfail=30 > gpurun_out/c92_pytest.log 2>&1
-echo "pytest rc=$?"; tail -n 4 gpurun_out/c92_pytest.log | cut -c1-300
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/c92_smoke.log 2>&1
-echo "smoke rc=$?"; tail -n 2 gpurun_out/c92_smoke.log
-timeout 900 python bench.py --impl reference --steps 8 --warmup 3 > gpurun_out/c92_bench_reference_arm.json 2> gpurun_out/c92_bench_reference_arm.err
-echo "reference arm rc=$?"
-timeout 900 python bench.py > gpurun_out/c92_bench_c2_default_flags.json 2> gpurun_out/c92_bench_c2.err
-echo "bench c2 (no flags) rc=$?"
+timeout 900 python -m pytest tests -m gpu -q --maxfail=30 > gpurun_out/c93_pytest.log 2>&1
+echo "pytest rc=$?"; tail -n 4 gpurun_out/c93_pytest.log | cut -c1-300
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/c93_smoke.log 2>&1
+echo "smoke rc=$?"; tail -n 2 gpurun_out/c93_smoke.log
+for mode in lazy eager lazy2 eager2; do
+  case $mode in eager*) export DOLO_EAGER_GRAD_ZERO=1;; *) export DOLO_EAGER_GRAD_ZERO=0;; esac
+  extra=""; [ "$mode" = lazy ] && extra="--profile-step gpurun_out/c93_step_profile_c4.json"
+  timeout 240 python bench.py --config c4 --no-cpu-baseline --no-gpu-reference $extra > gpurun_out/c93_bench_c4_$mode.json 2> gpurun_out/c93_bench_c4_$mode.err
+  echo "bench c4 $mode rc=$?"
+done
+unset DOLO_EAGER_GRAD_ZERO
+timeout 300 python bench.py --no-cpu-baseline --no-gpu-reference > gpurun_out/c93_bench_c2.json 2> gpurun_out/c93_bench_c2.err
+echo "bench c2 rc=$?"
 python - <<'PY'
 import json
-for f in ("c92_bench_reference_arm", "c92_bench_c2_default_flags"):
+for f in ("c93_bench_c4_lazy", "c93_bench_c4_eager", "c93_bench_c4_lazy2", "c93_bench_c4_eager2", "c93_bench_c2"):
     try:
         d = json.loads([l for l in open(f"gpurun_out/{f}.json") if l.startswith("{")][-1])
-        print(f, round(d["value"], 1), d.get("ms_per_step"), d.get("clocks"), d.get("vs_gpu_reference"), (d.get("e2e") or {}).get("value"), d.get("gpu_launches"), (d.get("roofline") or {}).get("frac"))
+        print(f, round(d["value"], 1), round(d.get("ms_per_step"), 2), d.get("clocks"), (d.get("e2e") or {}).get("value"), d.get("gpu_launches"), (d.get("roofline") or {}).get("frac"))
     except Exception as e:
         print(f, "failed", e); print(open(f"gpurun_out/{f}.err").read()[-1200:])
 PY
