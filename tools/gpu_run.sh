@@ -1,28 +1,21 @@
 #!/bin/bash
 # The commands of the CURRENT gpurun call (rewritten per call; git history keeps the earlier ones).
-# Call 93 (1 GPU): HEAD with the lazily cleared MoE expert gradients -- whole GPU suite, smoke(), C4 with and without the lazy
-# clearing on the same box, C2 line.
+# Call 94 (1 GPU, the round's last GPU minutes): compute-sanitizer memcheck over the kernel-level GPU tests of HEAD (round-2 kernels:
+# cluster-launch-control GEMM incl. the zero-writing K-grouped epilogue, split-softmax attention, dropout, decode, MoE), then the
+# C5 line at HEAD if time is left.
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --maxfail=30 > gpurun_out/c93_pytest.log 2>&1
-echo "pytest rc=$?"; tail -n 4 gpurun_out/c93_pytest.log | cut -c1-300
-timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/c93_smoke.log 2>&1
-echo "smoke rc=$?"; tail -n 2 gpurun_out/c93_smoke.log
-for mode in eager lazy; do  # the first run gets the cooler chip: a win of the second is conservative
-  case $mode in eager*) export DOLO_EAGER_GRAD_ZERO=1;; *) export DOLO_EAGER_GRAD_ZERO=0;; esac
-  extra=""; [ "$mode" = lazy ] && extra="--profile-step gpurun_out/c93_step_profile_c4.json"
-  timeout 240 python bench.py --config c4 --no-cpu-baseline --no-gpu-reference $extra > gpurun_out/c93_bench_c4_$mode.json 2> gpurun_out/c93_bench_c4_$mode.err
-  echo "bench c4 $mode rc=$?"
-done
-unset DOLO_EAGER_GRAD_ZERO
-timeout 300 python bench.py --no-cpu-baseline --no-gpu-reference > gpurun_out/c93_bench_c2.json 2> gpurun_out/c93_bench_c2.err
-echo "bench c2 rc=$?"
+timeout 170 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_moe.py \
+    tests/test_gpu_dropout.py tests/test_zzz_generation.py -q -m gpu -k "not full_size" -p no:cacheprovider \
+    > gpurun_out/c94_memcheck.log 2>&1
+echo "memcheck rc=$?"; grep -E "passed|failed|ERROR SUMMARY|Invalid|error" gpurun_out/c94_memcheck.log | tail -n 8 | cut -c1-300
+timeout 150 python bench.py --config c5 --no-cpu-baseline --no-gpu-reference > gpurun_out/c94_bench_c5.json 2> gpurun_out/c94_bench_c5.err
+echo "bench c5 rc=$?"
 python - <<'PY'
 import json
-for f in ("c93_bench_c4_eager", "c93_bench_c4_lazy", "c93_bench_c2"):
-    try:
-        d = json.loads([l for l in open(f"gpurun_out/{f}.json") if l.startswith("{")][-1])
-        print(f, round(d["value"], 1), round(d.get("ms_per_step"), 2), d.get("clocks"), (d.get("e2e") or {}).get("value"), d.get("gpu_launches"), (d.get("roofline") or {}).get("frac"))
-    except Exception as e:
-        print(f, "failed", e); print(open(f"gpurun_out/{f}.err").read()[-1200:])
+try:
+    d = json.loads([l for l in open("gpurun_out/c94_bench_c5.json") if l.startswith("{")][-1])
+    print("c5", round(d["value"], 1), round(d.get("ms_per_step"), 2), d.get("clocks"), (d.get("e2e") or {}).get("value"), d.get("gpu_launches"))
+except Exception as e:
+    print("c5 failed", e); print(open("gpurun_out/c94_bench_c5.err").read()[-800:])
 PY
