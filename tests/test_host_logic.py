@@ -455,3 +455,45 @@ def test_stage3_slot_table_never_hands_a_live_buffer_away():
                 resident_at_end = min(n_slots, n_layer)
                 assert len(gathers) - fwd == n_layer - resident_at_end
             assert t.is_fresh(0)
+
+
+def test_lazy_gradient_clearing_bookkeeping(monkeypatch):
+    """engine.zero_grad() leaves the buffers of weights whose FIRST gradient of a window comes from an overwriting weight-gradient GEMM
+    untouched (`_lazy_zero`): dense linears, the tied head / embedding, 3-D expert weights.  Everything that is accumulated by
+    reduction kernels or atomics is cleared: norm weights, biases, the MoE router, scatter-only embedding tables."""
+    from dolomite_engine_b200.engine import DolomiteEngine
+
+    common = dict(n_embd=256, n_head=4, n_layer=2, vocab_size=512, n_positions=64, attention_head_type="mha",
+                  normalization_function="rmsnorm", activation_function="swiglu", resid_pdrop=0, embd_pdrop=0, attn_pdrop=0)
+    moe = DolomiteEngine(MoEDolomiteConfig(num_experts=64, num_experts_per_tok=2, n_inner=64, add_bias=False,
+                                           position_embedding_type="rope", **{**common, "n_embd": 1024, "n_head": 8}), "cpu", seed=None)
+    for u in moe.units:
+        u.grad_full.fill_(7.0)
+    moe.zero_grad()
+    fresh = set(moe._fresh_grads)
+    assert "transformer.h.0.mlp.c_fc.weight" in fresh and "transformer.h.1.mlp.c_proj.weight" in fresh
+    assert "transformer.h.0.attn.c_attn.weight" in fresh and "transformer.wte.weight" in fresh  # tied: the head's wgrad writes first
+    gate = "transformer.h.0.mlp.gate.weight"  # 64 x 1024 elements = as large as a lazily cleared weight, but split-K ADDS into it
+    assert moe.units[1].gviews[gate].numel() >= moe._LAZY_ZERO_MIN_NUMEL and gate not in fresh
+    for name, unit, _ in moe.named_views():
+        v = unit.gviews[name]
+        assert bool((v == 7.0).all()) if name in fresh else bool((v == 0).all()), name
+    assert moe.take_fresh("transformer.h.0.mlp.c_fc.weight") and not moe.take_fresh("transformer.h.0.mlp.c_fc.weight")
+
+    dense = DolomiteEngine(GPTDolomiteConfig(n_inner=512, add_bias=True, position_embedding_type="learned_absolute",
+                                             tie_word_embeddings=False, **{**common, "n_positions": 1024}), "cpu", seed=None)
+    for u in dense.units:
+        u.grad_full.fill_(7.0)
+    dense.zero_grad()
+    fresh = set(dense._fresh_grads)
+    assert "lm_head.weight" in fresh and "transformer.h.1.mlp.c_fc.weight" in fresh
+    # embedding tables that only ever receive scattered atomics start from zero; so do biases and norm weights
+    for name in ("transformer.wte.weight", "transformer.wpe.weight", "transformer.h.0.mlp.c_fc.bias", "transformer.ln_f.weight"):
+        assert name not in fresh and bool((dict((n, u.gviews[n]) for n, u, _ in dense.named_views())[name] == 0).all()), name
+
+    monkeypatch.setenv("DOLO_EAGER_GRAD_ZERO", "1")  # A/B switch: every buffer is cleared, nothing is overwritten
+    eager = DolomiteEngine(MoEDolomiteConfig(num_experts=8, num_experts_per_tok=2, n_inner=128, add_bias=False,
+                                             position_embedding_type="rope", **common), "cpu", seed=None)
+    eager.units[1].grad_full.fill_(7.0)
+    eager.zero_grad()
+    assert not eager._fresh_grads and bool((eager.units[1].grad_full[: eager.units[1].numel] == 0).all())
