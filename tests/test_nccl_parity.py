@@ -24,6 +24,9 @@ CASES = {
     "stage3_reshard_bf16": (2, dict(COMM_DTYPE="bf16", RESHARD="1")),
     "stage3_reshard_fp32_accum2_ckpt": (2, dict(COMM_DTYPE="fp32", RESHARD="1", ACCUM="2", CKPT="2")),
     "hsdp_2x2_bf16": (4, dict(COMM_DTYPE="bf16", RESHARD="1", SHARD="2")),
+    # MoE blocks: expert weight gradients are written by overwriting K-grouped GEMMs into the shared (stage 3) gradient buffers
+    "moe_stage3_reshard_fp32_accum2": (2, dict(COMM_DTYPE="fp32", RESHARD="1", ACCUM="2", MOE="1")),
+    "moe_resident_bf16_accum2": (2, dict(COMM_DTYPE="bf16", RESHARD="0", ACCUM="2", MOE="1")),
 }
 
 

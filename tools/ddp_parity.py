@@ -5,7 +5,7 @@
 env: COMM_DTYPE=fp32|bf16 (wire dtype of the reduce-scatter), ACCUM=k (micro-steps per optimizer step, the first k-1
 under no_sync()), RESHARD=1 (what `stage: 3` means: block units share two parameter / gradient buffers, parameters are
 re-gathered in backward, gradients reduce-scattered per micro-step), CKPT=k (block activation checkpointing),
-SHARD=S (HSDP: S consecutive ranks per shard group).
+SHARD=S (HSDP: S consecutive ranks per shard group), MOE=1 (MoEDolomite blocks instead of dense ones).
 
 Every rank r feeds its own micro-batches to the sharded model (world_size = N); rank 0 additionally runs an unsharded
 copy of the same model over ALL micro-batches of all ranks.  Checks per step: (1) mean loss over ranks == mean loss
@@ -27,6 +27,8 @@ from dolomite_engine_b200.optimization import get_optimizer
 CFG = dict(model_type="gpt_dolomite", vocab_size=1024, n_positions=512, n_embd=320, n_layer=3, n_head=4, n_inner=640,
            attention_head_type="mha", position_embedding_type="rope", activation_function="swiglu",
            normalization_function="rmsnorm", add_bias=True, resid_pdrop=0, embd_pdrop=0, attn_pdrop=0, eos_token_id=7)
+# MOE=1: MoEDolomite blocks (8 experts, top-2, no biases): the K-grouped expert weight gradients overwrite their (pooled) buffers
+MOE_CFG = dict(CFG, model_type="moe_dolomite", num_experts=8, num_experts_per_tok=2, add_bias=False)
 OPT = {"lr": 1e-3, "weight_decay": 0.1, "betas": [0.9, 0.95], "eps": 1e-10}
 
 
@@ -43,6 +45,7 @@ def main():
     # SHARD=S: HSDP with S consecutive ranks per shard group, world / S replicas (zero_topology)
     shard = int(os.environ.get("SHARD", "0")) or None
     group, rep_group, s_world, s_rank = build_data_parallel_groups(shard, world // shard if shard else None)
+    CFG = MOE_CFG if os.environ.get("MOE", "0") == "1" else globals()["CFG"]
     w = ModelWrapperForPretraining(pretrained_config=dict(CFG), micro_batch_size=mbs, sequence_length=seq, device=dev,
                                    world_size=s_world, rank=s_rank)
     if os.environ.get("CKPT"):
@@ -114,7 +117,7 @@ def main():
     dist.destroy_process_group()
     if rank == 0:
         print("DDP_PARITY", "OK" if ok else "FAILED", f"(world {world}, wire {os.environ.get('COMM_DTYPE', 'fp32')}, accum {accum}, "
-              f"reshard {int(reshard)})", flush=True)
+              f"reshard {int(reshard)}, moe {os.environ.get('MOE', '0')})", flush=True)
     sys.exit(0 if flag.item() == 1.0 else 1)
 
 
