@@ -45,7 +45,8 @@ def main():
     # SHARD=S: HSDP with S consecutive ranks per shard group, world / S replicas (zero_topology)
     shard = int(os.environ.get("SHARD", "0")) or None
     group, rep_group, s_world, s_rank = build_data_parallel_groups(shard, world // shard if shard else None)
-    CFG = MOE_CFG if os.environ.get("MOE", "0") == "1" else globals()["CFG"]
+    moe = os.environ.get("MOE", "0") == "1"
+    CFG = MOE_CFG if moe else globals()["CFG"]
     w = ModelWrapperForPretraining(pretrained_config=dict(CFG), micro_batch_size=mbs, sequence_length=seq, device=dev,
                                    world_size=s_world, rank=s_rank)
     if os.environ.get("CKPT"):
@@ -99,6 +100,11 @@ def main():
                     rg = (ru.master.grad / world)[lo:hi]
                     worst = max(worst, ((g - rg).norm() / (rg.norm() + 1e-20)).item())
             gtol = (2e-2 if comm_dtype == torch.bfloat16 else 1e-5) if step == 0 else 5e-2
+            if moe and step > 0:
+                # the two trajectories drift apart (wire rounding, sign-like first Adam steps) and a router logit near a tie then
+                # selects another expert in one of them: a flip rate f moves the gradients by ~sqrt(2 f) (measured
+                # 1e-2 .. 7e-2 over steps 1-3, call 95).  Step 0 -- identical parameters -- keeps the strict bound.
+                gtol = 1.5e-1
             ptol = 1e-6 if step == 0 else 2e-2
             good = dl < 1e-3 and worst < gtol and pworst < ptol
             print(f"step {step}: loss {lsum.item():.6f} ref {rl:.6f} rel {dl:.2e}; shard-grad rel-L2 {worst:.2e}; "
