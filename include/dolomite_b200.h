@@ -241,7 +241,8 @@ int dolomite_b200_gemm_bf16_wgrad_multi(int n_problems, const void* const* dY, c
  *   grouped_m:  D[rows, N] = alpha * A[rows, K] . W[g]^T      W stored [G, N, K] (b_mn_major = 0: expert forward)
  *                                                         or W stored [G, K, N] (b_mn_major = 1: expert dgrad)
  *   grouped_k:  D[g][M, N] = alpha * A_g^T B_g + beta * D[g]  (expert wgrad, fp32): A [K_max, M], B [K_max, N] row-major,
- *               contraction over the rows [group_k_offsets[g], group_k_offsets[g+1]) of expert g.
+ *               contraction over the rows [group_k_offsets[g], group_k_offsets[g+1]) of expert g.  beta = 0 OVERWRITES: D need not
+ *               be initialised, and the slice of an expert with an empty row range is written as zeros; beta != 0 leaves it alone.
  * ------------------------------------------------------------------------------------------------ */
 int dolomite_b200_gemm_bf16_grouped_m(const void* A, int64_t lda, const void* B, int64_t ldb, int b_mn_major, void* D,
                                       int64_t ldd, float alpha, int64_t M_max, int64_t N, int64_t K,
