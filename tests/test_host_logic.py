@@ -497,3 +497,33 @@ def test_lazy_gradient_clearing_bookkeeping(monkeypatch):
     eager.units[1].grad_full.fill_(7.0)
     eager.zero_grad()
     assert not eager._fresh_grads and bool((eager.units[1].grad_full[: eager.units[1].numel] == 0).all())
+
+
+def test_lm_head_chunking_covers_the_token_rows_within_the_budget():
+    """engine._head_chunk_rows: the LM head + cross entropy run chunk by chunk so that [T, V] logits never exist.
+    Properties: chunks of `rows` rows cover T with no remainder beyond the last chunk, every chunk but the last has a multiple of 8
+    rows (it is the contraction length of the head's weight-gradient GEMM), a chunk's bf16 logits stay within the budget
+    (except the 8-row minimum), and the split is as even as the 8-row granularity allows."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from dolomite_engine_b200.engine import DolomiteEngine
+
+    @settings(max_examples=300, deadline=None)
+    @given(T=st.integers(1, 200_000), V=st.sampled_from([8, 264, 2048, 49152, 50304, 128256, 262144]),
+           budget=st.sampled_from([1 << 12, 1 << 20, 1 << 28, 1 << 30, 1 << 33]))
+    def check(T, V, budget):
+        rows = DolomiteEngine._head_chunk_rows(T, V, budget)
+        assert 1 <= rows <= T
+        n_chunks = -(-T // rows)
+        assert rows == T or rows % 8 == 0
+        assert rows * V * 2 <= budget or rows <= 8 or rows == T and T < 8  # 8 rows is the floor
+        cap = max(8, budget // (2 * V) // 8 * 8)
+        assert n_chunks >= -(-T // cap)  # never fewer chunks than the budget demands ...
+        assert n_chunks == -(-T // cap) or rows % 8 == 0 and n_chunks - -(-T // cap) <= 1  # ... and at most one more (rounding rows up to 8)
+        assert (n_chunks - 1) * rows < T  # the last chunk is not empty
+
+    check()
+    # the workloads of bench.py: C2 mbs 6 x 4096 tokens -> 3 chunks of 8192 rows (0.8 GB each); C5 8192 tokens -> 2 x 4096
+    assert DolomiteEngine._head_chunk_rows(24576, 49152) == 8192
+    assert DolomiteEngine._head_chunk_rows(8192, 128256) == 4096
