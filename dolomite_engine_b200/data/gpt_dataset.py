@@ -10,16 +10,24 @@ run fed by this module sees exactly the token stream the reference would have se
 * `PackedBatchLoader`     assembles micro-batches with one native gather straight into PINNED host memory from the memory
                     mapped .bin (no per-sample numpy concatenation, no worker processes), one batch ahead of the trainer
 
-FIM augmentation (fim_rate > 0) is not implemented (raises).
+* index cache     the three indices of a GPTDataset are stored / found under the reference's file names
+                    (`<md5 of the unique description>-GPTDataset-{document,sample,shuffle}_index.npy`, gpt_dataset.py:265-330), so
+                    caches written by either implementation are picked up by the other and every rank memory-maps ONE copy
+
+Fill-in-the-middle (`fim_rate` > 0) rewrites rows on the host (data/fim.py).
 """
 
 from __future__ import annotations
 
 import ctypes
+import hashlib
+import json
 import math
 import os
 import re
 import threading
+import warnings
+from collections import OrderedDict
 from queue import Queue
 
 import numpy as np
@@ -158,7 +166,8 @@ class GPTDataset:
     """Samples of S+1 tokens cut from the shuffled, epoch-repeated document stream (gpt_dataset.py:30-400)"""
 
     def __init__(self, indexed_dataset: MMapIndexedDataset, indexed_indices: np.ndarray, num_samples: int,
-                 sequence_length: int, random_seed: int = 1234, fim=None):
+                 sequence_length: int, random_seed: int = 1234, fim=None, *, index_split: str = "train",
+                 split: str | None = None, name: str | None = None, path_to_cache: str | None = None, cache: str = "off"):
         # fim: data.fim.FIMSpec or None; its random stream is seeded like the reference's (gpt_dataset.py:55)
         self.fim = fim if (fim is not None and fim.rate != 0) else None
         self.np_rng = np.random.RandomState(seed=random_seed)
@@ -167,7 +176,70 @@ class GPTDataset:
         self.num_samples = int(num_samples)
         self.sequence_length = int(sequence_length)
         self.random_seed = random_seed
-        self.document_index, self.sample_index, self.shuffle_index = self._build_indices()
+        # what identifies the indices on disk: megatron_dataset.py:52-61 (`_key_config_attributes` = name, split, random_seed,
+        # sequence_length of the GPTDatasetConfig) -- same keys, same order, same JSON layout, hence the same MD5 and file names
+        ident = OrderedDict()
+        ident["class"] = "GPTDataset"
+        ident["path_prefix"] = indexed_dataset.path_prefix
+        ident["num_samples"] = self.num_samples
+        ident["index_split"] = index_split  # Split.{train,valid,test}.name
+        ident["name"], ident["split"] = name, split
+        ident["random_seed"], ident["sequence_length"] = random_seed, self.sequence_length
+        self.unique_description = json.dumps(ident, indent=4)
+        self.unique_description_hash = hashlib.md5(self.unique_description.encode("utf-8")).hexdigest()
+        if cache not in ("off", "load", "build"):
+            raise ValueError(f"cache={cache!r}: off (build in memory), load (use stored indices when present, never write) or "
+                             "build (store them when missing, like the reference's caching_allowed ranks)")
+        self.path_to_cache, self.cache_mode, self.cache_hit = path_to_cache, cache, False
+        self.document_index, self.sample_index, self.shuffle_index = self._cached_indices()
+
+    def cache_paths(self) -> dict[str, str]:
+        """gpt_dataset.py:265-275: default directory `<path_prefix>/cache/GPTDataset_indices`"""
+        root = self.path_to_cache
+        if root is None:
+            root = os.path.join(self.indexed_dataset.path_prefix, "cache", "GPTDataset_indices")
+        return {k: os.path.join(root, f"{self.unique_description_hash}-GPTDataset-{k}")
+                for k in ("description.txt", "document_index.npy", "sample_index.npy", "shuffle_index.npy")}
+
+    def _cached_indices(self):
+        """gpt_dataset.py:241-400.  `build`: a miss builds the indices, stores them (description first, every array through a
+        temporary file + rename so that another node never maps half a file) and maps them back read-only; `load`: stored
+        indices are used when all four files exist, nothing is ever written; `off`: always in memory.  A cache directory that
+        cannot be written degrades to the in-memory indices with a warning (the reference raises there)."""
+        if self.cache_mode == "off":
+            return self._build_indices()
+        paths = self.cache_paths()
+        hit = all(os.path.isfile(v) for v in paths.values())
+        built = None
+        if not hit:
+            built = self._build_indices()
+            if self.cache_mode == "load":
+                return built
+            try:
+                os.makedirs(os.path.dirname(paths["description.txt"]), exist_ok=True)
+                with open(paths["description.txt"], "wt") as f:
+                    f.write(self.unique_description)
+                for key, arr in zip(("document_index.npy", "sample_index.npy", "shuffle_index.npy"), built):
+                    tmp = f"{paths[key]}.tmp{os.getpid()}.npy"
+                    np.save(tmp, arr, allow_pickle=True)
+                    os.replace(tmp, paths[key])
+            except OSError as e:
+                warnings.warn(f"GPTDataset indices not cached under {os.path.dirname(paths['description.txt'])} ({e}); "
+                              "set class_args.data_cache_path to a writable directory")
+                return built
+        else:
+            self.cache_hit = True
+            self._set_epoch_counters()
+        loaded = tuple(np.load(paths[k], allow_pickle=True, mmap_mode="r")
+                       for k in ("document_index.npy", "sample_index.npy", "shuffle_index.npy"))
+        if built is not None:  # what was just written must read back as what was built
+            assert all(a.shape == b.shape and a.dtype == b.dtype for a, b in zip(built, loaded))
+        return loaded
+
+    def _set_epoch_counters(self) -> None:
+        sizes = self.indexed_dataset.sequence_lengths
+        self.tokens_per_epoch = int(np.sum(sizes[self.indexed_indices]))
+        self.num_epochs = get_num_epochs(self.tokens_per_epoch, self.sequence_length, self.num_samples)
 
     def _build_indices(self):
         sizes = self.indexed_dataset.sequence_lengths
@@ -249,9 +321,31 @@ class BlendedDataset:
         return {"dataset_id": int(self.dataset_index[idx]), **ds[j]}
 
 
-def build_gpt_datasets(data_path, split: str, sizes: tuple[int, int, int], sequence_length: int, seed: int, fim=None):
+def build_gpt_datasets(data_path, split: str, sizes: tuple[int, int, int], sequence_length: int, seed: int, fim=None, *,
+                       data_cache_path: str | None = None, cache: str = "off", node_uses_local_storage: bool = False):
     """Options 1/2 of data/megatron/__init__.py:93-101 (`data_path` = one prefix, or [w1, prefix1, w2, prefix2, ...]):
-    -> (train, val, test), each a GPTDataset / BlendedDataset / None (blended_megatron_dataset_builder.py:61-226)"""
+    -> (train, val, test), each a GPTDataset / BlendedDataset / None (blended_megatron_dataset_builder.py:61-226).
+
+    `cache` = "build" follows blended_megatron_dataset_builder.py:330-366 under torch.distributed: rank 0 (and local rank 0 of every
+    node with `node_uses_local_storage`) builds and stores the indices, everybody meets at a barrier, the other ranks then find
+    them (mode "load": a rank that still misses them builds in memory instead of failing)."""
+    if cache == "build":
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            allowed = dist.get_rank() == 0 or (node_uses_local_storage and int(os.environ.get("LOCAL_RANK", "0")) == 0)
+            out = _build_gpt_datasets(data_path, split, sizes, sequence_length, seed, fim, data_cache_path, "build") if allowed else None
+            dist.barrier()
+            if not allowed:
+                out = _build_gpt_datasets(data_path, split, sizes, sequence_length, seed, fim, data_cache_path, "load")
+            return out
+    return _build_gpt_datasets(data_path, split, sizes, sequence_length, seed, fim, data_cache_path, cache)
+
+
+_SPLIT_NAMES = ("train", "valid", "test")  # data/megatron/utils/__init__.py:14-17 `Split`
+
+
+def _build_gpt_datasets(data_path, split: str, sizes, sequence_length: int, seed: int, fim, data_cache_path, cache: str):
     if isinstance(data_path, str):
         data_path = [data_path]
     split_v = parse_and_normalize_split(split)
@@ -265,7 +359,8 @@ def build_gpt_datasets(data_path, split: str, sizes: tuple[int, int, int], seque
             if split_v[i] == 0.0 or want[i] == 0:
                 out.append(None)
             else:
-                out.append(GPTDataset(ids, np.arange(bounds[i], bounds[i + 1], dtype=dt), want[i], sequence_length, seed, fim=fim))
+                out.append(GPTDataset(ids, np.arange(bounds[i], bounds[i + 1], dtype=dt), want[i], sequence_length, seed, fim=fim,
+                                      index_split=_SPLIT_NAMES[i], split=split, path_to_cache=data_cache_path, cache=cache))
         return out
 
     if len(data_path) == 1:

@@ -118,6 +118,17 @@ def _fim_spec(args: TrainingArgs, tokenizer=None):
     return FIMSpec.from_tokenizer(codec, rate, float(ca.get("fim_spm_rate", 0.5)))
 
 
+def _index_cache_args(class_args: dict) -> dict:
+    """`data_cache_path` / `node_uses_local_storage` of the reference's MegatronDataset class_args (data/megatron/__init__.py:85-89).
+    With a cache path the document / sample / shuffle indices are stored there under the reference's file names (rank 0 builds, the
+    others memory-map the same files); without one, indices the reference stored in its default place next to the data
+    (`<prefix>/cache/GPTDataset_indices`) are used when they exist and nothing is written (the reference would write there)."""
+    if class_args.get("data_cache_path"):
+        return dict(data_cache_path=class_args["data_cache_path"], cache="build",
+                    node_uses_local_storage=bool(class_args.get("node_uses_local_storage", False)))
+    return dict(cache="load")
+
+
 def make_megatron_dataloader(args: TrainingArgs, rank: int, world: int, consumed_samples: int = 0, tokenizer=None):
     """get_megatron_gpt_dataloaders (data/megatron/__init__.py:18-213), train split: Megatron .bin/.idx stores named by
     `class_args.data_path` (one prefix or [w1, prefix1, w2, prefix2, ...]) + `split`, cut into S+1-token samples, global
@@ -129,7 +140,7 @@ def make_megatron_dataloader(args: TrainingArgs, rank: int, world: int, consumed
     sizes = get_train_val_test_samples(tp.num_training_steps, tp.micro_batch_size, tp.gradient_accumulation_steps,
                                        getattr(tp, "eval_interval", None), ca.get("eval_steps"), world)
     train, _, _ = build_gpt_datasets(ca["data_path"], ca.get("split", "100,0,0"), sizes, ca["sequence_length"],
-                                     ca.get("seed", args.random_args.seed), fim=_fim_spec(args, tokenizer))
+                                     ca.get("seed", args.random_args.seed), fim=_fim_spec(args, tokenizer), **_index_cache_args(ca))
     sampler = MegatronBatchSampler(len(train), consumed_samples, tp.micro_batch_size, world, rank)
     return PackedBatchLoader(train, sampler, ca["sequence_length"])
 
@@ -145,7 +156,7 @@ def make_megatron_val_dataloader(args: TrainingArgs, rank: int, world: int):
     sizes = get_train_val_test_samples(tp.num_training_steps, tp.micro_batch_size, tp.gradient_accumulation_steps,
                                        tp.eval_interval, ca.get("eval_steps"), world)
     _, val, _ = build_gpt_datasets(ca["data_path"], ca.get("split", "100,0,0"), sizes, ca["sequence_length"],
-                                   ca.get("seed", args.random_args.seed))
+                                   ca.get("seed", args.random_args.seed), **_index_cache_args(ca))
     if val is None:
         return None
     return lambda: iter(PackedBatchLoader(val, MegatronBatchSampler(len(val), 0, tp.micro_batch_size, world, rank),

@@ -131,6 +131,30 @@ def main():
         out[f"case{ci}_take"] = np.asarray(take, dtype=np.int64)
         out[f"case{ci}_samples"] = np.stack([ds[i]["text"] for i in take])
 
+    # ---- the index cache AS THE REFERENCE WRITES IT (gpt_dataset.py:265-330): relative prefix + relative cache directory, so that
+    # the unique description (and its MD5 = the file names) does not depend on where the repository lives.  Committed under
+    # tests/golden/data_feed/ref_index_cache/: the product must find these files (cache hit) and must name its own files alike.
+    import shutil
+
+    cwd = os.getcwd()
+    os.chdir(OUT)
+    try:
+        shutil.rmtree("ref_index_cache", ignore_errors=True)
+        ids_rel = m["indexed_dataset"].MMapIndexedDataset("corpus_a")
+        cfg = Cfg(is_built_on_rank=True, random_seed=77, sequence_length=16, blend=["corpus_a"], split="90,10,0",
+                  path_to_cache="ref_index_cache", return_document_ids=False, fim_rate=0, fim_spm_rate=0.5)
+        ds = m["gpt_dataset"].GPTDataset(ids_rel, np.arange(0, 33, dtype=np.int32), 230, Split.train, None, cfg, True)
+        out["cache_description"] = np.asarray(ds.unique_description)
+        out["cache_hash"] = np.asarray(ds.unique_description_hash)
+        out["cache_files"] = np.asarray(sorted(os.listdir("ref_index_cache")))
+        out["cache_len"] = np.asarray(len(ds))
+        out["cache_samples"] = np.stack([ds[i]["text"] for i in range(0, len(ds), 7)])
+        # the validation split of the same configuration: only the description differs (index_split, num_samples)
+        dv = m["gpt_dataset"].GPTDataset(ids_rel, np.arange(33, 37, dtype=np.int32), 9, Split.valid, None, cfg, True)
+        out["cache_hash_valid"] = np.asarray(dv.unique_description_hash)
+    finally:
+        os.chdir(cwd)
+
     # ---- blending index + sampler straight from the reference helpers / class ----
     for bi, (w, size) in enumerate([([0.3, 0.7], 101), ([0.5, 0.25, 0.25], 64), ([1.0], 9), ([0.2, 0.2, 0.6], 1000)]):
         di = np.zeros(size, dtype=np.int16)

@@ -183,6 +183,26 @@ def test_yaml_megatron_dataset_feeds_the_training_loop_contract():
     assert torch.equal(next(it)["text"], seen[0][2])
 
 
+def test_yaml_data_cache_path_stores_the_indices_and_feeds_the_same_batches(tmp_path):
+    """class_args.data_cache_path (data/megatron/__init__.py:85): the indices are stored under the reference's file names and a second
+    start maps them instead of rebuilding; the token stream does not change"""
+    from dolomite_engine_b200.arguments import get_args_from_dict, load_yaml
+    from dolomite_engine_b200.pretrain import make_dataloader
+
+    d = load_yaml(os.path.join(os.path.dirname(HERE), "configs", "c1_tiny.yml"))
+    ca = dict(data_path=[os.path.join(GOLD, "corpus_a")], split="100,0,0", sequence_length=16, eval_steps=2, seed=7)
+    d["training_parameters"].update(num_training_steps=4, micro_batch_size=2, gradient_accumulation_steps=1, eval_interval=2)
+    batches = []
+    for extra in ({}, {"data_cache_path": str(tmp_path / "idx")}, {"data_cache_path": str(tmp_path / "idx")}):
+        d["datasets"] = [dict(class_name="MegatronDataset", data_name="Megatron", class_args={**ca, **extra})]
+        loader = make_dataloader(get_args_from_dict(d), None, 0, world=1)
+        batches.append([next(loader)["text"].clone() for _ in range(3)])
+    assert all(torch.equal(a, b) and torch.equal(a, c) for a, b, c in zip(*batches))
+    names = sorted(os.listdir(tmp_path / "idx"))
+    assert len(names) == 4 and all("-GPTDataset-" in n for n in names)
+    assert not os.path.exists(os.path.join(GOLD, "corpus_a", "cache"))  # nothing is written next to the data without being asked
+
+
 def test_validation_split_loader_and_evaluate_contract():
     """pretrain.evaluate: mean of the per-batch losses over eval_steps batches of the validation split, model back in train mode"""
     from dolomite_engine_b200.arguments import get_args_from_dict, load_yaml
@@ -288,3 +308,119 @@ def test_split_arithmetic_matches_reference():
         assert list(vec) == case["vector"], case["split"]
         for n, bounds in case["bounds"].items():
             assert list(get_split_indices(vec, int(n))) == bounds, (case["split"], n)
+
+
+# ------------------------------------------------------------------------------------------------
+# index cache (gpt_dataset.py:241-400 of the reference): same description, same MD5, same file names, interchangeable files
+# ------------------------------------------------------------------------------------------------
+_CACHE_CASE = dict(num_samples=230, sequence_length=16, random_seed=77, index_split="train", split="90,10,0")
+
+
+def _cache_case_dataset(**kw):
+    ids = MMapIndexedDataset("corpus_a")  # relative prefix: the description (hence the MD5) must not depend on the checkout path
+    c = _CACHE_CASE
+    return GPTDataset(ids, np.arange(0, 33, dtype=np.int32), c["num_samples"], c["sequence_length"], c["random_seed"],
+                      index_split=c["index_split"], split=c["split"], **kw)
+
+
+def test_index_cache_written_by_the_reference_is_found_and_used(exp, monkeypatch):
+    monkeypatch.chdir(GOLD)
+    ds = _cache_case_dataset(path_to_cache="ref_index_cache", cache="load")
+    assert ds.unique_description == str(exp["cache_description"]) and ds.unique_description_hash == str(exp["cache_hash"])
+    assert ds.cache_hit and isinstance(ds.sample_index, np.memmap) and isinstance(ds.shuffle_index, np.memmap)
+    assert sorted(os.path.basename(p) for p in ds.cache_paths().values()) == list(exp["cache_files"])
+    assert len(ds) == int(exp["cache_len"]) and ds.num_epochs >= 2
+    got = np.stack([ds[i]["text"] for i in range(0, len(ds), 7)])
+    assert np.array_equal(got, exp["cache_samples"])
+    # the in-memory build produces exactly what the reference stored (values and dtypes)
+    mem = _cache_case_dataset()
+    assert not mem.cache_hit
+    for a, b in ((mem.document_index, ds.document_index), (mem.sample_index, ds.sample_index), (mem.shuffle_index, ds.shuffle_index)):
+        assert a.dtype == b.dtype and np.array_equal(a, b)
+    # the validation split of the same configuration hashes like the reference's
+    ids = MMapIndexedDataset("corpus_a")
+    dv = GPTDataset(ids, np.arange(33, 37, dtype=np.int32), 9, 16, 77, index_split="valid", split="90,10,0",
+                    path_to_cache="ref_index_cache", cache="load")
+    assert dv.unique_description_hash == str(exp["cache_hash_valid"]) and dv.cache_hit
+
+
+def test_index_cache_build_store_reload_and_unwritable_directory(exp, monkeypatch, tmp_path):
+    monkeypatch.chdir(GOLD)
+    cache = str(tmp_path / "cache")
+    first = _cache_case_dataset(path_to_cache=cache, cache="build")
+    assert not first.cache_hit and isinstance(first.sample_index, np.memmap)  # built, stored, mapped back
+    assert sorted(os.listdir(cache)) == list(exp["cache_files"])  # the reference's file names; no temporary file left behind
+    for name in exp["cache_files"]:
+        ours, ref = os.path.join(cache, str(name)), os.path.join("ref_index_cache", str(name))
+        if str(name).endswith(".npy"):
+            a, b = np.load(ours), np.load(ref)
+            assert a.dtype == b.dtype and np.array_equal(a, b)
+        else:
+            assert open(ours).read() == open(ref).read()
+    again = _cache_case_dataset(path_to_cache=cache, cache="build")
+    assert again.cache_hit and np.array_equal(again[5]["text"], first[5]["text"])
+    # "load" never writes: a miss builds in memory
+    empty = str(tmp_path / "empty")
+    miss = _cache_case_dataset(path_to_cache=empty, cache="load")
+    assert not miss.cache_hit and not os.path.exists(empty) and np.array_equal(miss[5]["text"], first[5]["text"])
+    # a cache directory that cannot be created degrades to the in-memory indices (with a warning), it does not abort the run
+    blocker = tmp_path / "file"
+    blocker.write_text("x")
+    with pytest.warns(UserWarning, match="not cached"):
+        bad = _cache_case_dataset(path_to_cache=str(blocker / "sub"), cache="build")
+    assert np.array_equal(bad[5]["text"], first[5]["text"])
+    with pytest.raises(ValueError):
+        _cache_case_dataset(cache="sometimes")
+
+
+def test_build_gpt_datasets_stores_train_and_validation_indices(tmp_path):
+    cache = str(tmp_path / "c")
+    prefix = os.path.join(GOLD, "corpus_a")
+    t, v, _ = build_gpt_datasets(prefix, "80,20,0", (30, 5, 0), 16, 1234, data_cache_path=cache, cache="build")
+    files = sorted(os.listdir(cache))
+    assert len(files) == 8 and {f.split("-")[0] for f in files} == {t.unique_description_hash, v.unique_description_hash}
+    t2, v2, _ = build_gpt_datasets(prefix, "80,20,0", (30, 5, 0), 16, 1234, data_cache_path=cache, cache="load")
+    assert t2.cache_hit and v2.cache_hit and np.array_equal(t2[3]["text"], t[3]["text"]) and np.array_equal(v2[1]["text"], v[1]["text"])
+    # default directory of the reference: <path_prefix>/cache/GPTDataset_indices (nothing is written there in "load" mode)
+    t3, _, _ = build_gpt_datasets(prefix, "80,20,0", (30, 5, 0), 16, 1234, cache="load")
+    assert os.path.dirname(t3.cache_paths()["sample_index.npy"]) == os.path.join(prefix, "cache", "GPTDataset_indices")
+    assert not t3.cache_hit and not os.path.exists(os.path.join(prefix, "cache"))
+
+
+def _cache_worker(rank: int, world: int, port: int, cache: str, q):
+    import sys
+
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        t, _, _ = build_gpt_datasets(os.path.join(GOLD, "corpus_b"), "100,0,0", (57, 0, 0), 32, 1234, data_cache_path=cache, cache="build")
+        q.put((rank, bool(t.cache_hit), isinstance(t.sample_index, np.memmap), t[4]["text"].tolist()))
+    except Exception:  # noqa
+        import traceback
+
+        q.put((rank, traceback.format_exc(), None, None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rank_0_builds_the_index_cache_and_the_other_ranks_map_it(tmp_path, exp):
+    """blended_megatron_dataset_builder.py:330-366: caching ranks build first, a barrier, then everybody else loads"""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 77) % 2000
+    procs = [ctx.Process(target=_cache_worker, args=(r, 2, port, str(tmp_path / "shared"), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    (r0, hit0, map0, s0), (r1, hit1, map1, s1) = res
+    assert isinstance(hit0, bool), hit0
+    assert isinstance(hit1, bool), hit1
+    assert (r0, r1) == (0, 1) and not hit0 and hit1 and map0 and map1 and s0 == s1
+    assert len(os.listdir(tmp_path / "shared")) == 4
