@@ -321,36 +321,39 @@ class BlendedDataset:
         return {"dataset_id": int(self.dataset_index[idx]), **ds[j]}
 
 
-def build_gpt_datasets(data_path, split: str, sizes: tuple[int, int, int], sequence_length: int, seed: int, fim=None, *,
-                       data_cache_path: str | None = None, cache: str = "off", node_uses_local_storage: bool = False):
-    """Options 1/2 of data/megatron/__init__.py:93-101 (`data_path` = one prefix, or [w1, prefix1, w2, prefix2, ...]):
-    -> (train, val, test), each a GPTDataset / BlendedDataset / None (blended_megatron_dataset_builder.py:61-226).
+def build_gpt_datasets(data_path, split: str | None, sizes: tuple[int, int, int], sequence_length: int, seed: int, fim=None, *,
+                       blend_per_split: list | None = None, data_cache_path: str | None = None, cache: str = "off",
+                       node_uses_local_storage: bool = False):
+    """Options 1-3 of data/megatron/__init__.py:93-101 -> (train, val, test), each a GPTDataset / BlendedDataset / None
+    (blended_megatron_dataset_builder.py:61-226):
+      1 / 2  `data_path` = one prefix, or [w1, prefix1, w2, prefix2, ...], cut into the three splits by `split` ("98,1,1");
+      3      `blend_per_split` = [train blend, validation blend, test blend] (class_args train_data_path / val_data_path /
+             test_data_path): every split has its own stores and uses them whole; `data_path` must be None and `split` is ignored.
 
     `cache` = "build" follows blended_megatron_dataset_builder.py:330-366 under torch.distributed: rank 0 (and local rank 0 of every
     node with `node_uses_local_storage`) builds and stores the indices, everybody meets at a barrier, the other ranks then find
     them (mode "load": a rank that still misses them builds in memory instead of failing)."""
+    args = (data_path, split, sizes, sequence_length, seed, fim, data_cache_path)
     if cache == "build":
         import torch.distributed as dist
 
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             allowed = dist.get_rank() == 0 or (node_uses_local_storage and int(os.environ.get("LOCAL_RANK", "0")) == 0)
-            out = _build_gpt_datasets(data_path, split, sizes, sequence_length, seed, fim, data_cache_path, "build") if allowed else None
+            out = _build_gpt_datasets(*args, "build", blend_per_split) if allowed else None
             dist.barrier()
             if not allowed:
-                out = _build_gpt_datasets(data_path, split, sizes, sequence_length, seed, fim, data_cache_path, "load")
+                out = _build_gpt_datasets(*args, "load", blend_per_split)
             return out
-    return _build_gpt_datasets(data_path, split, sizes, sequence_length, seed, fim, data_cache_path, cache)
+    return _build_gpt_datasets(*args, cache, blend_per_split)
 
 
 _SPLIT_NAMES = ("train", "valid", "test")  # data/megatron/utils/__init__.py:14-17 `Split`
 
 
-def _build_gpt_datasets(data_path, split: str, sizes, sequence_length: int, seed: int, fim, data_cache_path, cache: str):
-    if isinstance(data_path, str):
-        data_path = [data_path]
-    split_v = parse_and_normalize_split(split)
-
-    def one(prefix: str, want: list[int]):
+def _build_gpt_datasets(data_path, split, sizes, sequence_length: int, seed: int, fim, data_cache_path, cache: str,
+                        blend_per_split=None):
+    def one(prefix: str, split_v: list[float], want: list[int], split_desc):
+        """_build_megatron_dataset_splits: the three GPTDatasets (or None) cut from ONE store"""
         ids = MMapIndexedDataset(prefix)
         bounds = get_split_indices(split_v, ids.sequence_lengths.shape[0])
         dt = np.int32 if max(bounds) <= np.iinfo(np.int32).max else np.int64
@@ -360,22 +363,46 @@ def _build_gpt_datasets(data_path, split: str, sizes, sequence_length: int, seed
                 out.append(None)
             else:
                 out.append(GPTDataset(ids, np.arange(bounds[i], bounds[i + 1], dtype=dt), want[i], sequence_length, seed, fim=fim,
-                                      index_split=_SPLIT_NAMES[i], split=split, path_to_cache=data_cache_path, cache=cache))
+                                      index_split=_SPLIT_NAMES[i], split=split_desc, path_to_cache=data_cache_path, cache=cache))
         return out
 
-    if len(data_path) == 1:
-        return tuple(one(data_path[0], list(sizes)))
-    weights = [float(data_path[i]) for i in range(0, len(data_path), 2)]
-    prefixes = [str(data_path[i]).strip() for i in range(1, len(data_path), 2)]
-    tot = sum(weights)
-    weights = [w / tot for w in weights]
-    per = [[int(math.ceil(n * w * 1.005)) for n in sizes] for w in weights]  # 0.5 % margin like the reference
-    parts = [one(p, per[k]) for k, p in enumerate(prefixes)]
-    res = []
-    for i in range(3):
-        dss = [parts[k][i] for k in range(len(prefixes))]
-        res.append(None if any(d is None for d in dss) else BlendedDataset(dss, weights, sizes[i]))
-    return tuple(res)
+    def blended(blend: list, split_v: list[float], want: list[int], split_desc) -> list:
+        """one blend (a single prefix or weight / prefix pairs) -> the three splits"""
+        if len(blend) == 1:
+            return one(blend[0], split_v, list(want), split_desc)
+        assert len(blend) % 2 == 0, "a blend is one prefix or [weight, prefix, weight, prefix, ...]"
+        weights = [float(blend[i]) for i in range(0, len(blend), 2)]
+        prefixes = [str(blend[i]).strip() for i in range(1, len(blend), 2)]
+        tot = sum(weights)
+        weights = [w / tot for w in weights]
+        per = [[int(math.ceil(n * w * 1.005)) for n in want] for w in weights]  # 0.5 % margin like the reference
+        parts = [one(p, split_v, per[k], split_desc) for k, p in enumerate(prefixes)]
+        res = []
+        for i in range(3):
+            dss = [parts[k][i] for k in range(len(prefixes))]
+            # the blend's length is the SUM of the per-store requests (margin included), blended_megatron_dataset_builder.py:98-117
+            res.append(None if any(d is None for d in dss) else BlendedDataset(dss, weights, sum(per[k][i] for k in range(len(prefixes)))))
+        return res
+
+    if blend_per_split is not None and any(blend_per_split):
+        # blended_megatron_dataset_config.py:68-74 / builder :122-170: the split string is dropped (the description stores null)
+        assert data_path is None, "blend (data_path) and blend_per_split (train / val / test data paths) are incompatible"
+        assert len(blend_per_split) == 3, "blend_per_split must contain 3 blends"
+        out = []
+        for i in range(3):
+            blend = blend_per_split[i]
+            if not blend:
+                out.append(None)
+                continue
+            blend = [blend] if isinstance(blend, str) else list(blend)
+            split_spoof, sizes_spoof = [0.0] * 3, [0] * 3
+            split_spoof[i], sizes_spoof[i] = 1.0, sizes[i]
+            out.append(blended(blend, split_spoof, sizes_spoof, None)[i])
+        return tuple(out)
+    assert split is not None, "both blend and split must be provided"
+    if isinstance(data_path, str):
+        data_path = [data_path]
+    return tuple(blended(list(data_path), parse_and_normalize_split(split), list(sizes), split))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -118,6 +118,26 @@ def _fim_spec(args: TrainingArgs, tokenizer=None):
     return FIMSpec.from_tokenizer(codec, rate, float(ca.get("fim_spm_rate", 0.5)))
 
 
+def _blend_per_split(class_args: dict):
+    """option 3 of data/megatron/__init__.py:78-84, 93-101: `train_data_path` / `val_data_path` / `test_data_path` (each one prefix or
+    [w1, prefix1, w2, prefix2, ...]) instead of `data_path` + `split`"""
+    per_split = [class_args.get("train_data_path"), class_args.get("val_data_path"), class_args.get("test_data_path")]
+    if not any(per_split):
+        return None
+    if class_args.get("data_path") is not None:
+        raise ValueError("MegatronDataset: data_path and train_data_path / val_data_path / test_data_path are incompatible")
+    return per_split
+
+
+def _data_sources(class_args: dict) -> tuple:
+    """(data_path, split) of options 1 / 2; (None, None) when the splits name their own stores"""
+    if _blend_per_split(class_args) is not None:
+        return None, None
+    if class_args.get("data_path") is None:
+        raise ValueError("MegatronDataset: class_args needs data_path (+ split) or train_data_path [/ val_data_path / test_data_path]")
+    return class_args["data_path"], class_args.get("split", "100,0,0")
+
+
 def _index_cache_args(class_args: dict) -> dict:
     """`data_cache_path` / `node_uses_local_storage` of the reference's MegatronDataset class_args (data/megatron/__init__.py:85-89).
     With a cache path the document / sample / shuffle indices are stored there under the reference's file names (rank 0 builds, the
@@ -139,8 +159,10 @@ def make_megatron_dataloader(args: TrainingArgs, rank: int, world: int, consumed
     ca = ds.class_args
     sizes = get_train_val_test_samples(tp.num_training_steps, tp.micro_batch_size, tp.gradient_accumulation_steps,
                                        getattr(tp, "eval_interval", None), ca.get("eval_steps"), world)
-    train, _, _ = build_gpt_datasets(ca["data_path"], ca.get("split", "100,0,0"), sizes, ca["sequence_length"],
-                                     ca.get("seed", args.random_args.seed), fim=_fim_spec(args, tokenizer), **_index_cache_args(ca))
+    train, _, _ = build_gpt_datasets(*_data_sources(ca), sizes, ca["sequence_length"], ca.get("seed", args.random_args.seed),
+                                     fim=_fim_spec(args, tokenizer), blend_per_split=_blend_per_split(ca), **_index_cache_args(ca))
+    if train is None:
+        raise ValueError("MegatronDataset: no training data (data_path with a zero train split, or no train_data_path)")
     sampler = MegatronBatchSampler(len(train), consumed_samples, tp.micro_batch_size, world, rank)
     return PackedBatchLoader(train, sampler, ca["sequence_length"])
 
@@ -155,8 +177,8 @@ def make_megatron_val_dataloader(args: TrainingArgs, rank: int, world: int):
         return None
     sizes = get_train_val_test_samples(tp.num_training_steps, tp.micro_batch_size, tp.gradient_accumulation_steps,
                                        tp.eval_interval, ca.get("eval_steps"), world)
-    _, val, _ = build_gpt_datasets(ca["data_path"], ca.get("split", "100,0,0"), sizes, ca["sequence_length"],
-                                   ca.get("seed", args.random_args.seed), **_index_cache_args(ca))
+    _, val, _ = build_gpt_datasets(*_data_sources(ca), sizes, ca["sequence_length"], ca.get("seed", args.random_args.seed),
+                                   blend_per_split=_blend_per_split(ca), **_index_cache_args(ca))
     if val is None:
         return None
     return lambda: iter(PackedBatchLoader(val, MegatronBatchSampler(len(val), 0, tp.micro_batch_size, world, rank),

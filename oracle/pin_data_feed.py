@@ -77,7 +77,7 @@ def import_reference_data_modules():
     load("dolomite_engine.data.megatron.utils", "data/megatron/utils/__init__.py", is_pkg=True)
     mods = {}
     for n in ("indexed_dataset", "blended_megatron_dataset_config", "megatron_dataset", "gpt_dataset", "blended_dataset",
-              "sampler"):
+              "sampler", "blended_megatron_dataset_builder"):
         mods[n] = load(f"dolomite_engine.data.megatron.{n}", f"data/megatron/{n}.py")
     return mods
 
@@ -154,6 +154,28 @@ def main():
         out["cache_hash_valid"] = np.asarray(dv.unique_description_hash)
     finally:
         os.chdir(cwd)
+
+    # ---- the reference's BUILDER (blended_megatron_dataset_builder.py): option 2 (weighted blend cut by `split`) and option 3
+    # (a blend per split): lengths of what it returns and the first samples of every split
+    Builder = m["blended_megatron_dataset_builder"].BlendedMegatronDatasetBuilder
+    pa, pb = os.path.join(OUT, "corpus_a"), os.path.join(OUT, "corpus_b")
+    builder_cases = {
+        "opt2": (dict(blend=["1", pa, "3", pb], split="90,10,0"), [40, 8, 0], 8, 1234),
+        "opt3": (dict(blend_per_split=[["2", pa, "1", pb], [pb], None]), [50, 6, 0], 8, 5),
+    }
+    for tag, (kw, sizes, S, seed) in builder_cases.items():
+        cfg = Cfg(is_built_on_rank=True, random_seed=seed, sequence_length=S, path_to_cache=os.path.join("/tmp", f"pin_builder_{tag}"),
+                  return_document_ids=False, fim_rate=0, fim_spm_rate=0.5, **kw)
+        splits = Builder(m["gpt_dataset"].GPTDataset, sizes, cfg, None).build()
+        out[f"builder_{tag}_lens"] = np.asarray([-1 if d is None else len(d) for d in splits], dtype=np.int64)
+        for i, d in enumerate(splits):
+            if d is None:
+                continue
+            n = min(len(d), 24)
+            out[f"builder_{tag}_split{i}_samples"] = np.stack([d[j]["text"] for j in range(n)])
+            if hasattr(d, "dataset_index"):
+                out[f"builder_{tag}_split{i}_dataset_index"] = np.asarray(d.dataset_index)
+                out[f"builder_{tag}_split{i}_dataset_sample_index"] = np.asarray(d.dataset_sample_index)
 
     # ---- blending index + sampler straight from the reference helpers / class ----
     for bi, (w, size) in enumerate([([0.3, 0.7], 101), ([0.5, 0.25, 0.25], 64), ([1.0], 9), ([0.2, 0.2, 0.6], 1000)]):

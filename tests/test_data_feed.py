@@ -156,7 +156,8 @@ def test_blended_dataset_and_builder(tmp_path):
     assert np.array_equal(first.numpy(), np.stack([bl[i]["text"] for i in range(4)]))
     train, val, test = build_gpt_datasets(["1", os.path.join(GOLD, "corpus_a"), "3", os.path.join(GOLD, "corpus_b")],
                                           "90,10,0", (40, 8, 0), S, 1234)
-    assert isinstance(train, BlendedDataset) and len(train) == 40 and len(val) == 8 and test is None
+    # the blend's length is the sum of the per-store requests incl. the 0.5 % margin: ceil(40 * .25 * 1.005) + ceil(40 * .75 * 1.005)
+    assert isinstance(train, BlendedDataset) and len(train) == 11 + 31 and len(val) == 3 + 7 and test is None
     t1, v1, _ = build_gpt_datasets(os.path.join(GOLD, "corpus_a"), "80,20,0", (30, 5, 0), S, 1234)
     assert isinstance(t1, GPTDataset) and t1.indexed_indices[-1] + 1 == v1.indexed_indices[0]
 
@@ -424,3 +425,59 @@ def test_rank_0_builds_the_index_cache_and_the_other_ranks_map_it(tmp_path, exp)
     assert isinstance(hit1, bool), hit1
     assert (r0, r1) == (0, 1) and not hit0 and hit1 and map0 and map1 and s0 == s1
     assert len(os.listdir(tmp_path / "shared")) == 4
+
+
+def _check_split_against_the_reference_builder(exp, tag, i, ds):
+    n = int(exp[f"builder_{tag}_lens"][i])
+    if n < 0:
+        assert ds is None
+        return
+    assert len(ds) == n
+    want = exp[f"builder_{tag}_split{i}_samples"]
+    assert np.array_equal(np.stack([ds[j]["text"] for j in range(want.shape[0])]), want)
+    if f"builder_{tag}_split{i}_dataset_index" in exp.files:
+        assert np.array_equal(ds.dataset_index, exp[f"builder_{tag}_split{i}_dataset_index"])
+        assert np.array_equal(ds.dataset_sample_index, exp[f"builder_{tag}_split{i}_dataset_sample_index"])
+
+
+def test_builder_options_match_the_reference_builder(exp):
+    """what BlendedMegatronDatasetBuilder.build() itself returned in this container (oracle/pin_data_feed.py): option 2 = weighted
+    blend cut by `split`; option 3 = one blend per split (class_args train_data_path / val_data_path / test_data_path)"""
+    pa, pb = os.path.join(GOLD, "corpus_a"), os.path.join(GOLD, "corpus_b")
+    got = build_gpt_datasets(["1", pa, "3", pb], "90,10,0", (40, 8, 0), 8, 1234)
+    for i in range(3):
+        _check_split_against_the_reference_builder(exp, "opt2", i, got[i])
+    got = build_gpt_datasets(None, None, (50, 6, 0), 8, 5, blend_per_split=[["2", pa, "1", pb], [pb], None])
+    for i in range(3):
+        _check_split_against_the_reference_builder(exp, "opt3", i, got[i])
+    assert got[1].unique_description.count('"split": null') == 1 and '"index_split": "valid"' in got[1].unique_description
+    with pytest.raises(AssertionError):
+        build_gpt_datasets(pa, "100,0,0", (5, 0, 0), 8, 5, blend_per_split=[[pb], None, None])
+    with pytest.raises(AssertionError):
+        build_gpt_datasets(pa, None, (5, 0, 0), 8, 5)
+
+
+def test_yaml_train_and_val_data_paths_feed_their_own_stores(exp):
+    """class_args train_data_path / val_data_path (option 3): the training loader reads the train blend, the validation loader the
+    validation store; the first rows are the ones the reference's builder produced"""
+    from dolomite_engine_b200.arguments import get_args_from_dict, load_yaml
+    from dolomite_engine_b200.pretrain import make_dataloader, make_megatron_val_dataloader
+
+    pa, pb = os.path.join(GOLD, "corpus_a"), os.path.join(GOLD, "corpus_b")
+    d = load_yaml(os.path.join(os.path.dirname(HERE), "configs", "c1_tiny.yml"))
+    d["datasets"] = [dict(class_name="MegatronDataset", data_name="Megatron",
+                          class_args=dict(train_data_path=["2", pa, "1", pb], val_data_path=[pb], sequence_length=8, eval_steps=3, seed=5))]
+    # train request = steps * mbs * accumulation * world = 50 samples like the pinned builder case; the validation store is read through a
+    # single GPTDataset, which holds whole epochs whatever the request (same first rows as the pinned case)
+    d["training_parameters"].update(num_training_steps=25, micro_batch_size=2, gradient_accumulation_steps=1, eval_interval=25,
+                                    eval_during_training=True)
+    args = get_args_from_dict(d)
+    it = make_dataloader(args, None, 0, world=1)
+    rows = torch.cat([next(it)["text"] for _ in range(3)]).numpy()
+    assert np.array_equal(rows, exp["builder_opt3_split0_samples"][:6])
+    val = make_megatron_val_dataloader(args, rank=0, world=1)
+    vrows = torch.cat([b["text"] for _, b in zip(range(2), val())]).numpy()
+    assert np.array_equal(vrows, exp["builder_opt3_split1_samples"][:4])
+    d["datasets"][0]["class_args"]["data_path"] = [pa]
+    with pytest.raises(ValueError):
+        make_dataloader(get_args_from_dict(d), None, 0, world=1)
