@@ -16,12 +16,47 @@ from torch.optim.lr_scheduler import LambdaLR
 from . import kernels as K
 
 
+def lr_scale_segments(unit, scale_of) -> list[tuple[int, int, float]]:
+    """[lo, hi) ranges of THIS RANK's shard of `unit` (offsets relative to the shard) with the learning-rate multiplier of the
+    parameter they belong to, adjacent ranges of equal multiplier merged.  A parameter owns the alignment gap behind it (the gap
+    holds zeros and zero gradients: any multiplier leaves it zero); a shard boundary may cut a parameter anywhere."""
+    lo_s, hi_s = unit.rank * unit.shard_numel, (unit.rank + 1) * unit.shard_numel
+    out: list[list] = []
+    for i, s in enumerate(unit.specs):
+        start = s.offset if i else 0
+        end = unit.specs[i + 1].offset if i + 1 < len(unit.specs) else unit.padded
+        lo, hi = max(start, lo_s), min(end, hi_s)
+        if lo >= hi:
+            continue
+        sc = float(scale_of(s.name))
+        if out and out[-1][2] == sc and out[-1][1] == lo - lo_s:
+            out[-1][1] = hi - lo_s
+        else:
+            out.append([lo - lo_s, hi - lo_s, sc])
+    if not out:  # a unit without parameters in this shard (padding only)
+        out.append([0, unit.shard_numel, 1.0])
+    return [tuple(x) for x in out]
+
+
+def mup_lr_scale(config):
+    """optimization/optimizer.py:86-126 (`params_group_method: mup`): every parameter of the Attention and MLP modules except
+    biases trains with lr / m_width; embeddings, norms, biases and the head keep lr"""
+    import re
+
+    pat = re.compile(r"^transformer\.h\.\d+\.(attn|mlp)\..*(?<!bias)$")
+    inv = 1.0 / float(config.m_width)
+    return lambda name: inv if pat.match(name) else 1.0
+
+
 class DolomiteFusedAdamW(Optimizer):
-    def __init__(self, params, lr=1e-5, betas=(0.9, 0.95), eps=1e-10, weight_decay=0.1, model=None):
+    def __init__(self, params, lr=1e-5, betas=(0.9, 0.95), eps=1e-10, weight_decay=0.1, model=None, lr_scale_of=None):
         defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self.model = model  # ShardedDataParallel: provides the clip coefficient and the bf16 targets
         self._step = 0
+        # parameter name -> learning-rate multiplier (muP parameter groups); None = one learning rate, one launch per shard
+        self.lr_scale_of = lr_scale_of
+        self._segments: dict[int, list[tuple[int, int, float]]] = {}
 
     def zero_grad(self, set_to_none: bool = False) -> None:
         """The reference's train_step calls `optimizer.zero_grad()` (train_utils.py:40).  The gradients this optimizer
@@ -50,8 +85,19 @@ class DolomiteFusedAdamW(Optimizer):
                 # world_size == 1: write the bf16 compute copy in the same pass; sharded: into own slice of the
                 # gather buffer is done by the all-gather prologue (cast), so skip here
                 pb = u.compute if engine.world_size == 1 else None
-                K.adamw_step(p.data, p.grad, st["exp_avg"], st["exp_avg_sq"], pb, group["lr"], b1, b2, group["eps"],
-                             group["weight_decay"], self._step, clip=clip)
+                if self.lr_scale_of is None:
+                    K.adamw_step(p.data, p.grad, st["exp_avg"], st["exp_avg_sq"], pb, group["lr"], b1, b2, group["eps"],
+                                 group["weight_decay"], self._step, clip=clip)
+                    continue
+                # the reference puts the muP parameters into a second torch param group with lr / m_width; here the groups are
+                # ranges of the flat shard: the same kernel runs once per range with the range's learning rate
+                key = id(u)
+                if key not in self._segments:
+                    self._segments[key] = lr_scale_segments(u, self.lr_scale_of)
+                for lo, hi, scale in self._segments[key]:
+                    K.adamw_step(p.data[lo:hi], p.grad[lo:hi], st["exp_avg"][lo:hi], st["exp_avg_sq"][lo:hi],
+                                 None if pb is None else pb[lo:hi], group["lr"] * scale, b1, b2, group["eps"],
+                                 group["weight_decay"], self._step, clip=clip)
         sdp.clip_coef.fill_(1.0)
         sdp.notify_fused_update()
 
@@ -72,15 +118,26 @@ def get_optimizer(optimizer_class_name: str, optimizer_class_args: dict, model, 
         raise ValueError(
             f"invalid class_name ({optimizer_class_name}) for optimizer; the B200 path provides {sorted(_OPTIMIZER_CLASSES)}"
         )
-    if params_group_method is not None:
-        raise NotImplementedError("muP parameter groups are out of scope of the B200 hot path")
     args = dict(optimizer_class_args)
     if "betas" in args:
         args["betas"] = tuple(args["betas"])
     cls = _OPTIMIZER_CLASSES[optimizer_class_name]
     params = list(model.parameters())
+    lr_scale_of = None
+    method = None if params_group_method is None else str(getattr(params_group_method, "value", params_group_method))
+    if method == "mup":
+        # optimization/optimizer.py:89-99: same three conditions as the reference's asserts
+        cfg = model.config
+        assert cfg.model_type == "gpt_dolomite", "mup is not supported with this model architecture"
+        assert cfg.init_method == "mup", "both init method for model and params group method for optimizer should be set to mup"
+        if cls is not DolomiteFusedAdamW:
+            raise NotImplementedError("params_group_method: mup needs class_name: DolomiteFusedAdamW here (the torch optimizers see "
+                                      "one flat fp32 shard per unit, which cannot be split into torch param groups)")
+        lr_scale_of = mup_lr_scale(cfg)
+    elif method is not None:
+        raise ValueError(f"unexpected params_group_method ({params_group_method})")
     if cls is DolomiteFusedAdamW:
-        return cls(params, model=model, **args)
+        return cls(params, model=model, lr_scale_of=lr_scale_of, **args)
     return cls(params, **args)
 
 
